@@ -1,0 +1,167 @@
+/*
+ * fwsim.h -- C ABI of libfwsim.so, the B200-native batched fixed-wing simulator.
+ *
+ * The reference (WdBlink/pyflyt-drone) is pure Python and has no FFI: its replaceable seams for this path are
+ *   - stable_baselines3 SubprocVecEnv([make_env(i) ...])   train/train_Fixedwing_Waypoints_v3.py:251
+ *                                                          train/train_Fixedwing_Waypoints_ObjLock.py:306
+ *   - gymnasium Env reset()/step()                         envs/fixedwing_envs/fixedwing_base_env.py:175-195,314-348
+ * This header is the boundary added beneath those seams; each entry point names the reference interface it
+ * replaces.  The Python host side (pyflyt_drone_b200/vec_env.py, gym_env.py) binds it with ctypes; the stub a
+ * reference maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions: every function returns 0 on success and a negative FW_E* code on failure (never throws);
+ * fw_last_error() gives a thread-local message.  The caller owns every I/O buffer; the library owns the
+ * per-env SoA state in HBM and frees it in fw_destroy().  All device work is enqueued on the caller's
+ * stream (`stream` is a cudaStream_t passed as void*, NULL = legacy default stream) with no implicit
+ * device synchronisation, except the *_host entry points which are synchronous by contract.
+ * A handle is not thread-safe; distinct handles (one per GPU) are independent.
+ */
+#ifndef FWSIM_H
+#define FWSIM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FW_ABI_VERSION 3
+
+#define FW_NSURF 5            /* cmd order: left aileron, right aileron, h-tail, v-tail, main wing */
+#define FW_MAX_TARGETS 16
+#define FW_MAX_COL 16
+#define FW_MAX_OBST 32
+
+/* error codes */
+#define FW_OK 0
+#define FW_EINVAL (-1)
+#define FW_ECUDA (-2)
+#define FW_ENOMEM (-3)
+#define FW_ESTATE (-4)
+
+/* per-env flag byte written by fw_step: info dict of the reference env packed into bits
+ * (fixedwing_base_env.py:212-215,296-312; fixedwing_waypoint_objlock_env.py:180-181,336-337) */
+#define FW_FLAG_TERM      1   /* termination */
+#define FW_FLAG_TRUNC     2   /* truncation */
+#define FW_FLAG_COLLISION 4   /* info["collision"] */
+#define FW_FLAG_OOB       8   /* info["out_of_bounds"] */
+#define FW_FLAG_COMPLETE  16  /* info["env_complete"] */
+#define FW_FLAG_STRIKE    32  /* info["duck_strike"] */
+
+#define FW_TASK_PHYSICS   0   /* dynamics + ground/dome termination, no observation (BASELINE config 2) */
+#define FW_TASK_WAYPOINTS 1   /* PyFlyt/Fixedwing-Waypoints-v3 + FlattenWaypointEnv */
+#define FW_TASK_OBJLOCK   2   /* FixedwingWaypointObjLockEnv + FlattenWaypointEnv */
+
+/* Everything the kernels need to know about the aircraft and the task.  Raw physical parameters only;
+ * derived constants are computed inside fw_create. */
+typedef struct FwConfig {
+    /* lifting surfaces -- my_models/fixedwing/fixewing.yaml:8-71 */
+    double cl_alpha_2d[FW_NSURF], chord[FW_NSURF], span[FW_NSURF], flap_to_chord[FW_NSURF], eta[FW_NSURF];
+    double alpha0_base_deg[FW_NSURF], stall_p_base_deg[FW_NSURF], stall_n_base_deg[FW_NSURF];
+    double cd0[FW_NSURF], defl_limit_deg[FW_NSURF], surf_tau[FW_NSURF];
+    double lift_unit[FW_NSURF][3], fwd_unit[FW_NSURF][3], r_surf[FW_NSURF][3];
+    /* motor -- fixewing.yaml:1-6 */
+    double total_thrust, thrust_coef, torque_coef, noise_ratio, motor_tau;
+    double r_motor[3], thrust_unit[3];
+    /* composite rigid body at the base-link CoM (from the URDF; see pyflyt_drone_b200/aircraft.py) */
+    double mass, com[3], inertia_o[9];
+    double col_pts[FW_MAX_COL][3];
+    double contact_margin;
+    /* simulator rates (PyFlyt Aviary: physics 240 Hz, control 120 Hz; env: agent_hz 30) */
+    double dt, gravity, rho, max_coord_vel;
+    /* upstream conventions that cannot be verified offline */
+    double ail_left_sign, ail_right_sign, pitch_sign, yaw_sign;
+    /* env */
+    double goal_reach, dome, spawn_size, min_height;
+    double start_pos[3], start_vel[3];
+    /* wind -- fixedwing_base_env.py:108-173, envs/utils.py:141-218 */
+    double wind_base[3], wind_base_lo[3], wind_base_hi[3];
+    double gust_amp[3], gust_amp_lo[3], gust_amp_hi[3];
+    double gust_freq, gust_phase;
+    /* objlock -- fixedwing_waypoint_objlock_env.py:42-168 */
+    double obst_radius, obst_h_lo, obst_h_hi, obst_safe, obst_scale, obst_max_pen;
+    double strike_dist, strike_reward, lock_step_reward, approach_scale, switch_min_area;
+    double duck_radius, cam_offset[3], cam_near, cam_far;
+
+    int32_t n_col;
+    int32_t physics_per_control, substeps_per_inner, inner_per_step, warmup_inner;
+    int32_t freestream_3d, cd90_degrees;
+    int32_t task, num_targets, sparse_reward, angle_repr, max_steps, context_len;
+    int32_t early_return_on_crash, complete_truncates;
+    int32_t wind_mode, wind_randomize, wind_rand_phase, wind_start_substep;
+    int32_t num_obstacles, cam_interval_substeps, lock_hold_steps, switch_min_seen, cam_res;
+    int32_t fast_trig;        /* 1: SFU sin/cos in the aero model (parity-tested); 0: libdevice */
+    int32_t _reserved[5];
+} FwConfig;
+
+/* Host-side view of the per-env state for parity injection / inspection.  Any pointer may be NULL
+ * (that field is skipped).  Arrays are row-major [n_envs, k] in HOST memory. */
+typedef struct FwStateHost {
+    float* pos;          /* [N,3] world */
+    float* quat;         /* [N,4] x,y,z,w body->world */
+    float* vel;          /* [N,3] world */
+    float* omega;        /* [N,3] world */
+    float* act;          /* [N,6] five surface actuations + throttle */
+    float* targets;      /* [N,num_targets,3] full original list */
+    int32_t* target_idx; /* [N] index of the current target (== num reached) */
+    int32_t* step_count; /* [N] */
+    int32_t* physics_steps; /* [N] */
+    uint32_t* episode;   /* [N] */
+    float* new_dist;     /* [N] WaypointHandler.new_distance */
+    float* wind;         /* [N,7] base xyz, gust amp xyz, phase */
+} FwStateHost;
+
+typedef struct FwSim* fw_handle;
+
+int fw_abi_version(void);
+const char* fw_last_error(void);
+int fw_config_size(void);
+
+/* Replaces: SubprocVecEnv([make_env(rank, seed) ...]) construction + the Aviary/URDF load of every worker
+ * (train_Fixedwing_Waypoints_v3.py:82-121,251).  env_id0 is the global id of env 0 (multi-GPU sharding:
+ * rank r owns [r*N, (r+1)*N); the RNG is keyed by the global id so results do not depend on the split). */
+int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, uint64_t seed, uint32_t env_id0, fw_handle* out);
+int fw_destroy(fw_handle h);
+int fw_num_envs(fw_handle h);
+int fw_obs_dim(fw_handle h);
+
+/* Replaces: VecEnv.reset() -> env.reset(seed=seed+rank) of every worker (fixedwing_base_env.py:193-257).
+ * mask_dev: optional device bytes [N], non-zero = reset that env; NULL = all.  obs_dev: [N, obs_dim] f32 or NULL. */
+int fw_reset(fw_handle h, const uint8_t* mask_dev, float* obs_dev, void* stream);
+
+/* Replaces: VecEnv.step_async/step_wait -> FlattenWaypointEnv.step -> FixedwingBaseEnv.step
+ * (fixedwing_base_env.py:314-348, flatten_waypoint_env.py:52-72) plus the SubprocVecEnv worker's
+ * reset-on-done.  act_dev [N,4] f32 in [-1,1]; obs_dev [N,obs_dim]; rew_dev [N]; flags_dev [N] bytes;
+ * term_obs_dev [N,obs_dim] or NULL (rows of done envs receive info["terminal_observation"]). */
+int fw_step(fw_handle h, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* flags_dev,
+            float* term_obs_dev, void* stream);
+
+/* Random-action workload (BASELINE config 2/5): actions U(-1,1)^4 drawn in-kernel from Philox keyed by
+ * (seed, global env id, step_index + i); n_steps env-steps per call, one kernel launch per env-step.
+ * rew_dev / flags_dev may be NULL. */
+int fw_step_random(fw_handle h, uint32_t step_index, int32_t n_steps, float* rew_dev, uint8_t* flags_dev,
+                   void* stream);
+
+/* Synchronous host-buffer variant of fw_step: the call SB3's VecEnv.step() makes (numpy in, numpy out).
+ * Copies actions H2D, steps, copies obs/reward/flags (and terminal obs when requested) D2H through
+ * internal pinned staging buffers on an internal stream, then waits. */
+int fw_step_host(fw_handle h, const float* act_host, float* obs_host, float* rew_host, uint8_t* flags_host,
+                 float* term_obs_host);
+int fw_reset_host(fw_handle h, float* obs_host);
+
+/* parity injection / inspection (synchronous) */
+int fw_set_state(fw_handle h, const FwStateHost* s);
+int fw_get_state(fw_handle h, FwStateHost* s);
+
+/* device-side episode accumulators: sums since the last call (synchronous, resets the counters).
+ * out[0]=episodes finished, [1]=sum return, [2]=sum length, [3]=sum targets reached,
+ * [4]=collisions, [5]=out-of-bounds, [6]=completed, [7]=strikes */
+int fw_episode_stats(fw_handle h, double out[8]);
+
+/* number of kernel launches issued through this handle so far (bench.py's gpu_launches) */
+int64_t fw_launch_count(fw_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,454 @@
+// fw_api.cu -- C ABI of libfwsim.so (include/fwsim.h): handle lifetime, constant folding, host<->device plumbing.
+// No torch types cross this boundary; the Python host binds it with ctypes (pyflyt_drone_b200/_lib.py).
+#include "../../include/fwsim.h"
+#include "fw_device.cuh"
+#include "fw_kernels.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t _e = (call);                                                              \
+        if (_e != cudaSuccess) return fail(FW_ECUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+struct FwSim {
+    FwConfig cfg;
+    FwDev dev;
+    FwPlanes pl;
+    int n, device, obs_dim;
+    char* plane_mem;
+    size_t plane_bytes;
+    cudaStream_t io_stream;
+    // *_host staging: pinned host + device mirrors
+    float *h_act, *h_obs, *h_rew, *h_term;
+    uint8_t* h_flg;
+    float *d_act, *d_obs, *d_rew, *d_term;
+    uint8_t* d_flg;
+    int64_t launches;
+};
+
+extern "C" int fw_abi_version(void) { return FW_ABI_VERSION; }
+extern "C" const char* fw_last_error(void) { return g_err.c_str(); }
+extern "C" int fw_config_size(void) { return (int)sizeof(FwConfig); }
+
+static bool invert6(const double A[36], double out[36]) {
+    double m[6][12];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) { m[i][j] = A[6 * i + j]; m[i][6 + j] = i == j ? 1.0 : 0.0; }
+    for (int i = 0; i < 6; ++i) {
+        int p = i;
+        for (int r = i + 1; r < 6; ++r) if (fabs(m[r][i]) > fabs(m[p][i])) p = r;
+        if (fabs(m[p][i]) < 1e-300) return false;
+        if (p != i) for (int k = 0; k < 12; ++k) std::swap(m[i][k], m[p][k]);
+        double inv = 1.0 / m[i][i];
+        for (int k = 0; k < 12; ++k) m[i][k] *= inv;
+        for (int r = 0; r < 6; ++r) {
+            if (r == i) continue;
+            double f = m[r][i];
+            if (f == 0.0) continue;
+            for (int k = 0; k < 12; ++k) m[r][k] -= f * m[i][k];
+        }
+    }
+    for (int i = 0; i < 6; ++i) for (int j = 0; j < 6; ++j) out[6 * i + j] = m[i][6 + j];
+    return true;
+}
+
+static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwDev& d) {
+    memset(&d, 0, sizeof(d));
+    const double PI = 3.14159265358979323846, DEG = PI / 180.0;
+    if (!(c.dt > 0) || !(c.mass > 0)) return fail(FW_EINVAL, "dt and mass must be positive");
+    if (c.task < 0 || c.task > 1) return fail(FW_EINVAL, "task %d not supported by this build (0 physics, 1 waypoints)", c.task);
+    if (c.num_targets < 0 || c.num_targets > FW_MAX_TARGETS) return fail(FW_EINVAL, "num_targets out of range");
+    if (c.task != 0 && c.num_targets < 1) return fail(FW_EINVAL, "waypoint task needs num_targets >= 1");
+    if (c.context_len < 0 || c.context_len > 4) return fail(FW_EINVAL, "context_len out of range");
+    if (c.n_col < 0 || c.n_col > FW_MAX_COL) return fail(FW_EINVAL, "n_col out of range");
+    if (c.physics_per_control < 1 || c.substeps_per_inner < 1 || c.inner_per_step < 1 || c.warmup_inner < 0)
+        return fail(FW_EINVAL, "bad step ratios");
+    if (c.substeps_per_inner % c.physics_per_control != 0)
+        return fail(FW_EINVAL, "substeps_per_inner must be a multiple of physics_per_control (control latch alignment)");
+    for (int s = 0; s < FW_NSURF; ++s) {
+        SurfDev& o = d.surf[s];
+        if (!(c.chord[s] > 0) || !(c.span[s] > 0) || !(c.surf_tau[s] > 0)) return fail(FW_EINVAL, "surface %d: bad geometry", s);
+        double ar = c.span[s] / c.chord[s];
+        double cla = c.cl_alpha_2d[s] * (ar / (ar + ((2.0 * (ar + 4.0)) / (ar + 2.0))));
+        double theta_f = acos(2.0 * c.flap_to_chord[s] - 1.0);
+        double aero_tau = 1.0 - ((theta_f - sin(theta_f)) / PI);
+        o.k_act = (float)(c.dt / c.surf_tau[s]);
+        o.defl_rad = (float)(c.defl_limit_deg[s] * DEG);
+        o.defl_deg = (float)c.defl_limit_deg[s];
+        o.cla = (float)cla;
+        o.tau_eta = (float)(aero_tau * c.eta[s]);
+        o.omf = (float)(1.0 - c.flap_to_chord[s]);
+        o.a0_base = (float)(c.alpha0_base_deg[s] * DEG);
+        o.asp_base = (float)(c.stall_p_base_deg[s] * DEG);
+        o.asn_base = (float)(c.stall_n_base_deg[s] * DEG);
+        o.inv_pi_ar = (float)(1.0 / (PI * ar));
+        o.cd0 = (float)c.cd0[s];
+        o.stall_k = (float)(0.41 * (1.0 - exp(-17.0 / ar)));
+        o.qarea = (float)(0.5 * c.rho * c.chord[s] * c.span[s]);
+        o.chord = (float)c.chord[s];
+        const double* l = c.lift_unit[s];
+        const double* f = c.fwd_unit[s];
+        double t[3] = {l[1] * f[2] - l[2] * f[1], l[2] * f[0] - l[0] * f[2], l[0] * f[1] - l[1] * f[0]};
+        for (int k = 0; k < 3; ++k) { o.lift[k] = (float)l[k]; o.fwd[k] = (float)f[k]; o.tq[k] = (float)t[k]; o.r[k] = (float)c.r_surf[s][k]; }
+    }
+    if (!(c.motor_tau > 0) || !(c.thrust_coef > 0)) return fail(FW_EINVAL, "bad motor constants");
+    d.motor_k = (float)(c.dt / c.motor_tau);
+    d.noise_ratio = (float)c.noise_ratio;
+    double max_rpm = sqrt(c.total_thrust / c.thrust_coef);
+    d.thrust_max = (float)(max_rpm * max_rpm * c.thrust_coef);
+    d.torque_max = (float)(max_rpm * max_rpm * c.torque_coef);
+    for (int k = 0; k < 3; ++k) { d.r_motor[k] = (float)c.r_motor[k]; d.thrust_unit[k] = (float)c.thrust_unit[k]; d.com[k] = (float)c.com[k]; }
+    d.mass = (float)c.mass;
+    for (int k = 0; k < 9; ++k) d.inertia[k] = (float)c.inertia_o[k];
+    {
+        double A[36] = {0}, Ai[36];
+        const double M = c.mass, cx = c.com[0], cy = c.com[1], cz = c.com[2];
+        const double Cx[3][3] = {{0, -cz, cy}, {cz, 0, -cx}, {-cy, cx, 0}};
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                A[6 * i + j] = c.inertia_o[3 * i + j];
+                A[6 * i + 3 + j] = M * Cx[i][j];
+                A[6 * (3 + i) + j] = -M * Cx[i][j];
+            }
+        for (int i = 0; i < 3; ++i) A[6 * (3 + i) + 3 + i] = M;
+        if (!invert6(A, Ai)) return fail(FW_EINVAL, "singular spatial inertia");
+        for (int k = 0; k < 36; ++k) d.minv[k] = (float)Ai[k];
+    }
+    double rad = 0.0;
+    for (int i = 0; i < c.n_col; ++i) {
+        double r2 = 0;
+        for (int k = 0; k < 3; ++k) { d.col[i][k] = (float)c.col_pts[i][k]; r2 += c.col_pts[i][k] * c.col_pts[i][k]; }
+        rad = fmax(rad, sqrt(r2));
+    }
+    d.col_radius = (float)(rad * 1.0001 + 1e-6);
+    d.contact_margin = (float)c.contact_margin;
+    d.n_col = c.n_col;
+    d.dt = (float)c.dt; d.gravity = (float)c.gravity; d.max_vel = (float)c.max_coord_vel;
+    d.sign_ail_l = (float)c.ail_left_sign; d.sign_ail_r = (float)c.ail_right_sign;
+    d.sign_pitch = (float)c.pitch_sign; d.sign_yaw = (float)c.yaw_sign;
+    d.substeps_per_inner = c.substeps_per_inner; d.inner_per_step = c.inner_per_step;
+    d.warmup_substeps = c.warmup_inner * c.substeps_per_inner;
+    d.freestream_3d = c.freestream_3d; d.cd90_degrees = c.cd90_degrees; d.fast_trig = c.fast_trig;
+    d.task = c.task; d.num_targets = c.num_targets; d.sparse_reward = c.sparse_reward; d.angle_repr = c.angle_repr;
+    d.max_steps = c.max_steps; d.context_len = c.context_len;
+    d.obs_dim = c.task == 0 ? 0 : ((c.angle_repr == 0 ? 12 : 13) + 4 + 6 + 3 * c.context_len);
+    d.early_return_on_crash = c.early_return_on_crash; d.complete_truncates = c.complete_truncates;
+    d.goal_reach = (float)c.goal_reach; d.dome = (float)c.dome; d.spawn_size = (float)c.spawn_size; d.min_height = (float)c.min_height;
+    for (int k = 0; k < 3; ++k) {
+        d.start_pos[k] = (float)c.start_pos[k]; d.start_vel[k] = (float)c.start_vel[k];
+        d.wind_base[k] = (float)c.wind_base[k]; d.wind_base_lo[k] = (float)c.wind_base_lo[k]; d.wind_base_hi[k] = (float)c.wind_base_hi[k];
+        d.gust_amp[k] = (float)c.gust_amp[k]; d.gust_amp_lo[k] = (float)c.gust_amp_lo[k]; d.gust_amp_hi[k] = (float)c.gust_amp_hi[k];
+    }
+    d.wind_mode = c.wind_mode; d.wind_randomize = c.wind_randomize; d.wind_rand_phase = c.wind_rand_phase;
+    d.wind_start_substep = c.wind_start_substep;
+    d.gust_omega = (float)(2.0 * PI * c.gust_freq); d.gust_phase = (float)c.gust_phase;
+    d.warm_cached = 0;
+    d.seed_lo = (uint32_t)(seed & 0xffffffffu); d.seed_hi = (uint32_t)(seed >> 32); d.env_id0 = env_id0;
+    d.n = n;
+    return FW_OK;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, uint64_t seed, uint32_t env_id0, fw_handle* out) {
+    if (!cfg || !out) return fail(FW_EINVAL, "null argument");
+    if (n_envs <= 0) return fail(FW_EINVAL, "n_envs must be positive");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0)
+        return fail(FW_ECUDA, "no CUDA device available (%s): libfwsim has no CPU fallback", cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(FW_EINVAL, "device %d out of range (%d visible)", device, ndev);
+    CU(cudaSetDevice(device));
+    FwSim* h = new FwSim();
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg; h->n = n_envs; h->device = device;
+    int rc = derive(*cfg, n_envs, seed, env_id0, h->dev);
+    if (rc != FW_OK) { delete h; return rc; }
+    h->obs_dim = h->dev.obs_dim;
+    const size_t N = (size_t)n_envs, T = (size_t)(cfg->num_targets > 0 ? cfg->num_targets : 1);
+    size_t off = 0, o_s[6], o_w0, o_w1, o_t, o_ep, o_st;
+    for (int k = 0; k < 6; ++k) { o_s[k] = off; off = align_up(off + N * 16, 256); }
+    o_w0 = off; off = align_up(off + N * 16, 256);
+    o_w1 = off; off = align_up(off + N * 16, 256);
+    o_t = off; off = align_up(off + T * 3 * N * 4, 256);
+    o_ep = off; off = align_up(off + N * 4, 256);
+    o_st = off; off = align_up(off + 8 * sizeof(double), 256);
+    h->plane_bytes = off;
+    ce = cudaMalloc((void**)&h->plane_mem, off);
+    if (ce != cudaSuccess) { delete h; return fail(FW_ENOMEM, "cudaMalloc(%zu): %s", off, cudaGetErrorString(ce)); }
+    cudaMemset(h->plane_mem, 0, off);
+    FwPlanes& pl = h->pl;
+    pl.s0 = (float4*)(h->plane_mem + o_s[0]); pl.s1 = (float4*)(h->plane_mem + o_s[1]);
+    pl.s2 = (float4*)(h->plane_mem + o_s[2]); pl.s3 = (float4*)(h->plane_mem + o_s[3]);
+    pl.s4 = (float4*)(h->plane_mem + o_s[4]); pl.s5 = (int4*)(h->plane_mem + o_s[5]);
+    pl.w0 = (float4*)(h->plane_mem + o_w0); pl.w1 = (float4*)(h->plane_mem + o_w1);
+    pl.targets = (float*)(h->plane_mem + o_t); pl.ep_ret = (float*)(h->plane_mem + o_ep);
+    pl.stats = (double*)(h->plane_mem + o_st);
+    // episode counter starts at -1 so that the first reset opens episode 0
+    cudaMemset(pl.s5, 0xff, N * 16);
+    CU(cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking));
+
+    // cache the deterministic warm-up result when no wind acts during it
+    if (h->dev.wind_mode == 0 || h->dev.wind_start_substep >= h->dev.warmup_substeps) {
+        float* d_warm = nullptr;
+        CU(cudaMalloc((void**)&d_warm, 20 * sizeof(float)));
+        CU(fwk_launch_warm(h->dev, h->pl, d_warm, h->io_stream));
+        h->launches++;
+        CU(cudaMemcpyAsync(h->dev.warm, d_warm, 20 * sizeof(float), cudaMemcpyDeviceToHost, h->io_stream));
+        CU(cudaStreamSynchronize(h->io_stream));
+        cudaFree(d_warm);
+        h->dev.warm_cached = 1;
+    }
+    CU(fwk_launch_reset(h->dev, h->pl, nullptr, nullptr, h->io_stream));
+    h->launches++;
+    CU(cudaStreamSynchronize(h->io_stream));
+    *out = h;
+    return FW_OK;
+}
+
+extern "C" int fw_destroy(fw_handle h) {
+    if (!h) return FW_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (h->plane_mem) cudaFree(h->plane_mem);
+    if (h->d_act) cudaFree(h->d_act);
+    if (h->d_obs) cudaFree(h->d_obs);
+    if (h->d_rew) cudaFree(h->d_rew);
+    if (h->d_term) cudaFree(h->d_term);
+    if (h->d_flg) cudaFree(h->d_flg);
+    if (h->h_act) cudaFreeHost(h->h_act);
+    if (h->h_obs) cudaFreeHost(h->h_obs);
+    if (h->h_rew) cudaFreeHost(h->h_rew);
+    if (h->h_term) cudaFreeHost(h->h_term);
+    if (h->h_flg) cudaFreeHost(h->h_flg);
+    if (h->io_stream) cudaStreamDestroy(h->io_stream);
+    delete h;
+    return FW_OK;
+}
+
+extern "C" int fw_num_envs(fw_handle h) { return h ? h->n : fail(FW_EINVAL, "null handle"); }
+extern "C" int fw_obs_dim(fw_handle h) { return h ? h->obs_dim : fail(FW_EINVAL, "null handle"); }
+extern "C" int64_t fw_launch_count(fw_handle h) { return h ? h->launches : 0; }
+
+extern "C" int fw_reset(fw_handle h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
+    if (!h) return fail(FW_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(fwk_launch_reset(h->dev, h->pl, mask_dev, obs_dev, (cudaStream_t)stream));
+    h->launches++;
+    return FW_OK;
+}
+
+extern "C" int fw_step(fw_handle h, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* flags_dev,
+                       float* term_obs_dev, void* stream) {
+    if (!h) return fail(FW_EINVAL, "null handle");
+    if (!act_dev) return fail(FW_EINVAL, "act_dev is null");
+    if ((reinterpret_cast<uintptr_t>(act_dev) & 15u) != 0) return fail(FW_EINVAL, "act_dev must be 16-byte aligned");
+    CU(cudaSetDevice(h->device));
+    CU(fwk_launch_step(h->dev, h->pl, act_dev, obs_dev, rew_dev, flags_dev, term_obs_dev, false, 0u, (cudaStream_t)stream));
+    h->launches++;
+    return FW_OK;
+}
+
+extern "C" int fw_step_random(fw_handle h, uint32_t step_index, int32_t n_steps, float* rew_dev, uint8_t* flags_dev,
+                              void* stream) {
+    if (!h) return fail(FW_EINVAL, "null handle");
+    if (n_steps < 0) return fail(FW_EINVAL, "n_steps < 0");
+    CU(cudaSetDevice(h->device));
+    for (int s = 0; s < n_steps; ++s) {
+        CU(fwk_launch_step(h->dev, h->pl, nullptr, nullptr, rew_dev, flags_dev, nullptr, true, step_index + (uint32_t)s,
+                           (cudaStream_t)stream));
+        h->launches++;
+    }
+    return FW_OK;
+}
+
+static int ensure_host_io(FwSim* h) {
+    if (h->h_act) return FW_OK;
+    const size_t N = (size_t)h->n, D = (size_t)(h->obs_dim > 0 ? h->obs_dim : 1);
+    CU(cudaMallocHost((void**)&h->h_act, N * 4 * sizeof(float)));
+    CU(cudaMallocHost((void**)&h->h_obs, N * D * sizeof(float)));
+    CU(cudaMallocHost((void**)&h->h_rew, N * sizeof(float)));
+    CU(cudaMallocHost((void**)&h->h_term, N * D * sizeof(float)));
+    CU(cudaMallocHost((void**)&h->h_flg, N));
+    CU(cudaMalloc((void**)&h->d_act, N * 4 * sizeof(float)));
+    CU(cudaMalloc((void**)&h->d_obs, N * D * sizeof(float)));
+    CU(cudaMalloc((void**)&h->d_rew, N * sizeof(float)));
+    CU(cudaMalloc((void**)&h->d_term, N * D * sizeof(float)));
+    CU(cudaMalloc((void**)&h->d_flg, N));
+    CU(cudaMemset(h->d_term, 0, N * D * sizeof(float)));
+    return FW_OK;
+}
+
+extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host, float* rew_host, uint8_t* flags_host,
+                            float* term_obs_host) {
+    if (!h) return fail(FW_EINVAL, "null handle");
+    if (!act_host) return fail(FW_EINVAL, "act_host is null");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_host_io(h);
+    if (rc != FW_OK) return rc;
+    const size_t N = (size_t)h->n, D = (size_t)h->obs_dim;
+    cudaStream_t st = h->io_stream;
+    memcpy(h->h_act, act_host, N * 4 * sizeof(float));
+    CU(cudaMemcpyAsync(h->d_act, h->h_act, N * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU(fwk_launch_step(h->dev, h->pl, h->d_act, D ? h->d_obs : nullptr, h->d_rew, h->d_flg,
+                       (term_obs_host && D) ? h->d_term : nullptr, false, 0u, st));
+    h->launches++;
+    if (obs_host && D) CU(cudaMemcpyAsync(h->h_obs, h->d_obs, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (rew_host) CU(cudaMemcpyAsync(h->h_rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (flags_host) CU(cudaMemcpyAsync(h->h_flg, h->d_flg, N, cudaMemcpyDeviceToHost, st));
+    if (term_obs_host && D) CU(cudaMemcpyAsync(h->h_term, h->d_term, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (obs_host && D) memcpy(obs_host, h->h_obs, N * D * sizeof(float));
+    if (rew_host) memcpy(rew_host, h->h_rew, N * sizeof(float));
+    if (flags_host) memcpy(flags_host, h->h_flg, N);
+    if (term_obs_host && D) memcpy(term_obs_host, h->h_term, N * D * sizeof(float));
+    return FW_OK;
+}
+
+extern "C" int fw_reset_host(fw_handle h, float* obs_host) {
+    if (!h) return fail(FW_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_host_io(h);
+    if (rc != FW_OK) return rc;
+    const size_t N = (size_t)h->n, D = (size_t)h->obs_dim;
+    cudaStream_t st = h->io_stream;
+    CU(fwk_launch_reset(h->dev, h->pl, nullptr, D ? h->d_obs : nullptr, st));
+    h->launches++;
+    if (obs_host && D) CU(cudaMemcpyAsync(h->h_obs, h->d_obs, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (obs_host && D) memcpy(obs_host, h->h_obs, N * D * sizeof(float));
+    return FW_OK;
+}
+
+// ------------------------------------------------------------------ state injection / inspection
+struct HostPlanes {
+    std::vector<float4> s[5];
+    std::vector<int4> s5;
+    std::vector<float4> w0, w1;
+    std::vector<float> targets;
+};
+
+static int pull(FwSim* h, HostPlanes& hp) {
+    const size_t N = (size_t)h->n, T = (size_t)(h->cfg.num_targets > 0 ? h->cfg.num_targets : 1);
+    float4* src[5] = {h->pl.s0, h->pl.s1, h->pl.s2, h->pl.s3, h->pl.s4};
+    CU(cudaDeviceSynchronize());
+    for (int k = 0; k < 5; ++k) { hp.s[k].resize(N); CU(cudaMemcpy(hp.s[k].data(), src[k], N * 16, cudaMemcpyDeviceToHost)); }
+    hp.s5.resize(N); CU(cudaMemcpy(hp.s5.data(), h->pl.s5, N * 16, cudaMemcpyDeviceToHost));
+    hp.w0.resize(N); CU(cudaMemcpy(hp.w0.data(), h->pl.w0, N * 16, cudaMemcpyDeviceToHost));
+    hp.w1.resize(N); CU(cudaMemcpy(hp.w1.data(), h->pl.w1, N * 16, cudaMemcpyDeviceToHost));
+    hp.targets.resize(T * 3 * N); CU(cudaMemcpy(hp.targets.data(), h->pl.targets, T * 3 * N * 4, cudaMemcpyDeviceToHost));
+    return FW_OK;
+}
+
+static int push(FwSim* h, const HostPlanes& hp) {
+    const size_t N = (size_t)h->n, T = (size_t)(h->cfg.num_targets > 0 ? h->cfg.num_targets : 1);
+    float4* dst[5] = {h->pl.s0, h->pl.s1, h->pl.s2, h->pl.s3, h->pl.s4};
+    for (int k = 0; k < 5; ++k) CU(cudaMemcpy(dst[k], hp.s[k].data(), N * 16, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->pl.s5, hp.s5.data(), N * 16, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->pl.w0, hp.w0.data(), N * 16, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->pl.w1, hp.w1.data(), N * 16, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->pl.targets, hp.targets.data(), T * 3 * N * 4, cudaMemcpyHostToDevice));
+    CU(cudaDeviceSynchronize());
+    return FW_OK;
+}
+
+extern "C" int fw_get_state(fw_handle h, FwStateHost* s) {
+    if (!h || !s) return fail(FW_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    HostPlanes hp;
+    int rc = pull(h, hp);
+    if (rc != FW_OK) return rc;
+    const size_t N = (size_t)h->n;
+    const int T = h->cfg.num_targets;
+    for (size_t i = 0; i < N; ++i) {
+        const float4 &a = hp.s[0][i], &b = hp.s[1][i], &c = hp.s[2][i], &d = hp.s[3][i], &f = hp.s[4][i];
+        const int4& g = hp.s5[i];
+        if (s->pos) { s->pos[3 * i] = a.x; s->pos[3 * i + 1] = a.y; s->pos[3 * i + 2] = a.z; }
+        if (s->quat) { s->quat[4 * i] = b.x; s->quat[4 * i + 1] = b.y; s->quat[4 * i + 2] = b.z; s->quat[4 * i + 3] = b.w; }
+        if (s->vel) { s->vel[3 * i] = c.x; s->vel[3 * i + 1] = c.y; s->vel[3 * i + 2] = c.z; }
+        if (s->omega) { s->omega[3 * i] = d.x; s->omega[3 * i + 1] = d.y; s->omega[3 * i + 2] = d.z; }
+        if (s->act) {
+            float* o = s->act + 6 * i;
+            o[0] = c.w; o[1] = d.w; o[2] = f.x; o[3] = f.y; o[4] = f.z; o[5] = a.w;
+        }
+        if (s->new_dist) s->new_dist[i] = f.w;
+        if (s->step_count) s->step_count[i] = g.x;
+        if (s->physics_steps) s->physics_steps[i] = g.y;
+        if (s->episode) s->episode[i] = (uint32_t)g.z;
+        if (s->target_idx) s->target_idx[i] = g.w;
+        if (s->wind) {
+            float* o = s->wind + 7 * i;
+            o[0] = hp.w0[i].x; o[1] = hp.w0[i].y; o[2] = hp.w0[i].z;
+            o[3] = hp.w1[i].x; o[4] = hp.w1[i].y; o[5] = hp.w1[i].z; o[6] = hp.w0[i].w;
+        }
+        if (s->targets)
+            for (int t = 0; t < T; ++t)
+                for (int k = 0; k < 3; ++k) s->targets[(i * T + t) * 3 + k] = hp.targets[(size_t)(t * 3 + k) * N + i];
+    }
+    return FW_OK;
+}
+
+extern "C" int fw_set_state(fw_handle h, const FwStateHost* s) {
+    if (!h || !s) return fail(FW_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    HostPlanes hp;
+    int rc = pull(h, hp);
+    if (rc != FW_OK) return rc;
+    const size_t N = (size_t)h->n;
+    const int T = h->cfg.num_targets;
+    for (size_t i = 0; i < N; ++i) {
+        float4 &a = hp.s[0][i], &b = hp.s[1][i], &c = hp.s[2][i], &d = hp.s[3][i], &f = hp.s[4][i];
+        int4& g = hp.s5[i];
+        if (s->pos) { a.x = s->pos[3 * i]; a.y = s->pos[3 * i + 1]; a.z = s->pos[3 * i + 2]; }
+        if (s->quat) { b.x = s->quat[4 * i]; b.y = s->quat[4 * i + 1]; b.z = s->quat[4 * i + 2]; b.w = s->quat[4 * i + 3]; }
+        if (s->vel) { c.x = s->vel[3 * i]; c.y = s->vel[3 * i + 1]; c.z = s->vel[3 * i + 2]; }
+        if (s->omega) { d.x = s->omega[3 * i]; d.y = s->omega[3 * i + 1]; d.z = s->omega[3 * i + 2]; }
+        if (s->act) {
+            const float* o = s->act + 6 * i;
+            c.w = o[0]; d.w = o[1]; f.x = o[2]; f.y = o[3]; f.z = o[4]; a.w = o[5];
+        }
+        if (s->new_dist) f.w = s->new_dist[i];
+        if (s->step_count) g.x = s->step_count[i];
+        if (s->physics_steps) g.y = s->physics_steps[i];
+        if (s->episode) g.z = (int)s->episode[i];
+        if (s->target_idx) g.w = s->target_idx[i];
+        if (s->wind) {
+            const float* o = s->wind + 7 * i;
+            hp.w0[i] = make_float4(o[0], o[1], o[2], o[6]);
+            hp.w1[i] = make_float4(o[3], o[4], o[5], 0.0f);
+        }
+        if (s->targets)
+            for (int t = 0; t < T; ++t)
+                for (int k = 0; k < 3; ++k) hp.targets[(size_t)(t * 3 + k) * N + i] = s->targets[(i * T + t) * 3 + k];
+    }
+    return push(h, hp);
+}
+
+extern "C" int fw_episode_stats(fw_handle h, double out[8]) {
+    if (!h || !out) return fail(FW_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, h->pl.stats, 8 * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemset(h->pl.stats, 0, 8 * sizeof(double)));
+    return FW_OK;
+}

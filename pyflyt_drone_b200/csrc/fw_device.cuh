@@ -1,0 +1,501 @@
+// fw_device.cuh -- device-side model of one fixed-wing environment (fp32, one thread per env).
+//
+// Replaces, per 240 Hz physics substep, what the reference runs through PyFlyt + PyBullet on the CPU:
+//   Fixedwing.update_control / update_physics / update_state, LiftingSurface(s), Motors, stepSimulation
+//   (call sites: /root/reference/envs/fixedwing_envs/fixedwing_base_env.py:331,339), and per agent step
+//   FixedwingBaseEnv.step (:314-348), compute_base_term_trunc_reward (:296-312), the waypoint
+//   compute_state / compute_term_trunc_reward (/root/reference/envs/fixedwing_waypoint_objlock_env.py:197-343)
+//   and FlattenWaypointEnv.observation (/root/reference/envs/flatten_waypoint_env.py:52-72).
+// Aircraft constants: /root/reference/my_models/fixedwing/fixewing.yaml:1-71 (folded into SurfDev by fw_api.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FWD_NSURF 5
+#define FWD_MAX_COL 16
+#define FWD_MAX_TARGETS 16
+
+#define FWD_STREAM_TARGETS 1u
+#define FWD_STREAM_NOISE 2u
+#define FWD_STREAM_ACTION 3u
+#define FWD_STREAM_WIND 4u
+#define FWD_STREAM_OBST 6u
+
+#define FWD_PI 3.14159265358979323846f
+#define FWD_HALF_PI 1.57079632679489661923f
+
+// per-surface constants, all derived on the host in double and rounded once
+struct SurfDev {
+    float k_act;        // dt / tau
+    float defl_rad;     // deflection limit, radians
+    float defl_deg;     // deflection limit, degrees
+    float cla;          // Cl_alpha_3D
+    float tau_eta;      // aero_tau * eta  (= delta_Cl / (cla * deflection))
+    float omf;          // 1 - flap_to_chord
+    float a0_base, asp_base, asn_base;  // radians
+    float inv_pi_ar;    // 1 / (pi * aspect)
+    float cd0;
+    float stall_k;      // 0.41 * (1 - exp(-17 / aspect))
+    float qarea;        // 0.5 * rho * area
+    float chord;
+    float lift[3], fwd[3], tq[3], r[3];
+};
+
+struct FwDev {
+    SurfDev surf[FWD_NSURF];
+    // motor
+    float motor_k, noise_ratio, thrust_max, torque_max;
+    float r_motor[3], thrust_unit[3];
+    // rigid body about O
+    float mass;
+    float com[3];
+    float inertia[9];
+    float minv[36];
+    float col[FWD_MAX_COL][3];
+    float col_radius, contact_margin;
+    int n_col;
+    // simulator
+    float dt, gravity, max_vel;
+    float sign_ail_l, sign_ail_r, sign_pitch, sign_yaw;
+    int substeps_per_inner, inner_per_step, warmup_substeps;
+    int freestream_3d, cd90_degrees, fast_trig;
+    // env
+    int task, num_targets, sparse_reward, angle_repr, max_steps, context_len, obs_dim;
+    int early_return_on_crash, complete_truncates;
+    float goal_reach, dome, spawn_size, min_height;
+    float start_pos[3], start_vel[3];
+    // wind
+    int wind_mode, wind_randomize, wind_rand_phase, wind_start_substep;
+    float wind_base[3], wind_base_lo[3], wind_base_hi[3];
+    float gust_amp[3], gust_amp_lo[3], gust_amp_hi[3];
+    float gust_omega, gust_phase;   // 2*pi*f
+    // cached post-warm-up state (valid when no wind acts during the warm-up): pos3 quat4 vel3 omega3 act5 thr
+    int warm_cached;
+    float warm[20];
+    // rng / sharding
+    uint32_t seed_lo, seed_hi, env_id0;
+    int n;
+};
+
+// SoA state in HBM: float4 planes (16-byte coalesced accesses, one plane element per env)
+struct FwPlanes {
+    float4* s0;   // pos.xyz, throttle
+    float4* s1;   // quat xyzw
+    float4* s2;   // vel.xyz, act0
+    float4* s3;   // omega.xyz, act1
+    float4* s4;   // act2, act3, act4, new_dist
+    int4* s5;     // step_count, physics_steps, episode, target_idx
+    float4* w0;   // wind base xyz, gust phase
+    float4* w1;   // gust amp xyz, -
+    float* targets;  // [T][3][N]
+    float* ep_ret;   // [N]
+    double* stats;   // [8] global episode accumulators
+};
+
+struct EnvState {
+    float px, py, pz;
+    float qx, qy, qz, qw;
+    float vx, vy, vz;
+    float wx, wy, wz;
+    float act[FWD_NSURF];
+    float thr;
+    float new_dist;
+    int step_count, physics_steps, tidx;
+    uint32_t episode;
+};
+
+// ------------------------------------------------------------------ RNG: Philox4x32-10
+__device__ __forceinline__ uint4 fw_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ float fw_u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+
+__device__ __forceinline__ void fw_normals4(const FwDev& p, uint32_t env, uint32_t episode, uint32_t idx, float n[4]) {
+    uint4 r = fw_philox(p.seed_lo, p.seed_hi, env, episode, idx, FWD_STREAM_NOISE);
+    float ra = sqrtf(-2.0f * logf(fw_u01(r.x))), rb = sqrtf(-2.0f * logf(fw_u01(r.z)));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * fw_u01(r.y), &s0, &c0);
+    sincospif(2.0f * fw_u01(r.w), &s1, &c1);
+    n[0] = ra * c0; n[1] = ra * s0; n[2] = rb * c1; n[3] = rb * s1;
+}
+
+// ------------------------------------------------------------------ math helpers
+__device__ __forceinline__ void fw_sincos(int fast, float x, float* s, float* c) {
+    if (fast) { *s = __sinf(x); *c = __cosf(x); }
+    else sincosf(x, s, c);
+}
+
+struct Mat3 { float m[9]; };
+
+__device__ __forceinline__ Mat3 fw_quat_mat(float x, float y, float z, float w) {
+    // pybullet getMatrixFromQuaternion; the state quaternion is kept normalised so s = 2/|q|^2 = 2
+    float s = 2.0f / (x * x + y * y + z * z + w * w);
+    float xs = x * s, ys = y * s, zs = z * s;
+    float wx = w * xs, wy = w * ys, wz = w * zs;
+    float xx = x * xs, xy = x * ys, xz = x * zs;
+    float yy = y * ys, yz = y * zs, zz = z * zs;
+    Mat3 R;
+    R.m[0] = 1.0f - (yy + zz); R.m[1] = xy - wz;          R.m[2] = xz + wy;
+    R.m[3] = xy + wz;          R.m[4] = 1.0f - (xx + zz); R.m[5] = yz - wx;
+    R.m[6] = xz - wy;          R.m[7] = yz + wx;          R.m[8] = 1.0f - (xx + yy);
+    return R;
+}
+
+// ------------------------------------------------------------------ lifting surface (Khan & Nahon model as used by PyFlyt)
+// Returns force (body frame) and the scalar pitching torque magnitude about the surface's torque axis.
+__device__ __forceinline__ void fw_surface(const FwDev& p, const SurfDev& sf, float act, float vx, float vy, float vz,
+                                           float& fx, float& fy, float& fz, float& tq) {
+    float vl = vx * sf.lift[0] + vy * sf.lift[1] + vz * sf.lift[2];
+    float vf = vx * sf.fwd[0] + vy * sf.fwd[1] + vz * sf.fwd[2];
+    float h2 = vl * vl + vf * vf;
+    float V2 = p.freestream_3d ? (vx * vx + vy * vy + vz * vz) : h2;
+    float alpha = atan2f(-vl, vf);
+    float inv_h = h2 > 0.0f ? rsqrtf(h2) : 0.0f;
+    float cosA = h2 > 0.0f ? vf * inv_h : 1.0f;
+    float sinA = -vl * inv_h;
+
+    float defl = act * sf.defl_rad;
+    float te = sf.tau_eta * defl;
+    float a0 = sf.a0_base - te;
+    float shift = sf.omf * te;
+    float asp = sf.asp_base - shift;
+    float asn = sf.asn_base - shift;
+    bool nostall = (asn < alpha) && (alpha < asp);
+
+    // induced angle: attached-flow value, or the post-stall linear decay to +-pi/2 (numpy.interp clamps)
+    float cl_lin = sf.cla * (alpha - a0);
+    float ai;
+    if (nostall) {
+        ai = cl_lin * sf.inv_pi_ar;
+    } else if (alpha > 0.0f) {
+        float ai_st = sf.cla * (asp - a0) * sf.inv_pi_ar;
+        float x0 = asp, x1 = FWD_HALF_PI;
+        ai = alpha <= x0 ? ai_st : (alpha >= x1 ? 0.0f : (0.0f - ai_st) / (x1 - x0) * (alpha - x0) + ai_st);
+    } else {
+        float ai_st = sf.cla * (asn - a0) * sf.inv_pi_ar;
+        float x0 = -FWD_HALF_PI, x1 = asn;
+        ai = alpha <= x0 ? 0.0f : (alpha >= x1 ? ai_st : (ai_st - 0.0f) / (x1 - x0) * (alpha - x0) + 0.0f);
+    }
+    float ae = alpha - a0 - ai;
+    float s, c;
+    fw_sincos(p.fast_trig, ae, &s, &c);
+
+    float Cl, Cd, CM;
+    if (nostall) {
+        float CT = sf.cd0 * c;
+        float CN = (cl_lin + CT * s) / c;
+        Cl = cl_lin;
+        Cd = CN * s + CT * c;
+        CM = -CN * (0.25f - 0.175f * (1.0f - (2.0f * ae) / FWD_PI));
+    } else {
+        float d = p.cd90_degrees ? act * sf.defl_deg : defl;
+        float cd90 = (-4.26e-2f) * (d * d) + (2.1e-1f) * d + 1.98f;
+        float CN = cd90 * s * (1.0f / (0.56f + 0.44f * fabsf(s)) - sf.stall_k);
+        float CT = 0.5f * sf.cd0 * c;
+        Cl = CN * c - CT * s;
+        Cd = CN * s + CT * c;
+        CM = -CN * (0.25f - 0.175f * (1.0f - (2.0f * fabsf(ae)) / FWD_PI));
+    }
+    float Q = sf.qarea * V2;
+    float lift = Cl * Q, drag = Cd * Q;
+    float fn = lift * cosA + drag * sinA;
+    float fp = lift * sinA - drag * cosA;
+    fx = sf.lift[0] * fn + sf.fwd[0] * fp;
+    fy = sf.lift[1] * fn + sf.fwd[1] * fp;
+    fz = sf.lift[2] * fn + sf.fwd[2] * fp;
+    tq = Q * CM * sf.chord;
+}
+
+// ------------------------------------------------------------------ one 240 Hz substep
+// cmd: latched actuator commands [5 surfaces + motor]; wind: world-frame wind seen by the surfaces
+// (already selected for this substep's time stamp); nz: N(0,1) draw for the motor noise.
+__device__ __forceinline__ void fw_substep(const FwDev& p, EnvState& e, const float cmd[6], float wnx, float wny,
+                                           float wnz, float nz, bool& contact) {
+    const float dt = p.dt;
+    Mat3 R = fw_quat_mat(e.qx, e.qy, e.qz, e.qw);
+    const float* m = R.m;
+    // body-frame velocities of O (R^T v, R^T w) and the wind in the body frame
+    float vbx = m[0] * (e.vx - wnx) + m[3] * (e.vy - wny) + m[6] * (e.vz - wnz);
+    float vby = m[1] * (e.vx - wnx) + m[4] * (e.vy - wny) + m[7] * (e.vz - wnz);
+    float vbz = m[2] * (e.vx - wnx) + m[5] * (e.vy - wny) + m[8] * (e.vz - wnz);
+    float wbx = m[0] * e.wx + m[3] * e.wy + m[6] * e.wz;
+    float wby = m[1] * e.wx + m[4] * e.wy + m[7] * e.wz;
+    float wbz = m[2] * e.wx + m[5] * e.wy + m[8] * e.wz;
+
+    float Fx = 0.f, Fy = 0.f, Fz = 0.f, Tx = 0.f, Ty = 0.f, Tz = 0.f;
+#pragma unroll
+    for (int s = 0; s < FWD_NSURF; ++s) {
+        const SurfDev& sf = p.surf[s];
+        e.act[s] += sf.k_act * (cmd[s] - e.act[s]);
+        // local airflow at the link CoM: v_O + w x r  (wind already subtracted from v_O)
+        float sx = vbx + (wby * sf.r[2] - wbz * sf.r[1]);
+        float sy = vby + (wbz * sf.r[0] - wbx * sf.r[2]);
+        float sz = vbz + (wbx * sf.r[1] - wby * sf.r[0]);
+        float fx, fy, fz, tq;
+        fw_surface(p, sf, e.act[s], sx, sy, sz, fx, fy, fz, tq);
+        Fx += fx; Fy += fy; Fz += fz;
+        Tx += sf.r[1] * fz - sf.r[2] * fy + tq * sf.tq[0];
+        Ty += sf.r[2] * fx - sf.r[0] * fz + tq * sf.tq[1];
+        Tz += sf.r[0] * fy - sf.r[1] * fx + tq * sf.tq[2];
+    }
+    {   // motor: first-order lag, multiplicative gaussian noise, thrust ~ rpm^2
+        e.thr += p.motor_k * (cmd[5] - e.thr);
+        e.thr += nz * e.thr * p.noise_ratio;
+        float t2 = e.thr * e.thr;
+        float thrust = t2 * p.thrust_max, torque = t2 * p.torque_max;
+        float fx = thrust * p.thrust_unit[0], fy = thrust * p.thrust_unit[1], fz = thrust * p.thrust_unit[2];
+        Fx += fx; Fy += fy; Fz += fz;
+        Tx += p.r_motor[1] * fz - p.r_motor[2] * fy + torque * p.thrust_unit[0];
+        Ty += p.r_motor[2] * fx - p.r_motor[0] * fz + torque * p.thrust_unit[1];
+        Tz += p.r_motor[0] * fy - p.r_motor[1] * fx + torque * p.thrust_unit[2];
+    }
+    // ground contact is detected on the pose entering the step (Bullet runs collision detection first)
+    if (e.pz <= p.col_radius + p.contact_margin) {
+        for (int i = 0; i < p.n_col; ++i) {
+            float z = e.pz + m[6] * p.col[i][0] + m[7] * p.col[i][1] + m[8] * p.col[i][2];
+            contact = contact || (z <= p.contact_margin);
+        }
+    }
+    // gravity on every link == M g at the composite CoM; g_body = R^T (0,0,-g)
+    float gx = -p.gravity * m[6], gy = -p.gravity * m[7], gz = -p.gravity * m[8];
+    Fx += p.mass * gx; Fy += p.mass * gy; Fz += p.mass * gz;
+    Tx += p.mass * (p.com[1] * gz - p.com[2] * gy);
+    Ty += p.mass * (p.com[2] * gx - p.com[0] * gz);
+    Tz += p.mass * (p.com[0] * gy - p.com[1] * gx);
+    // bias terms: w x (I w) and M w x (w x c)
+    float Iwx = p.inertia[0] * wbx + p.inertia[1] * wby + p.inertia[2] * wbz;
+    float Iwy = p.inertia[3] * wbx + p.inertia[4] * wby + p.inertia[5] * wbz;
+    float Iwz = p.inertia[6] * wbx + p.inertia[7] * wby + p.inertia[8] * wbz;
+    float b0 = Tx - (wby * Iwz - wbz * Iwy);
+    float b1 = Ty - (wbz * Iwx - wbx * Iwz);
+    float b2 = Tz - (wbx * Iwy - wby * Iwx);
+    float cx = wby * p.com[2] - wbz * p.com[1];
+    float cy = wbz * p.com[0] - wbx * p.com[2];
+    float cz = wbx * p.com[1] - wby * p.com[0];
+    float b3 = Fx - p.mass * (wby * cz - wbz * cy);
+    float b4 = Fy - p.mass * (wbz * cx - wbx * cz);
+    float b5 = Fz - p.mass * (wbx * cy - wby * cx);
+    float acc[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+        acc[i] = p.minv[6 * i + 0] * b0 + p.minv[6 * i + 1] * b1 + p.minv[6 * i + 2] * b2 +
+                 p.minv[6 * i + 3] * b3 + p.minv[6 * i + 4] * b4 + p.minv[6 * i + 5] * b5;
+    // to the world frame, semi-implicit Euler, Bullet's per-coordinate velocity clamp
+    float awx = m[0] * acc[0] + m[1] * acc[1] + m[2] * acc[2];
+    float awy = m[3] * acc[0] + m[4] * acc[1] + m[5] * acc[2];
+    float awz = m[6] * acc[0] + m[7] * acc[1] + m[8] * acc[2];
+    float Awx = m[0] * acc[3] + m[1] * acc[4] + m[2] * acc[5];
+    float Awy = m[3] * acc[3] + m[4] * acc[4] + m[5] * acc[5];
+    float Awz = m[6] * acc[3] + m[7] * acc[4] + m[8] * acc[5];
+    const float mv = p.max_vel;
+    e.wx = fminf(fmaxf(e.wx + awx * dt, -mv), mv);
+    e.wy = fminf(fmaxf(e.wy + awy * dt, -mv), mv);
+    e.wz = fminf(fmaxf(e.wz + awz * dt, -mv), mv);
+    e.vx = fminf(fmaxf(e.vx + Awx * dt, -mv), mv);
+    e.vy = fminf(fmaxf(e.vy + Awy * dt, -mv), mv);
+    e.vz = fminf(fmaxf(e.vz + Awz * dt, -mv), mv);
+    e.px += e.vx * dt; e.py += e.vy * dt; e.pz += e.vz * dt;
+    // exponential-map quaternion update with Bullet's pi/4-per-step limiter
+    {
+        float ang2 = e.wx * e.wx + e.wy * e.wy + e.wz * e.wz;
+        float ang = sqrtf(ang2);
+        if (ang * dt > 0.25f * FWD_PI) ang = 0.5f * FWD_HALF_PI / dt;
+        float k, cw;
+        float half = 0.5f * ang * dt;
+        if (ang < 0.001f) {
+            k = 0.5f * dt - (dt * dt * dt) * 0.020833333333f * ang * ang;
+            cw = cosf(half);
+        } else {
+            float sh;
+            sincosf(half, &sh, &cw);
+            k = sh / ang;
+        }
+        float ax = e.wx * k, ay = e.wy * k, az = e.wz * k;
+        float nx = cw * e.qx + e.qw * ax + (ay * e.qz - az * e.qy);
+        float ny = cw * e.qy + e.qw * ay + (az * e.qx - ax * e.qz);
+        float nzq = cw * e.qz + e.qw * az + (ax * e.qy - ay * e.qx);
+        float nw = cw * e.qw - (ax * e.qx + ay * e.qy + az * e.qz);
+        float inv = rsqrtf(nx * nx + ny * ny + nzq * nzq + nw * nw);
+        e.qx = nx * inv; e.qy = ny * inv; e.qz = nzq * inv; e.qw = nw * inv;
+    }
+    e.physics_steps += 1;
+}
+
+// wind seen by the force evaluation of physics step `ps` (cached by the state refresh of step ps-1)
+__device__ __forceinline__ void fw_wind(const FwDev& p, int ps, const float4& w0, const float4& w1, float& x, float& y,
+                                        float& z) {
+    x = y = z = 0.0f;
+    if (p.wind_mode == 0) return;
+    int stamp = ps - 1;
+    if (stamp < 0 || stamp < p.wind_start_substep) return;
+    if (p.wind_mode == 1) { x = w0.x; y = w0.y; z = w0.z; return; }
+    float s = sinf(p.gust_omega * ((float)stamp * p.dt) + w0.w);
+    x = w0.x + w1.x * s; y = w0.y + w1.y * s; z = w0.z + w1.z * s;
+}
+
+__device__ __forceinline__ void fw_map_setpoint(const FwDev& p, float roll, float pitch, float yaw, float thrust,
+                                                float cmd[6]) {
+    cmd[0] = p.sign_ail_l * roll;
+    cmd[1] = p.sign_ail_r * roll;
+    cmd[2] = p.sign_pitch * pitch;
+    cmd[3] = p.sign_yaw * yaw;
+    cmd[4] = 0.0f;
+    cmd[5] = thrust;
+}
+
+// pybullet getEulerFromQuaternion
+__device__ __forceinline__ void fw_euler(const EnvState& e, float& roll, float& pitch, float& yaw) {
+    float x = e.qx, y = e.qy, z = e.qz, w = e.qw;
+    float sarg = -2.0f * (x * z - w * y);
+    if (sarg <= -0.99999f) { roll = 0.0f; pitch = -FWD_HALF_PI; yaw = 2.0f * atan2f(x, -y); }
+    else if (sarg >= 0.99999f) { roll = 0.0f; pitch = FWD_HALF_PI; yaw = 2.0f * atan2f(-x, y); }
+    else {
+        roll = atan2f(2.0f * (y * z + w * x), w * w - x * x - y * y + z * z);
+        pitch = asinf(sarg);
+        yaw = atan2f(2.0f * (x * y + w * z), w * w + x * x - y * y - z * z);
+    }
+}
+
+// flattened observation of one env into `o` (row of obs_dim floats); target rows come from the planes
+__device__ __forceinline__ void fw_write_obs(const FwDev& p, const FwPlanes& pl, const EnvState& e, int i, int obs_tidx,
+                                             float a0, float a1, float a2, float a3, float* o) {
+    Mat3 R = fw_quat_mat(e.qx, e.qy, e.qz, e.qw);
+    const float* m = R.m;
+    float roll, pitch, yaw;
+    fw_euler(e, roll, pitch, yaw);
+    int k = 0;
+    o[k++] = m[0] * e.wx + m[3] * e.wy + m[6] * e.wz;
+    o[k++] = m[1] * e.wx + m[4] * e.wy + m[7] * e.wz;
+    o[k++] = m[2] * e.wx + m[5] * e.wy + m[8] * e.wz;
+    if (p.angle_repr == 0) { o[k++] = roll; o[k++] = pitch; o[k++] = yaw; }
+    else {
+        float sr, cr, sp, cp, sy, cy;
+        sincosf(0.5f * roll, &sr, &cr); sincosf(0.5f * pitch, &sp, &cp); sincosf(0.5f * yaw, &sy, &cy);
+        o[k++] = sr * cp * cy - cr * sp * sy;
+        o[k++] = cr * sp * cy + sr * cp * sy;
+        o[k++] = cr * cp * sy - sr * sp * cy;
+        o[k++] = cr * cp * cy + sr * sp * sy;
+    }
+    o[k++] = m[0] * e.vx + m[3] * e.vy + m[6] * e.vz;
+    o[k++] = m[1] * e.vx + m[4] * e.vy + m[7] * e.vz;
+    o[k++] = m[2] * e.vx + m[5] * e.vy + m[8] * e.vz;
+    o[k++] = e.px; o[k++] = e.py; o[k++] = e.pz;
+    o[k++] = a0; o[k++] = a1; o[k++] = a2; o[k++] = a3;
+#pragma unroll
+    for (int s = 0; s < FWD_NSURF; ++s) o[k++] = e.act[s];
+    o[k++] = e.thr;
+    for (int r = 0; r < p.context_len; ++r) {
+        int t = obs_tidx + r;
+        if (t < p.num_targets) {
+            float dx = pl.targets[(size_t)(t * 3 + 0) * p.n + i] - e.px;
+            float dy = pl.targets[(size_t)(t * 3 + 1) * p.n + i] - e.py;
+            float dz = pl.targets[(size_t)(t * 3 + 2) * p.n + i] - e.pz;
+            o[k++] = m[0] * dx + m[3] * dy + m[6] * dz;
+            o[k++] = m[1] * dx + m[4] * dy + m[7] * dz;
+            o[k++] = m[2] * dx + m[5] * dy + m[8] * dz;
+        } else { o[k++] = 0.0f; o[k++] = 0.0f; o[k++] = 0.0f; }
+    }
+}
+
+// begin_reset/end_reset for env i (global id gid): initial pose, wind/target sampling, warm-up
+__device__ __forceinline__ void fw_reset_env(const FwDev& p, const FwPlanes& pl, EnvState& e, int i, uint32_t gid,
+                                             uint32_t episode) {
+    e.episode = episode;
+    e.step_count = 0;
+    e.tidx = 0;
+    float4 w0 = make_float4(p.wind_base[0], p.wind_base[1], p.wind_base[2], p.gust_phase);
+    float4 w1 = make_float4(p.gust_amp[0], p.gust_amp[1], p.gust_amp[2], 0.0f);
+    if (p.wind_mode != 0) {
+        if (p.wind_randomize) {
+            uint4 r0 = fw_philox(p.seed_lo, p.seed_hi, gid, episode, 0u, FWD_STREAM_WIND);
+            uint4 r1 = fw_philox(p.seed_lo, p.seed_hi, gid, episode, 1u, FWD_STREAM_WIND);
+            w0.x = p.wind_base_lo[0] + fw_u01(r0.x) * (p.wind_base_hi[0] - p.wind_base_lo[0]);
+            w0.y = p.wind_base_lo[1] + fw_u01(r0.y) * (p.wind_base_hi[1] - p.wind_base_lo[1]);
+            w0.z = p.wind_base_lo[2] + fw_u01(r0.z) * (p.wind_base_hi[2] - p.wind_base_lo[2]);
+            if (p.wind_mode == 2) {
+                w1.x = p.gust_amp_lo[0] + fw_u01(r1.x) * (p.gust_amp_hi[0] - p.gust_amp_lo[0]);
+                w1.y = p.gust_amp_lo[1] + fw_u01(r1.y) * (p.gust_amp_hi[1] - p.gust_amp_lo[1]);
+                w1.z = p.gust_amp_lo[2] + fw_u01(r1.z) * (p.gust_amp_hi[2] - p.gust_amp_lo[2]);
+                if (p.wind_rand_phase) w0.w = 2.0f * FWD_PI * fw_u01(r0.w);
+            }
+        }
+        pl.w0[i] = w0; pl.w1[i] = w1;
+    }
+    if (p.warm_cached) {
+        e.px = p.warm[0]; e.py = p.warm[1]; e.pz = p.warm[2];
+        e.qx = p.warm[3]; e.qy = p.warm[4]; e.qz = p.warm[5]; e.qw = p.warm[6];
+        e.vx = p.warm[7]; e.vy = p.warm[8]; e.vz = p.warm[9];
+        e.wx = p.warm[10]; e.wy = p.warm[11]; e.wz = p.warm[12];
+#pragma unroll
+        for (int s = 0; s < FWD_NSURF; ++s) e.act[s] = p.warm[13 + s];
+        e.thr = p.warm[18];
+        e.physics_steps = p.warmup_substeps;
+    } else {
+        e.px = p.start_pos[0]; e.py = p.start_pos[1]; e.pz = p.start_pos[2];
+        e.qx = 0.f; e.qy = 0.f; e.qz = 0.f; e.qw = 1.f;
+        e.vx = p.start_vel[0]; e.vy = p.start_vel[1]; e.vz = p.start_vel[2];
+        e.wx = e.wy = e.wz = 0.f;
+#pragma unroll
+        for (int s = 0; s < FWD_NSURF; ++s) e.act[s] = 0.f;
+        e.thr = 0.f;
+        e.physics_steps = 0;
+        float cmd[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        bool contact = false;
+        for (int k = 0; k < p.warmup_substeps; ++k) {
+            float wx, wy, wz;
+            fw_wind(p, e.physics_steps, w0, w1, wx, wy, wz);
+            fw_substep(p, e, cmd, wx, wy, wz, 0.0f, contact);   // throttle is 0 during warm-up: noise term is 0
+        }
+    }
+    e.new_dist = 0.0f;
+    if (p.task != 0) {
+        float d0 = 0.f;
+        for (int t = 0; t < p.num_targets; ++t) {
+            uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid, episode, (uint32_t)t, FWD_STREAM_TARGETS);
+            float st, ct, sp, cp;
+            sincospif(2.0f * fw_u01(r.x), &st, &ct);
+            sincospif(2.0f * fw_u01(r.y), &sp, &cp);
+            float dist = 1.0f + fw_u01(r.z) * (p.spawn_size * 0.9f - 1.0f);
+            float x = dist * sp * ct, y = dist * sp * st, z = fabsf(dist * cp);
+            z = z > p.min_height ? z : p.min_height;
+            pl.targets[(size_t)(t * 3 + 0) * p.n + i] = x;
+            pl.targets[(size_t)(t * 3 + 1) * p.n + i] = y;
+            pl.targets[(size_t)(t * 3 + 2) * p.n + i] = z;
+            if (t == 0) {
+                float dx = x - e.px, dy = y - e.py, dz = z - e.pz;
+                d0 = sqrtf(dx * dx + dy * dy + dz * dz);
+            }
+        }
+        e.new_dist = d0;
+    }
+}
+
+__device__ __forceinline__ void fw_load(const FwPlanes& pl, int i, EnvState& e) {
+    float4 a = pl.s0[i], b = pl.s1[i], c = pl.s2[i], d = pl.s3[i], f = pl.s4[i];
+    int4 g = pl.s5[i];
+    e.px = a.x; e.py = a.y; e.pz = a.z; e.thr = a.w;
+    e.qx = b.x; e.qy = b.y; e.qz = b.z; e.qw = b.w;
+    e.vx = c.x; e.vy = c.y; e.vz = c.z; e.act[0] = c.w;
+    e.wx = d.x; e.wy = d.y; e.wz = d.z; e.act[1] = d.w;
+    e.act[2] = f.x; e.act[3] = f.y; e.act[4] = f.z; e.new_dist = f.w;
+    e.step_count = g.x; e.physics_steps = g.y; e.episode = (uint32_t)g.z; e.tidx = g.w;
+}
+
+__device__ __forceinline__ void fw_store(const FwPlanes& pl, int i, const EnvState& e) {
+    pl.s0[i] = make_float4(e.px, e.py, e.pz, e.thr);
+    pl.s1[i] = make_float4(e.qx, e.qy, e.qz, e.qw);
+    pl.s2[i] = make_float4(e.vx, e.vy, e.vz, e.act[0]);
+    pl.s3[i] = make_float4(e.wx, e.wy, e.wz, e.act[1]);
+    pl.s4[i] = make_float4(e.act[2], e.act[3], e.act[4], e.new_dist);
+    pl.s5[i] = make_int4(e.step_count, e.physics_steps, (int)e.episode, e.tidx);
+}

@@ -1,0 +1,239 @@
+// fw_kernels.cu -- sm_100a kernels of the batched fixed-wing env step.
+//
+// K1 fw_step_kernel : one thread per env; one launch == one agent step (30 Hz) == inner_per_step x
+//                     substeps_per_inner physics substeps at 240 Hz, fused with the waypoint observation,
+//                     reward, termination/truncation, SubprocVecEnv-style auto-reset and the flattened
+//                     observation write.  Replaces FixedwingBaseEnv.step + Aviary.step
+//                     (/root/reference/envs/fixedwing_envs/fixedwing_base_env.py:314-348) for all envs at once.
+// K2 fw_reset_kernel: masked reset (fixedwing_base_env.py:193-257).
+//
+// Memory plan: state lives in six float4/int4 SoA planes (fw_device.cuh FwPlanes): every access is a
+// 16-byte fully coalesced LDG.128/STG.128.  The [N,obs_dim] row-major observation the VecEnv contract
+// demands is staged per warp in shared memory and written with ONE bulk async copy
+// (cp.async.bulk.global.shared::cta -> SASS UBLKCP) of 32*obs_dim*4 contiguous bytes, instead of 32 strided
+// row stores.  Aircraft/task constants arrive as a __grid_constant__ kernel parameter, i.e. in the constant
+// bank: every FFMA reads them as a c[][] operand with no load instruction (all threads use the same address,
+// which is the case the constant cache is built for; shared-memory staging would add an LDS per use).
+#include "fw_device.cuh"
+#include "fw_kernels.h"
+
+#define FW_BLOCK 64
+
+__device__ __forceinline__ uint32_t fw_smem_addr(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// Flush one warp's staged observation rows (32 x D floats, dense) to global memory.
+__device__ __forceinline__ void fw_flush_obs(float* __restrict__ dst_base, const float* stage_warp, int D,
+                                             int first_env, int n, int lane, bool bulk_ok) {
+    const int rows = min(32, n - first_env);
+    float* dst = dst_base + (size_t)first_env * D;
+    if (bulk_ok && rows == 32) {
+        // generic-proxy writes -> async proxy, then one elected lane issues the TMA bulk store
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            uint32_t bytes = 32u * (uint32_t)D * 4u;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(dst), "r"(fw_smem_addr(stage_warp)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncwarp();
+    } else {
+        __syncwarp();
+        for (int k = lane; k < rows * D; k += 32) dst[k] = stage_warp[k];
+        __syncwarp();
+    }
+}
+
+template <int TASK, bool RANDOM_ACT>
+__global__ void __launch_bounds__(FW_BLOCK)
+fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4* __restrict__ act,
+               float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ flg,
+               float* __restrict__ term_obs, uint32_t step_index, int bulk_ok) {
+    extern __shared__ __align__(128) float stage[];
+    const int i = blockIdx.x * FW_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = p.obs_dim;
+    float* stage_warp = stage + (size_t)warp * 32 * D;
+    float* row = stage_warp + (size_t)lane * D;
+
+    if (i < p.n) {
+        const uint32_t gid = p.env_id0 + (uint32_t)i;
+        EnvState e;
+        fw_load(pl, i, e);
+        float a0, a1, a2, a3;
+        if (RANDOM_ACT) {
+            uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid, step_index, 0u, FWD_STREAM_ACTION);
+            a0 = 2.0f * fw_u01(r.x) - 1.0f; a1 = 2.0f * fw_u01(r.y) - 1.0f;
+            a2 = 2.0f * fw_u01(r.z) - 1.0f; a3 = 2.0f * fw_u01(r.w) - 1.0f;
+        } else {
+            float4 a = act[i];
+            a0 = a.x; a1 = a.y; a2 = a.z; a3 = a.w;
+        }
+        float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+        if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
+
+        // FixedwingBaseEnv.step: reward reset once, thrust remapped to [0,1], setpoint latched
+        float reward = -0.1f;
+        bool term = false, trunc = false, col = false, oob = false, complete = false;
+        float cmd[6];
+        fw_map_setpoint(p, a0, a1, a2, a3 * 0.5f + 0.5f, cmd);
+        float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+        bool have_noise = false;
+        int obs_tidx = e.tidx;
+
+        for (int it = 0; it < p.inner_per_step; ++it) {
+            if (term || trunc) break;
+            bool contact = false;                       // Aviary.step: contact_array &= False
+            for (int s = 0; s < p.substeps_per_inner; ++s) {
+                const int ps = e.physics_steps;
+                float nz = 0.0f;
+                if (p.noise_ratio > 0.0f) {
+                    if (!have_noise || (ps & 3) == 0) {
+                        float nn[4];
+                        fw_normals4(p, gid, e.episode, (uint32_t)ps >> 2, nn);
+                        n0 = nn[0]; n1 = nn[1]; n2 = nn[2]; n3 = nn[3];
+                        have_noise = true;
+                    }
+                    const int q = ps & 3;
+                    nz = q == 0 ? n0 : (q == 1 ? n1 : (q == 2 ? n2 : n3));
+                }
+                float wx, wy, wz;
+                fw_wind(p, ps, w0, w1, wx, wy, wz);
+                fw_substep(p, e, cmd, wx, wy, wz, nz, contact);
+            }
+            // compute_state: WaypointHandler.distance_to_targets (old <- new, new <- |delta_0|)
+            float old_dist = e.new_dist;
+            obs_tidx = e.tidx;
+            if (TASK == 1 && e.tidx < p.num_targets) {
+                float dx = pl.targets[(size_t)(e.tidx * 3 + 0) * p.n + i] - e.px;
+                float dy = pl.targets[(size_t)(e.tidx * 3 + 1) * p.n + i] - e.py;
+                float dz = pl.targets[(size_t)(e.tidx * 3 + 2) * p.n + i] - e.pz;
+                e.new_dist = sqrtf(dx * dx + dy * dy + dz * dz);
+            }
+            // compute_base_term_trunc_reward
+            if (e.step_count > p.max_steps) trunc = true;
+            if (contact) { reward = -100.0f; col = true; term = true; }
+            if (sqrtf(e.px * e.px + e.py * e.py + e.pz * e.pz) > p.dome) { reward = -100.0f; oob = true; term = true; }
+            if (TASK == 1 && !(p.early_return_on_crash && (col || oob))) {
+                if (!p.sparse_reward) {
+                    reward += fmaxf(3.0f * (old_dist - e.new_dist), 0.0f);
+                    reward += 1.0f / e.new_dist;
+                }
+                if (e.new_dist < p.goal_reach) {
+                    reward = 100.0f;
+                    e.tidx += 1;                                  // advance_targets
+                    const bool all = e.tidx >= p.num_targets;
+                    if (p.complete_truncates && all) trunc = true;
+                    complete = all;
+                }
+            }
+        }
+        e.step_count += 1;
+
+        const bool done = term || trunc;
+        if (TASK != 0) fw_write_obs(p, pl, e, i, obs_tidx, a0, a1, a2, a3, row);
+        float ep_ret = pl.ep_ret[i] + reward;
+        if (done) {
+            if (TASK != 0 && term_obs != nullptr)
+                for (int k = 0; k < D; ++k) term_obs[(size_t)i * D + k] = row[k];
+            atomicAdd(&pl.stats[0], 1.0);
+            atomicAdd(&pl.stats[1], (double)ep_ret);
+            atomicAdd(&pl.stats[2], (double)e.step_count);
+            atomicAdd(&pl.stats[3], (double)e.tidx);
+            if (col) atomicAdd(&pl.stats[4], 1.0);
+            if (oob) atomicAdd(&pl.stats[5], 1.0);
+            if (complete) atomicAdd(&pl.stats[6], 1.0);
+            // SubprocVecEnv worker: obs = env.reset()
+            fw_reset_env(p, pl, e, i, gid, e.episode + 1u);
+            if (TASK != 0) fw_write_obs(p, pl, e, i, 0, 0.f, 0.f, 0.f, 0.f, row);
+            ep_ret = 0.0f;
+        }
+        pl.ep_ret[i] = ep_ret;
+        fw_store(pl, i, e);
+        if (rew != nullptr) rew[i] = reward;
+        if (flg != nullptr)
+            flg[i] = (uint8_t)((term ? 1 : 0) | (trunc ? 2 : 0) | (col ? 4 : 0) | (oob ? 8 : 0) | (complete ? 16 : 0));
+    }
+    if (TASK != 0 && obs != nullptr) {
+        const int first_env = blockIdx.x * FW_BLOCK + warp * 32;
+        if (first_env < p.n) fw_flush_obs(obs, stage_warp, D, first_env, p.n, lane, bulk_ok != 0);
+    }
+}
+
+__global__ void __launch_bounds__(FW_BLOCK)
+fw_reset_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const uint8_t* __restrict__ mask,
+                float* __restrict__ obs, int bulk_ok) {
+    extern __shared__ __align__(128) float stage[];
+    const int i = blockIdx.x * FW_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = p.obs_dim;
+    float* stage_warp = stage + (size_t)warp * 32 * D;
+    float* row = stage_warp + (size_t)lane * D;
+    if (i < p.n) {
+        EnvState e;
+        fw_load(pl, i, e);
+        const bool sel = mask == nullptr || mask[i] != 0;
+        if (sel) {
+            fw_reset_env(p, pl, e, i, p.env_id0 + (uint32_t)i, e.episode + 1u);
+            pl.ep_ret[i] = 0.0f;
+            fw_store(pl, i, e);
+        }
+        // unselected envs re-emit their current observation (last action unknown -> zeros)
+        if (p.task != 0) fw_write_obs(p, pl, e, i, e.tidx, 0.f, 0.f, 0.f, 0.f, row);
+    }
+    if (p.task != 0 && obs != nullptr) {
+        const int first_env = blockIdx.x * FW_BLOCK + warp * 32;
+        if (first_env < p.n) fw_flush_obs(obs, stage_warp, D, first_env, p.n, lane, bulk_ok != 0);
+    }
+}
+
+// one thread: run the deterministic warm-up once so resets can copy its result
+__global__ void fw_warm_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, float* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    EnvState e;
+    FwDev q = p;   // local copy with task 0: no target sampling, no plane writes
+    q.task = 0; q.wind_mode = 0; q.warm_cached = 0;
+    fw_reset_env(q, pl, e, 0, 0u, 0u);
+    out[0] = e.px; out[1] = e.py; out[2] = e.pz;
+    out[3] = e.qx; out[4] = e.qy; out[5] = e.qz; out[6] = e.qw;
+    out[7] = e.vx; out[8] = e.vy; out[9] = e.vz;
+    out[10] = e.wx; out[11] = e.wy; out[12] = e.wz;
+    for (int s = 0; s < FWD_NSURF; ++s) out[13 + s] = e.act[s];
+    out[18] = e.thr; out[19] = 0.0f;
+}
+
+// ------------------------------------------------------------------ launchers
+static inline size_t stage_bytes(const FwDev& p) { return (size_t)(FW_BLOCK / 32) * 32 * (size_t)(p.obs_dim > 0 ? p.obs_dim : 1) * 4; }
+static inline int grid_for(int n) { return (n + FW_BLOCK - 1) / FW_BLOCK; }
+
+cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act, float* obs, float* rew, uint8_t* flg,
+                            float* term_obs, bool random_act, uint32_t step_index, cudaStream_t st) {
+    const int bulk_ok = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) && ((p.obs_dim * 128) % 16 == 0);
+    const size_t sm = stage_bytes(p);
+    const dim3 g(grid_for(p.n)), b(FW_BLOCK);
+    const float4* a4 = reinterpret_cast<const float4*>(act);
+    if (p.task == 0) {
+        if (random_act) fw_step_kernel<0, true><<<g, b, sm, st>>>(p, pl, a4, obs, rew, flg, term_obs, step_index, bulk_ok);
+        else fw_step_kernel<0, false><<<g, b, sm, st>>>(p, pl, a4, obs, rew, flg, term_obs, step_index, bulk_ok);
+    } else if (p.task == 1) {
+        if (random_act) fw_step_kernel<1, true><<<g, b, sm, st>>>(p, pl, a4, obs, rew, flg, term_obs, step_index, bulk_ok);
+        else fw_step_kernel<1, false><<<g, b, sm, st>>>(p, pl, a4, obs, rew, flg, term_obs, step_index, bulk_ok);
+    } else {
+        return cudaErrorNotSupported;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t fwk_launch_reset(const FwDev& p, const FwPlanes& pl, const uint8_t* mask, float* obs, cudaStream_t st) {
+    const int bulk_ok = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0);
+    fw_reset_kernel<<<grid_for(p.n), FW_BLOCK, stage_bytes(p), st>>>(p, pl, mask, obs, bulk_ok);
+    return cudaGetLastError();
+}
+
+cudaError_t fwk_launch_warm(const FwDev& p, const FwPlanes& pl, float* out, cudaStream_t st) {
+    fw_warm_kernel<<<1, 32, 0, st>>>(p, pl, out);
+    return cudaGetLastError();
+}

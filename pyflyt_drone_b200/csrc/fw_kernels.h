@@ -1,0 +1,12 @@
+// fw_kernels.h -- internal launcher interface between fw_api.cu (C ABI, host logic) and fw_kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct FwDev;
+struct FwPlanes;
+
+cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act, float* obs, float* rew, uint8_t* flg,
+                            float* term_obs, bool random_act, uint32_t step_index, cudaStream_t st);
+cudaError_t fwk_launch_reset(const FwDev& p, const FwPlanes& pl, const uint8_t* mask, float* obs, cudaStream_t st);
+cudaError_t fwk_launch_warm(const FwDev& p, const FwPlanes& pl, float* out, cudaStream_t st);

@@ -1,0 +1,258 @@
+"""FixedwingVecEnv -- the batched seam (SURVEY section 8 b, B1/B1').
+
+Drop-in for the one line of the reference that builds its training env
+(train/train_Fixedwing_Waypoints_v3.py:251, train/train_Fixedwing_Waypoints_ObjLock.py:306)::
+
+    env = SubprocVecEnv([make_env(i, seed) for i in range(num_envs)])        # reference
+    env = FixedwingVecEnv(num_envs, preset="waypoints_v3", seed=seed)        # this package
+
+It honours the stable-baselines3 ``VecEnv`` contract (attrs ``num_envs``/``observation_space``/``action_space``;
+``reset``/``step_async``/``step_wait``/``step``/``close``/``seed``/``get_attr``/``set_attr``/``env_method``/
+``env_is_wrapped``; auto-reset inside ``step`` with ``infos[i]["terminal_observation"]`` and
+``infos[i]["TimeLimit.truncated"]``) with host NumPy arrays, and adds a device-tensor lane (``step_tensor``)
+that never leaves HBM.  All arithmetic happens in libfwsim.so (sm_100a CUDA); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Sequence
+
+import numpy as np
+
+from . import _lib
+from .compat import spaces
+from .config import (EnvConfig, FLAG_COLLISION, FLAG_COMPLETE, FLAG_OOB, FLAG_STRIKE, FLAG_TERM, FLAG_TRUNC,
+                     make_config)
+
+_STATE_FIELDS = {
+    "pos": (np.float32, 3), "quat": (np.float32, 4), "vel": (np.float32, 3), "omega": (np.float32, 3),
+    "act": (np.float32, 6), "targets": (np.float32, None), "target_idx": (np.int32, 0),
+    "step_count": (np.int32, 0), "physics_steps": (np.int32, 0), "episode": (np.uint32, 0),
+    "new_dist": (np.float32, 0), "wind": (np.float32, 7),
+}
+
+
+class FixedwingVecEnv:
+    """``num_envs`` fixed-wing environments stepped by one CUDA kernel launch per agent step."""
+
+    metadata = {"render_modes": []}
+
+    def __init__(self, num_envs: int, preset: str = "waypoints_v3", config: EnvConfig | None = None,
+                 device: int = 0, seed: int = 0, env_id0: int = 0, info_mode: str = "auto", **overrides):
+        self.cfg = config if config is not None else make_config(preset, **overrides)
+        if config is not None and overrides:
+            self.cfg = self.cfg.replace(**overrides)
+        self.num_envs = int(num_envs)
+        self.device_index = int(device)
+        self._seed = int(seed)
+        self.env_id0 = int(env_id0)
+        self.lib = _lib.load()
+        self._c_cfg = self.cfg.to_c()
+        self._h = C.c_void_p()
+        _lib.check(self.lib.fw_create(C.byref(self._c_cfg), self.num_envs, self.device_index, self._seed,
+                                      self.env_id0, C.byref(self._h)))
+        self.obs_dim = int(self.lib.fw_obs_dim(self._h))
+        D = max(self.obs_dim, 1)
+        self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(self.obs_dim,), dtype=np.float32)
+        self.action_space = spaces.Box(low=-1.0, high=1.0, shape=(4,), dtype=np.float32)
+        if info_mode == "auto":
+            info_mode = "full" if self.num_envs <= 4096 else "lazy"
+        if info_mode not in ("full", "lazy"):
+            raise ValueError("info_mode must be 'auto', 'full' or 'lazy'")
+        self.info_mode = info_mode
+        # host arrays handed back to the caller (SB3 copies them into its rollout buffer)
+        self._h_obs = np.zeros((self.num_envs, D), dtype=np.float32)
+        self._h_rew = np.zeros(self.num_envs, dtype=np.float32)
+        self._h_flags = np.zeros(self.num_envs, dtype=np.uint8)
+        self._h_term = np.zeros((self.num_envs, D), dtype=np.float32)
+        self._pending: np.ndarray | None = None
+        self._t = None  # lazily created torch buffers for the tensor lane
+        self._closed = False
+
+    # ------------------------------------------------------------------ SB3 VecEnv (host NumPy lane)
+    def reset(self) -> np.ndarray:
+        _lib.check(self.lib.fw_reset_host(self._h, self._h_obs.ctypes.data_as(C.c_void_p)))
+        return self._h_obs[:, : self.obs_dim].copy()
+
+    def step_async(self, actions: np.ndarray) -> None:
+        if self._pending is not None:
+            raise RuntimeError("step_async called twice without step_wait")
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        if a.shape != (self.num_envs, 4):
+            raise ValueError(f"actions must have shape ({self.num_envs}, 4), got {a.shape}")
+        self._pending = a
+
+    def step_arrays(self, actions: np.ndarray, want_terminal_obs: bool = True):
+        """Host-buffer step without the per-env info dicts: (obs, rewards, flags, terminal_obs)."""
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        if a.shape != (self.num_envs, 4):
+            raise ValueError(f"actions must have shape ({self.num_envs}, 4), got {a.shape}")
+        p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
+        _lib.check(self.lib.fw_step_host(self._h, p(a), p(self._h_obs), p(self._h_rew), p(self._h_flags),
+                                         p(self._h_term) if want_terminal_obs else None))
+        return self._h_obs[:, : self.obs_dim], self._h_rew, self._h_flags, self._h_term[:, : self.obs_dim]
+
+    def step_wait(self):
+        if self._pending is None:
+            raise RuntimeError("step_wait called without step_async")
+        a, self._pending = self._pending, None
+        obs, rew, flags, term = self.step_arrays(a)
+        dones = (flags & (FLAG_TERM | FLAG_TRUNC)) != 0
+        infos = self._make_infos(flags, dones, term)
+        return obs.copy(), rew.copy(), dones, infos
+
+    def step(self, actions: np.ndarray):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def _info_of(self, f: int, tidx: int | None) -> dict:
+        d = {"out_of_bounds": bool(f & FLAG_OOB), "collision": bool(f & FLAG_COLLISION),
+             "env_complete": bool(f & FLAG_COMPLETE)}
+        if tidx is not None:
+            d["num_targets_reached"] = tidx
+        if self.cfg.task == 2:
+            d["duck_strike"] = bool(f & FLAG_STRIKE)
+        return d
+
+    def _make_infos(self, flags: np.ndarray, dones: np.ndarray, term: np.ndarray) -> list[dict]:
+        idx = np.nonzero(dones)[0]
+        if self.info_mode == "lazy":
+            blank = self._info_of(0, None)
+            infos: list[dict] = [blank] * self.num_envs
+        else:
+            infos = [self._info_of(int(f), None) for f in flags]
+        for i in idx:
+            f = int(flags[i])
+            d = self._info_of(f, None)
+            d["terminal_observation"] = term[i].copy()
+            d["TimeLimit.truncated"] = bool(f & FLAG_TRUNC) and not bool(f & FLAG_TERM)
+            infos[i] = d
+        return infos
+
+    def close(self) -> None:
+        if not self._closed and self._h:
+            self.lib.fw_destroy(self._h)
+            self._h = C.c_void_p()
+            self._closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def seed(self, seed: int | None = None) -> list[int | None]:
+        """SB3 API parity.  The Philox key is fixed at construction; re-seeding rebuilds the batch."""
+        if seed is not None and int(seed) != self._seed:
+            self._seed = int(seed)
+            self.lib.fw_destroy(self._h)
+            self._h = C.c_void_p()
+            _lib.check(self.lib.fw_create(C.byref(self._c_cfg), self.num_envs, self.device_index, self._seed,
+                                          self.env_id0, C.byref(self._h)))
+        return [self._seed + self.env_id0 + i for i in range(self.num_envs)]
+
+    def _indices(self, indices) -> Sequence[int]:
+        if indices is None:
+            return range(self.num_envs)
+        if isinstance(indices, int):
+            return [indices]
+        return indices
+
+    def get_attr(self, attr_name: str, indices=None) -> list[Any]:
+        val = getattr(self, attr_name) if hasattr(self, attr_name) else getattr(self.cfg, attr_name)
+        return [val for _ in self._indices(indices)]
+
+    def set_attr(self, attr_name: str, value: Any, indices=None) -> None:
+        raise NotImplementedError("per-env attributes are compiled into the batch config; rebuild the VecEnv")
+
+    def env_method(self, method_name: str, *args, indices=None, **kwargs) -> list[Any]:
+        raise NotImplementedError(f"env_method({method_name!r}) has no batched counterpart")
+
+    def env_is_wrapped(self, wrapper_class, indices=None) -> list[bool]:
+        return [False for _ in self._indices(indices)]
+
+    # ------------------------------------------------------------------ device-tensor lane (B1')
+    def _tensors(self):
+        if self._t is None:
+            import torch
+            dev = torch.device("cuda", self.device_index)
+            D = max(self.obs_dim, 1)
+            self._t = dict(
+                obs=torch.zeros((self.num_envs, D), dtype=torch.float32, device=dev),
+                rew=torch.zeros(self.num_envs, dtype=torch.float32, device=dev),
+                flags=torch.zeros(self.num_envs, dtype=torch.uint8, device=dev),
+                term=torch.zeros((self.num_envs, D), dtype=torch.float32, device=dev),
+            )
+        return self._t
+
+    @staticmethod
+    def _stream() -> int:
+        import torch
+        return int(torch.cuda.current_stream().cuda_stream)
+
+    def reset_tensor(self, mask=None):
+        t = self._tensors()
+        mp = None if mask is None else C.c_void_p(mask.data_ptr())
+        _lib.check(self.lib.fw_reset(self._h, mp, C.c_void_p(t["obs"].data_ptr()), C.c_void_p(self._stream())))
+        return t["obs"][:, : self.obs_dim]
+
+    def step_tensor(self, actions, want_terminal_obs: bool = False):
+        """actions: CUDA float32 [N,4] contiguous.  Returns views of persistent CUDA tensors
+        (obs, reward, flags[, terminal_obs]); valid until the next call.  No host sync."""
+        t = self._tensors()
+        if actions.dtype is not t["obs"].dtype or not actions.is_contiguous() or tuple(actions.shape) != (self.num_envs, 4):
+            raise ValueError("actions must be a contiguous CUDA float32 tensor of shape (num_envs, 4)")
+        _lib.check(self.lib.fw_step(
+            self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(t["obs"].data_ptr()) if self.obs_dim else None,
+            C.c_void_p(t["rew"].data_ptr()), C.c_void_p(t["flags"].data_ptr()),
+            C.c_void_p(t["term"].data_ptr()) if (want_terminal_obs and self.obs_dim) else None,
+            C.c_void_p(self._stream())))
+        if want_terminal_obs:
+            return t["obs"][:, : self.obs_dim], t["rew"], t["flags"], t["term"][:, : self.obs_dim]
+        return t["obs"][:, : self.obs_dim], t["rew"], t["flags"]
+
+    def step_random(self, step_index: int, n_steps: int = 1, with_outputs: bool = False):
+        """Random-action workload (BASELINE config 2): actions drawn in-kernel, n_steps launches."""
+        t = self._tensors() if with_outputs else None
+        _lib.check(self.lib.fw_step_random(
+            self._h, int(step_index) & 0xFFFFFFFF, int(n_steps),
+            C.c_void_p(t["rew"].data_ptr()) if t else None, C.c_void_p(t["flags"].data_ptr()) if t else None,
+            C.c_void_p(self._stream())))
+        return (t["rew"], t["flags"]) if t else None
+
+    # ------------------------------------------------------------------ parity injection / inspection
+    def get_state(self) -> dict[str, np.ndarray]:
+        n, T = self.num_envs, max(self.cfg.num_targets, 1)
+        out = {}
+        s = _lib.FwStateHostC()
+        for k, (dt, w) in _STATE_FIELDS.items():
+            shape = (n, T, 3) if k == "targets" else ((n,) if w == 0 else (n, w))
+            out[k] = np.zeros(shape, dtype=dt)
+            setattr(s, k, out[k].ctypes.data_as(C.c_void_p).value)
+        _lib.check(self.lib.fw_get_state(self._h, C.byref(s)))
+        return out
+
+    def set_state(self, state: dict[str, np.ndarray]) -> None:
+        n, T = self.num_envs, max(self.cfg.num_targets, 1)
+        s = _lib.FwStateHostC()
+        keep = []
+        for k, v in state.items():
+            if k not in _STATE_FIELDS:
+                raise KeyError(f"unknown state field {k!r}")
+            dt, w = _STATE_FIELDS[k]
+            shape = (n, T, 3) if k == "targets" else ((n,) if w == 0 else (n, w))
+            a = np.ascontiguousarray(np.asarray(v).astype(dt)).reshape(shape)
+            keep.append(a)
+            setattr(s, k, a.ctypes.data_as(C.c_void_p).value)
+        _lib.check(self.lib.fw_set_state(self._h, C.byref(s)))
+
+    def episode_stats(self) -> dict[str, float]:
+        out = (C.c_double * 8)()
+        _lib.check(self.lib.fw_episode_stats(self._h, out))
+        names = ["episodes", "return_sum", "length_sum", "targets_reached_sum", "collisions", "out_of_bounds",
+                 "completed", "strikes"]
+        return dict(zip(names, list(out)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.fw_launch_count(self._h))
