@@ -161,6 +161,10 @@ int fw_episode_stats(fw_handle h, double out[8]);
 /* number of kernel launches issued through this handle so far (bench.py's gpu_launches) */
 int64_t fw_launch_count(fw_handle h);
 
+/* FP32 FMA-chain peak (TFLOP/s, best of 5) of `device`, with its SM count and nominal clock: the roofline
+ * denominator for the FP32-bound env-step kernel (MEASURED_PEAKS.json has only HBM and bf16 tensor peaks). */
+int fw_measure_fp32_peak(int32_t device, double* tflops, int32_t* sm_count, int32_t* sm_clock_khz);
+
 #ifdef __cplusplus
 }
 #endif

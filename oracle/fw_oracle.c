@@ -66,8 +66,8 @@ void fwo_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* 24-bit uniform in (0,1): representable exactly in fp32 and fp64 */
-double fwo_u01(uint32_t x) { return ((double)(x >> 8) + 0.5) * (1.0 / 16777216.0); }
+/* 23-bit uniform in (0,1): (k + 0.5) / 2^23 needs 24 significant bits, exact in fp32 and fp64 */
+double fwo_u01(uint32_t x) { return ((double)(x >> 9) + 0.5) * (1.0 / 8388608.0); }
 
 void fwo_normals4(uint64_t seed, uint32_t env, uint32_t episode, uint32_t idx, double out[4]) {
     uint32_t r[4];
@@ -686,6 +686,9 @@ static void term_trunc_reward(const fwo_config* c, fwo_env* e) {
     if (c->early_return_on_crash && (e->info_collision || e->info_oob)) return;
 
     if (c->task == FWO_TASK_WAYPOINTS) {
+        /* upstream always truncates on the last waypoint, so an empty target list is never scored there;
+         * with complete_truncates == 0 (non-reference option) the waypoint terms simply stop */
+        if (e->n_remaining == 0) return;
         if (!c->sparse_reward) {
             double prog = (isinf(e->old_dist) || isinf(e->new_dist)) ? 0.0 : e->old_dist - e->new_dist;
             e->reward += fmax(3.0 * prog, 0.0);

@@ -43,6 +43,7 @@ SYMBOLS = [
     ("fw_get_state", C.c_int, [_P, C.POINTER(FwStateHostC)]),
     ("fw_episode_stats", C.c_int, [_P, C.POINTER(C.c_double)]),
     ("fw_launch_count", C.c_int64, [_P]),
+    ("fw_measure_fp32_peak", C.c_int, [C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 ]
 
 

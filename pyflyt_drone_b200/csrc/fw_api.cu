@@ -43,6 +43,7 @@ struct FwSim {
     float *d_act, *d_obs, *d_rew, *d_term;
     uint8_t* d_flg;
     int64_t launches;
+    bool fresh;   // true until the state created by fw_create has been stepped or overwritten
 };
 
 extern "C" int fw_abi_version(void) { return FW_ABI_VERSION; }
@@ -219,9 +220,10 @@ extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, ui
         cudaFree(d_warm);
         h->dev.warm_cached = 1;
     }
-    CU(fwk_launch_reset(h->dev, h->pl, nullptr, nullptr, h->io_stream));
+    CU(fwk_launch_reset(h->dev, h->pl, nullptr, nullptr, false, h->io_stream));
     h->launches++;
     CU(cudaStreamSynchronize(h->io_stream));
+    h->fresh = true;
     *out = h;
     return FW_OK;
 }
@@ -253,8 +255,11 @@ extern "C" int64_t fw_launch_count(fw_handle h) { return h ? h->launches : 0; }
 extern "C" int fw_reset(fw_handle h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
     if (!h) return fail(FW_EINVAL, "null handle");
     CU(cudaSetDevice(h->device));
-    CU(fwk_launch_reset(h->dev, h->pl, mask_dev, obs_dev, (cudaStream_t)stream));
+    // the first whole-batch reset after fw_create only emits the observation of the episode-0 state
+    const bool emit_only = h->fresh && mask_dev == nullptr;
+    CU(fwk_launch_reset(h->dev, h->pl, mask_dev, obs_dev, emit_only, (cudaStream_t)stream));
     h->launches++;
+    h->fresh = false;
     return FW_OK;
 }
 
@@ -266,6 +271,7 @@ extern "C" int fw_step(fw_handle h, const float* act_dev, float* obs_dev, float*
     CU(cudaSetDevice(h->device));
     CU(fwk_launch_step(h->dev, h->pl, act_dev, obs_dev, rew_dev, flags_dev, term_obs_dev, false, 0u, (cudaStream_t)stream));
     h->launches++;
+    h->fresh = false;
     return FW_OK;
 }
 
@@ -274,6 +280,7 @@ extern "C" int fw_step_random(fw_handle h, uint32_t step_index, int32_t n_steps,
     if (!h) return fail(FW_EINVAL, "null handle");
     if (n_steps < 0) return fail(FW_EINVAL, "n_steps < 0");
     CU(cudaSetDevice(h->device));
+    h->fresh = false;
     for (int s = 0; s < n_steps; ++s) {
         CU(fwk_launch_step(h->dev, h->pl, nullptr, nullptr, rew_dev, flags_dev, nullptr, true, step_index + (uint32_t)s,
                            (cudaStream_t)stream));
@@ -313,6 +320,7 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
     CU(fwk_launch_step(h->dev, h->pl, h->d_act, D ? h->d_obs : nullptr, h->d_rew, h->d_flg,
                        (term_obs_host && D) ? h->d_term : nullptr, false, 0u, st));
     h->launches++;
+    h->fresh = false;
     if (obs_host && D) CU(cudaMemcpyAsync(h->h_obs, h->d_obs, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (rew_host) CU(cudaMemcpyAsync(h->h_rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (flags_host) CU(cudaMemcpyAsync(h->h_flg, h->d_flg, N, cudaMemcpyDeviceToHost, st));
@@ -332,8 +340,9 @@ extern "C" int fw_reset_host(fw_handle h, float* obs_host) {
     if (rc != FW_OK) return rc;
     const size_t N = (size_t)h->n, D = (size_t)h->obs_dim;
     cudaStream_t st = h->io_stream;
-    CU(fwk_launch_reset(h->dev, h->pl, nullptr, D ? h->d_obs : nullptr, st));
+    CU(fwk_launch_reset(h->dev, h->pl, nullptr, D ? h->d_obs : nullptr, h->fresh, st));
     h->launches++;
+    h->fresh = false;
     if (obs_host && D) CU(cudaMemcpyAsync(h->h_obs, h->d_obs, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (obs_host && D) memcpy(obs_host, h->h_obs, N * D * sizeof(float));
@@ -441,6 +450,7 @@ extern "C" int fw_set_state(fw_handle h, const FwStateHost* s) {
             for (int t = 0; t < T; ++t)
                 for (int k = 0; k < 3; ++k) hp.targets[(size_t)(t * 3 + k) * N + i] = s->targets[(i * T + t) * 3 + k];
     }
+    h->fresh = false;
     return push(h, hp);
 }
 
@@ -450,5 +460,40 @@ extern "C" int fw_episode_stats(fw_handle h, double out[8]) {
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(out, h->pl.stats, 8 * sizeof(double), cudaMemcpyDeviceToHost));
     CU(cudaMemset(h->pl.stats, 0, 8 * sizeof(double)));
+    return FW_OK;
+}
+
+// FP32 FMA-chain peak of the device, for the roofline denominator of the (FP32-bound) env-step kernel.
+extern "C" int fw_measure_fp32_peak(int32_t device, double* tflops, int32_t* sm_count, int32_t* sm_clock_khz) {
+    if (!tflops) return fail(FW_EINVAL, "null argument");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0) return fail(FW_ECUDA, "no CUDA device available (%s)", cudaGetErrorString(ce));
+    if (device < 0 || device >= ndev) return fail(FW_EINVAL, "device out of range");
+    CU(cudaSetDevice(device));
+    int sms = 0, khz = 0;
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+    if (sm_count) *sm_count = sms;
+    if (sm_clock_khz) *sm_clock_khz = khz;
+    float* scratch = nullptr;
+    CU(cudaMalloc((void**)&scratch, 64));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    double flops = 0, best = 0;
+    CU(fwk_fma_peak(sms, 2000, scratch, &flops, 0));   // warm-up
+    CU(cudaDeviceSynchronize());
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0, 0));
+        CU(fwk_fma_peak(sms, 20000, scratch, &flops, 0));
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(scratch);
+    *tflops = best;
     return FW_OK;
 }

@@ -118,7 +118,7 @@ __device__ __forceinline__ uint4 fw_philox(uint32_t k0, uint32_t k1, uint32_t c0
     }
     return make_uint4(c0, c1, c2, c3);
 }
-__device__ __forceinline__ float fw_u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float fw_u01(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
 
 __device__ __forceinline__ void fw_normals4(const FwDev& p, uint32_t env, uint32_t episode, uint32_t idx, float n[4]) {
     uint4 r = fw_philox(p.seed_lo, p.seed_hi, env, episode, idx, FWD_STREAM_NOISE);

@@ -117,7 +117,7 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
             if (e.step_count > p.max_steps) trunc = true;
             if (contact) { reward = -100.0f; col = true; term = true; }
             if (sqrtf(e.px * e.px + e.py * e.py + e.pz * e.pz) > p.dome) { reward = -100.0f; oob = true; term = true; }
-            if (TASK == 1 && !(p.early_return_on_crash && (col || oob))) {
+            if (TASK == 1 && e.tidx < p.num_targets && !(p.early_return_on_crash && (col || oob))) {
                 if (!p.sparse_reward) {
                     reward += fmaxf(3.0f * (old_dist - e.new_dist), 0.0f);
                     reward += 1.0f / e.new_dist;
@@ -127,11 +127,11 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
                     e.tidx += 1;                                  // advance_targets
                     const bool all = e.tidx >= p.num_targets;
                     if (p.complete_truncates && all) trunc = true;
-                    complete = all;
                 }
             }
         }
         e.step_count += 1;
+        if (TASK == 1) complete = e.tidx >= p.num_targets;     // info["env_complete"] is sticky within an episode
 
         const bool done = term || trunc;
         if (TASK != 0) fw_write_obs(p, pl, e, i, obs_tidx, a0, a1, a2, a3, row);
@@ -165,7 +165,7 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
 
 __global__ void __launch_bounds__(FW_BLOCK)
 fw_reset_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const uint8_t* __restrict__ mask,
-                float* __restrict__ obs, int bulk_ok) {
+                float* __restrict__ obs, int bulk_ok, int emit_only) {
     extern __shared__ __align__(128) float stage[];
     const int i = blockIdx.x * FW_BLOCK + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -175,7 +175,7 @@ fw_reset_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const uint8_
     if (i < p.n) {
         EnvState e;
         fw_load(pl, i, e);
-        const bool sel = mask == nullptr || mask[i] != 0;
+        const bool sel = !emit_only && (mask == nullptr || mask[i] != 0);
         if (sel) {
             fw_reset_env(p, pl, e, i, p.env_id0 + (uint32_t)i, e.episode + 1u);
             pl.ep_ret[i] = 0.0f;
@@ -227,13 +227,37 @@ cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act
     return cudaGetLastError();
 }
 
-cudaError_t fwk_launch_reset(const FwDev& p, const FwPlanes& pl, const uint8_t* mask, float* obs, cudaStream_t st) {
+cudaError_t fwk_launch_reset(const FwDev& p, const FwPlanes& pl, const uint8_t* mask, float* obs, bool emit_only,
+                             cudaStream_t st) {
     const int bulk_ok = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0);
-    fw_reset_kernel<<<grid_for(p.n), FW_BLOCK, stage_bytes(p), st>>>(p, pl, mask, obs, bulk_ok);
+    fw_reset_kernel<<<grid_for(p.n), FW_BLOCK, stage_bytes(p), st>>>(p, pl, mask, obs, bulk_ok, emit_only ? 1 : 0);
     return cudaGetLastError();
 }
 
 cudaError_t fwk_launch_warm(const FwDev& p, const FwPlanes& pl, float* out, cudaStream_t st) {
     fw_warm_kernel<<<1, 32, 0, st>>>(p, pl, out);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ FP32 FMA-chain peak (roofline denominator)
+// MEASURED_PEAKS.json has no non-tensor FP32 entry; SURVEY section 8(d) asks the first GPU run to measure one.
+__global__ void __launch_bounds__(256) fw_fma_peak_kernel(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x * 1e-3f, x1 = x0 + 1.f, x2 = x0 + 2.f, x3 = x0 + 3.f;
+    float x4 = x0 + 4.f, x5 = x0 + 5.f, x6 = x0 + 6.f, x7 = x0 + 7.f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+        }
+    }
+    float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456f) out[0] = s;   // keep the chain alive
+}
+
+cudaError_t fwk_fma_peak(int sm_count, int iters, float* scratch, double* flops_per_launch, cudaStream_t st) {
+    const int blocks = sm_count * 8, threads = 256;
+    fw_fma_peak_kernel<<<blocks, threads, 0, st>>>(scratch, iters, 0.999f, 0.001f);
+    *flops_per_launch = (double)blocks * threads * (double)iters * 64.0 * 2.0;
     return cudaGetLastError();
 }

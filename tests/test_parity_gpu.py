@@ -1,0 +1,239 @@
+"""GPU parity: the sm_100a kernels (through the C ABI of libfwsim.so) against the fp64 oracle.
+
+Tolerance (BASELINE.json north_star): per-step state within 1e-4 relative (fp32 vs fp64, single step from an
+identical injected state), reward and termination/truncation/info flags matching exactly on those steps,
+trajectory divergence over a 1 s horizon (30 agent steps = 240 substeps) reported.  "Relative" is taken
+norm-wise per observation group with a floor of 1.0 on the reference norm, i.e.
+|x_gpu - x_ref|_inf <= 1e-4 * max(|x_ref|_inf, 1).
+"""
+import numpy as np
+import pytest
+
+import pyflyt_drone_b200 as fw
+from pyflyt_drone_b200.config import FLAG_TERM, FLAG_TRUNC
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+GROUPS_EULER = {"ang_vel": slice(0, 3), "ang_pos": slice(3, 6), "lin_vel": slice(6, 9), "lin_pos": slice(9, 12),
+                "action": slice(12, 16), "aux": slice(16, 22), "delta0": slice(22, 25), "delta1": slice(25, 28)}
+
+
+def group_err(got, ref, groups=GROUPS_EULER):
+    out = {}
+    for k, sl in groups.items():
+        d = np.abs(got[:, sl] - ref[:, sl]).max(axis=1)
+        scale = np.maximum(np.abs(ref[:, sl]).max(axis=1), 1.0)
+        out[k] = float((d / scale).max()) if len(d) else 0.0
+    return out
+
+
+def wrap_angles(obs):
+    o = obs.copy()
+    return o
+
+
+@pytest.fixture(scope="module")
+def fo(oracle_mod):
+    return oracle_mod
+
+
+def make_pair(fo, n, cfg, seed=7, env_id0=0):
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    env = FixedwingVecEnv(n, config=cfg, seed=seed, env_id0=env_id0)
+    orc = fo.OracleVecEnv(cfg.as_dict(), n, seed=seed, env_id0=env_id0)
+    return env, orc
+
+
+def angle_safe(og, oc):
+    """yaw/roll wrap at +-pi: compare angles modulo 2 pi."""
+    og = og.copy()
+    d = og[:, 3:6] - oc[:, 3:6]
+    og[:, 3:6] = oc[:, 3:6] + (d + np.pi) % (2 * np.pi) - np.pi
+    return og
+
+
+@pytest.mark.parametrize("fast_trig", [0, 1])
+def test_reset_parity(fo, fast_trig):
+    cfg = fw.waypoints_v3(fast_trig=fast_trig)
+    env, orc = make_pair(fo, 257, cfg)
+    og, oc = env.reset(), orc.reset()
+    errs = group_err(og, oc)
+    assert max(errs.values()) < RTOL, errs
+    sg, sc = env.get_state(), orc.get_state()
+    assert np.abs(sg["targets"] - sc["targets"]).max() < 1e-4 * 90
+    assert np.array_equal(sg["physics_steps"], sc["physics_steps"]) and np.array_equal(sg["episode"], sc["episode"])
+    env.close()
+
+
+@pytest.mark.parametrize("variant", ["sparse_euler", "dense_quat", "noise", "wind", "fast_trig", "signs"])
+def test_single_step_parity_from_injected_state(fo, variant):
+    kw = dict(noise_ratio=0.0)
+    groups = GROUPS_EULER
+    if variant == "dense_quat":
+        kw.update(sparse_reward=0, angle_repr=1)
+        groups = {"ang_vel": slice(0, 3), "quat": slice(3, 7), "lin_vel": slice(7, 10), "lin_pos": slice(10, 13),
+                  "action": slice(13, 17), "aux": slice(17, 23), "delta0": slice(23, 26), "delta1": slice(26, 29)}
+    elif variant == "noise":
+        kw.update(noise_ratio=0.02, sparse_reward=0)
+    elif variant == "fast_trig":
+        kw.update(fast_trig=1, sparse_reward=0)
+    elif variant == "signs":
+        kw.update(ail_left_sign=-1.0, ail_right_sign=1.0, pitch_sign=-1.0, freestream_3d=0, cd90_degrees=0)
+    wind = None
+    if variant == "wind":
+        wind = dict(enabled=True, mode="gust_sine", wind_enu_mps_range=[[-5, 5], [-5, 5], [-0.5, 0.5]],
+                    gust_amp_enu_mps_range=[[0, 3], [0, 3], [0, 0.3]], gust_freq_hz=0.2,
+                    randomize_on_reset=True, randomize_gust_phase=True)
+    cfg = fw.waypoints_v3(wind=wind, **kw)
+    if variant == "wind":
+        cfg = cfg.replace(wind_start_substep=0)     # env-hook flavour: wind acts during the warm-up too
+    N = 512
+    env, orc = make_pair(fo, N, cfg)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(1)
+    worst = {}
+    n_done = 0
+    for k in range(40):
+        # free-run the oracle, inject its state, step both once
+        env.set_state(orc.get_state())
+        a = rng.uniform(-1, 1, (N, 4)).astype(np.float32)
+        og, rg, fg, tg = env.step_arrays(a)
+        og, rg, fg, tg = og.copy(), rg.copy(), fg.copy().astype(np.int32), tg.copy()
+        oc, rc, fc, tc = orc.step(a.astype(np.float64))
+        assert np.array_equal(fg, fc), (k, np.nonzero(fg != fc))
+        done = (fc & (FLAG_TERM | FLAG_TRUNC)) != 0
+        n_done += int(done.sum())
+        if variant != "dense_quat":
+            og, tg = angle_safe(og, oc), angle_safe(tg, tc)
+        e = group_err(og, oc, groups)
+        if done.any():
+            et = group_err(tg[done], tc[done], groups)
+            e = {g: max(e[g], et[g]) for g in e}
+        for g, v in e.items():
+            worst[g] = max(worst.get(g, 0.0), v)
+        assert np.abs(rg - rc).max() <= 1e-4 * max(1.0, np.abs(rc).max()), k
+        sparse_like = np.isin(np.round(rc, 6), (-0.1, 100.0, -100.0))
+        assert np.abs(rg - rc)[sparse_like].max(initial=0.0) < 1e-6
+    print(f"\n[{variant}] single-step worst norm-wise relative error per group: "
+          + ", ".join(f"{g}={v:.2e}" for g, v in worst.items()) + f"; done events {n_done}")
+    assert max(worst.values()) < RTOL, worst
+    env.close()
+
+
+def test_one_second_free_run_divergence_is_reported_and_small(fo):
+    cfg = fw.waypoints_v3(noise_ratio=0.0)
+    N = 1024
+    env, orc = make_pair(fo, N, cfg)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(2)
+    alive = np.ones(N, bool)
+    div = []
+    for k in range(30):
+        a = rng.uniform(-1, 1, (N, 4)).astype(np.float32)
+        og, rg, fg, _ = env.step_arrays(a)
+        oc, rc, fc, _ = orc.step(a.astype(np.float64))
+        same = fg.astype(np.int32) == fc
+        alive &= same & ((fc & 3) == 0)
+        if alive.any():
+            div.append(float(np.abs(og[alive][:, 9:12] - oc[alive][:, 9:12]).max()))
+    print(f"\n1 s free-run (30 agent steps, 240 substeps, {int(alive.sum())}/{N} envs alive in both): "
+          f"max position divergence {div[-1]:.3e} m; per-step trace {['%.1e' % d for d in div[::5]]}")
+    assert alive.mean() > 0.9
+    assert div[-1] < 5e-3
+
+
+def test_ragged_batch_sizes_and_terminal_observation(fo):
+    cfg = fw.waypoints_v3(noise_ratio=0.0)
+    for n in (1, 31, 33, 65, 100):
+        env, orc = make_pair(fo, n, cfg, seed=3)
+        og, oc = env.reset(), orc.reset()
+        assert og.shape == (n, 28) and max(group_err(og, oc).values()) < RTOL
+        st = orc.get_state()
+        st["pos"][:, 2] = np.linspace(0.03, 0.5, n)    # most of them hit the ground this step
+        orc.set_state(st); env.set_state(st)
+        a = np.zeros((n, 4), np.float32)
+        obs, rew, dones, infos = env.step(a)
+        oc, rc, fc, tc = orc.step(a.astype(np.float64))
+        assert np.array_equal(env._h_flags.astype(np.int32), fc)
+        assert dones.sum() >= 1
+        for i in np.nonzero(dones)[0]:
+            assert infos[i]["collision"] and not infos[i]["TimeLimit.truncated"]
+            assert np.abs(infos[i]["terminal_observation"] - tc[i]).max() < 1e-3
+        # auto-reset rows hold the next episode's first observation
+        assert max(group_err(angle_safe(obs, oc), oc).values()) < RTOL
+        env.close()
+
+
+def test_random_action_lane_matches_oracle_rollout(fo):
+    for preset in ("physics_only", "waypoints_v3"):
+        cfg = fw.make_config(preset, noise_ratio=0.02)
+        N = 300
+        env, orc = make_pair(fo, N, cfg, seed=5, env_id0=1000)
+        env.reset() if cfg.task else None
+        orc.reset()
+        env.step_random(17, 8)
+        orc.rollout_random(8, step0=17)
+        sg, sc = env.get_state(), orc.get_state()
+        assert np.array_equal(sg["episode"], sc["episode"]) and np.array_equal(sg["step_count"], sc["step_count"])
+        assert np.abs(sg["pos"] - sc["pos"]).max() < 2e-3
+        assert np.abs(sg["quat"] - sc["quat"]).max() < 1e-3
+        env.close()
+
+
+def test_tensor_lane_equals_host_lane(fo):
+    import torch
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    cfg = fw.waypoints_v3()
+    a_env, b_env = FixedwingVecEnv(200, config=cfg, seed=1), FixedwingVecEnv(200, config=cfg, seed=1)
+    oa = a_env.reset()
+    ob = b_env.reset_tensor().cpu().numpy()
+    assert np.array_equal(oa, ob)
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        a = rng.uniform(-1, 1, (200, 4)).astype(np.float32)
+        o1, r1, f1, _ = a_env.step_arrays(a)
+        o2, r2, f2 = b_env.step_tensor(torch.from_numpy(a).cuda())
+        torch.cuda.synchronize()
+        assert np.array_equal(o1, o2.cpu().numpy()) and np.array_equal(r1, r2.cpu().numpy())
+        assert np.array_equal(f1, f2.cpu().numpy())
+    a_env.close(); b_env.close()
+
+
+def test_sharding_is_split_invariant(fo):
+    """Global env ids key the RNG: two half batches reproduce one full batch bit for bit (multi-GPU contract)."""
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    cfg = fw.waypoints_v3()
+    full = FixedwingVecEnv(128, config=cfg, seed=2)
+    lo, hi = FixedwingVecEnv(64, config=cfg, seed=2, env_id0=0), FixedwingVecEnv(64, config=cfg, seed=2, env_id0=64)
+    assert np.array_equal(full.reset(), np.concatenate([lo.reset(), hi.reset()]))
+    full.step_random(0, 40); lo.step_random(0, 40); hi.step_random(0, 40)
+    sf, sl, sh = full.get_state(), lo.get_state(), hi.get_state()
+    for k in ("pos", "quat", "episode", "targets"):
+        assert np.array_equal(sf[k], np.concatenate([sl[k], sh[k]])), k
+    for e in (full, lo, hi):
+        e.close()
+
+
+def test_full_size_invariants_65536():
+    """BASELINE config 2 size: properties that do not need the oracle."""
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    env = FixedwingVecEnv(65536, preset="waypoints_v3", seed=0)
+    env.reset()
+    total_done = 0
+    for s in range(0, 120, 20):
+        rew, flags = env.step_random(s, 20, with_outputs=True)
+    import torch
+    torch.cuda.synchronize()
+    st = env.get_state()
+    q = np.linalg.norm(st["quat"], axis=1)
+    assert np.abs(q - 1).max() < 1e-5
+    for k in ("pos", "vel", "omega", "act"):
+        assert np.isfinite(st[k]).all()
+    assert np.abs(st["vel"]).max() <= 100.0 and np.abs(st["omega"]).max() <= 100.0   # Bullet's clamp
+    assert np.linalg.norm(st["pos"], axis=1).max() <= 100.0 + 100 * 8 / 240 + 1e-3    # dome + one step
+    assert np.abs(st["act"][:, :5]).max() <= 1.0 + 1e-6 and st["act"][:, 5].min() >= -0.1
+    stats = env.episode_stats()
+    assert stats["episodes"] == st["episode"].astype(np.int64).sum()
+    assert stats["collisions"] + stats["out_of_bounds"] >= stats["episodes"] * 0.99
+    env.close()
