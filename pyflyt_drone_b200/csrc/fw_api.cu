@@ -149,6 +149,7 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
     d.substeps_per_inner = c.substeps_per_inner; d.inner_per_step = c.inner_per_step;
     d.warmup_substeps = c.warmup_inner * c.substeps_per_inner;
     d.freestream_3d = c.freestream_3d; d.cd90_degrees = c.cd90_degrees; d.fast_trig = c.fast_trig;
+    d.quat_limiter = (sqrt(3.0) * c.max_coord_vel * c.dt > 0.25 * PI) ? 1 : 0;
     d.task = c.task; d.num_targets = c.num_targets; d.sparse_reward = c.sparse_reward; d.angle_repr = c.angle_repr;
     d.max_steps = c.max_steps; d.context_len = c.context_len;
     d.obs_dim = c.task == 0 ? 0 : ((c.angle_repr == 0 ? 12 : 13) + 4 + 6 + 3 * c.context_len);

