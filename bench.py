@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast-trig", type=int, default=None)
+    ap.add_argument("--steps-per-launch", type=int, default=1,
+                    help="env-steps fused into one launch (state kept in registers); a bench step is one launch")
+    ap.add_argument("--no-graph", action="store_true", help="issue launches from the host loop instead of a CUDA graph")
     return ap.parse_args()
 
 
@@ -137,11 +140,11 @@ def oracle_rate(workload: str, threads: int, seconds: float, n_envs: int = 4096)
     env = fo.OracleVecEnv(cfg.as_dict(), n_envs, seed=0, nthreads=threads)
     env.reset()
     t0 = time.perf_counter()
-    env.rollout_random(2, 0)
+    env.rollout_random(2)
     probe = (time.perf_counter() - t0) / 2
-    steps = max(2, min(2000, int(seconds / max(probe, 1e-6))))
+    steps = max(2, min(20000, int(seconds / max(probe, 1e-6))))
     t0 = time.perf_counter()
-    done = env.rollout_random(steps, 2)
+    done = env.rollout_random(steps)
     dt = time.perf_counter() - t0
     return done / dt, f"{n_envs} envs x {steps} agent steps ({done} env-steps, {dt:.1f} s, {threads} threads, fp64 oracle port)"
 
@@ -157,12 +160,12 @@ def run_reference(args, rank: int, world: int):
     env = fo.OracleVecEnv(cfg.as_dict(), n_envs, seed=0, nthreads=threads)
     env.reset()
     # bound the run: K "steps" of the reference arm are K agent steps of the sample batch, capped to ~60 s
-    t0 = time.perf_counter(); env.rollout_random(1, 0); per = time.perf_counter() - t0
+    t0 = time.perf_counter(); env.rollout_random(1); per = time.perf_counter() - t0
     K = max(1, min(args.steps, int(60.0 / max(per, 1e-6))))
     W = max(1, min(args.warmup, max(1, int(5.0 / max(per, 1e-6)))))
-    env.rollout_random(W, 1)
+    env.rollout_random(W)
     t0 = time.perf_counter()
-    done = env.rollout_random(K, 1 + W)
+    done = env.rollout_random(K)
     dt = time.perf_counter() - t0
     v = done / dt
     sample = f"{n_envs} envs per step, {K} timed steps ({done} env-steps), {threads} host threads, {cpu_model()}"
@@ -209,9 +212,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             dist.barrier()
         torch.cuda.synchronize()
 
-    step = 0
-    for s in range(W):
-        envs[s % replicas].step_random(step, 1); step += 1
+    spl = max(1, args.steps_per_launch)
+    FixedwingVecEnv.rollout_random(envs, W, spl, use_graph=False)
     launches0 = sum(e.launch_count for e in envs)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -219,8 +221,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for s in range(K):
-        envs[s % replicas].step_random(step, 1); step += 1
+    FixedwingVecEnv.rollout_random(envs, K, spl, use_graph=not args.no_graph)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -229,7 +230,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    value = N * K * world / (ms * 1e-3)
+    value = N * K * spl * world / (ms * 1e-3)
     kernel_ms = ms / K          # back-to-back launches of one kernel: the mean launch-to-launch duration
 
     # ---- e2e: the VecEnv.step seam with host buffers (Waypoints-v3 task, obs/reward/flags come back) ----
@@ -258,7 +259,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         hbm_peak, peak_src = measured_peaks()
         tf, sms, khz = C.c_double(), C.c_int32(), C.c_int32()
         _lib.check(_lib.load().fw_measure_fp32_peak(local_rank, C.byref(tf), C.byref(sms), C.byref(khz)))
-        per_gpu = N / (kernel_ms * 1e-3)
+        per_gpu = N * spl / (kernel_ms * 1e-3)
         achieved_gbs = per_gpu * BYTES_PER_STEP[args.workload] / 1e9
         fp32_tf = per_gpu * FLOPS_PER_STEP[args.workload] / 1e12
         traffic = None
@@ -277,7 +278,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        if args.workload == "physics_only" else f"{args.workload}: {N} envs/GPU, random actions",
                        "envs_per_gpu": N, "substeps_per_env_step": 8, "physics_substeps_per_sec": value * 8,
                        "l2": f"rotating {replicas} env batches ({replicas * state_bytes / 2**20:.0f} MiB > 2x L2)",
-                       "fast_trig": int(cfg.fast_trig), "e2e_workload": "waypoints_v3 via FixedwingVecEnv.step_arrays (host numpy)"},
+                       "fast_trig": int(cfg.fast_trig), "env_steps_per_launch": spl,
+                       "launch": "host loop" if args.no_graph else f"CUDA graph of {replicas} launches", "e2e_workload": "waypoints_v3 via FixedwingVecEnv.step_arrays (host numpy)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,

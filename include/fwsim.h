@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 3
+#define FW_ABI_VERSION 4
 
 #define FW_NSURF 5            /* cmd order: left aileron, right aileron, h-tail, v-tail, main wing */
 #define FW_MAX_TARGETS 16
@@ -137,10 +137,16 @@ int fw_step(fw_handle h, const float* act_dev, float* obs_dev, float* rew_dev, u
             float* term_obs_dev, void* stream);
 
 /* Random-action workload (BASELINE config 2/5): actions U(-1,1)^4 drawn in-kernel from Philox keyed by
- * (seed, global env id, step_index + i); n_steps env-steps per call, one kernel launch per env-step.
+ * (seed, global env id, episode, step_count); n_steps env-steps, one kernel launch per env-step.
  * rew_dev / flags_dev may be NULL. */
-int fw_step_random(fw_handle h, uint32_t step_index, int32_t n_steps, float* rew_dev, uint8_t* flags_dev,
-                   void* stream);
+int fw_step_random(fw_handle h, int32_t n_steps, float* rew_dev, uint8_t* flags_dev, void* stream);
+
+/* Random-action sweep over a list of env batches on one device: launch j advances batch hs[j % n_handles] by
+ * steps_per_launch env-steps (state stays in registers between the fused steps; no observation is emitted).
+ * use_graph != 0 replays a cached CUDA graph of one round-robin pass so launches are issued back to back
+ * without host involvement.  Results are identical to fw_step_random step by step. */
+int fw_rollout_random(const fw_handle* hs, int32_t n_handles, int32_t n_launches, int32_t steps_per_launch,
+                      int32_t use_graph, void* stream);
 
 /* Synchronous host-buffer variant of fw_step: the call SB3's VecEnv.step() makes (numpy in, numpy out).
  * Copies actions H2D, steps, copies obs/reward/flags (and terminal obs when requested) D2H through
@@ -148,6 +154,10 @@ int fw_step_random(fw_handle h, uint32_t step_index, int32_t n_steps, float* rew
 int fw_step_host(fw_handle h, const float* act_host, float* obs_host, float* rew_host, uint8_t* flags_host,
                  float* term_obs_host);
 int fw_reset_host(fw_handle h, float* obs_host);
+/* The library's pinned staging buffers ([N,4] actions, [N,obs_dim] obs, [N] rewards, [N] flag bytes,
+ * [N,obs_dim] terminal obs).  Passing these very pointers to fw_step_host / fw_reset_host makes the call
+ * zero-copy on the host side (DMA straight from/to the caller-visible memory).  Owned by the handle. */
+int fw_host_buffers(fw_handle h, float** act, float** obs, float** rew, uint8_t** flags, float** term_obs);
 
 /* parity injection / inspection (synchronous) */
 int fw_set_state(fw_handle h, const FwStateHost* s);

@@ -80,9 +80,9 @@ void fwo_normals4(uint64_t seed, uint32_t env, uint32_t episode, uint32_t idx, d
     out[3] = rb * sin(2.0 * M_PI * u3);
 }
 
-void fwo_random_action(uint64_t seed, uint32_t env, uint32_t step, double out[4]) {
+void fwo_random_action(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step_count, double out[4]) {
     uint32_t r[4];
-    fwo_philox(seed, env, step, 0u, STREAM_ACTION, r);
+    fwo_philox(seed, env, episode, step_count, STREAM_ACTION, r);
     for (int i = 0; i < 4; ++i) out[i] = 2.0 * fwo_u01(r[i]) - 1.0;
 }
 
@@ -846,7 +846,7 @@ void fwo_step(const fwo_config* c, fwo_env* e, uint64_t seed, const double actio
 typedef struct {
     const fwo_config* c; fwo_env* envs; int lo, hi; uint64_t seed; uint32_t env_id0;
     const double* actions; double* obs; double* rewards; int32_t* flags; double* term_obs;
-    int steps; uint32_t step0; int mode;
+    int steps; int mode;
 } fwo_job;
 
 static void run_range(fwo_job* j) {
@@ -874,7 +874,7 @@ static void run_range(fwo_job* j) {
             double obs[FWO_MAX_OBS], a[4], r;
             int32_t fl;
             for (int s = 0; s < j->steps; ++s) {
-                fwo_random_action(j->seed, e->env_id, j->step0 + (uint32_t)s, a);
+                fwo_random_action(j->seed, e->env_id, e->episode, (uint32_t)e->step_count, a);
                 fwo_step(c, e, j->seed, a, obs, &r, &fl);
                 if (fl & (FWO_TERM | FWO_TRUNC)) {
                     uint32_t ep = e->episode + 1, id = e->env_id;
@@ -917,10 +917,9 @@ void fwo_vec_step(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, cons
     parallel_run(&j, n, nthreads);
 }
 
-long fwo_rollout_random(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, int steps,
-                        uint32_t step0, int nthreads) {
+long fwo_rollout_random(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, int steps, int nthreads) {
     fwo_job j; memset(&j, 0, sizeof(j));
-    j.c = c; j.envs = envs; j.seed = seed; j.steps = steps; j.step0 = step0; j.mode = 2;
+    j.c = c; j.envs = envs; j.seed = seed; j.steps = steps; j.mode = 2;
     parallel_run(&j, n, nthreads);
     return (long)n * steps;
 }

@@ -165,7 +165,7 @@ int fwo_obs_dim(const fwo_config* c);
 void fwo_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]);
 double fwo_u01(uint32_t x);
 void fwo_normals4(uint64_t seed, uint32_t env, uint32_t episode, uint32_t idx, double out[4]);
-void fwo_random_action(uint64_t seed, uint32_t env, uint32_t step, double out[4]);
+void fwo_random_action(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step_count, double out[4]);
 
 /* lifting-surface model ([UP-RECALL] PyFlyt LiftingSurface): returns Cl, Cd, CM */
 void fwo_aero_coeffs(const fwo_config* c, int s, double alpha, double actuation, double out[3]);
@@ -185,8 +185,7 @@ void fwo_vec_step(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, cons
 void fwo_vec_reset(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, uint32_t env_id0,
                    double* obs, int nthreads);
 /* random-action rollout used as the CPU baseline: returns env-steps executed */
-long fwo_rollout_random(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, int steps,
-                        uint32_t step0, int nthreads);
+long fwo_rollout_random(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, int steps, int nthreads);
 
 void fwo_compute_obs(const fwo_config* c, fwo_env* e, double* obs, int update_dist);
 void fwo_refresh_surface_vel(const fwo_config* c, fwo_env* e, int stamp);

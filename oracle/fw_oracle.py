@@ -100,7 +100,7 @@ def lib() -> C.CDLL:
         L.fwo_u01.argtypes = [_U]
         L.fwo_philox.argtypes = [C.c_uint64, _U, _U, _U, _U, C.POINTER(_U)]
         L.fwo_normals4.argtypes = [C.c_uint64, _U, _U, _U, C.POINTER(_D)]
-        L.fwo_random_action.argtypes = [C.c_uint64, _U, _U, C.POINTER(_D)]
+        L.fwo_random_action.argtypes = [C.c_uint64, _U, _U, _U, C.POINTER(_D)]
         L.fwo_aero_coeffs.argtypes = [C.POINTER(OConfig), C.c_int, _D, _D, C.POINTER(_D)]
         L.fwo_surface_force.argtypes = [C.POINTER(OConfig), C.c_int, _D, C.POINTER(_D), C.POINTER(_D), C.POINTER(_D)]
         L.fwo_substep.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_uint64]
@@ -110,7 +110,7 @@ def lib() -> C.CDLL:
         L.fwo_vec_step.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_int, C.c_uint64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.fwo_rollout_random.restype = C.c_long
-        L.fwo_rollout_random.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_int, C.c_uint64, C.c_int, _U, C.c_int]
+        L.fwo_rollout_random.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_int, C.c_uint64, C.c_int, C.c_int]
         L.fwo_compute_obs.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_void_p, C.c_int]
         L.fwo_refresh_surface_vel.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_int]
         L.fwo_quat_to_euler.argtypes = [C.POINTER(_D), C.POINTER(_D)]
@@ -180,9 +180,8 @@ class OracleVecEnv:
                             _ptr(term), self.nthreads)
         return obs[:, : self.obs_dim], rew, flags, term[:, : self.obs_dim]
 
-    def rollout_random(self, steps: int, step0: int = 0) -> int:
-        return int(self.L.fwo_rollout_random(C.byref(self.cfg), self.envs, self.n, self.seed, int(steps), int(step0),
-                                             self.nthreads))
+    def rollout_random(self, steps: int) -> int:
+        return int(self.L.fwo_rollout_random(C.byref(self.cfg), self.envs, self.n, self.seed, int(steps), self.nthreads))
 
     # ---- state exchange with the device path (same field meaning as FwStateHost) ----
     def get_state(self) -> dict:

@@ -36,9 +36,11 @@ SYMBOLS = [
     ("fw_obs_dim", C.c_int, [_P]),
     ("fw_reset", C.c_int, [_P, _P, _P, _P]),
     ("fw_step", C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
-    ("fw_step_random", C.c_int, [_P, C.c_uint32, C.c_int32, _P, _P, _P]),
+    ("fw_step_random", C.c_int, [_P, C.c_int32, _P, _P, _P]),
+    ("fw_rollout_random", C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     ("fw_step_host", C.c_int, [_P, _P, _P, _P, _P, _P]),
     ("fw_reset_host", C.c_int, [_P, _P]),
+    ("fw_host_buffers", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     ("fw_set_state", C.c_int, [_P, C.POINTER(FwStateHostC)]),
     ("fw_get_state", C.c_int, [_P, C.POINTER(FwStateHostC)]),
     ("fw_episode_stats", C.c_int, [_P, C.POINTER(C.c_double)]),

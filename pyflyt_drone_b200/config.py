@@ -163,7 +163,7 @@ class EnvConfig:
     cam_far: float = 255.0
     cam_res: int = 128
     # ---- device numerics ----
-    fast_trig: int = 0
+    fast_trig: int = 1                                   # SFU sin/cos in the aero model (parity-tested both ways)
 
     # ------------------------------------------------------------------
     @property

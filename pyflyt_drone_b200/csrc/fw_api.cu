@@ -169,6 +169,15 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
     return FW_OK;
 }
 
+// cached CUDA graph of one round-robin pass over a handle list
+struct MultiGraph {
+    std::vector<FwSim*> hs;
+    int spl = 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+};
+static MultiGraph g_multi;
+
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, uint64_t seed, uint32_t env_id0, fw_handle* out) {
@@ -233,6 +242,13 @@ extern "C" int fw_destroy(fw_handle h) {
     if (!h) return FW_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    for (FwSim* g : g_multi.hs)
+        if (g == h) {
+            if (g_multi.exec) cudaGraphExecDestroy(g_multi.exec);
+            if (g_multi.graph) cudaGraphDestroy(g_multi.graph);
+            g_multi = MultiGraph();
+            break;
+        }
     if (h->plane_mem) cudaFree(h->plane_mem);
     if (h->d_act) cudaFree(h->d_act);
     if (h->d_obs) cudaFree(h->d_obs);
@@ -270,21 +286,60 @@ extern "C" int fw_step(fw_handle h, const float* act_dev, float* obs_dev, float*
     if (!act_dev) return fail(FW_EINVAL, "act_dev is null");
     if ((reinterpret_cast<uintptr_t>(act_dev) & 15u) != 0) return fail(FW_EINVAL, "act_dev must be 16-byte aligned");
     CU(cudaSetDevice(h->device));
-    CU(fwk_launch_step(h->dev, h->pl, act_dev, obs_dev, rew_dev, flags_dev, term_obs_dev, false, 0u, (cudaStream_t)stream));
+    CU(fwk_launch_step(h->dev, h->pl, act_dev, obs_dev, rew_dev, flags_dev, term_obs_dev, false, 1, (cudaStream_t)stream));
     h->launches++;
     h->fresh = false;
     return FW_OK;
 }
 
-extern "C" int fw_step_random(fw_handle h, uint32_t step_index, int32_t n_steps, float* rew_dev, uint8_t* flags_dev,
-                              void* stream) {
+extern "C" int fw_step_random(fw_handle h, int32_t n_steps, float* rew_dev, uint8_t* flags_dev, void* stream) {
     if (!h) return fail(FW_EINVAL, "null handle");
     if (n_steps < 0) return fail(FW_EINVAL, "n_steps < 0");
     CU(cudaSetDevice(h->device));
     h->fresh = false;
     for (int s = 0; s < n_steps; ++s) {
-        CU(fwk_launch_step(h->dev, h->pl, nullptr, nullptr, rew_dev, flags_dev, nullptr, true, step_index + (uint32_t)s,
-                           (cudaStream_t)stream));
+        CU(fwk_launch_step(h->dev, h->pl, nullptr, nullptr, rew_dev, flags_dev, nullptr, true, 1, (cudaStream_t)stream));
+        h->launches++;
+    }
+    return FW_OK;
+}
+
+extern "C" int fw_rollout_random(const fw_handle* hs, int32_t n_handles, int32_t n_launches, int32_t steps_per_launch,
+                                 int32_t use_graph, void* stream) {
+    if (!hs || n_handles <= 0) return fail(FW_EINVAL, "empty handle list");
+    if (n_launches < 0 || steps_per_launch < 1) return fail(FW_EINVAL, "bad launch counts");
+    for (int k = 0; k < n_handles; ++k) {
+        if (!hs[k]) return fail(FW_EINVAL, "null handle in list");
+        if (hs[k]->device != hs[0]->device) return fail(FW_EINVAL, "handles of one rollout must share a device");
+        hs[k]->fresh = false;
+    }
+    CU(cudaSetDevice(hs[0]->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int done = 0;
+    if (use_graph && n_launches >= n_handles) {
+        bool hit = g_multi.exec && g_multi.spl == steps_per_launch && (int)g_multi.hs.size() == n_handles;
+        for (int k = 0; hit && k < n_handles; ++k) hit = g_multi.hs[k] == hs[k];
+        if (!hit) {
+            if (g_multi.exec) { cudaGraphExecDestroy(g_multi.exec); g_multi.exec = nullptr; }
+            if (g_multi.graph) { cudaGraphDestroy(g_multi.graph); g_multi.graph = nullptr; }
+            CU(cudaGraphCreate(&g_multi.graph, 0));
+            cudaGraphNode_t prev, node;
+            for (int k = 0; k < n_handles; ++k) {
+                CU(fwk_graph_add_random_step(g_multi.graph, k ? &prev : nullptr, hs[k]->dev, hs[k]->pl, steps_per_launch, &node));
+                prev = node;
+            }
+            CU(cudaGraphInstantiate(&g_multi.exec, g_multi.graph, 0));
+            g_multi.hs.assign(hs, hs + n_handles);
+            g_multi.spl = steps_per_launch;
+        }
+        const int rounds = n_launches / n_handles;
+        for (int r = 0; r < rounds; ++r) CU(cudaGraphLaunch(g_multi.exec, st));
+        done = rounds * n_handles;
+        for (int k = 0; k < n_handles; ++k) hs[k]->launches += rounds;
+    }
+    for (int j = done; j < n_launches; ++j) {
+        FwSim* h = hs[j % n_handles];
+        CU(fwk_launch_step(h->dev, h->pl, nullptr, nullptr, nullptr, nullptr, nullptr, true, steps_per_launch, st));
         h->launches++;
     }
     return FW_OK;
@@ -316,10 +371,10 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
     if (rc != FW_OK) return rc;
     const size_t N = (size_t)h->n, D = (size_t)h->obs_dim;
     cudaStream_t st = h->io_stream;
-    memcpy(h->h_act, act_host, N * 4 * sizeof(float));
+    if (act_host != h->h_act) memcpy(h->h_act, act_host, N * 4 * sizeof(float));
     CU(cudaMemcpyAsync(h->d_act, h->h_act, N * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
     CU(fwk_launch_step(h->dev, h->pl, h->d_act, D ? h->d_obs : nullptr, h->d_rew, h->d_flg,
-                       (term_obs_host && D) ? h->d_term : nullptr, false, 0u, st));
+                       (term_obs_host && D) ? h->d_term : nullptr, false, 1, st));
     h->launches++;
     h->fresh = false;
     if (obs_host && D) CU(cudaMemcpyAsync(h->h_obs, h->d_obs, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -327,10 +382,24 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
     if (flags_host) CU(cudaMemcpyAsync(h->h_flg, h->d_flg, N, cudaMemcpyDeviceToHost, st));
     if (term_obs_host && D) CU(cudaMemcpyAsync(h->h_term, h->d_term, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (obs_host && D) memcpy(obs_host, h->h_obs, N * D * sizeof(float));
-    if (rew_host) memcpy(rew_host, h->h_rew, N * sizeof(float));
-    if (flags_host) memcpy(flags_host, h->h_flg, N);
-    if (term_obs_host && D) memcpy(term_obs_host, h->h_term, N * D * sizeof(float));
+    // buffers obtained from fw_host_buffers are the pinned staging itself: nothing left to copy
+    if (obs_host && D && obs_host != h->h_obs) memcpy(obs_host, h->h_obs, N * D * sizeof(float));
+    if (rew_host && rew_host != h->h_rew) memcpy(rew_host, h->h_rew, N * sizeof(float));
+    if (flags_host && flags_host != h->h_flg) memcpy(flags_host, h->h_flg, N);
+    if (term_obs_host && D && term_obs_host != h->h_term) memcpy(term_obs_host, h->h_term, N * D * sizeof(float));
+    return FW_OK;
+}
+
+extern "C" int fw_host_buffers(fw_handle h, float** act, float** obs, float** rew, uint8_t** flags, float** term_obs) {
+    if (!h) return fail(FW_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_host_io(h);
+    if (rc != FW_OK) return rc;
+    if (act) *act = h->h_act;
+    if (obs) *obs = h->h_obs;
+    if (rew) *rew = h->h_rew;
+    if (flags) *flags = h->h_flg;
+    if (term_obs) *term_obs = h->h_term;
     return FW_OK;
 }
 
@@ -346,7 +415,7 @@ extern "C" int fw_reset_host(fw_handle h, float* obs_host) {
     h->fresh = false;
     if (obs_host && D) CU(cudaMemcpyAsync(h->h_obs, h->d_obs, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
-    if (obs_host && D) memcpy(obs_host, h->h_obs, N * D * sizeof(float));
+    if (obs_host && D && obs_host != h->h_obs) memcpy(obs_host, h->h_obs, N * D * sizeof(float));
     return FW_OK;
 }
 

@@ -17,6 +17,8 @@
 #include "fw_device.cuh"
 #include "fw_kernels.h"
 
+#include <cstring>
+
 #define FW_BLOCK 64
 // 8 resident blocks/SM x 64 threads x 128 registers = the whole 64K register file: 148 x 512 = 75,776 >= 65,536
 // envs, so a 64K-env launch is a single wave
@@ -50,115 +52,138 @@ __device__ __forceinline__ void fw_flush_obs(float* __restrict__ dst_base, const
     }
 }
 
+// One agent step of env i held in registers (FixedwingBaseEnv.step + SubprocVecEnv reset-on-done).
+// Returns the reward; flag bits in `bits`; the observation (if TASK != 0) is left in `row`.
+template <int TASK>
+__device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl, EnvState& e, int i, uint32_t gid,
+                                             float a0, float a1, float a2, float a3, const float4& w0_in,
+                                             const float4& w1_in, float& ep_ret, float* row, float* term_obs_row,
+                                             uint32_t& bits) {
+    float4 w0 = w0_in, w1 = w1_in;
+    // FixedwingBaseEnv.step: reward reset once, thrust remapped to [0,1], setpoint latched
+    float reward = -0.1f;
+    bool term = false, trunc = false, col = false, oob = false, complete = false;
+    float cmd[6];
+    fw_map_setpoint(p, a0, a1, a2, a3 * 0.5f + 0.5f, cmd);
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+    bool have_noise = false;
+    int obs_tidx = e.tidx;
+
+    for (int it = 0; it < p.inner_per_step; ++it) {
+        if (term || trunc) break;
+        bool contact = false;                       // Aviary.step: contact_array &= False
+        for (int s = 0; s < p.substeps_per_inner; ++s) {
+            const int ps = e.physics_steps;
+            float nz = 0.0f;
+            if (p.noise_ratio > 0.0f) {
+                if (!have_noise || (ps & 3) == 0) {
+                    float nn[4];
+                    fw_normals4(p, gid, e.episode, (uint32_t)ps >> 2, nn);
+                    n0 = nn[0]; n1 = nn[1]; n2 = nn[2]; n3 = nn[3];
+                    have_noise = true;
+                }
+                const int q = ps & 3;
+                nz = q == 0 ? n0 : (q == 1 ? n1 : (q == 2 ? n2 : n3));
+            }
+            float wx, wy, wz;
+            fw_wind(p, ps, w0, w1, wx, wy, wz);
+            fw_substep(p, e, cmd, wx, wy, wz, nz, contact);
+        }
+        // compute_state: WaypointHandler.distance_to_targets (old <- new, new <- |delta_0|)
+        float old_dist = e.new_dist;
+        obs_tidx = e.tidx;
+        if (TASK == 1 && e.tidx < p.num_targets) {
+            float dx = pl.targets[(size_t)(e.tidx * 3 + 0) * p.n + i] - e.px;
+            float dy = pl.targets[(size_t)(e.tidx * 3 + 1) * p.n + i] - e.py;
+            float dz = pl.targets[(size_t)(e.tidx * 3 + 2) * p.n + i] - e.pz;
+            e.new_dist = sqrtf(dx * dx + dy * dy + dz * dz);
+        }
+        // compute_base_term_trunc_reward
+        if (e.step_count > p.max_steps) trunc = true;
+        if (contact) { reward = -100.0f; col = true; term = true; }
+        if (sqrtf(e.px * e.px + e.py * e.py + e.pz * e.pz) > p.dome) { reward = -100.0f; oob = true; term = true; }
+        if (TASK == 1 && e.tidx < p.num_targets && !(p.early_return_on_crash && (col || oob))) {
+            if (!p.sparse_reward) {
+                reward += fmaxf(3.0f * (old_dist - e.new_dist), 0.0f);
+                reward += 1.0f / e.new_dist;
+            }
+            if (e.new_dist < p.goal_reach) {
+                reward = 100.0f;
+                e.tidx += 1;                                  // advance_targets
+                const bool all = e.tidx >= p.num_targets;
+                if (p.complete_truncates && all) trunc = true;
+            }
+        }
+    }
+    e.step_count += 1;
+    if (TASK == 1) complete = e.tidx >= p.num_targets;     // info["env_complete"] is sticky within an episode
+
+    const bool done = term || trunc;
+    if (TASK != 0 && row != nullptr) fw_write_obs(p, pl, e, i, obs_tidx, a0, a1, a2, a3, row);
+    ep_ret += reward;
+    if (done) {
+        if (TASK != 0 && term_obs_row != nullptr)
+            for (int k = 0; k < p.obs_dim; ++k) term_obs_row[k] = row[k];
+        atomicAdd(&pl.stats[0], 1.0);
+        atomicAdd(&pl.stats[1], (double)ep_ret);
+        atomicAdd(&pl.stats[2], (double)e.step_count);
+        atomicAdd(&pl.stats[3], (double)e.tidx);
+        if (col) atomicAdd(&pl.stats[4], 1.0);
+        if (oob) atomicAdd(&pl.stats[5], 1.0);
+        if (complete) atomicAdd(&pl.stats[6], 1.0);
+        // SubprocVecEnv worker: obs = env.reset()
+        fw_reset_env(p, pl, e, i, gid, e.episode + 1u);
+        if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
+        if (TASK != 0 && row != nullptr) fw_write_obs(p, pl, e, i, 0, 0.f, 0.f, 0.f, 0.f, row);
+        ep_ret = 0.0f;
+    }
+    bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (col ? 4u : 0u) | (oob ? 8u : 0u) | (complete ? 16u : 0u);
+    return reward;
+}
+
+// K1.  RANDOM_ACT: actions U(-1,1)^4 from Philox keyed (seed, global env id, episode, step_count); `spl` agent
+// steps per launch with the state held in registers between them (the random-action sweep never needs the
+// intermediate observations, so nothing but the final state goes back to HBM).
 template <int TASK, bool RANDOM_ACT>
 __global__ void __launch_bounds__(FW_BLOCK, FW_MIN_BLOCKS)
 fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4* __restrict__ act,
                float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ flg,
-               float* __restrict__ term_obs, uint32_t step_index, int bulk_ok) {
+               float* __restrict__ term_obs, int spl, int bulk_ok) {
     extern __shared__ __align__(128) float stage[];
     const int i = blockIdx.x * FW_BLOCK + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = p.obs_dim;
     float* stage_warp = stage + (size_t)warp * 32 * D;
-    float* row = stage_warp + (size_t)lane * D;
+    float* row = (TASK != 0 && obs != nullptr) ? stage_warp + (size_t)lane * D : nullptr;
 
     if (i < p.n) {
         const uint32_t gid = p.env_id0 + (uint32_t)i;
         EnvState e;
         fw_load(pl, i, e);
-        float a0, a1, a2, a3;
-        if (RANDOM_ACT) {
-            uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid, step_index, 0u, FWD_STREAM_ACTION);
-            a0 = 2.0f * fw_u01(r.x) - 1.0f; a1 = 2.0f * fw_u01(r.y) - 1.0f;
-            a2 = 2.0f * fw_u01(r.z) - 1.0f; a3 = 2.0f * fw_u01(r.w) - 1.0f;
-        } else {
-            float4 a = act[i];
-            a0 = a.x; a1 = a.y; a2 = a.z; a3 = a.w;
-        }
         float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
         if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
-
-        // FixedwingBaseEnv.step: reward reset once, thrust remapped to [0,1], setpoint latched
-        float reward = -0.1f;
-        bool term = false, trunc = false, col = false, oob = false, complete = false;
-        float cmd[6];
-        fw_map_setpoint(p, a0, a1, a2, a3 * 0.5f + 0.5f, cmd);
-        float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
-        bool have_noise = false;
-        int obs_tidx = e.tidx;
-
-        for (int it = 0; it < p.inner_per_step; ++it) {
-            if (term || trunc) break;
-            bool contact = false;                       // Aviary.step: contact_array &= False
-            for (int s = 0; s < p.substeps_per_inner; ++s) {
-                const int ps = e.physics_steps;
-                float nz = 0.0f;
-                if (p.noise_ratio > 0.0f) {
-                    if (!have_noise || (ps & 3) == 0) {
-                        float nn[4];
-                        fw_normals4(p, gid, e.episode, (uint32_t)ps >> 2, nn);
-                        n0 = nn[0]; n1 = nn[1]; n2 = nn[2]; n3 = nn[3];
-                        have_noise = true;
-                    }
-                    const int q = ps & 3;
-                    nz = q == 0 ? n0 : (q == 1 ? n1 : (q == 2 ? n2 : n3));
-                }
-                float wx, wy, wz;
-                fw_wind(p, ps, w0, w1, wx, wy, wz);
-                fw_substep(p, e, cmd, wx, wy, wz, nz, contact);
+        float ep_ret = pl.ep_ret[i];
+        float reward = 0.f;
+        uint32_t bits = 0u;
+        if (RANDOM_ACT) {
+            for (int st = 0; st < spl; ++st) {
+                uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid, e.episode, (uint32_t)e.step_count, FWD_STREAM_ACTION);
+                float a0 = 2.0f * fw_u01(r.x) - 1.0f, a1 = 2.0f * fw_u01(r.y) - 1.0f;
+                float a2 = 2.0f * fw_u01(r.z) - 1.0f, a3 = 2.0f * fw_u01(r.w) - 1.0f;
+                if (p.wind_mode != 0 && st > 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
+                reward = fw_env_step<TASK>(p, pl, e, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
+                                           st == spl - 1 ? row : nullptr, nullptr, bits);
             }
-            // compute_state: WaypointHandler.distance_to_targets (old <- new, new <- |delta_0|)
-            float old_dist = e.new_dist;
-            obs_tidx = e.tidx;
-            if (TASK == 1 && e.tidx < p.num_targets) {
-                float dx = pl.targets[(size_t)(e.tidx * 3 + 0) * p.n + i] - e.px;
-                float dy = pl.targets[(size_t)(e.tidx * 3 + 1) * p.n + i] - e.py;
-                float dz = pl.targets[(size_t)(e.tidx * 3 + 2) * p.n + i] - e.pz;
-                e.new_dist = sqrtf(dx * dx + dy * dy + dz * dz);
-            }
-            // compute_base_term_trunc_reward
-            if (e.step_count > p.max_steps) trunc = true;
-            if (contact) { reward = -100.0f; col = true; term = true; }
-            if (sqrtf(e.px * e.px + e.py * e.py + e.pz * e.pz) > p.dome) { reward = -100.0f; oob = true; term = true; }
-            if (TASK == 1 && e.tidx < p.num_targets && !(p.early_return_on_crash && (col || oob))) {
-                if (!p.sparse_reward) {
-                    reward += fmaxf(3.0f * (old_dist - e.new_dist), 0.0f);
-                    reward += 1.0f / e.new_dist;
-                }
-                if (e.new_dist < p.goal_reach) {
-                    reward = 100.0f;
-                    e.tidx += 1;                                  // advance_targets
-                    const bool all = e.tidx >= p.num_targets;
-                    if (p.complete_truncates && all) trunc = true;
-                }
-            }
-        }
-        e.step_count += 1;
-        if (TASK == 1) complete = e.tidx >= p.num_targets;     // info["env_complete"] is sticky within an episode
-
-        const bool done = term || trunc;
-        if (TASK != 0) fw_write_obs(p, pl, e, i, obs_tidx, a0, a1, a2, a3, row);
-        float ep_ret = pl.ep_ret[i] + reward;
-        if (done) {
-            if (TASK != 0 && term_obs != nullptr)
-                for (int k = 0; k < D; ++k) term_obs[(size_t)i * D + k] = row[k];
-            atomicAdd(&pl.stats[0], 1.0);
-            atomicAdd(&pl.stats[1], (double)ep_ret);
-            atomicAdd(&pl.stats[2], (double)e.step_count);
-            atomicAdd(&pl.stats[3], (double)e.tidx);
-            if (col) atomicAdd(&pl.stats[4], 1.0);
-            if (oob) atomicAdd(&pl.stats[5], 1.0);
-            if (complete) atomicAdd(&pl.stats[6], 1.0);
-            // SubprocVecEnv worker: obs = env.reset()
-            fw_reset_env(p, pl, e, i, gid, e.episode + 1u);
-            if (TASK != 0) fw_write_obs(p, pl, e, i, 0, 0.f, 0.f, 0.f, 0.f, row);
-            ep_ret = 0.0f;
+        } else {
+            float4 a = act[i];
+            reward = fw_env_step<TASK>(p, pl, e, i, gid, a.x, a.y, a.z, a.w, w0, w1, ep_ret, row,
+                                       (TASK != 0 && term_obs != nullptr && row != nullptr) ? term_obs + (size_t)i * D : nullptr,
+                                       bits);
         }
         pl.ep_ret[i] = ep_ret;
         fw_store(pl, i, e);
         if (rew != nullptr) rew[i] = reward;
-        if (flg != nullptr)
-            flg[i] = (uint8_t)((term ? 1 : 0) | (trunc ? 2 : 0) | (col ? 4 : 0) | (oob ? 8 : 0) | (complete ? 16 : 0));
+        if (flg != nullptr) flg[i] = (uint8_t)bits;
     }
     if (TASK != 0 && obs != nullptr) {
         const int first_env = blockIdx.x * FW_BLOCK + warp * 32;
@@ -212,22 +237,41 @@ __global__ void fw_warm_kernel(const __grid_constant__ FwDev p, const FwPlanes p
 static inline size_t stage_bytes(const FwDev& p) { return (size_t)(FW_BLOCK / 32) * 32 * (size_t)(p.obs_dim > 0 ? p.obs_dim : 1) * 4; }
 static inline int grid_for(int n) { return (n + FW_BLOCK - 1) / FW_BLOCK; }
 
+typedef void (*fw_step_fn)(const FwDev, const FwPlanes, const float4*, float*, float*, uint8_t*, float*, int, int);
+
+static fw_step_fn step_fn(int task, bool random_act) {
+    if (task == 0) return random_act ? fw_step_kernel<0, true> : fw_step_kernel<0, false>;
+    if (task == 1) return random_act ? fw_step_kernel<1, true> : fw_step_kernel<1, false>;
+    return nullptr;
+}
+
 cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act, float* obs, float* rew, uint8_t* flg,
-                            float* term_obs, bool random_act, uint32_t step_index, cudaStream_t st) {
+                            float* term_obs, bool random_act, int spl, cudaStream_t st) {
     const int bulk_ok = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) && ((p.obs_dim * 128) % 16 == 0);
-    const size_t sm = stage_bytes(p);
-    const dim3 g(grid_for(p.n)), b(FW_BLOCK);
-    const float4* a4 = reinterpret_cast<const float4*>(act);
-    if (p.task == 0) {
-        if (random_act) fw_step_kernel<0, true><<<g, b, sm, st>>>(p, pl, a4, obs, rew, flg, term_obs, step_index, bulk_ok);
-        else fw_step_kernel<0, false><<<g, b, sm, st>>>(p, pl, a4, obs, rew, flg, term_obs, step_index, bulk_ok);
-    } else if (p.task == 1) {
-        if (random_act) fw_step_kernel<1, true><<<g, b, sm, st>>>(p, pl, a4, obs, rew, flg, term_obs, step_index, bulk_ok);
-        else fw_step_kernel<1, false><<<g, b, sm, st>>>(p, pl, a4, obs, rew, flg, term_obs, step_index, bulk_ok);
-    } else {
-        return cudaErrorNotSupported;
-    }
+    fw_step_fn fn = step_fn(p.task, random_act);
+    if (fn == nullptr) return cudaErrorNotSupported;
+    fn<<<grid_for(p.n), FW_BLOCK, stage_bytes(p), st>>>(p, pl, reinterpret_cast<const float4*>(act), obs, rew, flg, term_obs,
+                                                         spl, bulk_ok);
     return cudaGetLastError();
+}
+
+// Append one random-action step launch to a CUDA graph (explicit node: works without stream capture, so the
+// graph can later be launched on any stream including the legacy default stream torch hands us).
+cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* dep, const FwDev& p, const FwPlanes& pl, int spl,
+                                      cudaGraphNode_t* out) {
+    fw_step_fn fn = step_fn(p.task, true);
+    if (fn == nullptr) return cudaErrorNotSupported;
+    FwDev pc = p; FwPlanes plc = pl;
+    const float4* act = nullptr; float* obs = nullptr; float* rew = nullptr; uint8_t* flg = nullptr; float* term = nullptr;
+    int spl_ = spl, bulk = 0;
+    void* args[] = {&pc, &plc, &act, &obs, &rew, &flg, &term, &spl_, &bulk};
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.func = (void*)fn;
+    kp.gridDim = dim3(grid_for(p.n)); kp.blockDim = dim3(FW_BLOCK);
+    kp.sharedMemBytes = (unsigned)stage_bytes(p);
+    kp.kernelParams = args; kp.extra = nullptr;
+    return cudaGraphAddKernelNode(out, g, dep, dep ? 1 : 0, &kp);
 }
 
 cudaError_t fwk_launch_reset(const FwDev& p, const FwPlanes& pl, const uint8_t* mask, float* obs, bool emit_only,

@@ -48,6 +48,18 @@ class FixedwingVecEnv:
         self.env_id0 = int(env_id0)
         self.lib = _lib.load()
         self._c_cfg = self.cfg.to_c()
+        if info_mode == "auto":
+            info_mode = "full" if self.num_envs <= 4096 else "lazy"
+        if info_mode not in ("full", "lazy"):
+            raise ValueError("info_mode must be 'auto', 'full' or 'lazy'")
+        self.info_mode = info_mode
+        self._open()
+        self._pending: np.ndarray | None = None
+        self._t = None  # lazily created torch buffers for the tensor lane
+        self._closed = False
+
+    def _open(self) -> None:
+        """Create the device batch and map the library's pinned staging buffers as NumPy views."""
         self._h = C.c_void_p()
         _lib.check(self.lib.fw_create(C.byref(self._c_cfg), self.num_envs, self.device_index, self._seed,
                                       self.env_id0, C.byref(self._h)))
@@ -55,19 +67,20 @@ class FixedwingVecEnv:
         D = max(self.obs_dim, 1)
         self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(self.obs_dim,), dtype=np.float32)
         self.action_space = spaces.Box(low=-1.0, high=1.0, shape=(4,), dtype=np.float32)
-        if info_mode == "auto":
-            info_mode = "full" if self.num_envs <= 4096 else "lazy"
-        if info_mode not in ("full", "lazy"):
-            raise ValueError("info_mode must be 'auto', 'full' or 'lazy'")
-        self.info_mode = info_mode
-        # host arrays handed back to the caller (SB3 copies them into its rollout buffer)
-        self._h_obs = np.zeros((self.num_envs, D), dtype=np.float32)
-        self._h_rew = np.zeros(self.num_envs, dtype=np.float32)
-        self._h_flags = np.zeros(self.num_envs, dtype=np.uint8)
-        self._h_term = np.zeros((self.num_envs, D), dtype=np.float32)
-        self._pending: np.ndarray | None = None
-        self._t = None  # lazily created torch buffers for the tensor lane
-        self._closed = False
+        # host arrays = NumPy views of the library's pinned staging buffers: the DMA engines read actions from
+        # and write observations to the very memory the caller sees (no extra host memcpy on either side)
+        ptrs = [C.c_void_p() for _ in range(5)]
+        _lib.check(self.lib.fw_host_buffers(self._h, *[C.byref(p) for p in ptrs]))
+
+        def view(ptr, shape, ctype, dtype):
+            n = int(np.prod(shape))
+            return np.frombuffer((ctype * n).from_address(ptr.value), dtype=dtype).reshape(shape)
+
+        self._h_act = view(ptrs[0], (self.num_envs, 4), C.c_float, np.float32)
+        self._h_obs = view(ptrs[1], (self.num_envs, D), C.c_float, np.float32)
+        self._h_rew = view(ptrs[2], (self.num_envs,), C.c_float, np.float32)
+        self._h_flags = view(ptrs[3], (self.num_envs,), C.c_uint8, np.uint8)
+        self._h_term = view(ptrs[4], (self.num_envs, D), C.c_float, np.float32)
 
     # ------------------------------------------------------------------ SB3 VecEnv (host NumPy lane)
     def reset(self) -> np.ndarray:
@@ -83,12 +96,13 @@ class FixedwingVecEnv:
         self._pending = a
 
     def step_arrays(self, actions: np.ndarray, want_terminal_obs: bool = True):
-        """Host-buffer step without the per-env info dicts: (obs, rewards, flags, terminal_obs)."""
-        a = np.ascontiguousarray(actions, dtype=np.float32)
-        if a.shape != (self.num_envs, 4):
-            raise ValueError(f"actions must have shape ({self.num_envs}, 4), got {a.shape}")
+        """Host-buffer step without the per-env info dicts: (obs, rewards, flags, terminal_obs).
+        The returned arrays are views of pinned memory owned by the env, valid until the next step."""
+        if np.shape(actions) != (self.num_envs, 4):
+            raise ValueError(f"actions must have shape ({self.num_envs}, 4), got {np.shape(actions)}")
+        np.copyto(self._h_act, actions, casting="same_kind")
         p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
-        _lib.check(self.lib.fw_step_host(self._h, p(a), p(self._h_obs), p(self._h_rew), p(self._h_flags),
+        _lib.check(self.lib.fw_step_host(self._h, p(self._h_act), p(self._h_obs), p(self._h_rew), p(self._h_flags),
                                          p(self._h_term) if want_terminal_obs else None))
         return self._h_obs[:, : self.obs_dim], self._h_rew, self._h_flags, self._h_term[:, : self.obs_dim]
 
@@ -131,6 +145,7 @@ class FixedwingVecEnv:
 
     def close(self) -> None:
         if not self._closed and self._h:
+            self._h_act = self._h_obs = self._h_rew = self._h_flags = self._h_term = None   # views die with the handle
             self.lib.fw_destroy(self._h)
             self._h = C.c_void_p()
             self._closed = True
@@ -145,10 +160,9 @@ class FixedwingVecEnv:
         """SB3 API parity.  The Philox key is fixed at construction; re-seeding rebuilds the batch."""
         if seed is not None and int(seed) != self._seed:
             self._seed = int(seed)
+            self._h_act = self._h_obs = self._h_rew = self._h_flags = self._h_term = None
             self.lib.fw_destroy(self._h)
-            self._h = C.c_void_p()
-            _lib.check(self.lib.fw_create(C.byref(self._c_cfg), self.num_envs, self.device_index, self._seed,
-                                          self.env_id0, C.byref(self._h)))
+            self._open()
         return [self._seed + self.env_id0 + i for i in range(self.num_envs)]
 
     def _indices(self, indices) -> Sequence[int]:
@@ -211,14 +225,22 @@ class FixedwingVecEnv:
             return t["obs"][:, : self.obs_dim], t["rew"], t["flags"], t["term"][:, : self.obs_dim]
         return t["obs"][:, : self.obs_dim], t["rew"], t["flags"]
 
-    def step_random(self, step_index: int, n_steps: int = 1, with_outputs: bool = False):
-        """Random-action workload (BASELINE config 2): actions drawn in-kernel, n_steps launches."""
+    def step_random(self, n_steps: int = 1, with_outputs: bool = False):
+        """Random-action workload (BASELINE config 2): actions drawn in-kernel, one launch per env-step."""
         t = self._tensors() if with_outputs else None
         _lib.check(self.lib.fw_step_random(
-            self._h, int(step_index) & 0xFFFFFFFF, int(n_steps),
+            self._h, int(n_steps),
             C.c_void_p(t["rew"].data_ptr()) if t else None, C.c_void_p(t["flags"].data_ptr()) if t else None,
             C.c_void_p(self._stream())))
         return (t["rew"], t["flags"]) if t else None
+
+    @staticmethod
+    def rollout_random(envs: "Sequence[FixedwingVecEnv]", n_launches: int, steps_per_launch: int = 1,
+                       use_graph: bool = True) -> None:
+        """Round-robin random-action sweep over several env batches of one device (see fw_rollout_random)."""
+        arr = (C.c_void_p * len(envs))(*[e._h for e in envs])
+        _lib.check(envs[0].lib.fw_rollout_random(arr, len(envs), int(n_launches), int(steps_per_launch),
+                                                 1 if use_graph else 0, C.c_void_p(envs[0]._stream())))
 
     # ------------------------------------------------------------------ parity injection / inspection
     def get_state(self) -> dict[str, np.ndarray]:

@@ -224,13 +224,13 @@ def test_random_action_stream_matches_rollout(fo):
     a = fo.OracleVecEnv(cfg.as_dict(), 3, seed=4)
     b = fo.OracleVecEnv(cfg.as_dict(), 3, seed=4)
     a.reset(); b.reset()
-    a.rollout_random(6, step0=10)
+    a.rollout_random(6)
     L = fo.lib()
     for s in range(6):
         act = np.zeros((3, 4))
         for i in range(3):
             out = (C.c_double * 4)()
-            L.fwo_random_action(4, i, 10 + s, out)
+            L.fwo_random_action(4, i, b.envs[i].episode, b.envs[i].step_count, out)
             act[i] = out[:]
         assert np.all(np.abs(act) < 1.0)
         b.step(act)

@@ -172,8 +172,8 @@ def test_random_action_lane_matches_oracle_rollout(fo):
         env, orc = make_pair(fo, N, cfg, seed=5, env_id0=1000)
         env.reset() if cfg.task else None
         orc.reset()
-        env.step_random(17, 8)
-        orc.rollout_random(8, step0=17)
+        env.step_random(8)
+        orc.rollout_random(8)
         sg, sc = env.get_state(), orc.get_state()
         assert np.array_equal(sg["episode"], sc["episode"]) and np.array_equal(sg["step_count"], sc["step_count"])
         assert np.abs(sg["pos"] - sc["pos"]).max() < 2e-3
@@ -207,12 +207,38 @@ def test_sharding_is_split_invariant(fo):
     full = FixedwingVecEnv(128, config=cfg, seed=2)
     lo, hi = FixedwingVecEnv(64, config=cfg, seed=2, env_id0=0), FixedwingVecEnv(64, config=cfg, seed=2, env_id0=64)
     assert np.array_equal(full.reset(), np.concatenate([lo.reset(), hi.reset()]))
-    full.step_random(0, 40); lo.step_random(0, 40); hi.step_random(0, 40)
+    full.step_random(40); lo.step_random(40); hi.step_random(40)
     sf, sl, sh = full.get_state(), lo.get_state(), hi.get_state()
     for k in ("pos", "quat", "episode", "targets"):
         assert np.array_equal(sf[k], np.concatenate([sl[k], sh[k]])), k
     for e in (full, lo, hi):
         e.close()
+
+
+def test_fused_and_graph_rollouts_are_bitwise_identical_to_single_step_launches():
+    """steps_per_launch > 1 keeps the state in registers between env-steps, and the CUDA-graph path replays
+    the same launches: both must reproduce the one-launch-per-step trajectory bit for bit."""
+    import torch
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    for preset in ("physics_only", "waypoints_v3"):
+        cfg = fw.make_config(preset)
+        ref = [FixedwingVecEnv(1000, config=cfg, seed=8, env_id0=k * 1000) for k in range(3)]
+        fused = [FixedwingVecEnv(1000, config=cfg, seed=8, env_id0=k * 1000) for k in range(3)]
+        graph = [FixedwingVecEnv(1000, config=cfg, seed=8, env_id0=k * 1000) for k in range(3)]
+        for e in ref:
+            e.step_random(48)
+        FixedwingVecEnv.rollout_random(fused, n_launches=3 * 6, steps_per_launch=8, use_graph=False)
+        FixedwingVecEnv.rollout_random(graph, n_launches=3 * 48 + 0, steps_per_launch=1, use_graph=True)
+        torch.cuda.synchronize()
+        for k in range(3):
+            a, b, c = ref[k].get_state(), fused[k].get_state(), graph[k].get_state()
+            for key in ("pos", "quat", "vel", "omega", "act", "episode", "step_count", "physics_steps", "targets"):
+                assert np.array_equal(a[key], b[key]), (preset, "fused", key)
+                assert np.array_equal(a[key], c[key]), (preset, "graph", key)
+        sa, sb = ref[0].episode_stats(), fused[0].episode_stats()
+        assert sa["episodes"] == sb["episodes"] and sa["episodes"] > 0
+        for e in ref + fused + graph:
+            e.close()
 
 
 def test_full_size_invariants_65536():
@@ -222,7 +248,7 @@ def test_full_size_invariants_65536():
     env.reset()
     total_done = 0
     for s in range(0, 120, 20):
-        rew, flags = env.step_random(s, 20, with_outputs=True)
+        rew, flags = env.step_random(20, with_outputs=True)
     import torch
     torch.cuda.synchronize()
     st = env.get_state()
