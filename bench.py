@@ -53,7 +53,6 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fast-trig", type=int, default=None)
     ap.add_argument("--steps-per-launch", type=int, default=1,
                     help="env-steps fused into one launch (state kept in registers); a bench step is one launch")
     ap.add_argument("--no-graph", action="store_true", help="issue launches from the host loop instead of a CUDA graph")
@@ -198,7 +197,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     from pyflyt_drone_b200 import _lib
     from pyflyt_drone_b200.vec_env import FixedwingVecEnv
 
-    over = {} if args.fast_trig is None else {"fast_trig": args.fast_trig}
+    over = {}
     cfg = fw.make_config(args.workload, **over)
     N = args.envs
     state_bytes = N * (6 * 16 + 4 + (cfg.num_targets * 12))
@@ -278,7 +277,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                        if args.workload == "physics_only" else f"{args.workload}: {N} envs/GPU, random actions",
                        "envs_per_gpu": N, "substeps_per_env_step": 8, "physics_substeps_per_sec": value * 8,
                        "l2": f"rotating {replicas} env batches ({replicas * state_bytes / 2**20:.0f} MiB > 2x L2)",
-                       "fast_trig": int(cfg.fast_trig), "env_steps_per_launch": spl,
+                       "env_steps_per_launch": spl,
                        "launch": "host loop" if args.no_graph else f"CUDA graph of {replicas} launches", "e2e_workload": "waypoints_v3 via FixedwingVecEnv.step_arrays (host numpy)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),

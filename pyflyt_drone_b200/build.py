@@ -15,6 +15,8 @@ LIB = os.path.join(HERE, "libfwsim.so")
 SOURCES = ["fw_api.cu", "fw_kernels.cu", "ppo_kernels.cu", "ppo_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    # flush fp32 denormals: MUFU.RCP/RSQ/SIN/COS then need no 2^24 rescue sequences (4-6 instructions each)
+    "--ftz=true",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--threads", "4",
 ]
 

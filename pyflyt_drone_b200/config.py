@@ -59,8 +59,7 @@ class FwConfigC(C.Structure):
         ("wind_mode", _I), ("wind_randomize", _I), ("wind_rand_phase", _I), ("wind_start_substep", _I),
         ("num_obstacles", _I), ("cam_interval_substeps", _I), ("lock_hold_steps", _I), ("switch_min_seen", _I),
         ("cam_res", _I),
-        ("fast_trig", _I),
-        ("_reserved", _I * 5),
+        ("_reserved", _I * 6),
     ]
 
 
@@ -162,8 +161,6 @@ class EnvConfig:
     cam_near: float = 0.1
     cam_far: float = 255.0
     cam_res: int = 128
-    # ---- device numerics ----
-    fast_trig: int = 1                                   # SFU sin/cos in the aero model (parity-tested both ways)
 
     # ------------------------------------------------------------------
     @property

@@ -109,7 +109,13 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
         const double* l = c.lift_unit[s];
         const double* f = c.fwd_unit[s];
         double t[3] = {l[1] * f[2] - l[2] * f[1], l[2] * f[0] - l[0] * f[2], l[0] * f[1] - l[1] * f[0]};
-        for (int k = 0; k < 3; ++k) { o.lift[k] = (float)l[k]; o.fwd[k] = (float)f[k]; o.tq[k] = (float)t[k]; o.r[k] = (float)c.r_surf[s][k]; }
+        const double* r = c.r_surf[s];
+        double ra[3] = {r[1] * l[2] - r[2] * l[1], r[2] * l[0] - r[0] * l[2], r[0] * l[1] - r[1] * l[0]};
+        double rb[3] = {r[1] * f[2] - r[2] * f[1], r[2] * f[0] - r[0] * f[2], r[0] * f[1] - r[1] * f[0]};
+        for (int k = 0; k < 3; ++k) {
+            o.lift[k] = (float)l[k]; o.fwd[k] = (float)f[k]; o.tq[k] = (float)t[k]; o.r[k] = (float)r[k];
+            o.ra[k] = (float)ra[k]; o.rb[k] = (float)rb[k];
+        }
     }
     if (!(c.motor_tau > 0) || !(c.thrust_coef > 0)) return fail(FW_EINVAL, "bad motor constants");
     d.motor_k = (float)(c.dt / c.motor_tau);
@@ -148,13 +154,13 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
     d.sign_pitch = (float)c.pitch_sign; d.sign_yaw = (float)c.yaw_sign;
     d.substeps_per_inner = c.substeps_per_inner; d.inner_per_step = c.inner_per_step;
     d.warmup_substeps = c.warmup_inner * c.substeps_per_inner;
-    d.freestream_3d = c.freestream_3d; d.cd90_degrees = c.cd90_degrees; d.fast_trig = c.fast_trig;
+    d.freestream_3d = c.freestream_3d; d.cd90_degrees = c.cd90_degrees;
     d.quat_limiter = (sqrt(3.0) * c.max_coord_vel * c.dt > 0.25 * PI) ? 1 : 0;
     d.task = c.task; d.num_targets = c.num_targets; d.sparse_reward = c.sparse_reward; d.angle_repr = c.angle_repr;
     d.max_steps = c.max_steps; d.context_len = c.context_len;
     d.obs_dim = c.task == 0 ? 0 : ((c.angle_repr == 0 ? 12 : 13) + 4 + 6 + 3 * c.context_len);
     d.early_return_on_crash = c.early_return_on_crash; d.complete_truncates = c.complete_truncates;
-    d.goal_reach = (float)c.goal_reach; d.dome = (float)c.dome; d.spawn_size = (float)c.spawn_size; d.min_height = (float)c.min_height;
+    d.goal_reach = (float)c.goal_reach; d.dome = (float)c.dome; d.dome2 = (float)(c.dome * c.dome); d.spawn_size = (float)c.spawn_size; d.min_height = (float)c.min_height;
     for (int k = 0; k < 3; ++k) {
         d.start_pos[k] = (float)c.start_pos[k]; d.start_vel[k] = (float)c.start_vel[k];
         d.wind_base[k] = (float)c.wind_base[k]; d.wind_base_lo[k] = (float)c.wind_base_lo[k]; d.wind_base_hi[k] = (float)c.wind_base_hi[k];

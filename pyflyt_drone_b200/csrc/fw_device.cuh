@@ -40,6 +40,7 @@ struct SurfDev {
     float qarea;        // 0.5 * rho * area
     float chord;
     float lift[3], fwd[3], tq[3], r[3];
+    float ra[3], rb[3];   // r x lift, r x fwd: moment arms of the normal / parallel force components about O
 };
 
 struct FwDev {
@@ -59,11 +60,11 @@ struct FwDev {
     float dt, gravity, max_vel;
     float sign_ail_l, sign_ail_r, sign_pitch, sign_yaw;
     int substeps_per_inner, inner_per_step, warmup_substeps;
-    int freestream_3d, cd90_degrees, fast_trig, quat_limiter;
+    int freestream_3d, cd90_degrees, quat_limiter;
     // env
     int task, num_targets, sparse_reward, angle_repr, max_steps, context_len, obs_dim;
     int early_return_on_crash, complete_truncates;
-    float goal_reach, dome, spawn_size, min_height;
+    float goal_reach, dome, dome2, spawn_size, min_height;
     float start_pos[3], start_vel[3];
     // wind
     int wind_mode, wind_randomize, wind_rand_phase, wind_start_substep;
@@ -122,18 +123,18 @@ __device__ __forceinline__ float fw_u01(uint32_t x) { return ((float)(x >> 9) + 
 
 __device__ __forceinline__ void fw_normals4(const FwDev& p, uint32_t env, uint32_t episode, uint32_t idx, float n[4]) {
     uint4 r = fw_philox(p.seed_lo, p.seed_hi, env, episode, idx, FWD_STREAM_NOISE);
-    float ra = sqrtf(-2.0f * logf(fw_u01(r.x))), rb = sqrtf(-2.0f * logf(fw_u01(r.z)));
-    float s0, c0, s1, c1;
-    sincospif(2.0f * fw_u01(r.y), &s0, &c0);
-    sincospif(2.0f * fw_u01(r.w), &s1, &c1);
+    // Box-Muller on SFU approximations (MUFU.LG2/SIN/COS): the 2e-7 absolute error is far below the
+    // 2 % multiplicative motor noise this feeds
+    float ra = sqrtf(-2.0f * __logf(fw_u01(r.x))), rb = sqrtf(-2.0f * __logf(fw_u01(r.z)));
+    float a0 = 2.0f * FWD_PI * fw_u01(r.y) - FWD_PI, a1 = 2.0f * FWD_PI * fw_u01(r.w) - FWD_PI;   // [-pi, pi)
+    float s0 = -__sinf(a0), c0 = -__cosf(a0), s1 = -__sinf(a1), c1 = -__cosf(a1);
     n[0] = ra * c0; n[1] = ra * s0; n[2] = rb * c1; n[3] = rb * s1;
 }
 
 // ------------------------------------------------------------------ math helpers
-__device__ __forceinline__ void fw_sincos(int fast, float x, float* s, float* c) {
-    if (fast) { *s = __sinf(x); *c = __cosf(x); }   // MUFU.SIN/COS: abs err 2^-21.4 on [-pi, pi]
-    else sincosf(x, s, c);
-}
+// MUFU.SIN/COS: absolute error 2^-21.4 on [-pi, pi], which is where the effective angle of attack lives.
+// (The libdevice sincosf was measured to give the same parity against the fp64 oracle at 6x the instructions.)
+__device__ __forceinline__ void fw_sincos(float x, float* s, float* c) { *s = __sinf(x); *c = __cosf(x); }
 
 // Branch-free atan2 (all quadrants): odd minimax polynomial of degree 17 on [0,1] (max abs error 1.1e-7,
 // checked against fp64 atan on 2e6 points) + SFU reciprocal; replaces libdevice atan2f (division slow path,
@@ -180,9 +181,10 @@ __device__ __forceinline__ Mat3 fw_quat_mat(float x, float y, float z, float w) 
 // Cl = CN cos - CT sin, Cd = CN sin + CT cos; only CN, CT and the |alpha_eff| in CM differ, so both are
 // evaluated and selected.  That keeps all five surfaces of a thread in one straight-line block the compiler
 // can interleave (ILP 5) and keeps warps convergent when only some aircraft are stalled.
-// Returns the force (body frame) and the scalar pitching torque about the surface's torque axis.
+// Returns the force components along the lift and forward units and the scalar pitching torque about the
+// surface's torque axis (lift x fwd).
 __device__ __forceinline__ void fw_surface(const FwDev& p, const SurfDev& sf, float act, float vx, float vy, float vz,
-                                           float& fx, float& fy, float& fz, float& tq) {
+                                           float& fn, float& fp, float& tq) {
     float vl = vx * sf.lift[0] + vy * sf.lift[1] + vz * sf.lift[2];
     float vf = vx * sf.fwd[0] + vy * sf.fwd[1] + vz * sf.fwd[2];
     float h2 = vl * vl + vf * vf;
@@ -211,7 +213,7 @@ __device__ __forceinline__ void fw_surface(const FwDev& p, const SurfDev& sf, fl
     float ai = nostall ? cl_lin * sf.inv_pi_ar : ai_stall;
     float ae = alpha - a0 - ai;
     float s, c;
-    fw_sincos(p.fast_trig, ae, &s, &c);
+    fw_sincos(ae, &s, &c);
 
     float CT_a = sf.cd0 * c;
     float CN_a = __fdividef(cl_lin + CT_a * s, c);
@@ -227,11 +229,8 @@ __device__ __forceinline__ void fw_surface(const FwDev& p, const SurfDev& sf, fl
 
     float Q = sf.qarea * V2;
     float lift = Cl * Q, drag = Cd * Q;
-    float fn = lift * cosA + drag * sinA;
-    float fp = lift * sinA - drag * cosA;
-    fx = sf.lift[0] * fn + sf.fwd[0] * fp;
-    fy = sf.lift[1] * fn + sf.fwd[1] * fp;
-    fz = sf.lift[2] * fn + sf.fwd[2] * fp;
+    fn = lift * cosA + drag * sinA;
+    fp = lift * sinA - drag * cosA;
     tq = Q * CM * sf.chord;
 }
 
@@ -260,12 +259,15 @@ __device__ __forceinline__ void fw_substep(const FwDev& p, EnvState& e, const fl
         float sx = vbx + (wby * sf.r[2] - wbz * sf.r[1]);
         float sy = vby + (wbz * sf.r[0] - wbx * sf.r[2]);
         float sz = vbz + (wbx * sf.r[1] - wby * sf.r[0]);
-        float fx, fy, fz, tq;
-        fw_surface(p, sf, e.act[s], sx, sy, sz, fx, fy, fz, tq);
-        Fx += fx; Fy += fy; Fz += fz;
-        Tx += sf.r[1] * fz - sf.r[2] * fy + tq * sf.tq[0];
-        Ty += sf.r[2] * fx - sf.r[0] * fz + tq * sf.tq[1];
-        Tz += sf.r[0] * fy - sf.r[1] * fx + tq * sf.tq[2];
+        float fn, fp, tq;
+        fw_surface(p, sf, e.act[s], sx, sy, sz, fn, fp, tq);
+        // force = lift*fn + fwd*fp at the link CoM; torque about O = fn (r x lift) + fp (r x fwd) + tq (lift x fwd)
+        Fx += sf.lift[0] * fn + sf.fwd[0] * fp;
+        Fy += sf.lift[1] * fn + sf.fwd[1] * fp;
+        Fz += sf.lift[2] * fn + sf.fwd[2] * fp;
+        Tx += sf.ra[0] * fn + sf.rb[0] * fp + sf.tq[0] * tq;
+        Ty += sf.ra[1] * fn + sf.rb[1] * fp + sf.tq[1] * tq;
+        Tz += sf.ra[2] * fn + sf.rb[2] * fp + sf.tq[2] * tq;
     }
     {   // motor: first-order lag, multiplicative gaussian noise, thrust ~ rpm^2
         e.thr += p.motor_k * (cmd[5] - e.thr);

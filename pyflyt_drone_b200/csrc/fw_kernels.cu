@@ -101,7 +101,7 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
         // compute_base_term_trunc_reward
         if (e.step_count > p.max_steps) trunc = true;
         if (contact) { reward = -100.0f; col = true; term = true; }
-        if (sqrtf(e.px * e.px + e.py * e.py + e.pz * e.pz) > p.dome) { reward = -100.0f; oob = true; term = true; }
+        if (e.px * e.px + e.py * e.py + e.pz * e.pz > p.dome2) { reward = -100.0f; oob = true; term = true; }
         if (TASK == 1 && e.tidx < p.num_targets && !(p.early_return_on_crash && (col || oob))) {
             if (!p.sparse_reward) {
                 reward += fmaxf(3.0f * (old_dist - e.new_dist), 0.0f);

@@ -53,9 +53,8 @@ def angle_safe(og, oc):
     return og
 
 
-@pytest.mark.parametrize("fast_trig", [0, 1])
-def test_reset_parity(fo, fast_trig):
-    cfg = fw.waypoints_v3(fast_trig=fast_trig)
+def test_reset_parity(fo):
+    cfg = fw.waypoints_v3()
     env, orc = make_pair(fo, 257, cfg)
     og, oc = env.reset(), orc.reset()
     errs = group_err(og, oc)
@@ -66,7 +65,7 @@ def test_reset_parity(fo, fast_trig):
     env.close()
 
 
-@pytest.mark.parametrize("variant", ["sparse_euler", "dense_quat", "noise", "wind", "fast_trig", "signs"])
+@pytest.mark.parametrize("variant", ["sparse_euler", "dense_quat", "noise", "wind", "signs"])
 def test_single_step_parity_from_injected_state(fo, variant):
     kw = dict(noise_ratio=0.0)
     groups = GROUPS_EULER
@@ -76,8 +75,6 @@ def test_single_step_parity_from_injected_state(fo, variant):
                   "action": slice(13, 17), "aux": slice(17, 23), "delta0": slice(23, 26), "delta1": slice(26, 29)}
     elif variant == "noise":
         kw.update(noise_ratio=0.02, sparse_reward=0)
-    elif variant == "fast_trig":
-        kw.update(fast_trig=1, sparse_reward=0)
     elif variant == "signs":
         kw.update(ail_left_sign=-1.0, ail_right_sign=1.0, pitch_sign=-1.0, freestream_3d=0, cd90_degrees=0)
     wind = None
