@@ -49,7 +49,12 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU per launch")
-    ap.add_argument("--workload", choices=["physics_only", "waypoints_v3"], default="physics_only")
+    ap.add_argument("--workload", choices=["physics_only", "waypoints_v3", "ppo"], default="physics_only",
+                    help="ppo = BASELINE configs[2]: PPO Fixedwing-Waypoints rollout+update (a step is one PPO iteration)")
+    ap.add_argument("--ppo-envs", type=int, default=4096)
+    ap.add_argument("--ppo-n-steps", type=int, default=128)
+    ap.add_argument("--ppo-minibatches", type=int, default=4)
+    ap.add_argument("--ppo-epochs", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -304,6 +309,54 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.destroy_process_group()
 
 
+def run_ppo(args, rank: int, local_rank: int, world: int):
+    """BASELINE configs[2]: PPO on Fixedwing-Waypoints (train_Fixedwing_Waypoints_v3 hyper-parameters, scaled
+    variant B of SURVEY 8d: n_steps 128, 4 minibatches per epoch).  A step = one rollout + one update."""
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from pyflyt_drone_b200.ppo import PPO
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    N, T = args.ppo_envs, args.ppo_n_steps
+    env = FixedwingVecEnv(N, preset="waypoints_v3", device=local_rank, seed=42, env_id0=rank * N)
+    model = PPO("MlpPolicy", env, learning_rate=3e-4, n_steps=T, batch_size=N * T // args.ppo_minibatches,
+                n_epochs=args.ppo_epochs, gamma=0.99, gae_lambda=0.95, clip_range=0.2, ent_coef=0.001, vf_coef=0.5,
+                max_grad_norm=0.5, seed=42)
+    K, W = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    model.learn(W * N * T * world)
+    model.stats.__init__()
+    l0 = env.launch_count
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    model.learn(K * N * T * world)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    if rank == 0:
+        st = model.stats
+        line = {"metric": "ppo_env_steps_per_sec", "value": K * N * T * world / dt, "unit": "env-steps/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "ppo: Fixedwing-Waypoints-v3 PPO rollout+update (BASELINE configs[2])",
+                           "envs_per_gpu": N, "n_steps": T, "minibatches_per_epoch": args.ppo_minibatches,
+                           "n_epochs": args.ppo_epochs, "rollout_s": st.rollout_s, "update_s": st.update_s,
+                           "rollout_env_steps_per_sec": st.env_steps / max(st.rollout_s, 1e-9),
+                           "update": "torch autograd on a flat parameter vector (library GEMMs)"},
+                "gpu_launches": int(env.launch_count - l0)}
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -311,6 +364,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "ppo":
+        run_ppo(args, rank, local_rank, world)
         return
     run_ours(args, rank, local_rank, world)
 

@@ -1,0 +1,72 @@
+/*
+ * fwppo.h -- C ABI of the PPO rollout kernels in libfwsim.so.
+ *
+ * These replace, for the whole env batch at once and without leaving HBM, what the reference obtains from
+ * stable_baselines3 around its env (train/train_Fixedwing_Waypoints_v3.py:260,293-337):
+ *   VecNormalize (obs / reward running moments, normalise + clip)   -> ppo_moments_update, ppo_reward_normalize
+ *   MlpPolicy forward (separate pi / vf towers 64-64 tanh, diagonal Gaussian, action clip)
+ *                                                                     -> ppo_policy_forward, ppo_value_forward
+ *   time-limit bootstrap r += gamma * V(terminal_obs)               -> ppo_timeout_bootstrap
+ *   RolloutBuffer.compute_returns_and_advantage (GAE)                -> ppo_gae
+ * Same conventions as fwsim.h: 0 = OK, negative = error, fw_last_error() for the message; all pointers are
+ * DEVICE pointers owned by the caller (torch tensors); work is enqueued on the caller's stream.
+ *
+ * Parameter vector layout (fp32, contiguous), H = 64 hidden units, D = obs_dim, A = 4 actions:
+ *   pi.W1[H,D] pi.b1[H] pi.W2[H,H] pi.b2[H] pi.W3[A,H] pi.b3[A]
+ *   vf.W1[H,D] vf.b1[H] vf.W2[H,H] vf.b2[H] vf.W3[1,H] vf.b3[1]  log_std[A]
+ * (row-major [out,in], i.e. torch.nn.Linear.weight), 12,361 floats for D = 28.
+ */
+#ifndef FWPPO_H
+#define FWPPO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPO_HIDDEN 64
+#define PPO_ACT 4
+#define PPO_MAX_OBS 32
+
+/* number of floats in the parameter vector for observation width d */
+int ppo_param_count(int32_t d);
+
+/* RunningMeanStd.update (batch-parallel Chan merge): x [n,d] fp32; stats = double[2*d+1] = mean[d], var[d], count.
+ * scratch: device doubles, at least 2*d+2, zero on first use (the call leaves it zeroed).
+ * accum (may be NULL): double[2*d+1] receiving += column sums, sums of squares and n -- the raw batch moments a
+ * multi-GPU run all-reduces once per rollout to reconcile the per-rank running statistics exactly. */
+int ppo_moments_update(const float* x, int32_t n, int32_t d, double* stats, double* scratch, double* accum,
+                       void* stream);
+
+/* Policy + value forward for n rows.  obs_raw [n,d]; obs_stats as above (NULL = no normalisation);
+ * writes obs_norm [n,d] (what the policy saw; may be NULL), act_env [n,4] (clipped to [-1,1], what the env
+ * gets), act_raw [n,4] (unclipped sample, what the rollout buffer stores), logp [n], value [n].
+ * Noise: Philox keyed (seed, env_id0 + row, step).  deterministic != 0 -> action = mean. */
+int ppo_policy_forward(const float* params, int32_t d, const float* obs_raw, const double* obs_stats, float clip_obs,
+                       int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step, int32_t deterministic,
+                       float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, void* stream);
+
+/* Value tower only (last_values of a rollout). */
+int ppo_value_forward(const float* params, int32_t d, const float* obs_raw, const double* obs_stats, float clip_obs,
+                      int32_t n, float* value, void* stream);
+
+/* VecNormalize reward path: ret = ret*gamma + r; ret_rms.update(ret); r_norm = clip(r / sqrt(var + eps), +-clip);
+ * ret[done] = 0.  flags are the env's flag bytes; done_out [n] receives 1.0/0.0.  ret_stats = double[3]
+ * (mean, var, count); scratch = double[3] zero on first use; accum (may be NULL) = double[3] raw sums as above. */
+int ppo_reward_normalize(const float* rew, const uint8_t* flags, int32_t n, float gamma, float clip_rew,
+                         float* ret, double* ret_stats, double* scratch, double* accum, float* rew_norm,
+                         float* done_out, void* stream);
+
+/* SB3 collect_rollouts: for envs that were truncated but not terminated, rew += gamma * V(terminal_obs). */
+int ppo_timeout_bootstrap(const float* params, int32_t d, const float* term_obs_raw, const double* obs_stats,
+                          float clip_obs, const uint8_t* flags, int32_t n, float gamma, float* rew_inout, void* stream);
+
+/* GAE over a [T,n] rollout: rewards, values, dones (done after step t), last_values [n] -> advantages, returns. */
+int ppo_gae(const float* rewards, const float* values, const float* dones, const float* last_values, int32_t T,
+            int32_t n, float gamma, float lam, float* advantages, float* returns, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,22 @@
+"""ctypes signatures of the PPO rollout kernels (include/fwppo.h)."""
+import ctypes as C
+
+_P = C.c_void_p
+_F = C.c_float
+PPO_SYMBOLS = [
+    ("ppo_param_count", C.c_int, [C.c_int32]),
+    ("ppo_moments_update", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    ("ppo_policy_forward", C.c_int, [_P, C.c_int32, _P, _P, _F, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32,
+                                     _P, _P, _P, _P, _P, _P]),
+    ("ppo_value_forward", C.c_int, [_P, C.c_int32, _P, _P, _F, C.c_int32, _P, _P]),
+    ("ppo_reward_normalize", C.c_int, [_P, _P, C.c_int32, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
+    ("ppo_timeout_bootstrap", C.c_int, [_P, C.c_int32, _P, _P, _F, _P, C.c_int32, _F, _P, _P]),
+    ("ppo_gae", C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _F, _F, _P, _P, _P]),
+]
+
+
+def bind(lib) -> None:
+    for name, res, args in PPO_SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args

@@ -46,6 +46,9 @@ struct FwSim {
     bool fresh;   // true until the state created by fw_create has been stepped or overwritten
 };
 
+// shared with ppo_api.cu so that fw_last_error() reports PPO kernel errors too
+extern "C" void fw_set_last_error_(const char* msg) { g_err = msg ? msg : ""; }
+
 extern "C" int fw_abi_version(void) { return FW_ABI_VERSION; }
 extern "C" const char* fw_last_error(void) { return g_err.c_str(); }
 extern "C" int fw_config_size(void) { return (int)sizeof(FwConfig); }

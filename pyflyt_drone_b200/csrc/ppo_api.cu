@@ -1,0 +1,102 @@
+// ppo_api.cu -- C ABI of the PPO rollout kernels (include/fwppo.h).  Thin argument checking over ppo_kernels.cu.
+#include "../../include/fwppo.h"
+#include "../../include/fwsim.h"
+#include "ppo_kernels.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+
+// error string shared with fw_api.cu through fw_last_error(): set via this hook
+extern "C" void fw_set_last_error_(const char* msg);
+
+static int pfail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    fw_set_last_error_(buf);
+    return code;
+}
+
+#define PCU(call)                                                                               \
+    do {                                                                                        \
+        cudaError_t _e = (call);                                                                \
+        if (_e != cudaSuccess) return pfail(FW_ECUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
+    } while (0)
+
+static int check_d(int d) {
+    if (d < 1 || d > PPO_MAX_OBS) return pfail(FW_EINVAL, "obs width %d out of range [1,%d]", d, PPO_MAX_OBS);
+    return FW_OK;
+}
+
+extern "C" int ppo_param_count(int32_t d) {
+    const int H = PPO_HIDDEN, A = PPO_ACT;
+    return (H * d + H + H * H + H + A * H + A) + (H * d + H + H * H + H + H + 1) + A;
+}
+
+extern "C" int ppo_moments_update(const float* x, int32_t n, int32_t d, double* stats, double* scratch, double* accum,
+                                  void* stream) {
+    if (!x || !stats || !scratch) return pfail(FW_EINVAL, "null argument");
+    if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
+    int rc = check_d(d);
+    if (rc) return rc;
+    PCU(ppok_moments(x, n, d, stats, scratch, accum, (cudaStream_t)stream));
+    return FW_OK;
+}
+
+extern "C" int ppo_policy_forward(const float* params, int32_t d, const float* obs_raw, const double* obs_stats,
+                                  float clip_obs, int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step,
+                                  int32_t deterministic, float* obs_norm, float* act_env, float* act_raw, float* logp,
+                                  float* value, void* stream) {
+    if (!params || !obs_raw || !act_env || !value) return pfail(FW_EINVAL, "null argument");
+    if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
+    int rc = check_d(d);
+    if (rc) return rc;
+    if ((reinterpret_cast<uintptr_t>(act_env) & 15u) || (act_raw && (reinterpret_cast<uintptr_t>(act_raw) & 15u)))
+        return pfail(FW_EINVAL, "action buffers must be 16-byte aligned");
+    PCU(ppok_forward(params, d, obs_raw, obs_stats, clip_obs, n, seed, env_id0, step, deterministic, obs_norm, act_env,
+                     act_raw, logp, value, 1, (cudaStream_t)stream));
+    return FW_OK;
+}
+
+extern "C" int ppo_value_forward(const float* params, int32_t d, const float* obs_raw, const double* obs_stats,
+                                 float clip_obs, int32_t n, float* value, void* stream) {
+    if (!params || !obs_raw || !value) return pfail(FW_EINVAL, "null argument");
+    if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
+    int rc = check_d(d);
+    if (rc) return rc;
+    PCU(ppok_forward(params, d, obs_raw, obs_stats, clip_obs, n, 0, 0, 0, 1, nullptr, nullptr, nullptr, nullptr, value, 0,
+                     (cudaStream_t)stream));
+    return FW_OK;
+}
+
+extern "C" int ppo_reward_normalize(const float* rew, const uint8_t* flags, int32_t n, float gamma, float clip_rew,
+                                    float* ret, double* ret_stats, double* scratch, double* accum, float* rew_norm,
+                                    float* done_out, void* stream) {
+    if (!rew || !flags || !ret || !ret_stats || !scratch || !rew_norm) return pfail(FW_EINVAL, "null argument");
+    if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
+    PCU(ppok_reward_normalize(rew, flags, n, gamma, clip_rew, ret, ret_stats, scratch, accum, rew_norm, done_out,
+                              (cudaStream_t)stream));
+    return FW_OK;
+}
+
+extern "C" int ppo_timeout_bootstrap(const float* params, int32_t d, const float* term_obs_raw, const double* obs_stats,
+                                     float clip_obs, const uint8_t* flags, int32_t n, float gamma, float* rew_inout,
+                                     void* stream) {
+    if (!params || !term_obs_raw || !flags || !rew_inout) return pfail(FW_EINVAL, "null argument");
+    if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
+    int rc = check_d(d);
+    if (rc) return rc;
+    PCU(ppok_bootstrap(params, d, term_obs_raw, obs_stats, clip_obs, flags, n, gamma, rew_inout, (cudaStream_t)stream));
+    return FW_OK;
+}
+
+extern "C" int ppo_gae(const float* rewards, const float* values, const float* dones, const float* last_values, int32_t T,
+                       int32_t n, float gamma, float lam, float* advantages, float* returns, void* stream) {
+    if (!rewards || !values || !dones || !last_values || !advantages || !returns) return pfail(FW_EINVAL, "null argument");
+    if (T <= 0 || n <= 0) return pfail(FW_EINVAL, "T and n must be positive");
+    PCU(ppok_gae(rewards, values, dones, last_values, T, n, gamma, lam, advantages, returns, (cudaStream_t)stream));
+    return FW_OK;
+}

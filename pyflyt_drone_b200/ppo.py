@@ -1,0 +1,384 @@
+"""PPO on device tensors around FixedwingVecEnv -- the training seam of the reference's scripts.
+
+Mirrors the reference's use of stable_baselines3 (train/train_Fixedwing_Waypoints_v3.py:260,293-337):
+``VecNormalize(env, norm_obs=True, norm_reward=True, clip_obs=10)`` then
+``PPO("MlpPolicy", env, learning_rate, n_steps, batch_size, n_epochs, gamma, gae_lambda, clip_range, ent_coef,
+vf_coef, max_grad_norm, seed, device).learn(total_timesteps)``.
+
+Rollout path (every agent step, no host sync): hand-written kernels of libfwsim.so --
+running moments (ppo_moments_update), policy/value forward + Gaussian sampling (ppo_policy_forward), env step
+(fw_step), reward normalisation (ppo_reward_normalize), time-limit bootstrap (ppo_timeout_bootstrap), and GAE
+(ppo_gae) once per rollout.  The minibatch update uses torch autograd on one flat parameter vector (library
+GEMMs: the layers are 28/64 wide, far below tensor-core efficiency either way) whose gradient is a single
+contiguous buffer -- exactly what the one collective of the path, the NCCL gradient all-reduce, wants.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import time
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from .vec_env import FixedwingVecEnv
+
+H, A = 64, 4
+
+
+def _p(t: torch.Tensor | None):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(int(torch.cuda.current_stream().cuda_stream))
+
+
+class FlatMlpPolicy:
+    """SB3 ``MlpPolicy`` (separate pi / vf towers [64, 64], tanh, state-independent log_std) stored as ONE flat
+    fp32 parameter vector in the layout of include/fwppo.h."""
+
+    def __init__(self, obs_dim: int, device: torch.device, seed: int = 0):
+        self.d = int(obs_dim)
+        self.device = device
+        lib = _lib.load()
+        self.count = int(lib.ppo_param_count(self.d))
+        shapes = [("pi.0.weight", (H, self.d)), ("pi.0.bias", (H,)), ("pi.2.weight", (H, H)), ("pi.2.bias", (H,)),
+                  ("action_net.weight", (A, H)), ("action_net.bias", (A,)),
+                  ("vf.0.weight", (H, self.d)), ("vf.0.bias", (H,)), ("vf.2.weight", (H, H)), ("vf.2.bias", (H,)),
+                  ("value_net.weight", (1, H)), ("value_net.bias", (1,)), ("log_std", (A,))]
+        self.slices, off = {}, 0
+        for name, shp in shapes:
+            n = int(np.prod(shp))
+            self.slices[name] = (off, off + n, shp)
+            off += n
+        assert off == self.count, (off, self.count)
+        g = torch.Generator(device="cpu").manual_seed(int(seed))
+        flat = torch.zeros(self.count, dtype=torch.float32)
+        gains = {"pi.0.weight": math.sqrt(2), "pi.2.weight": math.sqrt(2), "vf.0.weight": math.sqrt(2),
+                 "vf.2.weight": math.sqrt(2), "action_net.weight": 0.01, "value_net.weight": 1.0}
+        for name, (a, b, shp) in self.slices.items():
+            if name in gains:       # SB3 ActorCriticPolicy: orthogonal init, biases zero, log_std_init = 0
+                w = torch.empty(shp)
+                torch.nn.init.orthogonal_(w, gain=gains[name], generator=g)
+                flat[a:b] = w.reshape(-1)
+        self.theta = torch.nn.Parameter(flat.to(device))
+
+    def view(self, name: str, theta: torch.Tensor | None = None) -> torch.Tensor:
+        a, b, shp = self.slices[name]
+        return (self.theta if theta is None else theta)[a:b].view(shp)
+
+    def state_dict(self) -> dict[str, torch.Tensor]:
+        """Parameters under SB3's ActorCriticPolicy names (mlp_extractor.policy_net.{0,2}, action_net, ...)."""
+        m = {"pi.0": "mlp_extractor.policy_net.0", "pi.2": "mlp_extractor.policy_net.2", "vf.0": "mlp_extractor.value_net.0",
+             "vf.2": "mlp_extractor.value_net.2"}
+        out = {}
+        for name in self.slices:
+            base, _, leaf = name.rpartition(".")
+            key = f"{m[base]}.{leaf}" if base in m else name
+            out[key] = self.view(name).detach().clone()
+        return out
+
+    def load_state_dict(self, sd: dict[str, torch.Tensor]) -> None:
+        m = {"mlp_extractor.policy_net.0": "pi.0", "mlp_extractor.policy_net.2": "pi.2",
+             "mlp_extractor.value_net.0": "vf.0", "mlp_extractor.value_net.2": "vf.2"}
+        with torch.no_grad():
+            for key, val in sd.items():
+                base, _, leaf = key.rpartition(".")
+                name = f"{m[base]}.{leaf}" if base in m else key
+                if name in self.slices:
+                    self.view(name).copy_(val.to(self.device))
+
+    # ---- torch reference of the two towers (used by the update and by the tests as the fp32 reference)
+    def towers(self, obs_norm: torch.Tensor, theta: torch.Tensor | None = None):
+        v = lambda n: self.view(n, theta)  # noqa: E731
+        h = torch.tanh(torch.addmm(v("pi.0.bias"), obs_norm, v("pi.0.weight").t()))
+        h = torch.tanh(torch.addmm(v("pi.2.bias"), h, v("pi.2.weight").t()))
+        mean = torch.addmm(v("action_net.bias"), h, v("action_net.weight").t())
+        g = torch.tanh(torch.addmm(v("vf.0.bias"), obs_norm, v("vf.0.weight").t()))
+        g = torch.tanh(torch.addmm(v("vf.2.bias"), g, v("vf.2.weight").t()))
+        value = torch.addmm(v("value_net.bias"), g, v("value_net.weight").t()).squeeze(-1)
+        return mean, value
+
+    def evaluate_actions(self, obs_norm: torch.Tensor, actions: torch.Tensor):
+        mean, value = self.towers(obs_norm)
+        log_std = self.view("log_std")
+        z = (actions - mean) * torch.exp(-log_std)
+        logp = (-0.5 * z * z - log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + log_std).sum().expand_as(logp)
+        return value, logp, entropy
+
+
+class DeviceVecNormalize:
+    """stable_baselines3 ``VecNormalize`` statistics kept on the device in float64 (RunningMeanStd(eps=1e-4))."""
+
+    def __init__(self, obs_dim: int, num_envs: int, device: torch.device, norm_obs: bool = True, norm_reward: bool = True,
+                 clip_obs: float = 10.0, clip_reward: float = 10.0, gamma: float = 0.99, training: bool = True):
+        self.d, self.n = obs_dim, num_envs
+        self.norm_obs, self.norm_reward, self.training = norm_obs, norm_reward, training
+        self.clip_obs, self.clip_reward, self.gamma = float(clip_obs), float(clip_reward), float(gamma)
+        f64 = dict(dtype=torch.float64, device=device)
+        self.obs_stats = torch.cat([torch.zeros(obs_dim, **f64), torch.ones(obs_dim, **f64), torch.full((1,), 1e-4, **f64)])
+        self.ret_stats = torch.tensor([0.0, 1.0, 1e-4], **f64)
+        self.ret = torch.zeros(num_envs, dtype=torch.float32, device=device)
+        self.obs_scratch = torch.zeros(2 * obs_dim + 2, **f64)
+        self.ret_scratch = torch.zeros(4, **f64)
+        # raw batch sums since the last cross-rank sync (multi-GPU reconciliation), and the stats at that sync
+        self.obs_accum = torch.zeros(2 * obs_dim + 1, **f64)
+        self.ret_accum = torch.zeros(3, **f64)
+        self.obs_base = self.obs_stats.clone()
+        self.ret_base = self.ret_stats.clone()
+
+    def state_dict(self) -> dict:
+        d = self.d
+        return {"obs_rms.mean": self.obs_stats[:d].cpu().numpy(), "obs_rms.var": self.obs_stats[d:2 * d].cpu().numpy(),
+                "obs_rms.count": float(self.obs_stats[2 * d]), "ret_rms.mean": float(self.ret_stats[0]),
+                "ret_rms.var": float(self.ret_stats[1]), "ret_rms.count": float(self.ret_stats[2]),
+                "clip_obs": self.clip_obs, "clip_reward": self.clip_reward, "gamma": self.gamma,
+                "norm_obs": self.norm_obs, "norm_reward": self.norm_reward}
+
+    def load_state_dict(self, sd: dict) -> None:
+        d = self.d
+        dev = self.obs_stats.device
+        self.obs_stats[:d] = torch.as_tensor(sd["obs_rms.mean"], dtype=torch.float64, device=dev)
+        self.obs_stats[d:2 * d] = torch.as_tensor(sd["obs_rms.var"], dtype=torch.float64, device=dev)
+        self.obs_stats[2 * d] = float(sd["obs_rms.count"])
+        self.ret_stats[:] = torch.tensor([sd["ret_rms.mean"], sd["ret_rms.var"], sd["ret_rms.count"]], dtype=torch.float64)
+        self.obs_base.copy_(self.obs_stats); self.ret_base.copy_(self.ret_stats)
+        self.obs_accum.zero_(); self.ret_accum.zero_()
+
+    @staticmethod
+    def _merge(base: torch.Tensor, accum: torch.Tensor, d: int) -> torch.Tensor:
+        """base (mean, var, count) merged with raw sums (sum, sumsq, n) -- Chan et al., in float64."""
+        n = accum[2 * d]
+        if float(n) <= 0:
+            return base.clone()
+        bmean = accum[:d] / n
+        bvar = (accum[d:2 * d] / n - bmean * bmean).clamp_min(0.0)
+        mean, var, count = base[:d], base[d:2 * d], base[2 * d]
+        tot = count + n
+        delta = bmean - mean
+        out = base.clone()
+        out[:d] = mean + delta * n / tot
+        out[d:2 * d] = (var * count + bvar * n + delta * delta * count * n / tot) / tot
+        out[2 * d] = tot
+        return out
+
+    def sync_across_ranks(self) -> None:
+        """Exact reconciliation of the per-rank running statistics: all-reduce the raw batch sums accumulated
+        since the last sync and re-apply them to the common base (a 0.5 KB collective once per rollout)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            self.obs_base.copy_(self.obs_stats); self.ret_base.copy_(self.ret_stats)
+            self.obs_accum.zero_(); self.ret_accum.zero_()
+            return
+        buf = torch.cat([self.obs_accum, self.ret_accum])
+        dist.all_reduce(buf)
+        self.obs_stats.copy_(self._merge(self.obs_base, buf[: 2 * self.d + 1], self.d))
+        self.ret_stats.copy_(self._merge(self.ret_base, buf[2 * self.d + 1:], 1))
+        self.obs_base.copy_(self.obs_stats); self.ret_base.copy_(self.ret_stats)
+        self.obs_accum.zero_(); self.ret_accum.zero_()
+
+
+@dataclass
+class RolloutStats:
+    env_steps: int = 0
+    rollout_s: float = 0.0
+    update_s: float = 0.0
+
+
+class PPO:
+    """Keyword-compatible with the reference's ``PPO("MlpPolicy", env, ...)`` call
+    (train/train_Fixedwing_Waypoints_v3.py:293-310); ``env`` is a FixedwingVecEnv."""
+
+    def __init__(self, policy: str, env: FixedwingVecEnv, learning_rate: float = 3e-4, n_steps: int = 2048,
+                 batch_size: int = 64, n_epochs: int = 10, gamma: float = 0.99, gae_lambda: float = 0.95,
+                 clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
+                 seed: int = 0, device: str | torch.device | None = None, verbose: int = 0, tensorboard_log=None,
+                 normalize: bool = True, norm_reward: bool = True, clip_obs: float = 10.0):
+        if policy != "MlpPolicy":
+            raise ValueError("only 'MlpPolicy' (the policy the reference trains) is implemented")
+        if not torch.cuda.is_available():
+            raise RuntimeError("PPO rollouts run on CUDA kernels of libfwsim.so; no CUDA device is visible")
+        self.env = env
+        self.device = torch.device("cuda", env.device_index)
+        self.lib = _lib.load()
+        self.n_envs, self.d = env.num_envs, env.obs_dim
+        self.n_steps, self.batch_size, self.n_epochs = int(n_steps), int(batch_size), int(n_epochs)
+        self.gamma, self.gae_lambda, self.clip_range = float(gamma), float(gae_lambda), float(clip_range)
+        self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), float(max_grad_norm)
+        self.seed, self.verbose = int(seed), verbose
+        self.policy = FlatMlpPolicy(self.d, self.device, seed=seed)
+        self.optimizer = torch.optim.Adam([self.policy.theta], lr=learning_rate, eps=1e-5)   # SB3 default eps
+        self.vecnorm = DeviceVecNormalize(self.d, self.n_envs, self.device, norm_obs=normalize,
+                                          norm_reward=normalize and norm_reward, clip_obs=clip_obs, gamma=gamma)
+        T, N, D = self.n_steps, self.n_envs, self.d
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.buf = dict(obs=torch.zeros((T, N, D), **f32), act=torch.zeros((T, N, A), **f32),
+                        rew=torch.zeros((T, N), **f32), done=torch.zeros((T, N), **f32), val=torch.zeros((T, N), **f32),
+                        logp=torch.zeros((T, N), **f32), adv=torch.zeros((T, N), **f32), ret=torch.zeros((T, N), **f32))
+        self.act_env = torch.zeros((N, A), **f32)
+        self.last_values = torch.zeros(N, **f32)
+        self.num_timesteps = 0
+        self._global_step = 0
+        self._obs = None               # raw observation tensor (view of the env's persistent buffer)
+        self._gen = torch.Generator(device=self.device).manual_seed(seed)
+        self.stats = RolloutStats()
+        self.world = 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.world = dist.get_world_size()
+                dist.broadcast(self.policy.theta.data, src=0)          # one ncclBroadcast of the initial weights
+        except Exception:
+            self.world = 1
+
+    # ------------------------------------------------------------------ kernels
+    def _stats_ptr(self):
+        return _p(self.vecnorm.obs_stats) if self.vecnorm.norm_obs else None
+
+    def _update_obs_moments(self, obs_raw: torch.Tensor) -> None:
+        vn = self.vecnorm
+        if vn.norm_obs and vn.training:
+            _lib.check(self.lib.ppo_moments_update(_p(obs_raw), self.n_envs, self.d, _p(vn.obs_stats), _p(vn.obs_scratch),
+                                                   _p(vn.obs_accum), _stream()))
+
+    def _forward(self, obs_raw, t, deterministic=False):
+        b = self.buf
+        _lib.check(self.lib.ppo_policy_forward(
+            _p(self.policy.theta), self.d, _p(obs_raw), self._stats_ptr(), self.vecnorm.clip_obs, self.n_envs, self.seed,
+            self.env.env_id0, self._global_step & 0xFFFFFFFF, int(deterministic), _p(b["obs"][t]), _p(self.act_env),
+            _p(b["act"][t]), _p(b["logp"][t]), _p(b["val"][t]), _stream()))
+
+    def collect_rollouts(self) -> None:
+        env, vn, b = self.env, self.vecnorm, self.buf
+        if self._obs is None:
+            self._obs = env.reset_tensor()
+            vn.ret.zero_()
+            self._update_obs_moments(self._obs)
+        for t in range(self.n_steps):
+            self._forward(self._obs, t)
+            obs, rew, flags, term = env.step_tensor(self.act_env, want_terminal_obs=True)
+            self._update_obs_moments(obs)
+            if vn.norm_reward:
+                _lib.check(self.lib.ppo_reward_normalize(_p(rew), _p(flags), self.n_envs, vn.gamma, vn.clip_reward, _p(vn.ret),
+                                                         _p(vn.ret_stats), _p(vn.ret_scratch), _p(vn.ret_accum),
+                                                         _p(b["rew"][t]), _p(b["done"][t]), _stream()))
+            else:
+                b["rew"][t].copy_(rew)
+                b["done"][t].copy_((flags & 3) != 0)
+            _lib.check(self.lib.ppo_timeout_bootstrap(_p(self.policy.theta), self.d, _p(term), self._stats_ptr(), vn.clip_obs,
+                                                      _p(flags), self.n_envs, self.gamma, _p(b["rew"][t]), _stream()))
+            self._obs = obs
+            self._global_step += 1
+        _lib.check(self.lib.ppo_value_forward(_p(self.policy.theta), self.d, _p(self._obs), self._stats_ptr(), vn.clip_obs,
+                                              self.n_envs, _p(self.last_values), _stream()))
+        _lib.check(self.lib.ppo_gae(_p(b["rew"]), _p(b["val"]), _p(b["done"]), _p(self.last_values), self.n_steps,
+                                    self.n_envs, self.gamma, self.gae_lambda, _p(b["adv"]), _p(b["ret"]), _stream()))
+        self.num_timesteps += self.n_steps * self.n_envs * self.world
+
+    # ------------------------------------------------------------------ update (torch autograd on the flat vector)
+    def train(self) -> dict:
+        b = self.buf
+        T, N, D = self.n_steps, self.n_envs, self.d
+        total = T * N
+        obs, act = b["obs"].view(total, D), b["act"].view(total, A)
+        val, logp_old = b["val"].view(total), b["logp"].view(total)
+        adv, ret = b["adv"].view(total), b["ret"].view(total)
+        bs = min(self.batch_size, total)
+        theta = self.policy.theta
+        info = {}
+        for _ in range(self.n_epochs):
+            perm = torch.randperm(total, device=self.device, generator=self._gen)
+            for s in range(0, total, bs):
+                idx = perm[s:s + bs]
+                a = adv[idx]
+                if len(idx) > 1:
+                    a = (a - a.mean()) / (a.std() + 1e-8)
+                values, logp, entropy = self.policy.evaluate_actions(obs[idx], act[idx])
+                ratio = torch.exp(logp - logp_old[idx])
+                pl = -torch.min(a * ratio, a * torch.clamp(ratio, 1 - self.clip_range, 1 + self.clip_range)).mean()
+                vl = torch.nn.functional.mse_loss(ret[idx], values)
+                el = -entropy.mean()
+                loss = pl + self.ent_coef * el + self.vf_coef * vl
+                self.optimizer.zero_grad(set_to_none=False)
+                loss.backward()
+                if self.world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(theta.grad)                       # the path's one collective: 49 KB over NVLink
+                    theta.grad.div_(self.world)
+                torch.nn.utils.clip_grad_norm_([theta], self.max_grad_norm)
+                self.optimizer.step()
+        info.update(policy_loss=float(pl.detach()), value_loss=float(vl.detach()), loss=float(loss.detach()))
+        return info
+
+    def learn(self, total_timesteps: int, log_interval: int = 1, callback=None, progress_bar: bool = False,
+              reset_num_timesteps: bool = True) -> "PPO":
+        if reset_num_timesteps:
+            self.num_timesteps = 0
+        it = 0
+        while self.num_timesteps < total_timesteps:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            self.collect_rollouts()
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            self.vecnorm.sync_across_ranks()
+            info = self.train()
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            self.stats.env_steps += self.n_steps * self.n_envs * self.world
+            self.stats.rollout_s += t1 - t0
+            self.stats.update_s += t2 - t1
+            it += 1
+            if self.verbose and it % log_interval == 0:
+                ep = self.env.episode_stats()
+                n = max(ep["episodes"], 1.0)
+                print(f"[ppo] iter {it} timesteps {self.num_timesteps} sps {self.n_steps * self.n_envs * self.world / (t2 - t0):.3e} "
+                      f"rollout {t1 - t0:.3f}s update {t2 - t1:.3f}s ep_rew_mean {ep['return_sum'] / n:.2f} "
+                      f"ep_len_mean {ep['length_sum'] / n:.1f} targets/ep {ep['targets_reached_sum'] / n:.2f} "
+                      f"loss {info['loss']:.4f}", flush=True)
+            if callback is not None and callback(locals(), globals()) is False:
+                break
+        return self
+
+    # ------------------------------------------------------------------ inference / checkpoint
+    def predict(self, obs_raw: torch.Tensor, deterministic: bool = True) -> torch.Tensor:
+        obs_raw = obs_raw.to(self.device, torch.float32).contiguous()
+        n = obs_raw.shape[0]
+        act = torch.zeros((n, A), dtype=torch.float32, device=self.device)
+        val = torch.zeros(n, dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.ppo_policy_forward(_p(self.policy.theta), self.d, _p(obs_raw), self._stats_ptr(),
+                                               self.vecnorm.clip_obs, n, self.seed, 0, self._global_step & 0xFFFFFFFF,
+                                               int(deterministic), None, _p(act), None, None, _p(val), _stream()))
+        return act
+
+    def save(self, path: str) -> None:
+        torch.save({"policy": self.policy.state_dict(), "optimizer": self.optimizer.state_dict(),
+                    "vecnorm": self.vecnorm.state_dict(), "num_timesteps": self.num_timesteps,
+                    "global_step": self._global_step, "seed": self.seed, "obs_dim": self.d}, path)
+
+    def load(self, path: str) -> "PPO":
+        ck = torch.load(path, map_location=self.device, weights_only=False)
+        self.policy.load_state_dict(ck["policy"])
+        self.optimizer.load_state_dict(ck["optimizer"])
+        self.vecnorm.load_state_dict(ck["vecnorm"])
+        self.num_timesteps, self._global_step = ck["num_timesteps"], ck["global_step"]
+        return self
+
+    def get_parameters(self) -> dict:
+        return {"policy": self.policy.state_dict()}
+
+    def set_parameters(self, params: dict) -> None:
+        self.policy.load_state_dict(params["policy"])
+
+
+def smoke() -> None:
+    """Tiny rollout + update on cuda:0 (called from __graft_entry__.smoke)."""
+    env = FixedwingVecEnv(256, preset="waypoints_v3", seed=3)
+    model = PPO("MlpPolicy", env, n_steps=8, batch_size=512, n_epochs=2, seed=3)
+    model.learn(256 * 8 * 2)
+    assert torch.isfinite(model.policy.theta).all()
+    env.close()

@@ -1,0 +1,94 @@
+"""CPU tests of the PPO host logic, including the world_size-2 gloo paths (gradient all-reduce, statistics sync)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def test_flat_policy_layout_and_sb3_names():
+    from pyflyt_drone_b200.ppo import FlatMlpPolicy
+    pol = FlatMlpPolicy(28, torch.device("cpu"), seed=1)
+    assert pol.count == 12361      # 6,276 + 6,081 + 4
+    sd = pol.state_dict()
+    assert set(sd) == {"mlp_extractor.policy_net.0.weight", "mlp_extractor.policy_net.0.bias",
+                       "mlp_extractor.policy_net.2.weight", "mlp_extractor.policy_net.2.bias",
+                       "mlp_extractor.value_net.0.weight", "mlp_extractor.value_net.0.bias",
+                       "mlp_extractor.value_net.2.weight", "mlp_extractor.value_net.2.bias",
+                       "action_net.weight", "action_net.bias", "value_net.weight", "value_net.bias", "log_std"}
+    w = sd["mlp_extractor.policy_net.2.weight"]
+    assert torch.allclose(w @ w.t(), 2 * torch.eye(64), atol=1e-4)          # orthogonal, gain sqrt(2)
+    assert torch.allclose(sd["action_net.weight"] @ sd["action_net.weight"].t(), 1e-4 * torch.eye(4), atol=1e-6)
+    assert float(sd["log_std"].abs().max()) == 0.0 and float(sd["value_net.bias"].abs().max()) == 0.0
+    pol2 = FlatMlpPolicy(28, torch.device("cpu"), seed=2)
+    pol2.load_state_dict(sd)
+    assert torch.equal(pol2.theta, pol.theta)
+    # evaluate_actions is the diagonal-Gaussian log-prob / entropy of SB3
+    obs, act = torch.randn(5, 28), torch.randn(5, 4)
+    v, lp, ent = pol.evaluate_actions(obs, act)
+    mean, _ = pol.towers(obs)
+    ref = torch.distributions.Normal(mean, torch.ones(4)).log_prob(act).sum(-1)
+    assert torch.allclose(lp, ref, atol=1e-5)
+    assert torch.allclose(ent, torch.distributions.Normal(mean, torch.ones(4)).entropy().sum(-1), atol=1e-5)
+
+
+def test_moment_merge_is_chan():
+    from pyflyt_drone_b200.ppo import DeviceVecNormalize
+    rng = np.random.default_rng(0)
+    a, b = rng.normal(3, 2, (500, 4)), rng.normal(-1, 5, (300, 4))
+    base = torch.tensor(np.concatenate([a.mean(0), a.var(0), [500.0]]))
+    acc = torch.tensor(np.concatenate([b.sum(0), (b * b).sum(0), [300.0]]))
+    out = DeviceVecNormalize._merge(base, acc, 4).numpy()
+    both = np.concatenate([a, b])
+    assert np.allclose(out[:4], both.mean(0)) and np.allclose(out[4:8], both.var(0)) and out[8] == 800
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pyflyt_drone_b200.ppo import DeviceVecNormalize, FlatMlpPolicy
+    dev = torch.device("cpu")
+    # statistics sync: each rank accumulated its own batch; after the sync both hold the pooled moments
+    rng = np.random.default_rng(10 + rank)
+    x = rng.normal(rank * 3.0, 1.0 + rank, (400, 28))
+    vn = DeviceVecNormalize(28, 8, dev)
+    vn.obs_accum[:28] = torch.tensor(x.sum(0)); vn.obs_accum[28:56] = torch.tensor((x * x).sum(0)); vn.obs_accum[56] = 400
+    r = rng.normal(0, 2 + rank, 400)
+    vn.ret_accum[:] = torch.tensor([r.sum(), (r * r).sum(), 400.0])
+    vn.sync_across_ranks()
+    # gradient all-reduce: mean of per-rank gradients == gradient of the pooled batch (equal shard sizes)
+    pol = FlatMlpPolicy(28, dev, seed=0)
+    dist.broadcast(pol.theta.data, src=0)
+    g = torch.Generator().manual_seed(5)
+    obs, act = torch.randn(64, 28, generator=g), torch.randn(64, 4, generator=g)
+    sl = slice(rank * 32, (rank + 1) * 32)
+    v, lp, _ = pol.evaluate_actions(obs[sl], act[sl])
+    (lp.mean() + v.pow(2).mean()).backward()
+    dist.all_reduce(pol.theta.grad); pol.theta.grad.div_(world)
+    if rank == 0:
+        pol_full = FlatMlpPolicy(28, dev, seed=0)
+        v, lp, _ = pol_full.evaluate_actions(obs, act)
+        (lp.mean() + v.pow(2).mean()).backward()
+        torch.save({"obs_stats": vn.obs_stats, "ret_stats": vn.ret_stats, "grad": pol.theta.grad,
+                    "grad_full": pol_full.theta.grad}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_allreduce_and_stats_sync(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = torch.load(out, weights_only=False)
+    assert torch.allclose(res["grad"], res["grad_full"], atol=1e-6)
+    xs = [np.random.default_rng(10 + r).normal(r * 3.0, 1.0 + r, (400, 28)) for r in range(2)]
+    pooled = np.concatenate(xs)
+    st = res["obs_stats"].numpy()
+    assert np.allclose(st[:28], pooled.mean(0), atol=1e-3) and np.allclose(st[28:56], pooled.var(0), rtol=1e-3)
+    assert st[56] == pytest.approx(800 + 1e-4)
