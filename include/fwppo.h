@@ -42,10 +42,23 @@ int ppo_moments_update(const float* x, int32_t n, int32_t d, double* stats, doub
 /* Policy + value forward for n rows.  obs_raw [n,d]; obs_stats as above (NULL = no normalisation);
  * writes obs_norm [n,d] (what the policy saw; may be NULL), act_env [n,4] (clipped to [-1,1], what the env
  * gets), act_raw [n,4] (unclipped sample, what the rollout buffer stores), logp [n], value [n].
- * Noise: Philox keyed (seed, env_id0 + row, step).  deterministic != 0 -> action = mean. */
+ * Noise: Philox keyed (seed, env_id0 + row, step + *step_dev); step_dev (may be NULL) is a device counter so
+ * that a captured CUDA graph of a whole rollout draws fresh noise on every replay.
+ * deterministic != 0 -> action = mean. */
 int ppo_policy_forward(const float* params, int32_t d, const float* obs_raw, const double* obs_stats, float clip_obs,
-                       int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step, int32_t deterministic,
-                       float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, void* stream);
+                       int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev,
+                       int32_t deterministic, float* obs_norm, float* act_env, float* act_raw, float* logp,
+                       float* value, void* stream);
+
+/* Same contract as ppo_policy_forward, computed on the tcgen05 tensor cores (TF32 inputs, fp32 accumulate in
+ * TMEM; csrc/ppo_tc.cu): the hidden layers of both towers are 128x32x64 and 128x64x64 UMMA tiles per 128 envs. */
+int ppo_policy_forward_tc(const float* params, int32_t d, const float* obs_raw, const double* obs_stats, float clip_obs,
+                          int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev,
+                          int32_t deterministic, float* obs_norm, float* act_env, float* act_raw, float* logp,
+                          float* value, void* stream);
+
+/* counter[0] += inc on the device (one node of the rollout graph). */
+int ppo_counter_add(uint32_t* counter, uint32_t inc, void* stream);
 
 /* Value tower only (last_values of a rollout). */
 int ppo_value_forward(const float* params, int32_t d, const float* obs_raw, const double* obs_stats, float clip_obs,

@@ -48,16 +48,31 @@ extern "C" int ppo_moments_update(const float* x, int32_t n, int32_t d, double* 
 
 extern "C" int ppo_policy_forward(const float* params, int32_t d, const float* obs_raw, const double* obs_stats,
                                   float clip_obs, int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step,
-                                  int32_t deterministic, float* obs_norm, float* act_env, float* act_raw, float* logp,
-                                  float* value, void* stream) {
+                                  const uint32_t* step_dev, int32_t deterministic, float* obs_norm, float* act_env,
+                                  float* act_raw, float* logp, float* value, void* stream) {
     if (!params || !obs_raw || !act_env || !value) return pfail(FW_EINVAL, "null argument");
     if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
     int rc = check_d(d);
     if (rc) return rc;
     if ((reinterpret_cast<uintptr_t>(act_env) & 15u) || (act_raw && (reinterpret_cast<uintptr_t>(act_raw) & 15u)))
         return pfail(FW_EINVAL, "action buffers must be 16-byte aligned");
-    PCU(ppok_forward(params, d, obs_raw, obs_stats, clip_obs, n, seed, env_id0, step, deterministic, obs_norm, act_env,
-                     act_raw, logp, value, 1, (cudaStream_t)stream));
+    PCU(ppok_forward(params, d, obs_raw, obs_stats, clip_obs, n, seed, env_id0, step, step_dev, deterministic, obs_norm,
+                     act_env, act_raw, logp, value, 1, (cudaStream_t)stream));
+    return FW_OK;
+}
+
+extern "C" int ppo_policy_forward_tc(const float* params, int32_t d, const float* obs_raw, const double* obs_stats,
+                                     float clip_obs, int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step,
+                                     const uint32_t* step_dev, int32_t deterministic, float* obs_norm, float* act_env,
+                                     float* act_raw, float* logp, float* value, void* stream) {
+    if (!params || !obs_raw || !act_env || !value) return pfail(FW_EINVAL, "null argument");
+    if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
+    int rc = check_d(d);
+    if (rc) return rc;
+    if ((reinterpret_cast<uintptr_t>(act_env) & 15u) || (act_raw && (reinterpret_cast<uintptr_t>(act_raw) & 15u)))
+        return pfail(FW_EINVAL, "action buffers must be 16-byte aligned");
+    PCU(ppok_forward_tc(params, d, obs_raw, obs_stats, clip_obs, n, seed, env_id0, step, step_dev, deterministic, obs_norm,
+                        act_env, act_raw, logp, value, (cudaStream_t)stream));
     return FW_OK;
 }
 
@@ -67,8 +82,8 @@ extern "C" int ppo_value_forward(const float* params, int32_t d, const float* ob
     if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
     int rc = check_d(d);
     if (rc) return rc;
-    PCU(ppok_forward(params, d, obs_raw, obs_stats, clip_obs, n, 0, 0, 0, 1, nullptr, nullptr, nullptr, nullptr, value, 0,
-                     (cudaStream_t)stream));
+    PCU(ppok_forward(params, d, obs_raw, obs_stats, clip_obs, n, 0, 0, 0, nullptr, 1, nullptr, nullptr, nullptr, nullptr,
+                     value, 0, (cudaStream_t)stream));
     return FW_OK;
 }
 
@@ -98,5 +113,11 @@ extern "C" int ppo_gae(const float* rewards, const float* values, const float* d
     if (!rewards || !values || !dones || !last_values || !advantages || !returns) return pfail(FW_EINVAL, "null argument");
     if (T <= 0 || n <= 0) return pfail(FW_EINVAL, "T and n must be positive");
     PCU(ppok_gae(rewards, values, dones, last_values, T, n, gamma, lam, advantages, returns, (cudaStream_t)stream));
+    return FW_OK;
+}
+
+extern "C" int ppo_counter_add(uint32_t* counter, uint32_t inc, void* stream) {
+    if (!counter) return pfail(FW_EINVAL, "null argument");
+    PCU(ppok_counter_add(counter, inc, (cudaStream_t)stream));
     return FW_OK;
 }

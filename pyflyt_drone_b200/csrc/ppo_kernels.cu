@@ -128,7 +128,8 @@ __device__ __forceinline__ void stage_stats(const double* __restrict__ stats, in
 __global__ void __launch_bounds__(PPO_FWD_THREADS)
 ppo_forward_kernel(const float* __restrict__ params, int d, const float* __restrict__ obs_raw,
                    const double* __restrict__ stats, float clip, int n, uint32_t seed_lo, uint32_t seed_hi,
-                   uint32_t env_id0, uint32_t step, int deterministic, float* __restrict__ obs_norm,
+                   uint32_t env_id0, uint32_t step, const uint32_t* __restrict__ step_dev, int deterministic,
+                   float* __restrict__ obs_norm,
                    float* __restrict__ act_env, float* __restrict__ act_raw, float* __restrict__ logp,
                    float* __restrict__ value, int want_policy) {
     extern __shared__ __align__(16) float smem[];
@@ -157,7 +158,8 @@ ppo_forward_kernel(const float* __restrict__ params, int d, const float* __restr
     float mean[A];
     tower_forward<A>(s_pi, x, hbuf, mean);
     // diagonal Gaussian: a = mu + sigma * eps ; log pi(a) = sum -0.5 eps^2 - log sigma - 0.5 log 2pi
-    uint4 r = ppo_philox(seed_lo, seed_hi, env_id0 + (uint32_t)row, step, 0u, 7u);
+    const uint32_t step_eff = step + (step_dev != nullptr ? step_dev[0] : 0u);   // device counter: graph-replayable
+    uint4 r = ppo_philox(seed_lo, seed_hi, env_id0 + (uint32_t)row, step_eff, 0u, 7u);
     float ra = sqrtf(-2.0f * __logf(ppo_u01(r.x))), rb = sqrtf(-2.0f * __logf(ppo_u01(r.z)));
     float s0, c0, s1, c1;
     sincospif(2.0f * ppo_u01(r.y), &s0, &c0);
@@ -186,8 +188,9 @@ size_t ppo_forward_smem() {
 }
 
 cudaError_t ppok_forward(const float* params, int d, const float* obs_raw, const double* stats, float clip, int n,
-                         uint64_t seed, uint32_t env_id0, uint32_t step, int deterministic, float* obs_norm,
-                         float* act_env, float* act_raw, float* logp, float* value, int want_policy, cudaStream_t st) {
+                         uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev, int deterministic,
+                         float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, int want_policy,
+                         cudaStream_t st) {
     static bool attr_set = false;
     const size_t sm = ppo_forward_smem();
     if (!attr_set) {
@@ -197,7 +200,7 @@ cudaError_t ppok_forward(const float* params, int d, const float* obs_raw, const
     }
     const int grid = (n + PPO_FWD_THREADS - 1) / PPO_FWD_THREADS;
     ppo_forward_kernel<<<grid, PPO_FWD_THREADS, sm, st>>>(params, d, obs_raw, stats, clip, n, (uint32_t)(seed & 0xffffffffu),
-                                                          (uint32_t)(seed >> 32), env_id0, step, deterministic, obs_norm,
+                                                          (uint32_t)(seed >> 32), env_id0, step, step_dev, deterministic, obs_norm,
                                                           act_env, act_raw, logp, value, want_policy);
     return cudaGetLastError();
 }
@@ -392,5 +395,13 @@ ppo_gae_kernel(const float* __restrict__ rewards, const float* __restrict__ valu
 cudaError_t ppok_gae(const float* rewards, const float* values, const float* dones, const float* last_values, int T, int n,
                      float gamma, float lam, float* adv, float* ret, cudaStream_t st) {
     ppo_gae_kernel<<<(n + 255) / 256, 256, 0, st>>>(rewards, values, dones, last_values, T, n, gamma, lam, adv, ret);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ device-side step counter (CUDA-graph replay)
+__global__ void ppo_counter_add_kernel(uint32_t* ctr, uint32_t inc) { if (threadIdx.x == 0 && blockIdx.x == 0) ctr[0] += inc; }
+
+cudaError_t ppok_counter_add(uint32_t* ctr, uint32_t inc, cudaStream_t st) {
+    ppo_counter_add_kernel<<<1, 32, 0, st>>>(ctr, inc);
     return cudaGetLastError();
 }

@@ -1,0 +1,327 @@
+// ppo_tc.cu -- K4 on the 5th-generation tensor cores: the policy/value MLP forward over the whole env batch.
+//
+// One persistent CTA per SM walks 128-row tiles (128 envs).  Per tile and tower:
+//   X[128x32] (tf32, K-major canonical smem layout) x W1^T[32x64]  -> tcgen05.mma kind::tf32, accumulator in TMEM
+//   epilogue: tcgen05.ld (each thread owns one row = one env), + bias, tanh, write H1 back to smem as the next A
+//   H1[128x64] x W2^T[64x64] -> TMEM -> tcgen05.ld, + bias, tanh, 4-wide / 1-wide heads on CUDA cores
+// Both towers' GEMMs of a layer are issued back to back by one elected thread and complete on one mbarrier
+// (tcgen05.commit); their accumulators live side by side in 128 TMEM columns.  Weights stay resident in
+// shared memory for the CTA's lifetime.  Replaces stable_baselines3 ActorCriticPolicy.forward as called from
+// collect_rollouts (reference wiring: train/train_Fixedwing_Waypoints_v3.py:293-310).
+//
+// TF32 inputs (10-bit mantissa), fp32 accumulate: the rollout log-probabilities differ from the fp32 update
+// path by ~1e-3 absolute, far inside PPO's clip range; tests/test_ppo_gpu.py states the tolerance.
+#include "ppo_kernels.h"
+
+#include <cuda_runtime.h>
+
+#define H PPO_H
+#define A PPO_A
+#define DP PPO_DPAD
+#define TC_ROWS 128
+#define TC_TMEM_COLS 128
+
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// K-major, no-swizzle UMMA canonical layout of an [R x K] fp32 matrix: 8-row x 16-byte core matrices,
+// core matrices of one 8-row group contiguous along K (LBO = 128 B), groups K*32 B apart (SBO).
+__device__ __forceinline__ uint32_t tc_off(int r, int c, int K) {
+    return (uint32_t)((r >> 3) * (K * 32) + (c >> 2) * 128 + (r & 7) * 16 + (c & 3) * 4);
+}
+
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;        // descriptor version 1 (Blackwell); layout_type 0 = no swizzle
+    return d;
+}
+
+// instruction descriptor: D = F32, A = B = TF32, both K-major, N = 64, M = 128
+#define TC_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24))
+
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate) : "memory");
+}
+
+// D[128 x 64] (TMEM) = A[128 x K] (smem) * B[64 x K]^T (smem), K in steps of 8 (32 bytes of tf32 per instruction)
+__device__ __forceinline__ void tc_gemm(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, int K) {
+    for (int k8 = 0; k8 < K / 8; ++k8) {
+        uint64_t da = tc_desc(a_base + k8 * 256, 128, K * 32);
+        uint64_t db = tc_desc(b_base + k8 * 256, 128, K * 32);
+        tc_mma(tmem_d, da, db, k8 > 0 ? 1u : 0u);
+    }
+}
+
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+
+// Wait for the mbarrier phase.  try_wait suspends in hardware for a bounded time; the iteration cap turns a
+// malformed-descriptor hang into a trap (an error the host sees) instead of a wedged GPU.
+__device__ __forceinline__ void tc_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t it = 0;; ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (it > (1u << 22)) __trap();
+    }
+}
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+          "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+          "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float tc_tanh(float x) {
+    float e = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
+__device__ __forceinline__ uint4 tc_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+__device__ __forceinline__ float tc_u01(uint32_t x) { return ((float)(x >> 9) + 0.5f) * (1.0f / 8388608.0f); }
+
+// shared-memory plan (bytes); every MMA operand is 128-byte aligned
+struct TcSmem {
+    static constexpr int AX = 0;                          // X      [128 x 32]  16 KB
+    static constexpr int AH_PI = AX + TC_ROWS * DP * 4;   // H1 pi  [128 x 64]  32 KB
+    static constexpr int AH_VF = AH_PI + TC_ROWS * H * 4; // H1 vf  [128 x 64]  32 KB
+    static constexpr int W1_PI = AH_VF + TC_ROWS * H * 4; // W1 pi  [64 x 32]    8 KB
+    static constexpr int W1_VF = W1_PI + H * DP * 4;
+    static constexpr int W2_PI = W1_VF + H * DP * 4;      // W2 pi  [64 x 64]   16 KB
+    static constexpr int W2_VF = W2_PI + H * H * 4;
+    static constexpr int SMALL = W2_VF + H * H * 4;       // biases, heads, stats, barrier, tmem pointer
+    // floats inside SMALL
+    static constexpr int B1_PI = 0, B1_VF = 64, B2_PI = 128, B2_VF = 192, W3_PI = 256, W3_VF = 512, B3_PI = 576,
+                         B3_VF = 580, LOGSTD = 584, MEAN = 592, ISTD = 624, BAR = 656 /* 8-byte aligned */, TPTR = 660,
+                         NSMALL = 664;
+    static constexpr int TOTAL = SMALL + NSMALL * 4;
+};
+
+__device__ void tc_load_weight(char* smem, int off, const float* __restrict__ g, int K, int d) {
+    for (int i = threadIdx.x; i < H * K; i += blockDim.x) {
+        int j = i / K, k = i % K;
+        float v = k < d ? g[j * d + k] : 0.0f;
+        *reinterpret_cast<float*>(smem + off + tc_off(j, k, K)) = v;
+    }
+}
+
+__global__ void __launch_bounds__(TC_ROWS, 1)
+ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __restrict__ obs_raw,
+                      const double* __restrict__ stats, float clip, int n, uint32_t seed_lo, uint32_t seed_hi,
+                      uint32_t env_id0, uint32_t step, const uint32_t* __restrict__ step_dev, int deterministic,
+                      float* __restrict__ obs_norm, float* __restrict__ act_env, float* __restrict__ act_raw,
+                      float* __restrict__ logp, float* __restrict__ value) {
+    extern __shared__ __align__(1024) char smem[];
+    float* small = reinterpret_cast<float*>(smem + TcSmem::SMALL);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int pi_count = H * d + H + H * H + H + A * H + A;
+    const float* g_pi = params;
+    const float* g_vf = params + pi_count;
+    const int vf_count = H * d + H + H * H + H + H + 1;
+
+    // ---- one-time: weights into the canonical operand layout, small vectors, barrier, TMEM
+    tc_load_weight(smem, TcSmem::W1_PI, g_pi, DP, d);
+    tc_load_weight(smem, TcSmem::W1_VF, g_vf, DP, d);
+    tc_load_weight(smem, TcSmem::W2_PI, g_pi + H * d + H, H, H);
+    tc_load_weight(smem, TcSmem::W2_VF, g_vf + H * d + H, H, H);
+    if (tid < H) {
+        small[TcSmem::B1_PI + tid] = g_pi[H * d + tid];
+        small[TcSmem::B1_VF + tid] = g_vf[H * d + tid];
+        small[TcSmem::B2_PI + tid] = g_pi[H * d + H + H * H + tid];
+        small[TcSmem::B2_VF + tid] = g_vf[H * d + H + H * H + tid];
+        small[TcSmem::W3_VF + tid] = g_vf[H * d + H + H * H + H + tid];
+    }
+    for (int i = tid; i < A * H; i += blockDim.x) small[TcSmem::W3_PI + i] = g_pi[H * d + H + H * H + H + i];
+    if (tid < A) {
+        small[TcSmem::B3_PI + tid] = g_pi[H * d + H + H * H + H + A * H + tid];
+        small[TcSmem::LOGSTD + tid] = params[pi_count + vf_count + tid];
+    }
+    if (tid == 0) small[TcSmem::B3_VF] = g_vf[H * d + H + H * H + H + H];
+    if (tid < DP) {
+        if (stats != nullptr && tid < d) {
+            small[TcSmem::MEAN + tid] = (float)stats[tid];
+            small[TcSmem::ISTD + tid] = (float)(1.0 / sqrt(stats[d + tid] + 1e-8));
+        } else { small[TcSmem::MEAN + tid] = 0.0f; small[TcSmem::ISTD + tid] = 1.0f; }
+    }
+    const uint32_t bar = tc_smem_u32(&small[TcSmem::BAR]);
+    uint32_t* tptr = reinterpret_cast<uint32_t*>(&small[TcSmem::TPTR]);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(tc_smem_u32(tptr)), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tptr;
+    const uint32_t t_pi = tmem, t_vf = tmem + H;                       // column offsets 0 and 64
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;            // this warp's 32 TMEM lanes
+    const uint32_t s_base = tc_smem_u32(smem);
+    const uint32_t step_eff = step + (step_dev != nullptr ? step_dev[0] : 0u);
+    uint32_t phase = 0;
+
+    const int ntiles = (n + TC_ROWS - 1) / TC_ROWS;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int row = tile * TC_ROWS + tid;
+        const bool live = row < n;
+        // ---- stage the normalised observation row (VecNormalize.normalize_obs) as the A operand of layer 1
+#pragma unroll
+        for (int c4 = 0; c4 < DP / 4; ++c4) {
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = 4 * c4 + q;
+                float x = 0.0f;
+                if (live && k < d) {
+                    x = obs_raw[(size_t)row * d + k];
+                    if (stats != nullptr) x = fminf(fmaxf((x - small[TcSmem::MEAN + k]) * small[TcSmem::ISTD + k], -clip), clip);
+                    if (obs_norm != nullptr) obs_norm[(size_t)row * d + k] = x;
+                }
+                v[q] = x;
+            }
+            *reinterpret_cast<float4*>(smem + TcSmem::AX + tc_off(tid, 4 * c4, DP)) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tc_gemm(t_pi, s_base + TcSmem::AX, s_base + TcSmem::W1_PI, DP);
+            tc_gemm(t_vf, s_base + TcSmem::AX, s_base + TcSmem::W1_VF, DP);
+            tc_commit(bar);
+        }
+        tc_wait(bar, phase); phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- layer-1 epilogue: bias + tanh, H1 becomes the A operand of layer 2 (this thread's own row)
+#pragma unroll
+        for (int tower = 0; tower < 2; ++tower) {
+            const uint32_t tcol = tower == 0 ? t_pi : t_vf;
+            const float* b1 = small + (tower == 0 ? TcSmem::B1_PI : TcSmem::B1_VF);
+            const int ah = tower == 0 ? TcSmem::AH_PI : TcSmem::AH_VF;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float v[32];
+                tc_ld32(tcol + lane_base + half * 32, v);
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const int j = half * 32 + 4 * c4;
+                    float4 o = make_float4(tc_tanh(v[4 * c4 + 0] + b1[j + 0]), tc_tanh(v[4 * c4 + 1] + b1[j + 1]),
+                                           tc_tanh(v[4 * c4 + 2] + b1[j + 2]), tc_tanh(v[4 * c4 + 3] + b1[j + 3]));
+                    *reinterpret_cast<float4*>(smem + ah + tc_off(tid, j, H)) = o;
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            tc_gemm(t_pi, s_base + TcSmem::AH_PI, s_base + TcSmem::W2_PI, H);
+            tc_gemm(t_vf, s_base + TcSmem::AH_VF, s_base + TcSmem::W2_VF, H);
+            tc_commit(bar);
+        }
+        tc_wait(bar, phase); phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- layer-2 epilogue fused with the heads (4 action means, 1 value) on CUDA cores
+        float mean[A] = {small[TcSmem::B3_PI + 0], small[TcSmem::B3_PI + 1], small[TcSmem::B3_PI + 2], small[TcSmem::B3_PI + 3]};
+        float val = small[TcSmem::B3_VF];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tc_ld32(t_pi + lane_base + half * 32, v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int j = half * 32 + c;
+                const float h2 = tc_tanh(v[c] + small[TcSmem::B2_PI + j]);
+#pragma unroll
+                for (int a = 0; a < A; ++a) mean[a] = fmaf(small[TcSmem::W3_PI + a * H + j], h2, mean[a]);
+            }
+            tc_ld32(t_vf + lane_base + half * 32, v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int j = half * 32 + c;
+                val = fmaf(small[TcSmem::W3_VF + j], tc_tanh(v[c] + small[TcSmem::B2_VF + j]), val);
+            }
+        }
+        if (live) {
+            value[row] = val;
+            uint4 r = tc_philox(seed_lo, seed_hi, env_id0 + (uint32_t)row, step_eff, 0u, 7u);
+            float ra = sqrtf(-2.0f * __logf(tc_u01(r.x))), rb = sqrtf(-2.0f * __logf(tc_u01(r.z)));
+            float s0, c0, s1, c1;
+            sincospif(2.0f * tc_u01(r.y), &s0, &c0);
+            sincospif(2.0f * tc_u01(r.w), &s1, &c1);
+            float eps[A] = {ra * c0, ra * s0, rb * c1, rb * s1};
+            float lp = 0.0f, av[A];
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                const float ls = small[TcSmem::LOGSTD + a];
+                const float e = deterministic ? 0.0f : eps[a];
+                av[a] = fmaf(__expf(ls), e, mean[a]);
+                lp += -0.5f * e * e - ls - 0.91893853320467274178f;
+            }
+            reinterpret_cast<float4*>(act_env)[row] = make_float4(fminf(fmaxf(av[0], -1.f), 1.f), fminf(fmaxf(av[1], -1.f), 1.f),
+                                                                  fminf(fmaxf(av[2], -1.f), 1.f), fminf(fmaxf(av[3], -1.f), 1.f));
+            if (act_raw != nullptr) reinterpret_cast<float4*>(act_raw)[row] = make_float4(av[0], av[1], av[2], av[3]);
+            if (logp != nullptr) logp[row] = lp;
+        }
+        // the next tile overwrites AX / AH and the accumulators: order this tile's TMEM reads before it
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+    }
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)TC_TMEM_COLS) : "memory");
+}
+
+cudaError_t ppok_forward_tc(const float* params, int d, const float* obs_raw, const double* stats, float clip, int n,
+                            uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev, int deterministic,
+                            float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, cudaStream_t st) {
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(ppo_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem::TOTAL);
+        if (e != cudaSuccess) { sm_count = 0; return e; }
+    }
+    const int ntiles = (n + TC_ROWS - 1) / TC_ROWS;
+    const int grid = ntiles < sm_count ? ntiles : sm_count;          // persistent: one CTA per SM walks the tiles
+    ppo_forward_tc_kernel<<<grid, TC_ROWS, TcSmem::TOTAL, st>>>(params, d, obs_raw, stats, clip, n, (uint32_t)(seed & 0xffffffffu),
+                                                               (uint32_t)(seed >> 32), env_id0, step, step_dev, deterministic,
+                                                               obs_norm, act_env, act_raw, logp, value);
+    return cudaGetLastError();
+}

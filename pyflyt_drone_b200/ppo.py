@@ -197,7 +197,8 @@ class PPO:
                  batch_size: int = 64, n_epochs: int = 10, gamma: float = 0.99, gae_lambda: float = 0.95,
                  clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
                  seed: int = 0, device: str | torch.device | None = None, verbose: int = 0, tensorboard_log=None,
-                 normalize: bool = True, norm_reward: bool = True, clip_obs: float = 10.0):
+                 normalize: bool = True, norm_reward: bool = True, clip_obs: float = 10.0, use_cuda_graph: bool = True,
+                 tensor_core_forward: bool = True):
         if policy != "MlpPolicy":
             raise ValueError("only 'MlpPolicy' (the policy the reference trains) is implemented")
         if not torch.cuda.is_available():
@@ -222,7 +223,11 @@ class PPO:
         self.act_env = torch.zeros((N, A), **f32)
         self.last_values = torch.zeros(N, **f32)
         self.num_timesteps = 0
-        self._global_step = 0
+        self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)    # Philox step counter (uint32 bits)
+        self.use_graph = bool(use_cuda_graph)
+        self.tensor_core_forward = bool(tensor_core_forward)
+        self._graph = None
+        self._pending_capture = False
         self._obs = None               # raw observation tensor (view of the env's persistent buffer)
         self._gen = torch.Generator(device=self.device).manual_seed(seed)
         self.stats = RolloutStats()
@@ -247,17 +252,43 @@ class PPO:
 
     def _forward(self, obs_raw, t, deterministic=False):
         b = self.buf
-        _lib.check(self.lib.ppo_policy_forward(
+        fwd = self.lib.ppo_policy_forward_tc if self.tensor_core_forward else self.lib.ppo_policy_forward
+        _lib.check(fwd(
             _p(self.policy.theta), self.d, _p(obs_raw), self._stats_ptr(), self.vecnorm.clip_obs, self.n_envs, self.seed,
-            self.env.env_id0, self._global_step & 0xFFFFFFFF, int(deterministic), _p(b["obs"][t]), _p(self.act_env),
+            self.env.env_id0, t, _p(self._step_dev), int(deterministic), _p(b["obs"][t]), _p(self.act_env),
             _p(b["act"][t]), _p(b["logp"][t]), _p(b["val"][t]), _stream()))
 
     def collect_rollouts(self) -> None:
-        env, vn, b = self.env, self.vecnorm, self.buf
+        """One rollout of n_steps agent steps.  The kernel sequence is identical every time (persistent buffers,
+        step counter on the device), so it is captured once into a CUDA graph and replayed: ~7 launches per agent
+        step are then issued back to back by the GPU front end instead of by Python."""
+        env, vn = self.env, self.vecnorm
         if self._obs is None:
             self._obs = env.reset_tensor()
             vn.ret.zero_()
             self._update_obs_moments(self._obs)
+        if not self.use_graph:
+            self._rollout_body()
+        elif self._graph is None:
+            torch.cuda.synchronize()
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._rollout_body()                 # eager warm-up on the side stream (also a real rollout)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._graph = torch.cuda.CUDAGraph()
+            self._pending_capture = True
+        else:
+            if self._pending_capture:
+                with torch.cuda.graph(self._graph):
+                    self._rollout_body()
+                self._pending_capture = False
+            self._graph.replay()
+        self.num_timesteps += self.n_steps * self.n_envs * self.world
+
+    def _rollout_body(self) -> None:
+        env, vn, b = self.env, self.vecnorm, self.buf
         for t in range(self.n_steps):
             self._forward(self._obs, t)
             obs, rew, flags, term = env.step_tensor(self.act_env, want_terminal_obs=True)
@@ -272,12 +303,11 @@ class PPO:
             _lib.check(self.lib.ppo_timeout_bootstrap(_p(self.policy.theta), self.d, _p(term), self._stats_ptr(), vn.clip_obs,
                                                       _p(flags), self.n_envs, self.gamma, _p(b["rew"][t]), _stream()))
             self._obs = obs
-            self._global_step += 1
+        _lib.check(self.lib.ppo_counter_add(_p(self._step_dev), self.n_steps, _stream()))
         _lib.check(self.lib.ppo_value_forward(_p(self.policy.theta), self.d, _p(self._obs), self._stats_ptr(), vn.clip_obs,
                                               self.n_envs, _p(self.last_values), _stream()))
         _lib.check(self.lib.ppo_gae(_p(b["rew"]), _p(b["val"]), _p(b["done"]), _p(self.last_values), self.n_steps,
                                     self.n_envs, self.gamma, self.gae_lambda, _p(b["adv"]), _p(b["ret"]), _stream()))
-        self.num_timesteps += self.n_steps * self.n_envs * self.world
 
     # ------------------------------------------------------------------ update (torch autograd on the flat vector)
     def train(self) -> dict:
@@ -351,21 +381,22 @@ class PPO:
         act = torch.zeros((n, A), dtype=torch.float32, device=self.device)
         val = torch.zeros(n, dtype=torch.float32, device=self.device)
         _lib.check(self.lib.ppo_policy_forward(_p(self.policy.theta), self.d, _p(obs_raw), self._stats_ptr(),
-                                               self.vecnorm.clip_obs, n, self.seed, 0, self._global_step & 0xFFFFFFFF,
+                                               self.vecnorm.clip_obs, n, self.seed, 0, 0, _p(self._step_dev),
                                                int(deterministic), None, _p(act), None, None, _p(val), _stream()))
         return act
 
     def save(self, path: str) -> None:
         torch.save({"policy": self.policy.state_dict(), "optimizer": self.optimizer.state_dict(),
                     "vecnorm": self.vecnorm.state_dict(), "num_timesteps": self.num_timesteps,
-                    "global_step": self._global_step, "seed": self.seed, "obs_dim": self.d}, path)
+                    "global_step": int(self._step_dev.item()), "seed": self.seed, "obs_dim": self.d}, path)
 
     def load(self, path: str) -> "PPO":
         ck = torch.load(path, map_location=self.device, weights_only=False)
         self.policy.load_state_dict(ck["policy"])
         self.optimizer.load_state_dict(ck["optimizer"])
         self.vecnorm.load_state_dict(ck["vecnorm"])
-        self.num_timesteps, self._global_step = ck["num_timesteps"], ck["global_step"]
+        self.num_timesteps = ck["num_timesteps"]
+        self._step_dev.fill_(int(ck["global_step"]))
         return self
 
     def get_parameters(self) -> dict:

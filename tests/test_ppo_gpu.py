@@ -62,7 +62,7 @@ def test_policy_forward_matches_torch(model):
     stats[D:2 * D] = torch.linspace(0.5, 90, D, dtype=torch.float64)
     obs_norm = torch.zeros(N, D, device=dev); act_env = torch.zeros(N, 4, device=dev); act_raw = torch.zeros(N, 4, device=dev)
     logp = torch.zeros(N, device=dev); val = torch.zeros(N, device=dev)
-    _lib.check(model.lib.ppo_policy_forward(_p(model.policy.theta), D, _p(obs), _p(stats), 10.0, N, 77, 0, 3, 0, _p(obs_norm),
+    _lib.check(model.lib.ppo_policy_forward(_p(model.policy.theta), D, _p(obs), _p(stats), 10.0, N, 77, 0, 3, None, 0, _p(obs_norm),
                                             _p(act_env), _p(act_raw), _p(logp), _p(val), _stream()))
     ref_norm = torch.clamp((obs.double() - stats[:D]) / torch.sqrt(stats[D:2 * D] + 1e-8), -10, 10).float()
     assert torch.allclose(obs_norm, ref_norm, atol=2e-6, rtol=1e-6)
@@ -74,15 +74,47 @@ def test_policy_forward_matches_torch(model):
     assert torch.allclose(logp, lp2, atol=2e-4, rtol=1e-5)        # log-prob of the sampled (unclipped) action
     assert torch.equal(act_env, act_raw.clamp(-1, 1))
     eps = (act_raw - mean) * torch.exp(-model.policy.view("log_std"))
-    assert abs(float(eps.mean())) < 0.06 and abs(float(eps.std()) - 1) < 0.05
+    assert abs(float(eps.detach().mean())) < 0.06 and abs(float(eps.detach().std()) - 1) < 0.05
     # deterministic mode returns the mean; a different step index draws different noise
     det = torch.zeros(N, 4, device=dev)
-    _lib.check(model.lib.ppo_policy_forward(_p(model.policy.theta), D, _p(obs), _p(stats), 10.0, N, 77, 0, 3, 1, None,
+    _lib.check(model.lib.ppo_policy_forward(_p(model.policy.theta), D, _p(obs), _p(stats), 10.0, N, 77, 0, 3, None, 1, None,
                                             _p(det), None, None, _p(val), _stream()))
     assert torch.allclose(det, mean.clamp(-1, 1), atol=2e-5)
     v_only = torch.zeros(N, device=dev)
     _lib.check(model.lib.ppo_value_forward(_p(model.policy.theta), D, _p(obs), _p(stats), 10.0, N, _p(v_only), _stream()))
     assert torch.allclose(v_only, value, atol=2e-5, rtol=1e-5)
+
+
+def test_tensor_core_forward_matches_fp32_within_tf32_tolerance(model):
+    """tcgen05 kind::tf32 path vs the fp32 torch towers.  TF32 keeps 10 mantissa bits: pre-activations carry
+    ~5e-4 relative error, so means / values agree to ~5e-3 absolute and log-probs (sigma = 1) likewise."""
+    from pyflyt_drone_b200 import _lib
+    from pyflyt_drone_b200.ppo import _p, _stream
+    D, dev = 28, model.device
+    for N in (1, 127, 128, 1000, 40000):
+        obs = (torch.randn(N, D, device=dev, generator=model._gen) * 20).contiguous()
+        stats = model.vecnorm.obs_stats
+        stats[:D] = torch.linspace(-3, 3, D, dtype=torch.float64)
+        stats[D:2 * D] = torch.linspace(0.5, 90, D, dtype=torch.float64)
+        outs = {}
+        for name, fn in (("tc", model.lib.ppo_policy_forward_tc), ("cc", model.lib.ppo_policy_forward)):
+            o = dict(obs_norm=torch.zeros(N, D, device=dev), act_env=torch.zeros(N, 4, device=dev),
+                     act_raw=torch.zeros(N, 4, device=dev), logp=torch.zeros(N, device=dev), val=torch.zeros(N, device=dev))
+            _lib.check(fn(_p(model.policy.theta), D, _p(obs), _p(stats), 10.0, N, 77, 5, 3, None, 0, _p(o["obs_norm"]),
+                          _p(o["act_env"]), _p(o["act_raw"]), _p(o["logp"]), _p(o["val"]), _stream()))
+            outs[name] = o
+        torch.cuda.synchronize()
+        tc, cc = outs["tc"], outs["cc"]
+        assert torch.equal(tc["obs_norm"], cc["obs_norm"])
+        assert torch.equal(tc["logp"], cc["logp"])                    # same noise stream, log-prob depends on eps only
+        assert float((tc["val"] - cc["val"]).abs().max()) < 1e-2
+        assert float((tc["act_raw"] - cc["act_raw"]).abs().max()) < 1e-2
+        with torch.no_grad():
+            mean, value = model.policy.towers(cc["obs_norm"])
+            _, lp, _ = model.policy.evaluate_actions(cc["obs_norm"], tc["act_raw"])
+        assert float((tc["val"] - value).abs().max()) < 1e-2
+        assert float((lp - tc["logp"]).abs().max()) < 3e-2            # what the PPO ratio sees at epoch 0
+        assert float((lp - tc["logp"]).abs().mean()) < 3e-3
 
 
 def test_reward_normalize_and_bootstrap(model):
