@@ -192,7 +192,11 @@ def test_learn_runs_and_counts_timesteps(model):
     model.collect_rollouts()
     with torch.no_grad():
         _, lp, _ = model.policy.evaluate_actions(b["obs"].view(-1, 28), b["act"].view(-1, 4))
-    assert torch.allclose(lp, b["logp"].view(-1), atol=5e-4, rtol=1e-4)
+    err = (lp - b["logp"].view(-1)).abs()
+    if model.tensor_core_forward:       # TF32 tensor-core rollout vs fp32 re-evaluation
+        assert float(err.max()) < 3e-2 and float(err.mean()) < 3e-3
+    else:
+        assert float(err.max()) < 5e-4
 
 
 def test_checkpoint_round_trip(model, tmp_path):
