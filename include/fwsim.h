@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 5
+#define FW_ABI_VERSION 6
 
 #define FW_NSURF 5            /* cmd order: left aileron, right aileron, h-tail, v-tail, main wing */
 #define FW_MAX_TARGETS 16
@@ -108,6 +108,12 @@ typedef struct FwStateHost {
     uint32_t* episode;   /* [N] */
     float* new_dist;     /* [N] WaypointHandler.new_distance */
     float* wind;         /* [N,7] base xyz, gust amp xyz, phase */
+    /* ObjLock task only (ignored otherwise) */
+    float* duck;         /* [N,3] duck position */
+    float* obst;         /* [N,FW_MAX_OBST,3] cylinders x, y, height (first n_obst rows valid) */
+    float* ol_f;         /* [N,12] last cx,cy,area,depth | frame cx,cy,area,depth | frame dL,dC,dR | prev_est_dist */
+    int32_t* ol_i;       /* [N,9] duck_phase, has_prev, post_waypoints, cam_valid, frame_visible,
+                                  seen_consecutive, lock_steps, steps_since_seen, n_obst */
 } FwStateHost;
 
 typedef struct FwSim* fw_handle;

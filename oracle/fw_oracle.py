@@ -201,6 +201,18 @@ class OracleVecEnv:
             out["physics_steps"][i] = e.physics_steps; out["episode"][i] = e.episode
             out["new_dist"][i] = e.new_dist if np.isfinite(e.new_dist) else 0.0
             out["wind"][i, :3] = e.wind_base[:]; out["wind"][i, 3:6] = e.gust_amp[:]; out["wind"][i, 6] = e.gust_phase
+        if self.cfg.task == 2:
+            out["duck"] = np.zeros((n, 3)); out["obst"] = np.zeros((n, MAX_OBST, 3))
+            out["ol_f"] = np.zeros((n, 12)); out["ol_i"] = np.zeros((n, 9), np.int32)
+            for i in range(n):
+                e = self.envs[i]
+                out["duck"][i] = e.duck_pos[:]
+                for k in range(e.n_obst):
+                    out["obst"][i, k] = e.obst[k][:]
+                out["ol_f"][i] = [e.last_cx, e.last_cy, e.last_area, e.last_depth, e.frame_cx, e.frame_cy, e.frame_area,
+                                  e.frame_depth, e.frame_dl, e.frame_dc, e.frame_dr, e.prev_est_dist]
+                out["ol_i"][i] = [e.duck_phase, e.has_prev_dist, e.post_waypoints, e.cam_valid, e.frame_visible,
+                                  e.seen_consecutive, e.lock_steps, e.steps_since_seen, e.n_obst]
         return out
 
     def set_state(self, s: dict) -> None:
@@ -228,4 +240,16 @@ class OracleVecEnv:
                 e.target_idx = tidx; e.n_remaining = T - tidx
                 for t in range(T - tidx):
                     e.targets[t][:] = [float(x) for x in s["targets"][i][tidx + t]]
+            if "duck" in s: e.duck_pos[:] = [float(x) for x in s["duck"][i]]
+            if "ol_f" in s:
+                f = [float(x) for x in s["ol_f"][i]]
+                (e.last_cx, e.last_cy, e.last_area, e.last_depth, e.frame_cx, e.frame_cy, e.frame_area, e.frame_depth,
+                 e.frame_dl, e.frame_dc, e.frame_dr, e.prev_est_dist) = f
+            if "ol_i" in s:
+                v = [int(x) for x in s["ol_i"][i]]
+                (e.duck_phase, e.has_prev_dist, e.post_waypoints, e.cam_valid, e.frame_visible, e.seen_consecutive,
+                 e.lock_steps, e.steps_since_seen, e.n_obst) = v
+            if "obst" in s:
+                for k in range(MAX_OBST):
+                    e.obst[k][:] = [float(x) for x in s["obst"][i][k]]
             self.L.fwo_refresh_surface_vel(C.byref(self.cfg), C.byref(e), e.physics_steps - 1)

@@ -15,6 +15,7 @@ class FwStateHostC(C.Structure):
         ("pos", C.c_void_p), ("quat", C.c_void_p), ("vel", C.c_void_p), ("omega", C.c_void_p), ("act", C.c_void_p),
         ("targets", C.c_void_p), ("target_idx", C.c_void_p), ("step_count", C.c_void_p),
         ("physics_steps", C.c_void_p), ("episode", C.c_void_p), ("new_dist", C.c_void_p), ("wind", C.c_void_p),
+        ("duck", C.c_void_p), ("obst", C.c_void_p), ("ol_f", C.c_void_p), ("ol_i", C.c_void_p),
     ]
 
 

@@ -79,7 +79,9 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
     memset(&d, 0, sizeof(d));
     const double PI = 3.14159265358979323846, DEG = PI / 180.0;
     if (!(c.dt > 0) || !(c.mass > 0)) return fail(FW_EINVAL, "dt and mass must be positive");
-    if (c.task < 0 || c.task > 1) return fail(FW_EINVAL, "task %d not supported by this build (0 physics, 1 waypoints)", c.task);
+    if (c.task < 0 || c.task > 2) return fail(FW_EINVAL, "task %d unknown (0 physics, 1 waypoints, 2 waypoint+objlock)", c.task);
+    if (c.task == 2 && (c.num_obstacles < 0 || c.num_obstacles > FW_MAX_OBST)) return fail(FW_EINVAL, "num_obstacles out of range");
+    if (c.task == 2 && (c.cam_res < 3 || c.cam_res > 1024)) return fail(FW_EINVAL, "cam_res out of range");
     if (c.num_targets < 0 || c.num_targets > FW_MAX_TARGETS) return fail(FW_EINVAL, "num_targets out of range");
     if (c.task != 0 && c.num_targets < 1) return fail(FW_EINVAL, "waypoint task needs num_targets >= 1");
     if (c.context_len < 0 || c.context_len > 4) return fail(FW_EINVAL, "context_len out of range");
@@ -172,6 +174,14 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
     d.wind_mode = c.wind_mode; d.wind_randomize = c.wind_randomize; d.wind_rand_phase = c.wind_rand_phase;
     d.wind_start_substep = c.wind_start_substep;
     d.gust_omega = (float)(2.0 * PI * c.gust_freq); d.gust_phase = (float)c.gust_phase;
+    d.num_obstacles = c.num_obstacles; d.cam_interval = c.cam_interval_substeps; d.lock_hold = c.lock_hold_steps;
+    d.switch_min_seen = c.switch_min_seen; d.cam_res = c.cam_res;
+    d.obst_radius = (float)c.obst_radius; d.obst_h_lo = (float)c.obst_h_lo; d.obst_h_hi = (float)c.obst_h_hi;
+    d.obst_safe = (float)c.obst_safe; d.obst_scale = (float)c.obst_scale; d.obst_max_pen = (float)c.obst_max_pen;
+    d.strike_dist = (float)c.strike_dist; d.strike_reward = (float)c.strike_reward; d.lock_step_reward = (float)c.lock_step_reward;
+    d.approach_scale = (float)c.approach_scale; d.switch_min_area = (float)c.switch_min_area;
+    d.duck_radius = (float)c.duck_radius; d.cam_near = (float)c.cam_near; d.cam_far = (float)c.cam_far;
+    for (int k = 0; k < 3; ++k) d.cam_offset[k] = (float)c.cam_offset[k];
     d.warm_cached = 0;
     d.seed_lo = (uint32_t)(seed & 0xffffffffu); d.seed_hi = (uint32_t)(seed >> 32); d.env_id0 = env_id0;
     d.n = n;
@@ -206,13 +216,17 @@ extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, ui
     if (rc != FW_OK) { delete h; return rc; }
     h->obs_dim = h->dev.obs_dim;
     const size_t N = (size_t)n_envs, T = (size_t)(cfg->num_targets > 0 ? cfg->num_targets : 1);
-    size_t off = 0, o_s[6], o_w0, o_w1, o_t, o_ep, o_st;
+    size_t off = 0, o_s[6], o_w0, o_w1, o_t, o_ep, o_st, o_ol[5] = {0, 0, 0, 0, 0}, o_ob = 0;
     for (int k = 0; k < 6; ++k) { o_s[k] = off; off = align_up(off + N * 16, 256); }
     o_w0 = off; off = align_up(off + N * 16, 256);
     o_w1 = off; off = align_up(off + N * 16, 256);
     o_t = off; off = align_up(off + T * 3 * N * 4, 256);
     o_ep = off; off = align_up(off + N * 4, 256);
     o_st = off; off = align_up(off + 8 * sizeof(double), 256);
+    if (cfg->task == 2) {
+        for (int k = 0; k < 5; ++k) { o_ol[k] = off; off = align_up(off + N * 16, 256); }
+        o_ob = off; off = align_up(off + (size_t)FW_MAX_OBST * 3 * N * 4, 256);
+    }
     h->plane_bytes = off;
     ce = cudaMalloc((void**)&h->plane_mem, off);
     if (ce != cudaSuccess) { delete h; return fail(FW_ENOMEM, "cudaMalloc(%zu): %s", off, cudaGetErrorString(ce)); }
@@ -224,12 +238,17 @@ extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, ui
     pl.w0 = (float4*)(h->plane_mem + o_w0); pl.w1 = (float4*)(h->plane_mem + o_w1);
     pl.targets = (float*)(h->plane_mem + o_t); pl.ep_ret = (float*)(h->plane_mem + o_ep);
     pl.stats = (double*)(h->plane_mem + o_st);
+    if (cfg->task == 2) {
+        pl.dk = (float4*)(h->plane_mem + o_ol[0]); pl.v0 = (float4*)(h->plane_mem + o_ol[1]);
+        pl.v1 = (float4*)(h->plane_mem + o_ol[2]); pl.v2 = (float4*)(h->plane_mem + o_ol[3]);
+        pl.v3 = (int4*)(h->plane_mem + o_ol[4]); pl.obst = (float*)(h->plane_mem + o_ob);
+    }
     // episode counter starts at -1 so that the first reset opens episode 0
     cudaMemset(pl.s5, 0xff, N * 16);
     CU(cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking));
 
     // cache the deterministic warm-up result when no wind acts during it
-    if (h->dev.wind_mode == 0 || h->dev.wind_start_substep >= h->dev.warmup_substeps) {
+    if (h->dev.task != 2 && (h->dev.wind_mode == 0 || h->dev.wind_start_substep >= h->dev.warmup_substeps)) {
         float* d_warm = nullptr;
         CU(cudaMalloc((void**)&d_warm, 20 * sizeof(float)));
         CU(fwk_launch_warm(h->dev, h->pl, d_warm, h->io_stream));
@@ -434,6 +453,9 @@ struct HostPlanes {
     std::vector<int4> s5;
     std::vector<float4> w0, w1;
     std::vector<float> targets;
+    std::vector<float4> dk, v0, v1, v2;
+    std::vector<int4> v3;
+    std::vector<float> obst;
 };
 
 static int pull(FwSim* h, HostPlanes& hp) {
@@ -445,6 +467,16 @@ static int pull(FwSim* h, HostPlanes& hp) {
     hp.w0.resize(N); CU(cudaMemcpy(hp.w0.data(), h->pl.w0, N * 16, cudaMemcpyDeviceToHost));
     hp.w1.resize(N); CU(cudaMemcpy(hp.w1.data(), h->pl.w1, N * 16, cudaMemcpyDeviceToHost));
     hp.targets.resize(T * 3 * N); CU(cudaMemcpy(hp.targets.data(), h->pl.targets, T * 3 * N * 4, cudaMemcpyDeviceToHost));
+    if (h->cfg.task == 2) {
+        hp.dk.resize(N); hp.v0.resize(N); hp.v1.resize(N); hp.v2.resize(N); hp.v3.resize(N);
+        CU(cudaMemcpy(hp.dk.data(), h->pl.dk, N * 16, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(hp.v0.data(), h->pl.v0, N * 16, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(hp.v1.data(), h->pl.v1, N * 16, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(hp.v2.data(), h->pl.v2, N * 16, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(hp.v3.data(), h->pl.v3, N * 16, cudaMemcpyDeviceToHost));
+        hp.obst.resize((size_t)FW_MAX_OBST * 3 * N);
+        CU(cudaMemcpy(hp.obst.data(), h->pl.obst, (size_t)FW_MAX_OBST * 3 * N * 4, cudaMemcpyDeviceToHost));
+    }
     return FW_OK;
 }
 
@@ -456,6 +488,14 @@ static int push(FwSim* h, const HostPlanes& hp) {
     CU(cudaMemcpy(h->pl.w0, hp.w0.data(), N * 16, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->pl.w1, hp.w1.data(), N * 16, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->pl.targets, hp.targets.data(), T * 3 * N * 4, cudaMemcpyHostToDevice));
+    if (h->cfg.task == 2) {
+        CU(cudaMemcpy(h->pl.dk, hp.dk.data(), N * 16, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->pl.v0, hp.v0.data(), N * 16, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->pl.v1, hp.v1.data(), N * 16, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->pl.v2, hp.v2.data(), N * 16, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->pl.v3, hp.v3.data(), N * 16, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(h->pl.obst, hp.obst.data(), (size_t)FW_MAX_OBST * 3 * N * 4, cudaMemcpyHostToDevice));
+    }
     CU(cudaDeviceSynchronize());
     return FW_OK;
 }
@@ -492,6 +532,24 @@ extern "C" int fw_get_state(fw_handle h, FwStateHost* s) {
         if (s->targets)
             for (int t = 0; t < T; ++t)
                 for (int k = 0; k < 3; ++k) s->targets[(i * T + t) * 3 + k] = hp.targets[(size_t)(t * 3 + k) * N + i];
+        if (h->cfg.task == 2) {
+            const float4 &dk = hp.dk[i], &v0 = hp.v0[i], &v1 = hp.v1[i], &v2 = hp.v2[i];
+            const int4& v3 = hp.v3[i];
+            if (s->duck) { s->duck[3 * i] = dk.x; s->duck[3 * i + 1] = dk.y; s->duck[3 * i + 2] = dk.z; }
+            if (s->ol_f) {
+                float* o = s->ol_f + 12 * i;
+                o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w; o[4] = v1.x; o[5] = v1.y; o[6] = v1.z; o[7] = v1.w;
+                o[8] = v2.x; o[9] = v2.y; o[10] = v2.z; o[11] = v2.w;
+            }
+            if (s->ol_i) {
+                int32_t* o = s->ol_i + 9 * i;
+                o[0] = v3.x & 1; o[1] = (v3.x >> 1) & 1; o[2] = (v3.x >> 2) & 1; o[3] = (v3.x >> 3) & 1; o[4] = (v3.x >> 4) & 1;
+                o[5] = v3.y; o[6] = v3.z; o[7] = v3.w; o[8] = (v3.x >> 8) & 0xff;
+            }
+            if (s->obst)
+                for (int k = 0; k < FW_MAX_OBST; ++k)
+                    for (int c = 0; c < 3; ++c) s->obst[(i * FW_MAX_OBST + k) * 3 + c] = hp.obst[(size_t)(k * 3 + c) * N + i];
+        }
     }
     return FW_OK;
 }
@@ -528,6 +586,24 @@ extern "C" int fw_set_state(fw_handle h, const FwStateHost* s) {
         if (s->targets)
             for (int t = 0; t < T; ++t)
                 for (int k = 0; k < 3; ++k) hp.targets[(size_t)(t * 3 + k) * N + i] = s->targets[(i * T + t) * 3 + k];
+        if (h->cfg.task == 2) {
+            float4 &dk = hp.dk[i], &v0 = hp.v0[i], &v1 = hp.v1[i], &v2 = hp.v2[i];
+            int4& v3 = hp.v3[i];
+            if (s->duck) dk = make_float4(s->duck[3 * i], s->duck[3 * i + 1], s->duck[3 * i + 2], 0.0f);
+            if (s->ol_f) {
+                const float* o = s->ol_f + 12 * i;
+                v0 = make_float4(o[0], o[1], o[2], o[3]); v1 = make_float4(o[4], o[5], o[6], o[7]);
+                v2 = make_float4(o[8], o[9], o[10], o[11]);
+            }
+            if (s->ol_i) {
+                const int32_t* o = s->ol_i + 9 * i;
+                v3.x = (o[0] & 1) | ((o[1] & 1) << 1) | ((o[2] & 1) << 2) | ((o[3] & 1) << 3) | ((o[4] & 1) << 4) | ((o[8] & 0xff) << 8);
+                v3.y = o[5]; v3.z = o[6]; v3.w = o[7];
+            }
+            if (s->obst)
+                for (int k = 0; k < FW_MAX_OBST; ++k)
+                    for (int c = 0; c < 3; ++c) hp.obst[(size_t)(k * 3 + c) * N + i] = s->obst[(i * FW_MAX_OBST + k) * 3 + c];
+        }
     }
     h->fresh = false;
     return push(h, hp);

@@ -71,6 +71,11 @@ struct FwDev {
     float wind_base[3], wind_base_lo[3], wind_base_hi[3];
     float gust_amp[3], gust_amp_lo[3], gust_amp_hi[3];
     float gust_omega, gust_phase;   // 2*pi*f
+    // ObjLock task (fixedwing_waypoint_objlock_env.py:42-168)
+    int num_obstacles, cam_interval, lock_hold, switch_min_seen, cam_res;
+    float obst_radius, obst_h_lo, obst_h_hi, obst_safe, obst_scale, obst_max_pen;
+    float strike_dist, strike_reward, lock_step_reward, approach_scale, switch_min_area;
+    float duck_radius, cam_offset[3], cam_near, cam_far;
     // cached post-warm-up state (valid when no wind acts during the warm-up): pos3 quat4 vel3 omega3 act5 thr
     int warm_cached;
     float warm[20];
@@ -92,6 +97,13 @@ struct FwPlanes {
     float* targets;  // [T][3][N]
     float* ep_ret;   // [N]
     double* stats;   // [8] global episode accumulators
+    // ObjLock task only
+    float4* dk;      // duck xyz
+    float4* v0;      // last_cx, last_cy, last_area, last_depth
+    float4* v1;      // frame cx, cy, area, depth
+    float4* v2;      // frame d_left, d_center, d_right, prev_est_dist
+    int4* v3;        // bits (duck_phase, has_prev, post_wp, cam_valid, frame_visible, n_obst<<8), seen, lock, since
+    float* obst;     // [MAX_OBST][3][N]  x, y, height
 };
 
 struct EnvState {
@@ -393,7 +405,8 @@ __device__ __forceinline__ void fw_euler(const EnvState& e, float& roll, float& 
 
 // flattened observation of one env into `o` (row of obs_dim floats); target rows come from the planes
 __device__ __forceinline__ void fw_write_obs(const FwDev& p, const FwPlanes& pl, const EnvState& e, int i, int obs_tidx,
-                                             float a0, float a1, float a2, float a3, float* o) {
+                                             float a0, float a1, float a2, float a3, float* o, bool duck_row = false,
+                                             float dkx = 0.f, float dky = 0.f, float dkz = 0.f) {
     Mat3 R = fw_quat_mat(e.qx, e.qy, e.qz, e.qw);
     const float* m = R.m;
     float roll, pitch, yaw;
@@ -428,6 +441,12 @@ __device__ __forceinline__ void fw_write_obs(const FwDev& p, const FwPlanes& pl,
             o[k++] = m[0] * dx + m[3] * dy + m[6] * dz;
             o[k++] = m[1] * dx + m[4] * dy + m[7] * dz;
             o[k++] = m[2] * dx + m[5] * dy + m[8] * dz;
+        } else if (duck_row && t == p.num_targets) {
+            // ObjLock: the duck rides as one extra target row after the remaining waypoints (objlock_env.py:232-246)
+            float dx = dkx - e.px, dy = dky - e.py, dz = dkz - e.pz;
+            o[k++] = m[0] * dx + m[3] * dy + m[6] * dz;
+            o[k++] = m[1] * dx + m[4] * dy + m[7] * dz;
+            o[k++] = m[2] * dx + m[5] * dy + m[8] * dz;
         } else { o[k++] = 0.0f; o[k++] = 0.0f; o[k++] = 0.0f; }
     }
 }
@@ -435,24 +454,24 @@ __device__ __forceinline__ void fw_write_obs(const FwDev& p, const FwPlanes& pl,
 // end_reset: warmup_substeps substeps at zero setpoint.  Kept out of line: it is the rare path (only when a wind
 // field acts during the warm-up, otherwise resets copy the cached result) and inlining it would duplicate
 // the whole substep body and double the kernel's instruction-cache footprint.
-static __device__ __noinline__ void fw_warmup_loop(const FwDev& p, EnvState& e, float4 w0, float4 w1) {
+static __device__ __noinline__ void fw_warmup_loop(const FwDev& p, EnvState& e, float4 w0, float4 w1, int nsub) {
     float cmd[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     bool contact = false;
-    for (int k = 0; k < p.warmup_substeps; ++k) {
+    for (int k = 0; k < nsub; ++k) {
         float wx, wy, wz;
         fw_wind(p, e.physics_steps, w0, w1, wx, wy, wz);
         fw_substep(p, e, cmd, wx, wy, wz, 0.0f, contact);   // throttle is 0 during warm-up: noise term is 0
     }
 }
 
-// begin_reset/end_reset for env i (global id gid): initial pose, wind/target sampling, warm-up
-__device__ __forceinline__ void fw_reset_env(const FwDev& p, const FwPlanes& pl, EnvState& e, int i, uint32_t gid,
-                                             uint32_t episode) {
+// ---- reset pieces (begin_reset / WaypointHandler.reset / end_reset), composed per task by the kernels
+__device__ __forceinline__ void fw_reset_begin(const FwDev& p, const FwPlanes& pl, EnvState& e, int i, uint32_t gid,
+                                               uint32_t episode, float4& w0, float4& w1) {
     e.episode = episode;
     e.step_count = 0;
     e.tidx = 0;
-    float4 w0 = make_float4(p.wind_base[0], p.wind_base[1], p.wind_base[2], p.gust_phase);
-    float4 w1 = make_float4(p.gust_amp[0], p.gust_amp[1], p.gust_amp[2], 0.0f);
+    w0 = make_float4(p.wind_base[0], p.wind_base[1], p.wind_base[2], p.gust_phase);
+    w1 = make_float4(p.gust_amp[0], p.gust_amp[1], p.gust_amp[2], 0.0f);
     if (p.wind_mode != 0) {
         if (p.wind_randomize) {
             uint4 r0 = fw_philox(p.seed_lo, p.seed_hi, gid, episode, 0u, FWD_STREAM_WIND);
@@ -469,7 +488,37 @@ __device__ __forceinline__ void fw_reset_env(const FwDev& p, const FwPlanes& pl,
         }
         pl.w0[i] = w0; pl.w1[i] = w1;
     }
-    if (p.warm_cached) {
+    e.px = p.start_pos[0]; e.py = p.start_pos[1]; e.pz = p.start_pos[2];
+    e.qx = 0.f; e.qy = 0.f; e.qz = 0.f; e.qw = 1.f;
+    e.vx = p.start_vel[0]; e.vy = p.start_vel[1]; e.vz = p.start_vel[2];
+    e.wx = e.wy = e.wz = 0.f;
+#pragma unroll
+    for (int s = 0; s < FWD_NSURF; ++s) e.act[s] = 0.f;
+    e.thr = 0.f;
+    e.physics_steps = 0;
+    e.new_dist = 0.0f;
+}
+
+// WaypointHandler.reset: polar sampling of every target into the planes
+__device__ __forceinline__ void fw_sample_targets(const FwDev& p, const FwPlanes& pl, int i, uint32_t gid, uint32_t episode) {
+    for (int t = 0; t < p.num_targets; ++t) {
+        uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid, episode, (uint32_t)t, FWD_STREAM_TARGETS);
+        float st, ct, sp, cp;
+        sincospif(2.0f * fw_u01(r.x), &st, &ct);
+        sincospif(2.0f * fw_u01(r.y), &sp, &cp);
+        float dist = 1.0f + fw_u01(r.z) * (p.spawn_size * 0.9f - 1.0f);
+        float x = dist * sp * ct, y = dist * sp * st, z = fabsf(dist * cp);
+        z = z > p.min_height ? z : p.min_height;
+        pl.targets[(size_t)(t * 3 + 0) * p.n + i] = x;
+        pl.targets[(size_t)(t * 3 + 1) * p.n + i] = y;
+        pl.targets[(size_t)(t * 3 + 2) * p.n + i] = z;
+    }
+}
+
+// nsub warm-up substeps at zero setpoint (end_reset); copies the cached result when it is valid
+__device__ __forceinline__ void fw_warm(const FwDev& p, EnvState& e, const float4& w0, const float4& w1, int nsub,
+                                        bool allow_cache) {
+    if (allow_cache && p.warm_cached && nsub == p.warmup_substeps) {
         e.px = p.warm[0]; e.py = p.warm[1]; e.pz = p.warm[2];
         e.qx = p.warm[3]; e.qy = p.warm[4]; e.qz = p.warm[5]; e.qw = p.warm[6];
         e.vx = p.warm[7]; e.vy = p.warm[8]; e.vz = p.warm[9];
@@ -478,40 +527,31 @@ __device__ __forceinline__ void fw_reset_env(const FwDev& p, const FwPlanes& pl,
         for (int s = 0; s < FWD_NSURF; ++s) e.act[s] = p.warm[13 + s];
         e.thr = p.warm[18];
         e.physics_steps = p.warmup_substeps;
-    } else {
-        e.px = p.start_pos[0]; e.py = p.start_pos[1]; e.pz = p.start_pos[2];
-        e.qx = 0.f; e.qy = 0.f; e.qz = 0.f; e.qw = 1.f;
-        e.vx = p.start_vel[0]; e.vy = p.start_vel[1]; e.vz = p.start_vel[2];
-        e.wx = e.wy = e.wz = 0.f;
-#pragma unroll
-        for (int s = 0; s < FWD_NSURF; ++s) e.act[s] = 0.f;
-        e.thr = 0.f;
-        e.physics_steps = 0;
+    } else if (nsub > 0) {
         EnvState tmp = e;          // only this copy is address-taken (local memory); `e` stays in registers
-        fw_warmup_loop(p, tmp, w0, w1);
+        fw_warmup_loop(p, tmp, w0, w1, nsub);
         e = tmp;
     }
+}
+
+__device__ __forceinline__ void fw_reset_finish(const FwDev& p, const FwPlanes& pl, EnvState& e, int i) {
     e.new_dist = 0.0f;
-    if (p.task != 0) {
-        float d0 = 0.f;
-        for (int t = 0; t < p.num_targets; ++t) {
-            uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid, episode, (uint32_t)t, FWD_STREAM_TARGETS);
-            float st, ct, sp, cp;
-            sincospif(2.0f * fw_u01(r.x), &st, &ct);
-            sincospif(2.0f * fw_u01(r.y), &sp, &cp);
-            float dist = 1.0f + fw_u01(r.z) * (p.spawn_size * 0.9f - 1.0f);
-            float x = dist * sp * ct, y = dist * sp * st, z = fabsf(dist * cp);
-            z = z > p.min_height ? z : p.min_height;
-            pl.targets[(size_t)(t * 3 + 0) * p.n + i] = x;
-            pl.targets[(size_t)(t * 3 + 1) * p.n + i] = y;
-            pl.targets[(size_t)(t * 3 + 2) * p.n + i] = z;
-            if (t == 0) {
-                float dx = x - e.px, dy = y - e.py, dz = z - e.pz;
-                d0 = sqrtf(dx * dx + dy * dy + dz * dz);
-            }
-        }
-        e.new_dist = d0;
+    if (p.task != 0 && p.num_targets > 0) {
+        float dx = pl.targets[(size_t)0 * p.n + i] - e.px;
+        float dy = pl.targets[(size_t)1 * p.n + i] - e.py;
+        float dz = pl.targets[(size_t)2 * p.n + i] - e.pz;
+        e.new_dist = sqrtf(dx * dx + dy * dy + dz * dz);
     }
+}
+
+// begin_reset/end_reset for the physics-only and Waypoints tasks
+__device__ __forceinline__ void fw_reset_env(const FwDev& p, const FwPlanes& pl, EnvState& e, int i, uint32_t gid,
+                                             uint32_t episode) {
+    float4 w0, w1;
+    fw_reset_begin(p, pl, e, i, gid, episode, w0, w1);
+    if (p.task != 0) fw_sample_targets(p, pl, i, gid, episode);
+    fw_warm(p, e, w0, w1, p.warmup_substeps, true);
+    fw_reset_finish(p, pl, e, i);
 }
 
 __device__ __forceinline__ void fw_load(const FwPlanes& pl, int i, EnvState& e) {

@@ -15,6 +15,7 @@
 // bank: every FFMA reads them as a c[][] operand with no load instruction (all threads use the same address,
 // which is the case the constant cache is built for; shared-memory staging would add an LDS per use).
 #include "fw_device.cuh"
+#include "fw_objlock.cuh"
 #include "fw_kernels.h"
 
 #include <cstring>
@@ -54,15 +55,37 @@ __device__ __forceinline__ void fw_flush_obs(float* __restrict__ dst_base, const
 
 // One agent step of env i held in registers (FixedwingBaseEnv.step + SubprocVecEnv reset-on-done).
 // Returns the reward; flag bits in `bits`; the observation (if TASK != 0) is left in `row`.
+// ObjLock reset: begin_reset, waypoints, duck/obstacles, warm-up with the camera frame PyFlyt captures at physics
+// step 12 of it, then the compute_state of end_reset (fixedwing_waypoint_objlock_env.py:170-195)
+__device__ __forceinline__ void fw_reset_env_objlock(const FwDev& p, const FwPlanes& pl, EnvState& e, OlState& ol, float* so,
+                                                     int i, uint32_t gid, uint32_t episode, int tid) {
+    float4 w0, w1;
+    fw_reset_begin(p, pl, e, i, gid, episode, w0, w1);
+    fw_sample_targets(p, pl, i, gid, episode);
+    ol_reset(p, pl, ol, i, gid, episode, so, tid, FW_BLOCK);
+    int done = 0;
+    while (done < p.warmup_substeps) {
+        int next = p.warmup_substeps;
+        if (p.cam_interval > 0) next = min(next, (done / p.cam_interval + 1) * p.cam_interval);
+        fw_warm(p, e, w0, w1, next - done, false);
+        done = next;
+        if (p.cam_interval > 0 && done % p.cam_interval == 0 && done % p.substeps_per_inner == 0)
+            ol_capture(p, e, ol, so, tid, FW_BLOCK);
+    }
+    fw_reset_finish(p, pl, e, i);
+    ol_vision_and_phase(p, ol, e.tidx >= p.num_targets);
+}
+
 template <int TASK>
-__device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl, EnvState& e, int i, uint32_t gid,
-                                             float a0, float a1, float a2, float a3, const float4& w0_in,
+__device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl, EnvState& e, OlState& ol, float* so, int i,
+                                             uint32_t gid, float a0, float a1, float a2, float a3, const float4& w0_in,
                                              const float4& w1_in, float& ep_ret, float* row, float* term_obs_row,
                                              uint32_t& bits) {
+    const int tid = threadIdx.x;
     float4 w0 = w0_in, w1 = w1_in;
     // FixedwingBaseEnv.step: reward reset once, thrust remapped to [0,1], setpoint latched
     float reward = -0.1f;
-    bool term = false, trunc = false, col = false, oob = false, complete = false;
+    bool term = false, trunc = false, col = false, oob = false, complete = false, strike = false;
     float cmd[6];
     fw_map_setpoint(p, a0, a1, a2, a3 * 0.5f + 0.5f, cmd);
     float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
@@ -87,17 +110,21 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
             }
             float wx, wy, wz;
             fw_wind(p, ps, w0, w1, wx, wy, wz);
+            if (TASK == 2) contact = contact || ol_contact(p, e, ol, so, tid, FW_BLOCK);   // pose entering the step
             fw_substep(p, e, cmd, wx, wy, wz, nz, contact);
         }
+        // drone.update_last(): camera frame every cam_interval physics steps
+        if (TASK == 2 && p.cam_interval > 0 && (e.physics_steps % p.cam_interval) == 0) ol_capture(p, e, ol, so, tid, FW_BLOCK);
         // compute_state: WaypointHandler.distance_to_targets (old <- new, new <- |delta_0|)
         float old_dist = e.new_dist;
         obs_tidx = e.tidx;
-        if (TASK == 1 && e.tidx < p.num_targets) {
+        if (TASK >= 1 && e.tidx < p.num_targets) {
             float dx = pl.targets[(size_t)(e.tidx * 3 + 0) * p.n + i] - e.px;
             float dy = pl.targets[(size_t)(e.tidx * 3 + 1) * p.n + i] - e.py;
             float dz = pl.targets[(size_t)(e.tidx * 3 + 2) * p.n + i] - e.pz;
             e.new_dist = sqrtf(dx * dx + dy * dy + dz * dz);
         }
+        if (TASK == 2) ol_vision_and_phase(p, ol, e.tidx >= p.num_targets);
         // compute_base_term_trunc_reward
         if (e.step_count > p.max_steps) trunc = true;
         if (contact) { reward = -100.0f; col = true; term = true; }
@@ -114,12 +141,46 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
                 if (p.complete_truncates && all) trunc = true;
             }
         }
+        if (TASK == 2 && !(col || oob)) {          // early return on crash (objlock_env.py:282-283)
+            if (e.tidx < p.num_targets) {
+                if (!p.sparse_reward) {
+                    reward += fmaxf(3.0f * (old_dist - e.new_dist), 0.0f);
+                    reward += 1.0f / e.new_dist;
+                }
+                if (e.new_dist < p.goal_reach) {
+                    reward = 100.0f;
+                    e.tidx += 1;
+                    if (e.tidx >= p.num_targets) { term = false; trunc = false; }    // keep flying into the duck phase
+                }
+                reward -= ol_obstacle_penalty(p, ol, false);
+            } else {
+                term = false;
+                reward -= ol_obstacle_penalty(p, ol, true);
+                if (ol.duck_phase) {
+                    if (!p.sparse_reward && ol.last_depth > 0.0f) reward += 1.0f / fmaxf(ol.last_depth, 2.0f);
+                    if (ol.last_cx > 0.0f) {
+                        float ddx = ol.last_cx - 0.5f, ddy = ol.last_cy - 0.5f;
+                        if (sqrtf(ddx * ddx + ddy * ddy) < 0.35f) { ol.lock += 1; reward += p.lock_step_reward; }
+                        else ol.lock = 0;
+                    } else ol.lock = 0;
+                    const float est = ol.last_depth;
+                    if (ol.has_prev && est > 0.0f) {
+                        float diff = ol.prev_est - est;
+                        if (diff > 0.0f) reward += diff * p.approach_scale;
+                    }
+                    ol.prev_est = est; ol.has_prev = 1;
+                    if (ol.lock >= p.lock_hold && est > 0.0f && est <= p.strike_dist) {
+                        term = true; reward += p.strike_reward; complete = true; strike = true;
+                    }
+                }
+            }
+        }
     }
     e.step_count += 1;
     if (TASK == 1) complete = e.tidx >= p.num_targets;     // info["env_complete"] is sticky within an episode
 
     const bool done = term || trunc;
-    if (TASK != 0 && row != nullptr) fw_write_obs(p, pl, e, i, obs_tidx, a0, a1, a2, a3, row);
+    if (TASK != 0 && row != nullptr) fw_write_obs(p, pl, e, i, obs_tidx, a0, a1, a2, a3, row, TASK == 2, ol.dkx, ol.dky, ol.dkz);
     ep_ret += reward;
     if (done) {
         if (TASK != 0 && term_obs_row != nullptr)
@@ -131,13 +192,15 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
         if (col) atomicAdd(&pl.stats[4], 1.0);
         if (oob) atomicAdd(&pl.stats[5], 1.0);
         if (complete) atomicAdd(&pl.stats[6], 1.0);
+        if (strike) atomicAdd(&pl.stats[7], 1.0);
         // SubprocVecEnv worker: obs = env.reset()
-        fw_reset_env(p, pl, e, i, gid, e.episode + 1u);
+        if (TASK == 2) fw_reset_env_objlock(p, pl, e, ol, so, i, gid, e.episode + 1u, tid);
+        else fw_reset_env(p, pl, e, i, gid, e.episode + 1u);
         if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
-        if (TASK != 0 && row != nullptr) fw_write_obs(p, pl, e, i, 0, 0.f, 0.f, 0.f, 0.f, row);
+        if (TASK != 0 && row != nullptr) fw_write_obs(p, pl, e, i, 0, 0.f, 0.f, 0.f, 0.f, row, TASK == 2, ol.dkx, ol.dky, ol.dkz);
         ep_ret = 0.0f;
     }
-    bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (col ? 4u : 0u) | (oob ? 8u : 0u) | (complete ? 16u : 0u);
+    bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (col ? 4u : 0u) | (oob ? 8u : 0u) | (complete ? 16u : 0u) | (strike ? 32u : 0u);
     return reward;
 }
 
@@ -155,11 +218,14 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
     const int D = p.obs_dim;
     float* stage_warp = stage + (size_t)warp * 32 * D;
     float* row = (TASK != 0 && obs != nullptr) ? stage_warp + (size_t)lane * D : nullptr;
+    float* so = stage + (size_t)(FW_BLOCK / 32) * 32 * (D > 0 ? D : 1);       // ObjLock obstacle table [k][c][thread]
 
     if (i < p.n) {
         const uint32_t gid = p.env_id0 + (uint32_t)i;
         EnvState e;
         fw_load(pl, i, e);
+        OlState ol;
+        if (TASK == 2) { ol_load(pl, i, ol); ol_stage_obstacles(p, pl, i, ol.n_obst, so, threadIdx.x, FW_BLOCK); }
         float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
         if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
         float ep_ret = pl.ep_ret[i];
@@ -171,17 +237,18 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
                 float a0 = 2.0f * fw_u01(r.x) - 1.0f, a1 = 2.0f * fw_u01(r.y) - 1.0f;
                 float a2 = 2.0f * fw_u01(r.z) - 1.0f, a3 = 2.0f * fw_u01(r.w) - 1.0f;
                 if (p.wind_mode != 0 && st > 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
-                reward = fw_env_step<TASK>(p, pl, e, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
+                reward = fw_env_step<TASK>(p, pl, e, ol, so, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
                                            st == spl - 1 ? row : nullptr, nullptr, bits);
             }
         } else {
             float4 a = act[i];
-            reward = fw_env_step<TASK>(p, pl, e, i, gid, a.x, a.y, a.z, a.w, w0, w1, ep_ret, row,
+            reward = fw_env_step<TASK>(p, pl, e, ol, so, i, gid, a.x, a.y, a.z, a.w, w0, w1, ep_ret, row,
                                        (TASK != 0 && term_obs != nullptr && row != nullptr) ? term_obs + (size_t)i * D : nullptr,
                                        bits);
         }
         pl.ep_ret[i] = ep_ret;
         fw_store(pl, i, e);
+        if (TASK == 2) ol_store(pl, i, ol);
         if (rew != nullptr) rew[i] = reward;
         if (flg != nullptr) flg[i] = (uint8_t)bits;
     }
@@ -200,17 +267,25 @@ fw_reset_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const uint8_
     const int D = p.obs_dim;
     float* stage_warp = stage + (size_t)warp * 32 * D;
     float* row = stage_warp + (size_t)lane * D;
+    float* so = stage + (size_t)(FW_BLOCK / 32) * 32 * (D > 0 ? D : 1);
     if (i < p.n) {
         EnvState e;
         fw_load(pl, i, e);
+        OlState ol;
+        if (p.task == 2) ol_load(pl, i, ol);
         const bool sel = !emit_only && (mask == nullptr || mask[i] != 0);
         if (sel) {
-            fw_reset_env(p, pl, e, i, p.env_id0 + (uint32_t)i, e.episode + 1u);
+            if (p.task == 2) {
+                fw_reset_env_objlock(p, pl, e, ol, so, i, p.env_id0 + (uint32_t)i, e.episode + 1u, threadIdx.x);
+                ol_store(pl, i, ol);
+            } else {
+                fw_reset_env(p, pl, e, i, p.env_id0 + (uint32_t)i, e.episode + 1u);
+            }
             pl.ep_ret[i] = 0.0f;
             fw_store(pl, i, e);
         }
         // unselected envs re-emit their current observation (last action unknown -> zeros)
-        if (p.task != 0) fw_write_obs(p, pl, e, i, e.tidx, 0.f, 0.f, 0.f, 0.f, row);
+        if (p.task != 0) fw_write_obs(p, pl, e, i, e.tidx, 0.f, 0.f, 0.f, 0.f, row, p.task == 2, ol.dkx, ol.dky, ol.dkz);
     }
     if (p.task != 0 && obs != nullptr) {
         const int first_env = blockIdx.x * FW_BLOCK + warp * 32;
@@ -234,7 +309,11 @@ __global__ void fw_warm_kernel(const __grid_constant__ FwDev p, const FwPlanes p
 }
 
 // ------------------------------------------------------------------ launchers
-static inline size_t stage_bytes(const FwDev& p) { return (size_t)(FW_BLOCK / 32) * 32 * (size_t)(p.obs_dim > 0 ? p.obs_dim : 1) * 4; }
+static inline size_t stage_bytes(const FwDev& p) {
+    size_t obs = (size_t)(FW_BLOCK / 32) * 32 * (size_t)(p.obs_dim > 0 ? p.obs_dim : 1) * 4;
+    size_t obst = p.task == 2 ? (size_t)(p.num_obstacles > 0 ? p.num_obstacles : 1) * 3 * FW_BLOCK * 4 : 0;
+    return obs + obst;
+}
 static inline int grid_for(int n) { return (n + FW_BLOCK - 1) / FW_BLOCK; }
 
 typedef void (*fw_step_fn)(const FwDev, const FwPlanes, const float4*, float*, float*, uint8_t*, float*, int, int);
@@ -242,6 +321,7 @@ typedef void (*fw_step_fn)(const FwDev, const FwPlanes, const float4*, float*, f
 static fw_step_fn step_fn(int task, bool random_act) {
     if (task == 0) return random_act ? fw_step_kernel<0, true> : fw_step_kernel<0, false>;
     if (task == 1) return random_act ? fw_step_kernel<1, true> : fw_step_kernel<1, false>;
+    if (task == 2) return random_act ? fw_step_kernel<2, true> : fw_step_kernel<2, false>;
     return nullptr;
 }
 

@@ -1,0 +1,306 @@
+// fw_objlock.cuh -- device side of the Waypoint + ObjLock task (BASELINE config 4, "ground-truth target
+// observation, no YOLO"): duck/obstacle spawn, analytic pin-hole chase camera, the nine vision features, the
+// duck-phase state machine and the obstacle-avoidance / lock / approach / strike rewards.
+//
+// Restates /root/reference/envs/fixedwing_waypoint_objlock_env.py:
+//   reset/_spawn_duck/_spawn_obstacles  :170-195,382-519     compute_state            :197-276
+//   compute_term_trunc_reward           :278-343              _apply_obstacle_avoidance :347-380
+//   _compute_vision_features & helpers  :575-693              camera interval           :563-573
+// The reference rasterises a 128x128 segmentation/depth image with PyBullet (TinyRenderer) every 12 substeps and
+// reduces it to nine numbers; here the same nine numbers come from an analytic camera: duck = sphere,
+// obstacles = finite vertical cylinders, ground = plane z = 0, one ray per pixel column of the middle row.
+// That is a documented stand-in for the mesh renderer, restated identically in the fp64 oracle.
+#pragma once
+
+#include "fw_device.cuh"
+
+#define OL_MAX_OBST 32
+
+// per-env ObjLock state carried in registers during a step
+struct OlState {
+    float dkx, dky, dkz;                             // duck position (world)
+    float last_cx, last_cy, last_area, last_depth;   // _last_* of the reference
+    float f_cx, f_cy, f_area, f_depth;               // latest captured frame: duck silhouette
+    float f_dl, f_dc, f_dr;                          // latest captured frame: obstacle bands (metres)
+    float prev_est;                                  // _prev_est_dist_m
+    int duck_phase, has_prev, post_wp, cam_valid, f_visible;
+    int seen, lock, since;                           // _seen_consecutive, _lock_steps, _steps_since_seen
+    int n_obst;
+    float vis_dl, vis_dc, vis_dr;                    // duck_vision[6:9] of the current compute_state
+    float vis_flag;                                  // duck_vision[0]
+};
+
+__device__ __forceinline__ void ol_load(const FwPlanes& pl, int i, OlState& o) {
+    float4 d = pl.dk[i], a = pl.v0[i], b = pl.v1[i], c = pl.v2[i];
+    int4 g = pl.v3[i];
+    o.dkx = d.x; o.dky = d.y; o.dkz = d.z;
+    o.last_cx = a.x; o.last_cy = a.y; o.last_area = a.z; o.last_depth = a.w;
+    o.f_cx = b.x; o.f_cy = b.y; o.f_area = b.z; o.f_depth = b.w;
+    o.f_dl = c.x; o.f_dc = c.y; o.f_dr = c.z; o.prev_est = c.w;
+    o.duck_phase = g.x & 1; o.has_prev = (g.x >> 1) & 1; o.post_wp = (g.x >> 2) & 1; o.cam_valid = (g.x >> 3) & 1;
+    o.f_visible = (g.x >> 4) & 1; o.n_obst = (g.x >> 8) & 0xff;
+    o.seen = g.y; o.lock = g.z; o.since = g.w;
+    o.vis_dl = o.vis_dc = o.vis_dr = 0.0f; o.vis_flag = 0.0f;
+}
+
+__device__ __forceinline__ void ol_store(const FwPlanes& pl, int i, const OlState& o) {
+    pl.dk[i] = make_float4(o.dkx, o.dky, o.dkz, 0.0f);
+    pl.v0[i] = make_float4(o.last_cx, o.last_cy, o.last_area, o.last_depth);
+    pl.v1[i] = make_float4(o.f_cx, o.f_cy, o.f_area, o.f_depth);
+    pl.v2[i] = make_float4(o.f_dl, o.f_dc, o.f_dr, o.prev_est);
+    int bits = (o.duck_phase & 1) | ((o.has_prev & 1) << 1) | ((o.post_wp & 1) << 2) | ((o.cam_valid & 1) << 3) |
+               ((o.f_visible & 1) << 4) | ((o.n_obst & 0xff) << 8);
+    pl.v3[i] = make_int4(bits, o.seen, o.lock, o.since);
+}
+
+// obstacle table of this thread in shared memory: so[(k*3 + c) * FWD_OL_STRIDE + tid]
+#define OL_S(so, k, c, tid, stride) (so)[((k) * 3 + (c)) * (stride) + (tid)]
+
+__device__ __forceinline__ void ol_stage_obstacles(const FwDev& p, const FwPlanes& pl, int i, int n_obst, float* so, int tid,
+                                                   int stride) {
+    for (int k = 0; k < n_obst; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) OL_S(so, k, c, tid, stride) = pl.obst[(size_t)(k * 3 + c) * p.n + i];
+}
+
+// nearest positive hit of ray o + t d with the finite vertical cylinder (cx, cy, height h, radius r); inf if none
+__device__ __forceinline__ float ol_ray_cylinder(float ox, float oy, float oz, float dx, float dy, float dz, float cx,
+                                                 float cy, float h, float r) {
+    const float INF = __int_as_float(0x7f800000);
+    float px = ox - cx, py = oy - cy;
+    float a = dx * dx + dy * dy;
+    float best = INF;
+    if (a > 1e-12f) {
+        float b = px * dx + py * dy;
+        float cc = px * px + py * py - r * r;
+        float disc = b * b - a * cc;
+        if (disc >= 0.0f) {
+            float sq = sqrtf(disc);
+            float inv = 1.0f / a;
+            float t0 = (-b - sq) * inv, t1 = (-b + sq) * inv;
+            if (t0 > 0.0f) { float z = oz + t0 * dz; if (z >= 0.0f && z <= h && t0 < best) best = t0; }
+            if (t1 > 0.0f) { float z = oz + t1 * dz; if (z >= 0.0f && z <= h && t1 < best) best = t1; }
+        }
+    }
+    if (fabsf(dz) > 1e-12f) {     // top cap
+        float t = (h - oz) / dz;
+        if (t > 0.0f) {
+            float x = px + t * dx, y = py + t * dy;
+            if (x * x + y * y <= r * r && t < best) best = t;
+        }
+    }
+    return best;
+}
+
+__device__ __forceinline__ float ol_ray_sphere(float ox, float oy, float oz, float dx, float dy, float dz, float sx,
+                                               float sy, float sz, float r) {
+    const float INF = __int_as_float(0x7f800000);
+    float px = ox - sx, py = oy - sy, pz = oz - sz;
+    float a = dx * dx + dy * dy + dz * dz, b = px * dx + py * dy + pz * dz, cc = px * px + py * py + pz * pz - r * r;
+    float disc = b * b - a * cc;
+    if (disc < 0.0f) return INF;
+    float t = (-b - sqrtf(disc)) / a;
+    return t > 0.0f ? t : INF;
+}
+
+__device__ __forceinline__ float ol_depth_buf(const FwDev& p, float z) {
+    if (z < p.cam_near) z = p.cam_near;
+    if (z > p.cam_far) return 1.0f;
+    return p.cam_far * (z - p.cam_near) / ((p.cam_far - p.cam_near) * z);
+}
+__device__ __forceinline__ float ol_buf_to_m(const FwDev& p, float d) {
+    float denom = p.cam_far - (p.cam_far - p.cam_near) * d;
+    if (fabsf(denom) < 1e-9f) return p.cam_far;
+    return p.cam_far * p.cam_near / denom;
+}
+
+// Camera.capture_image stand-in + the image reductions of _compute_vision_features
+__device__ __forceinline__ void ol_capture(const FwDev& p, const EnvState& e, OlState& o, const float* so, int tid, int stride) {
+    const float INF = __int_as_float(0x7f800000);
+    Mat3 R = fw_quat_mat(e.qx, e.qy, e.qz, e.qw);
+    const float* m = R.m;
+    // camera position = pos + R * offset ; forward = -R*offset/|offset| ; up hint = body z
+    float ofx = m[0] * p.cam_offset[0] + m[1] * p.cam_offset[1] + m[2] * p.cam_offset[2];
+    float ofy = m[3] * p.cam_offset[0] + m[4] * p.cam_offset[1] + m[5] * p.cam_offset[2];
+    float ofz = m[6] * p.cam_offset[0] + m[7] * p.cam_offset[1] + m[8] * p.cam_offset[2];
+    float cx = e.px + ofx, cy = e.py + ofy, cz = e.pz + ofz;
+    float il = rsqrtf(ofx * ofx + ofy * ofy + ofz * ofz);
+    float fx = -ofx * il, fy = -ofy * il, fz = -ofz * il;
+    float ux = m[2], uy = m[5], uz = m[8];
+    float rx = fy * uz - fz * uy, ry = fz * ux - fx * uz, rz = fx * uy - fy * ux;
+    float rl = rsqrtf(rx * rx + ry * ry + rz * rz);
+    rx *= rl; ry *= rl; rz *= rl;
+    ux = ry * fz - rz * fy; uy = rz * fx - rx * fz; uz = rx * fy - ry * fx;
+
+    // duck silhouette: sphere of radius duck_radius resting on the ground
+    const float Rd = p.duck_radius;
+    float sx = o.dkx, sy = o.dky, sz = o.dkz + Rd;
+    float dvx = sx - cx, dvy = sy - cy, dvz = sz - cz;
+    float zc = dvx * fx + dvy * fy + dvz * fz, xc = dvx * rx + dvy * ry + dvz * rz, yc = dvx * ux + dvy * uy + dvz * uz;
+    int vis = 0;
+    if (zc - Rd > p.cam_near && fabsf(xc) <= zc + Rd && fabsf(yc) <= zc + Rd && zc - Rd < p.cam_far) {
+        vis = 1;
+        float dist = sqrtf(dvx * dvx + dvy * dvy + dvz * dvz);
+        float id = 1.0f / dist;
+        float ddx = dvx * id, ddy = dvy * id, ddz = dvz * id;
+        for (int k = 0; k < o.n_obst && vis; ++k) {
+            float t = ol_ray_cylinder(cx, cy, cz, ddx, ddy, ddz, OL_S(so, k, 0, tid, stride), OL_S(so, k, 1, tid, stride),
+                                      OL_S(so, k, 2, tid, stride), p.obst_radius);
+            if (t < dist - Rd) vis = 0;
+        }
+    }
+    o.f_visible = vis;
+    if (vis) {
+        float ccx = 0.5f + 0.5f * xc / zc, ccy = 0.5f - 0.5f * yc / zc;
+        o.f_cx = fminf(fmaxf(ccx, 0.0f), 1.0f);
+        o.f_cy = fminf(fmaxf(ccy, 0.0f), 1.0f);
+        float a = FWD_PI * (Rd / zc) * (Rd / zc) * 0.25f;
+        o.f_area = fminf(a, 1.0f);
+        o.f_depth = zc - Rd;
+    }
+    // obstacle bands: middle row, three column bands, mean depth-buffer value of non-duck pixels
+    const int w = p.cam_res, x1 = w / 3, x2 = 2 * w / 3, ymid = w / 2;
+    const float vrow = 2.0f * ((float)ymid + 0.5f) / (float)w - 1.0f;
+    float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
+    int c0 = 0, c1 = 0, c2 = 0;
+    for (int col = 0; col < w; ++col) {
+        float xn = 2.0f * ((float)col + 0.5f) / (float)w - 1.0f;
+        float dx = fx + xn * rx - vrow * ux, dy = fy + xn * ry - vrow * uy, dz = fz + xn * rz - vrow * uz;
+        float best = INF;
+        if (dz < -1e-12f) { float t = -cz / dz; if (t > 0.0f && t < best) best = t; }
+        for (int k = 0; k < o.n_obst; ++k) {
+            float t = ol_ray_cylinder(cx, cy, cz, dx, dy, dz, OL_S(so, k, 0, tid, stride), OL_S(so, k, 1, tid, stride),
+                                      OL_S(so, k, 2, tid, stride), p.obst_radius);
+            if (t < best) best = t;
+        }
+        float td = ol_ray_sphere(cx, cy, cz, dx, dy, dz, sx, sy, sz, Rd);
+        if (td < best) continue;                       // duck pixel: excluded from the band means
+        float db = (best < INF) ? ol_depth_buf(p, best) : 1.0f;
+        if (col < x1) { sum0 += db; c0++; } else if (col < x2) { sum1 += db; c1++; } else { sum2 += db; c2++; }
+    }
+    float m0 = c0 ? sum0 / (float)c0 : 0.0f, m1 = c1 ? sum1 / (float)c1 : 0.0f, m2 = c2 ? sum2 / (float)c2 : 0.0f;
+    o.f_dl = m0 > 0.0f ? ol_buf_to_m(p, m0) : 0.0f;
+    o.f_dc = m1 > 0.0f ? ol_buf_to_m(p, m1) : 0.0f;
+    o.f_dr = m2 > 0.0f ? ol_buf_to_m(p, m2) : 0.0f;
+    o.cam_valid = 1;
+}
+
+// _compute_vision_features + the phase switching of compute_state (fixedwing_waypoint_objlock_env.py:248-274)
+__device__ __forceinline__ void ol_vision_and_phase(const FwDev& p, OlState& o, bool all_reached) {
+    float visible = 0.0f, dl = 0.0f, dc = 0.0f, dr = 0.0f;
+    if (o.cam_valid) {
+        dl = o.f_dl; dc = o.f_dc; dr = o.f_dr;
+        if (!o.f_visible) {
+            o.since = min(o.since + 1, 60);
+        } else {
+            o.last_cx = o.f_cx; o.last_cy = o.f_cy; o.last_area = o.f_area; o.last_depth = o.f_depth;
+            o.since = 0;
+            visible = 1.0f;
+        }
+    }
+    o.vis_flag = visible; o.vis_dl = dl; o.vis_dc = dc; o.vis_dr = dr;
+    if (all_reached) {
+        o.post_wp = 1;
+        if (!o.duck_phase) {
+            const bool vis = visible > 0.5f && o.last_area >= p.switch_min_area;
+            o.seen = vis ? o.seen + 1 : 0;
+            if (o.seen >= p.switch_min_seen) o.duck_phase = 1;
+        }
+    } else {
+        o.post_wp = 0;
+        o.duck_phase = 0;
+    }
+}
+
+__device__ __forceinline__ float ol_obstacle_penalty(const FwDev& p, const OlState& o, bool duck_phase) {
+    const float INF = __int_as_float(0x7f800000);
+    float dmin = INF;
+    if (o.vis_dl > 0.0f && o.vis_dl < dmin) dmin = o.vis_dl;
+    if (o.vis_dc > 0.0f && o.vis_dc < dmin) dmin = o.vis_dc;
+    if (o.vis_dr > 0.0f && o.vis_dr < dmin) dmin = o.vis_dr;
+    if (!(dmin < INF)) return 0.0f;
+    if (p.obst_safe <= 0.0f || dmin >= p.obst_safe) return 0.0f;
+    float scale = p.obst_scale * (duck_phase ? 0.5f : 1.0f);
+    return fminf(scale * (p.obst_safe - dmin) / p.obst_safe, p.obst_max_pen);
+}
+
+// contact with obstacles / duck on the pose entering the step (collision probe points vs cylinders and sphere)
+__device__ __forceinline__ bool ol_contact(const FwDev& p, const EnvState& e, const OlState& o, const float* so, int tid,
+                                           int stride) {
+    bool hit = false;
+    const float reach = p.col_radius + p.contact_margin;
+    // cheap reject first: most aircraft are nowhere near an obstacle, so the rotation matrix is rarely needed
+    bool near_any = false;
+    for (int k = 0; k < o.n_obst; ++k) {
+        float ddx = e.px - OL_S(so, k, 0, tid, stride), ddy = e.py - OL_S(so, k, 1, tid, stride);
+        float rr = p.obst_radius + reach;
+        near_any = near_any || (ddx * ddx + ddy * ddy <= rr * rr && e.pz <= OL_S(so, k, 2, tid, stride) + reach);
+    }
+    {
+        float ddx = e.px - o.dkx, ddy = e.py - o.dky, ddz = e.pz - (o.dkz + p.duck_radius);
+        float rr = p.duck_radius + reach;
+        near_any = near_any || (ddx * ddx + ddy * ddy + ddz * ddz <= rr * rr);
+    }
+    if (!near_any) return false;
+    Mat3 R = fw_quat_mat(e.qx, e.qy, e.qz, e.qw);
+    const float* m = R.m;
+    for (int k = 0; k < o.n_obst; ++k) {
+        float ox = OL_S(so, k, 0, tid, stride), oy = OL_S(so, k, 1, tid, stride), oh = OL_S(so, k, 2, tid, stride);
+        float ddx = e.px - ox, ddy = e.py - oy;
+        float rr = p.obst_radius + reach;
+        if (ddx * ddx + ddy * ddy > rr * rr || e.pz > oh + reach) continue;     // conservative prune
+        const float r2 = (p.obst_radius + p.contact_margin) * (p.obst_radius + p.contact_margin);
+        for (int c = 0; c < p.n_col; ++c) {
+            float wx = e.px + m[0] * p.col[c][0] + m[1] * p.col[c][1] + m[2] * p.col[c][2];
+            float wy = e.py + m[3] * p.col[c][0] + m[4] * p.col[c][1] + m[5] * p.col[c][2];
+            float wz = e.pz + m[6] * p.col[c][0] + m[7] * p.col[c][1] + m[8] * p.col[c][2];
+            float qx = wx - ox, qy = wy - oy;
+            hit = hit || (qx * qx + qy * qy <= r2 && wz <= oh + p.contact_margin);
+        }
+    }
+    {
+        float sx = o.dkx, sy = o.dky, sz = o.dkz + p.duck_radius;
+        float ddx = e.px - sx, ddy = e.py - sy, ddz = e.pz - sz;
+        float rr = p.duck_radius + reach;
+        if (ddx * ddx + ddy * ddy + ddz * ddz <= rr * rr) {
+            const float r2 = (p.duck_radius + p.contact_margin) * (p.duck_radius + p.contact_margin);
+            for (int c = 0; c < p.n_col; ++c) {
+                float wx = e.px + m[0] * p.col[c][0] + m[1] * p.col[c][1] + m[2] * p.col[c][2] - sx;
+                float wy = e.py + m[3] * p.col[c][0] + m[4] * p.col[c][1] + m[5] * p.col[c][2] - sy;
+                float wz = e.pz + m[6] * p.col[c][0] + m[7] * p.col[c][1] + m[8] * p.col[c][2] - sz;
+                hit = hit || (wx * wx + wy * wy + wz * wz <= r2);
+            }
+        }
+    }
+    return hit;
+}
+
+// _reset_duck_phase_state + _spawn_duck + _spawn_obstacles (targets must already be sampled)
+__device__ __forceinline__ void ol_reset(const FwDev& p, const FwPlanes& pl, OlState& o, int i, uint32_t gid, uint32_t episode,
+                                         float* so, int tid, int stride) {
+    o.duck_phase = 0; o.seen = 0; o.lock = 0; o.has_prev = 0; o.prev_est = 0.0f;
+    o.last_cx = 0.5f; o.last_cy = 0.5f; o.last_area = 0.0f; o.last_depth = 0.0f;
+    o.since = 60; o.post_wp = 0; o.cam_valid = 0; o.f_visible = 0;
+    o.f_cx = o.f_cy = o.f_area = o.f_depth = 0.0f; o.f_dl = o.f_dc = o.f_dr = 0.0f;
+    o.vis_dl = o.vis_dc = o.vis_dr = 0.0f; o.vis_flag = 0.0f;
+    if (p.num_targets > 0) {
+        const int t = p.num_targets - 1;
+        o.dkx = pl.targets[(size_t)(t * 3 + 0) * p.n + i];
+        o.dky = pl.targets[(size_t)(t * 3 + 1) * p.n + i];
+    } else { o.dkx = 10.0f; o.dky = 0.0f; }
+    o.dkz = 0.05f;
+    int n = 0;
+    for (int k = 0; k < p.num_obstacles; ++k) {
+        uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid, episode, (uint32_t)k, FWD_STREAM_OBST);
+        float h = p.obst_h_lo + fw_u01(r.x) * (p.obst_h_hi - p.obst_h_lo);
+        float x = -0.5f * p.dome + fw_u01(r.y) * p.dome;
+        float y = -0.5f * p.dome + fw_u01(r.z) * p.dome;
+        if (x * x + y * y < 100.0f) continue;
+        OL_S(so, n, 0, tid, stride) = x; OL_S(so, n, 1, tid, stride) = y; OL_S(so, n, 2, tid, stride) = h;
+        pl.obst[(size_t)(n * 3 + 0) * p.n + i] = x;
+        pl.obst[(size_t)(n * 3 + 1) * p.n + i] = y;
+        pl.obst[(size_t)(n * 3 + 2) * p.n + i] = h;
+        ++n;
+    }
+    o.n_obst = n;
+}

@@ -29,7 +29,10 @@ _STATE_FIELDS = {
     "act": (np.float32, 6), "targets": (np.float32, None), "target_idx": (np.int32, 0),
     "step_count": (np.int32, 0), "physics_steps": (np.int32, 0), "episode": (np.uint32, 0),
     "new_dist": (np.float32, 0), "wind": (np.float32, 7),
+    # ObjLock task only
+    "duck": (np.float32, 3), "obst": (np.float32, (32, 3)), "ol_f": (np.float32, 12), "ol_i": (np.int32, 9),
 }
+_OBJLOCK_FIELDS = ("duck", "obst", "ol_f", "ol_i")
 
 
 class FixedwingVecEnv:
@@ -248,11 +251,21 @@ class FixedwingVecEnv:
         out = {}
         s = _lib.FwStateHostC()
         for k, (dt, w) in _STATE_FIELDS.items():
-            shape = (n, T, 3) if k == "targets" else ((n,) if w == 0 else (n, w))
+            if k in _OBJLOCK_FIELDS and self.cfg.task != 2:
+                continue
+            shape = self._state_shape(k, w, n, T)
             out[k] = np.zeros(shape, dtype=dt)
             setattr(s, k, out[k].ctypes.data_as(C.c_void_p).value)
         _lib.check(self.lib.fw_get_state(self._h, C.byref(s)))
         return out
+
+    @staticmethod
+    def _state_shape(k, w, n, T):
+        if k == "targets":
+            return (n, T, 3)
+        if isinstance(w, tuple):
+            return (n, *w)
+        return (n,) if w == 0 else (n, w)
 
     def set_state(self, state: dict[str, np.ndarray]) -> None:
         n, T = self.num_envs, max(self.cfg.num_targets, 1)
@@ -262,7 +275,9 @@ class FixedwingVecEnv:
             if k not in _STATE_FIELDS:
                 raise KeyError(f"unknown state field {k!r}")
             dt, w = _STATE_FIELDS[k]
-            shape = (n, T, 3) if k == "targets" else ((n,) if w == 0 else (n, w))
+            if k in _OBJLOCK_FIELDS and self.cfg.task != 2:
+                continue
+            shape = self._state_shape(k, w, n, T)
             a = np.ascontiguousarray(np.asarray(v).astype(dt)).reshape(shape)
             keep.append(a)
             setattr(s, k, a.ctypes.data_as(C.c_void_p).value)

@@ -1,0 +1,124 @@
+"""GPU parity of the Waypoint+ObjLock task (BASELINE config 4) against the fp64 oracle: reset (duck, obstacles,
+wind, warm-up camera frame), single-step from injected state incl. the duck-phase state machine, and a
+free-running flag comparison.  Tolerances as in test_parity_gpu.py."""
+import numpy as np
+import pytest
+
+import pyflyt_drone_b200 as fw
+from pyflyt_drone_b200.config import FLAG_TERM, FLAG_TRUNC
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+GROUPS = {"ang_vel": slice(0, 3), "ang_pos": slice(3, 6), "lin_vel": slice(6, 9), "lin_pos": slice(9, 12),
+          "action": slice(12, 16), "aux": slice(16, 22), "delta0": slice(22, 25), "delta1": slice(25, 28)}
+
+
+@pytest.fixture(scope="module")
+def fo(oracle_mod):
+    return oracle_mod
+
+
+def group_err(got, ref):
+    out = {}
+    for k, sl in GROUPS.items():
+        d = np.abs(got[:, sl] - ref[:, sl]).max(axis=1)
+        out[k] = float((d / np.maximum(np.abs(ref[:, sl]).max(axis=1), 1.0)).max()) if len(d) else 0.0
+    return out
+
+
+def angle_safe(og, oc):
+    og = og.copy()
+    d = og[:, 3:6] - oc[:, 3:6]
+    og[:, 3:6] = oc[:, 3:6] + (d + np.pi) % (2 * np.pi) - np.pi
+    return og
+
+
+def pair(fo, n, cfg, seed=11):
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    return FixedwingVecEnv(n, config=cfg, seed=seed), fo.OracleVecEnv(cfg.as_dict(), n, seed=seed)
+
+
+def test_objlock_reset_parity(fo):
+    cfg = fw.waypoint_objlock()
+    env, orc = pair(fo, 300, cfg)
+    og, oc = env.reset(), orc.reset()
+    assert max(group_err(og, oc).values()) < RTOL
+    sg, sc = env.get_state(), orc.get_state()
+    assert np.array_equal(sg["ol_i"], sc["ol_i"])
+    n = sc["ol_i"][:, 8]
+    for i in range(300):
+        assert np.abs(sg["obst"][i, : n[i]] - sc["obst"][i, : n[i]]).max() < 1e-4
+    assert np.abs(sg["duck"] - sc["duck"]).max() < 1e-4
+    assert np.abs(sg["wind"] - sc["wind"]).max() < 1e-5
+    assert np.abs(sg["ol_f"] - sc["ol_f"]).max() < 2e-3 * 255      # band distances are metres up to far = 255
+    env.close()
+
+
+@pytest.mark.parametrize("scenario", ["random_flight", "duck_phase"])
+def test_objlock_single_step_parity(fo, scenario):
+    cfg = fw.waypoint_objlock(noise_ratio=0.0)
+    N = 512
+    env, orc = pair(fo, N, cfg)
+    env.reset(); orc.reset()
+    rng = np.random.default_rng(3)
+    if scenario == "duck_phase":
+        # put every env past its waypoints, 40-70 m from its duck and looking at it
+        st = orc.get_state()
+        T = cfg.num_targets
+        st["target_idx"][:] = T
+        ang = rng.uniform(-np.pi, np.pi, N)
+        dist = rng.uniform(40, 70, N)
+        st["pos"][:, 0] = st["duck"][:, 0] - dist * np.cos(ang)
+        st["pos"][:, 1] = st["duck"][:, 1] - dist * np.sin(ang)
+        st["pos"][:, 2] = rng.uniform(15, 30, N)
+        st["quat"][:] = np.stack([0 * ang, 0 * ang, np.sin(ang / 2), np.cos(ang / 2)], 1)
+        st["vel"][:] = np.stack([20 * np.cos(ang), 20 * np.sin(ang), 0 * ang], 1)
+        st["omega"][:] = 0
+        keep = np.linalg.norm(st["pos"], axis=1) < 95
+        st["pos"][~keep] = [0, 0, 20]
+        orc.set_state(st)
+    worst, mism, events = {}, 0, dict(done=0, phase=0, lock=0, strike=0, visible=0)
+    for k in range(60):
+        env.set_state(orc.get_state())
+        a = rng.uniform(-1, 1, (N, 4)).astype(np.float32)
+        if scenario == "duck_phase":
+            a[:, :3] *= 0.15
+        og, rg, fg, tg = env.step_arrays(a)
+        og, rg, fg, tg = og.copy(), rg.copy(), fg.copy().astype(np.int32), tg.copy()
+        oc, rc, fc, tc = orc.step(a.astype(np.float64))
+        sg, sc = env.get_state(), orc.get_state()
+        mism += int((fg != fc).sum()) + int((sg["ol_i"] != sc["ol_i"]).sum())
+        done = (fc & (FLAG_TERM | FLAG_TRUNC)) != 0
+        ok = fg == fc
+        e = group_err(angle_safe(og, oc)[ok], oc[ok])
+        for g, v in e.items():
+            worst[g] = max(worst.get(g, 0.0), v)
+        assert np.abs(rg - rc)[ok].max() <= 2e-4 * max(1.0, np.abs(rc).max())
+        assert np.abs(sg["ol_f"] - sc["ol_f"])[ok].max() < 1e-3 * 255
+        events["done"] += int(done.sum()); events["phase"] += int(sc["ol_i"][:, 0].sum())
+        events["lock"] += int((sc["ol_i"][:, 6] > 0).sum()); events["strike"] += int(((fc & 32) != 0).sum())
+        events["visible"] += int(sc["ol_i"][:, 4].sum())
+    print(f"\n[objlock/{scenario}] worst group rel err " + ", ".join(f"{g}={v:.1e}" for g, v in worst.items())
+          + f"; flag/state-machine mismatches {mism}; events {events}")
+    assert max(worst.values()) < RTOL
+    assert mism == 0
+    if scenario == "duck_phase":
+        assert events["phase"] > 0 and events["visible"] > 0
+    env.close()
+
+
+def test_objlock_random_rollout_matches_oracle_counters(fo):
+    cfg = fw.waypoint_objlock()
+    N = 256
+    env, orc = pair(fo, N, cfg, seed=21)
+    env.reset(); orc.reset()
+    env.step_random(16)
+    orc.rollout_random(16)
+    sg, sc = env.get_state(), orc.get_state()
+    same = np.array_equal(sg["episode"], sc["episode"])
+    agree = float((sg["episode"] == sc["episode"]).mean())
+    print(f"\n[objlock] 16-step random rollout: episode counters agree on {agree * 100:.1f}% of envs")
+    assert agree > 0.97
+    ok = sg["episode"] == sc["episode"]
+    assert np.abs(sg["pos"][ok] - sc["pos"][ok]).max() < 5e-3
+    env.close()
