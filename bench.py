@@ -37,8 +37,8 @@ if ROOT not in sys.path:
 
 METRIC = "fixedwing_env_steps_per_sec"
 UNIT = "env-steps/s"
-BYTES_PER_STEP = {"physics_only": 152, "waypoints_v3": 332}       # SURVEY.md section 8(d), figures of record
-FLOPS_PER_STEP = {"physics_only": 6400, "waypoints_v3": 7000}
+BYTES_PER_STEP = {"physics_only": 152, "waypoints_v3": 332, "waypoint_objlock": 400}
+FLOPS_PER_STEP = {"physics_only": 6400, "waypoints_v3": 7000, "waypoint_objlock": 7000}
 L2_BYTES = 126 * 1024 * 1024
 
 
@@ -49,8 +49,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU per launch")
-    ap.add_argument("--workload", choices=["physics_only", "waypoints_v3", "ppo"], default="physics_only",
+    ap.add_argument("--workload", choices=["physics_only", "waypoints_v3", "waypoint_objlock", "ppo"], default="physics_only",
                     help="ppo = BASELINE configs[2]: PPO Fixedwing-Waypoints rollout+update (a step is one PPO iteration)")
+    ap.add_argument("--ppo-preset", choices=["waypoints_v3", "waypoint_objlock"], default="waypoints_v3")
     ap.add_argument("--ppo-envs", type=int, default=4096)
     ap.add_argument("--ppo-n-steps", type=int, default=128)
     ap.add_argument("--ppo-minibatches", type=int, default=4)
@@ -205,7 +206,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     over = {}
     cfg = fw.make_config(args.workload, **over)
     N = args.envs
-    state_bytes = N * (6 * 16 + 4 + (cfg.num_targets * 12))
+    state_bytes = N * (6 * 16 + 4 + (cfg.num_targets * 12) + (5 * 16 + 32 * 12 if cfg.task == 2 else 0))
     replicas = max(2, int(np.ceil(2 * L2_BYTES / state_bytes)))
     envs = [FixedwingVecEnv(N, config=cfg, device=local_rank, seed=1234, env_id0=(rank * replicas + r) * N)
             for r in range(replicas)]
@@ -320,7 +321,7 @@ def run_ppo(args, rank: int, local_rank: int, world: int):
     from pyflyt_drone_b200.ppo import PPO
     from pyflyt_drone_b200.vec_env import FixedwingVecEnv
     N, T = args.ppo_envs, args.ppo_n_steps
-    env = FixedwingVecEnv(N, preset="waypoints_v3", device=local_rank, seed=42, env_id0=rank * N)
+    env = FixedwingVecEnv(N, preset=args.ppo_preset, device=local_rank, seed=42, env_id0=rank * N)
     model = PPO("MlpPolicy", env, learning_rate=3e-4, n_steps=T, batch_size=N * T // args.ppo_minibatches,
                 n_epochs=args.ppo_epochs, gamma=0.99, gae_lambda=0.95, clip_range=0.2, ent_coef=0.001, vf_coef=0.5,
                 max_grad_norm=0.5, seed=42)
@@ -344,7 +345,7 @@ def run_ppo(args, rank: int, local_rank: int, world: int):
         line = {"metric": "ppo_env_steps_per_sec", "value": K * N * T * world / dt, "unit": "env-steps/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": "ppo: Fixedwing-Waypoints-v3 PPO rollout+update (BASELINE configs[2])",
+                "config": {"workload": f"ppo: {args.ppo_preset} PPO rollout+update (BASELINE configs[2]/[3])",
                            "envs_per_gpu": N, "n_steps": T, "minibatches_per_epoch": args.ppo_minibatches,
                            "n_epochs": args.ppo_epochs, "rollout_s": st.rollout_s, "update_s": st.update_s,
                            "rollout_env_steps_per_sec": st.env_steps / max(st.rollout_s, 1e-9),

@@ -103,15 +103,18 @@ __device__ __forceinline__ float ol_ray_sphere(float ox, float oy, float oz, flo
     return t > 0.0f ? t : INF;
 }
 
-__device__ __forceinline__ float ol_depth_buf(const FwDev& p, float z) {
-    if (z < p.cam_near) z = p.cam_near;
-    if (z > p.cam_far) return 1.0f;
-    return p.cam_far * (z - p.cam_near) / ((p.cam_far - p.cam_near) * z);
+// The reference averages OpenGL depth-BUFFER values d = far (z - near) / ((far - near) z) over a band and maps the
+// mean back to metres with z = far near / (far - (far - near) d).  Since d is affine in 1/z, that round trip is
+// exactly the HARMONIC mean of the clamped depths, 1 / mean(1 / clamp(z, near, far)) (a miss counts as z = far).
+// The harmonic form is what the kernel evaluates: the literal form loses all fp32 precision near d = 1.
+__device__ __forceinline__ float ol_inv_depth(const FwDev& p, float z) {
+    return 1.0f / fminf(fmaxf(z, p.cam_near), p.cam_far);
 }
-__device__ __forceinline__ float ol_buf_to_m(const FwDev& p, float d) {
-    float denom = p.cam_far - (p.cam_far - p.cam_near) * d;
-    if (fabsf(denom) < 1e-9f) return p.cam_far;
-    return p.cam_far * p.cam_near / denom;
+__device__ __forceinline__ float ol_band_metres(const FwDev& p, float sum_inv, int cnt) {
+    if (cnt == 0) return 0.0f;
+    float mean_inv = sum_inv / (float)cnt;
+    if (mean_inv * p.cam_near >= 1.0f) return 0.0f;       // every pixel on the near plane: mean buffer value 0 -> 0.0
+    return 1.0f / mean_inv;
 }
 
 // Camera.capture_image stand-in + the image reductions of _compute_vision_features
@@ -175,13 +178,12 @@ __device__ __forceinline__ void ol_capture(const FwDev& p, const EnvState& e, Ol
         }
         float td = ol_ray_sphere(cx, cy, cz, dx, dy, dz, sx, sy, sz, Rd);
         if (td < best) continue;                       // duck pixel: excluded from the band means
-        float db = (best < INF) ? ol_depth_buf(p, best) : 1.0f;
-        if (col < x1) { sum0 += db; c0++; } else if (col < x2) { sum1 += db; c1++; } else { sum2 += db; c2++; }
+        float iv = (best < INF) ? ol_inv_depth(p, best) : 1.0f / p.cam_far;
+        if (col < x1) { sum0 += iv; c0++; } else if (col < x2) { sum1 += iv; c1++; } else { sum2 += iv; c2++; }
     }
-    float m0 = c0 ? sum0 / (float)c0 : 0.0f, m1 = c1 ? sum1 / (float)c1 : 0.0f, m2 = c2 ? sum2 / (float)c2 : 0.0f;
-    o.f_dl = m0 > 0.0f ? ol_buf_to_m(p, m0) : 0.0f;
-    o.f_dc = m1 > 0.0f ? ol_buf_to_m(p, m1) : 0.0f;
-    o.f_dr = m2 > 0.0f ? ol_buf_to_m(p, m2) : 0.0f;
+    o.f_dl = ol_band_metres(p, sum0, c0);
+    o.f_dc = ol_band_metres(p, sum1, c1);
+    o.f_dr = ol_band_metres(p, sum2, c2);
     o.cam_valid = 1;
 }
 
