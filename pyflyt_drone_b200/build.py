@@ -17,6 +17,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # flush fp32 denormals: MUFU.RCP/RSQ/SIN/COS then need no 2^24 rescue sequences (4-6 instructions each)
     "--ftz=true",
+    # IEEE-rounded division / sqrt cost 10-20 instructions each; the 2-ulp SFU forms are far inside the parity
+    # tolerance (1e-4 relative per step) and are what the hot loops are written for
+    "--prec-div=false", "--prec-sqrt=false",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--threads", "4",
 ]
 

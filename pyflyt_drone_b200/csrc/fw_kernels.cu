@@ -311,7 +311,7 @@ __global__ void fw_warm_kernel(const __grid_constant__ FwDev p, const FwPlanes p
 // ------------------------------------------------------------------ launchers
 static inline size_t stage_bytes(const FwDev& p) {
     size_t obs = (size_t)(FW_BLOCK / 32) * 32 * (size_t)(p.obs_dim > 0 ? p.obs_dim : 1) * 4;
-    size_t obst = p.task == 2 ? (size_t)(p.num_obstacles > 0 ? p.num_obstacles : 1) * 3 * FW_BLOCK * 4 : 0;
+    size_t obst = p.task == 2 ? (size_t)(p.num_obstacles > 0 ? p.num_obstacles : 1) * 4 * FW_BLOCK * 4 : 0;
     return obs + obst;
 }
 static inline int grid_for(int n) { return (n + FW_BLOCK - 1) / FW_BLOCK; }

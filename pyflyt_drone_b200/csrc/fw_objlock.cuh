@@ -53,14 +53,15 @@ __device__ __forceinline__ void ol_store(const FwPlanes& pl, int i, const OlStat
     pl.v3[i] = make_int4(bits, o.seen, o.lock, o.since);
 }
 
-// obstacle table of this thread in shared memory: so[(k*3 + c) * FWD_OL_STRIDE + tid]
-#define OL_S(so, k, c, tid, stride) (so)[((k) * 3 + (c)) * (stride) + (tid)]
+// obstacle table of this thread in shared memory: so[(k*4 + c) * stride + tid]; c = x, y, height, and a scratch
+// word holding the pixel-column interval of the current camera frame
+#define OL_S(so, k, c, tid, stride) (so)[((k) * 4 + (c)) * (stride) + (tid)]
 
 __device__ __forceinline__ void ol_stage_obstacles(const FwDev& p, const FwPlanes& pl, int i, int n_obst, float* so, int tid,
                                                    int stride) {
     for (int k = 0; k < n_obst; ++k)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) OL_S(so, k, c, tid, stride) = pl.obst[(size_t)(k * 3 + c) * p.n + i];
+        for (int c = 0; c < 3; ++c) OL_S(so, k, c, tid, stride) = pl.obst[(size_t)(k * 3 + c) * p.n + i];   // c = 3: scratch
 }
 
 // nearest positive hit of ray o + t d with the finite vertical cylinder (cx, cy, height h, radius r); inf if none
@@ -117,8 +118,37 @@ __device__ __forceinline__ float ol_band_metres(const FwDev& p, float sum_inv, i
     return 1.0f / mean_inv;
 }
 
+// Conservative pixel-column interval [lo, hi] of the middle row whose rays can pass within `rad` (horizontally) of
+// the vertical axis through (px, py) relative to the camera.  Horizontal ray directions form the family A + xn B
+// (xn = normalised column coordinate in [-1, 1]); |cross(A + xn B, P)| <= rad |A + xn B| is a quadratic in xn.
+// Columns outside the interval cannot hit the cylinder / sphere, so skipping them leaves the frame unchanged.
+__device__ __forceinline__ void ol_col_interval(float Ax, float Ay, float Bx, float By, float AA, float AB, float BB,
+                                                float px, float py, float rad, int w, int& lo, int& hi) {
+    const float rr = rad * rad * 1.01f + 1e-4f;
+    const float cA = Ax * py - Ay * px, cB = Bx * py - By * px;
+    const float qa = cB * cB - rr * BB, qb = cA * cB - rr * AB, qc = cA * cA - rr * AA;
+    lo = 0; hi = w - 1;
+    if (qa > 1e-7f) {
+        const float disc = qb * qb - qa * qc;
+        if (disc < 0.0f) { lo = 1; hi = 0; return; }
+        const float sq = sqrtf(disc), inv = 1.0f / qa;
+        const float x0 = (-qb - sq) * inv, x1 = (-qb + sq) * inv;
+        const float c0 = (x0 + 1.0f) * 0.5f * (float)w - 0.5f, c1 = (x1 + 1.0f) * 0.5f * (float)w - 0.5f;
+        lo = max(0, (int)floorf(fmaxf(c0, -4.0f)) - 1);
+        hi = min(w - 1, (int)ceilf(fminf(c1, (float)w + 4.0f)) + 1);
+    }
+}
+
+__device__ __forceinline__ void ol_mask_set(uint32_t (&mask)[4], int lo, int hi) {
+#pragma unroll
+    for (int wd = 0; wd < 4; ++wd) {
+        const int a = max(lo - 32 * wd, 0), b = min(hi - 32 * wd, 31);
+        if (a <= b) mask[wd] |= (0xffffffffu >> (31 - b)) & (0xffffffffu << a);
+    }
+}
+
 // Camera.capture_image stand-in + the image reductions of _compute_vision_features
-__device__ __forceinline__ void ol_capture(const FwDev& p, const EnvState& e, OlState& o, const float* so, int tid, int stride) {
+__device__ __forceinline__ void ol_capture(const FwDev& p, const EnvState& e, OlState& o, float* so, int tid, int stride) {
     const float INF = __int_as_float(0x7f800000);
     Mat3 R = fw_quat_mat(e.qx, e.qy, e.qz, e.qw);
     const float* m = R.m;
@@ -161,23 +191,51 @@ __device__ __forceinline__ void ol_capture(const FwDev& p, const EnvState& e, Ol
         o.f_area = fminf(a, 1.0f);
         o.f_depth = zc - Rd;
     }
-    // obstacle bands: middle row, three column bands, mean depth-buffer value of non-duck pixels
+    // obstacle bands: middle row, three column bands, harmonic-mean depth of non-duck pixels.
+    // First the (few) columns each cylinder / the duck can cover, so that most columns only meet the ground.
     const int w = p.cam_res, x1 = w / 3, x2 = 2 * w / 3, ymid = w / 2;
     const float vrow = 2.0f * ((float)ymid + 0.5f) / (float)w - 1.0f;
+    const float Ax = fx - vrow * ux, Ay = fy - vrow * uy, Az = fz - vrow * uz;
+    const float AA = Ax * Ax + Ay * Ay, AB = Ax * rx + Ay * ry, BB = rx * rx + ry * ry;
+    const bool use_mask = w <= 128;
+    uint32_t cmask[4] = {0u, 0u, 0u, 0u}, dmask[4] = {0u, 0u, 0u, 0u};
+    for (int k = 0; k < o.n_obst; ++k) {
+        int lo, hi;
+        ol_col_interval(Ax, Ay, rx, ry, AA, AB, BB, OL_S(so, k, 0, tid, stride) - cx, OL_S(so, k, 1, tid, stride) - cy,
+                        p.obst_radius, w, lo, hi);
+        OL_S(so, k, 3, tid, stride) = __int_as_float((lo & 0xffff) | (hi << 16));
+        if (use_mask) ol_mask_set(cmask, lo, hi);
+    }
+    {
+        int lo, hi;
+        ol_col_interval(Ax, Ay, rx, ry, AA, AB, BB, sx - cx, sy - cy, Rd, w, lo, hi);
+        if (use_mask) ol_mask_set(dmask, lo, hi);
+    }
     float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
     int c0 = 0, c1 = 0, c2 = 0;
     for (int col = 0; col < w; ++col) {
         float xn = 2.0f * ((float)col + 0.5f) / (float)w - 1.0f;
-        float dx = fx + xn * rx - vrow * ux, dy = fy + xn * ry - vrow * uy, dz = fz + xn * rz - vrow * uz;
+        float dx = Ax + xn * rx, dy = Ay + xn * ry, dz = Az + xn * rz;
         float best = INF;
         if (dz < -1e-12f) { float t = -cz / dz; if (t > 0.0f && t < best) best = t; }
-        for (int k = 0; k < o.n_obst; ++k) {
-            float t = ol_ray_cylinder(cx, cy, cz, dx, dy, dz, OL_S(so, k, 0, tid, stride), OL_S(so, k, 1, tid, stride),
-                                      OL_S(so, k, 2, tid, stride), p.obst_radius);
-            if (t < best) best = t;
+        const int wd = (col >> 5) & 3;      // select chain instead of a dynamically indexed (local-memory) array
+        const uint32_t cw = wd == 0 ? cmask[0] : (wd == 1 ? cmask[1] : (wd == 2 ? cmask[2] : cmask[3]));
+        const uint32_t dw = wd == 0 ? dmask[0] : (wd == 1 ? dmask[1] : (wd == 2 ? dmask[2] : dmask[3]));
+        const bool maybe_cyl = !use_mask || ((cw >> (col & 31)) & 1u);
+        if (maybe_cyl) {
+            for (int k = 0; k < o.n_obst; ++k) {
+                const int iv = __float_as_int(OL_S(so, k, 3, tid, stride));
+                if (col < (iv & 0xffff) || col > (iv >> 16)) continue;
+                float t = ol_ray_cylinder(cx, cy, cz, dx, dy, dz, OL_S(so, k, 0, tid, stride), OL_S(so, k, 1, tid, stride),
+                                          OL_S(so, k, 2, tid, stride), p.obst_radius);
+                if (t < best) best = t;
+            }
         }
-        float td = ol_ray_sphere(cx, cy, cz, dx, dy, dz, sx, sy, sz, Rd);
-        if (td < best) continue;                       // duck pixel: excluded from the band means
+        const bool maybe_duck = !use_mask || ((dw >> (col & 31)) & 1u);
+        if (maybe_duck) {
+            float td = ol_ray_sphere(cx, cy, cz, dx, dy, dz, sx, sy, sz, Rd);
+            if (td < best) continue;                   // duck pixel: excluded from the band means
+        }
         float iv = (best < INF) ? ol_inv_depth(p, best) : 1.0f / p.cam_far;
         if (col < x1) { sum0 += iv; c0++; } else if (col < x2) { sum1 += iv; c1++; } else { sum2 += iv; c2++; }
     }
