@@ -55,37 +55,15 @@ __device__ __forceinline__ void fw_flush_obs(float* __restrict__ dst_base, const
 
 // One agent step of env i held in registers (FixedwingBaseEnv.step + SubprocVecEnv reset-on-done).
 // Returns the reward; flag bits in `bits`; the observation (if TASK != 0) is left in `row`.
-// ObjLock reset: begin_reset, waypoints, duck/obstacles, warm-up with the camera frame PyFlyt captures at physics
-// step 12 of it, then the compute_state of end_reset (fixedwing_waypoint_objlock_env.py:170-195)
-__device__ __forceinline__ void fw_reset_env_objlock(const FwDev& p, const FwPlanes& pl, EnvState& e, OlState& ol, float* so,
-                                                     int i, uint32_t gid, uint32_t episode, int tid) {
-    float4 w0, w1;
-    fw_reset_begin(p, pl, e, i, gid, episode, w0, w1);
-    fw_sample_targets(p, pl, i, gid, episode);
-    ol_reset(p, pl, ol, i, gid, episode, so, tid, FW_BLOCK);
-    int done = 0;
-    while (done < p.warmup_substeps) {
-        int next = p.warmup_substeps;
-        if (p.cam_interval > 0) next = min(next, (done / p.cam_interval + 1) * p.cam_interval);
-        fw_warm(p, e, w0, w1, next - done, false);
-        done = next;
-        if (p.cam_interval > 0 && done % p.cam_interval == 0 && done % p.substeps_per_inner == 0)
-            ol_capture(p, e, ol, so, tid, FW_BLOCK);
-    }
-    fw_reset_finish(p, pl, e, i);
-    ol_vision_and_phase(p, ol, e.tidx >= p.num_targets);
-}
-
 template <int TASK>
-__device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl, EnvState& e, OlState& ol, float* so, int i,
+__device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl, EnvState& e, int i,
                                              uint32_t gid, float a0, float a1, float a2, float a3, const float4& w0_in,
                                              const float4& w1_in, float& ep_ret, float* row, float* term_obs_row,
                                              uint32_t& bits) {
-    const int tid = threadIdx.x;
     float4 w0 = w0_in, w1 = w1_in;
     // FixedwingBaseEnv.step: reward reset once, thrust remapped to [0,1], setpoint latched
     float reward = -0.1f;
-    bool term = false, trunc = false, col = false, oob = false, complete = false, strike = false;
+    bool term = false, trunc = false, col = false, oob = false, complete = false;
     float cmd[6];
     fw_map_setpoint(p, a0, a1, a2, a3 * 0.5f + 0.5f, cmd);
     float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
@@ -110,11 +88,8 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
             }
             float wx, wy, wz;
             fw_wind(p, ps, w0, w1, wx, wy, wz);
-            if (TASK == 2) contact = contact || ol_contact(p, e, ol, so, tid, FW_BLOCK);   // pose entering the step
             fw_substep(p, e, cmd, wx, wy, wz, nz, contact);
         }
-        // drone.update_last(): camera frame every cam_interval physics steps
-        if (TASK == 2 && p.cam_interval > 0 && (e.physics_steps % p.cam_interval) == 0) ol_capture(p, e, ol, so, tid, FW_BLOCK);
         // compute_state: WaypointHandler.distance_to_targets (old <- new, new <- |delta_0|)
         float old_dist = e.new_dist;
         obs_tidx = e.tidx;
@@ -124,7 +99,6 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
             float dz = pl.targets[(size_t)(e.tidx * 3 + 2) * p.n + i] - e.pz;
             e.new_dist = sqrtf(dx * dx + dy * dy + dz * dz);
         }
-        if (TASK == 2) ol_vision_and_phase(p, ol, e.tidx >= p.num_targets);
         // compute_base_term_trunc_reward
         if (e.step_count > p.max_steps) trunc = true;
         if (contact) { reward = -100.0f; col = true; term = true; }
@@ -141,46 +115,12 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
                 if (p.complete_truncates && all) trunc = true;
             }
         }
-        if (TASK == 2 && !(col || oob)) {          // early return on crash (objlock_env.py:282-283)
-            if (e.tidx < p.num_targets) {
-                if (!p.sparse_reward) {
-                    reward += fmaxf(3.0f * (old_dist - e.new_dist), 0.0f);
-                    reward += 1.0f / e.new_dist;
-                }
-                if (e.new_dist < p.goal_reach) {
-                    reward = 100.0f;
-                    e.tidx += 1;
-                    if (e.tidx >= p.num_targets) { term = false; trunc = false; }    // keep flying into the duck phase
-                }
-                reward -= ol_obstacle_penalty(p, ol, false);
-            } else {
-                term = false;
-                reward -= ol_obstacle_penalty(p, ol, true);
-                if (ol.duck_phase) {
-                    if (!p.sparse_reward && ol.last_depth > 0.0f) reward += 1.0f / fmaxf(ol.last_depth, 2.0f);
-                    if (ol.last_cx > 0.0f) {
-                        float ddx = ol.last_cx - 0.5f, ddy = ol.last_cy - 0.5f;
-                        if (sqrtf(ddx * ddx + ddy * ddy) < 0.35f) { ol.lock += 1; reward += p.lock_step_reward; }
-                        else ol.lock = 0;
-                    } else ol.lock = 0;
-                    const float est = ol.last_depth;
-                    if (ol.has_prev && est > 0.0f) {
-                        float diff = ol.prev_est - est;
-                        if (diff > 0.0f) reward += diff * p.approach_scale;
-                    }
-                    ol.prev_est = est; ol.has_prev = 1;
-                    if (ol.lock >= p.lock_hold && est > 0.0f && est <= p.strike_dist) {
-                        term = true; reward += p.strike_reward; complete = true; strike = true;
-                    }
-                }
-            }
-        }
     }
     e.step_count += 1;
     if (TASK == 1) complete = e.tidx >= p.num_targets;     // info["env_complete"] is sticky within an episode
 
     const bool done = term || trunc;
-    if (TASK != 0 && row != nullptr) fw_write_obs(p, pl, e, i, obs_tidx, a0, a1, a2, a3, row, TASK == 2, ol.dkx, ol.dky, ol.dkz);
+    if (TASK != 0 && row != nullptr) fw_write_obs(p, pl, e, i, obs_tidx, a0, a1, a2, a3, row);
     ep_ret += reward;
     if (done) {
         if (TASK != 0 && term_obs_row != nullptr)
@@ -192,15 +132,13 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
         if (col) atomicAdd(&pl.stats[4], 1.0);
         if (oob) atomicAdd(&pl.stats[5], 1.0);
         if (complete) atomicAdd(&pl.stats[6], 1.0);
-        if (strike) atomicAdd(&pl.stats[7], 1.0);
         // SubprocVecEnv worker: obs = env.reset()
-        if (TASK == 2) fw_reset_env_objlock(p, pl, e, ol, so, i, gid, e.episode + 1u, tid);
-        else fw_reset_env(p, pl, e, i, gid, e.episode + 1u);
+        fw_reset_env(p, pl, e, i, gid, e.episode + 1u);
         if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
-        if (TASK != 0 && row != nullptr) fw_write_obs(p, pl, e, i, 0, 0.f, 0.f, 0.f, 0.f, row, TASK == 2, ol.dkx, ol.dky, ol.dkz);
+        if (TASK != 0 && row != nullptr) fw_write_obs(p, pl, e, i, 0, 0.f, 0.f, 0.f, 0.f, row);
         ep_ret = 0.0f;
     }
-    bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (col ? 4u : 0u) | (oob ? 8u : 0u) | (complete ? 16u : 0u) | (strike ? 32u : 0u);
+    bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (col ? 4u : 0u) | (oob ? 8u : 0u) | (complete ? 16u : 0u);
     return reward;
 }
 
@@ -218,14 +156,11 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
     const int D = p.obs_dim;
     float* stage_warp = stage + (size_t)warp * 32 * D;
     float* row = (TASK != 0 && obs != nullptr) ? stage_warp + (size_t)lane * D : nullptr;
-    float* so = stage + (size_t)(FW_BLOCK / 32) * 32 * (D > 0 ? D : 1);       // ObjLock obstacle table [k][c][thread]
 
     if (i < p.n) {
         const uint32_t gid = p.env_id0 + (uint32_t)i;
         EnvState e;
         fw_load(pl, i, e);
-        OlState ol;
-        if (TASK == 2) { ol_load(pl, i, ol); ol_stage_obstacles(p, pl, i, ol.n_obst, so, threadIdx.x, FW_BLOCK); }
         float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
         if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
         float ep_ret = pl.ep_ret[i];
@@ -237,18 +172,17 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
                 float a0 = 2.0f * fw_u01(r.x) - 1.0f, a1 = 2.0f * fw_u01(r.y) - 1.0f;
                 float a2 = 2.0f * fw_u01(r.z) - 1.0f, a3 = 2.0f * fw_u01(r.w) - 1.0f;
                 if (p.wind_mode != 0 && st > 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
-                reward = fw_env_step<TASK>(p, pl, e, ol, so, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
+                reward = fw_env_step<TASK>(p, pl, e, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
                                            st == spl - 1 ? row : nullptr, nullptr, bits);
             }
         } else {
             float4 a = act[i];
-            reward = fw_env_step<TASK>(p, pl, e, ol, so, i, gid, a.x, a.y, a.z, a.w, w0, w1, ep_ret, row,
+            reward = fw_env_step<TASK>(p, pl, e, i, gid, a.x, a.y, a.z, a.w, w0, w1, ep_ret, row,
                                        (TASK != 0 && term_obs != nullptr && row != nullptr) ? term_obs + (size_t)i * D : nullptr,
                                        bits);
         }
         pl.ep_ret[i] = ep_ret;
         fw_store(pl, i, e);
-        if (TASK == 2) ol_store(pl, i, ol);
         if (rew != nullptr) rew[i] = reward;
         if (flg != nullptr) flg[i] = (uint8_t)bits;
     }
@@ -267,27 +201,264 @@ fw_reset_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const uint8_
     const int D = p.obs_dim;
     float* stage_warp = stage + (size_t)warp * 32 * D;
     float* row = stage_warp + (size_t)lane * D;
-    float* so = stage + (size_t)(FW_BLOCK / 32) * 32 * (D > 0 ? D : 1);
     if (i < p.n) {
         EnvState e;
         fw_load(pl, i, e);
-        OlState ol;
-        if (p.task == 2) ol_load(pl, i, ol);
         const bool sel = !emit_only && (mask == nullptr || mask[i] != 0);
         if (sel) {
-            if (p.task == 2) {
-                fw_reset_env_objlock(p, pl, e, ol, so, i, p.env_id0 + (uint32_t)i, e.episode + 1u, threadIdx.x);
-                ol_store(pl, i, ol);
-            } else {
-                fw_reset_env(p, pl, e, i, p.env_id0 + (uint32_t)i, e.episode + 1u);
-            }
+            fw_reset_env(p, pl, e, i, p.env_id0 + (uint32_t)i, e.episode + 1u);
             pl.ep_ret[i] = 0.0f;
             fw_store(pl, i, e);
         }
         // unselected envs re-emit their current observation (last action unknown -> zeros)
-        if (p.task != 0) fw_write_obs(p, pl, e, i, e.tidx, 0.f, 0.f, 0.f, 0.f, row, p.task == 2, ol.dkx, ol.dky, ol.dkz);
+        if (p.task != 0) fw_write_obs(p, pl, e, i, e.tidx, 0.f, 0.f, 0.f, 0.f, row);
     }
     if (p.task != 0 && obs != nullptr) {
+        const int first_env = blockIdx.x * FW_BLOCK + warp * 32;
+        if (first_env < p.n) fw_flush_obs(obs, stage_warp, D, first_env, p.n, lane, bulk_ok != 0);
+    }
+}
+
+// ================================================================== Waypoint + ObjLock task (warp-converged kernels)
+// The camera frame is produced warp-cooperatively (fw_objlock.cuh: ol_capture_warp), so every lane of a warp has to
+// arrive at each capture point: these kernels replace `break` / early exits by per-lane predicates.
+
+// reset of the lanes with `doing` set: begin_reset, waypoints, duck/obstacles, warm-up with the camera frame PyFlyt
+// captures at physics step 12 of it, then the compute_state of end_reset (fixedwing_waypoint_objlock_env.py:170-195)
+__device__ __forceinline__ void ol_reset_lanes(const FwDev& p, const FwPlanes& pl, bool doing, EnvState& e, OlState& ol,
+                                               float* so, float* depth_row, int i, uint32_t gid, uint32_t episode, int tid) {
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+    if (doing) {
+        fw_reset_begin(p, pl, e, i, gid, episode, w0, w1);
+        fw_sample_targets(p, pl, i, gid, episode);
+        ol_reset(p, pl, ol, i, gid, episode, so, tid, FW_BLOCK);
+    }
+    __syncwarp();
+    int dn = 0;
+    while (dn < p.warmup_substeps) {                       // trip count depends on the config only: warp-uniform
+        int next = p.warmup_substeps;
+        if (p.cam_interval > 0) next = min(next, (dn / p.cam_interval + 1) * p.cam_interval);
+        if (doing) fw_warm(p, e, w0, w1, next - dn, false);
+        dn = next;
+        const bool need = doing && p.cam_interval > 0 && dn % p.cam_interval == 0 && dn % p.substeps_per_inner == 0;
+        ol_capture_warp(p, need, e, ol, so, tid, FW_BLOCK, depth_row);
+    }
+    if (doing) {
+        fw_reset_finish(p, pl, e, i);
+        ol_vision_and_phase(p, ol, e.tidx >= p.num_targets);
+    }
+}
+
+// one agent step for the whole warp; `active` = lane owns an env
+__device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPlanes& pl, bool active, EnvState& e, OlState& ol,
+                                                     float* so, float* depth_row, int i, uint32_t gid, float a0, float a1,
+                                                     float a2, float a3, float4& w0, float4& w1, float& ep_ret, float* row,
+                                                     float* term_obs_row, uint32_t& bits) {
+    const int tid = threadIdx.x;
+    float reward = -0.1f;
+    bool term = false, trunc = false, col = false, oob = false, complete = false, strike = false;
+    float cmd[6];
+    fw_map_setpoint(p, a0, a1, a2, a3 * 0.5f + 0.5f, cmd);
+    float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+    bool have_noise = false;
+    int obs_tidx = e.tidx;
+
+    for (int it = 0; it < p.inner_per_step; ++it) {
+        const bool run = active && !(term || trunc);        // FixedwingBaseEnv.step: `if termination or truncation: break`
+        bool contact = false;
+        if (run) {
+            for (int s = 0; s < p.substeps_per_inner; ++s) {
+                const int ps = e.physics_steps;
+                float nz = 0.0f;
+                if (p.noise_ratio > 0.0f) {
+                    if (!have_noise || (ps & 3) == 0) {
+                        float nn[4];
+                        fw_normals4(p, gid, e.episode, (uint32_t)ps >> 2, nn);
+                        n0 = nn[0]; n1 = nn[1]; n2 = nn[2]; n3 = nn[3];
+                        have_noise = true;
+                    }
+                    const int q = ps & 3;
+                    nz = q == 0 ? n0 : (q == 1 ? n1 : (q == 2 ? n2 : n3));
+                }
+                float wx, wy, wz;
+                fw_wind(p, ps, w0, w1, wx, wy, wz);
+                contact = contact || ol_contact(p, e, ol, so, tid, FW_BLOCK);          // pose entering the step
+                fw_substep(p, e, cmd, wx, wy, wz, nz, contact);
+            }
+        }
+        // drone.update_last(): camera frame every cam_interval physics steps
+        const bool need = run && p.cam_interval > 0 && (e.physics_steps % p.cam_interval) == 0;
+        ol_capture_warp(p, need, e, ol, so, tid, FW_BLOCK, depth_row);
+        if (run) {
+            // compute_state
+            float old_dist = e.new_dist;
+            obs_tidx = e.tidx;
+            if (e.tidx < p.num_targets) {
+                float dx = pl.targets[(size_t)(e.tidx * 3 + 0) * p.n + i] - e.px;
+                float dy = pl.targets[(size_t)(e.tidx * 3 + 1) * p.n + i] - e.py;
+                float dz = pl.targets[(size_t)(e.tidx * 3 + 2) * p.n + i] - e.pz;
+                e.new_dist = sqrtf(dx * dx + dy * dy + dz * dz);
+            }
+            ol_vision_and_phase(p, ol, e.tidx >= p.num_targets);
+            // compute_base_term_trunc_reward
+            if (e.step_count > p.max_steps) trunc = true;
+            if (contact) { reward = -100.0f; col = true; term = true; }
+            if (e.px * e.px + e.py * e.py + e.pz * e.pz > p.dome2) { reward = -100.0f; oob = true; term = true; }
+            if (!(col || oob)) {                       // early return on crash (objlock_env.py:282-283)
+                if (e.tidx < p.num_targets) {
+                    if (!p.sparse_reward) {
+                        reward += fmaxf(3.0f * (old_dist - e.new_dist), 0.0f);
+                        reward += 1.0f / e.new_dist;
+                    }
+                    if (e.new_dist < p.goal_reach) {
+                        reward = 100.0f;
+                        e.tidx += 1;
+                        if (e.tidx >= p.num_targets) { term = false; trunc = false; }    // keep flying into the duck phase
+                    }
+                    reward -= ol_obstacle_penalty(p, ol, false);
+                } else {
+                    term = false;
+                    reward -= ol_obstacle_penalty(p, ol, true);
+                    if (ol.duck_phase) {
+                        if (!p.sparse_reward && ol.last_depth > 0.0f) reward += 1.0f / fmaxf(ol.last_depth, 2.0f);
+                        if (ol.last_cx > 0.0f) {
+                            float ddx = ol.last_cx - 0.5f, ddy = ol.last_cy - 0.5f;
+                            if (sqrtf(ddx * ddx + ddy * ddy) < 0.35f) { ol.lock += 1; reward += p.lock_step_reward; }
+                            else ol.lock = 0;
+                        } else ol.lock = 0;
+                        const float est = ol.last_depth;
+                        if (ol.has_prev && est > 0.0f) {
+                            float diff = ol.prev_est - est;
+                            if (diff > 0.0f) reward += diff * p.approach_scale;
+                        }
+                        ol.prev_est = est; ol.has_prev = 1;
+                        if (ol.lock >= p.lock_hold && est > 0.0f && est <= p.strike_dist) {
+                            term = true; reward += p.strike_reward; complete = true; strike = true;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (active) e.step_count += 1;
+    const bool done = active && (term || trunc);
+    if (active && row != nullptr) fw_write_obs(p, pl, e, i, obs_tidx, a0, a1, a2, a3, row, true, ol.dkx, ol.dky, ol.dkz);
+    if (active) ep_ret += reward;
+    if (__any_sync(0xffffffffu, done)) {
+        if (done) {
+            if (term_obs_row != nullptr)
+                for (int k = 0; k < p.obs_dim; ++k) term_obs_row[k] = row[k];
+            atomicAdd(&pl.stats[0], 1.0);
+            atomicAdd(&pl.stats[1], (double)ep_ret);
+            atomicAdd(&pl.stats[2], (double)e.step_count);
+            atomicAdd(&pl.stats[3], (double)e.tidx);
+            if (col) atomicAdd(&pl.stats[4], 1.0);
+            if (oob) atomicAdd(&pl.stats[5], 1.0);
+            if (complete) atomicAdd(&pl.stats[6], 1.0);
+            if (strike) atomicAdd(&pl.stats[7], 1.0);
+        }
+        // SubprocVecEnv worker: obs = env.reset()
+        ol_reset_lanes(p, pl, done, e, ol, so, depth_row, i, gid, e.episode + 1u, tid);
+        if (done) {
+            if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
+            if (row != nullptr) fw_write_obs(p, pl, e, i, 0, 0.f, 0.f, 0.f, 0.f, row, true, ol.dkx, ol.dky, ol.dkz);
+            ep_ret = 0.0f;
+        }
+    }
+    bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (col ? 4u : 0u) | (oob ? 8u : 0u) | (complete ? 16u : 0u) | (strike ? 32u : 0u);
+    return reward;
+}
+
+// smem: [obs staging (FW_BLOCK x D)] [obstacle table (num_obstacles x 3 x FW_BLOCK)] [depth rows (warps x cam_res)]
+__device__ __forceinline__ void ol_smem_carve(const FwDev& p, float* stage, float*& so, float*& depth_row) {
+    so = stage + (size_t)FW_BLOCK * (p.obs_dim > 0 ? p.obs_dim : 1);
+    depth_row = so + (size_t)(p.num_obstacles > 0 ? p.num_obstacles : 1) * 3 * FW_BLOCK + (size_t)(threadIdx.x >> 5) * p.cam_res;
+}
+
+// 7 blocks/SM x 64 threads x 146 registers: 148 x 448 = 66,304 >= 65,536 envs, still a single wave
+template <bool RANDOM_ACT>
+__global__ void __launch_bounds__(FW_BLOCK, 7)
+fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4* __restrict__ act,
+                       float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ flg,
+                       float* __restrict__ term_obs, int spl, int bulk_ok) {
+    extern __shared__ __align__(128) float stage[];
+    const int i = blockIdx.x * FW_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = p.obs_dim;
+    float* stage_warp = stage + (size_t)warp * 32 * D;
+    float* row = obs != nullptr ? stage_warp + (size_t)lane * D : nullptr;
+    float *so, *depth_row;
+    ol_smem_carve(p, stage, so, depth_row);
+    const bool active = i < p.n;
+    const uint32_t gid = p.env_id0 + (uint32_t)i;
+    EnvState e = {};
+    OlState ol = {};
+    float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+    float ep_ret = 0.f, reward = 0.f;
+    uint32_t bits = 0u;
+    if (active) {
+        fw_load(pl, i, e);
+        ol_load(pl, i, ol);
+        ol_stage_obstacles(p, pl, i, ol.n_obst, so, threadIdx.x, FW_BLOCK);
+        if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
+        ep_ret = pl.ep_ret[i];
+    }
+    __syncwarp();
+    const int nsteps = RANDOM_ACT ? spl : 1;
+    for (int st = 0; st < nsteps; ++st) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        if (active) {
+            if (RANDOM_ACT) {
+                uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid, e.episode, (uint32_t)e.step_count, FWD_STREAM_ACTION);
+                a0 = 2.0f * fw_u01(r.x) - 1.0f; a1 = 2.0f * fw_u01(r.y) - 1.0f;
+                a2 = 2.0f * fw_u01(r.z) - 1.0f; a3 = 2.0f * fw_u01(r.w) - 1.0f;
+            } else {
+                float4 a = act[i];
+                a0 = a.x; a1 = a.y; a2 = a.z; a3 = a.w;
+            }
+        }
+        reward = fw_env_step_objlock(p, pl, active, e, ol, so, depth_row, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
+                                     (st == nsteps - 1) ? row : nullptr,
+                                     (!RANDOM_ACT && term_obs != nullptr && row != nullptr && active) ? term_obs + (size_t)i * D : nullptr,
+                                     bits);
+    }
+    if (active) {
+        pl.ep_ret[i] = ep_ret;
+        fw_store(pl, i, e);
+        ol_store(pl, i, ol);
+        if (rew != nullptr) rew[i] = reward;
+        if (flg != nullptr) flg[i] = (uint8_t)bits;
+    }
+    if (obs != nullptr) {
+        const int first_env = blockIdx.x * FW_BLOCK + warp * 32;
+        if (first_env < p.n) fw_flush_obs(obs, stage_warp, D, first_env, p.n, lane, bulk_ok != 0);
+    }
+}
+
+__global__ void __launch_bounds__(FW_BLOCK)
+fw_reset_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const uint8_t* __restrict__ mask,
+                        float* __restrict__ obs, int bulk_ok, int emit_only) {
+    extern __shared__ __align__(128) float stage[];
+    const int i = blockIdx.x * FW_BLOCK + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = p.obs_dim;
+    float* stage_warp = stage + (size_t)warp * 32 * D;
+    float* row = stage_warp + (size_t)lane * D;
+    float *so, *depth_row;
+    ol_smem_carve(p, stage, so, depth_row);
+    const bool active = i < p.n;
+    EnvState e = {};
+    OlState ol = {};
+    if (active) { fw_load(pl, i, e); ol_load(pl, i, ol); }
+    const bool sel = active && !emit_only && (mask == nullptr || mask[i] != 0);
+    ol_reset_lanes(p, pl, sel, e, ol, so, depth_row, i, p.env_id0 + (uint32_t)i, e.episode + 1u, threadIdx.x);
+    if (sel) {
+        pl.ep_ret[i] = 0.0f;
+        fw_store(pl, i, e);
+        ol_store(pl, i, ol);
+    }
+    if (active) fw_write_obs(p, pl, e, i, e.tidx, 0.f, 0.f, 0.f, 0.f, row, true, ol.dkx, ol.dky, ol.dkz);
+    if (obs != nullptr) {
         const int first_env = blockIdx.x * FW_BLOCK + warp * 32;
         if (first_env < p.n) fw_flush_obs(obs, stage_warp, D, first_env, p.n, lane, bulk_ok != 0);
     }
@@ -311,7 +482,8 @@ __global__ void fw_warm_kernel(const __grid_constant__ FwDev p, const FwPlanes p
 // ------------------------------------------------------------------ launchers
 static inline size_t stage_bytes(const FwDev& p) {
     size_t obs = (size_t)(FW_BLOCK / 32) * 32 * (size_t)(p.obs_dim > 0 ? p.obs_dim : 1) * 4;
-    size_t obst = p.task == 2 ? (size_t)(p.num_obstacles > 0 ? p.num_obstacles : 1) * 4 * FW_BLOCK * 4 : 0;
+    size_t obst = p.task == 2 ? ((size_t)(p.num_obstacles > 0 ? p.num_obstacles : 1) * 3 * FW_BLOCK +
+                                 (size_t)(FW_BLOCK / 32) * p.cam_res) * 4 : 0;
     return obs + obst;
 }
 static inline int grid_for(int n) { return (n + FW_BLOCK - 1) / FW_BLOCK; }
@@ -321,7 +493,7 @@ typedef void (*fw_step_fn)(const FwDev, const FwPlanes, const float4*, float*, f
 static fw_step_fn step_fn(int task, bool random_act) {
     if (task == 0) return random_act ? fw_step_kernel<0, true> : fw_step_kernel<0, false>;
     if (task == 1) return random_act ? fw_step_kernel<1, true> : fw_step_kernel<1, false>;
-    if (task == 2) return random_act ? fw_step_kernel<2, true> : fw_step_kernel<2, false>;
+    if (task == 2) return random_act ? fw_step_objlock_kernel<true> : fw_step_objlock_kernel<false>;
     return nullptr;
 }
 
@@ -357,7 +529,8 @@ cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* dep, const
 cudaError_t fwk_launch_reset(const FwDev& p, const FwPlanes& pl, const uint8_t* mask, float* obs, bool emit_only,
                              cudaStream_t st) {
     const int bulk_ok = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0);
-    fw_reset_kernel<<<grid_for(p.n), FW_BLOCK, stage_bytes(p), st>>>(p, pl, mask, obs, bulk_ok, emit_only ? 1 : 0);
+    if (p.task == 2) fw_reset_objlock_kernel<<<grid_for(p.n), FW_BLOCK, stage_bytes(p), st>>>(p, pl, mask, obs, bulk_ok, emit_only ? 1 : 0);
+    else fw_reset_kernel<<<grid_for(p.n), FW_BLOCK, stage_bytes(p), st>>>(p, pl, mask, obs, bulk_ok, emit_only ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -53,15 +53,14 @@ __device__ __forceinline__ void ol_store(const FwPlanes& pl, int i, const OlStat
     pl.v3[i] = make_int4(bits, o.seen, o.lock, o.since);
 }
 
-// obstacle table of this thread in shared memory: so[(k*4 + c) * stride + tid]; c = x, y, height, and a scratch
-// word holding the pixel-column interval of the current camera frame
-#define OL_S(so, k, c, tid, stride) (so)[((k) * 4 + (c)) * (stride) + (tid)]
+// obstacle table of this thread in shared memory: so[(k*3 + c) * stride + tid]; c = x, y, height
+#define OL_S(so, k, c, tid, stride) (so)[((k) * 3 + (c)) * (stride) + (tid)]
 
 __device__ __forceinline__ void ol_stage_obstacles(const FwDev& p, const FwPlanes& pl, int i, int n_obst, float* so, int tid,
                                                    int stride) {
     for (int k = 0; k < n_obst; ++k)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) OL_S(so, k, c, tid, stride) = pl.obst[(size_t)(k * 3 + c) * p.n + i];   // c = 3: scratch
+        for (int c = 0; c < 3; ++c) OL_S(so, k, c, tid, stride) = pl.obst[(size_t)(k * 3 + c) * p.n + i];
 }
 
 // nearest positive hit of ray o + t d with the finite vertical cylinder (cx, cy, height h, radius r); inf if none
@@ -139,110 +138,156 @@ __device__ __forceinline__ void ol_col_interval(float Ax, float Ay, float Bx, fl
     }
 }
 
-__device__ __forceinline__ void ol_mask_set(uint32_t (&mask)[4], int lo, int hi) {
-#pragma unroll
-    for (int wd = 0; wd < 4; ++wd) {
-        const int a = max(lo - 32 * wd, 0), b = min(hi - 32 * wd, 31);
-        if (a <= b) mask[wd] |= (0xffffffffu >> (31 - b)) & (0xffffffffu << a);
-    }
-}
-
-// Camera.capture_image stand-in + the image reductions of _compute_vision_features
-__device__ __forceinline__ void ol_capture(const FwDev& p, const EnvState& e, OlState& o, float* so, int tid, int stride) {
+// Camera.capture_image stand-in + the image reductions of _compute_vision_features, WARP-COOPERATIVE.
+// A thread-per-env ray caster does cam_res x n_obst cylinder tests per frame and, because every aircraft sees a
+// different obstacle layout, SIMT execution cannot skip any of them.  Here the 32 lanes of the warp serve one
+// capturing env at a time: lanes = obstacles (each rasterises only the few pixel columns its cylinder can cover,
+// into a shared depth row with atomicMin), then lanes = pixel columns (duck mask, inverse depth, band sums by
+// shuffle).  Must be called by all 32 lanes; `need` marks the lanes whose env captures a frame now.
+__device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const EnvState& e, OlState& o, const float* so,
+                                                int tid, int stride, float* depth_row) {
+    const unsigned FULL = 0xffffffffu;
     const float INF = __int_as_float(0x7f800000);
-    Mat3 R = fw_quat_mat(e.qx, e.qy, e.qz, e.qw);
-    const float* m = R.m;
-    // camera position = pos + R * offset ; forward = -R*offset/|offset| ; up hint = body z
-    float ofx = m[0] * p.cam_offset[0] + m[1] * p.cam_offset[1] + m[2] * p.cam_offset[2];
-    float ofy = m[3] * p.cam_offset[0] + m[4] * p.cam_offset[1] + m[5] * p.cam_offset[2];
-    float ofz = m[6] * p.cam_offset[0] + m[7] * p.cam_offset[1] + m[8] * p.cam_offset[2];
-    float cx = e.px + ofx, cy = e.py + ofy, cz = e.pz + ofz;
-    float il = rsqrtf(ofx * ofx + ofy * ofy + ofz * ofz);
-    float fx = -ofx * il, fy = -ofy * il, fz = -ofz * il;
-    float ux = m[2], uy = m[5], uz = m[8];
-    float rx = fy * uz - fz * uy, ry = fz * ux - fx * uz, rz = fx * uy - fy * ux;
-    float rl = rsqrtf(rx * rx + ry * ry + rz * rz);
-    rx *= rl; ry *= rl; rz *= rl;
-    ux = ry * fz - rz * fy; uy = rz * fx - rx * fz; uz = rx * fy - ry * fx;
-
-    // duck silhouette: sphere of radius duck_radius resting on the ground
+    const int lane = tid & 31;
+    unsigned pending = __ballot_sync(FULL, need);
+    if (pending == 0u) return;
+    // every capturing lane prepares its own camera (position, ray family A + xn r, duck sphere)
+    float cx = 0.f, cy = 0.f, cz = 0.f, Ax = 0.f, Ay = 0.f, Az = 0.f, rx = 0.f, ry = 0.f, rz = 0.f;
+    float sx = 0.f, sy = 0.f, sz = 0.f, zc = 1.f, xc = 0.f, yc = 0.f, ddx = 0.f, ddy = 0.f, ddz = 0.f, dist = 0.f;
+    int cand = 0;
     const float Rd = p.duck_radius;
-    float sx = o.dkx, sy = o.dky, sz = o.dkz + Rd;
-    float dvx = sx - cx, dvy = sy - cy, dvz = sz - cz;
-    float zc = dvx * fx + dvy * fy + dvz * fz, xc = dvx * rx + dvy * ry + dvz * rz, yc = dvx * ux + dvy * uy + dvz * uz;
-    int vis = 0;
-    if (zc - Rd > p.cam_near && fabsf(xc) <= zc + Rd && fabsf(yc) <= zc + Rd && zc - Rd < p.cam_far) {
-        vis = 1;
-        float dist = sqrtf(dvx * dvx + dvy * dvy + dvz * dvz);
-        float id = 1.0f / dist;
-        float ddx = dvx * id, ddy = dvy * id, ddz = dvz * id;
-        for (int k = 0; k < o.n_obst && vis; ++k) {
-            float t = ol_ray_cylinder(cx, cy, cz, ddx, ddy, ddz, OL_S(so, k, 0, tid, stride), OL_S(so, k, 1, tid, stride),
-                                      OL_S(so, k, 2, tid, stride), p.obst_radius);
-            if (t < dist - Rd) vis = 0;
-        }
-    }
-    o.f_visible = vis;
-    if (vis) {
-        float ccx = 0.5f + 0.5f * xc / zc, ccy = 0.5f - 0.5f * yc / zc;
-        o.f_cx = fminf(fmaxf(ccx, 0.0f), 1.0f);
-        o.f_cy = fminf(fmaxf(ccy, 0.0f), 1.0f);
-        float a = FWD_PI * (Rd / zc) * (Rd / zc) * 0.25f;
-        o.f_area = fminf(a, 1.0f);
-        o.f_depth = zc - Rd;
-    }
-    // obstacle bands: middle row, three column bands, harmonic-mean depth of non-duck pixels.
-    // First the (few) columns each cylinder / the duck can cover, so that most columns only meet the ground.
     const int w = p.cam_res, x1 = w / 3, x2 = 2 * w / 3, ymid = w / 2;
     const float vrow = 2.0f * ((float)ymid + 0.5f) / (float)w - 1.0f;
-    const float Ax = fx - vrow * ux, Ay = fy - vrow * uy, Az = fz - vrow * uz;
-    const float AA = Ax * Ax + Ay * Ay, AB = Ax * rx + Ay * ry, BB = rx * rx + ry * ry;
-    const bool use_mask = w <= 128;
-    uint32_t cmask[4] = {0u, 0u, 0u, 0u}, dmask[4] = {0u, 0u, 0u, 0u};
-    for (int k = 0; k < o.n_obst; ++k) {
-        int lo, hi;
-        ol_col_interval(Ax, Ay, rx, ry, AA, AB, BB, OL_S(so, k, 0, tid, stride) - cx, OL_S(so, k, 1, tid, stride) - cy,
-                        p.obst_radius, w, lo, hi);
-        OL_S(so, k, 3, tid, stride) = __int_as_float((lo & 0xffff) | (hi << 16));
-        if (use_mask) ol_mask_set(cmask, lo, hi);
+    if (need) {
+        Mat3 R = fw_quat_mat(e.qx, e.qy, e.qz, e.qw);
+        const float* m = R.m;
+        // camera position = pos + R * offset ; forward = -R*offset/|offset| ; up hint = body z
+        float ofx = m[0] * p.cam_offset[0] + m[1] * p.cam_offset[1] + m[2] * p.cam_offset[2];
+        float ofy = m[3] * p.cam_offset[0] + m[4] * p.cam_offset[1] + m[5] * p.cam_offset[2];
+        float ofz = m[6] * p.cam_offset[0] + m[7] * p.cam_offset[1] + m[8] * p.cam_offset[2];
+        cx = e.px + ofx; cy = e.py + ofy; cz = e.pz + ofz;
+        float il = rsqrtf(ofx * ofx + ofy * ofy + ofz * ofz);
+        float fx = -ofx * il, fy = -ofy * il, fz = -ofz * il;
+        float ux = m[2], uy = m[5], uz = m[8];
+        rx = fy * uz - fz * uy; ry = fz * ux - fx * uz; rz = fx * uy - fy * ux;
+        float rl = rsqrtf(rx * rx + ry * ry + rz * rz);
+        rx *= rl; ry *= rl; rz *= rl;
+        ux = ry * fz - rz * fy; uy = rz * fx - rx * fz; uz = rx * fy - ry * fx;
+        Ax = fx - vrow * ux; Ay = fy - vrow * uy; Az = fz - vrow * uz;
+        // duck silhouette: sphere of radius duck_radius resting on the ground
+        sx = o.dkx; sy = o.dky; sz = o.dkz + Rd;
+        float dvx = sx - cx, dvy = sy - cy, dvz = sz - cz;
+        zc = dvx * fx + dvy * fy + dvz * fz; xc = dvx * rx + dvy * ry + dvz * rz; yc = dvx * ux + dvy * uy + dvz * uz;
+        cand = (zc - Rd > p.cam_near && fabsf(xc) <= zc + Rd && fabsf(yc) <= zc + Rd && zc - Rd < p.cam_far) ? 1 : 0;
+        dist = sqrtf(dvx * dvx + dvy * dvy + dvz * dvz);
+        float id = 1.0f / dist;
+        ddx = dvx * id; ddy = dvy * id; ddz = dvz * id;
     }
-    {
-        int lo, hi;
-        ol_col_interval(Ax, Ay, rx, ry, AA, AB, BB, sx - cx, sy - cy, Rd, w, lo, hi);
-        if (use_mask) ol_mask_set(dmask, lo, hi);
-    }
-    float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
-    int c0 = 0, c1 = 0, c2 = 0;
-    for (int col = 0; col < w; ++col) {
-        float xn = 2.0f * ((float)col + 0.5f) / (float)w - 1.0f;
-        float dx = Ax + xn * rx, dy = Ay + xn * ry, dz = Az + xn * rz;
-        float best = INF;
-        if (dz < -1e-12f) { float t = -cz / dz; if (t > 0.0f && t < best) best = t; }
-        const int wd = (col >> 5) & 3;      // select chain instead of a dynamically indexed (local-memory) array
-        const uint32_t cw = wd == 0 ? cmask[0] : (wd == 1 ? cmask[1] : (wd == 2 ? cmask[2] : cmask[3]));
-        const uint32_t dw = wd == 0 ? dmask[0] : (wd == 1 ? dmask[1] : (wd == 2 ? dmask[2] : dmask[3]));
-        const bool maybe_cyl = !use_mask || ((cw >> (col & 31)) & 1u);
-        if (maybe_cyl) {
-            for (int k = 0; k < o.n_obst; ++k) {
-                const int iv = __float_as_int(OL_S(so, k, 3, tid, stride));
-                if (col < (iv & 0xffff) || col > (iv >> 16)) continue;
-                float t = ol_ray_cylinder(cx, cy, cz, dx, dy, dz, OL_S(so, k, 0, tid, stride), OL_S(so, k, 1, tid, stride),
-                                          OL_S(so, k, 2, tid, stride), p.obst_radius);
-                if (t < best) best = t;
+    while (pending) {
+        const int s = __ffs(pending) - 1;
+        pending &= pending - 1u;
+        const int src = (tid & ~31) | s;                      // shared-memory column of the capturing env
+        const float bcx = __shfl_sync(FULL, cx, s), bcy = __shfl_sync(FULL, cy, s), bcz = __shfl_sync(FULL, cz, s);
+        const float bAx = __shfl_sync(FULL, Ax, s), bAy = __shfl_sync(FULL, Ay, s), bAz = __shfl_sync(FULL, Az, s);
+        const float brx = __shfl_sync(FULL, rx, s), bry = __shfl_sync(FULL, ry, s), brz = __shfl_sync(FULL, rz, s);
+        const float bsx = __shfl_sync(FULL, sx, s), bsy = __shfl_sync(FULL, sy, s), bsz = __shfl_sync(FULL, sz, s);
+        const float bdx = __shfl_sync(FULL, ddx, s), bdy = __shfl_sync(FULL, ddy, s), bdz = __shfl_sync(FULL, ddz, s);
+        const float bdist = __shfl_sync(FULL, dist, s);
+        const int bcand = __shfl_sync(FULL, cand, s), bn = __shfl_sync(FULL, o.n_obst, s);
+        // phase 0 (lanes = columns): the ground plane
+        for (int col = lane; col < w; col += 32) {
+            float xn = 2.0f * ((float)col + 0.5f) / (float)w - 1.0f;
+            float dz = bAz + xn * brz;
+            float best = INF;
+            if (dz < -1e-12f) { float t = -bcz / dz; if (t > 0.0f) best = t; }
+            depth_row[col] = best;
+        }
+        __syncwarp();
+        // phase A: lane k owns cylinder k for the set-up (column interval, duck-occlusion ray); the (cylinder,
+        // column) pairs to rasterise are then dealt out evenly over the 32 lanes through a warp prefix sum, so a
+        // wide nearby cylinder does not serialise the warp behind one lane
+        bool occl = false;
+        const float AA = bAx * bAx + bAy * bAy, AB = bAx * brx + bAy * bry, BB = brx * brx + bry * bry;
+        float ox = 0.f, oy = 0.f, oh = 0.f;
+        int lo = 1, hi = 0;
+        if (lane < bn) {
+            ox = OL_S(so, lane, 0, src, stride); oy = OL_S(so, lane, 1, src, stride); oh = OL_S(so, lane, 2, src, stride);
+            ol_col_interval(bAx, bAy, brx, bry, AA, AB, BB, ox - bcx, oy - bcy, p.obst_radius, w, lo, hi);
+            if (bcand) {
+                float t = ol_ray_cylinder(bcx, bcy, bcz, bdx, bdy, bdz, ox, oy, oh, p.obst_radius);
+                occl = t < bdist - Rd;
             }
         }
-        const bool maybe_duck = !use_mask || ((dw >> (col & 31)) & 1u);
-        if (maybe_duck) {
-            float td = ol_ray_sphere(cx, cy, cz, dx, dy, dz, sx, sy, sz, Rd);
-            if (td < best) continue;                   // duck pixel: excluded from the band means
+        const int wdt = max(hi - lo + 1, 0);
+        int scan = wdt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int t = __shfl_up_sync(FULL, scan, off);
+            if (lane >= off) scan += t;
         }
-        float iv = (best < INF) ? ol_inv_depth(p, best) : 1.0f / p.cam_far;
-        if (col < x1) { sum0 += iv; c0++; } else if (col < x2) { sum1 += iv; c1++; } else { sum2 += iv; c2++; }
+        const int total = __shfl_sync(FULL, scan, 31);
+        const int start = scan - wdt;
+        for (int base = 0; base < total; base += 32) {
+            const int pidx = base + lane;
+            int k = 0;                                   // owner = number of lanes whose inclusive scan <= pidx
+#pragma unroll
+            for (int stp = 16; stp > 0; stp >>= 1) {
+                const int candk = k + stp;
+                const int sv = __shfl_sync(FULL, scan, (candk - 1) & 31);
+                if (candk <= 32 && sv <= pidx) k = candk;
+            }
+            const int kk = k & 31;
+            const int klo = __shfl_sync(FULL, lo, kk), kst = __shfl_sync(FULL, start, kk);
+            const float kx = __shfl_sync(FULL, ox, kk), ky = __shfl_sync(FULL, oy, kk), kh = __shfl_sync(FULL, oh, kk);
+            if (pidx < total) {
+                const int col = klo + (pidx - kst);
+                float xn = 2.0f * ((float)col + 0.5f) / (float)w - 1.0f;
+                float t = ol_ray_cylinder(bcx, bcy, bcz, bAx + xn * brx, bAy + xn * bry, bAz + xn * brz, kx, ky, kh, p.obst_radius);
+                if (t < INF) atomicMin(reinterpret_cast<int*>(&depth_row[col]), __float_as_int(t));
+            }
+        }
+        const unsigned hidden = __ballot_sync(FULL, occl);
+        __syncwarp();
+        // phase B (lanes = columns): duck pixels drop out, the rest feed the three harmonic band means
+        int dlo, dhi;
+        ol_col_interval(bAx, bAy, brx, bry, AA, AB, BB, bsx - bcx, bsy - bcy, Rd, w, dlo, dhi);
+        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
+        int c0 = 0, c1 = 0, c2 = 0;
+        for (int col = lane; col < w; col += 32) {
+            float best = depth_row[col];
+            if (col >= dlo && col <= dhi) {
+                float xn = 2.0f * ((float)col + 0.5f) / (float)w - 1.0f;
+                float td = ol_ray_sphere(bcx, bcy, bcz, bAx + xn * brx, bAy + xn * bry, bAz + xn * brz, bsx, bsy, bsz, Rd);
+                if (td < best) continue;
+            }
+            float iv = (best < INF) ? ol_inv_depth(p, best) : 1.0f / p.cam_far;
+            if (col < x1) { sum0 += iv; c0++; } else if (col < x2) { sum1 += iv; c1++; } else { sum2 += iv; c2++; }
+        }
+        // NOTE: fp32 addition is not associative; the oracle sums columns left to right in fp64, so the order
+        // here only moves the last bits of a quantity that is compared with a 2e-4 relative tolerance
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            sum0 += __shfl_xor_sync(FULL, sum0, off); sum1 += __shfl_xor_sync(FULL, sum1, off); sum2 += __shfl_xor_sync(FULL, sum2, off);
+            c0 += __shfl_xor_sync(FULL, c0, off); c1 += __shfl_xor_sync(FULL, c1, off); c2 += __shfl_xor_sync(FULL, c2, off);
+        }
+        if (lane == s) {
+            const int vis = (cand && hidden == 0u) ? 1 : 0;
+            o.f_visible = vis;
+            if (vis) {
+                float ccx = 0.5f + 0.5f * xc / zc, ccy = 0.5f - 0.5f * yc / zc;
+                o.f_cx = fminf(fmaxf(ccx, 0.0f), 1.0f);
+                o.f_cy = fminf(fmaxf(ccy, 0.0f), 1.0f);
+                float a = FWD_PI * (Rd / zc) * (Rd / zc) * 0.25f;
+                o.f_area = fminf(a, 1.0f);
+                o.f_depth = zc - Rd;
+            }
+            o.f_dl = ol_band_metres(p, sum0, c0);
+            o.f_dc = ol_band_metres(p, sum1, c1);
+            o.f_dr = ol_band_metres(p, sum2, c2);
+            o.cam_valid = 1;
+        }
+        __syncwarp();
     }
-    o.f_dl = ol_band_metres(p, sum0, c0);
-    o.f_dc = ol_band_metres(p, sum1, c1);
-    o.f_dr = ol_band_metres(p, sum2, c2);
-    o.cam_valid = 1;
 }
 
 // _compute_vision_features + the phase switching of compute_state (fixedwing_waypoint_objlock_env.py:248-274)
