@@ -79,6 +79,26 @@ int ppo_timeout_bootstrap(const float* params, int32_t d, const float* term_obs_
 int ppo_gae(const float* rewards, const float* values, const float* dones, const float* last_values, int32_t T,
             int32_t n, float gamma, float lam, float* advantages, float* returns, void* stream);
 
+/* ---- PPO minibatch update (stable_baselines3 PPO.train for one minibatch), csrc/ppo_update_tc.cu ----
+ * ppo_minibatch_grad: gradient of
+ *     -mean(min(A r, A clip(r, 1 +- clip_range))) - ent_coef * mean(entropy) + vf_coef * mean((ret - V)^2)
+ * over the `batch` samples idx[0..batch) (int64 row indices into the flattened rollout buffers), with the
+ * per-minibatch advantage normalisation (A - mean) / (std + 1e-8), r = exp(logp - logp_old).  Forward and backward
+ * of both towers run on the tcgen05 tensor cores (TF32).  grad receives all ppo_param_count(d) entries;
+ * stats[8] (may be NULL) = sums over the minibatch of {policy loss, squared value error, approx KL, clipped,
+ * ratio, samples, 0, 0}.  workspace: ppo_update_workspace_floats(d) floats, 16-byte aligned, zero on first use. */
+int ppo_update_workspace_floats(int32_t d);
+int ppo_minibatch_grad(const float* params, int32_t d, const float* obs_norm, const float* act, const float* logp_old,
+                       const float* adv, const float* ret, const int64_t* idx, int32_t batch, float clip_range,
+                       float ent_coef, float vf_coef, float* workspace, float* grad, float* stats, void* stream);
+
+/* torch.nn.utils.clip_grad_norm_(max_grad_norm) followed by torch.optim.Adam.step (no weight decay / amsgrad) on the
+ * flat parameter vector; grad is pre-multiplied by grad_scale (1 / world_size after the NCCL sum).
+ * step_counter: device int32 incremented by the call (bias correction). */
+int ppo_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t n_params, float lr,
+                  float beta1, float beta2, float eps, float max_grad_norm, float grad_scale, int32_t* step_counter,
+                  float* grad_norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

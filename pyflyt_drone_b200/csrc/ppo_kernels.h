@@ -24,3 +24,10 @@ cudaError_t ppok_gae(const float* rewards, const float* values, const float* don
 cudaError_t ppok_forward_tc(const float* params, int d, const float* obs_raw, const double* stats, float clip, int n,
                             uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev, int deterministic,
                             float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, cudaStream_t st);
+int ppok_update_grid(int batch);
+cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, const float* act, const float* logp_old,
+                                const float* adv, const float* ret, const long long* idx, int batch, float clip_range,
+                                float ent_coef, float vf_coef, double* scratch, float* adv_stats, float* partial,
+                                float* stats_partial, float* grad, float* stats, cudaStream_t st);
+cudaError_t ppok_adam(float* params, const float* grad, float* m, float* v, int P, float lr, float beta1, float beta2, float eps,
+                      float max_norm, float grad_scale, int* step_ctr, float* norm_out, cudaStream_t st);

@@ -1,0 +1,592 @@
+// ppo_update_tc.cu -- K6: the PPO minibatch gradient (forward + backward of both MLP towers and the clipped
+// surrogate / value / entropy losses) fused into ONE kernel on the tcgen05 tensor cores, plus the partial-sum
+// reduction and the clipped Adam step.  Replaces stable_baselines3 PPO.train()'s per-minibatch
+// evaluate_actions -> loss -> backward -> clip_grad_norm_ -> Adam.step
+// (reference wiring: /root/reference/train/train_Fixedwing_Waypoints_v3.py:293-337).
+//
+// Work decomposition: a persistent CTA (128 threads = 128 samples per tile, thread == sample == TMEM lane) walks
+// tiles of the minibatch.  All matrix products are tcgen05.mma kind::tf32 with fp32 accumulators in TMEM:
+//   forward   X[128x32] W1^T, H1[128x64] W2^T                      (A, B K-major)
+//   dgrad     dZ2[128x64] W2                                          (B read MN-major from the same smem copy)
+//   wgrad     [dZ2_pi|dZ2_vf]^T H1, [dZ1_pi|dZ1_vf]^T X, [H2_pi|H2_vf]^T dOut, bias sums against a ones column
+//             (A and B read MN-major: the activation buffers written row-per-thread for the forward pass ARE
+//              the transposed operands the weight gradients need -- no transposes, no extra copies)
+// Both towers are stacked along M (= 128 output neurons) for the weight gradients, which accumulate in TMEM
+// across all tiles of the CTA and are read out once at the end into a per-CTA partial gradient.
+#include "ppo_kernels.h"
+
+#include <cuda_runtime.h>
+
+#define H PPO_H
+#define A PPO_A
+#define DP PPO_DPAD
+#define UT_ROWS 128
+#define UT_TMEM_COLS 512
+
+__device__ __forceinline__ uint32_t ut_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// K-major canonical (no swizzle) offset of element (r, c) in an [R x K] fp32 matrix; see ppo_tc.cu
+__device__ __forceinline__ uint32_t ut_off(int r, int c, int K) {
+    return (uint32_t)((r >> 3) * (K * 32) + (c >> 2) * 128 + (r & 7) * 16 + (c & 3) * 4);
+}
+
+__device__ __forceinline__ uint64_t ut_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// instruction descriptor: D = F32, A = B = TF32, M = 128; majors and N vary
+__device__ __forceinline__ constexpr uint32_t ut_idesc(int n, int a_mn, int b_mn) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
+           ((uint32_t)(UT_ROWS >> 4) << 24);
+}
+
+__device__ __forceinline__ void ut_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// D[128 x N] (+)= A B^T over `ksteps` instructions of K = 8; per instruction the operand start addresses advance by
+// a_step / b_step bytes (256 for a K-major operand, its LBO for an MN-major one)
+__device__ __forceinline__ void ut_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step,
+                                        uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step, int ksteps,
+                                        uint32_t idesc, uint32_t accumulate_first) {
+    for (int k = 0; k < ksteps; ++k)
+        ut_mma(tmem_d, ut_desc(a_addr + k * a_step, a_lbo, a_sbo), ut_desc(b_addr + k * b_step, b_lbo, b_sbo), idesc,
+               k > 0 ? 1u : accumulate_first);
+}
+
+__device__ __forceinline__ void ut_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void ut_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t it = 0;; ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (it > (1u << 22)) __trap();
+    }
+}
+
+__device__ __forceinline__ void ut_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]),
+          "=r"(u[16]), "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]),
+          "=r"(u[24]), "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void ut_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t* u = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]),
+          "=r"(u[8]), "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float ut_tanh(float x) {
+    float e = __expf(2.0f * x);
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
+#define UT_FENCE_SYNC()                                                   \
+    do {                                                                  \
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      \
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");  \
+        __syncthreads();                                                  \
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");   \
+    } while (0)
+
+// shared-memory plan (bytes)
+struct UtSmem {
+    static constexpr int XB = 0;                              // X            [128 x 32]    16 KB
+    static constexpr int H1C = XB + UT_ROWS * DP * 4;         // H1 pi|vf     [128 x 128]   64 KB (later dZ1)
+    static constexpr int H2C = H1C + UT_ROWS * 2 * H * 4;     // H2 pi|vf     [128 x 128]   64 KB (later dZ2)
+    static constexpr int DO = H2C + UT_ROWS * 2 * H * 4;      // dOut|1       [128 x 16]     8 KB
+    static constexpr int W1_PI = DO + UT_ROWS * 16 * 4;       // W1           [64 x 32]      8 KB each
+    static constexpr int W1_VF = W1_PI + H * DP * 4;
+    static constexpr int W2_PI = W1_VF + H * DP * 4;          // W2           [64 x 64]     16 KB each
+    static constexpr int W2_VF = W2_PI + H * H * 4;
+    static constexpr int SMALL = W2_VF + H * H * 4;
+    // floats inside SMALL
+    static constexpr int B1 = 0 /* pi 64 | vf 64 */, B2 = 128, W3_PI = 256 /* [4][64] */, W3_VF = 512, B3_PI = 576, B3_VF = 580,
+                         LOGSTD = 584, RED = 592 /* 24 block-reduction slots */, BAR = 616, TPTR = 620, NSMALL = 624;
+    static constexpr int TOTAL = SMALL + NSMALL * 4;
+};
+
+// TMEM column plan
+#define UT_T0 0      // 128: forward / dgrad scratch (pi cols 0-63, vf cols 64-127)
+#define UT_DA 128    // 64 : [dZ2]^T H1_pi   (rows 0-63 = dW2_pi)
+#define UT_DB 192    // 64 : [dZ2]^T H1_vf   (rows 64-127 = dW2_vf)
+#define UT_DW1 256   // 32 : [dZ1]^T X       (rows 0-63 dW1_pi, 64-127 dW1_vf)
+#define UT_D3 288    // 16 : [H2]^T dOut     (rows 0-63 x cols 0-3 = dW3_pi^T ; rows 64-127 x col 4 = dW3_vf)
+#define UT_DB2 304   // 16 : [dZ2]^T dOut|1  (col 5 = db2)
+#define UT_DB1 320   // 16 : [dZ1]^T dOut|1  (col 5 = db1)
+
+__device__ void ut_load_weight(char* smem, int off, const float* __restrict__ g, int K, int d) {
+    for (int i = threadIdx.x; i < H * K; i += blockDim.x) {
+        int j = i / K, k = i % K;
+        *reinterpret_cast<float*>(smem + off + ut_off(j, k, K)) = k < d ? g[j * d + k] : 0.0f;
+    }
+}
+
+struct PpoLossCfg { float clip_range, ent_coef, vf_coef, inv_batch; };
+
+// out_partial: [gridDim.x][P] gradient partial sums; out_stats: [gridDim.x][8] (pi loss, v loss, entropy, approx kl,
+// clip fraction, sum ratio, -, samples), all already divided by the minibatch size where they are means
+__global__ void __launch_bounds__(UT_ROWS, 1)
+ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restrict__ obs, const float* __restrict__ act,
+                   const float* __restrict__ logp_old, const float* __restrict__ adv, const float* __restrict__ ret,
+                   const long long* __restrict__ idx, int batch, const float* __restrict__ adv_stats, PpoLossCfg cfg,
+                   float* __restrict__ out_partial, float* __restrict__ out_stats, int P) {
+    extern __shared__ __align__(1024) char smem[];
+    float* small = reinterpret_cast<float*>(smem + UtSmem::SMALL);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int pi_count = H * d + H + H * H + H + A * H + A;
+    const int vf_count = H * d + H + H * H + H + H + 1;
+    const float* g_pi = params;
+    const float* g_vf = params + pi_count;
+
+    ut_load_weight(smem, UtSmem::W1_PI, g_pi, DP, d);
+    ut_load_weight(smem, UtSmem::W1_VF, g_vf, DP, d);
+    ut_load_weight(smem, UtSmem::W2_PI, g_pi + H * d + H, H, H);
+    ut_load_weight(smem, UtSmem::W2_VF, g_vf + H * d + H, H, H);
+    if (tid < H) {
+        small[UtSmem::B1 + tid] = g_pi[H * d + tid];
+        small[UtSmem::B1 + H + tid] = g_vf[H * d + tid];
+        small[UtSmem::B2 + tid] = g_pi[H * d + H + H * H + tid];
+        small[UtSmem::B2 + H + tid] = g_vf[H * d + H + H * H + tid];
+        small[UtSmem::W3_VF + tid] = g_vf[H * d + H + H * H + H + tid];
+    }
+    for (int i = tid; i < A * H; i += blockDim.x) small[UtSmem::W3_PI + i] = g_pi[H * d + H + H * H + H + i];
+    if (tid < A) {
+        small[UtSmem::B3_PI + tid] = g_pi[H * d + H + H * H + H + A * H + tid];
+        small[UtSmem::LOGSTD + tid] = params[pi_count + vf_count + tid];
+    }
+    if (tid == 0) small[UtSmem::B3_VF] = g_vf[H * d + H + H * H + H + H];
+    if (tid < 24) small[UtSmem::RED + tid] = 0.0f;
+    const uint32_t bar = ut_smem_u32(&small[UtSmem::BAR]);
+    uint32_t* tptr = reinterpret_cast<uint32_t*>(&small[UtSmem::TPTR]);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     :: "r"(ut_smem_u32(tptr)), "r"((uint32_t)UT_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tptr;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t sb = ut_smem_u32(smem);
+    uint32_t phase = 0;
+
+    const float adv_mean = adv_stats[0], adv_istd = 1.0f / (adv_stats[1] + 1e-8f);
+    float sigma_inv[A], logstd[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) { logstd[a] = small[UtSmem::LOGSTD + a]; sigma_inv[a] = __expf(-logstd[a]); }
+
+    // per-thread running sums over this CTA's samples: db3_pi[4], db3_vf, dlogstd[4], loss statistics[6]
+    float acc_db3[A] = {0.f, 0.f, 0.f, 0.f}, acc_db3v = 0.f, acc_dls[A] = {0.f, 0.f, 0.f, 0.f};
+    float st_pl = 0.f, st_vl = 0.f, st_kl = 0.f, st_clip = 0.f, st_ratio = 0.f, st_n = 0.f;
+
+    const int ntiles = (batch + UT_ROWS - 1) / UT_ROWS;
+    uint32_t first = 0;        // 0 on the first tile of this CTA: weight-gradient accumulators start from zero
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int srow = tile * UT_ROWS + tid;
+        const bool live = srow < batch;
+        const long long g = live ? idx[srow] : 0;
+        // ---- S0: gather the sample's (already normalised) observation as the A operand of layer 1
+#pragma unroll
+        for (int c4 = 0; c4 < DP / 4; ++c4) {
+            float v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int k = 4 * c4 + q; v[q] = (live && k < d) ? obs[(size_t)g * d + k] : 0.0f; }
+            *reinterpret_cast<float4*>(smem + UtSmem::XB + ut_off(tid, 4 * c4, DP)) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        UT_FENCE_SYNC();
+        // ---- M1: forward layer 1, both towers
+        if (tid == 0) {
+            ut_gemm(tmem + UT_T0, sb + UtSmem::XB, 128, DP * 32, 256, sb + UtSmem::W1_PI, 128, DP * 32, 256, DP / 8, ut_idesc(H, 0, 0), 0u);
+            ut_gemm(tmem + UT_T0 + H, sb + UtSmem::XB, 128, DP * 32, 256, sb + UtSmem::W1_VF, 128, DP * 32, 256, DP / 8, ut_idesc(H, 0, 0), 0u);
+            ut_commit(bar);
+        }
+        ut_wait(bar, phase); phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- E1: H1 = tanh(. + b1) into the stacked [pi | vf] buffer
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {          // q = tower*2 + half
+            float v[32];
+            ut_ld32(tmem + UT_T0 + lane_base + q * 32, v);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const int j = q * 32 + 4 * c4;
+                float4 o = make_float4(ut_tanh(v[4 * c4 + 0] + small[UtSmem::B1 + j + 0]), ut_tanh(v[4 * c4 + 1] + small[UtSmem::B1 + j + 1]),
+                                       ut_tanh(v[4 * c4 + 2] + small[UtSmem::B1 + j + 2]), ut_tanh(v[4 * c4 + 3] + small[UtSmem::B1 + j + 3]));
+                *reinterpret_cast<float4*>(smem + UtSmem::H1C + ut_off(tid, j, 2 * H)) = o;
+            }
+        }
+        UT_FENCE_SYNC();
+        // ---- M2: forward layer 2 (A = the tower's 64-column sub-block of H1C)
+        if (tid == 0) {
+            ut_gemm(tmem + UT_T0, sb + UtSmem::H1C, 128, 2 * H * 32, 256, sb + UtSmem::W2_PI, 128, H * 32, 256, H / 8, ut_idesc(H, 0, 0), 0u);
+            ut_gemm(tmem + UT_T0 + H, sb + UtSmem::H1C + 16 * 128, 128, 2 * H * 32, 256, sb + UtSmem::W2_VF, 128, H * 32, 256, H / 8,
+                    ut_idesc(H, 0, 0), 0u);
+            ut_commit(bar);
+        }
+        ut_wait(bar, phase); phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- E2: H2 = tanh(. + b2) into H2C; heads on CUDA cores
+        float mean[A] = {small[UtSmem::B3_PI + 0], small[UtSmem::B3_PI + 1], small[UtSmem::B3_PI + 2], small[UtSmem::B3_PI + 3]};
+        float val = small[UtSmem::B3_VF];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float v[32];
+            ut_ld32(tmem + UT_T0 + lane_base + q * 32, v);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const int j = q * 32 + 4 * c4;
+                float h[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    h[r] = ut_tanh(v[4 * c4 + r] + small[UtSmem::B2 + j + r]);
+                    if (q < 2) {
+#pragma unroll
+                        for (int a = 0; a < A; ++a) mean[a] = fmaf(small[UtSmem::W3_PI + a * H + j + r], h[r], mean[a]);
+                    } else {
+                        val = fmaf(small[UtSmem::W3_VF + j + r - H], h[r], val);
+                    }
+                }
+                *reinterpret_cast<float4*>(smem + UtSmem::H2C + ut_off(tid, j, 2 * H)) = make_float4(h[0], h[1], h[2], h[3]);
+            }
+        }
+        // ---- losses and their gradients w.r.t. the head outputs (stable_baselines3 PPO.train)
+        float dout[A] = {0.f, 0.f, 0.f, 0.f}, doutv = 0.f;
+        if (live) {
+            const float4 a4 = reinterpret_cast<const float4*>(act)[g];
+            const float av[A] = {a4.x, a4.y, a4.z, a4.w};
+            float z[A], lp = 0.0f;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                z[a] = (av[a] - mean[a]) * sigma_inv[a];
+                lp += -0.5f * z[a] * z[a] - logstd[a] - 0.91893853320467274178f;
+            }
+            const float lr = lp - logp_old[g];
+            const float ratio = __expf(lr);
+            const float an = (adv[g] - adv_mean) * adv_istd;
+            const float s1 = an * ratio, s2 = an * fminf(fmaxf(ratio, 1.0f - cfg.clip_range), 1.0f + cfg.clip_range);
+            // d/dlogp of -min(s1, s2): the unclipped branch carries gradient, the clamped one does not
+            const float dlp = (s1 <= s2) ? -an * ratio * cfg.inv_batch : 0.0f;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                dout[a] = dlp * z[a] * sigma_inv[a];
+                acc_db3[a] += dout[a];
+                acc_dls[a] += dlp * (z[a] * z[a] - 1.0f);
+            }
+            const float r = ret[g];
+            doutv = cfg.vf_coef * 2.0f * (val - r) * cfg.inv_batch;
+            acc_db3v += doutv;
+            st_pl += -fminf(s1, s2); st_vl += (r - val) * (r - val);
+            st_kl += (ratio - 1.0f) - lr; st_clip += (fabsf(ratio - 1.0f) > cfg.clip_range) ? 1.0f : 0.0f;
+            st_ratio += ratio; st_n += 1.0f;
+        }
+        {   // dOut row: [dmean0..3, dvalue, 1, 0...]; the ones column turns the same MMAs into bias-gradient sums
+            *reinterpret_cast<float4*>(smem + UtSmem::DO + ut_off(tid, 0, 16)) = make_float4(dout[0], dout[1], dout[2], dout[3]);
+            *reinterpret_cast<float4*>(smem + UtSmem::DO + ut_off(tid, 4, 16)) = make_float4(doutv, live ? 1.0f : 0.0f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(smem + UtSmem::DO + ut_off(tid, 8, 16)) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(smem + UtSmem::DO + ut_off(tid, 12, 16)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        UT_FENCE_SYNC();
+        // ---- M3: head weight gradients  D3 += [H2]^T dOut   (A, B MN-major views; K = 128 samples)
+        if (tid == 0) {
+            ut_gemm(tmem + UT_D3, sb + UtSmem::H2C, 2 * H * 32, 128, 2 * H * 32, sb + UtSmem::DO, 16 * 32, 128, 16 * 32, UT_ROWS / 8,
+                    ut_idesc(16, 1, 1), first);
+            ut_commit(bar);
+        }
+        ut_wait(bar, phase); phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- E3: dZ2 = (dOut W3) * (1 - H2^2), in place over H2C
+#pragma unroll
+        for (int c4 = 0; c4 < 2 * H / 4; ++c4) {
+            const int j = 4 * c4;
+            float4* ptr = reinterpret_cast<float4*>(smem + UtSmem::H2C + ut_off(tid, j, 2 * H));
+            float4 h = *ptr;
+            float hv[4] = {h.x, h.y, h.z, h.w}, o[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float dh;
+                if (j < H) {
+                    dh = dout[0] * small[UtSmem::W3_PI + 0 * H + j + r] + dout[1] * small[UtSmem::W3_PI + 1 * H + j + r] +
+                         dout[2] * small[UtSmem::W3_PI + 2 * H + j + r] + dout[3] * small[UtSmem::W3_PI + 3 * H + j + r];
+                } else {
+                    dh = doutv * small[UtSmem::W3_VF + j + r - H];
+                }
+                o[r] = dh * (1.0f - hv[r] * hv[r]);
+            }
+            *ptr = make_float4(o[0], o[1], o[2], o[3]);
+        }
+        UT_FENCE_SYNC();
+        // ---- M4: layer-2 weight / bias gradients and the data gradient into layer 1
+        if (tid == 0) {
+            // Da += [dZ2]^T H1_pi ; Db += [dZ2]^T H1_vf   (rows 0-63 of Da and 64-127 of Db are the wanted blocks)
+            ut_gemm(tmem + UT_DA, sb + UtSmem::H2C, 2 * H * 32, 128, 2 * H * 32, sb + UtSmem::H1C, 2 * H * 32, 128, 2 * H * 32, UT_ROWS / 8,
+                    ut_idesc(H, 1, 1), first);
+            ut_gemm(tmem + UT_DB, sb + UtSmem::H2C, 2 * H * 32, 128, 2 * H * 32, sb + UtSmem::H1C + 16 * 128, 2 * H * 32, 128, 2 * H * 32,
+                    UT_ROWS / 8, ut_idesc(H, 1, 1), first);
+            ut_gemm(tmem + UT_DB2, sb + UtSmem::H2C, 2 * H * 32, 128, 2 * H * 32, sb + UtSmem::DO, 16 * 32, 128, 16 * 32, UT_ROWS / 8,
+                    ut_idesc(16, 1, 1), first);
+            // dH1 = dZ2 W2: A = the tower's K-major sub-block of H2C, B = W2 read MN-major (n = input unit, k = output unit)
+            ut_gemm(tmem + UT_T0, sb + UtSmem::H2C, 128, 2 * H * 32, 256, sb + UtSmem::W2_PI, H * 32, 128, H * 32, H / 8, ut_idesc(H, 0, 1), 0u);
+            ut_gemm(tmem + UT_T0 + H, sb + UtSmem::H2C + 16 * 128, 128, 2 * H * 32, 256, sb + UtSmem::W2_VF, H * 32, 128, H * 32, H / 8,
+                    ut_idesc(H, 0, 1), 0u);
+            ut_commit(bar);
+        }
+        ut_wait(bar, phase); phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- E4: dZ1 = dH1 * (1 - H1^2), in place over H1C
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float v[32];
+            ut_ld32(tmem + UT_T0 + lane_base + q * 32, v);
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const int j = q * 32 + 4 * c4;
+                float4* ptr = reinterpret_cast<float4*>(smem + UtSmem::H1C + ut_off(tid, j, 2 * H));
+                float4 h = *ptr;
+                *ptr = make_float4(v[4 * c4 + 0] * (1.0f - h.x * h.x), v[4 * c4 + 1] * (1.0f - h.y * h.y),
+                                   v[4 * c4 + 2] * (1.0f - h.z * h.z), v[4 * c4 + 3] * (1.0f - h.w * h.w));
+            }
+        }
+        UT_FENCE_SYNC();
+        // ---- M5: layer-1 weight / bias gradients
+        if (tid == 0) {
+            ut_gemm(tmem + UT_DW1, sb + UtSmem::H1C, 2 * H * 32, 128, 2 * H * 32, sb + UtSmem::XB, DP * 32, 128, DP * 32, UT_ROWS / 8,
+                    ut_idesc(DP, 1, 1), first);
+            ut_gemm(tmem + UT_DB1, sb + UtSmem::H1C, 2 * H * 32, 128, 2 * H * 32, sb + UtSmem::DO, 16 * 32, 128, 16 * 32, UT_ROWS / 8,
+                    ut_idesc(16, 1, 1), first);
+            ut_commit(bar);
+        }
+        ut_wait(bar, phase); phase ^= 1u;       // XB / H1C / DO are rewritten by the next tile
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        first = 1u;
+    }
+
+    // ---- read the accumulated weight gradients out of TMEM into this CTA's partial (thread == output neuron row)
+    float* outp = out_partial + (size_t)blockIdx.x * P;
+    const bool is_pi = tid < H;
+    const int j = is_pi ? tid : tid - H;                 // neuron index inside the tower
+    const int tower_off = is_pi ? 0 : pi_count;
+    const int o_w1 = tower_off, o_b1 = o_w1 + H * d, o_w2 = o_b1 + H, o_b2 = o_w2 + H * H, o_w3 = o_b2 + H;
+    if (first != 0u) {
+        {   // dW2: rows 0-63 of Da, rows 64-127 of Db
+            const uint32_t src = tmem + (is_pi ? UT_DA : UT_DB) + lane_base;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float v[32];
+                ut_ld32(src + half * 32, v);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) outp[o_w2 + j * H + half * 32 + c] = v[c];
+            }
+        }
+        {   // dW1
+            float v[32];
+            ut_ld32(tmem + UT_DW1 + lane_base, v);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) if (c < d) outp[o_w1 + j * d + c] = v[c];
+        }
+        {   // head weights, biases
+            float v3[16], vb2[16], vb1[16];
+            ut_ld16(tmem + UT_D3 + lane_base, v3);
+            ut_ld16(tmem + UT_DB2 + lane_base, vb2);
+            ut_ld16(tmem + UT_DB1 + lane_base, vb1);
+            if (is_pi) {
+#pragma unroll
+                for (int a = 0; a < A; ++a) outp[o_w3 + a * H + j] = v3[a];
+            } else {
+                outp[o_w3 + j] = v3[4];
+            }
+            outp[o_b2 + j] = vb2[5];
+            outp[o_b1 + j] = vb1[5];
+        }
+    } else {
+        // this CTA had no tile: its partial is all zeros
+        for (int k = tid; k < P; k += blockDim.x) outp[k] = 0.0f;
+    }
+    // small sums: warp shuffle then shared atomics (24 slots), then thread 0..23 writes them
+    float red[20] = {acc_db3[0], acc_db3[1], acc_db3[2], acc_db3[3], acc_db3v, acc_dls[0], acc_dls[1], acc_dls[2], acc_dls[3],
+                     st_pl, st_vl, st_kl, st_clip, st_ratio, st_n, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 15; ++k) {
+        float x = red[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        if ((tid & 31) == 0) atomicAdd(&small[UtSmem::RED + k], x);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < A) {
+        outp[pi_count - A + tid] = small[UtSmem::RED + tid];                                  // db3_pi
+        // entropy bonus: loss += -ent_coef * mean(entropy), d/dlog_std = -ent_coef (added once, by CTA 0)
+        outp[pi_count + vf_count + tid] = small[UtSmem::RED + 5 + tid] + (blockIdx.x == 0 ? -cfg.ent_coef : 0.0f);
+    }
+    if (tid == 0) outp[pi_count + vf_count - 1] = small[UtSmem::RED + 4];                     // db3_vf
+    if (tid < 8) {
+        float v = 0.0f;
+        if (tid < 6) v = small[UtSmem::RED + 9 + tid];
+        out_stats[(size_t)blockIdx.x * 8 + tid] = v;
+    }
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)UT_TMEM_COLS) : "memory");
+}
+
+// ------------------------------------------------------------------ minibatch advantage statistics (mean, unbiased std)
+__global__ void __launch_bounds__(256)
+ppo_adv_stats_kernel(const float* __restrict__ adv, const long long* __restrict__ idx, int batch, double* __restrict__ scratch,
+                     float* __restrict__ out) {
+    __shared__ double s_a[8], s_b[8];
+    __shared__ bool is_last;
+    double a = 0.0, b = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < batch; i += gridDim.x * blockDim.x) {
+        double v = (double)adv[idx[i]];
+        a += v; b += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_b[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ta = 0, tb = 0;
+        for (int k = 0; k < 8; ++k) { ta += s_a[k]; tb += s_b[k]; }
+        atomicAdd(&scratch[0], ta); atomicAdd(&scratch[1], tb);
+        __threadfence();
+        double prev = atomicAdd(&scratch[2], 1.0);
+        is_last = (prev == (double)(gridDim.x - 1));
+    }
+    __syncthreads();
+    if (!is_last || threadIdx.x != 0) return;
+    __threadfence();
+    volatile double* sc = scratch;
+    double n = (double)batch, mean = sc[0] / n;
+    double var = batch > 1 ? (sc[1] - n * mean * mean) / (n - 1.0) : 0.0;       // torch.std(): unbiased
+    if (var < 0.0) var = 0.0;
+    out[0] = (float)mean; out[1] = (float)sqrt(var);
+    scratch[0] = 0.0; scratch[1] = 0.0; scratch[2] = 0.0;
+}
+
+// ------------------------------------------------------------------ partial-gradient reduction: grad[k] = sum_c partial[c][k]
+__global__ void __launch_bounds__(256)
+ppo_grad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ stats_partial, int ncta, int P,
+                       float* __restrict__ grad, float* __restrict__ stats) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < P) {
+        float s = 0.0f;
+        for (int c = 0; c < ncta; ++c) s += partial[(size_t)c * P + k];
+        grad[k] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 8 && stats != nullptr) {
+        float s = 0.0f;
+        for (int c = 0; c < ncta; ++c) s += stats_partial[(size_t)c * 8 + threadIdx.x];
+        stats[threadIdx.x] = s;
+    }
+}
+
+// ------------------------------------------------------------------ clip_grad_norm_ + Adam, one block
+__global__ void __launch_bounds__(1024)
+ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, int P,
+                float lr, float beta1, float beta2, float eps, float max_norm, float grad_scale, int* __restrict__ step_ctr,
+                float* __restrict__ norm_out) {
+    __shared__ float s_red[32];
+    __shared__ float s_coef;
+    float ss = 0.0f;
+    for (int k = threadIdx.x; k < P; k += blockDim.x) { float g = grad[k] * grad_scale; ss = fmaf(g, g, ss); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float x = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (threadIdx.x == 0) {
+            const float norm = sqrtf(x);
+            s_coef = fminf(1.0f, max_norm / (norm + 1e-6f));          // torch.nn.utils.clip_grad_norm_
+            if (norm_out != nullptr) norm_out[0] = norm;
+            step_ctr[0] += 1;
+        }
+    }
+    __syncthreads();
+    const float coef = s_coef * grad_scale;
+    const int t = step_ctr[0];
+    const float bc1 = 1.0f - powf(beta1, (float)t), bc2 = 1.0f - powf(beta2, (float)t);
+    for (int k = threadIdx.x; k < P; k += blockDim.x) {
+        const float g = grad[k] * coef;
+        const float mk = beta1 * m[k] + (1.0f - beta1) * g;
+        const float vk = beta2 * v[k] + (1.0f - beta2) * g * g;
+        m[k] = mk; v[k] = vk;
+        params[k] -= lr * (mk / bc1) / (sqrtf(vk / bc2) + eps);        // torch.optim.Adam (no amsgrad, no weight decay)
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+static int g_ut_sm_count = 0;
+
+int ppok_update_grid(int batch) {
+    if (g_ut_sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+        if (cudaDeviceGetAttribute(&g_ut_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        if (cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL) != cudaSuccess) {
+            g_ut_sm_count = 0;
+            return -1;
+        }
+    }
+    const int ntiles = (batch + UT_ROWS - 1) / UT_ROWS;
+    return ntiles < g_ut_sm_count ? ntiles : g_ut_sm_count;
+}
+
+cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, const float* act, const float* logp_old,
+                                const float* adv, const float* ret, const long long* idx, int batch, float clip_range,
+                                float ent_coef, float vf_coef, double* scratch, float* adv_stats, float* partial,
+                                float* stats_partial, float* grad, float* stats, cudaStream_t st) {
+    const int grid = ppok_update_grid(batch);
+    if (grid <= 0) return cudaErrorUnknown;
+    const int H_ = PPO_H, A_ = PPO_A;
+    const int P = (H_ * d + H_ + H_ * H_ + H_ + A_ * H_ + A_) + (H_ * d + H_ + H_ * H_ + H_ + H_ + 1) + A_;
+    int sblocks = (batch + 256 * 8 - 1) / (256 * 8);
+    if (sblocks > 256) sblocks = 256;
+    ppo_adv_stats_kernel<<<sblocks, 256, 0, st>>>(adv, idx, batch, scratch, adv_stats);
+    PpoLossCfg cfg{clip_range, ent_coef, vf_coef, 1.0f / (float)batch};
+    ppo_grad_tc_kernel<<<grid, UT_ROWS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, adv_stats, cfg,
+                                                             partial, stats_partial, P);
+    ppo_grad_reduce_kernel<<<(P + 255) / 256, 256, 0, st>>>(partial, stats_partial, grid, P, grad, stats);
+    return cudaGetLastError();
+}
+
+cudaError_t ppok_adam(float* params, const float* grad, float* m, float* v, int P, float lr, float beta1, float beta2, float eps,
+                      float max_norm, float grad_scale, int* step_ctr, float* norm_out, cudaStream_t st) {
+    ppo_adam_kernel<<<1, 1024, 0, st>>>(params, grad, m, v, P, lr, beta1, beta2, eps, max_norm, grad_scale, step_ctr, norm_out);
+    return cudaGetLastError();
+}

@@ -8,9 +8,11 @@ vf_coef, max_grad_norm, seed, device).learn(total_timesteps)``.
 Rollout path (every agent step, no host sync): hand-written kernels of libfwsim.so --
 running moments (ppo_moments_update), policy/value forward + Gaussian sampling (ppo_policy_forward), env step
 (fw_step), reward normalisation (ppo_reward_normalize), time-limit bootstrap (ppo_timeout_bootstrap), and GAE
-(ppo_gae) once per rollout.  The minibatch update uses torch autograd on one flat parameter vector (library
-GEMMs: the layers are 28/64 wide, far below tensor-core efficiency either way) whose gradient is a single
-contiguous buffer -- exactly what the one collective of the path, the NCCL gradient all-reduce, wants.
+(ppo_gae) once per rollout.  The minibatch update is hand-written too (update="kernel"): one fused tcgen05
+forward+backward kernel per minibatch (ppo_minibatch_grad) and one clip+Adam kernel (ppo_adam_step) on ONE flat
+parameter vector, whose gradient is a single contiguous 49 KB buffer -- exactly what the one collective of the
+path, the NCCL gradient all-reduce, wants.  update="torch" keeps a plain autograd implementation as the fp32
+reference the tests compare against.
 """
 from __future__ import annotations
 
@@ -198,7 +200,7 @@ class PPO:
                  clip_range: float = 0.2, ent_coef: float = 0.0, vf_coef: float = 0.5, max_grad_norm: float = 0.5,
                  seed: int = 0, device: str | torch.device | None = None, verbose: int = 0, tensorboard_log=None,
                  normalize: bool = True, norm_reward: bool = True, clip_obs: float = 10.0, use_cuda_graph: bool = True,
-                 tensor_core_forward: bool = True):
+                 tensor_core_forward: bool = True, update: str = "kernel"):
         if policy != "MlpPolicy":
             raise ValueError("only 'MlpPolicy' (the policy the reference trains) is implemented")
         if not torch.cuda.is_available():
@@ -224,6 +226,16 @@ class PPO:
         self.last_values = torch.zeros(N, **f32)
         self.num_timesteps = 0
         self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)    # Philox step counter (uint32 bits)
+        if update not in ("kernel", "torch"):
+            raise ValueError("update must be 'kernel' (hand-written tcgen05 kernels) or 'torch' (autograd reference)")
+        self.update = update
+        P = self.policy.count
+        self._ws = torch.zeros(int(self.lib.ppo_update_workspace_floats(self.d)), **f32)
+        self._grad = torch.zeros(P, **f32)
+        self._adam_m, self._adam_v = torch.zeros(P, **f32), torch.zeros(P, **f32)
+        self._adam_t = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._grad_norm = torch.zeros(1, **f32)
+        self._stats, self._stats_mb = torch.zeros(8, **f32), torch.zeros(8, **f32)
         self.use_graph = bool(use_cuda_graph)
         self.tensor_core_forward = bool(tensor_core_forward)
         self._graph = None
@@ -309,8 +321,43 @@ class PPO:
         _lib.check(self.lib.ppo_gae(_p(b["rew"]), _p(b["val"]), _p(b["done"]), _p(self.last_values), self.n_steps,
                                     self.n_envs, self.gamma, self.gae_lambda, _p(b["adv"]), _p(b["ret"]), _stream()))
 
-    # ------------------------------------------------------------------ update (torch autograd on the flat vector)
+    # ------------------------------------------------------------------ update
+    def _minibatch_grad_kernel(self, idx: torch.Tensor, grad: torch.Tensor, stats: torch.Tensor | None = None) -> None:
+        """Fused tcgen05 forward+backward of one minibatch (csrc/ppo_update_tc.cu) into `grad`."""
+        b = self.buf
+        _lib.check(self.lib.ppo_minibatch_grad(
+            _p(self.policy.theta), self.d, _p(b["obs"]), _p(b["act"]), _p(b["logp"]), _p(b["adv"]), _p(b["ret"]), _p(idx),
+            int(idx.numel()), self.clip_range, self.ent_coef, self.vf_coef, _p(self._ws), _p(grad), _p(stats), _stream()))
+
     def train(self) -> dict:
+        return self._train_kernel() if self.update == "kernel" else self._train_torch()
+
+    def _train_kernel(self) -> dict:
+        """SB3 PPO.train with hand-written kernels: per minibatch one fused gradient kernel (tensor cores), the
+        NCCL all-reduce of the 49 KB gradient when world > 1, and one clip+Adam kernel.  No host sync inside."""
+        total = self.n_steps * self.n_envs
+        bs = min(self.batch_size, total)
+        theta = self.policy.theta.data
+        lr, (b1, b2), eps = (self.optimizer.param_groups[0][k] for k in ("lr", "betas", "eps"))
+        self._stats.zero_()
+        for _ in range(self.n_epochs):
+            perm = torch.randperm(total, device=self.device, generator=self._gen)
+            for s in range(0, total, bs):
+                idx = perm[s:s + bs]
+                self._minibatch_grad_kernel(idx, self._grad, self._stats_mb)
+                if self.world > 1:
+                    import torch.distributed as dist
+                    dist.all_reduce(self._grad)                       # the path's one collective: 49 KB over NVLink
+                _lib.check(self.lib.ppo_adam_step(_p(theta), _p(self._grad), _p(self._adam_m), _p(self._adam_v),
+                                                  self.policy.count, lr, b1, b2, eps, self.max_grad_norm, 1.0 / self.world,
+                                                  _p(self._adam_t), _p(self._grad_norm), _stream()))
+        st = self._stats_mb
+        n = max(float(st[5]), 1.0)
+        return dict(policy_loss=float(st[0]) / n, value_loss=float(st[1]) / n, approx_kl=float(st[2]) / n,
+                    clip_fraction=float(st[3]) / n, loss=float(st[0]) / n + self.vf_coef * float(st[1]) / n,
+                    grad_norm=float(self._grad_norm))
+
+    def _train_torch(self) -> dict:
         b = self.buf
         T, N, D = self.n_steps, self.n_envs, self.d
         total = T * N
@@ -387,6 +434,7 @@ class PPO:
 
     def save(self, path: str) -> None:
         torch.save({"policy": self.policy.state_dict(), "optimizer": self.optimizer.state_dict(),
+                    "adam": {"m": self._adam_m.clone(), "v": self._adam_v.clone(), "t": int(self._adam_t.item())},
                     "vecnorm": self.vecnorm.state_dict(), "num_timesteps": self.num_timesteps,
                     "global_step": int(self._step_dev.item()), "seed": self.seed, "obs_dim": self.d}, path)
 
@@ -394,6 +442,8 @@ class PPO:
         ck = torch.load(path, map_location=self.device, weights_only=False)
         self.policy.load_state_dict(ck["policy"])
         self.optimizer.load_state_dict(ck["optimizer"])
+        if "adam" in ck:
+            self._adam_m.copy_(ck["adam"]["m"]); self._adam_v.copy_(ck["adam"]["v"]); self._adam_t.fill_(int(ck["adam"]["t"]))
         self.vecnorm.load_state_dict(ck["vecnorm"])
         self.num_timesteps = ck["num_timesteps"]
         self._step_dev.fill_(int(ck["global_step"]))

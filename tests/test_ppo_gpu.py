@@ -209,3 +209,101 @@ def test_checkpoint_round_trip(model, tmp_path):
         model.policy.theta.zero_()
     model.load(p)
     assert torch.equal(theta, model.policy.theta)
+
+
+def _torch_minibatch_grad(model, idx):
+    """Plain PyTorch fp32 reference of one SB3 PPO minibatch gradient on the flat parameter vector."""
+    b = model.buf
+    D = model.d
+    obs, act = b["obs"].view(-1, D)[idx], b["act"].view(-1, 4)[idx]
+    adv, ret, lp_old = b["adv"].view(-1)[idx], b["ret"].view(-1)[idx], b["logp"].view(-1)[idx]
+    a = (adv - adv.mean()) / (adv.std() + 1e-8)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    values, logp, entropy = model.policy.evaluate_actions(obs, act)
+    ratio = torch.exp(logp - lp_old)
+    pl = -torch.min(a * ratio, a * torch.clamp(ratio, 1 - model.clip_range, 1 + model.clip_range)).mean()
+    vl = torch.nn.functional.mse_loss(ret, values)
+    loss = pl - model.ent_coef * entropy.mean() + model.vf_coef * vl
+    model.policy.theta.grad = None
+    loss.backward()
+    g = model.policy.theta.grad.detach().clone()
+    model.policy.theta.grad = None
+    return g, float(pl), float(vl), float(((ratio - 1) - (logp - lp_old)).mean())
+
+
+@pytest.mark.parametrize("batch", [100, 128, 4000, 16000])
+def test_fused_tensor_core_gradient_matches_torch_autograd(model, batch):
+    """ppo_minibatch_grad (tcgen05, TF32 operands, fp32 accumulate) vs torch autograd in fp32.  Tolerance: per
+    parameter tensor, relative L2 error <= 2e-2 and cosine >= 0.9995 (TF32 keeps 10 mantissa bits)."""
+    model.collect_rollouts()
+    with torch.no_grad():      # move the policy away from the data-collecting one so that ratios / clipping are live
+        model.policy.theta.add_(0.02 * torch.randn(model.policy.count, device=model.device, generator=model._gen))
+    total = model.n_steps * model.n_envs
+    idx = torch.randperm(total, device=model.device, generator=model._gen)[:batch]
+    ref, pl, vl, kl = _torch_minibatch_grad(model, idx)
+    got = torch.zeros_like(ref)
+    stats = torch.zeros(8, device=model.device)
+    model._minibatch_grad_kernel(idx, got, stats)
+    torch.cuda.synchronize()
+    for name, (a, b, shp) in model.policy.slices.items():
+        r, g = ref[a:b], got[a:b]
+        rel = float((g - r).norm() / (r.norm() + 1e-12))
+        cos = float(torch.dot(g, r) / (g.norm() * r.norm() + 1e-20))
+        assert rel < 2e-2 and cos > 0.9995, (name, rel, cos, float(r.norm()))
+    assert float((got - ref).norm() / ref.norm()) < 1e-2
+    n = float(stats[5])
+    assert n == batch
+    assert float(stats[0]) / n == pytest.approx(pl, rel=2e-2, abs=2e-3)
+    assert float(stats[1]) / n == pytest.approx(vl, rel=2e-2, abs=2e-3)
+    assert float(stats[2]) / n == pytest.approx(kl, rel=5e-2, abs=1e-3)
+
+
+def test_adam_step_matches_torch_optim(model):
+    from pyflyt_drone_b200 import _lib
+    from pyflyt_drone_b200.ppo import _p, _stream
+    P, dev = model.policy.count, model.device
+    g = model._gen
+    theta = torch.randn(P, device=dev, generator=g) * 0.1
+    ref = torch.nn.Parameter(theta.clone())
+    opt = torch.optim.Adam([ref], lr=3e-4, eps=1e-5)
+    mine = theta.clone()
+    m, v = torch.zeros(P, device=dev), torch.zeros(P, device=dev)
+    t = torch.zeros(1, dtype=torch.int32, device=dev)
+    norm = torch.zeros(1, device=dev)
+    for it in range(5):
+        grad = torch.randn(P, device=dev, generator=g) * (0.001 if it % 2 else 0.05)      # below and above the clip norm
+        ref.grad = (grad / 2).clone()
+        ref_norm = torch.nn.utils.clip_grad_norm_([ref], 0.5)
+        opt.step()
+        _lib.check(model.lib.ppo_adam_step(_p(mine), _p(grad), _p(m), _p(v), P, 3e-4, 0.9, 0.999, 1e-5, 0.5, 0.5, _p(t), _p(norm),
+                                           _stream()))
+        torch.cuda.synchronize()
+        assert float(norm) == pytest.approx(float(ref_norm), rel=1e-5)
+        assert torch.allclose(mine, ref.detach(), atol=1e-7, rtol=1e-5)
+    assert int(t) == 5
+
+
+def test_kernel_update_learns_like_the_torch_update():
+    """Same seed, same rollouts at iteration 0: after one PPO iteration the two update paths must land on nearly
+    the same parameters (TF32 vs fp32 gradients through 8 Adam steps)."""
+    from pyflyt_drone_b200.ppo import PPO
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    out = {}
+    for mode in ("kernel", "torch"):
+        env = FixedwingVecEnv(512, preset="waypoints_v3", seed=9)
+        m = PPO("MlpPolicy", env, n_steps=16, batch_size=2048, n_epochs=2, seed=9, ent_coef=0.001, update=mode,
+                tensor_core_forward=False, use_cuda_graph=False)
+        m.learn(16 * 512)
+        out[mode] = m.policy.theta.detach().clone()
+        env.close()
+    diff = (out["kernel"] - out["torch"]).abs().max()
+    moved = (out["torch"] - FlatInit.theta(28, 9)).abs().max()
+    assert float(moved) > 1e-4
+    assert float(diff) < 0.1 * float(moved) + 2e-5
+
+
+class FlatInit:
+    @staticmethod
+    def theta(d, seed):
+        from pyflyt_drone_b200.ppo import FlatMlpPolicy
+        return FlatMlpPolicy(d, torch.device("cuda", 0), seed=seed).theta.detach()
