@@ -349,7 +349,8 @@ def run_ppo(args, rank: int, local_rank: int, world: int):
                            "envs_per_gpu": N, "n_steps": T, "minibatches_per_epoch": args.ppo_minibatches,
                            "n_epochs": args.ppo_epochs, "rollout_s": st.rollout_s, "update_s": st.update_s,
                            "rollout_env_steps_per_sec": st.env_steps / max(st.rollout_s, 1e-9),
-                           "update": "torch autograd on a flat parameter vector (library GEMMs)"},
+                           "update": "fused tcgen05 minibatch gradient kernel + clip/Adam kernel (csrc/ppo_update_tc.cu)",
+                           "forward": "tcgen05 kind::tf32 policy/value forward (csrc/ppo_tc.cu)", "rollout": "CUDA graph"},
                 "gpu_launches": int(env.launch_count - l0)}
         print(json.dumps(line), flush=True)
     env.close()

@@ -5,16 +5,21 @@
 // (reference wiring: /root/reference/train/train_Fixedwing_Waypoints_v3.py:293-337).
 //
 // Work decomposition: a persistent CTA (128 threads = 128 samples per tile, thread == sample == TMEM lane) walks
-// tiles of the minibatch.  All matrix products are tcgen05.mma kind::tf32 with fp32 accumulators in TMEM:
-//   forward   X[128x32] W1^T, H1[128x64] W2^T                      (A, B K-major)
-//   dgrad     dZ2[128x64] W2                                          (B read MN-major from the same smem copy)
+// tiles of the minibatch.  All matrix products are tcgen05.mma with fp32 accumulators in TMEM:
+//   forward   X[128x32] W1^T, H1[128x64] W2^T        kind::tf32, A and B K-major (the log-probability ratio needs
+//                                                     the forward pass to agree with the rollout to ~1e-3)
+//   dgrad     dZ2[128x64] W2                          kind::f16 (bf16), B read MN-major from the forward-layout copy
 //   wgrad     [dZ2_pi|dZ2_vf]^T H1, [dZ1_pi|dZ1_vf]^T X, [H2_pi|H2_vf]^T dOut, bias sums against a ones column
-//             (A and B read MN-major: the activation buffers written row-per-thread for the forward pass ARE
-//              the transposed operands the weight gradients need -- no transposes, no extra copies)
+//             kind::f16 (bf16), A and B read MN-major: the activation rows each thread writes for its own sample ARE
+//             the transposed operands the weight gradients need -- no transposes, no extra copies.
+//             (Measured on B200: kind::tf32 returns zeros for MN-major operands in the no-swizzle layout, bf16
+//             handles all four major combinations -- scripts/tc_probe.cu -- hence bf16 for the backward products;
+//             tanh' is recomputed from the fp32 pre-activations kept in TMEM, not from rounded activations.)
 // Both towers are stacked along M (= 128 output neurons) for the weight gradients, which accumulate in TMEM
 // across all tiles of the CTA and are read out once at the end into a per-CTA partial gradient.
 #include "ppo_kernels.h"
 
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #define H PPO_H
@@ -30,6 +35,18 @@ __device__ __forceinline__ uint32_t ut_off(int r, int c, int K) {
     return (uint32_t)((r >> 3) * (K * 32) + (c >> 2) * 128 + (r & 7) * 16 + (c & 3) * 4);
 }
 
+// same canonical layout for bf16 (8 elements per 16-byte chunk)
+__device__ __forceinline__ uint32_t ut_off16(int r, int c, int K) {
+    return (uint32_t)((r >> 3) * (K * 16) + (c >> 3) * 128 + (r & 7) * 16 + (c & 7) * 2);
+}
+__device__ __forceinline__ uint32_t ut_pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint4 ut_pack8(const float* v) {
+    return make_uint4(ut_pack2(v[0], v[1]), ut_pack2(v[2], v[3]), ut_pack2(v[4], v[5]), ut_pack2(v[6], v[7]));
+}
+
 __device__ __forceinline__ uint64_t ut_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
@@ -39,27 +56,35 @@ __device__ __forceinline__ uint64_t ut_desc(uint32_t saddr, uint32_t lbo_bytes, 
     return d;
 }
 
-// instruction descriptor: D = F32, A = B = TF32, M = 128; majors and N vary
-__device__ __forceinline__ constexpr uint32_t ut_idesc(int n, int a_mn, int b_mn) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) |
-           ((uint32_t)(UT_ROWS >> 4) << 24);
+// instruction descriptor: D = F32, M = 128; fmt 2 = TF32 (kind::tf32), 1 = BF16 (kind::f16); majors and N vary
+__device__ __forceinline__ constexpr uint32_t ut_idesc(int fmt, int n, int a_mn, int b_mn) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(UT_ROWS >> 4) << 24);
 }
 
+template <bool BF16>
 __device__ __forceinline__ void ut_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+    if (BF16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+            :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+            :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 
-// D[128 x N] (+)= A B^T over `ksteps` instructions of K = 8; per instruction the operand start addresses advance by
-// a_step / b_step bytes (256 for a K-major operand, its LBO for an MN-major one)
+// D[128 x N] (+)= A B^T over `ksteps` instructions (K = 8 tf32 / 16 bf16 each); per instruction the operand start
+// addresses advance by a_step / b_step bytes (256 for a K-major operand; LBO resp. 2*LBO for an MN-major one)
+template <bool BF16>
 __device__ __forceinline__ void ut_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step,
                                         uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step, int ksteps,
                                         uint32_t idesc, uint32_t accumulate_first) {
     for (int k = 0; k < ksteps; ++k)
-        ut_mma(tmem_d, ut_desc(a_addr + k * a_step, a_lbo, a_sbo), ut_desc(b_addr + k * b_step, b_lbo, b_sbo), idesc,
-               k > 0 ? 1u : accumulate_first);
+        ut_mma<BF16>(tmem_d, ut_desc(a_addr + k * a_step, a_lbo, a_sbo), ut_desc(b_addr + k * b_step, b_lbo, b_sbo), idesc,
+                     k > 0 ? 1u : accumulate_first);
 }
 
 __device__ __forceinline__ void ut_commit(uint32_t bar) {
@@ -117,17 +142,21 @@ __device__ __forceinline__ float ut_tanh(float x) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");   \
     } while (0)
 
-// shared-memory plan (bytes)
+// shared-memory plan (bytes): 222.5 KB of the 227 KB a CTA may own
 struct UtSmem {
-    static constexpr int XB = 0;                              // X            [128 x 32]    16 KB
-    static constexpr int H1C = XB + UT_ROWS * DP * 4;         // H1 pi|vf     [128 x 128]   64 KB (later dZ1)
-    static constexpr int H2C = H1C + UT_ROWS * 2 * H * 4;     // H2 pi|vf     [128 x 128]   64 KB (later dZ2)
-    static constexpr int DO = H2C + UT_ROWS * 2 * H * 4;      // dOut|1       [128 x 16]     8 KB
-    static constexpr int W1_PI = DO + UT_ROWS * 16 * 4;       // W1           [64 x 32]      8 KB each
+    static constexpr int XB = 0;                              // X  f32       [128 x 32]    16 KB  forward L1 A
+    static constexpr int H1C = XB + UT_ROWS * DP * 4;         // H1 f32 pi|vf [128 x 128]   64 KB  forward L2 A
+    static constexpr int H2B = H1C + UT_ROWS * 2 * H * 4;     // H2 bf16 pi|vf[128 x 128]   32 KB  wgrad L3 A; then dZ2
+    static constexpr int H1B = H2B + UT_ROWS * 2 * H * 2;     // H1 bf16 pi|vf[128 x 128]   32 KB  wgrad L2 B; then dZ1
+    static constexpr int XBB = H1B + UT_ROWS * 2 * H * 2;     // X  bf16      [128 x 32]     8 KB  wgrad L1 B
+    static constexpr int DO = XBB + UT_ROWS * DP * 2;         // dOut|1 bf16  [128 x 16]     4 KB
+    static constexpr int W1_PI = DO + UT_ROWS * 16 * 2;       // W1 f32       [64 x 32]      8 KB each
     static constexpr int W1_VF = W1_PI + H * DP * 4;
-    static constexpr int W2_PI = W1_VF + H * DP * 4;          // W2           [64 x 64]     16 KB each
+    static constexpr int W2_PI = W1_VF + H * DP * 4;          // W2 f32       [64 x 64]     16 KB each
     static constexpr int W2_VF = W2_PI + H * H * 4;
-    static constexpr int SMALL = W2_VF + H * H * 4;
+    static constexpr int W2B_PI = W2_VF + H * H * 4;          // W2 bf16      [64 x 64]      8 KB each (dgrad B)
+    static constexpr int W2B_VF = W2B_PI + H * H * 2;
+    static constexpr int SMALL = W2B_VF + H * H * 2;
     // floats inside SMALL
     static constexpr int B1 = 0 /* pi 64 | vf 64 */, B2 = 128, W3_PI = 256 /* [4][64] */, W3_VF = 512, B3_PI = 576, B3_VF = 580,
                          LOGSTD = 584, RED = 592 /* 24 block-reduction slots */, BAR = 616, TPTR = 620, NSMALL = 624;
@@ -135,22 +164,25 @@ struct UtSmem {
 };
 
 // TMEM column plan
-#define UT_T0 0      // 128: forward / dgrad scratch (pi cols 0-63, vf cols 64-127)
-#define UT_DA 128    // 64 : [dZ2]^T H1_pi   (rows 0-63 = dW2_pi)
-#define UT_DB 192    // 64 : [dZ2]^T H1_vf   (rows 64-127 = dW2_vf)
-#define UT_DW1 256   // 32 : [dZ1]^T X       (rows 0-63 dW1_pi, 64-127 dW1_vf)
-#define UT_D3 288    // 16 : [H2]^T dOut     (rows 0-63 x cols 0-3 = dW3_pi^T ; rows 64-127 x col 4 = dW3_vf)
-#define UT_DB2 304   // 16 : [dZ2]^T dOut|1  (col 5 = db2)
-#define UT_DB1 320   // 16 : [dZ1]^T dOut|1  (col 5 = db1)
+#define UT_T1 0      // 128: layer-1 pre-activations (pi cols 0-63, vf 64-127), kept for tanh' in the backward pass
+#define UT_T2 128    // 128: layer-2 pre-activations, later the data gradient dH1
+#define UT_DA 256    // 64 : [dZ2]^T H1_pi   (rows 0-63 = dW2_pi)
+#define UT_DB 320    // 64 : [dZ2]^T H1_vf   (rows 64-127 = dW2_vf)
+#define UT_DW1 384   // 32 : [dZ1]^T X       (rows 0-63 dW1_pi, 64-127 dW1_vf)
+#define UT_D3 416    // 16 : [H2]^T dOut     (rows 0-63 x cols 0-3 = dW3_pi^T ; rows 64-127 x col 4 = dW3_vf)
+#define UT_DB2 432   // 16 : [dZ2]^T dOut|1  (col 5 = db2)
+#define UT_DB1 448   // 16 : [dZ1]^T dOut|1  (col 5 = db1)
 
-__device__ void ut_load_weight(char* smem, int off, const float* __restrict__ g, int K, int d) {
+__device__ void ut_load_weight(char* smem, int off, const float* __restrict__ g, int K, int d, int off_bf16 = -1) {
     for (int i = threadIdx.x; i < H * K; i += blockDim.x) {
         int j = i / K, k = i % K;
-        *reinterpret_cast<float*>(smem + off + ut_off(j, k, K)) = k < d ? g[j * d + k] : 0.0f;
+        const float v = k < d ? g[j * d + k] : 0.0f;
+        *reinterpret_cast<float*>(smem + off + ut_off(j, k, K)) = v;
+        if (off_bf16 >= 0) *reinterpret_cast<__nv_bfloat16*>(smem + off_bf16 + ut_off16(j, k, K)) = __float2bfloat16(v);
     }
 }
 
-struct PpoLossCfg { float clip_range, ent_coef, vf_coef, inv_batch; };
+struct PpoLossCfg { float clip_range, ent_coef, vf_coef, inv_batch, grad_scale, inv_grad_scale; };
 
 // out_partial: [gridDim.x][P] gradient partial sums; out_stats: [gridDim.x][8] (pi loss, v loss, entropy, approx kl,
 // clip fraction, sum ratio, -, samples), all already divided by the minibatch size where they are means
@@ -169,8 +201,8 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
 
     ut_load_weight(smem, UtSmem::W1_PI, g_pi, DP, d);
     ut_load_weight(smem, UtSmem::W1_VF, g_vf, DP, d);
-    ut_load_weight(smem, UtSmem::W2_PI, g_pi + H * d + H, H, H);
-    ut_load_weight(smem, UtSmem::W2_VF, g_vf + H * d + H, H, H);
+    ut_load_weight(smem, UtSmem::W2_PI, g_pi + H * d + H, H, H, UtSmem::W2B_PI);
+    ut_load_weight(smem, UtSmem::W2_VF, g_vf + H * d + H, H, H, UtSmem::W2B_VF);
     if (tid < H) {
         small[UtSmem::B1 + tid] = g_pi[H * d + tid];
         small[UtSmem::B1 + H + tid] = g_vf[H * d + tid];
@@ -219,60 +251,68 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         const int srow = tile * UT_ROWS + tid;
         const bool live = srow < batch;
         const long long g = live ? idx[srow] : 0;
-        // ---- S0: gather the sample's (already normalised) observation as the A operand of layer 1
+        // ---- S0: gather the sample's (already normalised) observation: fp32 A operand of layer 1, bf16 B of wgrad L1
 #pragma unroll
-        for (int c4 = 0; c4 < DP / 4; ++c4) {
-            float v[4];
+        for (int c8 = 0; c8 < DP / 8; ++c8) {
+            float v[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { const int k = 4 * c4 + q; v[q] = (live && k < d) ? obs[(size_t)g * d + k] : 0.0f; }
-            *reinterpret_cast<float4*>(smem + UtSmem::XB + ut_off(tid, 4 * c4, DP)) = make_float4(v[0], v[1], v[2], v[3]);
+            for (int q = 0; q < 8; ++q) { const int k = 8 * c8 + q; v[q] = (live && k < d) ? obs[(size_t)g * d + k] : 0.0f; }
+            *reinterpret_cast<float4*>(smem + UtSmem::XB + ut_off(tid, 8 * c8, DP)) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(smem + UtSmem::XB + ut_off(tid, 8 * c8 + 4, DP)) = make_float4(v[4], v[5], v[6], v[7]);
+            *reinterpret_cast<uint4*>(smem + UtSmem::XBB + ut_off16(tid, 8 * c8, DP)) = ut_pack8(v);
         }
         UT_FENCE_SYNC();
-        // ---- M1: forward layer 1, both towers
+        // ---- M1: forward layer 1, both towers (tf32)
         if (tid == 0) {
-            ut_gemm(tmem + UT_T0, sb + UtSmem::XB, 128, DP * 32, 256, sb + UtSmem::W1_PI, 128, DP * 32, 256, DP / 8, ut_idesc(H, 0, 0), 0u);
-            ut_gemm(tmem + UT_T0 + H, sb + UtSmem::XB, 128, DP * 32, 256, sb + UtSmem::W1_VF, 128, DP * 32, 256, DP / 8, ut_idesc(H, 0, 0), 0u);
+            ut_gemm<false>(tmem + UT_T1, sb + UtSmem::XB, 128, DP * 32, 256, sb + UtSmem::W1_PI, 128, DP * 32, 256, DP / 8,
+                           ut_idesc(2, H, 0, 0), 0u);
+            ut_gemm<false>(tmem + UT_T1 + H, sb + UtSmem::XB, 128, DP * 32, 256, sb + UtSmem::W1_VF, 128, DP * 32, 256, DP / 8,
+                           ut_idesc(2, H, 0, 0), 0u);
             ut_commit(bar);
         }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- E1: H1 = tanh(. + b1) into the stacked [pi | vf] buffer
+        // ---- E1: H1 = tanh(z1 + b1): fp32 for the forward, bf16 for the weight gradient of layer 2
 #pragma unroll
         for (int q = 0; q < 4; ++q) {          // q = tower*2 + half
             float v[32];
-            ut_ld32(tmem + UT_T0 + lane_base + q * 32, v);
+            ut_ld32(tmem + UT_T1 + lane_base + q * 32, v);
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-                const int j = q * 32 + 4 * c4;
-                float4 o = make_float4(ut_tanh(v[4 * c4 + 0] + small[UtSmem::B1 + j + 0]), ut_tanh(v[4 * c4 + 1] + small[UtSmem::B1 + j + 1]),
-                                       ut_tanh(v[4 * c4 + 2] + small[UtSmem::B1 + j + 2]), ut_tanh(v[4 * c4 + 3] + small[UtSmem::B1 + j + 3]));
-                *reinterpret_cast<float4*>(smem + UtSmem::H1C + ut_off(tid, j, 2 * H)) = o;
+            for (int c8 = 0; c8 < 4; ++c8) {
+                const int j = q * 32 + 8 * c8;
+                float h[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) h[r] = ut_tanh(v[8 * c8 + r] + small[UtSmem::B1 + j + r]);
+                *reinterpret_cast<float4*>(smem + UtSmem::H1C + ut_off(tid, j, 2 * H)) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(smem + UtSmem::H1C + ut_off(tid, j + 4, 2 * H)) = make_float4(h[4], h[5], h[6], h[7]);
+                *reinterpret_cast<uint4*>(smem + UtSmem::H1B + ut_off16(tid, j, 2 * H)) = ut_pack8(h);
             }
         }
         UT_FENCE_SYNC();
         // ---- M2: forward layer 2 (A = the tower's 64-column sub-block of H1C)
         if (tid == 0) {
-            ut_gemm(tmem + UT_T0, sb + UtSmem::H1C, 128, 2 * H * 32, 256, sb + UtSmem::W2_PI, 128, H * 32, 256, H / 8, ut_idesc(H, 0, 0), 0u);
-            ut_gemm(tmem + UT_T0 + H, sb + UtSmem::H1C + 16 * 128, 128, 2 * H * 32, 256, sb + UtSmem::W2_VF, 128, H * 32, 256, H / 8,
-                    ut_idesc(H, 0, 0), 0u);
+            ut_gemm<false>(tmem + UT_T2, sb + UtSmem::H1C, 128, 2 * H * 32, 256, sb + UtSmem::W2_PI, 128, H * 32, 256, H / 8,
+                           ut_idesc(2, H, 0, 0), 0u);
+            ut_gemm<false>(tmem + UT_T2 + H, sb + UtSmem::H1C + 16 * 128, 128, 2 * H * 32, 256, sb + UtSmem::W2_VF, 128, H * 32, 256, H / 8,
+                           ut_idesc(2, H, 0, 0), 0u);
             ut_commit(bar);
         }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- E2: H2 = tanh(. + b2) into H2C; heads on CUDA cores
+        // ---- E2: H2 = tanh(z2 + b2) (bf16 copy for the head weight gradient); heads on CUDA cores
         float mean[A] = {small[UtSmem::B3_PI + 0], small[UtSmem::B3_PI + 1], small[UtSmem::B3_PI + 2], small[UtSmem::B3_PI + 3]};
         float val = small[UtSmem::B3_VF];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float v[32];
-            ut_ld32(tmem + UT_T0 + lane_base + q * 32, v);
+            ut_ld32(tmem + UT_T2 + lane_base + q * 32, v);
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-                const int j = q * 32 + 4 * c4;
-                float h[4];
+            for (int c8 = 0; c8 < 4; ++c8) {
+                const int j = q * 32 + 8 * c8;
+                float h[8];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    h[r] = ut_tanh(v[4 * c4 + r] + small[UtSmem::B2 + j + r]);
+                for (int r = 0; r < 8; ++r) {
+                    h[r] = ut_tanh(v[8 * c8 + r] + small[UtSmem::B2 + j + r]);
                     if (q < 2) {
 #pragma unroll
                         for (int a = 0; a < A; ++a) mean[a] = fmaf(small[UtSmem::W3_PI + a * H + j + r], h[r], mean[a]);
@@ -280,7 +320,7 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
                         val = fmaf(small[UtSmem::W3_VF + j + r - H], h[r], val);
                     }
                 }
-                *reinterpret_cast<float4*>(smem + UtSmem::H2C + ut_off(tid, j, 2 * H)) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(smem + UtSmem::H2B + ut_off16(tid, j, 2 * H)) = ut_pack8(h);
             }
         }
         // ---- losses and their gradients w.r.t. the head outputs (stable_baselines3 PPO.train)
@@ -313,83 +353,95 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
             st_kl += (ratio - 1.0f) - lr; st_clip += (fabsf(ratio - 1.0f) > cfg.clip_range) ? 1.0f : 0.0f;
             st_ratio += ratio; st_n += 1.0f;
         }
-        {   // dOut row: [dmean0..3, dvalue, 1, 0...]; the ones column turns the same MMAs into bias-gradient sums
-            *reinterpret_cast<float4*>(smem + UtSmem::DO + ut_off(tid, 0, 16)) = make_float4(dout[0], dout[1], dout[2], dout[3]);
-            *reinterpret_cast<float4*>(smem + UtSmem::DO + ut_off(tid, 4, 16)) = make_float4(doutv, live ? 1.0f : 0.0f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(smem + UtSmem::DO + ut_off(tid, 8, 16)) = make_float4(0.f, 0.f, 0.f, 0.f);
-            *reinterpret_cast<float4*>(smem + UtSmem::DO + ut_off(tid, 12, 16)) = make_float4(0.f, 0.f, 0.f, 0.f);
+        {   // dOut row (bf16): [dmean0..3, dvalue, 1, 0...]; the ones column turns the same MMAs into bias-gradient sums.
+            // The gradients are scaled up before rounding to bf16 so that 1/batch factors do not underflow its range.
+            const float sc = cfg.grad_scale;
+            float row16[16] = {dout[0] * sc, dout[1] * sc, dout[2] * sc, dout[3] * sc, doutv * sc, live ? 1.0f : 0.0f, 0.f, 0.f,
+                               0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            *reinterpret_cast<uint4*>(smem + UtSmem::DO + ut_off16(tid, 0, 16)) = ut_pack8(row16);
+            *reinterpret_cast<uint4*>(smem + UtSmem::DO + ut_off16(tid, 8, 16)) = ut_pack8(row16 + 8);
         }
         UT_FENCE_SYNC();
-        // ---- M3: head weight gradients  D3 += [H2]^T dOut   (A, B MN-major views; K = 128 samples)
+        // ---- M3: head weight gradients  D3 += [H2]^T dOut   (bf16, A and B MN-major; K = 128 samples)
         if (tid == 0) {
-            ut_gemm(tmem + UT_D3, sb + UtSmem::H2C, 2 * H * 32, 128, 2 * H * 32, sb + UtSmem::DO, 16 * 32, 128, 16 * 32, UT_ROWS / 8,
-                    ut_idesc(16, 1, 1), first);
+            ut_gemm<true>(tmem + UT_D3, sb + UtSmem::H2B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16,
+                          UT_ROWS / 16, ut_idesc(1, 16, 1, 1), first);
             ut_commit(bar);
         }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- E3: dZ2 = (dOut W3) * (1 - H2^2), in place over H2C
-#pragma unroll
-        for (int c4 = 0; c4 < 2 * H / 4; ++c4) {
-            const int j = 4 * c4;
-            float4* ptr = reinterpret_cast<float4*>(smem + UtSmem::H2C + ut_off(tid, j, 2 * H));
-            float4 h = *ptr;
-            float hv[4] = {h.x, h.y, h.z, h.w}, o[4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                float dh;
-                if (j < H) {
-                    dh = dout[0] * small[UtSmem::W3_PI + 0 * H + j + r] + dout[1] * small[UtSmem::W3_PI + 1 * H + j + r] +
-                         dout[2] * small[UtSmem::W3_PI + 2 * H + j + r] + dout[3] * small[UtSmem::W3_PI + 3 * H + j + r];
-                } else {
-                    dh = doutv * small[UtSmem::W3_VF + j + r - H];
-                }
-                o[r] = dh * (1.0f - hv[r] * hv[r]);
-            }
-            *ptr = make_float4(o[0], o[1], o[2], o[3]);
-        }
-        UT_FENCE_SYNC();
-        // ---- M4: layer-2 weight / bias gradients and the data gradient into layer 1
-        if (tid == 0) {
-            // Da += [dZ2]^T H1_pi ; Db += [dZ2]^T H1_vf   (rows 0-63 of Da and 64-127 of Db are the wanted blocks)
-            ut_gemm(tmem + UT_DA, sb + UtSmem::H2C, 2 * H * 32, 128, 2 * H * 32, sb + UtSmem::H1C, 2 * H * 32, 128, 2 * H * 32, UT_ROWS / 8,
-                    ut_idesc(H, 1, 1), first);
-            ut_gemm(tmem + UT_DB, sb + UtSmem::H2C, 2 * H * 32, 128, 2 * H * 32, sb + UtSmem::H1C + 16 * 128, 2 * H * 32, 128, 2 * H * 32,
-                    UT_ROWS / 8, ut_idesc(H, 1, 1), first);
-            ut_gemm(tmem + UT_DB2, sb + UtSmem::H2C, 2 * H * 32, 128, 2 * H * 32, sb + UtSmem::DO, 16 * 32, 128, 16 * 32, UT_ROWS / 8,
-                    ut_idesc(16, 1, 1), first);
-            // dH1 = dZ2 W2: A = the tower's K-major sub-block of H2C, B = W2 read MN-major (n = input unit, k = output unit)
-            ut_gemm(tmem + UT_T0, sb + UtSmem::H2C, 128, 2 * H * 32, 256, sb + UtSmem::W2_PI, H * 32, 128, H * 32, H / 8, ut_idesc(H, 0, 1), 0u);
-            ut_gemm(tmem + UT_T0 + H, sb + UtSmem::H2C + 16 * 128, 128, 2 * H * 32, 256, sb + UtSmem::W2_VF, H * 32, 128, H * 32, H / 8,
-                    ut_idesc(H, 0, 1), 0u);
-            ut_commit(bar);
-        }
-        ut_wait(bar, phase); phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- E4: dZ1 = dH1 * (1 - H1^2), in place over H1C
+        // ---- E3: dZ2 = (dOut W3) * tanh'(z2), tanh' recomputed from the fp32 pre-activations still in TMEM;
+        //      written (bf16, scaled) over the H2 copy
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float v[32];
-            ut_ld32(tmem + UT_T0 + lane_base + q * 32, v);
+            ut_ld32(tmem + UT_T2 + lane_base + q * 32, v);
 #pragma unroll
-            for (int c4 = 0; c4 < 8; ++c4) {
-                const int j = q * 32 + 4 * c4;
-                float4* ptr = reinterpret_cast<float4*>(smem + UtSmem::H1C + ut_off(tid, j, 2 * H));
-                float4 h = *ptr;
-                *ptr = make_float4(v[4 * c4 + 0] * (1.0f - h.x * h.x), v[4 * c4 + 1] * (1.0f - h.y * h.y),
-                                   v[4 * c4 + 2] * (1.0f - h.z * h.z), v[4 * c4 + 3] * (1.0f - h.w * h.w));
+            for (int c8 = 0; c8 < 4; ++c8) {
+                const int j = q * 32 + 8 * c8;
+                float o[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float h = ut_tanh(v[8 * c8 + r] + small[UtSmem::B2 + j + r]);
+                    float dh;
+                    if (q < 2) {
+                        dh = dout[0] * small[UtSmem::W3_PI + 0 * H + j + r] + dout[1] * small[UtSmem::W3_PI + 1 * H + j + r] +
+                             dout[2] * small[UtSmem::W3_PI + 2 * H + j + r] + dout[3] * small[UtSmem::W3_PI + 3 * H + j + r];
+                    } else {
+                        dh = doutv * small[UtSmem::W3_VF + j + r - H];
+                    }
+                    o[r] = dh * (1.0f - h * h) * cfg.grad_scale;
+                }
+                *reinterpret_cast<uint4*>(smem + UtSmem::H2B + ut_off16(tid, j, 2 * H)) = ut_pack8(o);
             }
         }
         UT_FENCE_SYNC();
-        // ---- M5: layer-1 weight / bias gradients
+        // ---- M4: layer-2 weight / bias gradients and the data gradient into layer 1 (bf16)
         if (tid == 0) {
-            ut_gemm(tmem + UT_DW1, sb + UtSmem::H1C, 2 * H * 32, 128, 2 * H * 32, sb + UtSmem::XB, DP * 32, 128, DP * 32, UT_ROWS / 8,
-                    ut_idesc(DP, 1, 1), first);
-            ut_gemm(tmem + UT_DB1, sb + UtSmem::H1C, 2 * H * 32, 128, 2 * H * 32, sb + UtSmem::DO, 16 * 32, 128, 16 * 32, UT_ROWS / 8,
-                    ut_idesc(16, 1, 1), first);
+            // Da += [dZ2]^T H1_pi ; Db += [dZ2]^T H1_vf   (rows 0-63 of Da and 64-127 of Db are the wanted blocks)
+            ut_gemm<true>(tmem + UT_DA, sb + UtSmem::H2B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::H1B, 2 * H * 16, 128, 2 * 2 * H * 16,
+                          UT_ROWS / 16, ut_idesc(1, H, 1, 1), first);
+            ut_gemm<true>(tmem + UT_DB, sb + UtSmem::H2B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::H1B + 8 * 128, 2 * H * 16, 128,
+                          2 * 2 * H * 16, UT_ROWS / 16, ut_idesc(1, H, 1, 1), first);
+            ut_gemm<true>(tmem + UT_DB2, sb + UtSmem::H2B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16,
+                          UT_ROWS / 16, ut_idesc(1, 16, 1, 1), first);
+            // dH1 = dZ2 W2: A = the tower's K-major sub-block of the dZ2 buffer, B = W2 (bf16) read MN-major
+            ut_gemm<true>(tmem + UT_T2, sb + UtSmem::H2B, 128, 2 * H * 16, 256, sb + UtSmem::W2B_PI, H * 16, 128, 2 * H * 16, H / 16,
+                          ut_idesc(1, H, 0, 1), 0u);
+            ut_gemm<true>(tmem + UT_T2 + H, sb + UtSmem::H2B + 8 * 128, 128, 2 * H * 16, 256, sb + UtSmem::W2B_VF, H * 16, 128, 2 * H * 16,
+                          H / 16, ut_idesc(1, H, 0, 1), 0u);
             ut_commit(bar);
         }
-        ut_wait(bar, phase); phase ^= 1u;       // XB / H1C / DO are rewritten by the next tile
+        ut_wait(bar, phase); phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- E4: dZ1 = dH1 * tanh'(z1) (z1 still in TMEM), written (bf16, already scaled) over the H1 copy
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float v[32], z1[32];
+            ut_ld32(tmem + UT_T2 + lane_base + q * 32, v);
+            ut_ld32(tmem + UT_T1 + lane_base + q * 32, z1);
+#pragma unroll
+            for (int c8 = 0; c8 < 4; ++c8) {
+                const int j = q * 32 + 8 * c8;
+                float o[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const float h = ut_tanh(z1[8 * c8 + r] + small[UtSmem::B1 + j + r]);
+                    o[r] = v[8 * c8 + r] * (1.0f - h * h);
+                }
+                *reinterpret_cast<uint4*>(smem + UtSmem::H1B + ut_off16(tid, j, 2 * H)) = ut_pack8(o);
+            }
+        }
+        UT_FENCE_SYNC();
+        // ---- M5: layer-1 weight / bias gradients (bf16)
+        if (tid == 0) {
+            ut_gemm<true>(tmem + UT_DW1, sb + UtSmem::H1B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::XBB, DP * 16, 128, 2 * DP * 16,
+                          UT_ROWS / 16, ut_idesc(1, DP, 1, 1), first);
+            ut_gemm<true>(tmem + UT_DB1, sb + UtSmem::H1B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16,
+                          UT_ROWS / 16, ut_idesc(1, 16, 1, 1), first);
+            ut_commit(bar);
+        }
+        ut_wait(bar, phase); phase ^= 1u;       // the operand buffers are rewritten by the next tile
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         first = 1u;
     }
@@ -408,14 +460,14 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
                 float v[32];
                 ut_ld32(src + half * 32, v);
 #pragma unroll
-                for (int c = 0; c < 32; ++c) outp[o_w2 + j * H + half * 32 + c] = v[c];
+                for (int c = 0; c < 32; ++c) outp[o_w2 + j * H + half * 32 + c] = v[c] * cfg.inv_grad_scale;
             }
         }
         {   // dW1
             float v[32];
             ut_ld32(tmem + UT_DW1 + lane_base, v);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) if (c < d) outp[o_w1 + j * d + c] = v[c];
+            for (int c = 0; c < 32; ++c) if (c < d) outp[o_w1 + j * d + c] = v[c] * cfg.inv_grad_scale;
         }
         {   // head weights, biases
             float v3[16], vb2[16], vb1[16];
@@ -424,12 +476,12 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
             ut_ld16(tmem + UT_DB1 + lane_base, vb1);
             if (is_pi) {
 #pragma unroll
-                for (int a = 0; a < A; ++a) outp[o_w3 + a * H + j] = v3[a];
+                for (int a = 0; a < A; ++a) outp[o_w3 + a * H + j] = v3[a] * cfg.inv_grad_scale;
             } else {
-                outp[o_w3 + j] = v3[4];
+                outp[o_w3 + j] = v3[4] * cfg.inv_grad_scale;
             }
-            outp[o_b2 + j] = vb2[5];
-            outp[o_b1 + j] = vb1[5];
+            outp[o_b2 + j] = vb2[5] * cfg.inv_grad_scale;
+            outp[o_b1 + j] = vb1[5] * cfg.inv_grad_scale;
         }
     } else {
         // this CTA had no tile: its partial is all zeros
@@ -578,7 +630,11 @@ cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, co
     int sblocks = (batch + 256 * 8 - 1) / (256 * 8);
     if (sblocks > 256) sblocks = 256;
     ppo_adv_stats_kernel<<<sblocks, 256, 0, st>>>(adv, idx, batch, scratch, adv_stats);
-    PpoLossCfg cfg{clip_range, ent_coef, vf_coef, 1.0f / (float)batch};
+    // per-sample head gradients carry a 1/batch factor; rescale them to O(1) before the bf16 rounding of the backward
+    // operands (a power of two, so the scaling itself is exact) and undo it when the accumulators are read out
+    float gs = 1.0f;
+    while (gs < (float)batch && gs < 1048576.0f) gs *= 2.0f;
+    PpoLossCfg cfg{clip_range, ent_coef, vf_coef, 1.0f / (float)batch, gs, 1.0f / gs};
     ppo_grad_tc_kernel<<<grid, UT_ROWS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, adv_stats, cfg,
                                                              partial, stats_partial, P);
     ppo_grad_reduce_kernel<<<(P + 255) / 256, 256, 0, st>>>(partial, stats_partial, grid, P, grad, stats);
