@@ -71,9 +71,11 @@ int ppo_reward_normalize(const float* rew, const uint8_t* flags, int32_t n, floa
                          float* ret, double* ret_stats, double* scratch, double* accum, float* rew_norm,
                          float* done_out, void* stream);
 
-/* SB3 collect_rollouts: for envs that were truncated but not terminated, rew += gamma * V(terminal_obs). */
+/* SB3 collect_rollouts: for envs that were truncated but not terminated, rew += gamma * V(terminal_obs).
+ * value_scratch: n floats (the value tower is evaluated for every row, the add is masked by the flags). */
 int ppo_timeout_bootstrap(const float* params, int32_t d, const float* term_obs_raw, const double* obs_stats,
-                          float clip_obs, const uint8_t* flags, int32_t n, float gamma, float* rew_inout, void* stream);
+                          float clip_obs, const uint8_t* flags, int32_t n, float gamma, float* rew_inout,
+                          float* value_scratch, void* stream);
 
 /* GAE over a [T,n] rollout: rewards, values, dones (done after step t), last_values [n] -> advantages, returns. */
 int ppo_gae(const float* rewards, const float* values, const float* dones, const float* last_values, int32_t T,

@@ -13,7 +13,7 @@ PPO_SYMBOLS = [
     ("ppo_counter_add", C.c_int, [_P, C.c_uint32, _P]),
     ("ppo_value_forward", C.c_int, [_P, C.c_int32, _P, _P, _F, C.c_int32, _P, _P]),
     ("ppo_reward_normalize", C.c_int, [_P, _P, C.c_int32, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
-    ("ppo_timeout_bootstrap", C.c_int, [_P, C.c_int32, _P, _P, _F, _P, C.c_int32, _F, _P, _P]),
+    ("ppo_timeout_bootstrap", C.c_int, [_P, C.c_int32, _P, _P, _F, _P, C.c_int32, _F, _P, _P, _P]),
     ("ppo_update_workspace_floats", C.c_int, [C.c_int32]),
     ("ppo_minibatch_grad", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, _F, _F, _F, _P, _P, _P, _P]),
     ("ppo_adam_step", C.c_int, [_P, _P, _P, _P, C.c_int32, _F, _F, _F, _F, _F, _F, _P, _P, _P]),

@@ -99,12 +99,13 @@ extern "C" int ppo_reward_normalize(const float* rew, const uint8_t* flags, int3
 
 extern "C" int ppo_timeout_bootstrap(const float* params, int32_t d, const float* term_obs_raw, const double* obs_stats,
                                      float clip_obs, const uint8_t* flags, int32_t n, float gamma, float* rew_inout,
-                                     void* stream) {
-    if (!params || !term_obs_raw || !flags || !rew_inout) return pfail(FW_EINVAL, "null argument");
+                                     float* value_scratch, void* stream) {
+    if (!params || !term_obs_raw || !flags || !rew_inout || !value_scratch) return pfail(FW_EINVAL, "null argument");
     if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
     int rc = check_d(d);
     if (rc) return rc;
-    PCU(ppok_bootstrap(params, d, term_obs_raw, obs_stats, clip_obs, flags, n, gamma, rew_inout, (cudaStream_t)stream));
+    PCU(ppok_bootstrap(params, d, term_obs_raw, obs_stats, clip_obs, flags, n, gamma, rew_inout, value_scratch,
+                       (cudaStream_t)stream));
     return FW_OK;
 }
 

@@ -329,46 +329,25 @@ cudaError_t ppok_reward_normalize(const float* rew, const uint8_t* flags, int n,
     return cudaGetLastError();
 }
 
-// ------------------------------------------------------------------ time-limit bootstrap (rare rows; weights from L2)
-__global__ void __launch_bounds__(128)
-ppo_bootstrap_kernel(const float* __restrict__ params, int d, const float* __restrict__ term_obs,
-                     const double* __restrict__ stats, float clip, const uint8_t* __restrict__ flags, int n, float gamma,
-                     float* __restrict__ rew) {
+// ------------------------------------------------------------------ time-limit bootstrap
+// r += gamma * V(terminal_obs) for rows that were truncated but not terminated.  The value tower runs over ALL rows
+// with the batched forward kernel (a masked per-row MLP reading weights from global memory measured 100+ us per
+// step as soon as a fraction of a percent of the rows was truncated); this kernel only applies the masked add.
+__global__ void __launch_bounds__(256)
+ppo_bootstrap_add_kernel(const float* __restrict__ vterm, const uint8_t* __restrict__ flags, int n, float gamma,
+                         float* __restrict__ rew) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t f = flags[i];
-    if (!((f & 2u) != 0 && (f & 1u) == 0)) return;       // TimeLimit.truncated = truncated and not terminated
-    const int pi_count = H * d + H + H * H + H + A * H + A;
-    const float* w1 = params + pi_count;
-    const float* b1 = w1 + H * d;
-    const float* w2 = b1 + H;
-    const float* b2 = w2 + H * H;
-    const float* w3 = b2 + H;
-    const float* b3 = w3 + H;
-    float x[PPO_DPAD];
-    for (int k = 0; k < d; ++k) {
-        float v = term_obs[(size_t)i * d + k];
-        if (stats != nullptr) v = fminf(fmaxf((v - (float)stats[k]) * (float)(1.0 / sqrt(stats[d + k] + 1e-8)), -clip), clip);
-        x[k] = v;
-    }
-    float h1[H];
-    for (int j = 0; j < H; ++j) {
-        float acc = b1[j];
-        for (int k = 0; k < d; ++k) acc = fmaf(w1[j * d + k], x[k], acc);
-        h1[j] = ppo_tanh(acc);
-    }
-    float out = b3[0];
-    for (int j = 0; j < H; ++j) {
-        float acc = b2[j];
-        for (int k = 0; k < H; ++k) acc = fmaf(w2[j * H + k], h1[k], acc);
-        out = fmaf(w3[j], ppo_tanh(acc), out);
-    }
-    rew[i] = fmaf(gamma, out, rew[i]);
+    if ((f & 2u) != 0 && (f & 1u) == 0) rew[i] = fmaf(gamma, vterm[i], rew[i]);    // TimeLimit.truncated
 }
 
 cudaError_t ppok_bootstrap(const float* params, int d, const float* term_obs, const double* stats, float clip,
-                           const uint8_t* flags, int n, float gamma, float* rew, cudaStream_t st) {
-    ppo_bootstrap_kernel<<<(n + 127) / 128, 128, 0, st>>>(params, d, term_obs, stats, clip, flags, n, gamma, rew);
+                           const uint8_t* flags, int n, float gamma, float* rew, float* value_scratch, cudaStream_t st) {
+    cudaError_t e = ppok_forward(params, d, term_obs, stats, clip, n, 0, 0, 0, nullptr, 1, nullptr, nullptr, nullptr, nullptr,
+                                 value_scratch, 0, st);
+    if (e != cudaSuccess) return e;
+    ppo_bootstrap_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(value_scratch, flags, n, gamma, rew);
     return cudaGetLastError();
 }
 

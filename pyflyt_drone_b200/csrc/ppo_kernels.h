@@ -18,7 +18,7 @@ cudaError_t ppok_reward_normalize(const float* rew, const uint8_t* flags, int n,
                                   double* ret_stats, double* scratch, double* accum, float* rew_norm, float* done_out,
                                   cudaStream_t st);
 cudaError_t ppok_bootstrap(const float* params, int d, const float* term_obs, const double* stats, float clip,
-                           const uint8_t* flags, int n, float gamma, float* rew, cudaStream_t st);
+                           const uint8_t* flags, int n, float gamma, float* rew, float* value_scratch, cudaStream_t st);
 cudaError_t ppok_gae(const float* rewards, const float* values, const float* dones, const float* last_values, int T, int n,
                      float gamma, float lam, float* adv, float* ret, cudaStream_t st);
 cudaError_t ppok_forward_tc(const float* params, int d, const float* obs_raw, const double* stats, float clip, int n,

@@ -224,6 +224,7 @@ class PPO:
                         logp=torch.zeros((T, N), **f32), adv=torch.zeros((T, N), **f32), ret=torch.zeros((T, N), **f32))
         self.act_env = torch.zeros((N, A), **f32)
         self.last_values = torch.zeros(N, **f32)
+        self._vterm = torch.zeros(N, **f32)
         self.num_timesteps = 0
         self._step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)    # Philox step counter (uint32 bits)
         if update not in ("kernel", "torch"):
@@ -313,7 +314,8 @@ class PPO:
                 b["rew"][t].copy_(rew)
                 b["done"][t].copy_((flags & 3) != 0)
             _lib.check(self.lib.ppo_timeout_bootstrap(_p(self.policy.theta), self.d, _p(term), self._stats_ptr(), vn.clip_obs,
-                                                      _p(flags), self.n_envs, self.gamma, _p(b["rew"][t]), _stream()))
+                                                      _p(flags), self.n_envs, self.gamma, _p(b["rew"][t]), _p(self._vterm),
+                                                      _stream()))
             self._obs = obs
         _lib.check(self.lib.ppo_counter_add(_p(self._step_dev), self.n_steps, _stream()))
         _lib.check(self.lib.ppo_value_forward(_p(self.policy.theta), self.d, _p(self._obs), self._stats_ptr(), vn.clip_obs,

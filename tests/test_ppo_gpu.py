@@ -147,8 +147,9 @@ def test_reward_normalize_and_bootstrap(model):
     flags = torch.from_numpy(rng.integers(0, 4, N).astype(np.uint8)).to(dev)
     rew = torch.zeros(N, device=dev)
     stats = model.vecnorm.obs_stats
+    scratch = torch.zeros(N, device=dev)
     _lib.check(model.lib.ppo_timeout_bootstrap(_p(model.policy.theta), D, _p(term), _p(stats), 10.0, _p(flags), N, 0.99,
-                                               _p(rew), _stream()))
+                                               _p(rew), _p(scratch), _stream()))
     with torch.no_grad():
         norm = torch.clamp((term.double() - stats[:D]) / torch.sqrt(stats[D:2 * D] + 1e-8), -10, 10).float()
         _, v = model.policy.towers(norm)
