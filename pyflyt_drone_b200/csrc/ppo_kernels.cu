@@ -131,8 +131,17 @@ ppo_forward_kernel(const float* __restrict__ params, int d, const float* __restr
                    uint32_t env_id0, uint32_t step, const uint32_t* __restrict__ step_dev, int deterministic,
                    float* __restrict__ obs_norm,
                    float* __restrict__ act_env, float* __restrict__ act_raw, float* __restrict__ logp,
-                   float* __restrict__ value, int want_policy) {
+                   float* __restrict__ value, int want_policy, const uint8_t* __restrict__ boot_flags, float boot_gamma,
+                   float* __restrict__ boot_rew) {
     extern __shared__ __align__(16) float smem[];
+    // time-limit bootstrap mode: only blocks holding a truncated-but-not-terminated row do any work (truncations
+    // arrive in bursts -- every env of a synchronised batch hits the step limit together -- and are absent otherwise)
+    bool boot_need = false;
+    if (boot_flags != nullptr) {
+        const int r0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (r0 < n) { const uint32_t f = boot_flags[r0]; boot_need = (f & 2u) != 0 && (f & 1u) == 0; }
+        if (!__syncthreads_or(boot_need ? 1 : 0)) return;
+    }
     float* s_pi = smem;
     float* s_vf = s_pi + TowerOff<A>::SIZE;
     float* s_mean = s_vf + TowerOff<1>::SIZE;
@@ -153,6 +162,10 @@ ppo_forward_kernel(const float* __restrict__ params, int d, const float* __restr
     load_obs(obs_raw, stats ? s_mean : nullptr, s_istd, clip, d, row, x, obs_norm);
     float v[1];
     tower_forward<1>(s_vf, x, hbuf, v);
+    if (boot_flags != nullptr) {
+        if (boot_need) boot_rew[row] = fmaf(boot_gamma, v[0], boot_rew[row]);    // TimeLimit.truncated
+        return;
+    }
     value[row] = v[0];
     if (!want_policy) return;
     float mean[A];
@@ -190,7 +203,7 @@ size_t ppo_forward_smem() {
 cudaError_t ppok_forward(const float* params, int d, const float* obs_raw, const double* stats, float clip, int n,
                          uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev, int deterministic,
                          float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, int want_policy,
-                         cudaStream_t st) {
+                         cudaStream_t st, const uint8_t* boot_flags, float boot_gamma, float* boot_rew) {
     static bool attr_set = false;
     const size_t sm = ppo_forward_smem();
     if (!attr_set) {
@@ -201,7 +214,8 @@ cudaError_t ppok_forward(const float* params, int d, const float* obs_raw, const
     const int grid = (n + PPO_FWD_THREADS - 1) / PPO_FWD_THREADS;
     ppo_forward_kernel<<<grid, PPO_FWD_THREADS, sm, st>>>(params, d, obs_raw, stats, clip, n, (uint32_t)(seed & 0xffffffffu),
                                                           (uint32_t)(seed >> 32), env_id0, step, step_dev, deterministic, obs_norm,
-                                                          act_env, act_raw, logp, value, want_policy);
+                                                          act_env, act_raw, logp, value, want_policy, boot_flags, boot_gamma,
+                                                          boot_rew);
     return cudaGetLastError();
 }
 
@@ -330,25 +344,14 @@ cudaError_t ppok_reward_normalize(const float* rew, const uint8_t* flags, int n,
 }
 
 // ------------------------------------------------------------------ time-limit bootstrap
-// r += gamma * V(terminal_obs) for rows that were truncated but not terminated.  The value tower runs over ALL rows
-// with the batched forward kernel (a masked per-row MLP reading weights from global memory measured 100+ us per
-// step as soon as a fraction of a percent of the rows was truncated); this kernel only applies the masked add.
-__global__ void __launch_bounds__(256)
-ppo_bootstrap_add_kernel(const float* __restrict__ vterm, const uint8_t* __restrict__ flags, int n, float gamma,
-                         float* __restrict__ rew) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t f = flags[i];
-    if ((f & 2u) != 0 && (f & 1u) == 0) rew[i] = fmaf(gamma, vterm[i], rew[i]);    // TimeLimit.truncated
-}
-
+// r += gamma * V(terminal_obs) for rows that were truncated but not terminated: the batched value forward in its
+// bootstrap mode (blocks without such a row exit before staging the weights; a masked per-row MLP reading weights
+// from global memory measured 100+ us per step during a truncation burst, the unmasked forward 80 us on every step).
 cudaError_t ppok_bootstrap(const float* params, int d, const float* term_obs, const double* stats, float clip,
                            const uint8_t* flags, int n, float gamma, float* rew, float* value_scratch, cudaStream_t st) {
-    cudaError_t e = ppok_forward(params, d, term_obs, stats, clip, n, 0, 0, 0, nullptr, 1, nullptr, nullptr, nullptr, nullptr,
-                                 value_scratch, 0, st);
-    if (e != cudaSuccess) return e;
-    ppo_bootstrap_add_kernel<<<(n + 255) / 256, 256, 0, st>>>(value_scratch, flags, n, gamma, rew);
-    return cudaGetLastError();
+    (void)value_scratch;
+    return ppok_forward(params, d, term_obs, stats, clip, n, 0, 0, 0, nullptr, 1, nullptr, nullptr, nullptr, nullptr,
+                        nullptr, 0, st, flags, gamma, rew);
 }
 
 // ------------------------------------------------------------------ K5: GAE, one thread per env, coalesced over envs

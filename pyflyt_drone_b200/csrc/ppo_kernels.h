@@ -11,7 +11,8 @@
 cudaError_t ppok_forward(const float* params, int d, const float* obs_raw, const double* stats, float clip, int n,
                          uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev, int deterministic,
                          float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, int want_policy,
-                         cudaStream_t st);
+                         cudaStream_t st, const uint8_t* boot_flags = nullptr, float boot_gamma = 0.0f,
+                         float* boot_rew = nullptr);
 cudaError_t ppok_counter_add(uint32_t* ctr, uint32_t inc, cudaStream_t st);
 cudaError_t ppok_moments(const float* x, int n, int d, double* stats, double* scratch, double* accum, cudaStream_t st);
 cudaError_t ppok_reward_normalize(const float* rew, const uint8_t* flags, int n, float gamma, float clip, float* ret,
