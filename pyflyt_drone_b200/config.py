@@ -308,6 +308,35 @@ def physics_only(**overrides) -> EnvConfig:
 PRESETS = {"waypoints_v3": waypoints_v3, "waypoint_objlock": waypoint_objlock, "physics_only": physics_only}
 
 
+def from_gym_kwargs(preset: str = "waypoints_v3", *, sparse_reward=None, num_targets=None, goal_reach_distance=None,
+                    flight_dome_size=None, max_duration_seconds=None, agent_hz=None, angle_representation=None,
+                    context_length=None, wind=None, **overrides) -> EnvConfig:
+    """Preset + the keyword names the reference passes to ``gym.make`` / ``FlattenWaypointEnv``
+    (train/train_Fixedwing_Waypoints_v3.py:100-117), translated to EnvConfig fields.  ``None`` keeps the preset."""
+    over = dict(overrides)
+    if sparse_reward is not None:
+        over["sparse_reward"] = int(bool(sparse_reward))
+    if num_targets is not None:
+        over["num_targets"] = int(num_targets)
+    if goal_reach_distance is not None:
+        over["goal_reach"] = float(goal_reach_distance)
+    if flight_dome_size is not None:
+        over["dome"] = over["spawn_size"] = float(flight_dome_size)
+    if agent_hz is not None:
+        if 120 % int(agent_hz) != 0:
+            raise ValueError("agent_hz must divide 120")           # fixedwing_base_env.py:97-100
+        over["inner_per_step"] = 120 // int(agent_hz)
+    if max_duration_seconds is not None:
+        over["max_steps"] = int((agent_hz or 30) * max_duration_seconds)
+    if angle_representation is not None:
+        if angle_representation not in ("euler", "quaternion"):
+            raise ValueError(f"angle_representation must be either `euler` or `quaternion`, not {angle_representation}")
+        over["angle_repr"] = 0 if angle_representation == "euler" else 1
+    if context_length is not None:
+        over["context_len"] = int(context_length)
+    return PRESETS[preset](wind=wind, **over) if preset != "physics_only" else PRESETS[preset](**over)
+
+
 def make_config(preset: str = "waypoints_v3", **overrides) -> EnvConfig:
     if preset not in PRESETS:
         raise KeyError(f"unknown preset {preset!r}; choose from {sorted(PRESETS)}")

@@ -123,3 +123,20 @@ def test_config_round_trips_into_c_struct():
     assert c.num_targets == 8 and c.n_col == 8 and c.wind_mode == 2
     assert c.r_surf[4][2] == pytest.approx(0.05) and c.col_pts[0][0] == pytest.approx(0.6)
     assert c.lift_unit[3][1] == 1.0 and c.gust_amp_hi[2] == pytest.approx(0.3)
+
+
+def test_from_gym_kwargs_reproduces_the_training_script_preset():
+    """The keyword names of the reference's gym.make call (train_Fixedwing_Waypoints_v3.py:100-110) map onto the preset."""
+    import pytest
+    from pyflyt_drone_b200 import from_gym_kwargs, waypoints_v3
+    cfg = from_gym_kwargs("waypoints_v3", sparse_reward=True, num_targets=8, goal_reach_distance=4.0,
+                          angle_representation="euler", flight_dome_size=100.0, max_duration_seconds=120.0, agent_hz=30,
+                          context_length=2, wind=None)
+    assert cfg == waypoints_v3()
+    other = from_gym_kwargs("waypoints_v3", num_targets=4, goal_reach_distance=2.0, agent_hz=60, max_duration_seconds=10.0,
+                            angle_representation="quaternion")
+    assert (other.num_targets, other.goal_reach, other.inner_per_step, other.max_steps, other.angle_repr) == (4, 2.0, 2, 600, 1)
+    with pytest.raises(ValueError):
+        from_gym_kwargs("waypoints_v3", agent_hz=50)           # fixedwing_base_env.py:97-100: agent_hz must divide 120
+    with pytest.raises(ValueError):
+        from_gym_kwargs("waypoints_v3", angle_representation="dcm")
