@@ -221,6 +221,7 @@ cudaError_t ppok_forward(const float* params, int d, const float* obs_raw, const
 
 // ------------------------------------------------------------------ K7: running moments (RunningMeanStd.update)
 // scratch = double[2*d + 2]: column sums, column sums of squares, block-arrival counter (as double), spare.
+#define MOM_ROWS 128          // rows per block: 512 blocks at 65,536 envs, every load of a thread in flight at once
 __global__ void __launch_bounds__(256)
 ppo_moments_kernel(const float* __restrict__ x, int n, int d, double* __restrict__ stats, double* __restrict__ scratch,
                    double* __restrict__ accum, int rows_per_block) {
@@ -231,11 +232,17 @@ ppo_moments_kernel(const float* __restrict__ x, int n, int d, double* __restrict
     const int col = threadIdx.x & 31, lane_row = threadIdx.x >> 5;
     const int r0 = blockIdx.x * rows_per_block, r1 = min(n, r0 + rows_per_block);
     float sum = 0.0f, sq = 0.0f;
-    if (col < d)
-        for (int r = r0 + lane_row; r < r1; r += 8) {
-            float v = x[(size_t)r * d + col];
-            sum += v; sq = fmaf(v, v, sq);
+    if (col < d) {
+        // all of this thread's loads are issued before the first add (MOM_ROWS / 8 = 16 independent requests)
+        float v[MOM_ROWS / 8];
+#pragma unroll
+        for (int k = 0; k < MOM_ROWS / 8; ++k) {
+            const int r = r0 + lane_row + 8 * k;
+            v[k] = r < r1 ? x[(size_t)r * d + col] : 0.0f;
         }
+#pragma unroll
+        for (int k = 0; k < MOM_ROWS / 8; ++k) { sum += v[k]; sq = fmaf(v[k], v[k], sq); }
+    }
     s_sum[lane_row][col] = sum; s_sq[lane_row][col] = sq;
     __syncthreads();
     if (lane_row == 0 && col < d) {
@@ -274,7 +281,7 @@ ppo_moments_kernel(const float* __restrict__ x, int n, int d, double* __restrict
 }
 
 cudaError_t ppok_moments(const float* x, int n, int d, double* stats, double* scratch, double* accum, cudaStream_t st) {
-    const int rows_per_block = 1024;
+    const int rows_per_block = MOM_ROWS;
     const int grid = (n + rows_per_block - 1) / rows_per_block;
     ppo_moments_kernel<<<grid, 256, 0, st>>>(x, n, d, stats, scratch, accum, rows_per_block);
     return cudaGetLastError();

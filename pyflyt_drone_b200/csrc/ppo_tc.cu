@@ -19,6 +19,7 @@
 #define A PPO_A
 #define DP PPO_DPAD
 #define TC_ROWS 128
+#define TC_THREADS 512
 #define TC_TMEM_COLS 128
 
 __device__ __forceinline__ uint32_t tc_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -90,9 +91,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// MUFU.TANH (max relative error 2^-11, the order of the TF32 operand rounding); ppo_update_tc.cu uses the same
+// instruction so that the update's log-probabilities reproduce the rollout's.
 __device__ __forceinline__ float tc_tanh(float x) {
-    float e = __expf(2.0f * x);
-    return 1.0f - __fdividef(2.0f, e + 1.0f);
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 __device__ __forceinline__ uint4 tc_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
@@ -134,7 +138,46 @@ __device__ void tc_load_weight(char* smem, int off, const float* __restrict__ g,
     }
 }
 
-__global__ void __launch_bounds__(TC_ROWS, 1)
+// load + normalise (VecNormalize.normalize_obs) 8 consecutive columns [8*part, 8*part+8) of observation row `grow_g`;
+// optionally store the normalised values (what the rollout buffer keeps).  Rows of a tile are contiguous in memory,
+// so the four threads of a row and the eight rows of a warp read one 896-byte span.
+__device__ __forceinline__ void tc_load8(const float* __restrict__ obs_raw, float* __restrict__ obs_norm, int d, int grow_g,
+                                         bool live, int part, bool have_stats, const float* s_mean, const float* s_istd,
+                                         float clip, float (&x)[8]) {
+    float raw[8];
+    const bool vec = (d & 3) == 0;
+    if (vec) {
+        const float4* src = reinterpret_cast<const float4*>(obs_raw + (size_t)grow_g * d);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (live && 8 * part < d) a = src[2 * part];
+        if (live && 8 * part + 4 < d) b = src[2 * part + 1];
+        raw[0] = a.x; raw[1] = a.y; raw[2] = a.z; raw[3] = a.w; raw[4] = b.x; raw[5] = b.y; raw[6] = b.z; raw[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const int k = 8 * part + i; raw[i] = (live && k < d) ? obs_raw[(size_t)grow_g * d + k] : 0.0f; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int k = 8 * part + i;
+        float v = raw[i];
+        if (have_stats) v = fminf(fmaxf((v - s_mean[k]) * s_istd[k], -clip), clip);
+        x[i] = (live && k < d) ? v : 0.0f;
+    }
+    if (obs_norm != nullptr && live) {
+        if (vec) {
+            float4* dst = reinterpret_cast<float4*>(obs_norm + (size_t)grow_g * d);
+            if (8 * part < d) dst[2 * part] = make_float4(x[0], x[1], x[2], x[3]);
+            if (8 * part + 4 < d) dst[2 * part + 1] = make_float4(x[4], x[5], x[6], x[7]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const int k = 8 * part + i; if (k < d) obs_norm[(size_t)grow_g * d + k] = x[i]; }
+        }
+    }
+}
+
+// 512 threads = 4 warpgroups: TMEM lane (= env row of the tile) = tid & 127; warpgroup q = tid >> 7 owns hidden units
+// [32q, 32q+32) of the stacked pi|vf layers in both epilogues (q 0,1 = policy tower, 2,3 = value tower).
+__global__ void __launch_bounds__(TC_THREADS, 1)
 ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __restrict__ obs_raw,
                       const double* __restrict__ stats, float clip, int n, uint32_t seed_lo, uint32_t seed_hi,
                       uint32_t env_id0, uint32_t step, const uint32_t* __restrict__ step_dev, int deterministic,
@@ -143,6 +186,8 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
     extern __shared__ __align__(1024) char smem[];
     float* small = reinterpret_cast<float*>(smem + TcSmem::SMALL);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int q = tid >> 7, lrow = tid & (TC_ROWS - 1);
+    const int grow = tid >> 2, gpart = tid & 3;
     const int pi_count = H * d + H + H * H + H + A * H + A;
     const float* g_pi = params;
     const float* g_vf = params + pi_count;
@@ -160,7 +205,7 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
         small[TcSmem::B2_VF + tid] = g_vf[H * d + H + H * H + tid];
         small[TcSmem::W3_VF + tid] = g_vf[H * d + H + H * H + H + tid];
     }
-    for (int i = tid; i < A * H; i += blockDim.x) small[TcSmem::W3_PI + i] = g_pi[H * d + H + H * H + H + i];
+    for (int i = tid; i < A * H; i += blockDim.x) small[TcSmem::W3_PI + (i % H) * A + i / H] = g_pi[H * d + H + H * H + H + i];   // [j][a]
     if (tid < A) {
         small[TcSmem::B3_PI + tid] = g_pi[H * d + H + H * H + H + A * H + tid];
         small[TcSmem::LOGSTD + tid] = params[pi_count + vf_count + tid];
@@ -188,32 +233,29 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tptr;
     const uint32_t t_pi = tmem, t_vf = tmem + H;                       // column offsets 0 and 64
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;            // this warp's 32 TMEM lanes
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;      // a warp may touch TMEM lanes 32*(warp%4)..+31
     const uint32_t s_base = tc_smem_u32(smem);
     const uint32_t step_eff = step + (step_dev != nullptr ? step_dev[0] : 0u);
+    const bool have_stats = stats != nullptr;
     uint32_t phase = 0;
+    // this warpgroup's slice: tower, first hidden unit inside the tower, TMEM columns, H1 buffer, parameter vectors
+    const bool is_pi = q < 2;
+    const int j0 = (q & 1) * 32;
+    const uint32_t tcol = (is_pi ? t_pi : t_vf) + j0;
+    const int ah = is_pi ? TcSmem::AH_PI : TcSmem::AH_VF;
+    const float* b1 = small + (is_pi ? TcSmem::B1_PI : TcSmem::B1_VF) + j0;
+    const float* b2 = small + (is_pi ? TcSmem::B2_PI : TcSmem::B2_VF) + j0;
 
     const int ntiles = (n + TC_ROWS - 1) / TC_ROWS;
+    float xcur[8];
+    if ((int)blockIdx.x < ntiles) {
+        const int gr = blockIdx.x * TC_ROWS + grow;
+        tc_load8(obs_raw, obs_norm, d, gr, gr < n, gpart, have_stats, small + TcSmem::MEAN, small + TcSmem::ISTD, clip, xcur);
+    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int row = tile * TC_ROWS + tid;
-        const bool live = row < n;
-        // ---- stage the normalised observation row (VecNormalize.normalize_obs) as the A operand of layer 1
-#pragma unroll
-        for (int c4 = 0; c4 < DP / 4; ++c4) {
-            float v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int k = 4 * c4 + q;
-                float x = 0.0f;
-                if (live && k < d) {
-                    x = obs_raw[(size_t)row * d + k];
-                    if (stats != nullptr) x = fminf(fmaxf((x - small[TcSmem::MEAN + k]) * small[TcSmem::ISTD + k], -clip), clip);
-                    if (obs_norm != nullptr) obs_norm[(size_t)row * d + k] = x;
-                }
-                v[q] = x;
-            }
-            *reinterpret_cast<float4*>(smem + TcSmem::AX + tc_off(tid, 4 * c4, DP)) = make_float4(v[0], v[1], v[2], v[3]);
-        }
+        // ---- stage the normalised observation slice as the A operand of layer 1
+        *reinterpret_cast<float4*>(smem + TcSmem::AX + tc_off(grow, 8 * gpart, DP)) = make_float4(xcur[0], xcur[1], xcur[2], xcur[3]);
+        *reinterpret_cast<float4*>(smem + TcSmem::AX + tc_off(grow, 8 * gpart + 4, DP)) = make_float4(xcur[4], xcur[5], xcur[6], xcur[7]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -223,25 +265,25 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
             tc_gemm(t_vf, s_base + TcSmem::AX, s_base + TcSmem::W1_VF, DP);
             tc_commit(bar);
         }
+        // the next tile's observations are requested now and land while this tile is processed
+        {
+            const int nt = tile + gridDim.x;
+            const int gr = nt * TC_ROWS + grow;
+            tc_load8(obs_raw, obs_norm, d, gr, nt < ntiles && gr < n, gpart, have_stats, small + TcSmem::MEAN,
+                     small + TcSmem::ISTD, clip, xcur);
+        }
         tc_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- layer-1 epilogue: bias + tanh, H1 becomes the A operand of layer 2 (this thread's own row)
+        // ---- layer-1 epilogue: bias + tanh, H1 becomes the A operand of layer 2 (this thread's row, 32 hidden units)
+        {
+            float v[32];
+            tc_ld32(tcol + lane_base, v);
 #pragma unroll
-        for (int tower = 0; tower < 2; ++tower) {
-            const uint32_t tcol = tower == 0 ? t_pi : t_vf;
-            const float* b1 = small + (tower == 0 ? TcSmem::B1_PI : TcSmem::B1_VF);
-            const int ah = tower == 0 ? TcSmem::AH_PI : TcSmem::AH_VF;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float v[32];
-                tc_ld32(tcol + lane_base + half * 32, v);
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    const int j = half * 32 + 4 * c4;
-                    float4 o = make_float4(tc_tanh(v[4 * c4 + 0] + b1[j + 0]), tc_tanh(v[4 * c4 + 1] + b1[j + 1]),
-                                           tc_tanh(v[4 * c4 + 2] + b1[j + 2]), tc_tanh(v[4 * c4 + 3] + b1[j + 3]));
-                    *reinterpret_cast<float4*>(smem + ah + tc_off(tid, j, H)) = o;
-                }
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 b = *reinterpret_cast<const float4*>(b1 + 4 * c4);
+                float4 o = make_float4(tc_tanh(v[4 * c4 + 0] + b.x), tc_tanh(v[4 * c4 + 1] + b.y),
+                                       tc_tanh(v[4 * c4 + 2] + b.z), tc_tanh(v[4 * c4 + 3] + b.w));
+                *reinterpret_cast<float4*>(smem + ah + tc_off(lrow, j0 + 4 * c4, H)) = o;
             }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -253,52 +295,69 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
             tc_gemm(t_vf, s_base + TcSmem::AH_VF, s_base + TcSmem::W2_VF, H);
             tc_commit(bar);
         }
-        tc_wait(bar, phase); phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- layer-2 epilogue fused with the heads (4 action means, 1 value) on CUDA cores
-        float mean[A] = {small[TcSmem::B3_PI + 0], small[TcSmem::B3_PI + 1], small[TcSmem::B3_PI + 2], small[TcSmem::B3_PI + 3]};
-        float val = small[TcSmem::B3_VF];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float v[32];
-            tc_ld32(t_pi + lane_base + half * 32, v);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int j = half * 32 + c;
-                const float h2 = tc_tanh(v[c] + small[TcSmem::B2_PI + j]);
-#pragma unroll
-                for (int a = 0; a < A; ++a) mean[a] = fmaf(small[TcSmem::W3_PI + a * H + j], h2, mean[a]);
-            }
-            tc_ld32(t_vf + lane_base + half * 32, v);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const int j = half * 32 + c;
-                val = fmaf(small[TcSmem::W3_VF + j], tc_tanh(v[c] + small[TcSmem::B2_VF + j]), val);
-            }
-        }
-        if (live) {
-            value[row] = val;
+        // Gaussian noise for this row (warpgroup 0), drawn while the layer-2 MMAs run
+        const int row = tile * TC_ROWS + lrow;
+        const bool live = row < n;
+        float eps[A] = {0.f, 0.f, 0.f, 0.f};
+        if (q == 0 && live && !deterministic) {
             uint4 r = tc_philox(seed_lo, seed_hi, env_id0 + (uint32_t)row, step_eff, 0u, 7u);
             float ra = sqrtf(-2.0f * __logf(tc_u01(r.x))), rb = sqrtf(-2.0f * __logf(tc_u01(r.z)));
             float s0, c0, s1, c1;
             sincospif(2.0f * tc_u01(r.y), &s0, &c0);
             sincospif(2.0f * tc_u01(r.w), &s1, &c1);
-            float eps[A] = {ra * c0, ra * s0, rb * c1, rb * s1};
+            eps[0] = ra * c0; eps[1] = ra * s0; eps[2] = rb * c1; eps[3] = rb * s1;
+        }
+        tc_wait(bar, phase); phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // ---- layer-2 epilogue: partial head sums over this warpgroup's 32 hidden units (AX is dead: reuse it)
+        {
+            float v[32];
+            tc_ld32(tcol + lane_base, v);
+            float ps[A] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c4 = 0; c4 < 8; ++c4) {
+                const float4 b = *reinterpret_cast<const float4*>(b2 + 4 * c4);
+                const float h2[4] = {tc_tanh(v[4 * c4 + 0] + b.x), tc_tanh(v[4 * c4 + 1] + b.y), tc_tanh(v[4 * c4 + 2] + b.z),
+                                     tc_tanh(v[4 * c4 + 3] + b.w)};
+                if (is_pi) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float4 w = *reinterpret_cast<const float4*>(small + TcSmem::W3_PI + (j0 + 4 * c4 + r) * A);
+                        ps[0] = fmaf(w.x, h2[r], ps[0]); ps[1] = fmaf(w.y, h2[r], ps[1]);
+                        ps[2] = fmaf(w.z, h2[r], ps[2]); ps[3] = fmaf(w.w, h2[r], ps[3]);
+                    }
+                } else {
+                    const float4 w = *reinterpret_cast<const float4*>(small + TcSmem::W3_VF + j0 + 4 * c4);
+                    ps[0] = fmaf(w.x, h2[0], ps[0]); ps[0] = fmaf(w.y, h2[1], ps[0]);
+                    ps[0] = fmaf(w.z, h2[2], ps[0]); ps[0] = fmaf(w.w, h2[3], ps[0]);
+                }
+            }
+            *reinterpret_cast<float4*>(smem + TcSmem::AX + (q * TC_ROWS + lrow) * 16) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        // ---- heads, diagonal-Gaussian sample and log-probability: one thread per env
+        if (q == 0 && live) {
+            const float4 p0 = *reinterpret_cast<const float4*>(smem + TcSmem::AX + (0 * TC_ROWS + lrow) * 16);
+            const float4 p1 = *reinterpret_cast<const float4*>(smem + TcSmem::AX + (1 * TC_ROWS + lrow) * 16);
+            const float pv0 = *reinterpret_cast<const float*>(smem + TcSmem::AX + (2 * TC_ROWS + lrow) * 16);
+            const float pv1 = *reinterpret_cast<const float*>(smem + TcSmem::AX + (3 * TC_ROWS + lrow) * 16);
+            const float mean[A] = {small[TcSmem::B3_PI + 0] + p0.x + p1.x, small[TcSmem::B3_PI + 1] + p0.y + p1.y,
+                                   small[TcSmem::B3_PI + 2] + p0.z + p1.z, small[TcSmem::B3_PI + 3] + p0.w + p1.w};
+            value[row] = small[TcSmem::B3_VF] + pv0 + pv1;
             float lp = 0.0f, av[A];
 #pragma unroll
             for (int a = 0; a < A; ++a) {
                 const float ls = small[TcSmem::LOGSTD + a];
-                const float e = deterministic ? 0.0f : eps[a];
-                av[a] = fmaf(__expf(ls), e, mean[a]);
-                lp += -0.5f * e * e - ls - 0.91893853320467274178f;
+                av[a] = fmaf(__expf(ls), eps[a], mean[a]);
+                lp += -0.5f * eps[a] * eps[a] - ls - 0.91893853320467274178f;
             }
             reinterpret_cast<float4*>(act_env)[row] = make_float4(fminf(fmaxf(av[0], -1.f), 1.f), fminf(fmaxf(av[1], -1.f), 1.f),
                                                                   fminf(fmaxf(av[2], -1.f), 1.f), fminf(fmaxf(av[3], -1.f), 1.f));
             if (act_raw != nullptr) reinterpret_cast<float4*>(act_raw)[row] = make_float4(av[0], av[1], av[2], av[3]);
             if (logp != nullptr) logp[row] = lp;
         }
-        // the next tile overwrites AX / AH and the accumulators: order this tile's TMEM reads before it
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        // the next tile overwrites AX (head partials) / AH and the accumulators
         __syncthreads();
     }
     if (warp == 0)
@@ -320,7 +379,7 @@ cudaError_t ppok_forward_tc(const float* params, int d, const float* obs_raw, co
     }
     const int ntiles = (n + TC_ROWS - 1) / TC_ROWS;
     const int grid = ntiles < sm_count ? ntiles : sm_count;          // persistent: one CTA per SM walks the tiles
-    ppo_forward_tc_kernel<<<grid, TC_ROWS, TcSmem::TOTAL, st>>>(params, d, obs_raw, stats, clip, n, (uint32_t)(seed & 0xffffffffu),
+    ppo_forward_tc_kernel<<<grid, TC_THREADS, TcSmem::TOTAL, st>>>(params, d, obs_raw, stats, clip, n, (uint32_t)(seed & 0xffffffffu),
                                                                (uint32_t)(seed >> 32), env_id0, step, step_dev, deterministic,
                                                                obs_norm, act_env, act_raw, logp, value);
     return cudaGetLastError();

@@ -26,6 +26,7 @@
 #define A PPO_A
 #define DP PPO_DPAD
 #define UT_ROWS 128
+#define UT_THREADS 512
 #define UT_TMEM_COLS 512
 
 __device__ __forceinline__ uint32_t ut_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -129,9 +130,12 @@ __device__ __forceinline__ void ut_ld16(uint32_t taddr, float (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// MUFU.TANH: one SFU instruction, max relative error 2^-11 -- the same order as the TF32 operand rounding of the
+// forward GEMMs.  The rollout forward (ppo_tc.cu) uses the same instruction, so log-probability ratios are consistent.
 __device__ __forceinline__ float ut_tanh(float x) {
-    float e = __expf(2.0f * x);
-    return 1.0f - __fdividef(2.0f, e + 1.0f);
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 #define UT_FENCE_SYNC()                                                   \
@@ -146,6 +150,8 @@ __device__ __forceinline__ float ut_tanh(float x) {
 struct UtSmem {
     static constexpr int XB = 0;                              // X  f32       [128 x 32]    16 KB  forward L1 A
     static constexpr int H1C = XB + UT_ROWS * DP * 4;         // H1 f32 pi|vf [128 x 128]   64 KB  forward L2 A
+    static constexpr int DZ2 = H1C;                           // dZ2 bf16     [128 x 128]   32 KB  aliases H1C (dead after M2)
+    static constexpr int DZ1 = H1C + UT_ROWS * 2 * H * 2;     // dZ1 bf16     [128 x 128]   32 KB  second half of H1C
     static constexpr int H2B = H1C + UT_ROWS * 2 * H * 4;     // H2 bf16 pi|vf[128 x 128]   32 KB  wgrad L3 A; then dZ2
     static constexpr int H1B = H2B + UT_ROWS * 2 * H * 2;     // H1 bf16 pi|vf[128 x 128]   32 KB  wgrad L2 B; then dZ1
     static constexpr int XBB = H1B + UT_ROWS * 2 * H * 2;     // X  bf16      [128 x 32]     8 KB  wgrad L1 B
@@ -158,7 +164,7 @@ struct UtSmem {
     static constexpr int W2B_VF = W2B_PI + H * H * 2;
     static constexpr int SMALL = W2B_VF + H * H * 2;
     // floats inside SMALL
-    static constexpr int B1 = 0 /* pi 64 | vf 64 */, B2 = 128, W3_PI = 256 /* [4][64] */, W3_VF = 512, B3_PI = 576, B3_VF = 580,
+    static constexpr int B1 = 0 /* pi 64 | vf 64 */, B2 = 128, W3_PI = 256 /* [64][4]: one float4 per hidden unit */, W3_VF = 512, B3_PI = 576, B3_VF = 580,
                          LOGSTD = 584, RED = 592 /* 24 block-reduction slots */, BAR = 616, TPTR = 620, NSMALL = 624;
     static constexpr int TOTAL = SMALL + NSMALL * 4;
 };
@@ -184,9 +190,28 @@ __device__ void ut_load_weight(char* smem, int off, const float* __restrict__ g,
 
 struct PpoLossCfg { float clip_range, ent_coef, vf_coef, inv_batch, grad_scale, inv_grad_scale; };
 
-// out_partial: [gridDim.x][P] gradient partial sums; out_stats: [gridDim.x][8] (pi loss, v loss, entropy, approx kl,
-// clip fraction, sum ratio, -, samples), all already divided by the minibatch size where they are means
-__global__ void __launch_bounds__(UT_ROWS, 1)
+// gather 8 consecutive observation columns [8*part, 8*part+8) of rollout row g (zero beyond d / for dead rows)
+__device__ __forceinline__ void ut_gather8(const float* __restrict__ obs, int d, long long g, bool live, int part, float (&x)[8]) {
+    if ((d & 3) == 0) {                                   // rows are 16-byte aligned: two vector loads
+        const float4* src = reinterpret_cast<const float4*>(obs + (size_t)g * d);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        if (live && 8 * part < d) a = src[2 * part];
+        if (live && 8 * part + 4 < d) b = src[2 * part + 1];
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const int k = 8 * part + i; x[i] = (live && k < d) ? obs[(size_t)g * d + k] : 0.0f; }
+    }
+}
+
+// out_partial: [gridDim.x][P] gradient partial sums; out_stats: [gridDim.x][8] (pi loss, v loss, approx kl, clip
+// fraction, sum ratio, samples, -, -) as sums over the CTA's samples
+//
+// 512 threads = 4 warpgroups.  TMEM lane (= sample row of the tile) = tid & 127; warpgroup q = tid >> 7 owns the 32
+// activation columns [32q, 32q+32) of the stacked pi|vf layer (q 0,1 = policy tower, 2,3 = value tower) in every
+// epilogue, so the per-thread serial work is a quarter of a row and 16 warps hide each other's TMEM/SFU latency.
+// tanh' factors are kept in registers (packed bf16) from the forward epilogues instead of being recomputed.
+__global__ void __launch_bounds__(UT_THREADS, 1)
 ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restrict__ obs, const float* __restrict__ act,
                    const float* __restrict__ logp_old, const float* __restrict__ adv, const float* __restrict__ ret,
                    const long long* __restrict__ idx, int batch, const float* __restrict__ adv_stats, PpoLossCfg cfg,
@@ -194,6 +219,9 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
     extern __shared__ __align__(1024) char smem[];
     float* small = reinterpret_cast<float*>(smem + UtSmem::SMALL);
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int q = tid >> 7;                  // warpgroup = column block
+    const int row = tid & (UT_ROWS - 1);     // sample row inside the tile = TMEM lane
+    const int grow = tid >> 2, gpart = tid & 3;   // gather role: row, 8-column part
     const int pi_count = H * d + H + H * H + H + A * H + A;
     const int vf_count = H * d + H + H * H + H + H + 1;
     const float* g_pi = params;
@@ -210,7 +238,7 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         small[UtSmem::B2 + H + tid] = g_vf[H * d + H + H * H + tid];
         small[UtSmem::W3_VF + tid] = g_vf[H * d + H + H * H + H + tid];
     }
-    for (int i = tid; i < A * H; i += blockDim.x) small[UtSmem::W3_PI + i] = g_pi[H * d + H + H * H + H + i];
+    for (int i = tid; i < A * H; i += blockDim.x) small[UtSmem::W3_PI + (i % H) * A + i / H] = g_pi[H * d + H + H * H + H + i];   // [j][a]
     if (tid < A) {
         small[UtSmem::B3_PI + tid] = g_pi[H * d + H + H * H + H + A * H + tid];
         small[UtSmem::LOGSTD + tid] = params[pi_count + vf_count + tid];
@@ -232,37 +260,30 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tptr;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;     // a warp may touch TMEM lanes 32*(warp%4)..+31
     const uint32_t sb = ut_smem_u32(smem);
     uint32_t phase = 0;
 
     const float adv_mean = adv_stats[0], adv_istd = 1.0f / (adv_stats[1] + 1e-8f);
-    float sigma_inv[A], logstd[A];
-#pragma unroll
-    for (int a = 0; a < A; ++a) { logstd[a] = small[UtSmem::LOGSTD + a]; sigma_inv[a] = __expf(-logstd[a]); }
 
-    // per-thread running sums over this CTA's samples: db3_pi[4], db3_vf, dlogstd[4], loss statistics[6]
+    // per-thread running sums over this CTA's samples (warpgroup 0 only): db3_pi[4], db3_vf, dlogstd[4], loss statistics[6]
     float acc_db3[A] = {0.f, 0.f, 0.f, 0.f}, acc_db3v = 0.f, acc_dls[A] = {0.f, 0.f, 0.f, 0.f};
     float st_pl = 0.f, st_vl = 0.f, st_kl = 0.f, st_clip = 0.f, st_ratio = 0.f, st_n = 0.f;
 
     const int ntiles = (batch + UT_ROWS - 1) / UT_ROWS;
     uint32_t first = 0;        // 0 on the first tile of this CTA: weight-gradient accumulators start from zero
+    float xcur[8];             // this thread's 8 gathered observation columns of the current tile (prefetched)
+    if ((int)blockIdx.x < ntiles) {
+        const int sr = blockIdx.x * UT_ROWS + grow;
+        const bool lv = sr < batch;
+        ut_gather8(obs, d, lv ? idx[sr] : 0, lv, gpart, xcur);
+    }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int srow = tile * UT_ROWS + tid;
-        const bool live = srow < batch;
-        const long long g = live ? idx[srow] : 0;
-        // ---- S0: gather the sample's (already normalised) observation: fp32 A operand of layer 1, bf16 B of wgrad L1
-#pragma unroll
-        for (int c8 = 0; c8 < DP / 8; ++c8) {
-            float v[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) { const int k = 8 * c8 + q; v[q] = (live && k < d) ? obs[(size_t)g * d + k] : 0.0f; }
-            *reinterpret_cast<float4*>(smem + UtSmem::XB + ut_off(tid, 8 * c8, DP)) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(smem + UtSmem::XB + ut_off(tid, 8 * c8 + 4, DP)) = make_float4(v[4], v[5], v[6], v[7]);
-            *reinterpret_cast<uint4*>(smem + UtSmem::XBB + ut_off16(tid, 8 * c8, DP)) = ut_pack8(v);
-        }
+        // ---- S0: the gathered (already normalised) observations become the fp32 A operand of layer 1
+        *reinterpret_cast<float4*>(smem + UtSmem::XB + ut_off(grow, 8 * gpart, DP)) = make_float4(xcur[0], xcur[1], xcur[2], xcur[3]);
+        *reinterpret_cast<float4*>(smem + UtSmem::XB + ut_off(grow, 8 * gpart + 4, DP)) = make_float4(xcur[4], xcur[5], xcur[6], xcur[7]);
         UT_FENCE_SYNC();
-        // ---- M1: forward layer 1, both towers (tf32)
+        // ---- M1: forward layer 1, both towers (tf32).  The commit also covers the previous tile's M5.
         if (tid == 0) {
             ut_gemm<false>(tmem + UT_T1, sb + UtSmem::XB, 128, DP * 32, 256, sb + UtSmem::W1_PI, 128, DP * 32, 256, DP / 8,
                            ut_idesc(2, H, 0, 0), 0u);
@@ -270,22 +291,47 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
                            ut_idesc(2, H, 0, 0), 0u);
             ut_commit(bar);
         }
+        // loss inputs of this thread's sample (warpgroup 0), requested now and consumed after layer 2
+        const int srow = tile * UT_ROWS + row;
+        const bool live = srow < batch;
+        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float lpo = 0.f, advv = 0.f, retv = 0.f;
+        if (q == 0 && live) {
+            const long long g = idx[srow];
+            a4 = reinterpret_cast<const float4*>(act)[g];
+            lpo = logp_old[g]; advv = adv[g]; retv = ret[g];
+        }
+        // prefetch the next tile's observation slice; it lands while this tile is being processed
+        float xnext[8];
+        {
+            const int nt = tile + gridDim.x;
+            const int sr = nt * UT_ROWS + grow;
+            const bool lv = nt < ntiles && sr < batch;
+            ut_gather8(obs, d, lv ? idx[sr] : 0, lv, gpart, xnext);
+        }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- E1: H1 = tanh(z1 + b1): fp32 for the forward, bf16 for the weight gradient of layer 2
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {          // q = tower*2 + half
+        // bf16 copy of X: B operand of the layer-1 weight gradient (the previous tile's M5 has drained by now)
+        *reinterpret_cast<uint4*>(smem + UtSmem::XBB + ut_off16(grow, 8 * gpart, DP)) = ut_pack8(xcur);
+        // ---- E1: H1 = tanh(z1 + b1): fp32 for the forward, bf16 for the weight gradient of layer 2; keep 1 - H1^2
+        uint32_t d1p[16], d2p[16];
+        {
             float v[32];
             ut_ld32(tmem + UT_T1 + lane_base + q * 32, v);
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
                 const int j = q * 32 + 8 * c8;
-                float h[8];
+                float h[8], dd[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) h[r] = ut_tanh(v[8 * c8 + r] + small[UtSmem::B1 + j + r]);
-                *reinterpret_cast<float4*>(smem + UtSmem::H1C + ut_off(tid, j, 2 * H)) = make_float4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<float4*>(smem + UtSmem::H1C + ut_off(tid, j + 4, 2 * H)) = make_float4(h[4], h[5], h[6], h[7]);
-                *reinterpret_cast<uint4*>(smem + UtSmem::H1B + ut_off16(tid, j, 2 * H)) = ut_pack8(h);
+                const float4 ba = *reinterpret_cast<const float4*>(small + UtSmem::B1 + j), bb = *reinterpret_cast<const float4*>(small + UtSmem::B1 + j + 4);
+                const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+                for (int r = 0; r < 8; ++r) { h[r] = ut_tanh(v[8 * c8 + r] + bias[r]); dd[r] = fmaf(-h[r], h[r], 1.0f); }
+                *reinterpret_cast<float4*>(smem + UtSmem::H1C + ut_off(row, j, 2 * H)) = make_float4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<float4*>(smem + UtSmem::H1C + ut_off(row, j + 4, 2 * H)) = make_float4(h[4], h[5], h[6], h[7]);
+                *reinterpret_cast<uint4*>(smem + UtSmem::H1B + ut_off16(row, j, 2 * H)) = ut_pack8(h);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) d1p[4 * c8 + r] = ut_pack2(dd[2 * r], dd[2 * r + 1]);
             }
         }
         UT_FENCE_SYNC();
@@ -299,187 +345,211 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- E2: H2 = tanh(z2 + b2) (bf16 copy for the head weight gradient); heads on CUDA cores
-        float mean[A] = {small[UtSmem::B3_PI + 0], small[UtSmem::B3_PI + 1], small[UtSmem::B3_PI + 2], small[UtSmem::B3_PI + 3]};
-        float val = small[UtSmem::B3_VF];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        // ---- E2: H2 = tanh(z2 + b2) (bf16 copy for the head weight gradient); partial head sums over this
+        //      warpgroup's 32 hidden units (policy: 4 action means; value: 1)
+        {
             float v[32];
             ut_ld32(tmem + UT_T2 + lane_base + q * 32, v);
+            float ps[A] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
                 const int j = q * 32 + 8 * c8;
                 float h[8];
 #pragma unroll
-                for (int r = 0; r < 8; ++r) {
-                    h[r] = ut_tanh(v[8 * c8 + r] + small[UtSmem::B2 + j + r]);
-                    if (q < 2) {
+                const float4 ba = *reinterpret_cast<const float4*>(small + UtSmem::B2 + j), bb = *reinterpret_cast<const float4*>(small + UtSmem::B2 + j + 4);
+                const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                        for (int a = 0; a < A; ++a) mean[a] = fmaf(small[UtSmem::W3_PI + a * H + j + r], h[r], mean[a]);
-                    } else {
-                        val = fmaf(small[UtSmem::W3_VF + j + r - H], h[r], val);
+                for (int r = 0; r < 8; ++r) h[r] = ut_tanh(v[8 * c8 + r] + bias[r]);
+                if (q < 2) {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const float4 w = *reinterpret_cast<const float4*>(small + UtSmem::W3_PI + (j + r) * A);
+                        ps[0] = fmaf(w.x, h[r], ps[0]); ps[1] = fmaf(w.y, h[r], ps[1]);
+                        ps[2] = fmaf(w.z, h[r], ps[2]); ps[3] = fmaf(w.w, h[r], ps[3]);
                     }
+                } else {
+                    const float4 wa = *reinterpret_cast<const float4*>(small + UtSmem::W3_VF + j - H), wb = *reinterpret_cast<const float4*>(small + UtSmem::W3_VF + j - H + 4);
+                    ps[0] = fmaf(wa.x, h[0], ps[0]); ps[0] = fmaf(wa.y, h[1], ps[0]); ps[0] = fmaf(wa.z, h[2], ps[0]); ps[0] = fmaf(wa.w, h[3], ps[0]);
+                    ps[0] = fmaf(wb.x, h[4], ps[0]); ps[0] = fmaf(wb.y, h[5], ps[0]); ps[0] = fmaf(wb.z, h[6], ps[0]); ps[0] = fmaf(wb.w, h[7], ps[0]);
                 }
-                *reinterpret_cast<uint4*>(smem + UtSmem::H2B + ut_off16(tid, j, 2 * H)) = ut_pack8(h);
-            }
-        }
-        // ---- losses and their gradients w.r.t. the head outputs (stable_baselines3 PPO.train)
-        float dout[A] = {0.f, 0.f, 0.f, 0.f}, doutv = 0.f;
-        if (live) {
-            const float4 a4 = reinterpret_cast<const float4*>(act)[g];
-            const float av[A] = {a4.x, a4.y, a4.z, a4.w};
-            float z[A], lp = 0.0f;
+                *reinterpret_cast<uint4*>(smem + UtSmem::H2B + ut_off16(row, j, 2 * H)) = ut_pack8(h);
 #pragma unroll
-            for (int a = 0; a < A; ++a) {
-                z[a] = (av[a] - mean[a]) * sigma_inv[a];
-                lp += -0.5f * z[a] * z[a] - logstd[a] - 0.91893853320467274178f;
+                for (int r = 0; r < 4; ++r)
+                    d2p[4 * c8 + r] = ut_pack2(fmaf(-h[2 * r], h[2 * r], 1.0f), fmaf(-h[2 * r + 1], h[2 * r + 1], 1.0f));
             }
-            const float lr = lp - logp_old[g];
-            const float ratio = __expf(lr);
-            const float an = (adv[g] - adv_mean) * adv_istd;
-            const float s1 = an * ratio, s2 = an * fminf(fmaxf(ratio, 1.0f - cfg.clip_range), 1.0f + cfg.clip_range);
-            // d/dlogp of -min(s1, s2): the unclipped branch carries gradient, the clamped one does not
-            const float dlp = (s1 <= s2) ? -an * ratio * cfg.inv_batch : 0.0f;
-#pragma unroll
-            for (int a = 0; a < A; ++a) {
-                dout[a] = dlp * z[a] * sigma_inv[a];
-                acc_db3[a] += dout[a];
-                acc_dls[a] += dlp * (z[a] * z[a] - 1.0f);
-            }
-            const float r = ret[g];
-            doutv = cfg.vf_coef * 2.0f * (val - r) * cfg.inv_batch;
-            acc_db3v += doutv;
-            st_pl += -fminf(s1, s2); st_vl += (r - val) * (r - val);
-            st_kl += (ratio - 1.0f) - lr; st_clip += (fabsf(ratio - 1.0f) > cfg.clip_range) ? 1.0f : 0.0f;
-            st_ratio += ratio; st_n += 1.0f;
+            // XB is dead after M1: its first 8 KB carry the head partials, the next 4 KB the per-row output gradients
+            *reinterpret_cast<float4*>(smem + UtSmem::XB + (q * UT_ROWS + row) * 16) = make_float4(ps[0], ps[1], ps[2], ps[3]);
         }
-        {   // dOut row (bf16): [dmean0..3, dvalue, 1, 0...]; the ones column turns the same MMAs into bias-gradient sums.
+        __syncthreads();
+        // ---- losses and their gradients w.r.t. the head outputs (stable_baselines3 PPO.train), one thread per sample
+        if (q == 0) {
+            const float4 p0 = *reinterpret_cast<const float4*>(smem + UtSmem::XB + (0 * UT_ROWS + row) * 16);
+            const float4 p1 = *reinterpret_cast<const float4*>(smem + UtSmem::XB + (1 * UT_ROWS + row) * 16);
+            const float pv0 = *reinterpret_cast<const float*>(smem + UtSmem::XB + (2 * UT_ROWS + row) * 16);
+            const float pv1 = *reinterpret_cast<const float*>(smem + UtSmem::XB + (3 * UT_ROWS + row) * 16);
+            const float mean[A] = {small[UtSmem::B3_PI + 0] + p0.x + p1.x, small[UtSmem::B3_PI + 1] + p0.y + p1.y,
+                                   small[UtSmem::B3_PI + 2] + p0.z + p1.z, small[UtSmem::B3_PI + 3] + p0.w + p1.w};
+            const float val = small[UtSmem::B3_VF] + pv0 + pv1;
+            float dout[A] = {0.f, 0.f, 0.f, 0.f}, doutv = 0.f;
+            if (live) {
+                const float av[A] = {a4.x, a4.y, a4.z, a4.w};
+                float z[A], sinv[A], lp = 0.0f;
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    const float ls = small[UtSmem::LOGSTD + a];
+                    sinv[a] = __expf(-ls);
+                    z[a] = (av[a] - mean[a]) * sinv[a];
+                    lp += -0.5f * z[a] * z[a] - ls - 0.91893853320467274178f;
+                }
+                const float lr = lp - lpo;
+                const float ratio = __expf(lr);
+                const float an = (advv - adv_mean) * adv_istd;
+                const float s1 = an * ratio, s2 = an * fminf(fmaxf(ratio, 1.0f - cfg.clip_range), 1.0f + cfg.clip_range);
+                // d/dlogp of -min(s1, s2): the unclipped branch carries gradient, the clamped one does not
+                const float dlp = (s1 <= s2) ? -an * ratio * cfg.inv_batch : 0.0f;
+#pragma unroll
+                for (int a = 0; a < A; ++a) {
+                    dout[a] = dlp * z[a] * sinv[a];
+                    acc_db3[a] += dout[a];
+                    acc_dls[a] += dlp * (z[a] * z[a] - 1.0f);
+                }
+                doutv = cfg.vf_coef * 2.0f * (val - retv) * cfg.inv_batch;
+                acc_db3v += doutv;
+                st_pl += -fminf(s1, s2); st_vl += (retv - val) * (retv - val);
+                st_kl += (ratio - 1.0f) - lr; st_clip += (fabsf(ratio - 1.0f) > cfg.clip_range) ? 1.0f : 0.0f;
+                st_ratio += ratio; st_n += 1.0f;
+            }
+            // dOut row (bf16): [dmean0..3, dvalue, 1, 0...]; the ones column turns the same MMAs into bias-gradient sums.
             // The gradients are scaled up before rounding to bf16 so that 1/batch factors do not underflow its range.
             const float sc = cfg.grad_scale;
             float row16[16] = {dout[0] * sc, dout[1] * sc, dout[2] * sc, dout[3] * sc, doutv * sc, live ? 1.0f : 0.0f, 0.f, 0.f,
                                0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            *reinterpret_cast<uint4*>(smem + UtSmem::DO + ut_off16(tid, 0, 16)) = ut_pack8(row16);
-            *reinterpret_cast<uint4*>(smem + UtSmem::DO + ut_off16(tid, 8, 16)) = ut_pack8(row16 + 8);
+            *reinterpret_cast<uint4*>(smem + UtSmem::DO + ut_off16(row, 0, 16)) = ut_pack8(row16);
+            *reinterpret_cast<uint4*>(smem + UtSmem::DO + ut_off16(row, 8, 16)) = ut_pack8(row16 + 8);
+            // fp32 copy (pre-scaled) for the other warpgroups' dZ2
+            *reinterpret_cast<float4*>(smem + UtSmem::XB + 8192 + row * 32) = make_float4(row16[0], row16[1], row16[2], row16[3]);
+            *reinterpret_cast<float*>(smem + UtSmem::XB + 8192 + row * 32 + 16) = row16[4];
         }
         UT_FENCE_SYNC();
-        // ---- M3: head weight gradients  D3 += [H2]^T dOut   (bf16, A and B MN-major; K = 128 samples)
-        if (tid == 0) {
-            ut_gemm<true>(tmem + UT_D3, sb + UtSmem::H2B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16,
-                          UT_ROWS / 16, ut_idesc(1, 16, 1, 1), first);
-            ut_commit(bar);
-        }
-        ut_wait(bar, phase); phase ^= 1u;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- E3: dZ2 = (dOut W3) * tanh'(z2), tanh' recomputed from the fp32 pre-activations still in TMEM;
-        //      written (bf16, scaled) over the H2 copy
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float v[32];
-            ut_ld32(tmem + UT_T2 + lane_base + q * 32, v);
+        // ---- E3: dZ2 = (dOut W3) * tanh'(z2) for this warpgroup's columns (bf16, scaled) into the first half of the
+        //      H1C area (dead after M2) -- the H2 copy stays intact for the head weight gradient
+        {
+            const float4 do4 = *reinterpret_cast<const float4*>(smem + UtSmem::XB + 8192 + row * 32);
+            const float dov = *reinterpret_cast<const float*>(smem + UtSmem::XB + 8192 + row * 32 + 16);
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
                 const int j = q * 32 + 8 * c8;
                 float o[8];
 #pragma unroll
+                float wv[8];
+                if (q >= 2) {
+                    const float4 wa = *reinterpret_cast<const float4*>(small + UtSmem::W3_VF + j - H), wb = *reinterpret_cast<const float4*>(small + UtSmem::W3_VF + j - H + 4);
+                    wv[0] = wa.x; wv[1] = wa.y; wv[2] = wa.z; wv[3] = wa.w; wv[4] = wb.x; wv[5] = wb.y; wv[6] = wb.z; wv[7] = wb.w;
+                }
+#pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const float h = ut_tanh(v[8 * c8 + r] + small[UtSmem::B2 + j + r]);
                     float dh;
                     if (q < 2) {
-                        dh = dout[0] * small[UtSmem::W3_PI + 0 * H + j + r] + dout[1] * small[UtSmem::W3_PI + 1 * H + j + r] +
-                             dout[2] * small[UtSmem::W3_PI + 2 * H + j + r] + dout[3] * small[UtSmem::W3_PI + 3 * H + j + r];
+                        const float4 w = *reinterpret_cast<const float4*>(small + UtSmem::W3_PI + (j + r) * A);
+                        dh = do4.x * w.x + do4.y * w.y + do4.z * w.z + do4.w * w.w;
                     } else {
-                        dh = doutv * small[UtSmem::W3_VF + j + r - H];
+                        dh = dov * wv[r];
                     }
-                    o[r] = dh * (1.0f - h * h) * cfg.grad_scale;
+                    const __nv_bfloat162 dd = *reinterpret_cast<const __nv_bfloat162*>(&d2p[4 * c8 + (r >> 1)]);
+                    o[r] = dh * ((r & 1) ? __high2float(dd) : __low2float(dd));
                 }
-                *reinterpret_cast<uint4*>(smem + UtSmem::H2B + ut_off16(tid, j, 2 * H)) = ut_pack8(o);
+                *reinterpret_cast<uint4*>(smem + UtSmem::DZ2 + ut_off16(row, j, 2 * H)) = ut_pack8(o);
             }
         }
         UT_FENCE_SYNC();
-        // ---- M4: layer-2 weight / bias gradients and the data gradient into layer 1 (bf16)
+        // ---- M3 + M4: head / layer-2 weight and bias gradients and the data gradient into layer 1 (bf16)
         if (tid == 0) {
+            // D3 += [H2]^T dOut   (A and B MN-major; K = 128 samples)
+            ut_gemm<true>(tmem + UT_D3, sb + UtSmem::H2B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16,
+                          UT_ROWS / 16, ut_idesc(1, 16, 1, 1), first);
             // Da += [dZ2]^T H1_pi ; Db += [dZ2]^T H1_vf   (rows 0-63 of Da and 64-127 of Db are the wanted blocks)
-            ut_gemm<true>(tmem + UT_DA, sb + UtSmem::H2B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::H1B, 2 * H * 16, 128, 2 * 2 * H * 16,
+            ut_gemm<true>(tmem + UT_DA, sb + UtSmem::DZ2, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::H1B, 2 * H * 16, 128, 2 * 2 * H * 16,
                           UT_ROWS / 16, ut_idesc(1, H, 1, 1), first);
-            ut_gemm<true>(tmem + UT_DB, sb + UtSmem::H2B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::H1B + 8 * 128, 2 * H * 16, 128,
+            ut_gemm<true>(tmem + UT_DB, sb + UtSmem::DZ2, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::H1B + 8 * 128, 2 * H * 16, 128,
                           2 * 2 * H * 16, UT_ROWS / 16, ut_idesc(1, H, 1, 1), first);
-            ut_gemm<true>(tmem + UT_DB2, sb + UtSmem::H2B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16,
+            ut_gemm<true>(tmem + UT_DB2, sb + UtSmem::DZ2, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16,
                           UT_ROWS / 16, ut_idesc(1, 16, 1, 1), first);
             // dH1 = dZ2 W2: A = the tower's K-major sub-block of the dZ2 buffer, B = W2 (bf16) read MN-major
-            ut_gemm<true>(tmem + UT_T2, sb + UtSmem::H2B, 128, 2 * H * 16, 256, sb + UtSmem::W2B_PI, H * 16, 128, 2 * H * 16, H / 16,
+            ut_gemm<true>(tmem + UT_T2, sb + UtSmem::DZ2, 128, 2 * H * 16, 256, sb + UtSmem::W2B_PI, H * 16, 128, 2 * H * 16, H / 16,
                           ut_idesc(1, H, 0, 1), 0u);
-            ut_gemm<true>(tmem + UT_T2 + H, sb + UtSmem::H2B + 8 * 128, 128, 2 * H * 16, 256, sb + UtSmem::W2B_VF, H * 16, 128, 2 * H * 16,
+            ut_gemm<true>(tmem + UT_T2 + H, sb + UtSmem::DZ2 + 8 * 128, 128, 2 * H * 16, 256, sb + UtSmem::W2B_VF, H * 16, 128, 2 * H * 16,
                           H / 16, ut_idesc(1, H, 0, 1), 0u);
             ut_commit(bar);
         }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- E4: dZ1 = dH1 * tanh'(z1) (z1 still in TMEM), written (bf16, already scaled) over the H1 copy
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float v[32], z1[32];
+        // ---- E4: dZ1 = dH1 * tanh'(z1) (bf16, already scaled) into the second half of the H1C area
+        {
+            float v[32];
             ut_ld32(tmem + UT_T2 + lane_base + q * 32, v);
-            ut_ld32(tmem + UT_T1 + lane_base + q * 32, z1);
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
                 const int j = q * 32 + 8 * c8;
                 float o[8];
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const float h = ut_tanh(z1[8 * c8 + r] + small[UtSmem::B1 + j + r]);
-                    o[r] = v[8 * c8 + r] * (1.0f - h * h);
+                    const __nv_bfloat162 dd = *reinterpret_cast<const __nv_bfloat162*>(&d1p[4 * c8 + (r >> 1)]);
+                    o[r] = v[8 * c8 + r] * ((r & 1) ? __high2float(dd) : __low2float(dd));
                 }
-                *reinterpret_cast<uint4*>(smem + UtSmem::H1B + ut_off16(tid, j, 2 * H)) = ut_pack8(o);
+                *reinterpret_cast<uint4*>(smem + UtSmem::DZ1 + ut_off16(row, j, 2 * H)) = ut_pack8(o);
             }
         }
         UT_FENCE_SYNC();
-        // ---- M5: layer-1 weight / bias gradients (bf16)
+        // ---- M5: layer-1 weight / bias gradients (bf16); not waited for here -- the next tile's first commit (or the
+        //      one after the loop) covers it, and nothing it reads is rewritten before that wait
         if (tid == 0) {
-            ut_gemm<true>(tmem + UT_DW1, sb + UtSmem::H1B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::XBB, DP * 16, 128, 2 * DP * 16,
+            ut_gemm<true>(tmem + UT_DW1, sb + UtSmem::DZ1, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::XBB, DP * 16, 128, 2 * DP * 16,
                           UT_ROWS / 16, ut_idesc(1, DP, 1, 1), first);
-            ut_gemm<true>(tmem + UT_DB1, sb + UtSmem::H1B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16,
+            ut_gemm<true>(tmem + UT_DB1, sb + UtSmem::DZ1, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16,
                           UT_ROWS / 16, ut_idesc(1, 16, 1, 1), first);
-            ut_commit(bar);
         }
-        ut_wait(bar, phase); phase ^= 1u;       // the operand buffers are rewritten by the next tile
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         first = 1u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xcur[i] = xnext[i];
+    }
+    if (first != 0u) {
+        if (tid == 0) ut_commit(bar);
+        ut_wait(bar, phase); phase ^= 1u;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
 
-    // ---- read the accumulated weight gradients out of TMEM into this CTA's partial (thread == output neuron row)
+    // ---- read the accumulated weight gradients out of TMEM into this CTA's partial
+    //      (TMEM lane = output neuron: lanes 0-63 policy tower, 64-127 value tower; warpgroup q takes a column slice)
     float* outp = out_partial + (size_t)blockIdx.x * P;
-    const bool is_pi = tid < H;
-    const int j = is_pi ? tid : tid - H;                 // neuron index inside the tower
+    const bool is_pi = row < H;
+    const int j = is_pi ? row : row - H;                 // neuron index inside the tower
     const int tower_off = is_pi ? 0 : pi_count;
     const int o_w1 = tower_off, o_b1 = o_w1 + H * d, o_w2 = o_b1 + H, o_b2 = o_w2 + H * H, o_w3 = o_b2 + H;
     if (first != 0u) {
-        {   // dW2: rows 0-63 of Da, rows 64-127 of Db
-            const uint32_t src = tmem + (is_pi ? UT_DA : UT_DB) + lane_base;
+        {   // dW2: rows 0-63 of Da, rows 64-127 of Db; 16 columns per warpgroup
+            float v[16];
+            ut_ld16(tmem + (is_pi ? UT_DA : UT_DB) + lane_base + q * 16, v);
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float v[32];
-                ut_ld32(src + half * 32, v);
-#pragma unroll
-                for (int c = 0; c < 32; ++c) outp[o_w2 + j * H + half * 32 + c] = v[c] * cfg.inv_grad_scale;
-            }
+            for (int c = 0; c < 16; ++c) outp[o_w2 + j * H + q * 16 + c] = v[c] * cfg.inv_grad_scale;
         }
-        {   // dW1
-            float v[32];
-            ut_ld32(tmem + UT_DW1 + lane_base, v);
+        if (q < 2) {   // dW1: 16 columns each
+            float v[16];
+            ut_ld16(tmem + UT_DW1 + lane_base + q * 16, v);
 #pragma unroll
-            for (int c = 0; c < 32; ++c) if (c < d) outp[o_w1 + j * d + c] = v[c] * cfg.inv_grad_scale;
-        }
-        {   // head weights, biases
-            float v3[16], vb2[16], vb1[16];
+            for (int c = 0; c < 16; ++c) if (q * 16 + c < d) outp[o_w1 + j * d + q * 16 + c] = v[c] * cfg.inv_grad_scale;
+        } else if (q == 2) {   // head weights
+            float v3[16];
             ut_ld16(tmem + UT_D3 + lane_base, v3);
-            ut_ld16(tmem + UT_DB2 + lane_base, vb2);
-            ut_ld16(tmem + UT_DB1 + lane_base, vb1);
             if (is_pi) {
 #pragma unroll
                 for (int a = 0; a < A; ++a) outp[o_w3 + a * H + j] = v3[a] * cfg.inv_grad_scale;
             } else {
                 outp[o_w3 + j] = v3[4] * cfg.inv_grad_scale;
             }
+        } else {               // hidden biases (ones column)
+            float vb2[16], vb1[16];
+            ut_ld16(tmem + UT_DB2 + lane_base, vb2);
+            ut_ld16(tmem + UT_DB1 + lane_base, vb1);
             outp[o_b2 + j] = vb2[5] * cfg.inv_grad_scale;
             outp[o_b1 + j] = vb1[5] * cfg.inv_grad_scale;
         }
@@ -487,15 +557,17 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         // this CTA had no tile: its partial is all zeros
         for (int k = tid; k < P; k += blockDim.x) outp[k] = 0.0f;
     }
-    // small sums: warp shuffle then shared atomics (24 slots), then thread 0..23 writes them
-    float red[20] = {acc_db3[0], acc_db3[1], acc_db3[2], acc_db3[3], acc_db3v, acc_dls[0], acc_dls[1], acc_dls[2], acc_dls[3],
-                     st_pl, st_vl, st_kl, st_clip, st_ratio, st_n, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // small sums (held by warpgroup 0): warp shuffle then shared atomics (24 slots), then threads 0..23 write them
+    if (q == 0) {
+        float red[15] = {acc_db3[0], acc_db3[1], acc_db3[2], acc_db3[3], acc_db3v, acc_dls[0], acc_dls[1], acc_dls[2], acc_dls[3],
+                         st_pl, st_vl, st_kl, st_clip, st_ratio, st_n};
 #pragma unroll
-    for (int k = 0; k < 15; ++k) {
-        float x = red[k];
+        for (int k = 0; k < 15; ++k) {
+            float x = red[k];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-        if ((tid & 31) == 0) atomicAdd(&small[UtSmem::RED + k], x);
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+            if ((tid & 31) == 0) atomicAdd(&small[UtSmem::RED + k], x);
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -549,56 +621,83 @@ ppo_adv_stats_kernel(const float* __restrict__ adv, const long long* __restrict_
 }
 
 // ------------------------------------------------------------------ partial-gradient reduction: grad[k] = sum_c partial[c][k]
-__global__ void __launch_bounds__(256)
+// block = 64 parameters x 16 slices of the CTA axis: 16 independent load chains per parameter instead of one
+#define RED_KX 64
+#define RED_CY 16
+__global__ void __launch_bounds__(RED_KX * RED_CY)
 ppo_grad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ stats_partial, int ncta, int P,
                        float* __restrict__ grad, float* __restrict__ stats) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < P) {
-        float s = 0.0f;
-        for (int c = 0; c < ncta; ++c) s += partial[(size_t)c * P + k];
-        grad[k] = s;
+    __shared__ float s_part[RED_CY][RED_KX + 1];
+    const int kx = threadIdx.x % RED_KX, cy = threadIdx.x / RED_KX;
+    const int k = blockIdx.x * RED_KX + kx;
+    float s = 0.0f;
+    if (k < P)
+        for (int c = cy; c < ncta; c += RED_CY) s += partial[(size_t)c * P + k];
+    s_part[cy][kx] = s;
+    __syncthreads();
+    if (cy == 0 && k < P) {
+        float t = 0.0f;
+#pragma unroll
+        for (int c = 0; c < RED_CY; ++c) t += s_part[c][kx];          // fixed order: deterministic
+        grad[k] = t;
     }
     if (blockIdx.x == 0 && threadIdx.x < 8 && stats != nullptr) {
-        float s = 0.0f;
-        for (int c = 0; c < ncta; ++c) s += stats_partial[(size_t)c * 8 + threadIdx.x];
-        stats[threadIdx.x] = s;
+        float t = 0.0f;
+        for (int c = 0; c < ncta; ++c) t += stats_partial[(size_t)c * 8 + threadIdx.x];
+        stats[threadIdx.x] = t;
     }
 }
 
 // ------------------------------------------------------------------ clip_grad_norm_ + Adam, one block
-__global__ void __launch_bounds__(1024)
+#define ADAM_THREADS 1024
+#define ADAM_PER 16          // parameters per thread held in registers: P <= 16384
+__global__ void __launch_bounds__(ADAM_THREADS)
 ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, int P,
                 float lr, float beta1, float beta2, float eps, float max_norm, float grad_scale, int* __restrict__ step_ctr,
                 float* __restrict__ norm_out) {
     __shared__ float s_red[32];
     __shared__ float s_coef;
+    // every load of the update is issued before the norm reduction so that the second pass only does arithmetic
+    float g[ADAM_PER], mk[ADAM_PER], vk[ADAM_PER], pk[ADAM_PER];
     float ss = 0.0f;
-    for (int k = threadIdx.x; k < P; k += blockDim.x) { float g = grad[k] * grad_scale; ss = fmaf(g, g, ss); }
+#pragma unroll
+    for (int i = 0; i < ADAM_PER; ++i) {
+        const int k = threadIdx.x + i * ADAM_THREADS;
+        const bool ok = k < P;
+        g[i] = ok ? grad[k] * grad_scale : 0.0f;
+        mk[i] = ok ? m[k] : 0.0f; vk[i] = ok ? v[k] : 0.0f; pk[i] = ok ? params[k] : 0.0f;
+        ss = fmaf(g[i], g[i], ss);
+    }
+    const int t = step_ctr[0] + 1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
     __syncthreads();
     if (threadIdx.x < 32) {
-        float x = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : 0.0f;
+        float x = s_red[threadIdx.x];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (threadIdx.x == 0) {
             const float norm = sqrtf(x);
             s_coef = fminf(1.0f, max_norm / (norm + 1e-6f));          // torch.nn.utils.clip_grad_norm_
             if (norm_out != nullptr) norm_out[0] = norm;
-            step_ctr[0] += 1;
+            step_ctr[0] = t;
         }
     }
     __syncthreads();
-    const float coef = s_coef * grad_scale;
-    const int t = step_ctr[0];
+    const float coef = s_coef;
     const float bc1 = 1.0f - powf(beta1, (float)t), bc2 = 1.0f - powf(beta2, (float)t);
-    for (int k = threadIdx.x; k < P; k += blockDim.x) {
-        const float g = grad[k] * coef;
-        const float mk = beta1 * m[k] + (1.0f - beta1) * g;
-        const float vk = beta2 * v[k] + (1.0f - beta2) * g * g;
-        m[k] = mk; v[k] = vk;
-        params[k] -= lr * (mk / bc1) / (sqrtf(vk / bc2) + eps);        // torch.optim.Adam (no amsgrad, no weight decay)
+    const float inv_bc1 = 1.0f / bc1, inv_bc2 = 1.0f / bc2;
+#pragma unroll
+    for (int i = 0; i < ADAM_PER; ++i) {
+        const int k = threadIdx.x + i * ADAM_THREADS;
+        if (k < P) {
+            const float gg = g[i] * coef;
+            const float m1 = beta1 * mk[i] + (1.0f - beta1) * gg;
+            const float v1 = beta2 * vk[i] + (1.0f - beta2) * gg * gg;
+            m[k] = m1; v[k] = v1;
+            params[k] = pk[i] - lr * (m1 * inv_bc1) / (sqrtf(v1 * inv_bc2) + eps);   // torch.optim.Adam (no amsgrad / decay)
+        }
     }
 }
 
@@ -627,22 +726,23 @@ cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, co
     if (grid <= 0) return cudaErrorUnknown;
     const int H_ = PPO_H, A_ = PPO_A;
     const int P = (H_ * d + H_ + H_ * H_ + H_ + A_ * H_ + A_) + (H_ * d + H_ + H_ * H_ + H_ + H_ + 1) + A_;
-    int sblocks = (batch + 256 * 8 - 1) / (256 * 8);
-    if (sblocks > 256) sblocks = 256;
+    int sblocks = (batch + 255) / 256;            // one gathered element per thread up to 4 blocks per SM
+    if (sblocks > 592) sblocks = 592;
     ppo_adv_stats_kernel<<<sblocks, 256, 0, st>>>(adv, idx, batch, scratch, adv_stats);
     // per-sample head gradients carry a 1/batch factor; rescale them to O(1) before the bf16 rounding of the backward
     // operands (a power of two, so the scaling itself is exact) and undo it when the accumulators are read out
     float gs = 1.0f;
     while (gs < (float)batch && gs < 1048576.0f) gs *= 2.0f;
     PpoLossCfg cfg{clip_range, ent_coef, vf_coef, 1.0f / (float)batch, gs, 1.0f / gs};
-    ppo_grad_tc_kernel<<<grid, UT_ROWS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, adv_stats, cfg,
+    ppo_grad_tc_kernel<<<grid, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, adv_stats, cfg,
                                                              partial, stats_partial, P);
-    ppo_grad_reduce_kernel<<<(P + 255) / 256, 256, 0, st>>>(partial, stats_partial, grid, P, grad, stats);
+    ppo_grad_reduce_kernel<<<(P + RED_KX - 1) / RED_KX, RED_KX * RED_CY, 0, st>>>(partial, stats_partial, grid, P, grad, stats);
     return cudaGetLastError();
 }
 
 cudaError_t ppok_adam(float* params, const float* grad, float* m, float* v, int P, float lr, float beta1, float beta2, float eps,
                       float max_norm, float grad_scale, int* step_ctr, float* norm_out, cudaStream_t st) {
-    ppo_adam_kernel<<<1, 1024, 0, st>>>(params, grad, m, v, P, lr, beta1, beta2, eps, max_norm, grad_scale, step_ctr, norm_out);
+    if (P > ADAM_THREADS * ADAM_PER) return cudaErrorInvalidValue;
+    ppo_adam_kernel<<<1, ADAM_THREADS, 0, st>>>(params, grad, m, v, P, lr, beta1, beta2, eps, max_norm, grad_scale, step_ctr, norm_out);
     return cudaGetLastError();
 }
