@@ -42,19 +42,22 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, 
 // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 64, M = 128
 #define TC_IDESC ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(H >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24))
 
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
+#define TC_IDESC128 ((1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(2 * H >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24))
+
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-        :: "r"(tmem_d), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate) : "memory");
+        :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 
 // D[128 x 64] (TMEM) = A[128 x K] (smem) * B[64 x K]^T (smem), K in steps of 8 (32 bytes of tf32 per instruction)
-__device__ __forceinline__ void tc_gemm(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, int K) {
+__device__ __forceinline__ void tc_gemm(uint32_t tmem_d, uint32_t a_base, uint32_t b_base, int K, uint32_t idesc = TC_IDESC) {
+    uint64_t da = tc_desc(a_base, 128, K * 32), db = tc_desc(b_base, 128, K * 32);
+#pragma unroll 1
     for (int k8 = 0; k8 < K / 8; ++k8) {
-        uint64_t da = tc_desc(a_base + k8 * 256, 128, K * 32);
-        uint64_t db = tc_desc(b_base + k8 * 256, 128, K * 32);
-        tc_mma(tmem_d, da, db, k8 > 0 ? 1u : 0u);
+        tc_mma(tmem_d, da, db, idesc, k8 > 0 ? 1u : 0u);
+        da += 16; db += 16;            // 256 bytes further along K: only the start-address field changes
     }
 }
 
@@ -127,7 +130,8 @@ struct TcSmem {
     static constexpr int B1_PI = 0, B1_VF = 64, B2_PI = 128, B2_VF = 192, W3_PI = 256, W3_VF = 512, B3_PI = 576,
                          B3_VF = 580, LOGSTD = 584, MEAN = 592, ISTD = 624, BAR = 656 /* 8-byte aligned */, TPTR = 660,
                          NSMALL = 664;
-    static constexpr int TOTAL = SMALL + NSMALL * 4;
+    static constexpr int HP = SMALL + NSMALL * 4;          // head partial sums [4 warpgroups][128 rows] float4, 8 KB
+    static constexpr int TOTAL = HP + 4 * TC_ROWS * 16;
 };
 
 __device__ void tc_load_weight(char* smem, int off, const float* __restrict__ g, int K, int d) {
@@ -261,8 +265,7 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            tc_gemm(t_pi, s_base + TcSmem::AX, s_base + TcSmem::W1_PI, DP);
-            tc_gemm(t_vf, s_base + TcSmem::AX, s_base + TcSmem::W1_VF, DP);
+            tc_gemm(t_pi, s_base + TcSmem::AX, s_base + TcSmem::W1_PI, DP, TC_IDESC128);   // W1_pi|W1_vf: one N = 128 B operand
             tc_commit(bar);
         }
         // the next tile's observations are requested now and land while this tile is processed
@@ -309,7 +312,7 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
         }
         tc_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- layer-2 epilogue: partial head sums over this warpgroup's 32 hidden units (AX is dead: reuse it)
+        // ---- layer-2 epilogue: partial head sums over this warpgroup's 32 hidden units
         {
             float v[32];
             tc_ld32(tcol + lane_base, v);
@@ -332,16 +335,16 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
                     ps[0] = fmaf(w.z, h2[2], ps[0]); ps[0] = fmaf(w.w, h2[3], ps[0]);
                 }
             }
-            *reinterpret_cast<float4*>(smem + TcSmem::AX + (q * TC_ROWS + lrow) * 16) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+            *reinterpret_cast<float4*>(smem + TcSmem::HP + (q * TC_ROWS + lrow) * 16) = make_float4(ps[0], ps[1], ps[2], ps[3]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         // ---- heads, diagonal-Gaussian sample and log-probability: one thread per env
         if (q == 0 && live) {
-            const float4 p0 = *reinterpret_cast<const float4*>(smem + TcSmem::AX + (0 * TC_ROWS + lrow) * 16);
-            const float4 p1 = *reinterpret_cast<const float4*>(smem + TcSmem::AX + (1 * TC_ROWS + lrow) * 16);
-            const float pv0 = *reinterpret_cast<const float*>(smem + TcSmem::AX + (2 * TC_ROWS + lrow) * 16);
-            const float pv1 = *reinterpret_cast<const float*>(smem + TcSmem::AX + (3 * TC_ROWS + lrow) * 16);
+            const float4 p0 = *reinterpret_cast<const float4*>(smem + TcSmem::HP + (0 * TC_ROWS + lrow) * 16);
+            const float4 p1 = *reinterpret_cast<const float4*>(smem + TcSmem::HP + (1 * TC_ROWS + lrow) * 16);
+            const float pv0 = *reinterpret_cast<const float*>(smem + TcSmem::HP + (2 * TC_ROWS + lrow) * 16);
+            const float pv1 = *reinterpret_cast<const float*>(smem + TcSmem::HP + (3 * TC_ROWS + lrow) * 16);
             const float mean[A] = {small[TcSmem::B3_PI + 0] + p0.x + p1.x, small[TcSmem::B3_PI + 1] + p0.y + p1.y,
                                    small[TcSmem::B3_PI + 2] + p0.z + p1.z, small[TcSmem::B3_PI + 3] + p0.w + p1.w};
             value[row] = small[TcSmem::B3_VF] + pv0 + pv1;
@@ -357,9 +360,10 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
             if (act_raw != nullptr) reinterpret_cast<float4*>(act_raw)[row] = make_float4(av[0], av[1], av[2], av[3]);
             if (logp != nullptr) logp[row] = lp;
         }
-        // the next tile overwrites AX (head partials) / AH and the accumulators
-        __syncthreads();
+        // no trailing barrier: the partials live outside the operand buffers, and the two block-wide syncs of the next
+        // tile separate these reads from the next writes
     }
+    __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)TC_TMEM_COLS) : "memory");
 }

@@ -78,14 +78,18 @@ __device__ __forceinline__ void ut_mma(uint32_t tmem_d, uint64_t da, uint64_t db
 }
 
 // D[128 x N] (+)= A B^T over `ksteps` instructions (K = 8 tf32 / 16 bf16 each); per instruction the operand start
-// addresses advance by a_step / b_step bytes (256 for a K-major operand; LBO resp. 2*LBO for an MN-major one)
-template <bool BF16>
+// addresses advance by a_step / b_step bytes (256 for a K-major operand; LBO resp. 2*LBO for an MN-major one).
+// The descriptors are built once per GEMM; a k step only bumps the 14-bit start-address field (no carry: every
+// operand lies below 256 KB).
+template <bool BF16, int KSTEPS>
 __device__ __forceinline__ void ut_gemm(uint32_t tmem_d, uint32_t a_addr, uint32_t a_lbo, uint32_t a_sbo, uint32_t a_step,
-                                        uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step, int ksteps,
+                                        uint32_t b_addr, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_step,
                                         uint32_t idesc, uint32_t accumulate_first) {
-    for (int k = 0; k < ksteps; ++k)
-        ut_mma<BF16>(tmem_d, ut_desc(a_addr + k * a_step, a_lbo, a_sbo), ut_desc(b_addr + k * b_step, b_lbo, b_sbo), idesc,
-                     k > 0 ? 1u : accumulate_first);
+    const uint64_t da = ut_desc(a_addr, a_lbo, a_sbo), db = ut_desc(b_addr, b_lbo, b_sbo);
+    const uint64_t ia = a_step >> 4, ib = b_step >> 4;
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k)      // unrolled: the descriptors of all k steps are independent adds
+        ut_mma<BF16>(tmem_d, da + k * ia, db + k * ib, idesc, k > 0 ? 1u : accumulate_first);
 }
 
 __device__ __forceinline__ void ut_commit(uint32_t bar) {
@@ -190,18 +194,32 @@ __device__ void ut_load_weight(char* smem, int off, const float* __restrict__ g,
 
 struct PpoLossCfg { float clip_range, ent_coef, vf_coef, inv_batch, grad_scale, inv_grad_scale; };
 
-// gather 8 consecutive observation columns [8*part, 8*part+8) of rollout row g (zero beyond d / for dead rows)
-__device__ __forceinline__ void ut_gather8(const float* __restrict__ obs, int d, long long g, bool live, int part, float (&x)[8]) {
-    if ((d & 3) == 0) {                                   // rows are 16-byte aligned: two vector loads
-        const float4* src = reinterpret_cast<const float4*>(obs + (size_t)g * d);
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-        if (live && 8 * part < d) a = src[2 * part];
-        if (live && 8 * part + 4 < d) b = src[2 * part + 1];
-        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+// Asynchronously gather 8 consecutive observation columns [8*part, 8*part+8) of rollout row g straight into the
+// fp32 layer-1 A operand (cp.async with zero fill for padding columns and dead rows): the random 112-byte row reads
+// cost DRAM latency, and unlike register loads they cannot stall the issuing warp.
+__device__ __forceinline__ void ut_gather_async(char* smem, const float* __restrict__ obs, int d, long long g, bool live,
+                                                int grow, int part) {
+    const float* src = obs + (size_t)g * d;
+    if ((d & 3) == 0) {                                   // rows are 16-byte aligned: two 16-byte copies
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = 8 * part + 4 * h;
+            const uint32_t dst = ut_smem_u32(smem + UtSmem::XB + ut_off(grow, k, DP));
+            const bool ok = live && k < d;
+            const float* sp = ok ? src + k : obs;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(sp), "r"(ok ? 16 : 0) : "memory");
+        }
     } else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const int k = 8 * part + i; x[i] = (live && k < d) ? obs[(size_t)g * d + k] : 0.0f; }
+        for (int i = 0; i < 8; ++i) {
+            const int k = 8 * part + i;
+            const uint32_t dst = ut_smem_u32(smem + UtSmem::XB + ut_off(grow, k, DP));
+            const bool ok = live && k < d;
+            const float* sp = ok ? src + k : obs;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(sp), "r"(ok ? 4 : 0) : "memory");
+        }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // out_partial: [gridDim.x][P] gradient partial sums; out_stats: [gridDim.x][8] (pi loss, v loss, approx kl, clip
@@ -272,47 +290,62 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
 
     const int ntiles = (batch + UT_ROWS - 1) / UT_ROWS;
     uint32_t first = 0;        // 0 on the first tile of this CTA: weight-gradient accumulators start from zero
-    float xcur[8];             // this thread's 8 gathered observation columns of the current tile (prefetched)
+    // Row indices run one tile ahead of the rows they address, so that neither the observation gather nor the
+    // loss-input gather ever waits for an index: g_loss = this tile's sample, g_gat = next tile's gather row.
+    long long g_loss = 0, g_gat = 0;
     if ((int)blockIdx.x < ntiles) {
         const int sr = blockIdx.x * UT_ROWS + grow;
         const bool lv = sr < batch;
-        ut_gather8(obs, d, lv ? idx[sr] : 0, lv, gpart, xcur);
+        ut_gather_async(smem, obs, d, lv ? idx[sr] : 0, lv, grow, gpart);
+        const int sl = blockIdx.x * UT_ROWS + row;
+        g_loss = sl < batch ? idx[sl] : 0;
+        const int sn = (blockIdx.x + gridDim.x) * UT_ROWS + grow;
+        g_gat = sn < batch ? idx[sn] : 0;
     }
+    uint32_t m5_pending = 0;   // the previous tile's layer-1 weight-gradient MMAs are issued together with this tile's M1
+    uint32_t m5_acc = 0;
+    // M5: layer-1 weight / bias gradients (bf16): DW1 += [dZ1]^T X ; DB1 += [dZ1]^T dOut|1
+#define UT_ISSUE_M5()                                                                                                   \
+    do {                                                                                                                \
+        ut_gemm<true, UT_ROWS / 16>(tmem + UT_DW1, sb + UtSmem::DZ1, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::XBB,  \
+                                    DP * 16, 128, 2 * DP * 16, ut_idesc(1, DP, 1, 1), m5_acc);                          \
+        ut_gemm<true, UT_ROWS / 16>(tmem + UT_DB1, sb + UtSmem::DZ1, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO,   \
+                                    16 * 16, 128, 2 * 16 * 16, ut_idesc(1, 16, 1, 1), m5_acc);                          \
+    } while (0)
+
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // ---- S0: the gathered (already normalised) observations become the fp32 A operand of layer 1
-        *reinterpret_cast<float4*>(smem + UtSmem::XB + ut_off(grow, 8 * gpart, DP)) = make_float4(xcur[0], xcur[1], xcur[2], xcur[3]);
-        *reinterpret_cast<float4*>(smem + UtSmem::XB + ut_off(grow, 8 * gpart + 4, DP)) = make_float4(xcur[4], xcur[5], xcur[6], xcur[7]);
-        UT_FENCE_SYNC();
-        // ---- M1: forward layer 1, both towers (tf32).  The commit also covers the previous tile's M5.
+        // ---- S0: the gathered (already normalised) observations are the fp32 A operand of layer 1: wait for this
+        //      thread's async copies (issued one tile ago), then make them visible block-wide
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        UT_FENCE_SYNC();       // also publishes the previous tile's dZ1
+        // ---- M5 of the previous tile, then M1: forward layer 1, both towers in one N = 128 GEMM (W1_pi and W1_vf are
+        //      adjacent and form one [128 x 32] K-major B operand).  One commit covers both.
         if (tid == 0) {
-            ut_gemm<false>(tmem + UT_T1, sb + UtSmem::XB, 128, DP * 32, 256, sb + UtSmem::W1_PI, 128, DP * 32, 256, DP / 8,
-                           ut_idesc(2, H, 0, 0), 0u);
-            ut_gemm<false>(tmem + UT_T1 + H, sb + UtSmem::XB, 128, DP * 32, 256, sb + UtSmem::W1_VF, 128, DP * 32, 256, DP / 8,
-                           ut_idesc(2, H, 0, 0), 0u);
+            if (m5_pending) UT_ISSUE_M5();
+            ut_gemm<false, DP / 8>(tmem + UT_T1, sb + UtSmem::XB, 128, DP * 32, 256, sb + UtSmem::W1_PI, 128, DP * 32, 256,
+                           ut_idesc(2, 2 * H, 0, 0), 0u);
             ut_commit(bar);
         }
-        // loss inputs of this thread's sample (warpgroup 0), requested now and consumed after layer 2
+        m5_acc = m5_pending;
+        // loss inputs of this thread's sample, requested now and consumed after layer 2 (every warpgroup evaluates the
+        // loss of its row redundantly: cheaper than a block-wide hand-off of the output gradients)
         const int srow = tile * UT_ROWS + row;
         const bool live = srow < batch;
         float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
         float lpo = 0.f, advv = 0.f, retv = 0.f;
-        if (q == 0 && live) {
-            const long long g = idx[srow];
-            a4 = reinterpret_cast<const float4*>(act)[g];
-            lpo = logp_old[g]; advv = adv[g]; retv = ret[g];
-        }
-        // prefetch the next tile's observation slice; it lands while this tile is being processed
-        float xnext[8];
-        {
-            const int nt = tile + gridDim.x;
-            const int sr = nt * UT_ROWS + grow;
-            const bool lv = nt < ntiles && sr < batch;
-            ut_gather8(obs, d, lv ? idx[sr] : 0, lv, gpart, xnext);
+        if (live) {
+            a4 = reinterpret_cast<const float4*>(act)[g_loss];
+            lpo = logp_old[g_loss]; advv = adv[g_loss]; retv = ret[g_loss];
         }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // bf16 copy of X: B operand of the layer-1 weight gradient (the previous tile's M5 has drained by now)
-        *reinterpret_cast<uint4*>(smem + UtSmem::XBB + ut_off16(grow, 8 * gpart, DP)) = ut_pack8(xcur);
+        {
+            const float4 xa = *reinterpret_cast<const float4*>(smem + UtSmem::XB + ut_off(grow, 8 * gpart, DP));
+            const float4 xb = *reinterpret_cast<const float4*>(smem + UtSmem::XB + ut_off(grow, 8 * gpart + 4, DP));
+            const float x8[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            *reinterpret_cast<uint4*>(smem + UtSmem::XBB + ut_off16(grow, 8 * gpart, DP)) = ut_pack8(x8);
+        }
         // ---- E1: H1 = tanh(z1 + b1): fp32 for the forward, bf16 for the weight gradient of layer 2; keep 1 - H1^2
         uint32_t d1p[16], d2p[16];
         {
@@ -322,7 +355,6 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
             for (int c8 = 0; c8 < 4; ++c8) {
                 const int j = q * 32 + 8 * c8;
                 float h[8], dd[8];
-#pragma unroll
                 const float4 ba = *reinterpret_cast<const float4*>(small + UtSmem::B1 + j), bb = *reinterpret_cast<const float4*>(small + UtSmem::B1 + j + 4);
                 const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
@@ -337,9 +369,9 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         UT_FENCE_SYNC();
         // ---- M2: forward layer 2 (A = the tower's 64-column sub-block of H1C)
         if (tid == 0) {
-            ut_gemm<false>(tmem + UT_T2, sb + UtSmem::H1C, 128, 2 * H * 32, 256, sb + UtSmem::W2_PI, 128, H * 32, 256, H / 8,
+            ut_gemm<false, H / 8>(tmem + UT_T2, sb + UtSmem::H1C, 128, 2 * H * 32, 256, sb + UtSmem::W2_PI, 128, H * 32, 256,
                            ut_idesc(2, H, 0, 0), 0u);
-            ut_gemm<false>(tmem + UT_T2 + H, sb + UtSmem::H1C + 16 * 128, 128, 2 * H * 32, 256, sb + UtSmem::W2_VF, 128, H * 32, 256, H / 8,
+            ut_gemm<false, H / 8>(tmem + UT_T2 + H, sb + UtSmem::H1C + 16 * 128, 128, 2 * H * 32, 256, sb + UtSmem::W2_VF, 128, H * 32, 256,
                            ut_idesc(2, H, 0, 0), 0u);
             ut_commit(bar);
         }
@@ -355,7 +387,6 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
             for (int c8 = 0; c8 < 4; ++c8) {
                 const int j = q * 32 + 8 * c8;
                 float h[8];
-#pragma unroll
                 const float4 ba = *reinterpret_cast<const float4*>(small + UtSmem::B2 + j), bb = *reinterpret_cast<const float4*>(small + UtSmem::B2 + j + 4);
                 const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
@@ -377,12 +408,13 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
                 for (int r = 0; r < 4; ++r)
                     d2p[4 * c8 + r] = ut_pack2(fmaf(-h[2 * r], h[2 * r], 1.0f), fmaf(-h[2 * r + 1], h[2 * r + 1], 1.0f));
             }
-            // XB is dead after M1: its first 8 KB carry the head partials, the next 4 KB the per-row output gradients
+            // XB is dead after M1: its first 8 KB carry the head partials of the four warpgroups
             *reinterpret_cast<float4*>(smem + UtSmem::XB + (q * UT_ROWS + row) * 16) = make_float4(ps[0], ps[1], ps[2], ps[3]);
         }
         __syncthreads();
-        // ---- losses and their gradients w.r.t. the head outputs (stable_baselines3 PPO.train), one thread per sample
-        if (q == 0) {
+        // ---- losses and their gradients w.r.t. the head outputs (stable_baselines3 PPO.train)
+        float dout[A] = {0.f, 0.f, 0.f, 0.f}, doutv = 0.f;     // pre-scaled by grad_scale
+        {
             const float4 p0 = *reinterpret_cast<const float4*>(smem + UtSmem::XB + (0 * UT_ROWS + row) * 16);
             const float4 p1 = *reinterpret_cast<const float4*>(smem + UtSmem::XB + (1 * UT_ROWS + row) * 16);
             const float pv0 = *reinterpret_cast<const float*>(smem + UtSmem::XB + (2 * UT_ROWS + row) * 16);
@@ -390,7 +422,6 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
             const float mean[A] = {small[UtSmem::B3_PI + 0] + p0.x + p1.x, small[UtSmem::B3_PI + 1] + p0.y + p1.y,
                                    small[UtSmem::B3_PI + 2] + p0.z + p1.z, small[UtSmem::B3_PI + 3] + p0.w + p1.w};
             const float val = small[UtSmem::B3_VF] + pv0 + pv1;
-            float dout[A] = {0.f, 0.f, 0.f, 0.f}, doutv = 0.f;
             if (live) {
                 const float av[A] = {a4.x, a4.y, a4.z, a4.w};
                 float z[A], sinv[A], lp = 0.0f;
@@ -407,40 +438,37 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
                 const float s1 = an * ratio, s2 = an * fminf(fmaxf(ratio, 1.0f - cfg.clip_range), 1.0f + cfg.clip_range);
                 // d/dlogp of -min(s1, s2): the unclipped branch carries gradient, the clamped one does not
                 const float dlp = (s1 <= s2) ? -an * ratio * cfg.inv_batch : 0.0f;
+                const float dv = cfg.vf_coef * 2.0f * (val - retv) * cfg.inv_batch;
 #pragma unroll
-                for (int a = 0; a < A; ++a) {
-                    dout[a] = dlp * z[a] * sinv[a];
-                    acc_db3[a] += dout[a];
-                    acc_dls[a] += dlp * (z[a] * z[a] - 1.0f);
+                for (int a = 0; a < A; ++a) dout[a] = dlp * z[a] * sinv[a];
+                if (q == 0) {     // sums are kept once per sample
+#pragma unroll
+                    for (int a = 0; a < A; ++a) { acc_db3[a] += dout[a]; acc_dls[a] += dlp * (z[a] * z[a] - 1.0f); }
+                    acc_db3v += dv;
+                    st_pl += -fminf(s1, s2); st_vl += (retv - val) * (retv - val);
+                    st_kl += (ratio - 1.0f) - lr; st_clip += (fabsf(ratio - 1.0f) > cfg.clip_range) ? 1.0f : 0.0f;
+                    st_ratio += ratio; st_n += 1.0f;
                 }
-                doutv = cfg.vf_coef * 2.0f * (val - retv) * cfg.inv_batch;
-                acc_db3v += doutv;
-                st_pl += -fminf(s1, s2); st_vl += (retv - val) * (retv - val);
-                st_kl += (ratio - 1.0f) - lr; st_clip += (fabsf(ratio - 1.0f) > cfg.clip_range) ? 1.0f : 0.0f;
-                st_ratio += ratio; st_n += 1.0f;
+                // scaled up before rounding to bf16 so that 1/batch factors do not underflow its range
+#pragma unroll
+                for (int a = 0; a < A; ++a) dout[a] *= cfg.grad_scale;
+                doutv = dv * cfg.grad_scale;
             }
-            // dOut row (bf16): [dmean0..3, dvalue, 1, 0...]; the ones column turns the same MMAs into bias-gradient sums.
-            // The gradients are scaled up before rounding to bf16 so that 1/batch factors do not underflow its range.
-            const float sc = cfg.grad_scale;
-            float row16[16] = {dout[0] * sc, dout[1] * sc, dout[2] * sc, dout[3] * sc, doutv * sc, live ? 1.0f : 0.0f, 0.f, 0.f,
-                               0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            *reinterpret_cast<uint4*>(smem + UtSmem::DO + ut_off16(row, 0, 16)) = ut_pack8(row16);
-            *reinterpret_cast<uint4*>(smem + UtSmem::DO + ut_off16(row, 8, 16)) = ut_pack8(row16 + 8);
-            // fp32 copy (pre-scaled) for the other warpgroups' dZ2
-            *reinterpret_cast<float4*>(smem + UtSmem::XB + 8192 + row * 32) = make_float4(row16[0], row16[1], row16[2], row16[3]);
-            *reinterpret_cast<float*>(smem + UtSmem::XB + 8192 + row * 32 + 16) = row16[4];
+            if (q == 0) {
+                // dOut row (bf16): [dmean0..3, dvalue, 1, 0...]; the ones column turns the same MMAs into bias-gradient sums
+                float row16[16] = {dout[0], dout[1], dout[2], dout[3], doutv, live ? 1.0f : 0.0f, 0.f, 0.f,
+                                   0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                *reinterpret_cast<uint4*>(smem + UtSmem::DO + ut_off16(row, 0, 16)) = ut_pack8(row16);
+                *reinterpret_cast<uint4*>(smem + UtSmem::DO + ut_off16(row, 8, 16)) = ut_pack8(row16 + 8);
+            }
         }
-        UT_FENCE_SYNC();
         // ---- E3: dZ2 = (dOut W3) * tanh'(z2) for this warpgroup's columns (bf16, scaled) into the first half of the
         //      H1C area (dead after M2) -- the H2 copy stays intact for the head weight gradient
         {
-            const float4 do4 = *reinterpret_cast<const float4*>(smem + UtSmem::XB + 8192 + row * 32);
-            const float dov = *reinterpret_cast<const float*>(smem + UtSmem::XB + 8192 + row * 32 + 16);
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
                 const int j = q * 32 + 8 * c8;
                 float o[8];
-#pragma unroll
                 float wv[8];
                 if (q >= 2) {
                     const float4 wa = *reinterpret_cast<const float4*>(small + UtSmem::W3_VF + j - H), wb = *reinterpret_cast<const float4*>(small + UtSmem::W3_VF + j - H + 4);
@@ -451,9 +479,9 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
                     float dh;
                     if (q < 2) {
                         const float4 w = *reinterpret_cast<const float4*>(small + UtSmem::W3_PI + (j + r) * A);
-                        dh = do4.x * w.x + do4.y * w.y + do4.z * w.z + do4.w * w.w;
+                        dh = dout[0] * w.x + dout[1] * w.y + dout[2] * w.z + dout[3] * w.w;
                     } else {
-                        dh = dov * wv[r];
+                        dh = doutv * wv[r];
                     }
                     const __nv_bfloat162 dd = *reinterpret_cast<const __nv_bfloat162*>(&d2p[4 * c8 + (r >> 1)]);
                     o[r] = dh * ((r & 1) ? __high2float(dd) : __low2float(dd));
@@ -462,28 +490,35 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
             }
         }
         UT_FENCE_SYNC();
+        // XB (layer-1 operand, then head partials) is free from here on: start the next tile's observation gather, and
+        // fetch the indices for the iteration after it
+        {
+            const int nt = tile + gridDim.x;
+            const int sr = nt * UT_ROWS + grow;
+            ut_gather_async(smem, obs, d, g_gat, nt < ntiles && sr < batch, grow, gpart);
+            const int sl = nt * UT_ROWS + row;
+            g_loss = (nt < ntiles && sl < batch) ? idx[sl] : 0;
+            const int sn = (nt + gridDim.x) * UT_ROWS + grow;
+            g_gat = sn < batch ? idx[sn] : 0;
+        }
         // ---- M3 + M4: head / layer-2 weight and bias gradients and the data gradient into layer 1 (bf16)
         if (tid == 0) {
             // D3 += [H2]^T dOut   (A and B MN-major; K = 128 samples)
-            ut_gemm<true>(tmem + UT_D3, sb + UtSmem::H2B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16,
-                          UT_ROWS / 16, ut_idesc(1, 16, 1, 1), first);
-            // Da += [dZ2]^T H1_pi ; Db += [dZ2]^T H1_vf   (rows 0-63 of Da and 64-127 of Db are the wanted blocks)
-            ut_gemm<true>(tmem + UT_DA, sb + UtSmem::DZ2, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::H1B, 2 * H * 16, 128, 2 * 2 * H * 16,
-                          UT_ROWS / 16, ut_idesc(1, H, 1, 1), first);
-            ut_gemm<true>(tmem + UT_DB, sb + UtSmem::DZ2, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::H1B + 8 * 128, 2 * H * 16, 128,
-                          2 * 2 * H * 16, UT_ROWS / 16, ut_idesc(1, H, 1, 1), first);
-            ut_gemm<true>(tmem + UT_DB2, sb + UtSmem::DZ2, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16,
-                          UT_ROWS / 16, ut_idesc(1, 16, 1, 1), first);
+            ut_gemm<true, UT_ROWS / 16>(tmem + UT_D3, sb + UtSmem::H2B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16, ut_idesc(1, 16, 1, 1), first);
+            // [Da | Db] += [dZ2]^T [H1_pi | H1_vf] as one N = 128 GEMM: rows 0-63 x cols 0-63 = dW2_pi,
+            // rows 64-127 x cols 64-127 = dW2_vf (the cross-tower blocks are computed and ignored)
+            ut_gemm<true, UT_ROWS / 16>(tmem + UT_DA, sb + UtSmem::DZ2, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::H1B, 2 * H * 16, 128, 2 * 2 * H * 16, ut_idesc(1, 2 * H, 1, 1), first);
+            ut_gemm<true, UT_ROWS / 16>(tmem + UT_DB2, sb + UtSmem::DZ2, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16, ut_idesc(1, 16, 1, 1), first);
             // dH1 = dZ2 W2: A = the tower's K-major sub-block of the dZ2 buffer, B = W2 (bf16) read MN-major
-            ut_gemm<true>(tmem + UT_T2, sb + UtSmem::DZ2, 128, 2 * H * 16, 256, sb + UtSmem::W2B_PI, H * 16, 128, 2 * H * 16, H / 16,
+            ut_gemm<true, H / 16>(tmem + UT_T2, sb + UtSmem::DZ2, 128, 2 * H * 16, 256, sb + UtSmem::W2B_PI, H * 16, 128, 2 * H * 16,
                           ut_idesc(1, H, 0, 1), 0u);
-            ut_gemm<true>(tmem + UT_T2 + H, sb + UtSmem::DZ2 + 8 * 128, 128, 2 * H * 16, 256, sb + UtSmem::W2B_VF, H * 16, 128, 2 * H * 16,
-                          H / 16, ut_idesc(1, H, 0, 1), 0u);
+            ut_gemm<true, H / 16>(tmem + UT_T2 + H, sb + UtSmem::DZ2 + 8 * 128, 128, 2 * H * 16, 256, sb + UtSmem::W2B_VF, H * 16, 128, 2 * H * 16, ut_idesc(1, H, 0, 1), 0u);
             ut_commit(bar);
         }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- E4: dZ1 = dH1 * tanh'(z1) (bf16, already scaled) into the second half of the H1C area
+        // ---- E4: dZ1 = dH1 * tanh'(z1) (bf16, already scaled) into the second half of the H1C area; its MMAs (M5)
+        //      go out with the next tile's M1, after the block-wide sync that follows the next S0
         {
             float v[32];
             ut_ld32(tmem + UT_T2 + lane_base + q * 32, v);
@@ -499,24 +534,17 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
                 *reinterpret_cast<uint4*>(smem + UtSmem::DZ1 + ut_off16(row, j, 2 * H)) = ut_pack8(o);
             }
         }
-        UT_FENCE_SYNC();
-        // ---- M5: layer-1 weight / bias gradients (bf16); not waited for here -- the next tile's first commit (or the
-        //      one after the loop) covers it, and nothing it reads is rewritten before that wait
-        if (tid == 0) {
-            ut_gemm<true>(tmem + UT_DW1, sb + UtSmem::DZ1, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::XBB, DP * 16, 128, 2 * DP * 16,
-                          UT_ROWS / 16, ut_idesc(1, DP, 1, 1), first);
-            ut_gemm<true>(tmem + UT_DB1, sb + UtSmem::DZ1, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16,
-                          UT_ROWS / 16, ut_idesc(1, 16, 1, 1), first);
-        }
         first = 1u;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xcur[i] = xnext[i];
+        m5_pending = 1u;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");      // the last iteration's (empty) look-ahead gather
     if (first != 0u) {
-        if (tid == 0) ut_commit(bar);
+        UT_FENCE_SYNC();
+        if (tid == 0) { UT_ISSUE_M5(); ut_commit(bar); }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
+#undef UT_ISSUE_M5
 
     // ---- read the accumulated weight gradients out of TMEM into this CTA's partial
     //      (TMEM lane = output neuron: lanes 0-63 policy tower, 64-127 value tower; warpgroup q takes a column slice)
