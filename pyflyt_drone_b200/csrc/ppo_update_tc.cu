@@ -155,9 +155,9 @@ struct UtSmem {
     static constexpr int XB = 0;                              // X  f32       [128 x 32]    16 KB  forward L1 A
     static constexpr int H1C = XB + UT_ROWS * DP * 4;         // H1 f32 pi|vf [128 x 128]   64 KB  forward L2 A
     static constexpr int DZ2 = H1C;                           // dZ2 bf16     [128 x 128]   32 KB  aliases H1C (dead after M2)
-    static constexpr int DZ1 = H1C + UT_ROWS * 2 * H * 2;     // dZ1 bf16     [128 x 128]   32 KB  second half of H1C
-    static constexpr int H2B = H1C + UT_ROWS * 2 * H * 4;     // H2 bf16 pi|vf[128 x 128]   32 KB  wgrad L3 A; then dZ2
-    static constexpr int H1B = H2B + UT_ROWS * 2 * H * 2;     // H1 bf16 pi|vf[128 x 128]   32 KB  wgrad L2 B; then dZ1
+    static constexpr int H2B = H1C + UT_ROWS * 2 * H * 4;     // H2 bf16 pi|vf[128 x 128]   32 KB  wgrad L3 A
+    static constexpr int DZ1 = H2B;                           // dZ1 bf16     [128 x 128]   32 KB  aliases H2B (dead after M3)
+    static constexpr int H1B = H2B + UT_ROWS * 2 * H * 2;     // H1 bf16 pi|vf[128 x 128]   32 KB  wgrad L2 B
     static constexpr int XBB = H1B + UT_ROWS * 2 * H * 2;     // X  bf16      [128 x 32]     8 KB  wgrad L1 B
     static constexpr int DO = XBB + UT_ROWS * DP * 2;         // dOut|1 bf16  [128 x 16]     4 KB
     static constexpr int W1_PI = DO + UT_ROWS * 16 * 2;       // W1 f32       [64 x 32]      8 KB each
@@ -318,13 +318,14 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         //      thread's async copies (issued one tile ago), then make them visible block-wide
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         UT_FENCE_SYNC();       // also publishes the previous tile's dZ1
-        // ---- M5 of the previous tile, then M1: forward layer 1, both towers in one N = 128 GEMM (W1_pi and W1_vf are
-        //      adjacent and form one [128 x 32] K-major B operand).  One commit covers both.
+        // ---- M1: forward layer 1, both towers in one N = 128 GEMM (W1_pi and W1_vf are adjacent and form one
+        //      [128 x 32] K-major B operand); then, behind the commit, M5 of the previous tile: it runs under E1 and is
+        //      covered by M2's commit, before anything it reads (dZ1 = the H2 buffer, X bf16, dOut) is rewritten
         if (tid == 0) {
-            if (m5_pending) UT_ISSUE_M5();
             ut_gemm<false, DP / 8>(tmem + UT_T1, sb + UtSmem::XB, 128, DP * 32, 256, sb + UtSmem::W1_PI, 128, DP * 32, 256,
                            ut_idesc(2, 2 * H, 0, 0), 0u);
             ut_commit(bar);
+            if (m5_pending) UT_ISSUE_M5();
         }
         m5_acc = m5_pending;
         // loss inputs of this thread's sample, requested now and consumed after layer 2 (every warpgroup evaluates the
@@ -339,12 +340,14 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // bf16 copy of X: B operand of the layer-1 weight gradient (the previous tile's M5 has drained by now)
+        // bf16 copy of X (B operand of the layer-1 weight gradient): packed now, stored once the previous tile's M5,
+        // which still reads the old copy, has drained (after the M2 wait)
+        uint4 xbb;
         {
             const float4 xa = *reinterpret_cast<const float4*>(smem + UtSmem::XB + ut_off(grow, 8 * gpart, DP));
             const float4 xb = *reinterpret_cast<const float4*>(smem + UtSmem::XB + ut_off(grow, 8 * gpart + 4, DP));
             const float x8[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-            *reinterpret_cast<uint4*>(smem + UtSmem::XBB + ut_off16(grow, 8 * gpart, DP)) = ut_pack8(x8);
+            xbb = ut_pack8(x8);
         }
         // ---- E1: H1 = tanh(z1 + b1): fp32 for the forward, bf16 for the weight gradient of layer 2; keep 1 - H1^2
         uint32_t d1p[16], d2p[16];
@@ -377,6 +380,7 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        *reinterpret_cast<uint4*>(smem + UtSmem::XBB + ut_off16(grow, 8 * gpart, DP)) = xbb;
         // ---- E2: H2 = tanh(z2 + b2) (bf16 copy for the head weight gradient); partial head sums over this
         //      warpgroup's 32 hidden units (policy: 4 action means; value: 1)
         {
@@ -501,24 +505,26 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
             const int sn = (nt + gridDim.x) * UT_ROWS + grow;
             g_gat = sn < batch ? idx[sn] : 0;
         }
-        // ---- M3 + M4: head / layer-2 weight and bias gradients and the data gradient into layer 1 (bf16)
+        // ---- M3 + M4 (bf16).  Committed part: the head weight gradient (reads the H2 copy that E4 overwrites) and the
+        //      data gradient into layer 1 (E4 consumes it).  The layer-2 weight / bias gradients go out behind the commit:
+        //      they run under E4 and the next tile's S0 and are covered by the next commit.
         if (tid == 0) {
             // D3 += [H2]^T dOut   (A and B MN-major; K = 128 samples)
             ut_gemm<true, UT_ROWS / 16>(tmem + UT_D3, sb + UtSmem::H2B, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16, ut_idesc(1, 16, 1, 1), first);
-            // [Da | Db] += [dZ2]^T [H1_pi | H1_vf] as one N = 128 GEMM: rows 0-63 x cols 0-63 = dW2_pi,
-            // rows 64-127 x cols 64-127 = dW2_vf (the cross-tower blocks are computed and ignored)
-            ut_gemm<true, UT_ROWS / 16>(tmem + UT_DA, sb + UtSmem::DZ2, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::H1B, 2 * H * 16, 128, 2 * 2 * H * 16, ut_idesc(1, 2 * H, 1, 1), first);
-            ut_gemm<true, UT_ROWS / 16>(tmem + UT_DB2, sb + UtSmem::DZ2, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16, ut_idesc(1, 16, 1, 1), first);
             // dH1 = dZ2 W2: A = the tower's K-major sub-block of the dZ2 buffer, B = W2 (bf16) read MN-major
             ut_gemm<true, H / 16>(tmem + UT_T2, sb + UtSmem::DZ2, 128, 2 * H * 16, 256, sb + UtSmem::W2B_PI, H * 16, 128, 2 * H * 16,
                           ut_idesc(1, H, 0, 1), 0u);
             ut_gemm<true, H / 16>(tmem + UT_T2 + H, sb + UtSmem::DZ2 + 8 * 128, 128, 2 * H * 16, 256, sb + UtSmem::W2B_VF, H * 16, 128, 2 * H * 16, ut_idesc(1, H, 0, 1), 0u);
             ut_commit(bar);
+            // [Da | Db] += [dZ2]^T [H1_pi | H1_vf] as one N = 128 GEMM: rows 0-63 x cols 0-63 = dW2_pi,
+            // rows 64-127 x cols 64-127 = dW2_vf (the cross-tower blocks are computed and ignored)
+            ut_gemm<true, UT_ROWS / 16>(tmem + UT_DA, sb + UtSmem::DZ2, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::H1B, 2 * H * 16, 128, 2 * 2 * H * 16, ut_idesc(1, 2 * H, 1, 1), first);
+            ut_gemm<true, UT_ROWS / 16>(tmem + UT_DB2, sb + UtSmem::DZ2, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16, ut_idesc(1, 16, 1, 1), first);
         }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        // ---- E4: dZ1 = dH1 * tanh'(z1) (bf16, already scaled) into the second half of the H1C area; its MMAs (M5)
-        //      go out with the next tile's M1, after the block-wide sync that follows the next S0
+        // ---- E4: dZ1 = dH1 * tanh'(z1) (bf16, already scaled) over the H2 copy (M3 has consumed it); its MMAs (M5)
+        //      go out behind the next tile's M1
         {
             float v[32];
             ut_ld32(tmem + UT_T2 + lane_base + q * 32, v);
