@@ -328,16 +328,6 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
             if (m5_pending) UT_ISSUE_M5();
         }
         m5_acc = m5_pending;
-        // loss inputs of this thread's sample, requested now and consumed after layer 2 (every warpgroup evaluates the
-        // loss of its row redundantly: cheaper than a block-wide hand-off of the output gradients)
-        const int srow = tile * UT_ROWS + row;
-        const bool live = srow < batch;
-        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float lpo = 0.f, advv = 0.f, retv = 0.f;
-        if (live) {
-            a4 = reinterpret_cast<const float4*>(act)[g_loss];
-            lpo = logp_old[g_loss]; advv = adv[g_loss]; retv = ret[g_loss];
-        }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // bf16 copy of X (B operand of the layer-1 weight gradient): packed now, stored once the previous tile's M5,
@@ -348,6 +338,17 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
             const float4 xb = *reinterpret_cast<const float4*>(smem + UtSmem::XB + ut_off(grow, 8 * gpart + 4, DP));
             const float x8[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
             xbb = ut_pack8(x8);
+        }
+        // loss inputs of the tile's samples: gathered by warpgroup 0 only (four separate random lines per sample; doing it
+        // in all four warpgroups quadrupled the L1 wavefronts and stalled the block on the load queue), requested here so
+        // that they fly under E1, M2 and E2, and shared through smem next to the head partials
+        const int srow = tile * UT_ROWS + row;
+        const bool live = srow < batch;
+        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float lpo = 0.f, advv = 0.f, retv = 0.f;
+        if (q == 0 && live) {
+            a4 = reinterpret_cast<const float4*>(act)[g_loss];
+            lpo = logp_old[g_loss]; advv = adv[g_loss]; retv = ret[g_loss];
         }
         // ---- E1: H1 = tanh(z1 + b1): fp32 for the forward, bf16 for the weight gradient of layer 2; keep 1 - H1^2
         uint32_t d1p[16], d2p[16];
@@ -412,10 +413,20 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
                 for (int r = 0; r < 4; ++r)
                     d2p[4 * c8 + r] = ut_pack2(fmaf(-h[2 * r], h[2 * r], 1.0f), fmaf(-h[2 * r + 1], h[2 * r + 1], 1.0f));
             }
-            // XB is dead after M1: its first 8 KB carry the head partials of the four warpgroups
+            // XB is dead after M1: its first 8 KB carry the head partials of the four warpgroups, the next 4 KB the
+            // loss inputs of each row
             *reinterpret_cast<float4*>(smem + UtSmem::XB + (q * UT_ROWS + row) * 16) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+            if (q == 0) {
+                *reinterpret_cast<float4*>(smem + UtSmem::XB + 8192 + row * 32) = a4;
+                *reinterpret_cast<float4*>(smem + UtSmem::XB + 8192 + row * 32 + 16) = make_float4(lpo, advv, retv, 0.f);
+            }
         }
         __syncthreads();
+        if (q != 0) {
+            a4 = *reinterpret_cast<const float4*>(smem + UtSmem::XB + 8192 + row * 32);
+            const float4 t = *reinterpret_cast<const float4*>(smem + UtSmem::XB + 8192 + row * 32 + 16);
+            lpo = t.x; advv = t.y; retv = t.z;
+        }
         // ---- losses and their gradients w.r.t. the head outputs (stable_baselines3 PPO.train)
         float dout[A] = {0.f, 0.f, 0.f, 0.f}, doutv = 0.f;     // pre-scaled by grad_scale
         {
