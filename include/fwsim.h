@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 6
+#define FW_ABI_VERSION 7
 
 #define FW_NSURF 5            /* cmd order: left aileron, right aileron, h-tail, v-tail, main wing */
 #define FW_MAX_TARGETS 16
@@ -90,7 +90,8 @@ typedef struct FwConfig {
     int32_t early_return_on_crash, complete_truncates;
     int32_t wind_mode, wind_randomize, wind_rand_phase, wind_start_substep;
     int32_t num_obstacles, cam_interval_substeps, lock_hold_steps, switch_min_seen, cam_res;
-    int32_t _reserved[6];
+    int32_t force_generic_kernel;   /* 1 = never pick the kernels specialised for the standard aircraft layout (testing) */
+    int32_t _reserved[5];
 } FwConfig;
 
 /* Host-side view of the per-env state for parity injection / inspection.  Any pointer may be NULL

@@ -59,7 +59,8 @@ class FwConfigC(C.Structure):
         ("wind_mode", _I), ("wind_randomize", _I), ("wind_rand_phase", _I), ("wind_start_substep", _I),
         ("num_obstacles", _I), ("cam_interval_substeps", _I), ("lock_hold_steps", _I), ("switch_min_seen", _I),
         ("cam_res", _I),
-        ("_reserved", _I * 6),
+        ("force_generic_kernel", _I),
+        ("_reserved", _I * 5),
     ]
 
 
@@ -161,6 +162,7 @@ class EnvConfig:
     cam_near: float = 0.1
     cam_far: float = 255.0
     cam_res: int = 128
+    force_generic_kernel: int = 0                       # testing: run the generic kernels even for the standard layout
 
     # ------------------------------------------------------------------
     @property

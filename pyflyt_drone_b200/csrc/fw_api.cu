@@ -144,6 +144,25 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
         for (int i = 0; i < 3; ++i) A[6 * (3 + i) + 3 + i] = M;
         if (!invert6(A, Ai)) return fail(FW_EINVAL, "singular spatial inertia");
         for (int k = 0; k < 36; ++k) d.minv[k] = (float)Ai[k];
+        // Standard layout (fw_substep<STD>): +x forward units, lift +z (+y for the vertical tail, surface 3), thrust
+        // along +x, and an inverse spatial inertia that splits into the lateral {wx, wz, vy} / longitudinal
+        // {wy, vx, vz} blocks of an aircraft symmetric about its xz plane.  Anything else runs the generic kernels.
+        bool std_ok = true;
+        for (int s = 0; s < FWD_NSURF; ++s) {
+            const double* l = c.lift_unit[s];
+            const double* f = c.fwd_unit[s];
+            const bool lift_ok = s == 3 ? (l[0] == 0 && l[1] == 1 && l[2] == 0) : (l[0] == 0 && l[1] == 0 && l[2] == 1);
+            std_ok = std_ok && lift_ok && f[0] == 1 && f[1] == 0 && f[2] == 0;
+        }
+        std_ok = std_ok && c.thrust_unit[0] == 1 && c.thrust_unit[1] == 0 && c.thrust_unit[2] == 0;
+        double amax = 0;
+        for (int k = 0; k < 36; ++k) amax = fmax(amax, fabs(Ai[k]));
+        for (int i = 0; i < 6; ++i)
+            for (int j = 0; j < 6; ++j) {
+                const bool lat_i = (i == 0 || i == 2 || i == 4), lat_j = (j == 0 || j == 2 || j == 4);
+                if (lat_i != lat_j && fabs(Ai[6 * i + j]) > 1e-12 * amax) std_ok = false;
+            }
+        d.std_geom = (std_ok && c.force_generic_kernel == 0) ? 1 : 0;
     }
     double rad = 0.0;
     for (int i = 0; i < c.n_col; ++i) {

@@ -79,6 +79,8 @@ struct FwDev {
     // cached post-warm-up state (valid when no wind acts during the warm-up): pos3 quat4 vel3 omega3 act5 thr
     int warm_cached;
     float warm[20];
+    // 1 when the aircraft has the standard layout the STD kernels are specialised for (see fw_substep)
+    int std_geom;
     // rng / sharding
     uint32_t seed_lo, seed_hi, env_id0;
     int n;
@@ -195,10 +197,13 @@ __device__ __forceinline__ Mat3 fw_quat_mat(float x, float y, float z, float w) 
 // can interleave (ILP 5) and keeps warps convergent when only some aircraft are stalled.
 // Returns the force components along the lift and forward units and the scalar pitching torque about the
 // surface's torque axis (lift x fwd).
+// STD (standard layout, checked on the host): forward unit = +x and lift unit = +z, or +y when LIFT_Y -- the two dot
+// products are plain component picks.
+template <bool STD = false, bool LIFT_Y = false>
 __device__ __forceinline__ void fw_surface(const FwDev& p, const SurfDev& sf, float act, float vx, float vy, float vz,
                                            float& fn, float& fp, float& tq) {
-    float vl = vx * sf.lift[0] + vy * sf.lift[1] + vz * sf.lift[2];
-    float vf = vx * sf.fwd[0] + vy * sf.fwd[1] + vz * sf.fwd[2];
+    float vl = STD ? (LIFT_Y ? vy : vz) : vx * sf.lift[0] + vy * sf.lift[1] + vz * sf.lift[2];
+    float vf = STD ? vx : vx * sf.fwd[0] + vy * sf.fwd[1] + vz * sf.fwd[2];
     float h2 = vl * vl + vf * vf;
     float V2 = p.freestream_3d ? (vx * vx + vy * vy + vz * vz) : h2;
     float alpha = fw_atan2(-vl, vf);
@@ -249,6 +254,12 @@ __device__ __forceinline__ void fw_surface(const FwDev& p, const SurfDev& sf, fl
 // ------------------------------------------------------------------ one 240 Hz substep
 // cmd: latched actuator commands [5 surfaces + motor]; wind: world-frame wind seen by the surfaces
 // (already selected for this substep's time stamp); nz: N(0,1) draw for the motor noise.
+//
+// STD = the reference aircraft's layout, verified by derive() before a STD kernel is chosen: every surface's forward
+// unit is +x; lift unit +z for surfaces 0,1,2,4 and +y for surface 3 (vertical tail); thrust along +x; the aircraft
+// is symmetric about its xz plane, so the inverse spatial inertia splits into a lateral {wx, wz, vy} and a
+// longitudinal {wy, vx, vz} 3x3 block.  The arithmetic is the generic path's with the structural zeros skipped.
+template <bool STD = false>
 __device__ __forceinline__ void fw_substep(const FwDev& p, EnvState& e, const float cmd[6], float wnx, float wny,
                                            float wnz, float nz, bool& contact) {
     const float dt = p.dt;
@@ -272,25 +283,46 @@ __device__ __forceinline__ void fw_substep(const FwDev& p, EnvState& e, const fl
         float sy = vby + (wbz * sf.r[0] - wbx * sf.r[2]);
         float sz = vbz + (wbx * sf.r[1] - wby * sf.r[0]);
         float fn, fp, tq;
-        fw_surface(p, sf, e.act[s], sx, sy, sz, fn, fp, tq);
         // force = lift*fn + fwd*fp at the link CoM; torque about O = fn (r x lift) + fp (r x fwd) + tq (lift x fwd)
-        Fx += sf.lift[0] * fn + sf.fwd[0] * fp;
-        Fy += sf.lift[1] * fn + sf.fwd[1] * fp;
-        Fz += sf.lift[2] * fn + sf.fwd[2] * fp;
-        Tx += sf.ra[0] * fn + sf.rb[0] * fp + sf.tq[0] * tq;
-        Ty += sf.ra[1] * fn + sf.rb[1] * fp + sf.tq[1] * tq;
-        Tz += sf.ra[2] * fn + sf.rb[2] * fp + sf.tq[2] * tq;
+        if (STD && s != 3) {            // lift +z, fwd +x: ra = (ry, -rx, 0), rb = (0, rz, -ry), lift x fwd = +y
+            fw_surface<true, false>(p, sf, e.act[s], sx, sy, sz, fn, fp, tq);
+            Fx += fp; Fz += fn;
+            Tx += sf.ra[0] * fn;
+            Ty += sf.ra[1] * fn + sf.rb[1] * fp + tq;
+            Tz += sf.rb[2] * fp;
+        } else if (STD) {               // lift +y, fwd +x: ra = (-rz, 0, rx), rb = (0, rz, -ry), lift x fwd = -z
+            fw_surface<true, true>(p, sf, e.act[s], sx, sy, sz, fn, fp, tq);
+            Fx += fp; Fy += fn;
+            Tx += sf.ra[0] * fn;
+            Ty += sf.rb[1] * fp;
+            Tz += sf.ra[2] * fn + sf.rb[2] * fp - tq;
+        } else {
+            fw_surface(p, sf, e.act[s], sx, sy, sz, fn, fp, tq);
+            Fx += sf.lift[0] * fn + sf.fwd[0] * fp;
+            Fy += sf.lift[1] * fn + sf.fwd[1] * fp;
+            Fz += sf.lift[2] * fn + sf.fwd[2] * fp;
+            Tx += sf.ra[0] * fn + sf.rb[0] * fp + sf.tq[0] * tq;
+            Ty += sf.ra[1] * fn + sf.rb[1] * fp + sf.tq[1] * tq;
+            Tz += sf.ra[2] * fn + sf.rb[2] * fp + sf.tq[2] * tq;
+        }
     }
     {   // motor: first-order lag, multiplicative gaussian noise, thrust ~ rpm^2
         e.thr += p.motor_k * (cmd[5] - e.thr);
         e.thr += nz * e.thr * p.noise_ratio;
         float t2 = e.thr * e.thr;
         float thrust = t2 * p.thrust_max, torque = t2 * p.torque_max;
-        float fx = thrust * p.thrust_unit[0], fy = thrust * p.thrust_unit[1], fz = thrust * p.thrust_unit[2];
-        Fx += fx; Fy += fy; Fz += fz;
-        Tx += p.r_motor[1] * fz - p.r_motor[2] * fy + torque * p.thrust_unit[0];
-        Ty += p.r_motor[2] * fx - p.r_motor[0] * fz + torque * p.thrust_unit[1];
-        Tz += p.r_motor[0] * fy - p.r_motor[1] * fx + torque * p.thrust_unit[2];
+        if (STD) {                      // thrust along +x
+            Fx += thrust;
+            Tx += torque;
+            Ty += p.r_motor[2] * thrust;
+            Tz -= p.r_motor[1] * thrust;
+        } else {
+            float fx = thrust * p.thrust_unit[0], fy = thrust * p.thrust_unit[1], fz = thrust * p.thrust_unit[2];
+            Fx += fx; Fy += fy; Fz += fz;
+            Tx += p.r_motor[1] * fz - p.r_motor[2] * fy + torque * p.thrust_unit[0];
+            Ty += p.r_motor[2] * fx - p.r_motor[0] * fz + torque * p.thrust_unit[1];
+            Tz += p.r_motor[0] * fy - p.r_motor[1] * fx + torque * p.thrust_unit[2];
+        }
     }
     // ground contact is detected on the pose entering the step (Bullet runs collision detection first)
     if (e.pz <= p.col_radius + p.contact_margin) {
@@ -319,10 +351,20 @@ __device__ __forceinline__ void fw_substep(const FwDev& p, EnvState& e, const fl
     float b4 = Fy - p.mass * (wbz * cx - wbx * cz);
     float b5 = Fz - p.mass * (wbx * cy - wby * cx);
     float acc[6];
+    if (STD) {
+        // lateral block {0: wx, 2: wz, 4: vy} and longitudinal block {1: wy, 3: vx, 5: vz}
+        acc[0] = p.minv[0] * b0 + p.minv[2] * b2 + p.minv[4] * b4;
+        acc[2] = p.minv[12] * b0 + p.minv[14] * b2 + p.minv[16] * b4;
+        acc[4] = p.minv[24] * b0 + p.minv[26] * b2 + p.minv[28] * b4;
+        acc[1] = p.minv[7] * b1 + p.minv[9] * b3 + p.minv[11] * b5;
+        acc[3] = p.minv[19] * b1 + p.minv[21] * b3 + p.minv[23] * b5;
+        acc[5] = p.minv[31] * b1 + p.minv[33] * b3 + p.minv[35] * b5;
+    } else {
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
-        acc[i] = p.minv[6 * i + 0] * b0 + p.minv[6 * i + 1] * b1 + p.minv[6 * i + 2] * b2 +
-                 p.minv[6 * i + 3] * b3 + p.minv[6 * i + 4] * b4 + p.minv[6 * i + 5] * b5;
+        for (int i = 0; i < 6; ++i)
+            acc[i] = p.minv[6 * i + 0] * b0 + p.minv[6 * i + 1] * b1 + p.minv[6 * i + 2] * b2 +
+                     p.minv[6 * i + 3] * b3 + p.minv[6 * i + 4] * b4 + p.minv[6 * i + 5] * b5;
+    }
     // to the world frame, semi-implicit Euler, Bullet's per-coordinate velocity clamp
     float awx = m[0] * acc[0] + m[1] * acc[1] + m[2] * acc[2];
     float awy = m[3] * acc[0] + m[4] * acc[1] + m[5] * acc[2];

@@ -55,7 +55,7 @@ __device__ __forceinline__ void fw_flush_obs(float* __restrict__ dst_base, const
 
 // One agent step of env i held in registers (FixedwingBaseEnv.step + SubprocVecEnv reset-on-done).
 // Returns the reward; flag bits in `bits`; the observation (if TASK != 0) is left in `row`.
-template <int TASK>
+template <int TASK, bool STD>
 __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl, EnvState& e, int i,
                                              uint32_t gid, float a0, float a1, float a2, float a3, const float4& w0_in,
                                              const float4& w1_in, float& ep_ret, float* row, float* term_obs_row,
@@ -88,7 +88,7 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
             }
             float wx, wy, wz;
             fw_wind(p, ps, w0, w1, wx, wy, wz);
-            fw_substep(p, e, cmd, wx, wy, wz, nz, contact);
+            fw_substep<STD>(p, e, cmd, wx, wy, wz, nz, contact);
         }
         // compute_state: WaypointHandler.distance_to_targets (old <- new, new <- |delta_0|)
         float old_dist = e.new_dist;
@@ -145,7 +145,7 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
 // K1.  RANDOM_ACT: actions U(-1,1)^4 from Philox keyed (seed, global env id, episode, step_count); `spl` agent
 // steps per launch with the state held in registers between them (the random-action sweep never needs the
 // intermediate observations, so nothing but the final state goes back to HBM).
-template <int TASK, bool RANDOM_ACT>
+template <int TASK, bool RANDOM_ACT, bool STD>
 __global__ void __launch_bounds__(FW_BLOCK, FW_MIN_BLOCKS)
 fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4* __restrict__ act,
                float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ flg,
@@ -172,12 +172,12 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
                 float a0 = 2.0f * fw_u01(r.x) - 1.0f, a1 = 2.0f * fw_u01(r.y) - 1.0f;
                 float a2 = 2.0f * fw_u01(r.z) - 1.0f, a3 = 2.0f * fw_u01(r.w) - 1.0f;
                 if (p.wind_mode != 0 && st > 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
-                reward = fw_env_step<TASK>(p, pl, e, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
+                reward = fw_env_step<TASK, STD>(p, pl, e, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
                                            st == spl - 1 ? row : nullptr, nullptr, bits);
             }
         } else {
             float4 a = act[i];
-            reward = fw_env_step<TASK>(p, pl, e, i, gid, a.x, a.y, a.z, a.w, w0, w1, ep_ret, row,
+            reward = fw_env_step<TASK, STD>(p, pl, e, i, gid, a.x, a.y, a.z, a.w, w0, w1, ep_ret, row,
                                        (TASK != 0 && term_obs != nullptr && row != nullptr) ? term_obs + (size_t)i * D : nullptr,
                                        bits);
         }
@@ -490,9 +490,11 @@ static inline int grid_for(int n) { return (n + FW_BLOCK - 1) / FW_BLOCK; }
 
 typedef void (*fw_step_fn)(const FwDev, const FwPlanes, const float4*, float*, float*, uint8_t*, float*, int, int);
 
-static fw_step_fn step_fn(int task, bool random_act) {
-    if (task == 0) return random_act ? fw_step_kernel<0, true> : fw_step_kernel<0, false>;
-    if (task == 1) return random_act ? fw_step_kernel<1, true> : fw_step_kernel<1, false>;
+static fw_step_fn step_fn(int task, bool random_act, bool std_geom) {
+    if (task == 0 && std_geom) return random_act ? fw_step_kernel<0, true, true> : fw_step_kernel<0, false, true>;
+    if (task == 1 && std_geom) return random_act ? fw_step_kernel<1, true, true> : fw_step_kernel<1, false, true>;
+    if (task == 0) return random_act ? fw_step_kernel<0, true, false> : fw_step_kernel<0, false, false>;
+    if (task == 1) return random_act ? fw_step_kernel<1, true, false> : fw_step_kernel<1, false, false>;
     if (task == 2) return random_act ? fw_step_objlock_kernel<true> : fw_step_objlock_kernel<false>;
     return nullptr;
 }
@@ -500,7 +502,7 @@ static fw_step_fn step_fn(int task, bool random_act) {
 cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act, float* obs, float* rew, uint8_t* flg,
                             float* term_obs, bool random_act, int spl, cudaStream_t st) {
     const int bulk_ok = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) && ((p.obs_dim * 128) % 16 == 0);
-    fw_step_fn fn = step_fn(p.task, random_act);
+    fw_step_fn fn = step_fn(p.task, random_act, p.std_geom != 0);
     if (fn == nullptr) return cudaErrorNotSupported;
     fn<<<grid_for(p.n), FW_BLOCK, stage_bytes(p), st>>>(p, pl, reinterpret_cast<const float4*>(act), obs, rew, flg, term_obs,
                                                          spl, bulk_ok);
@@ -511,7 +513,7 @@ cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act
 // graph can later be launched on any stream including the legacy default stream torch hands us).
 cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* dep, const FwDev& p, const FwPlanes& pl, int spl,
                                       cudaGraphNode_t* out) {
-    fw_step_fn fn = step_fn(p.task, true);
+    fw_step_fn fn = step_fn(p.task, true, p.std_geom != 0);
     if (fn == nullptr) return cudaErrorNotSupported;
     FwDev pc = p; FwPlanes plc = pl;
     const float4* act = nullptr; float* obs = nullptr; float* rew = nullptr; uint8_t* flg = nullptr; float* term = nullptr;
