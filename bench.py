@@ -219,6 +219,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
 
     spl = max(1, args.steps_per_launch)
     FixedwingVecEnv.rollout_random(envs, W, spl, use_graph=False)
+    if not args.no_graph:
+        # one untimed pass through the launch graph: its construction / instantiation is not part of a step
+        FixedwingVecEnv.rollout_random(envs, replicas, spl, use_graph=True)
     launches0 = sum(e.launch_count for e in envs)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
