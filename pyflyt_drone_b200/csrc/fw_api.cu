@@ -111,6 +111,11 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
         o.stall_k = (float)(0.41 * (1.0 - exp(-17.0 / ar)));
         o.qarea = (float)(0.5 * c.rho * c.chord[s] * c.span[s]);
         o.chord = (float)c.chord[s];
+        o.k_te = (float)(aero_tau * c.eta[s] * c.defl_limit_deg[s] * DEG);
+        o.k_shift = (float)((1.0 - c.flap_to_chord[s]) * aero_tau * c.eta[s] * c.defl_limit_deg[s] * DEG);
+        o.cm0c = (float)(0.075 * c.chord[s]);
+        o.cm1c = (float)(0.175 * 2.0 / PI * c.chord[s]);
+        o.cla_ipa = (float)(cla / (PI * ar));
         const double* l = c.lift_unit[s];
         const double* f = c.fwd_unit[s];
         double t[3] = {l[1] * f[2] - l[2] * f[1], l[2] * f[0] - l[0] * f[2], l[0] * f[1] - l[1] * f[0]};

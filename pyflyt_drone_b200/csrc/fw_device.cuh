@@ -41,6 +41,9 @@ struct SurfDev {
     float chord;
     float lift[3], fwd[3], tq[3], r[3];
     float ra[3], rb[3];   // r x lift, r x fwd: moment arms of the normal / parallel force components about O
+    // folded products (one FMA each in the kernel): te = k_te * act; shift = k_shift * act;
+    // CM * chord = -CN * (cm0c + cm1c * |alpha_eff|); induced-angle slope cla * inv_pi_ar
+    float k_te, k_shift, cm0c, cm1c, cla_ipa;
 };
 
 struct FwDev {
@@ -204,51 +207,54 @@ __device__ __forceinline__ void fw_surface(const FwDev& p, const SurfDev& sf, fl
                                            float& fn, float& fp, float& tq) {
     float vl = STD ? (LIFT_Y ? vy : vz) : vx * sf.lift[0] + vy * sf.lift[1] + vz * sf.lift[2];
     float vf = STD ? vx : vx * sf.fwd[0] + vy * sf.fwd[1] + vz * sf.fwd[2];
-    float h2 = vl * vl + vf * vf;
-    float V2 = p.freestream_3d ? (vx * vx + vy * vy + vz * vz) : h2;
+    float h2 = fmaf(vl, vl, vf * vf);
+    float V2;
+    if (STD) { const float vo = LIFT_Y ? vz : vy; V2 = p.freestream_3d ? fmaf(vo, vo, h2) : h2; }   // the third component
+    else V2 = p.freestream_3d ? fmaf(vz, vz, fmaf(vy, vy, vx * vx)) : h2;
     float alpha = fw_atan2(-vl, vf);
     float inv_h = rsqrtf(fmaxf(h2, 1e-30f));
-    float cosA = vf * inv_h, sinA = -vl * inv_h;
 
-    float defl = act * sf.defl_rad;
-    float te = sf.tau_eta * defl;
-    float a0 = sf.a0_base - te;
-    float shift = sf.omf * te;
-    float asp = sf.asp_base - shift;
-    float asn = sf.asn_base - shift;
+    // deflection shifts of the zero-lift and stall angles, each one FMA on the actuator state
+    float a0 = fmaf(-sf.k_te, act, sf.a0_base);
+    float asp = fmaf(-sf.k_shift, act, sf.asp_base);
+    float asn = fmaf(-sf.k_shift, act, sf.asn_base);
     const bool nostall = (asn < alpha) && (alpha < asp);
     const bool pos = alpha > 0.0f;
 
     // induced angle: attached-flow value, or its stall value decaying linearly to 0 at +-pi/2
     // (numpy.interp semantics: clamped outside the two-point table)
-    float cl_lin = sf.cla * (alpha - a0);
+    float aa = alpha - a0;
+    float cl_lin = sf.cla * aa;
     float ast = pos ? asp : asn;
     float num = pos ? FWD_HALF_PI - alpha : alpha + FWD_HALF_PI;
     float den = pos ? FWD_HALF_PI - asp : asn + FWD_HALF_PI;
     float fac = __saturatef(__fdividef(num, den));
-    float ai_stall = sf.cla * (ast - a0) * sf.inv_pi_ar * fac;
-    float ai = nostall ? cl_lin * sf.inv_pi_ar : ai_stall;
-    float ae = alpha - a0 - ai;
+    float ai_stall = sf.cla_ipa * (ast - a0) * fac;
+    float ai = nostall ? sf.cla_ipa * aa : ai_stall;
+    float ae = aa - ai;
     float s, c;
     fw_sincos(ae, &s, &c);
 
     float CT_a = sf.cd0 * c;
-    float CN_a = __fdividef(cl_lin + CT_a * s, c);
-    float d = p.cd90_degrees ? act * sf.defl_deg : defl;
+    float CN_a = __fdividef(fmaf(CT_a, s, cl_lin), c);
+    float d = p.cd90_degrees ? act * sf.defl_deg : act * sf.defl_rad;
     float cd90 = fmaf(fmaf(-4.26e-2f, d, 2.1e-1f), d, 1.98f);
-    float CN_s = cd90 * s * (__fdividef(1.0f, 0.56f + 0.44f * fabsf(s)) - sf.stall_k);
+    float CN_s = cd90 * s * (__fdividef(1.0f, fmaf(0.44f, fabsf(s), 0.56f)) - sf.stall_k);
     float CN = nostall ? CN_a : CN_s;
     float CT = nostall ? CT_a : 0.5f * CT_a;
-    float Cl = CN * c - CT * s;
-    float Cd = CN * s + CT * c;
+    float Cl = fmaf(CN, c, -CT * s);
+    float Cd = fmaf(CN, s, CT * c);
     float aem = nostall ? ae : fabsf(ae);
-    float CM = -CN * (0.25f - 0.175f * (1.0f - aem * (2.0f / FWD_PI)));
+    // CM = -CN (0.25 - 0.175 (1 - 2 aem / pi)) = -CN (0.075 + 0.35 aem / pi); the chord is folded into the constants
+    float CMc = -CN * fmaf(aem, sf.cm1c, sf.cm0c);
 
+    // lift = Cl Q, drag = Cd Q rotated by alpha (cos = vf/h, sin = -vl/h):
+    //   normal = Q (Cl vf - Cd vl) / h,  parallel = -Q (Cl vl + Cd vf) / h
     float Q = sf.qarea * V2;
-    float lift = Cl * Q, drag = Cd * Q;
-    fn = lift * cosA + drag * sinA;
-    fp = lift * sinA - drag * cosA;
-    tq = Q * CM * sf.chord;
+    float Qi = Q * inv_h;
+    fn = Qi * fmaf(Cl, vf, -Cd * vl);
+    fp = -Qi * fmaf(Cl, vl, Cd * vf);
+    tq = Q * CMc;
 }
 
 // ------------------------------------------------------------------ one 240 Hz substep
@@ -279,9 +285,9 @@ __device__ __forceinline__ void fw_substep(const FwDev& p, EnvState& e, const fl
         const SurfDev& sf = p.surf[s];
         e.act[s] += sf.k_act * (cmd[s] - e.act[s]);
         // local airflow at the link CoM: v_O + w x r  (wind already subtracted from v_O)
-        float sx = vbx + (wby * sf.r[2] - wbz * sf.r[1]);
-        float sy = vby + (wbz * sf.r[0] - wbx * sf.r[2]);
-        float sz = vbz + (wbx * sf.r[1] - wby * sf.r[0]);
+        float sx = fmaf(wby, sf.r[2], fmaf(-wbz, sf.r[1], vbx));
+        float sy = fmaf(wbz, sf.r[0], fmaf(-wbx, sf.r[2], vby));
+        float sz = fmaf(wbx, sf.r[1], fmaf(-wby, sf.r[0], vbz));
         float fn, fp, tq;
         // force = lift*fn + fwd*fp at the link CoM; torque about O = fn (r x lift) + fp (r x fwd) + tq (lift x fwd)
         if (STD && s != 3) {            // lift +z, fwd +x: ra = (ry, -rx, 0), rb = (0, rz, -ry), lift x fwd = +y
