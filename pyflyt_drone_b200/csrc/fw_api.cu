@@ -29,6 +29,8 @@ static int fail(int code, const char* fmt, ...) {
         if (_e != cudaSuccess) return fail(FW_ECUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
     } while (0)
 
+#define FW_HOST_CHUNKS 4      // host lane: chunks per step (kernel of chunk c+1 overlaps the D2H copy of chunk c)
+
 struct FwSim {
     FwConfig cfg;
     FwDev dev;
@@ -37,6 +39,7 @@ struct FwSim {
     char* plane_mem;
     size_t plane_bytes;
     cudaStream_t io_stream;
+    cudaStream_t io_streams[2];   // host lane: io_stream and a second stream, chunks alternate between them
     // *_host staging: pinned host + device mirrors
     float *h_act, *h_obs, *h_rew, *h_term;
     uint8_t* h_flg;
@@ -209,6 +212,7 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
     d.warm_cached = 0;
     d.seed_lo = (uint32_t)(seed & 0xffffffffu); d.seed_hi = (uint32_t)(seed >> 32); d.env_id0 = env_id0;
     d.n = n;
+    d.i_begin = 0; d.i_end = n;
     return FW_OK;
 }
 
@@ -270,6 +274,9 @@ extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, ui
     // episode counter starts at -1 so that the first reset opens episode 0
     cudaMemset(pl.s5, 0xff, N * 16);
     CU(cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking));
+    h->io_streams[0] = h->io_stream;
+    CU(cudaStreamCreateWithFlags(&h->io_streams[1], cudaStreamNonBlocking));
+
 
     // cache the deterministic warm-up result when no wind acts during it
     if (h->dev.task != 2 && (h->dev.wind_mode == 0 || h->dev.wind_start_substep >= h->dev.warmup_substeps)) {
@@ -313,6 +320,7 @@ extern "C" int fw_destroy(fw_handle h) {
     if (h->h_term) cudaFreeHost(h->h_term);
     if (h->h_flg) cudaFreeHost(h->h_flg);
     if (h->io_stream) cudaStreamDestroy(h->io_stream);
+    if (h->io_streams[1]) cudaStreamDestroy(h->io_streams[1]);
     delete h;
     return FW_OK;
 }
@@ -422,18 +430,32 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
     int rc = ensure_host_io(h);
     if (rc != FW_OK) return rc;
     const size_t N = (size_t)h->n, D = (size_t)h->obs_dim;
-    cudaStream_t st = h->io_stream;
-    if (act_host != h->h_act) memcpy(h->h_act, act_host, N * 4 * sizeof(float));
-    CU(cudaMemcpyAsync(h->d_act, h->h_act, N * 4 * sizeof(float), cudaMemcpyHostToDevice, st));
-    CU(fwk_launch_step(h->dev, h->pl, h->d_act, D ? h->d_obs : nullptr, h->d_rew, h->d_flg,
-                       (term_obs_host && D) ? h->d_term : nullptr, false, 1, st));
-    h->launches++;
+    // The batch is cut into chunks, alternating between two streams: [step kernel -> D2H observations] of chunk c+1 runs
+    // while the copy engine drains chunk c, and caller-owned (pageable) actions are staged chunk by chunk under that GPU
+    // work.  The small per-env streams get no DMA operations of their own (each costs microseconds of fixed latency): the
+    // kernel reads the actions from and writes rewards and flags to the pinned host buffers directly (unified addressing;
+    // posted PCIe writes, complete when the kernel is); only the observations (95 % of the bytes) go through device
+    // memory and the copy engine.
+    const bool want_term = term_obs_host && D;
+    const int chunks = h->n >= 16384 ? FW_HOST_CHUNKS : 1;
+    const int per = (((h->n + chunks - 1) / chunks) + 63) / 64 * 64;
+    for (int c = 0; c < chunks; ++c) {
+        const int c0 = c * per, c1 = (c + 1) * per < h->n ? (c + 1) * per : h->n;
+        if (c0 >= c1) break;
+        const size_t n0 = (size_t)c0, cn = (size_t)(c1 - c0);
+        cudaStream_t st = h->io_streams[c & 1];
+        if (act_host != h->h_act) memcpy(h->h_act + n0 * 4, act_host + n0 * 4, cn * 4 * sizeof(float));
+        FwDev pc = h->dev;
+        pc.i_begin = c0; pc.i_end = c1;
+        CU(fwk_launch_step(pc, h->pl, h->h_act, D ? h->d_obs : nullptr, h->h_rew, h->h_flg, want_term ? h->d_term : nullptr,
+                           false, 1, st));
+        h->launches++;
+        if (obs_host && D) CU(cudaMemcpyAsync(h->h_obs + n0 * D, h->d_obs + n0 * D, cn * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (want_term) CU(cudaMemcpyAsync(h->h_term + n0 * D, h->d_term + n0 * D, cn * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
     h->fresh = false;
-    if (obs_host && D) CU(cudaMemcpyAsync(h->h_obs, h->d_obs, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (rew_host) CU(cudaMemcpyAsync(h->h_rew, h->d_rew, N * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (flags_host) CU(cudaMemcpyAsync(h->h_flg, h->d_flg, N, cudaMemcpyDeviceToHost, st));
-    if (term_obs_host && D) CU(cudaMemcpyAsync(h->h_term, h->d_term, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
+    CU(cudaStreamSynchronize(h->io_streams[0]));
+    if (chunks > 1) CU(cudaStreamSynchronize(h->io_streams[1]));
     // buffers obtained from fw_host_buffers are the pinned staging itself: nothing left to copy
     if (obs_host && D && obs_host != h->h_obs) memcpy(obs_host, h->h_obs, N * D * sizeof(float));
     if (rew_host && rew_host != h->h_rew) memcpy(rew_host, h->h_rew, N * sizeof(float));

@@ -87,6 +87,9 @@ struct FwDev {
     // rng / sharding
     uint32_t seed_lo, seed_hi, env_id0;
     int n;
+    // env range [i_begin, i_end) a step launch covers (whole batch by default; the host lane launches chunks so that
+    // the device-to-host copy of one chunk overlaps the kernel of the next)
+    int i_begin, i_end;
 };
 
 // SoA state in HBM: float4 planes (16-byte coalesced accesses, one plane element per env)

@@ -151,13 +151,13 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
                float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ flg,
                float* __restrict__ term_obs, int spl, int bulk_ok) {
     extern __shared__ __align__(128) float stage[];
-    const int i = blockIdx.x * FW_BLOCK + threadIdx.x;
+    const int i = p.i_begin + blockIdx.x * FW_BLOCK + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = p.obs_dim;
     float* stage_warp = stage + (size_t)warp * 32 * D;
     float* row = (TASK != 0 && obs != nullptr) ? stage_warp + (size_t)lane * D : nullptr;
 
-    if (i < p.n) {
+    if (i < p.i_end) {
         const uint32_t gid = p.env_id0 + (uint32_t)i;
         EnvState e;
         fw_load(pl, i, e);
@@ -187,8 +187,8 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
         if (flg != nullptr) flg[i] = (uint8_t)bits;
     }
     if (TASK != 0 && obs != nullptr) {
-        const int first_env = blockIdx.x * FW_BLOCK + warp * 32;
-        if (first_env < p.n) fw_flush_obs(obs, stage_warp, D, first_env, p.n, lane, bulk_ok != 0);
+        const int first_env = p.i_begin + blockIdx.x * FW_BLOCK + warp * 32;
+        if (first_env < p.i_end) fw_flush_obs(obs, stage_warp, D, first_env, p.i_end, lane, bulk_ok != 0);
     }
 }
 
@@ -382,14 +382,14 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
                        float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ flg,
                        float* __restrict__ term_obs, int spl, int bulk_ok) {
     extern __shared__ __align__(128) float stage[];
-    const int i = blockIdx.x * FW_BLOCK + threadIdx.x;
+    const int i = p.i_begin + blockIdx.x * FW_BLOCK + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = p.obs_dim;
     float* stage_warp = stage + (size_t)warp * 32 * D;
     float* row = obs != nullptr ? stage_warp + (size_t)lane * D : nullptr;
     float *so, *depth_row;
     ol_smem_carve(p, stage, so, depth_row);
-    const bool active = i < p.n;
+    const bool active = i < p.i_end;
     const uint32_t gid = p.env_id0 + (uint32_t)i;
     EnvState e = {};
     OlState ol = {};
@@ -430,8 +430,8 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
         if (flg != nullptr) flg[i] = (uint8_t)bits;
     }
     if (obs != nullptr) {
-        const int first_env = blockIdx.x * FW_BLOCK + warp * 32;
-        if (first_env < p.n) fw_flush_obs(obs, stage_warp, D, first_env, p.n, lane, bulk_ok != 0);
+        const int first_env = p.i_begin + blockIdx.x * FW_BLOCK + warp * 32;
+        if (first_env < p.i_end) fw_flush_obs(obs, stage_warp, D, first_env, p.i_end, lane, bulk_ok != 0);
     }
 }
 
@@ -504,7 +504,7 @@ cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act
     const int bulk_ok = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) && ((p.obs_dim * 128) % 16 == 0);
     fw_step_fn fn = step_fn(p.task, random_act, p.std_geom != 0);
     if (fn == nullptr) return cudaErrorNotSupported;
-    fn<<<grid_for(p.n), FW_BLOCK, stage_bytes(p), st>>>(p, pl, reinterpret_cast<const float4*>(act), obs, rew, flg, term_obs,
+    fn<<<grid_for(p.i_end - p.i_begin), FW_BLOCK, stage_bytes(p), st>>>(p, pl, reinterpret_cast<const float4*>(act), obs, rew, flg, term_obs,
                                                          spl, bulk_ok);
     return cudaGetLastError();
 }
@@ -522,10 +522,30 @@ cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* dep, const
     cudaKernelNodeParams kp;
     memset(&kp, 0, sizeof(kp));
     kp.func = (void*)fn;
-    kp.gridDim = dim3(grid_for(p.n)); kp.blockDim = dim3(FW_BLOCK);
+    kp.gridDim = dim3(grid_for(p.i_end - p.i_begin)); kp.blockDim = dim3(FW_BLOCK);
     kp.sharedMemBytes = (unsigned)stage_bytes(p);
     kp.kernelParams = args; kp.extra = nullptr;
     return cudaGraphAddKernelNode(out, g, dep, dep ? 1 : 0, &kp);
+}
+
+// Append one policy-action step launch over [p.i_begin, p.i_end) to a CUDA graph (the host lane's per-step graph).
+cudaError_t fwk_graph_add_step(cudaGraph_t g, const cudaGraphNode_t* deps, int ndeps, const FwDev& p, const FwPlanes& pl,
+                               const float* act_, float* obs_, float* rew_, uint8_t* flg_, float* term_, cudaGraphNode_t* out) {
+    fw_step_fn fn = step_fn(p.task, false, p.std_geom != 0);
+    if (fn == nullptr) return cudaErrorNotSupported;
+    FwDev pc = p; FwPlanes plc = pl;
+    const float4* act = reinterpret_cast<const float4*>(act_);
+    float* obs = obs_; float* rew = rew_; uint8_t* flg = flg_; float* term = term_;
+    int spl_ = 1;
+    int bulk = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) && ((p.obs_dim * 128) % 16 == 0);
+    void* args[] = {&pc, &plc, &act, &obs, &rew, &flg, &term, &spl_, &bulk};
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.func = (void*)fn;
+    kp.gridDim = dim3(grid_for(p.i_end - p.i_begin)); kp.blockDim = dim3(FW_BLOCK);
+    kp.sharedMemBytes = (unsigned)stage_bytes(p);
+    kp.kernelParams = args; kp.extra = nullptr;
+    return cudaGraphAddKernelNode(out, g, deps, ndeps, &kp);
 }
 
 cudaError_t fwk_launch_reset(const FwDev& p, const FwPlanes& pl, const uint8_t* mask, float* obs, bool emit_only,

@@ -103,11 +103,20 @@ class FixedwingVecEnv:
         The returned arrays are views of pinned memory owned by the env, valid until the next step."""
         if np.shape(actions) != (self.num_envs, 4):
             raise ValueError(f"actions must have shape ({self.num_envs}, 4), got {np.shape(actions)}")
-        np.copyto(self._h_act, actions, casting="same_kind")
+        # the library stages caller-owned actions into its pinned buffer chunk by chunk, overlapped with the GPU work;
+        # actions written straight into ``action_buffer`` skip that copy
+        a = actions if (isinstance(actions, np.ndarray) and actions.dtype == np.float32 and actions.flags.c_contiguous) \
+            else np.ascontiguousarray(actions, dtype=np.float32)
         p = lambda x: x.ctypes.data_as(C.c_void_p)  # noqa: E731
-        _lib.check(self.lib.fw_step_host(self._h, p(self._h_act), p(self._h_obs), p(self._h_rew), p(self._h_flags),
+        _lib.check(self.lib.fw_step_host(self._h, p(a), p(self._h_obs), p(self._h_rew), p(self._h_flags),
                                          p(self._h_term) if want_terminal_obs else None))
         return self._h_obs[:, : self.obs_dim], self._h_rew, self._h_flags, self._h_term[:, : self.obs_dim]
+
+    @property
+    def action_buffer(self) -> np.ndarray:
+        """The env's pinned [num_envs, 4] float32 action staging buffer: a policy that writes its actions here and
+        passes this very array to ``step_arrays`` avoids the host-side staging copy."""
+        return self._h_act
 
     def step_wait(self):
         if self._pending is None:
