@@ -81,6 +81,11 @@ int ppo_timeout_bootstrap(const float* params, int32_t d, const float* term_obs_
 int ppo_gae(const float* rewards, const float* values, const float* dones, const float* last_values, int32_t T,
             int32_t n, float gamma, float lam, float* advantages, float* returns, void* stream);
 
+/* Minibatch order of one epoch: out[0..n) = a keyed pseudo-random permutation of 0..n-1 (device int64), a fresh one per
+ * (seed, epoch).  Replaces the np.random.permutation of RolloutBuffer.get (a Feistel bijection with cycle walking
+ * instead of a sort). */
+int ppo_random_permutation(int64_t* out, int64_t n, uint64_t seed, uint64_t epoch, void* stream);
+
 /* ---- PPO minibatch update (stable_baselines3 PPO.train for one minibatch), csrc/ppo_update_tc.cu ----
  * ppo_minibatch_grad: gradient of
  *     -mean(min(A r, A clip(r, 1 +- clip_range))) - ent_coef * mean(entropy) + vf_coef * mean((ret - V)^2)

@@ -117,6 +117,13 @@ extern "C" int ppo_gae(const float* rewards, const float* values, const float* d
     return FW_OK;
 }
 
+extern "C" int ppo_random_permutation(int64_t* out, int64_t n, uint64_t seed, uint64_t epoch, void* stream) {
+    if (!out || n < 0) return pfail(FW_EINVAL, "ppo_random_permutation: null output or negative length");
+    if (n >= (1ll << 62)) return pfail(FW_EINVAL, "ppo_random_permutation: n too large");
+    PCU(ppok_permutation(reinterpret_cast<long long*>(out), (long long)n, seed, epoch, (cudaStream_t)stream));
+    return FW_OK;
+}
+
 extern "C" int ppo_counter_add(uint32_t* counter, uint32_t inc, void* stream) {
     if (!counter) return pfail(FW_EINVAL, "null argument");
     PCU(ppok_counter_add(counter, inc, (cudaStream_t)stream));

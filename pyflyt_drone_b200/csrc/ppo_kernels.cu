@@ -361,6 +361,42 @@ cudaError_t ppok_bootstrap(const float* params, int d, const float* term_obs, co
                         nullptr, 0, st, flags, gamma, rew);
 }
 
+// ------------------------------------------------------------------ minibatch permutation
+// A keyed pseudo-random permutation of [0, n): 4-round Feistel network on 2*hb bits (2^(2 hb) >= n) with cycle walking.
+// Replaces torch.randperm (a 4 M-key radix sort, ~0.4 ms per epoch at 65,536 envs x 64 steps) by one ~20 us pass;
+// every epoch gets a fresh key.  stable_baselines3 draws np.random.permutation here (RolloutBuffer.get).
+__device__ __forceinline__ uint32_t ppo_mix32(uint32_t x, uint32_t k) {
+    x ^= k; x *= 0x9E3779B1u; x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13; x *= 0xC2B2AE3Du; x ^= x >> 16;
+    return x;
+}
+__global__ void __launch_bounds__(256)
+ppo_permutation_kernel(long long* __restrict__ out, long long n, int hb, uint32_t k0, uint32_t k1) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t mask = (1u << hb) - 1u;
+    unsigned long long x = (unsigned long long)i;
+    do {                                     // cycle walking: re-encrypt until the value falls inside [0, n)
+        uint32_t L = (uint32_t)(x >> hb) & mask, R = (uint32_t)x & mask;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t t = L ^ (ppo_mix32(R, k0 + 0x9E3779B9u * (uint32_t)r) ^ ppo_mix32(R ^ k1, (uint32_t)r)) & mask;
+            L = R; R = t & mask;
+        }
+        x = ((unsigned long long)L << hb) | R;
+    } while (x >= (unsigned long long)n);
+    out[i] = (long long)x;
+}
+
+cudaError_t ppok_permutation(long long* out, long long n, uint64_t seed, uint64_t epoch, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    int hb = 1;
+    while (hb < 31 && (1ull << (2 * hb)) < (unsigned long long)n) ++hb;
+    const uint32_t k0 = (uint32_t)(seed ^ (epoch * 0x9E3779B97F4A7C15ull));
+    const uint32_t k1 = (uint32_t)((seed >> 32) ^ ((epoch * 0xC2B2AE3D27D4EB4Full) >> 32) ^ 0xA5A5A5A5u);
+    ppo_permutation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out, n, hb, k0, k1);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ K5: GAE, one thread per env, coalesced over envs
 __global__ void __launch_bounds__(256)
 ppo_gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const float* __restrict__ dones,
