@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--ppo-minibatches", type=int, default=4)
     ap.add_argument("--ppo-epochs", type=int, default=20)
     ap.add_argument("--e2e-steps", type=int, default=200)
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--steps-per-launch", type=int, default=1,
                     help="env-steps fused into one launch (state kept in registers); a bench step is one launch")
@@ -136,6 +136,14 @@ def cpu_model() -> str:
     return "unknown"
 
 
+def workload_name(workload: str, n: int) -> str:
+    """config.workload, identical for our arm and the reference arm."""
+    if workload == "physics_only":
+        return (f"{workload}: BASELINE configs[1] batched fixed-wing physics step, {n} envs/GPU, in-kernel Philox random "
+                f"actions, motor noise on")
+    return f"{workload}: {n} envs/GPU, random actions"
+
+
 def oracle_rate(workload: str, threads: int, seconds: float, n_envs: int = 4096):
     """Time the fp64 oracle (oracle/) on a bounded sample of the same workload: random actions from the
     same Philox stream, same auto-reset.  Returns (env-steps/s, sample description)."""
@@ -178,8 +186,11 @@ def run_reference(args, rank: int, world: int):
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "envs_per_step": n_envs,
-                   "note": "reference CPU path restated as the fp64 oracle port: PyFlyt/pybullet are not installable offline"},
+        "config": {"workload": workload_name(args.workload, args.envs), "envs_per_gpu": args.envs,
+                   "sample_envs_per_step": n_envs,
+                   "note": "reference CPU path restated as the fp64 oracle port (PyFlyt/pybullet are not installable "
+                           "offline); each step is a bounded sample of the workload: one agent step of a "
+                           f"{n_envs}-env slice of the batch on all host threads"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -281,9 +292,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: BASELINE configs[1] batched fixed-wing physics step, "
-                                   f"{N} envs/GPU, in-kernel Philox random actions, motor noise on"
-                       if args.workload == "physics_only" else f"{args.workload}: {N} envs/GPU, random actions",
+            "config": {"workload": workload_name(args.workload, N),
                        "envs_per_gpu": N, "substeps_per_env_step": 8, "physics_substeps_per_sec": value * 8,
                        "l2": f"rotating {replicas} env batches ({replicas * state_bytes / 2**20:.0f} MiB > 2x L2)",
                        "env_steps_per_launch": spl,
@@ -331,7 +340,6 @@ def run_ppo(args, rank: int, local_rank: int, world: int):
     K, W = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
     model.learn(W * N * T * world)
     model.stats.__init__()
-    l0 = env.launch_count
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -354,7 +362,11 @@ def run_ppo(args, rank: int, local_rank: int, world: int):
                            "rollout_env_steps_per_sec": st.env_steps / max(st.rollout_s, 1e-9),
                            "update": "fused tcgen05 minibatch gradient kernel + clip/Adam kernel (csrc/ppo_update_tc.cu)",
                            "forward": "tcgen05 kind::tf32 policy/value forward (csrc/ppo_tc.cu)", "rollout": "CUDA graph"},
-                "gpu_launches": int(env.launch_count - l0)}
+                # the rollout is one CUDA-graph replay, which bypasses the C-side launch counter: count this repo's kernels
+                # from the launch sequence instead -- per rollout step: obs moments, policy forward, env step, return
+                # moments, reward finalise, bootstrap value forward, step counter; per rollout: last values, GAE; per
+                # epoch: permutation; per minibatch: advantage stats, gradient, partial reduce, clip+Adam
+                "gpu_launches": int(K * (T * 7 + 2 + args.ppo_epochs * (1 + args.ppo_minibatches * 4)))}
         print(json.dumps(line), flush=True)
     env.close()
     if world > 1:
