@@ -38,6 +38,24 @@ def _stream() -> C.c_void_p:
     return C.c_void_p(int(torch.cuda.current_stream().cuda_stream))
 
 
+def export_vecnorm_npz(sd: dict, path: str) -> None:
+    """VecNormalize statistics (DeviceVecNormalize.state_dict()) under SB3's attribute names, as a plain .npz."""
+    np.savez(path, obs_rms_mean=np.asarray(sd["obs_rms.mean"], np.float64), obs_rms_var=np.asarray(sd["obs_rms.var"], np.float64),
+             obs_rms_count=np.float64(sd["obs_rms.count"]), ret_rms_mean=np.float64(sd["ret_rms.mean"]),
+             ret_rms_var=np.float64(sd["ret_rms.var"]), ret_rms_count=np.float64(sd["ret_rms.count"]),
+             clip_obs=np.float64(sd["clip_obs"]), clip_reward=np.float64(sd["clip_reward"]), gamma=np.float64(sd["gamma"]),
+             epsilon=np.float64(1e-8), norm_obs=np.bool_(sd.get("norm_obs", True)), norm_reward=np.bool_(sd.get("norm_reward", True)))
+
+
+def import_vecnorm_npz(path: str) -> dict:
+    z = np.load(path)
+    return {"obs_rms.mean": z["obs_rms_mean"], "obs_rms.var": z["obs_rms_var"], "obs_rms.count": float(z["obs_rms_count"]),
+            "ret_rms.mean": float(z["ret_rms_mean"]), "ret_rms.var": float(z["ret_rms_var"]),
+            "ret_rms.count": float(z["ret_rms_count"]), "clip_obs": float(z["clip_obs"]),
+            "clip_reward": float(z["clip_reward"]), "gamma": float(z["gamma"]),
+            "norm_obs": bool(z["norm_obs"]), "norm_reward": bool(z["norm_reward"])}
+
+
 class FlatMlpPolicy:
     """SB3 ``MlpPolicy`` (separate pi / vf towers [64, 64], tanh, state-independent log_std) stored as ONE flat
     fp32 parameter vector in the layout of include/fwppo.h."""
@@ -459,6 +477,32 @@ class PPO:
         self.vecnorm.load_state_dict(ck["vecnorm"])
         self.num_timesteps = ck["num_timesteps"]
         self._step_dev.fill_(int(ck["global_step"]))
+        return self
+
+    def export_sb3(self, directory: str) -> dict:
+        """Write what stable_baselines3 needs to replay this policy in the reference's eval scripts
+        (eval/eval_waypoints.py:96-107 loads a VecNormalize and a PPO model):
+          policy.pth   -- ``ActorCriticPolicy.state_dict()`` (MlpPolicy, net_arch pi=vf=[64, 64], Tanh): load with
+                          ``model.policy.load_state_dict(torch.load("policy.pth"))``
+          vecnorm.npz  -- the running moments under VecNormalize's attribute names: obs_rms_{mean,var,count},
+                          ret_rms_{mean,var,count}, clip_obs, clip_reward, gamma, epsilon
+        A full ``model.zip`` / ``vecnorm.pkl`` needs stable_baselines3's own classes to pickle and is left to the
+        machine that has them.  Returns the two paths."""
+        import os
+        os.makedirs(directory, exist_ok=True)
+        pol_path, vn_path = os.path.join(directory, "policy.pth"), os.path.join(directory, "vecnorm.npz")
+        torch.save({k: v.detach().cpu() for k, v in self.policy.state_dict().items()}, pol_path)
+        export_vecnorm_npz(self.vecnorm.state_dict(), vn_path)
+        return {"policy": pol_path, "vecnorm": vn_path}
+
+    def import_sb3(self, directory: str) -> "PPO":
+        """Inverse of export_sb3; also accepts a policy.pth saved from a real SB3 ``model.policy.state_dict()``."""
+        import os
+        sd = torch.load(os.path.join(directory, "policy.pth"), map_location="cpu", weights_only=True)
+        self.policy.load_state_dict(sd)
+        vn = os.path.join(directory, "vecnorm.npz")
+        if os.path.exists(vn):
+            self.vecnorm.load_state_dict(import_vecnorm_npz(vn))
         return self
 
     def get_parameters(self) -> dict:

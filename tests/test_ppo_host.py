@@ -35,6 +35,51 @@ def test_flat_policy_layout_and_sb3_names():
     assert torch.allclose(ent, torch.distributions.Normal(mean, torch.ones(4)).entropy().sum(-1), atol=1e-5)
 
 
+def test_policy_state_dict_loads_into_an_sb3_shaped_module(tmp_path):
+    """the exported policy.pth must load, strict, into a module with stable_baselines3's
+    ActorCriticPolicy structure (mlp_extractor.policy_net / value_net = Sequential(Linear, Tanh, Linear, Tanh),
+    action_net, value_net, log_std) and give the same outputs; the VecNormalize moments round-trip through the .npz."""
+    import torch.nn as nn
+    from pyflyt_drone_b200.ppo import FlatMlpPolicy, export_vecnorm_npz, import_vecnorm_npz
+
+    class Extractor(nn.Module):
+        def __init__(self, d):
+            super().__init__()
+            self.policy_net = nn.Sequential(nn.Linear(d, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh())
+            self.value_net = nn.Sequential(nn.Linear(d, 64), nn.Tanh(), nn.Linear(64, 64), nn.Tanh())
+
+    class Sb3Shaped(nn.Module):
+        def __init__(self, d):
+            super().__init__()
+            self.mlp_extractor = Extractor(d)
+            self.action_net = nn.Linear(64, 4)
+            self.value_net = nn.Linear(64, 1)
+            self.log_std = nn.Parameter(torch.zeros(4))
+
+    pol = FlatMlpPolicy(28, torch.device("cpu"), seed=3)
+    with torch.no_grad():
+        pol.theta.add_(0.05 * torch.randn(pol.count, generator=torch.Generator().manual_seed(0)))
+    path = tmp_path / "policy.pth"
+    torch.save({k: v.cpu() for k, v in pol.state_dict().items()}, path)
+    m = Sb3Shaped(28)
+    m.load_state_dict(torch.load(path, weights_only=True), strict=True)
+    obs = torch.randn(7, 28)
+    mean, val = pol.towers(obs)
+    assert torch.allclose(m.action_net(m.mlp_extractor.policy_net(obs)), mean, atol=1e-6)
+    assert torch.allclose(m.value_net(m.mlp_extractor.value_net(obs)).squeeze(-1), val.reshape(-1), atol=1e-6)
+    assert torch.equal(m.log_std.detach(), pol.view("log_std").detach())
+    # and back: a state_dict coming from such a module restores the flat vector
+    pol2 = FlatMlpPolicy(28, torch.device("cpu"), seed=9)
+    pol2.load_state_dict(m.state_dict())
+    assert torch.equal(pol2.theta, pol.theta)
+    sd = {"obs_rms.mean": np.arange(28.0), "obs_rms.var": np.arange(28.0) + 1, "obs_rms.count": 1234.0, "ret_rms.mean": 0.5,
+          "ret_rms.var": 2.0, "ret_rms.count": 99.0, "clip_obs": 10.0, "clip_reward": 10.0, "gamma": 0.99,
+          "norm_obs": True, "norm_reward": True}
+    export_vecnorm_npz(sd, str(tmp_path / "vecnorm.npz"))
+    back = import_vecnorm_npz(str(tmp_path / "vecnorm.npz"))
+    assert np.array_equal(back["obs_rms.mean"], sd["obs_rms.mean"]) and back["ret_rms.var"] == 2.0 and back["gamma"] == 0.99
+
+
 def test_moment_merge_is_chan():
     from pyflyt_drone_b200.ppo import DeviceVecNormalize
     rng = np.random.default_rng(0)
