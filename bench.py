@@ -37,8 +37,9 @@ if ROOT not in sys.path:
 
 METRIC = "fixedwing_env_steps_per_sec"
 UNIT = "env-steps/s"
-BYTES_PER_STEP = {"physics_only": 152, "waypoints_v3": 332, "waypoint_objlock": 400}
-FLOPS_PER_STEP = {"physics_only": 6400, "waypoints_v3": 7000, "waypoint_objlock": 7000}
+# SURVEY.md section 8(d); lowlevel (2 substeps per env-step): state 76 in + 76 out, action 24, target 12, obs 84, reward 4
+BYTES_PER_STEP = {"physics_only": 152, "waypoints_v3": 332, "waypoint_objlock": 400, "lowlevel": 276}
+FLOPS_PER_STEP = {"physics_only": 6400, "waypoints_v3": 7000, "waypoint_objlock": 7000, "lowlevel": 1750}
 L2_BYTES = 126 * 1024 * 1024
 
 
@@ -49,7 +50,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU per launch")
-    ap.add_argument("--workload", choices=["physics_only", "waypoints_v3", "waypoint_objlock", "ppo"], default="physics_only",
+    ap.add_argument("--workload", choices=["physics_only", "waypoints_v3", "waypoint_objlock", "lowlevel", "ppo"], default="physics_only",
                     help="ppo = BASELINE configs[2]: PPO Fixedwing-Waypoints rollout+update (a step is one PPO iteration)")
     ap.add_argument("--ppo-preset", choices=["waypoints_v3", "waypoint_objlock"], default="waypoints_v3")
     ap.add_argument("--ppo-envs", type=int, default=4096)
@@ -293,7 +294,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.workload, N),
-                       "envs_per_gpu": N, "substeps_per_env_step": 8, "physics_substeps_per_sec": value * 8,
+                       "envs_per_gpu": N, "substeps_per_env_step": cfg.inner_per_step * cfg.substeps_per_inner,
+                       "physics_substeps_per_sec": value * cfg.inner_per_step * cfg.substeps_per_inner,
                        "l2": f"rotating {replicas} env batches ({replicas * state_bytes / 2**20:.0f} MiB > 2x L2)",
                        "env_steps_per_launch": spl,
                        "launch": "host loop" if args.no_graph else f"CUDA graph of {replicas} launches", "e2e_workload": "waypoints_v3 via FixedwingVecEnv.step_arrays (host numpy)"},

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 7
+#define FW_ABI_VERSION 8
 
 #define FW_NSURF 5            /* cmd order: left aileron, right aileron, h-tail, v-tail, main wing */
 #define FW_MAX_TARGETS 16
@@ -86,7 +86,9 @@ typedef struct FwConfig {
     int32_t n_col;
     int32_t physics_per_control, substeps_per_inner, inner_per_step, warmup_inner;
     int32_t freestream_3d, cd90_degrees;
-    int32_t task, num_targets, sparse_reward, angle_repr, max_steps, context_len;
+    int32_t task;   /* 0 physics only, 1 Waypoints-v3, 2 Waypoint+ObjLock, 3 low-level tracking (FixedwingLowLevelEnv:
+                     * 21-float obs, 6-channel action, one Aviary.step per env step, truncation at step_count >= max_steps) */
+    int32_t num_targets, sparse_reward, angle_repr, max_steps, context_len;
     int32_t early_return_on_crash, complete_truncates;
     int32_t wind_mode, wind_randomize, wind_rand_phase, wind_start_substep;
     int32_t num_obstacles, cam_interval_substeps, lock_hold_steps, switch_min_seen, cam_res;
@@ -130,6 +132,9 @@ int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, uint64_t seed
 int fw_destroy(fw_handle h);
 int fw_num_envs(fw_handle h);
 int fw_obs_dim(fw_handle h);
+/* action width: 4 ([roll, pitch, yaw, thrust], Fixedwing mode 0) or 6 for task 3, the low-level env
+ * ([left ail, right ail, h-tail, v-tail, main wing, thrust], mode -1; envs/fixedwing_envs/fixedwing_lowlevel_env.py) */
+int fw_act_dim(fw_handle h);
 
 /* Replaces: VecEnv.reset() -> env.reset(seed=seed+rank) of every worker (fixedwing_base_env.py:193-257).
  * mask_dev: optional device bytes [N], non-zero = reset that env; NULL = all.  obs_dev: [N, obs_dim] f32 or NULL. */
@@ -137,7 +142,7 @@ int fw_reset(fw_handle h, const uint8_t* mask_dev, float* obs_dev, void* stream)
 
 /* Replaces: VecEnv.step_async/step_wait -> FlattenWaypointEnv.step -> FixedwingBaseEnv.step
  * (fixedwing_base_env.py:314-348, flatten_waypoint_env.py:52-72) plus the SubprocVecEnv worker's
- * reset-on-done.  act_dev [N,4] f32 in [-1,1]; obs_dev [N,obs_dim]; rew_dev [N]; flags_dev [N] bytes;
+ * reset-on-done.  act_dev [N,fw_act_dim] f32 in [-1,1]; obs_dev [N,obs_dim]; rew_dev [N]; flags_dev [N] bytes;
  * term_obs_dev [N,obs_dim] or NULL (rows of done envs receive info["terminal_observation"]). */
 int fw_step(fw_handle h, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* flags_dev,
             float* term_obs_dev, void* stream);

@@ -43,8 +43,11 @@
 int fwo_config_size(void) { return (int)sizeof(fwo_config); }
 int fwo_env_size(void) { return (int)sizeof(fwo_env); }
 
+int fwo_act_dim(const fwo_config* c) { return c->task == FWO_TASK_LOWLEVEL ? 6 : 4; }
+
 int fwo_obs_dim(const fwo_config* c) {
     if (c->task == FWO_TASK_PHYSICS) return 0;
+    if (c->task == FWO_TASK_LOWLEVEL) return 21;      /* fixedwing_lowlevel_env.py:64-68 */
     int att = (c->angle_repr == 0 ? 12 : 13) + 4 + 6;
     return att + 3 * c->context_len;
 }
@@ -84,6 +87,14 @@ void fwo_random_action(uint64_t seed, uint32_t env, uint32_t episode, uint32_t s
     uint32_t r[4];
     fwo_philox(seed, env, episode, step_count, STREAM_ACTION, r);
     for (int i = 0; i < 4; ++i) out[i] = 2.0 * fwo_u01(r[i]) - 1.0;
+}
+
+void fwo_random_action6(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step_count, double out[6]) {
+    uint32_t r[4];
+    fwo_random_action(seed, env, episode, step_count, out);
+    fwo_philox(seed, env, episode, step_count | 0x40000000u, STREAM_ACTION, r);
+    out[4] = 2.0 * fwo_u01(r[0]) - 1.0;
+    out[5] = 2.0 * fwo_u01(r[1]) - 1.0;
 }
 
 /* ------------------------------------------------------------------ small vector helpers */
@@ -291,6 +302,12 @@ static void solve6(double A[6][6], double b[6]) {
 }
 
 static void map_setpoint(const fwo_config* c, fwo_env* e) {
+    if (c->task == FWO_TASK_LOWLEVEL) {
+        /* [UP-RECALL] Fixedwing.update_control mode -1: cmd = setpoint (6 channels, surface order of the YAML +
+         * motor); docstring of fixedwing_lowlevel_env.py:13-14 agrees on the order */
+        for (int k = 0; k < 6; ++k) e->cmd[k] = e->setpoint[k];
+        return;
+    }
     /* [UP-RECALL] Fixedwing.update_control mode 0: [roll,pitch,yaw,thrust] ->
      * [left ail, right ail, h-tail, v-tail, main wing, motor] */
     e->cmd[0] = c->ail_left_sign * e->setpoint[0];
@@ -803,6 +820,50 @@ static void spawn_duck_obstacles(const fwo_config* c, fwo_env* e, uint64_t seed)
     }
 }
 
+/* FixedwingLowLevelEnv._compute_obs (fixedwing_lowlevel_env.py:143-156): Aviary.state(0) flattened
+ * [ang_vel_body, euler, lin_vel_body, lin_pos] + previous action (6) + target (3) */
+static void lowlevel_obs(const fwo_config* c, fwo_env* e, double* obs) {
+    (void)c;
+    if (!obs) return;
+    double R[9], rpy[3], wb[3], vb[3];
+    fwo_quat_to_mat(e->quat, R);
+    fwo_quat_to_euler(e->quat, rpy);
+    matT_vec(R, e->omega, wb);
+    matT_vec(R, e->vel, vb);
+    int k = 0;
+    for (int i = 0; i < 3; ++i) obs[k++] = wb[i];
+    for (int i = 0; i < 3; ++i) obs[k++] = rpy[i];
+    for (int i = 0; i < 3; ++i) obs[k++] = vb[i];
+    for (int i = 0; i < 3; ++i) obs[k++] = e->pos[i];
+    for (int i = 0; i < 6; ++i) obs[k++] = e->last_action[i];
+    for (int i = 0; i < 3; ++i) obs[k++] = e->target_ref[i];
+}
+
+static double wrap_pi(double a) {            /* FixedwingLowLevelEnv._wrap_pi: Python's % is the floored modulo */
+    double m = fmod(a + M_PI, 2.0 * M_PI);
+    if (m < 0.0) m += 2.0 * M_PI;
+    return m - M_PI;
+}
+
+/* FixedwingLowLevelEnv.step (fixedwing_lowlevel_env.py:97-141): one Aviary.step per env step */
+static void lowlevel_step(const fwo_config* c, fwo_env* e, uint64_t seed, const double* action, double* obs) {
+    e->step_count += 1;                                          /* self._episode_steps += 1 */
+    for (int k = 0; k < 6; ++k) { e->last_action[k] = action[k]; e->setpoint[k] = action[k]; }
+    aviary_step(c, e, seed);
+    lowlevel_obs(c, e, obs);
+    double R[9], rpy[3], vb[3];
+    fwo_quat_to_mat(e->quat, R);
+    fwo_quat_to_euler(e->quat, rpy);
+    matT_vec(R, e->vel, vb);
+    const double speed = sqrt(dot3(vb, vb)), alt = e->pos[2];
+    const double psi_err = fabs(wrap_pi(e->target_ref[0] - rpy[2]));
+    const double h_err = fabs(e->target_ref[1] - alt), v_err = fabs(e->target_ref[2] - speed);
+    e->reward = -(1.0 * psi_err + 1.0 * h_err + 0.5 * v_err) + 0.1;
+    e->termination = 0; e->truncation = 0; e->info_oob = 0;
+    if (alt < 1.0 || alt > 100.0) { e->termination = 1; e->reward -= 100.0; e->info_oob = 1; }
+    if (e->step_count >= c->max_steps) e->truncation = 1;        /* `>= 2000` */
+}
+
 void fwo_reset(const fwo_config* c, fwo_env* e, uint64_t seed, uint32_t env_id, uint32_t episode, double* obs) {
     memset(e, 0, sizeof(*e));
     e->env_id = env_id; e->episode = episode;
@@ -811,15 +872,31 @@ void fwo_reset(const fwo_config* c, fwo_env* e, uint64_t seed, uint32_t env_id, 
     e->quat[3] = 1.0;
     fwo_refresh_surface_vel(c, e, -1);                 /* Aviary.reset: drone.update_state() before any wind */
     sample_wind(c, e, seed);                           /* _maybe_apply_wind_field */
-    if (c->task != FWO_TASK_PHYSICS) sample_targets(c, e, seed);
+    if (c->task == FWO_TASK_LOWLEVEL) {
+        /* fixedwing_lowlevel_env.py:87-91: psi_ref ~ U(-pi, pi), h_ref ~ U(5, 20), V_ref ~ U(10, 20) */
+        uint32_t r[4];
+        fwo_philox(seed, env_id, episode, 0u, STREAM_TARGETS, r);
+        e->target_ref[0] = -M_PI + 2.0 * M_PI * fwo_u01(r[0]);
+        e->target_ref[1] = 5.0 + 15.0 * fwo_u01(r[1]);
+        e->target_ref[2] = 10.0 + 10.0 * fwo_u01(r[2]);
+    } else if (c->task != FWO_TASK_PHYSICS) sample_targets(c, e, seed);
     if (c->task == FWO_TASK_OBJLOCK) spawn_duck_obstacles(c, e, seed);
     /* end_reset: set_mode(0) -> zero setpoint; 10 x Aviary.step; compute_state */
     for (int i = 0; i < c->warmup_inner; ++i) aviary_step(c, e, seed);
-    fwo_compute_obs(c, e, obs, 1);
+    if (c->task == FWO_TASK_LOWLEVEL) lowlevel_obs(c, e, obs);
+    else fwo_compute_obs(c, e, obs, 1);
 }
 
-void fwo_step(const fwo_config* c, fwo_env* e, uint64_t seed, const double action[4],
+void fwo_step(const fwo_config* c, fwo_env* e, uint64_t seed, const double* action,
               double* obs, double* reward, int32_t* flags) {
+    if (c->task == FWO_TASK_LOWLEVEL) {
+        lowlevel_step(c, e, seed, action, obs);
+        e->ep_return += e->reward;
+        e->ep_length += 1;
+        if (reward) *reward = e->reward;
+        if (flags) *flags = (e->termination ? FWO_TERM : 0) | (e->truncation ? FWO_TRUNC : 0) | (e->info_oob ? FWO_OOB : 0);
+        return;
+    }
     e->reward = -0.1;
     for (int k = 0; k < 4; ++k) { e->last_action[k] = action[k]; e->setpoint[k] = action[k]; }
     e->setpoint[3] = action[3] / 2.0 + 0.5;
@@ -861,7 +938,7 @@ static void run_range(fwo_job* j) {
             double* o = j->obs ? j->obs + (size_t)i * D : tmp;
             int32_t fl = 0;
             double r = 0;
-            fwo_step(c, e, j->seed, j->actions + (size_t)i * 4, o, &r, &fl);
+            fwo_step(c, e, j->seed, j->actions + (size_t)i * fwo_act_dim(c), o, &r, &fl);
             if (j->rewards) j->rewards[i] = r;
             if (j->flags) j->flags[i] = fl;
             if (fl & (FWO_TERM | FWO_TRUNC)) {
@@ -871,10 +948,11 @@ static void run_range(fwo_job* j) {
                 fwo_reset(c, e, j->seed, id, ep, o);
             }
         } else {
-            double obs[FWO_MAX_OBS], a[4], r;
+            double obs[FWO_MAX_OBS], a[FWO_MAX_ACT], r;
             int32_t fl;
             for (int s = 0; s < j->steps; ++s) {
-                fwo_random_action(j->seed, e->env_id, e->episode, (uint32_t)e->step_count, a);
+                if (fwo_act_dim(c) == 6) fwo_random_action6(j->seed, e->env_id, e->episode, (uint32_t)e->step_count, a);
+                else fwo_random_action(j->seed, e->env_id, e->episode, (uint32_t)e->step_count, a);
                 fwo_step(c, e, j->seed, a, obs, &r, &fl);
                 if (fl & (FWO_TERM | FWO_TRUNC)) {
                     uint32_t ep = e->episode + 1, id = e->env_id;

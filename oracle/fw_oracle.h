@@ -40,6 +40,8 @@ extern "C" {
 #define FWO_TASK_PHYSICS   0  /* dynamics + ground/dome termination only (BASELINE config 2) */
 #define FWO_TASK_WAYPOINTS 1  /* PyFlyt/Fixedwing-Waypoints-v3 + FlattenWaypointEnv */
 #define FWO_TASK_OBJLOCK   2  /* FixedwingWaypointObjLockEnv + FlattenWaypointEnv */
+#define FWO_TASK_LOWLEVEL  3  /* FixedwingLowLevelEnv: mode -1 six-channel control, psi/h/V tracking (fixedwing_lowlevel_env.py) */
+#define FWO_MAX_ACT 6
 
 typedef struct {
     /* ---- lifting surfaces: my_models/fixedwing/fixewing.yaml:8-71 ---- */
@@ -124,9 +126,10 @@ typedef struct {
     double act[FWO_NSURF];
     double throttle;
     double surf_vel[FWO_NSURF][3];  /* cached local surface velocities (update_state) */
-    double setpoint[4];   /* aviary setpoint (thrust already remapped to [0,1]) */
+    double setpoint[FWO_MAX_ACT];   /* aviary setpoint (mode 0: 4 channels, thrust already remapped to [0,1]; mode -1: 6) */
     double cmd[6];
-    double last_action[4];
+    double last_action[FWO_MAX_ACT];
+    double target_ref[3];           /* low-level task: psi_ref, h_ref, V_ref */
     double targets[FWO_MAX_TARGETS][3];
     int32_t n_remaining;  /* len(waypoints.targets) */
     int32_t target_idx;   /* index of targets[0] in the original list */
@@ -166,6 +169,8 @@ void fwo_philox(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c
 double fwo_u01(uint32_t x);
 void fwo_normals4(uint64_t seed, uint32_t env, uint32_t episode, uint32_t idx, double out[4]);
 void fwo_random_action(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step_count, double out[4]);
+/* channels 4,5 of a six-channel action: a second Philox call at index step_count | 0x40000000 */
+void fwo_random_action6(uint64_t seed, uint32_t env, uint32_t episode, uint32_t step_count, double out[6]);
 
 /* lifting-surface model ([UP-RECALL] PyFlyt LiftingSurface): returns Cl, Cd, CM */
 void fwo_aero_coeffs(const fwo_config* c, int s, double alpha, double actuation, double out[3]);
@@ -177,7 +182,8 @@ void fwo_substep(const fwo_config* c, fwo_env* e, uint64_t seed);
 
 /* gymnasium-level API */
 void fwo_reset(const fwo_config* c, fwo_env* e, uint64_t seed, uint32_t env_id, uint32_t episode, double* obs);
-void fwo_step(const fwo_config* c, fwo_env* e, uint64_t seed, const double action[4],
+int fwo_act_dim(const fwo_config* c);   /* 4, or 6 for the low-level task */
+void fwo_step(const fwo_config* c, fwo_env* e, uint64_t seed, const double* action,
               double* obs, double* reward, int32_t* flags);
 /* SubprocVecEnv worker semantics: step, and on done stash terminal obs then reset */
 void fwo_vec_step(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, const double* actions,

@@ -55,7 +55,7 @@ class OConfig(C.Structure):
 class OEnv(C.Structure):
     _fields_ = [
         ("pos", _V3), ("quat", _D * 4), ("vel", _V3), ("omega", _V3), ("act", _D * NSURF), ("throttle", _D),
-        ("surf_vel", _V3 * NSURF), ("setpoint", _D * 4), ("cmd", _D * 6), ("last_action", _D * 4),
+        ("surf_vel", _V3 * NSURF), ("setpoint", _D * 6), ("cmd", _D * 6), ("last_action", _D * 6), ("target_ref", _V3),
         ("targets", _V3 * MAX_TARGETS), ("n_remaining", _I), ("target_idx", _I), ("old_dist", _D), ("new_dist", _D),
         ("step_count", _I), ("physics_steps", _I), ("termination", _I), ("truncation", _I),
         ("info_collision", _I), ("info_oob", _I), ("info_complete", _I), ("info_strike", _I),
@@ -96,6 +96,9 @@ def lib() -> C.CDLL:
         L.fwo_env_size.restype = C.c_int
         L.fwo_obs_dim.restype = C.c_int
         L.fwo_obs_dim.argtypes = [C.POINTER(OConfig)]
+        L.fwo_act_dim.restype = C.c_int
+        L.fwo_act_dim.argtypes = [C.POINTER(OConfig)]
+        L.fwo_random_action6.argtypes = [C.c_uint64, _U, _U, _U, C.POINTER(_D)]
         L.fwo_u01.restype = _D
         L.fwo_u01.argtypes = [_U]
         L.fwo_philox.argtypes = [C.c_uint64, _U, _U, _U, _U, C.POINTER(_U)]
@@ -164,6 +167,7 @@ class OracleVecEnv:
         self.n, self.seed, self.env_id0, self.nthreads = int(n), int(seed), int(env_id0), int(nthreads)
         self.envs = (OEnv * self.n)()
         self.obs_dim = self.L.fwo_obs_dim(C.byref(self.cfg))
+        self.act_dim = self.L.fwo_act_dim(C.byref(self.cfg))
         self.num_targets = int(cfg["num_targets"])
 
     def reset(self) -> np.ndarray:
@@ -172,7 +176,7 @@ class OracleVecEnv:
         return obs[:, : self.obs_dim]
 
     def step(self, actions: np.ndarray):
-        a = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.n, 4)
+        a = np.ascontiguousarray(actions, dtype=np.float64).reshape(self.n, self.act_dim)
         D = max(self.obs_dim, 1)
         obs = np.zeros((self.n, D)); term = np.zeros((self.n, D))
         rew = np.zeros(self.n); flags = np.zeros(self.n, dtype=np.int32)
@@ -197,6 +201,8 @@ class OracleVecEnv:
             # original list: already-reached targets are unknown to the oracle -> leave zeros before target_idx
             for t in range(e.n_remaining):
                 out["targets"][i, e.target_idx + t] = e.targets[t][:]
+            if self.cfg.task == 3:                       # low-level task: the tracked reference rides in slot 0
+                out["targets"][i, 0] = e.target_ref[:]
             out["target_idx"][i] = e.target_idx; out["step_count"][i] = e.step_count
             out["physics_steps"][i] = e.physics_steps; out["episode"][i] = e.episode
             out["new_dist"][i] = e.new_dist if np.isfinite(e.new_dist) else 0.0
@@ -234,7 +240,9 @@ class OracleVecEnv:
                 w = s["wind"][i]
                 e.wind_base[:] = [float(x) for x in w[:3]]; e.gust_amp[:] = [float(x) for x in w[3:6]]
                 e.gust_phase = float(w[6])
-            if "targets" in s:
+            if "targets" in s and self.cfg.task == 3:
+                e.target_ref[:] = [float(x) for x in s["targets"][i][0]]
+            elif "targets" in s:
                 tidx = int(s["target_idx"][i]) if "target_idx" in s else e.target_idx
                 T = self.num_targets
                 e.target_idx = tidx; e.n_remaining = T - tidx

@@ -35,6 +35,7 @@ SYMBOLS = [
     ("fw_destroy", C.c_int, [_P]),
     ("fw_num_envs", C.c_int, [_P]),
     ("fw_obs_dim", C.c_int, [_P]),
+    ("fw_act_dim", C.c_int, [_P]),
     ("fw_reset", C.c_int, [_P, _P, _P, _P]),
     ("fw_step", C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     ("fw_step_random", C.c_int, [_P, C.c_int32, _P, _P, _P]),

@@ -18,7 +18,7 @@ from . import aircraft
 
 NSURF, MAX_TARGETS, MAX_COL, MAX_OBST = 5, 16, 16, 32
 
-TASK_PHYSICS, TASK_WAYPOINTS, TASK_OBJLOCK = 0, 1, 2
+TASK_PHYSICS, TASK_WAYPOINTS, TASK_OBJLOCK, TASK_LOWLEVEL = 0, 1, 2, 3
 
 FLAG_TERM, FLAG_TRUNC, FLAG_COLLISION, FLAG_OOB, FLAG_COMPLETE, FLAG_STRIKE = 1, 2, 4, 8, 16, 32
 
@@ -307,7 +307,17 @@ def physics_only(**overrides) -> EnvConfig:
     return cfg.replace(**overrides) if overrides else cfg
 
 
-PRESETS = {"waypoints_v3": waypoints_v3, "waypoint_objlock": waypoint_objlock, "physics_only": physics_only}
+def lowlevel(wind: dict | None = None, **overrides) -> EnvConfig:
+    """FixedwingLowLevelEnv (envs/fixedwing_envs/fixedwing_lowlevel_env.py:22-72): mode -1 six-channel control, start
+    (0,0,10) at 15 m/s, one Aviary.step per env step, no warm-up, 2,000-step episodes, psi/h/V tracking."""
+    cfg = EnvConfig(task=TASK_LOWLEVEL, num_targets=1, angle_repr=0, max_steps=2000, context_len=0, inner_per_step=1,
+                    warmup_inner=0, start_pos=[0.0, 0.0, 10.0], start_vel=[15.0, 0.0, 0.0],
+                    **_wind_fields(wind, "env")).with_aircraft()
+    return cfg.replace(**overrides) if overrides else cfg
+
+
+PRESETS = {"waypoints_v3": waypoints_v3, "waypoint_objlock": waypoint_objlock, "physics_only": physics_only,
+           "lowlevel": lowlevel}
 
 
 def from_gym_kwargs(preset: str = "waypoints_v3", *, sparse_reward=None, num_targets=None, goal_reach_distance=None,

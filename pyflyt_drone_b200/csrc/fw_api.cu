@@ -82,7 +82,7 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
     memset(&d, 0, sizeof(d));
     const double PI = 3.14159265358979323846, DEG = PI / 180.0;
     if (!(c.dt > 0) || !(c.mass > 0)) return fail(FW_EINVAL, "dt and mass must be positive");
-    if (c.task < 0 || c.task > 2) return fail(FW_EINVAL, "task %d unknown (0 physics, 1 waypoints, 2 waypoint+objlock)", c.task);
+    if (c.task < 0 || c.task > 3) return fail(FW_EINVAL, "task %d unknown (0 physics, 1 waypoints, 2 waypoint+objlock, 3 low-level)", c.task);
     if (c.task == 2 && (c.num_obstacles < 0 || c.num_obstacles > FW_MAX_OBST)) return fail(FW_EINVAL, "num_obstacles out of range");
     if (c.task == 2 && (c.cam_res < 3 || c.cam_res > 1024)) return fail(FW_EINVAL, "cam_res out of range");
     if (c.num_targets < 0 || c.num_targets > FW_MAX_TARGETS) return fail(FW_EINVAL, "num_targets out of range");
@@ -190,7 +190,8 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
     d.quat_limiter = (sqrt(3.0) * c.max_coord_vel * c.dt > 0.25 * PI) ? 1 : 0;
     d.task = c.task; d.num_targets = c.num_targets; d.sparse_reward = c.sparse_reward; d.angle_repr = c.angle_repr;
     d.max_steps = c.max_steps; d.context_len = c.context_len;
-    d.obs_dim = c.task == 0 ? 0 : ((c.angle_repr == 0 ? 12 : 13) + 4 + 6 + 3 * c.context_len);
+    d.obs_dim = c.task == 0 ? 0 : (c.task == 3 ? 21 : ((c.angle_repr == 0 ? 12 : 13) + 4 + 6 + 3 * c.context_len));
+    d.act_dim = c.task == 3 ? 6 : 4;
     d.early_return_on_crash = c.early_return_on_crash; d.complete_truncates = c.complete_truncates;
     d.goal_reach = (float)c.goal_reach; d.dome = (float)c.dome; d.dome2 = (float)(c.dome * c.dome); d.spawn_size = (float)c.spawn_size; d.min_height = (float)c.min_height;
     for (int k = 0; k < 3; ++k) {
@@ -327,6 +328,7 @@ extern "C" int fw_destroy(fw_handle h) {
 
 extern "C" int fw_num_envs(fw_handle h) { return h ? h->n : fail(FW_EINVAL, "null handle"); }
 extern "C" int fw_obs_dim(fw_handle h) { return h ? h->obs_dim : fail(FW_EINVAL, "null handle"); }
+extern "C" int fw_act_dim(fw_handle h) { return h ? h->dev.act_dim : fail(FW_EINVAL, "null handle"); }
 extern "C" int64_t fw_launch_count(fw_handle h) { return h ? h->launches : 0; }
 
 extern "C" int fw_reset(fw_handle h, const uint8_t* mask_dev, float* obs_dev, void* stream) {
@@ -408,12 +410,13 @@ extern "C" int fw_rollout_random(const fw_handle* hs, int32_t n_handles, int32_t
 static int ensure_host_io(FwSim* h) {
     if (h->h_act) return FW_OK;
     const size_t N = (size_t)h->n, D = (size_t)(h->obs_dim > 0 ? h->obs_dim : 1);
-    CU(cudaMallocHost((void**)&h->h_act, N * 4 * sizeof(float)));
+    const size_t Aw = (size_t)h->dev.act_dim;
+    CU(cudaMallocHost((void**)&h->h_act, N * Aw * sizeof(float)));
     CU(cudaMallocHost((void**)&h->h_obs, N * D * sizeof(float)));
     CU(cudaMallocHost((void**)&h->h_rew, N * sizeof(float)));
     CU(cudaMallocHost((void**)&h->h_term, N * D * sizeof(float)));
     CU(cudaMallocHost((void**)&h->h_flg, N));
-    CU(cudaMalloc((void**)&h->d_act, N * 4 * sizeof(float)));
+    CU(cudaMalloc((void**)&h->d_act, N * Aw * sizeof(float)));
     CU(cudaMalloc((void**)&h->d_obs, N * D * sizeof(float)));
     CU(cudaMalloc((void**)&h->d_rew, N * sizeof(float)));
     CU(cudaMalloc((void**)&h->d_term, N * D * sizeof(float)));
@@ -444,7 +447,8 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
         if (c0 >= c1) break;
         const size_t n0 = (size_t)c0, cn = (size_t)(c1 - c0);
         cudaStream_t st = h->io_streams[c & 1];
-        if (act_host != h->h_act) memcpy(h->h_act + n0 * 4, act_host + n0 * 4, cn * 4 * sizeof(float));
+        const size_t Aw = (size_t)h->dev.act_dim;
+        if (act_host != h->h_act) memcpy(h->h_act + n0 * Aw, act_host + n0 * Aw, cn * Aw * sizeof(float));
         FwDev pc = h->dev;
         pc.i_begin = c0; pc.i_end = c1;
         CU(fwk_launch_step(pc, h->pl, h->h_act, D ? h->d_obs : nullptr, h->h_rew, h->h_flg, want_term ? h->d_term : nullptr,

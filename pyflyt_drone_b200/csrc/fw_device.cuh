@@ -65,7 +65,7 @@ struct FwDev {
     int substeps_per_inner, inner_per_step, warmup_substeps;
     int freestream_3d, cd90_degrees, quat_limiter;
     // env
-    int task, num_targets, sparse_reward, angle_repr, max_steps, context_len, obs_dim;
+    int task, num_targets, sparse_reward, angle_repr, max_steps, context_len, obs_dim, act_dim;
     int early_return_on_crash, complete_truncates;
     float goal_reach, dome, dome2, spawn_size, min_height;
     float start_pos[3], start_vel[3];
@@ -502,6 +502,34 @@ __device__ __forceinline__ void fw_write_obs(const FwDev& p, const FwPlanes& pl,
     }
 }
 
+// FixedwingLowLevelEnv._compute_obs (fixedwing_lowlevel_env.py:143-156): Aviary.state(0) flattened
+// [ang_vel_body, euler, lin_vel_body, lin_pos], the previous action (6) and the target [psi_ref, h_ref, V_ref];
+// also returns yaw and the body-frame speed the reward needs
+__device__ __forceinline__ void fw_write_obs_lowlevel(const FwPlanes& pl, const EnvState& e, int i, int n, const float a[6],
+                                                      float* o, float& yaw_out, float& speed_out, float tref[3]) {
+    Mat3 R = fw_quat_mat(e.qx, e.qy, e.qz, e.qw);
+    const float* m = R.m;
+    float roll, pitch, yaw;
+    fw_euler(e, roll, pitch, yaw);
+    const float vbx = m[0] * e.vx + m[3] * e.vy + m[6] * e.vz;
+    const float vby = m[1] * e.vx + m[4] * e.vy + m[7] * e.vz;
+    const float vbz = m[2] * e.vx + m[5] * e.vy + m[8] * e.vz;
+    tref[0] = pl.targets[(size_t)0 * n + i]; tref[1] = pl.targets[(size_t)1 * n + i]; tref[2] = pl.targets[(size_t)2 * n + i];
+    yaw_out = yaw;
+    speed_out = sqrtf(vbx * vbx + vby * vby + vbz * vbz);
+    if (o == nullptr) return;
+    int k = 0;
+    o[k++] = m[0] * e.wx + m[3] * e.wy + m[6] * e.wz;
+    o[k++] = m[1] * e.wx + m[4] * e.wy + m[7] * e.wz;
+    o[k++] = m[2] * e.wx + m[5] * e.wy + m[8] * e.wz;
+    o[k++] = roll; o[k++] = pitch; o[k++] = yaw;
+    o[k++] = vbx; o[k++] = vby; o[k++] = vbz;
+    o[k++] = e.px; o[k++] = e.py; o[k++] = e.pz;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) o[k++] = a[c];
+    o[k++] = tref[0]; o[k++] = tref[1]; o[k++] = tref[2];
+}
+
 // end_reset: warmup_substeps substeps at zero setpoint.  Kept out of line: it is the rare path (only when a wind
 // field acts during the warm-up, otherwise resets copy the cached result) and inlining it would duplicate
 // the whole substep body and double the kernel's instruction-cache footprint.
@@ -552,6 +580,15 @@ __device__ __forceinline__ void fw_reset_begin(const FwDev& p, const FwPlanes& p
 
 // WaypointHandler.reset: polar sampling of every target into the planes
 __device__ __forceinline__ void fw_sample_targets(const FwDev& p, const FwPlanes& pl, int i, uint32_t gid, uint32_t episode) {
+    if (p.task == 3) {
+        // FixedwingLowLevelEnv.reset (fixedwing_lowlevel_env.py:87-91): psi_ref ~ U(-pi, pi), h_ref ~ U(5, 20),
+        // V_ref ~ U(10, 20); the tracked reference rides in target slot 0
+        uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid, episode, 0u, FWD_STREAM_TARGETS);
+        pl.targets[(size_t)0 * p.n + i] = -FWD_PI + 2.0f * FWD_PI * fw_u01(r.x);
+        pl.targets[(size_t)1 * p.n + i] = 5.0f + 15.0f * fw_u01(r.y);
+        pl.targets[(size_t)2 * p.n + i] = 10.0f + 10.0f * fw_u01(r.z);
+        return;
+    }
     for (int t = 0; t < p.num_targets; ++t) {
         uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid, episode, (uint32_t)t, FWD_STREAM_TARGETS);
         float st, ct, sp, cp;
@@ -587,7 +624,7 @@ __device__ __forceinline__ void fw_warm(const FwDev& p, EnvState& e, const float
 
 __device__ __forceinline__ void fw_reset_finish(const FwDev& p, const FwPlanes& pl, EnvState& e, int i) {
     e.new_dist = 0.0f;
-    if (p.task != 0 && p.num_targets > 0) {
+    if (p.task != 0 && p.task != 3 && p.num_targets > 0) {
         float dx = pl.targets[(size_t)0 * p.n + i] - e.px;
         float dy = pl.targets[(size_t)1 * p.n + i] - e.py;
         float dz = pl.targets[(size_t)2 * p.n + i] - e.pz;

@@ -142,6 +142,62 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
     return reward;
 }
 
+// FixedwingLowLevelEnv.step (fixedwing_lowlevel_env.py:97-141): six-channel surface/thrust command (Fixedwing mode -1),
+// ONE Aviary.step (2 physics substeps) per env step, psi/h/V tracking reward, altitude-band termination, truncation at
+// `max_steps` (>=); SubprocVecEnv reset-on-done.  No warm-up substeps and no ground-contact / dome test in this env.
+template <bool STD>
+__device__ __forceinline__ float fw_env_step_lowlevel(const FwDev& p, const FwPlanes& pl, EnvState& e, int i, uint32_t gid,
+                                                      const float a[6], const float4& w0_in, const float4& w1_in, float& ep_ret,
+                                                      float* row, float* term_obs_row, uint32_t& bits) {
+    float4 w0 = w0_in, w1 = w1_in;
+    e.step_count += 1;                                   // self._episode_steps += 1
+    float cmd[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) cmd[c] = a[c];             // mode -1: cmd = setpoint
+    bool contact = false;
+    float nn[4] = {0.f, 0.f, 0.f, 0.f};
+    bool have_noise = false;
+    for (int s = 0; s < p.substeps_per_inner; ++s) {
+        const int ps = e.physics_steps;
+        float nz = 0.0f;
+        if (p.noise_ratio > 0.0f) {
+            if (!have_noise || (ps & 3) == 0) { fw_normals4(p, gid, e.episode, (uint32_t)ps >> 2, nn); have_noise = true; }
+            const int q = ps & 3;
+            nz = q == 0 ? nn[0] : (q == 1 ? nn[1] : (q == 2 ? nn[2] : nn[3]));
+        }
+        float wx, wy, wz;
+        fw_wind(p, ps, w0, w1, wx, wy, wz);
+        fw_substep<STD>(p, e, cmd, wx, wy, wz, nz, contact);
+    }
+    float yaw, speed, tref[3];
+    fw_write_obs_lowlevel(pl, e, i, p.n, a, row, yaw, speed, tref);
+    // _wrap_pi with Python's floored modulo
+    float dpsi = tref[0] - yaw + FWD_PI;
+    dpsi -= 2.0f * FWD_PI * floorf(dpsi * (0.5f / FWD_PI));
+    dpsi -= FWD_PI;
+    float reward = -(fabsf(dpsi) + fabsf(tref[1] - e.pz) + 0.5f * fabsf(tref[2] - speed)) + 0.1f;
+    bool term = false, oob = false;
+    if (e.pz < 1.0f || e.pz > 100.0f) { term = true; oob = true; reward -= 100.0f; }
+    const bool trunc = e.step_count >= p.max_steps;
+    ep_ret += reward;
+    if (term || trunc) {
+        if (term_obs_row != nullptr && row != nullptr)
+            for (int k = 0; k < p.obs_dim; ++k) term_obs_row[k] = row[k];
+        atomicAdd(&pl.stats[0], 1.0);
+        atomicAdd(&pl.stats[1], (double)ep_ret);
+        atomicAdd(&pl.stats[2], (double)e.step_count);
+        if (oob) atomicAdd(&pl.stats[5], 1.0);
+        fw_reset_env(p, pl, e, i, gid, e.episode + 1u);
+        if (row != nullptr) {
+            const float z6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            fw_write_obs_lowlevel(pl, e, i, p.n, z6, row, yaw, speed, tref);
+        }
+        ep_ret = 0.0f;
+    }
+    bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (oob ? 8u : 0u);
+    return reward;
+}
+
 // K1.  RANDOM_ACT: actions U(-1,1)^4 from Philox keyed (seed, global env id, episode, step_count); `spl` agent
 // steps per launch with the state held in registers between them (the random-action sweep never needs the
 // intermediate observations, so nothing but the final state goes back to HBM).
@@ -155,7 +211,7 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = p.obs_dim;
     float* stage_warp = stage + (size_t)warp * 32 * D;
-    float* row = (TASK != 0 && obs != nullptr) ? stage_warp + (size_t)lane * D : nullptr;
+    float* row = (TASK != 0 && TASK != 3 && obs != nullptr) ? stage_warp + (size_t)lane * D : nullptr;
 
     if (i < p.i_end) {
         const uint32_t gid = p.env_id0 + (uint32_t)i;
@@ -166,7 +222,27 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
         float ep_ret = pl.ep_ret[i];
         float reward = 0.f;
         uint32_t bits = 0u;
-        if (RANDOM_ACT) {
+        if (TASK == 3) {
+            float* orow = obs != nullptr ? stage_warp + (size_t)lane * D : nullptr;
+            const int nst = RANDOM_ACT ? spl : 1;
+            for (int st = 0; st < nst; ++st) {
+                float a6[6];
+                if (RANDOM_ACT) {
+                    uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid, e.episode, (uint32_t)e.step_count, FWD_STREAM_ACTION);
+                    uint4 r2 = fw_philox(p.seed_lo, p.seed_hi, gid, e.episode, (uint32_t)e.step_count | 0x40000000u, FWD_STREAM_ACTION);
+                    a6[0] = 2.0f * fw_u01(r.x) - 1.0f; a6[1] = 2.0f * fw_u01(r.y) - 1.0f; a6[2] = 2.0f * fw_u01(r.z) - 1.0f;
+                    a6[3] = 2.0f * fw_u01(r.w) - 1.0f; a6[4] = 2.0f * fw_u01(r2.x) - 1.0f; a6[5] = 2.0f * fw_u01(r2.y) - 1.0f;
+                } else {
+                    const float2* af = reinterpret_cast<const float2*>(act) + (size_t)i * 3;     // [N, 6] row-major
+                    const float2 u0 = af[0], u1 = af[1], u2 = af[2];
+                    a6[0] = u0.x; a6[1] = u0.y; a6[2] = u1.x; a6[3] = u1.y; a6[4] = u2.x; a6[5] = u2.y;
+                }
+                if (p.wind_mode != 0 && st > 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
+                reward = fw_env_step_lowlevel<STD>(p, pl, e, i, gid, a6, w0, w1, ep_ret, st == nst - 1 ? orow : nullptr,
+                                                   (!RANDOM_ACT && term_obs != nullptr && orow != nullptr) ? term_obs + (size_t)i * D : nullptr,
+                                                   bits);
+            }
+        } else if (RANDOM_ACT) {
             for (int st = 0; st < spl; ++st) {
                 uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid, e.episode, (uint32_t)e.step_count, FWD_STREAM_ACTION);
                 float a0 = 2.0f * fw_u01(r.x) - 1.0f, a1 = 2.0f * fw_u01(r.y) - 1.0f;
@@ -211,7 +287,11 @@ fw_reset_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const uint8_
             fw_store(pl, i, e);
         }
         // unselected envs re-emit their current observation (last action unknown -> zeros)
-        if (p.task != 0) fw_write_obs(p, pl, e, i, e.tidx, 0.f, 0.f, 0.f, 0.f, row);
+        if (p.task == 3) {
+            const float z6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float yaw, speed, tref[3];
+            fw_write_obs_lowlevel(pl, e, i, p.n, z6, row, yaw, speed, tref);
+        } else if (p.task != 0) fw_write_obs(p, pl, e, i, e.tidx, 0.f, 0.f, 0.f, 0.f, row);
     }
     if (p.task != 0 && obs != nullptr) {
         const int first_env = blockIdx.x * FW_BLOCK + warp * 32;
@@ -493,6 +573,8 @@ typedef void (*fw_step_fn)(const FwDev, const FwPlanes, const float4*, float*, f
 static fw_step_fn step_fn(int task, bool random_act, bool std_geom) {
     if (task == 0 && std_geom) return random_act ? fw_step_kernel<0, true, true> : fw_step_kernel<0, false, true>;
     if (task == 1 && std_geom) return random_act ? fw_step_kernel<1, true, true> : fw_step_kernel<1, false, true>;
+    if (task == 3 && std_geom) return random_act ? fw_step_kernel<3, true, true> : fw_step_kernel<3, false, true>;
+    if (task == 3) return random_act ? fw_step_kernel<3, true, false> : fw_step_kernel<3, false, false>;
     if (task == 0) return random_act ? fw_step_kernel<0, true, false> : fw_step_kernel<0, false, false>;
     if (task == 1) return random_act ? fw_step_kernel<1, true, false> : fw_step_kernel<1, false, false>;
     if (task == 2) return random_act ? fw_step_objlock_kernel<true> : fw_step_objlock_kernel<false>;

@@ -251,6 +251,53 @@ class FixedwingWaypointsEnv:
         raise ValueError("rendering is out of scope for the batched simulator")
 
 
+class FixedwingLowLevelEnv:
+    """Single-env gymnasium view of the low-level tracking task, the interface of
+    envs/fixedwing_envs/fixedwing_lowlevel_env.py:10-163: 6-channel action [left_ail, right_ail, hstab, vstab, flap,
+    thrust] in [-1, 1], 21-float observation, ``info["target"] = [psi_ref, h_ref, V_ref]``."""
+
+    metadata = {"render_modes": [], "name": "fixedwing_lowlevel_env"}
+
+    def __init__(self, render_mode=None, wind_config: dict | None = None, device: int = 0, seed: int = 0):
+        if render_mode is not None:
+            raise ValueError("rendering is out of scope for the batched simulator")
+        self.cfg: EnvConfig = make_config("lowlevel", wind=wind_config)
+        self._vec = FixedwingVecEnv(1, config=self.cfg, device=device, seed=int(seed))
+        self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(21,), dtype=np.float64)
+        self.action_space = spaces.Box(low=-1.0, high=1.0, shape=(6,), dtype=np.float64)
+        self.prev_action = np.zeros(6)
+        self.target = np.zeros(3)
+        self._needs_reset = True
+        self.unwrapped = self
+
+    def reset(self, *, seed: int | None = None, options: dict | None = None):
+        if seed is not None:
+            self._vec.seed(int(seed))
+        obs = self._vec.reset()[0].astype(np.float64)
+        self.prev_action = np.zeros(6)
+        self.target = obs[18:21].copy()
+        self._needs_reset = False
+        return obs, {"target": self.target.copy()}
+
+    def step(self, action):
+        if self._needs_reset:
+            raise RuntimeError("call reset() before step() (the previous episode has ended)")
+        a = np.asarray(action, dtype=np.float32).reshape(1, 6)
+        self.prev_action = a[0].astype(np.float64)
+        obs, rew, flags, term = self._vec.step_arrays(a, want_terminal_obs=True)
+        f = int(flags[0])
+        terminated, truncated = bool(f & FLAG_TERM), bool(f & FLAG_TRUNC)
+        if terminated or truncated:          # the device batch has already auto-reset: hand back the terminal observation
+            self._needs_reset = True
+            out = term[0].astype(np.float64)
+        else:
+            out = obs[0].astype(np.float64)
+        return out, float(rew[0]), terminated, truncated, {"target": self.target.copy()}
+
+    def close(self) -> None:
+        self._vec.close()
+
+
 class FlattenWaypointEnv:
     """Dict -> Box flattening of a waypoints env, as envs/flatten_waypoint_env.py:14-72 (zero padded)."""
 

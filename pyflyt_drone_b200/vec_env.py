@@ -67,9 +67,10 @@ class FixedwingVecEnv:
         _lib.check(self.lib.fw_create(C.byref(self._c_cfg), self.num_envs, self.device_index, self._seed,
                                       self.env_id0, C.byref(self._h)))
         self.obs_dim = int(self.lib.fw_obs_dim(self._h))
+        self.act_dim = int(self.lib.fw_act_dim(self._h))     # 4, or 6 for the low-level task
         D = max(self.obs_dim, 1)
         self.observation_space = spaces.Box(low=-np.inf, high=np.inf, shape=(self.obs_dim,), dtype=np.float32)
-        self.action_space = spaces.Box(low=-1.0, high=1.0, shape=(4,), dtype=np.float32)
+        self.action_space = spaces.Box(low=-1.0, high=1.0, shape=(self.act_dim,), dtype=np.float32)
         # host arrays = NumPy views of the library's pinned staging buffers: the DMA engines read actions from
         # and write observations to the very memory the caller sees (no extra host memcpy on either side)
         ptrs = [C.c_void_p() for _ in range(5)]
@@ -79,7 +80,7 @@ class FixedwingVecEnv:
             n = int(np.prod(shape))
             return np.frombuffer((ctype * n).from_address(ptr.value), dtype=dtype).reshape(shape)
 
-        self._h_act = view(ptrs[0], (self.num_envs, 4), C.c_float, np.float32)
+        self._h_act = view(ptrs[0], (self.num_envs, self.act_dim), C.c_float, np.float32)
         self._h_obs = view(ptrs[1], (self.num_envs, D), C.c_float, np.float32)
         self._h_rew = view(ptrs[2], (self.num_envs,), C.c_float, np.float32)
         self._h_flags = view(ptrs[3], (self.num_envs,), C.c_uint8, np.uint8)
@@ -94,15 +95,15 @@ class FixedwingVecEnv:
         if self._pending is not None:
             raise RuntimeError("step_async called twice without step_wait")
         a = np.ascontiguousarray(actions, dtype=np.float32)
-        if a.shape != (self.num_envs, 4):
-            raise ValueError(f"actions must have shape ({self.num_envs}, 4), got {a.shape}")
+        if a.shape != (self.num_envs, self.act_dim):
+            raise ValueError(f"actions must have shape ({self.num_envs}, {self.act_dim}), got {a.shape}")
         self._pending = a
 
     def step_arrays(self, actions: np.ndarray, want_terminal_obs: bool = True):
         """Host-buffer step without the per-env info dicts: (obs, rewards, flags, terminal_obs).
         The returned arrays are views of pinned memory owned by the env, valid until the next step."""
-        if np.shape(actions) != (self.num_envs, 4):
-            raise ValueError(f"actions must have shape ({self.num_envs}, 4), got {np.shape(actions)}")
+        if np.shape(actions) != (self.num_envs, self.act_dim):
+            raise ValueError(f"actions must have shape ({self.num_envs}, {self.act_dim}), got {np.shape(actions)}")
         # the library stages caller-owned actions into its pinned buffer chunk by chunk, overlapped with the GPU work;
         # actions written straight into ``action_buffer`` skip that copy
         a = actions if (isinstance(actions, np.ndarray) and actions.dtype == np.float32 and actions.flags.c_contiguous) \
@@ -226,8 +227,8 @@ class FixedwingVecEnv:
         """actions: CUDA float32 [N,4] contiguous.  Returns views of persistent CUDA tensors
         (obs, reward, flags[, terminal_obs]); valid until the next call.  No host sync."""
         t = self._tensors()
-        if actions.dtype is not t["obs"].dtype or not actions.is_contiguous() or tuple(actions.shape) != (self.num_envs, 4):
-            raise ValueError("actions must be a contiguous CUDA float32 tensor of shape (num_envs, 4)")
+        if actions.dtype is not t["obs"].dtype or not actions.is_contiguous() or tuple(actions.shape) != (self.num_envs, self.act_dim):
+            raise ValueError(f"actions must be a contiguous CUDA float32 tensor of shape (num_envs, {self.act_dim})")
         _lib.check(self.lib.fw_step(
             self._h, C.c_void_p(actions.data_ptr()), C.c_void_p(t["obs"].data_ptr()) if self.obs_dim else None,
             C.c_void_p(t["rew"].data_ptr()), C.c_void_p(t["flags"].data_ptr()),

@@ -61,7 +61,7 @@ def test_dense_reward_accumulates_over_four_inner_iterations(fo):
     obs, rew, flags, _ = env.step(ZERO)
     L = fo.lib()
     clone.setpoint[3] = 0.5
-    clone.last_action[:] = [0.0] * 4
+    clone.last_action[:] = [0.0] * 6
     expect = -0.1
     for _ in range(4):
         clone.contact = 0

@@ -67,3 +67,27 @@ def test_objlock_env_dict_observation():
     o, r, term, trunc, info = env.step(np.zeros(4))
     assert np.isfinite(r)
     env.close()
+
+
+def test_lowlevel_gym_view_matches_the_reference_interface():
+    """envs/fixedwing_envs/fixedwing_lowlevel_env.py: Box(21) obs, Box(6) action, info["target"], 2000-step truncation."""
+    from pyflyt_drone_b200.gym_env import FixedwingLowLevelEnv
+    env = FixedwingLowLevelEnv(seed=3)
+    assert env.observation_space.shape == (21,) and env.action_space.shape == (6,)
+    obs, info = env.reset(seed=3)
+    assert obs.shape == (21,) and np.allclose(obs[9:12], [0, 0, 10.0]) and np.allclose(info["target"], obs[18:21])
+    a = np.array([0.1, -0.1, 0.2, 0.0, 0.0, 0.7])
+    total, steps = 0.0, 0
+    while True:
+        obs, r, term, trunc, info = env.step(a)
+        total += r; steps += 1
+        assert np.allclose(obs[12:18], a, atol=1e-6) and np.allclose(obs[18:21], info["target"])
+        if term or trunc:
+            break
+        assert 1.0 <= obs[11] <= 100.0
+    assert steps <= 2000 and (trunc == (steps == 2000) or term)
+    if term:
+        assert obs[11] < 1.0 or obs[11] > 100.0
+    with pytest.raises(RuntimeError):
+        env.step(a)
+    env.close()
