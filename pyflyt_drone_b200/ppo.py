@@ -227,6 +227,9 @@ class PPO:
         self.device = torch.device("cuda", env.device_index)
         self.lib = _lib.load()
         self.n_envs, self.d = env.num_envs, env.obs_dim
+        if getattr(env, "act_dim", A) != A:
+            raise ValueError(f"the PPO kernels are built for {A}-channel actions (MlpPolicy of the Waypoints / ObjLock "
+                             f"scripts); this env has {env.act_dim}")
         self.n_steps, self.batch_size, self.n_epochs = int(n_steps), int(batch_size), int(n_epochs)
         self.gamma, self.gae_lambda, self.clip_range = float(gamma), float(gae_lambda), float(clip_range)
         self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), float(max_grad_norm)
