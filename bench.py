@@ -79,7 +79,8 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clocks / throttle reasons during the timed region (the quantities of the B200_PROFILING.md nvidia-smi recipe,
+    read through NVML when nvidia_ml_py is importable, else by polling nvidia-smi)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -89,8 +90,38 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
 
+    def _nvml(self):
+        """Fast path: NVML through nvidia_ml_py (sub-millisecond per sample, so a 40 ms timed region still gets tens of
+        samples); None when the module or the device is not available -> nvidia-smi polling."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                    ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                    ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+
+            def sample():
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                return [str(sm), str(mx), "0"] + ["Active" if (r & b) else "Not Active" for _, b in bits]
+            sample()
+            return sample
+        except Exception:
+            return None
+
     def run(self):
+        sample = self._nvml()
         while not self._stop_evt.is_set():
+            if sample is not None:
+                try:
+                    self.samples.append(sample())
+                except Exception:
+                    pass
+                self._stop_evt.wait(0.002)
+                continue
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
@@ -244,6 +275,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     FixedwingVecEnv.rollout_random(envs, K, spl, use_graph=not args.no_graph)
     e1.record()
     barrier()
+    clocks = sampler.stop() if sampler else None       # sampled during the timed region only
     ms = e0.elapsed_time(e1)
     launches = sum(e.launch_count for e in envs) - launches0
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
@@ -273,7 +305,6 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     e2e_value = N * args.e2e_steps * world / float(t.item())
     h2d = N * 4 * 4
     d2h = N * venv.obs_dim * 4 + N * 4 + N
-    clocks = sampler.stop() if sampler else None
 
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
