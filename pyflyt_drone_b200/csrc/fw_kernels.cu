@@ -610,26 +610,6 @@ cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* dep, const
     return cudaGraphAddKernelNode(out, g, dep, dep ? 1 : 0, &kp);
 }
 
-// Append one policy-action step launch over [p.i_begin, p.i_end) to a CUDA graph (the host lane's per-step graph).
-cudaError_t fwk_graph_add_step(cudaGraph_t g, const cudaGraphNode_t* deps, int ndeps, const FwDev& p, const FwPlanes& pl,
-                               const float* act_, float* obs_, float* rew_, uint8_t* flg_, float* term_, cudaGraphNode_t* out) {
-    fw_step_fn fn = step_fn(p.task, false, p.std_geom != 0);
-    if (fn == nullptr) return cudaErrorNotSupported;
-    FwDev pc = p; FwPlanes plc = pl;
-    const float4* act = reinterpret_cast<const float4*>(act_);
-    float* obs = obs_; float* rew = rew_; uint8_t* flg = flg_; float* term = term_;
-    int spl_ = 1;
-    int bulk = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) && ((p.obs_dim * 128) % 16 == 0);
-    void* args[] = {&pc, &plc, &act, &obs, &rew, &flg, &term, &spl_, &bulk};
-    cudaKernelNodeParams kp;
-    memset(&kp, 0, sizeof(kp));
-    kp.func = (void*)fn;
-    kp.gridDim = dim3(grid_for(p.i_end - p.i_begin)); kp.blockDim = dim3(FW_BLOCK);
-    kp.sharedMemBytes = (unsigned)stage_bytes(p);
-    kp.kernelParams = args; kp.extra = nullptr;
-    return cudaGraphAddKernelNode(out, g, deps, ndeps, &kp);
-}
-
 cudaError_t fwk_launch_reset(const FwDev& p, const FwPlanes& pl, const uint8_t* mask, float* obs, bool emit_only,
                              cudaStream_t st) {
     const int bulk_ok = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0);

@@ -10,8 +10,6 @@ cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act
                             float* term_obs, bool random_act, int spl, cudaStream_t st);
 cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* dep, const FwDev& p, const FwPlanes& pl, int spl,
                                       cudaGraphNode_t* out);
-cudaError_t fwk_graph_add_step(cudaGraph_t g, const cudaGraphNode_t* deps, int ndeps, const FwDev& p, const FwPlanes& pl,
-                               const float* act, float* obs, float* rew, uint8_t* flg, float* term, cudaGraphNode_t* out);
 cudaError_t fwk_launch_reset(const FwDev& p, const FwPlanes& pl, const uint8_t* mask, float* obs, bool emit_only,
                              cudaStream_t st);
 cudaError_t fwk_launch_warm(const FwDev& p, const FwPlanes& pl, float* out, cudaStream_t st);
