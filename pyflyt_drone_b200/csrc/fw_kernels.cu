@@ -23,7 +23,9 @@
 #define FW_BLOCK 64
 // 8 resident blocks/SM x 64 threads x 128 registers = the whole 64K register file: 148 x 512 = 75,776 >= 65,536
 // envs, so a 64K-env launch is a single wave
+#ifndef FW_MIN_BLOCKS
 #define FW_MIN_BLOCKS 8
+#endif
 
 __device__ __forceinline__ uint32_t fw_smem_addr(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
