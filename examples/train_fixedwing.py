@@ -77,6 +77,12 @@ def main():
             os.makedirs(cfg["model_dir"], exist_ok=True)
             model.save(os.path.join(cfg["model_dir"], "final_model.pt"))
             print("saved", os.path.join(cfg["model_dir"], "final_model.pt"))
+            paths = model.export_sb3(os.path.join(cfg["model_dir"], "sb3_export"))      # policy.pth + vecnorm.npz for SB3
+            print("exported", paths)
+            # the reference's eval flow (eval/eval_waypoints.py): frozen statistics, raw returns, deterministic actions
+            mean_r, std_r, mean_len, targets = model.evaluate_policy(n_eval_episodes=100)
+            print(f"evaluation over 100 episodes: reward {mean_r:.2f} +/- {std_r:.2f}, length {mean_len:.1f}, "
+                  f"targets reached per episode {targets:.2f}")
         env.close()
         if world > 1:
             dist.destroy_process_group()

@@ -465,6 +465,48 @@ class PPO:
                                                int(deterministic), None, _p(act), None, None, _p(val), _stream()))
         return act
 
+    def evaluate_policy(self, env=None, n_eval_episodes: int = 100, deterministic: bool = True, max_steps: int | None = None):
+        """stable_baselines3.common.evaluation.evaluate_policy as the reference uses it (eval/eval_waypoints.py:96-160,
+        WaypointEvalCallback in train_Fixedwing_Waypoints_v3.py:163-172): frozen VecNormalize statistics, raw (un-normalised)
+        rewards, deterministic actions by default.  Runs every env of ``env`` (default: the training env's configuration
+        on a fresh batch) on the device until ``n_eval_episodes`` episodes have finished; returns
+        ``(mean_reward, std_reward, mean_length, mean_targets_reached)`` over the first episodes to finish."""
+        from .vec_env import FixedwingVecEnv
+        own = env is None
+        if own:
+            n = min(self.n_envs, max(64, int(n_eval_episodes)))
+            env = FixedwingVecEnv(n, config=self.env.cfg, device=self.env.device_index, seed=self.seed + 7919,
+                                  env_id0=self.env.env_id0 + (1 << 24))
+        obs = env.reset_tensor()
+        n = env.num_envs
+        ret = torch.zeros(n, dtype=torch.float64, device=self.device)
+        length = torch.zeros(n, dtype=torch.int64, device=self.device)
+        done_ret, done_len = [], []
+        have = 0
+        limit = max_steps if max_steps is not None else 4 * int(env.cfg.max_steps) + 8
+        for _ in range(limit):
+            act = self.predict(obs, deterministic=deterministic)
+            obs, rew, flags = env.step_tensor(act)
+            ret += rew.double()
+            length += 1
+            fin = (flags & 3) != 0
+            k = int(fin.sum())
+            if k:
+                done_ret.append(ret[fin].clone()); done_len.append(length[fin].clone())
+                ret[fin] = 0.0; length[fin] = 0
+                have += k
+                if have >= n_eval_episodes:
+                    break
+        stats = env.episode_stats()
+        if own:
+            env.close()
+        if not done_ret:
+            return float("nan"), float("nan"), float("nan"), float("nan")
+        r = torch.cat(done_ret)[:n_eval_episodes]
+        ln = torch.cat(done_len)[:n_eval_episodes].double()
+        targets = stats["targets_reached_sum"] / max(stats["episodes"], 1.0)
+        return float(r.mean()), float(r.std(unbiased=False)), float(ln.mean()), float(targets)
+
     def save(self, path: str) -> None:
         torch.save({"policy": self.policy.state_dict(), "optimizer": self.optimizer.state_dict(),
                     "adam": {"m": self._adam_m.clone(), "v": self._adam_v.clone(), "t": int(self._adam_t.item())},

@@ -348,3 +348,26 @@ class FlatInit:
     def theta(d, seed):
         from pyflyt_drone_b200.ppo import FlatMlpPolicy
         return FlatMlpPolicy(d, torch.device("cuda", 0), seed=seed).theta.detach()
+
+
+def test_evaluate_policy_reports_raw_episode_returns():
+    """The reference's eval flow (eval/eval_waypoints.py:96-160): frozen statistics, raw rewards, deterministic policy.
+    On the sparse Waypoints task the first thing PPO learns is to stay in the air (the return first DROPS: -0.1 per
+    step for many more steps), then to reach waypoints: a briefly trained policy must fly much longer and reach more
+    waypoints than the random-initialised one, and evaluation must not touch the training statistics."""
+    from pyflyt_drone_b200.ppo import PPO
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    env = FixedwingVecEnv(2048, preset="waypoints_v3", seed=21)
+    m = PPO("MlpPolicy", env, n_steps=64, batch_size=2048 * 16, n_epochs=10, seed=21)
+    r0, s0, l0, t0 = m.evaluate_policy(n_eval_episodes=256)
+    assert np.isfinite([r0, s0, l0, t0]).all() and l0 >= 1 and r0 < 0          # an untrained policy crashes: -100 - 0.1/step
+    count = float(m.vecnorm.obs_stats[-1])
+    m.learn(40 * 64 * 2048)
+    before = m.vecnorm.obs_stats.clone()
+    r1, s1, l1, t1 = m.evaluate_policy(n_eval_episodes=256)
+    assert torch.equal(before, m.vecnorm.obs_stats)                             # env.training = False
+    assert float(m.vecnorm.obs_stats[-1]) > count
+    print(f"\n[evaluate_policy] untrained: return {r0:.1f} +- {s0:.1f}, length {l0:.0f}, targets {t0:.3f}; after 5.2 M steps: "
+          f"return {r1:.1f} +- {s1:.1f}, length {l1:.0f}, targets {t1:.3f}")
+    assert l1 > 1.3 * l0 and t1 > 1.5 * t0, (r0, r1, l0, l1, t0, t1)
+    env.close()
