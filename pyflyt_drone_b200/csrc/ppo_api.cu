@@ -31,9 +31,56 @@ static int check_d(int d) {
     return FW_OK;
 }
 
-extern "C" int ppo_param_count(int32_t d) {
-    const int H = PPO_HIDDEN, A = PPO_ACT;
-    return (H * d + H + H * H + H + A * H + A) + (H * d + H + H * H + H + H + 1) + A;
+static int check_a(int a) {
+    if (a != 4 && a != 6) return pfail(FW_EINVAL, "action width %d not supported (4 or 6)", a);
+    return 0;
+}
+
+extern "C" int ppo_param_count_a(int32_t d, int32_t a) {
+    const int H = PPO_HIDDEN;
+    return (H * d + H + H * H + H + a * H + a) + (H * d + H + H * H + H + H + 1) + a;
+}
+extern "C" int ppo_param_count(int32_t d) { return ppo_param_count_a(d, PPO_ACT); }
+
+extern "C" int ppo_policy_forward_a(const float* params, int32_t d, int32_t a, const float* obs_raw, const double* obs_stats,
+                                    float clip_obs, int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step,
+                                    const uint32_t* step_dev, int32_t deterministic, float* obs_norm, float* act_env,
+                                    float* act_raw, float* logp, float* value, void* stream) {
+    if (!params || !obs_raw || !act_env || !value) return pfail(FW_EINVAL, "null argument");
+    if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
+    int rc = check_d(d);
+    if (rc) return rc;
+    if ((rc = check_a(a)) != 0) return rc;
+    if ((reinterpret_cast<uintptr_t>(act_env) & 15u) || (act_raw && (reinterpret_cast<uintptr_t>(act_raw) & 15u)))
+        return pfail(FW_EINVAL, "action buffers must be 16-byte aligned");
+    PCU(ppok_forward(params, d, obs_raw, obs_stats, clip_obs, n, seed, env_id0, step, step_dev, deterministic, obs_norm,
+                     act_env, act_raw, logp, value, 1, (cudaStream_t)stream, nullptr, 0.0f, nullptr, a));
+    return FW_OK;
+}
+
+extern "C" int ppo_value_forward_a(const float* params, int32_t d, int32_t a, const float* obs_raw, const double* obs_stats,
+                                   float clip_obs, int32_t n, float* value, void* stream) {
+    if (!params || !obs_raw || !value) return pfail(FW_EINVAL, "null argument");
+    if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
+    int rc = check_d(d);
+    if (rc) return rc;
+    if ((rc = check_a(a)) != 0) return rc;
+    PCU(ppok_forward(params, d, obs_raw, obs_stats, clip_obs, n, 0, 0, 0, nullptr, 1, nullptr, nullptr, nullptr, nullptr,
+                     value, 0, (cudaStream_t)stream, nullptr, 0.0f, nullptr, a));
+    return FW_OK;
+}
+
+extern "C" int ppo_timeout_bootstrap_a(const float* params, int32_t d, int32_t a, const float* term_obs_raw,
+                                       const double* obs_stats, float clip_obs, const uint8_t* flags, int32_t n, float gamma,
+                                       float* rew_inout, void* stream) {
+    if (!params || !term_obs_raw || !flags || !rew_inout) return pfail(FW_EINVAL, "null argument");
+    if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
+    int rc = check_d(d);
+    if (rc) return rc;
+    if ((rc = check_a(a)) != 0) return rc;
+    PCU(ppok_bootstrap(params, d, term_obs_raw, obs_stats, clip_obs, flags, n, gamma, rew_inout, nullptr,
+                       (cudaStream_t)stream, a));
+    return FW_OK;
 }
 
 extern "C" int ppo_moments_update(const float* x, int32_t n, int32_t d, double* stats, double* scratch, double* accum,

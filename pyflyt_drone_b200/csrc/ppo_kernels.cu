@@ -125,6 +125,8 @@ __device__ __forceinline__ void stage_stats(const double* __restrict__ stats, in
 }
 
 // ------------------------------------------------------------------ K4: policy + value forward, one thread per env
+// AO = action width: 4 (roll, pitch, yaw, thrust) or 6 (the low-level env's surface / thrust channels)
+template <int AO>
 __global__ void __launch_bounds__(PPO_FWD_THREADS)
 ppo_forward_kernel(const float* __restrict__ params, int d, const float* __restrict__ obs_raw,
                    const double* __restrict__ stats, float clip, int n, uint32_t seed_lo, uint32_t seed_hi,
@@ -143,17 +145,17 @@ ppo_forward_kernel(const float* __restrict__ params, int d, const float* __restr
         if (!__syncthreads_or(boot_need ? 1 : 0)) return;
     }
     float* s_pi = smem;
-    float* s_vf = s_pi + TowerOff<A>::SIZE;
+    float* s_vf = s_pi + TowerOff<AO>::SIZE;
     float* s_mean = s_vf + TowerOff<1>::SIZE;
     float* s_istd = s_mean + DP;
     float* s_logstd = s_istd + DP;
-    float* hbuf = s_logstd + 4;
-    const int pi_count = H * d + H + H * H + H + A * H + A;
+    float* hbuf = s_logstd + 8;
+    const int pi_count = H * d + H + H * H + H + AO * H + AO;
     const int vf_count = H * d + H + H * H + H + H + 1;
-    if (want_policy) load_tower<A>(s_pi, params, d);
+    if (want_policy) load_tower<AO>(s_pi, params, d);
     load_tower<1>(s_vf, params + pi_count, d);
     stage_stats(stats, d, s_mean, s_istd);
-    if (threadIdx.x < A) s_logstd[threadIdx.x] = params[pi_count + vf_count + threadIdx.x];
+    if (threadIdx.x < AO) s_logstd[threadIdx.x] = params[pi_count + vf_count + threadIdx.x];
     __syncthreads();
 
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -168,55 +170,78 @@ ppo_forward_kernel(const float* __restrict__ params, int d, const float* __restr
     }
     value[row] = v[0];
     if (!want_policy) return;
-    float mean[A];
-    tower_forward<A>(s_pi, x, hbuf, mean);
+    float mean[AO];
+    tower_forward<AO>(s_pi, x, hbuf, mean);
     // diagonal Gaussian: a = mu + sigma * eps ; log pi(a) = sum -0.5 eps^2 - log sigma - 0.5 log 2pi
     const uint32_t step_eff = step + (step_dev != nullptr ? step_dev[0] : 0u);   // device counter: graph-replayable
-    uint4 r = ppo_philox(seed_lo, seed_hi, env_id0 + (uint32_t)row, step_eff, 0u, 7u);
-    float ra = sqrtf(-2.0f * __logf(ppo_u01(r.x))), rb = sqrtf(-2.0f * __logf(ppo_u01(r.z)));
-    float s0, c0, s1, c1;
-    sincospif(2.0f * ppo_u01(r.y), &s0, &c0);
-    sincospif(2.0f * ppo_u01(r.w), &s1, &c1);
-    float eps[A] = {ra * c0, ra * s0, rb * c1, rb * s1};
-    float lp = 0.0f;
-    float4 ae, ar;
-    float av[A];
+    float eps[AO];
 #pragma unroll
-    for (int a = 0; a < A; ++a) {
+    for (int g = 0; g < (AO + 3) / 4; ++g) {          // four normals per Philox call; channels 4.. use counter word 2 = 1
+        uint4 r = ppo_philox(seed_lo, seed_hi, env_id0 + (uint32_t)row, step_eff, (uint32_t)g, 7u);
+        float ra = sqrtf(-2.0f * __logf(ppo_u01(r.x))), rb = sqrtf(-2.0f * __logf(ppo_u01(r.z)));
+        float s0, c0, s1, c1;
+        sincospif(2.0f * ppo_u01(r.y), &s0, &c0);
+        sincospif(2.0f * ppo_u01(r.w), &s1, &c1);
+        const float e4[4] = {ra * c0, ra * s0, rb * c1, rb * s1};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (4 * g + k < AO) eps[4 * g + k] = e4[k];
+    }
+    float lp = 0.0f;
+    float av[AO], ac[AO];
+#pragma unroll
+    for (int a = 0; a < AO; ++a) {
         float ls = s_logstd[a];
         float e = deterministic ? 0.0f : eps[a];
         av[a] = fmaf(__expf(ls), e, mean[a]);
+        ac[a] = fminf(fmaxf(av[a], -1.f), 1.f);
         lp += -0.5f * e * e - ls - 0.91893853320467274178f;
     }
-    ar = make_float4(av[0], av[1], av[2], av[3]);
-    ae = make_float4(fminf(fmaxf(av[0], -1.f), 1.f), fminf(fmaxf(av[1], -1.f), 1.f),
-                     fminf(fmaxf(av[2], -1.f), 1.f), fminf(fmaxf(av[3], -1.f), 1.f));
-    reinterpret_cast<float4*>(act_env)[row] = ae;
-    if (act_raw != nullptr) reinterpret_cast<float4*>(act_raw)[row] = ar;
+    // rows are AO floats wide: 8-byte aligned for the even widths supported
+#pragma unroll
+    for (int a = 0; a < AO; a += 2) {
+        reinterpret_cast<float2*>(act_env + (size_t)row * AO)[a / 2] = make_float2(ac[a], ac[a + 1]);
+        if (act_raw != nullptr) reinterpret_cast<float2*>(act_raw + (size_t)row * AO)[a / 2] = make_float2(av[a], av[a + 1]);
+    }
     if (logp != nullptr) logp[row] = lp;
 }
 
-size_t ppo_forward_smem() {
-    return (size_t)(TowerOff<A>::SIZE + TowerOff<1>::SIZE + 2 * DP + 4 + H * PPO_FWD_THREADS) * sizeof(float);
+template <int AO>
+static size_t ppo_forward_smem_t() {
+    return (size_t)(TowerOff<AO>::SIZE + TowerOff<1>::SIZE + 2 * DP + 8 + H * PPO_FWD_THREADS) * sizeof(float);
+}
+size_t ppo_forward_smem() { return ppo_forward_smem_t<A>(); }
+
+template <int AO>
+static cudaError_t ppok_forward_t(const float* params, int d, const float* obs_raw, const double* stats, float clip, int n,
+                                  uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev, int deterministic,
+                                  float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, int want_policy,
+                                  cudaStream_t st, const uint8_t* boot_flags, float boot_gamma, float* boot_rew) {
+    static bool attr_set = false;
+    const size_t sm = ppo_forward_smem_t<AO>();
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(ppo_forward_kernel<AO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int grid = (n + PPO_FWD_THREADS - 1) / PPO_FWD_THREADS;
+    ppo_forward_kernel<AO><<<grid, PPO_FWD_THREADS, sm, st>>>(params, d, obs_raw, stats, clip, n, (uint32_t)(seed & 0xffffffffu),
+                                                              (uint32_t)(seed >> 32), env_id0, step, step_dev, deterministic,
+                                                              obs_norm, act_env, act_raw, logp, value, want_policy, boot_flags,
+                                                              boot_gamma, boot_rew);
+    return cudaGetLastError();
 }
 
 cudaError_t ppok_forward(const float* params, int d, const float* obs_raw, const double* stats, float clip, int n,
                          uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev, int deterministic,
                          float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, int want_policy,
-                         cudaStream_t st, const uint8_t* boot_flags, float boot_gamma, float* boot_rew) {
-    static bool attr_set = false;
-    const size_t sm = ppo_forward_smem();
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ppo_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    const int grid = (n + PPO_FWD_THREADS - 1) / PPO_FWD_THREADS;
-    ppo_forward_kernel<<<grid, PPO_FWD_THREADS, sm, st>>>(params, d, obs_raw, stats, clip, n, (uint32_t)(seed & 0xffffffffu),
-                                                          (uint32_t)(seed >> 32), env_id0, step, step_dev, deterministic, obs_norm,
-                                                          act_env, act_raw, logp, value, want_policy, boot_flags, boot_gamma,
-                                                          boot_rew);
-    return cudaGetLastError();
+                         cudaStream_t st, const uint8_t* boot_flags, float boot_gamma, float* boot_rew, int a) {
+    if (a == 4)
+        return ppok_forward_t<4>(params, d, obs_raw, stats, clip, n, seed, env_id0, step, step_dev, deterministic, obs_norm,
+                                 act_env, act_raw, logp, value, want_policy, st, boot_flags, boot_gamma, boot_rew);
+    if (a == 6)
+        return ppok_forward_t<6>(params, d, obs_raw, stats, clip, n, seed, env_id0, step, step_dev, deterministic, obs_norm,
+                                 act_env, act_raw, logp, value, want_policy, st, boot_flags, boot_gamma, boot_rew);
+    return cudaErrorInvalidValue;
 }
 
 // ------------------------------------------------------------------ K7: running moments (RunningMeanStd.update)
@@ -355,10 +380,10 @@ cudaError_t ppok_reward_normalize(const float* rew, const uint8_t* flags, int n,
 // bootstrap mode (blocks without such a row exit before staging the weights; a masked per-row MLP reading weights
 // from global memory measured 100+ us per step during a truncation burst, the unmasked forward 80 us on every step).
 cudaError_t ppok_bootstrap(const float* params, int d, const float* term_obs, const double* stats, float clip,
-                           const uint8_t* flags, int n, float gamma, float* rew, float* value_scratch, cudaStream_t st) {
+                           const uint8_t* flags, int n, float gamma, float* rew, float* value_scratch, cudaStream_t st, int a) {
     (void)value_scratch;
     return ppok_forward(params, d, term_obs, stats, clip, n, 0, 0, 0, nullptr, 1, nullptr, nullptr, nullptr, nullptr,
-                        nullptr, 0, st, flags, gamma, rew);
+                        nullptr, 0, st, flags, gamma, rew, a);
 }
 
 // ------------------------------------------------------------------ minibatch permutation

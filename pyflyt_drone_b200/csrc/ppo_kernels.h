@@ -12,7 +12,7 @@ cudaError_t ppok_forward(const float* params, int d, const float* obs_raw, const
                          uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev, int deterministic,
                          float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, int want_policy,
                          cudaStream_t st, const uint8_t* boot_flags = nullptr, float boot_gamma = 0.0f,
-                         float* boot_rew = nullptr);
+                         float* boot_rew = nullptr, int a = PPO_A);
 cudaError_t ppok_counter_add(uint32_t* ctr, uint32_t inc, cudaStream_t st);
 cudaError_t ppok_permutation(long long* out, long long n, uint64_t seed, uint64_t epoch, cudaStream_t st);
 cudaError_t ppok_moments(const float* x, int n, int d, double* stats, double* scratch, double* accum, cudaStream_t st);
@@ -20,7 +20,8 @@ cudaError_t ppok_reward_normalize(const float* rew, const uint8_t* flags, int n,
                                   double* ret_stats, double* scratch, double* accum, float* rew_norm, float* done_out,
                                   cudaStream_t st);
 cudaError_t ppok_bootstrap(const float* params, int d, const float* term_obs, const double* stats, float clip,
-                           const uint8_t* flags, int n, float gamma, float* rew, float* value_scratch, cudaStream_t st);
+                           const uint8_t* flags, int n, float gamma, float* rew, float* value_scratch, cudaStream_t st,
+                           int a = PPO_A);
 cudaError_t ppok_gae(const float* rewards, const float* values, const float* dones, const float* last_values, int T, int n,
                      float gamma, float lam, float* adv, float* ret, cudaStream_t st);
 cudaError_t ppok_forward_tc(const float* params, int d, const float* obs_raw, const double* stats, float clip, int n,

@@ -60,15 +60,18 @@ class FlatMlpPolicy:
     """SB3 ``MlpPolicy`` (separate pi / vf towers [64, 64], tanh, state-independent log_std) stored as ONE flat
     fp32 parameter vector in the layout of include/fwppo.h."""
 
-    def __init__(self, obs_dim: int, device: torch.device, seed: int = 0):
+    def __init__(self, obs_dim: int, device: torch.device, seed: int = 0, act_dim: int = A):
         self.d = int(obs_dim)
+        self.a = int(act_dim)
         self.device = device
         lib = _lib.load()
-        self.count = int(lib.ppo_param_count(self.d))
+        self.count = int(lib.ppo_param_count_a(self.d, self.a))
+        if self.count <= 0 or self.a not in (4, 6):
+            raise ValueError(f"unsupported action width {self.a} (4 or 6)")
         shapes = [("pi.0.weight", (H, self.d)), ("pi.0.bias", (H,)), ("pi.2.weight", (H, H)), ("pi.2.bias", (H,)),
-                  ("action_net.weight", (A, H)), ("action_net.bias", (A,)),
+                  ("action_net.weight", (self.a, H)), ("action_net.bias", (self.a,)),
                   ("vf.0.weight", (H, self.d)), ("vf.0.bias", (H,)), ("vf.2.weight", (H, H)), ("vf.2.bias", (H,)),
-                  ("value_net.weight", (1, H)), ("value_net.bias", (1,)), ("log_std", (A,))]
+                  ("value_net.weight", (1, H)), ("value_net.bias", (1,)), ("log_std", (self.a,))]
         self.slices, off = {}, 0
         for name, shp in shapes:
             n = int(np.prod(shp))
@@ -227,23 +230,23 @@ class PPO:
         self.device = torch.device("cuda", env.device_index)
         self.lib = _lib.load()
         self.n_envs, self.d = env.num_envs, env.obs_dim
-        if getattr(env, "act_dim", A) != A:
-            raise ValueError(f"the PPO kernels are built for {A}-channel actions (MlpPolicy of the Waypoints / ObjLock "
-                             f"scripts); this env has {env.act_dim}")
+        self.a = int(getattr(env, "act_dim", A))
+        if self.a not in (4, 6):
+            raise ValueError(f"PPO supports 4- or 6-channel actions; this env has {self.a}")
         self.n_steps, self.batch_size, self.n_epochs = int(n_steps), int(batch_size), int(n_epochs)
         self.gamma, self.gae_lambda, self.clip_range = float(gamma), float(gae_lambda), float(clip_range)
         self.ent_coef, self.vf_coef, self.max_grad_norm = float(ent_coef), float(vf_coef), float(max_grad_norm)
         self.seed, self.verbose = int(seed), verbose
-        self.policy = FlatMlpPolicy(self.d, self.device, seed=seed)
+        self.policy = FlatMlpPolicy(self.d, self.device, seed=seed, act_dim=self.a)
         self.optimizer = torch.optim.Adam([self.policy.theta], lr=learning_rate, eps=1e-5)   # SB3 default eps
         self.vecnorm = DeviceVecNormalize(self.d, self.n_envs, self.device, norm_obs=normalize,
                                           norm_reward=normalize and norm_reward, clip_obs=clip_obs, gamma=gamma)
         T, N, D = self.n_steps, self.n_envs, self.d
         f32 = dict(dtype=torch.float32, device=self.device)
-        self.buf = dict(obs=torch.zeros((T, N, D), **f32), act=torch.zeros((T, N, A), **f32),
+        self.buf = dict(obs=torch.zeros((T, N, D), **f32), act=torch.zeros((T, N, self.a), **f32),
                         rew=torch.zeros((T, N), **f32), done=torch.zeros((T, N), **f32), val=torch.zeros((T, N), **f32),
                         logp=torch.zeros((T, N), **f32), adv=torch.zeros((T, N), **f32), ret=torch.zeros((T, N), **f32))
-        self.act_env = torch.zeros((N, A), **f32)
+        self.act_env = torch.zeros((N, self.a), **f32)
         self.last_values = torch.zeros(N, **f32)
         self._vterm = torch.zeros(N, **f32)
         self.num_timesteps = 0
@@ -251,6 +254,12 @@ class PPO:
         if update not in ("kernel", "torch"):
             raise ValueError("update must be 'kernel' (hand-written tcgen05 kernels) or 'torch' (autograd reference)")
         self.update = update
+        if self.a != A:
+            # The tensor-core forward (K4) and the fused update (K6) are built for the 4-channel policies of the
+            # Waypoints / ObjLock scripts.  Six-channel policies (train_lowlevel_cmd.py) roll out with the CUDA-core
+            # forward kernel and update through the torch autograd path.
+            self.update = "torch"
+            tensor_core_forward = False
         P = self.policy.count
         self._ws = torch.zeros(int(self.lib.ppo_update_workspace_floats(self.d)), **f32)
         self._grad = torch.zeros(P, **f32)
@@ -286,6 +295,12 @@ class PPO:
 
     def _forward(self, obs_raw, t, deterministic=False):
         b = self.buf
+        if self.a != A:
+            _lib.check(self.lib.ppo_policy_forward_a(
+                _p(self.policy.theta), self.d, self.a, _p(obs_raw), self._stats_ptr(), self.vecnorm.clip_obs, self.n_envs,
+                self.seed, self.env.env_id0, t, _p(self._step_dev), int(deterministic), _p(b["obs"][t]), _p(self.act_env),
+                _p(b["act"][t]), _p(b["logp"][t]), _p(b["val"][t]), _stream()))
+            return
         fwd = self.lib.ppo_policy_forward_tc if self.tensor_core_forward else self.lib.ppo_policy_forward
         _lib.check(fwd(
             _p(self.policy.theta), self.d, _p(obs_raw), self._stats_ptr(), self.vecnorm.clip_obs, self.n_envs, self.seed,
@@ -334,13 +349,13 @@ class PPO:
             else:
                 b["rew"][t].copy_(rew)
                 b["done"][t].copy_((flags & 3) != 0)
-            _lib.check(self.lib.ppo_timeout_bootstrap(_p(self.policy.theta), self.d, _p(term), self._stats_ptr(), vn.clip_obs,
-                                                      _p(flags), self.n_envs, self.gamma, _p(b["rew"][t]), _p(self._vterm),
-                                                      _stream()))
+            _lib.check(self.lib.ppo_timeout_bootstrap_a(_p(self.policy.theta), self.d, self.a, _p(term), self._stats_ptr(),
+                                                        vn.clip_obs, _p(flags), self.n_envs, self.gamma, _p(b["rew"][t]),
+                                                        _stream()))
             self._obs = obs
         _lib.check(self.lib.ppo_counter_add(_p(self._step_dev), self.n_steps, _stream()))
-        _lib.check(self.lib.ppo_value_forward(_p(self.policy.theta), self.d, _p(self._obs), self._stats_ptr(), vn.clip_obs,
-                                              self.n_envs, _p(self.last_values), _stream()))
+        _lib.check(self.lib.ppo_value_forward_a(_p(self.policy.theta), self.d, self.a, _p(self._obs), self._stats_ptr(),
+                                                vn.clip_obs, self.n_envs, _p(self.last_values), _stream()))
         _lib.check(self.lib.ppo_gae(_p(b["rew"]), _p(b["val"]), _p(b["done"]), _p(self.last_values), self.n_steps,
                                     self.n_envs, self.gamma, self.gae_lambda, _p(b["adv"]), _p(b["ret"]), _stream()))
 
@@ -394,7 +409,7 @@ class PPO:
         b = self.buf
         T, N, D = self.n_steps, self.n_envs, self.d
         total = T * N
-        obs, act = b["obs"].view(total, D), b["act"].view(total, A)
+        obs, act = b["obs"].view(total, D), b["act"].view(total, self.a)
         val, logp_old = b["val"].view(total), b["logp"].view(total)
         adv, ret = b["adv"].view(total), b["ret"].view(total)
         bs = min(self.batch_size, total)
@@ -458,11 +473,11 @@ class PPO:
     def predict(self, obs_raw: torch.Tensor, deterministic: bool = True) -> torch.Tensor:
         obs_raw = obs_raw.to(self.device, torch.float32).contiguous()
         n = obs_raw.shape[0]
-        act = torch.zeros((n, A), dtype=torch.float32, device=self.device)
+        act = torch.zeros((n, self.a), dtype=torch.float32, device=self.device)
         val = torch.zeros(n, dtype=torch.float32, device=self.device)
-        _lib.check(self.lib.ppo_policy_forward(_p(self.policy.theta), self.d, _p(obs_raw), self._stats_ptr(),
-                                               self.vecnorm.clip_obs, n, self.seed, 0, 0, _p(self._step_dev),
-                                               int(deterministic), None, _p(act), None, None, _p(val), _stream()))
+        _lib.check(self.lib.ppo_policy_forward_a(_p(self.policy.theta), self.d, self.a, _p(obs_raw), self._stats_ptr(),
+                                                 self.vecnorm.clip_obs, n, self.seed, 0, 0, _p(self._step_dev),
+                                                 int(deterministic), None, _p(act), None, None, _p(val), _stream()))
         return act
 
     def evaluate_policy(self, env=None, n_eval_episodes: int = 100, deterministic: bool = True, max_steps: int | None = None):

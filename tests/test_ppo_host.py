@@ -137,3 +137,18 @@ def test_two_rank_gloo_gradient_allreduce_and_stats_sync(tmp_path):
     st = res["obs_stats"].numpy()
     assert np.allclose(st[:28], pooled.mean(0), atol=1e-3) and np.allclose(st[28:56], pooled.var(0), rtol=1e-3)
     assert st[56] == pytest.approx(800 + 1e-4)
+
+
+def test_six_channel_policy_layout():
+    """train/train_lowlevel_cmd.py trains MlpPolicy on FixedwingLowLevelEnv: Box(21) observations, Box(6) actions."""
+    from pyflyt_drone_b200.ppo import FlatMlpPolicy
+    pol = FlatMlpPolicy(21, torch.device("cpu"), seed=1, act_dim=6)
+    assert pol.count == (64 * 21 + 64 + 64 * 64 + 64 + 6 * 64 + 6) + (64 * 21 + 64 + 64 * 64 + 64 + 64 + 1) + 6
+    sd = pol.state_dict()
+    assert sd["action_net.weight"].shape == (6, 64) and sd["log_std"].shape == (6,) and sd["value_net.weight"].shape == (1, 64)
+    obs, act = torch.randn(5, 21), torch.randn(5, 6)
+    v, lp, ent = pol.evaluate_actions(obs, act)
+    mean, _ = pol.towers(obs)
+    assert torch.allclose(lp, torch.distributions.Normal(mean, torch.ones(6)).log_prob(act).sum(-1), atol=1e-5)
+    with pytest.raises(ValueError):
+        FlatMlpPolicy(21, torch.device("cpu"), act_dim=5)
