@@ -2,7 +2,8 @@
 """PPO training on the B200-native simulator with the reference's TRAIN_CONFIG keys.
 
 Counterpart of /root/reference/train/train_Fixedwing_Waypoints_v3.py (--task waypoints) and
-train_Fixedwing_Waypoints_ObjLock.py (--task objlock): same hyper-parameter dictionary, same flow
+train_Fixedwing_Waypoints_ObjLock.py (--task objlock) / train_lowlevel_cmd.py (--task lowlevel): same hyper-parameter
+dictionary, same flow
 (vectorised env -> observation/reward normalisation -> PPO("MlpPolicy", ...).learn -> save model + vecnorm),
 with SubprocVecEnv/VecNormalize/PPO replaced by their device-resident equivalents.
 
@@ -29,6 +30,11 @@ TRAIN_CONFIG = {
         "clip_range": 0.2, "ent_coef": 0.001, "vf_coef": 0.5, "max_grad_norm": 0.5, "seed": 42,
         "model_dir": "models/obj_strike_ppo_b200", "flight_dome_size": 100.0, "max_duration_seconds": 120.0,
         "context_length": 2, "preset": "waypoint_objlock",
+    },
+    "lowlevel": {    # train_lowlevel_cmd.py:27-49 (FixedwingLowLevelEnv: 6-channel actions, psi/h/V tracking)
+        "total_timesteps": 2_000_000, "num_envs": 32, "learning_rate": 3e-4, "n_steps": 2048, "batch_size": 64, "n_epochs": 10,
+        "gamma": 0.99, "gae_lambda": 0.95, "clip_range": 0.2, "ent_coef": 0.0, "vf_coef": 0.5, "max_grad_norm": 0.5, "seed": 42,
+        "model_dir": "models/lowlevel_ppo_b200", "preset": "lowlevel",
     },
 }
 
@@ -57,11 +63,15 @@ def main():
     from pyflyt_drone_b200.ppo import PPO
     from pyflyt_drone_b200.vec_env import FixedwingVecEnv
 
-    env = FixedwingVecEnv(cfg["num_envs"], preset=cfg["preset"], device=local_rank, seed=cfg["seed"],
-                          env_id0=rank * cfg["num_envs"], num_targets=cfg["num_targets"],
-                          goal_reach=float(cfg["goal_reach_distance"]), sparse_reward=int(cfg["sparse_reward"]),
-                          dome=cfg["flight_dome_size"], max_steps=int(30 * cfg["max_duration_seconds"]),
-                          context_len=cfg["context_length"])
+    if args.task == "lowlevel":
+        env = FixedwingVecEnv(cfg["num_envs"], preset="lowlevel", device=local_rank, seed=cfg["seed"],
+                              env_id0=rank * cfg["num_envs"])
+    else:
+        env = FixedwingVecEnv(cfg["num_envs"], preset=cfg["preset"], device=local_rank, seed=cfg["seed"],
+                              env_id0=rank * cfg["num_envs"], num_targets=cfg["num_targets"],
+                              goal_reach=float(cfg["goal_reach_distance"]), sparse_reward=int(cfg["sparse_reward"]),
+                              dome=cfg["flight_dome_size"], max_steps=int(30 * cfg["max_duration_seconds"]),
+                              context_len=cfg["context_length"])
     model = PPO("MlpPolicy", env, learning_rate=cfg["learning_rate"], n_steps=cfg["n_steps"], batch_size=cfg["batch_size"],
                 n_epochs=cfg["n_epochs"], gamma=cfg["gamma"], gae_lambda=cfg["gae_lambda"], clip_range=cfg["clip_range"],
                 ent_coef=cfg["ent_coef"], vf_coef=cfg["vf_coef"], max_grad_norm=cfg["max_grad_norm"], seed=cfg["seed"],
