@@ -135,6 +135,14 @@ class ClockSampler(threading.Thread):
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
+        if not self.samples:
+            # a timed region shorter than one polling interval: read the clocks once, right after it
+            sample = self._nvml()
+            try:
+                if sample is not None:
+                    self.samples.append(sample())
+            except Exception:
+                pass
         sm, mx, reasons = [], [], set()
         for p in self.samples:
             try:
@@ -265,6 +273,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     if not args.no_graph:
         # one untimed pass through the launch graph: its construction / instantiation is not part of a step
         FixedwingVecEnv.rollout_random(envs, replicas, spl, use_graph=True)
+        if K % replicas:
+            FixedwingVecEnv.rollout_random(envs, K % replicas, spl, use_graph=True)     # and the graph of the tail
     launches0 = sum(e.launch_count for e in envs)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:

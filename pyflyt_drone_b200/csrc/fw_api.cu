@@ -224,7 +224,29 @@ struct MultiGraph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
 };
-static MultiGraph g_multi;
+static MultiGraph g_multi;     // one full round-robin pass over the handle list
+static MultiGraph g_rem;       // the launches left over after the full passes (a prefix of the list)
+
+// (re)build `mg` as a chain of `count` random-step launches over hs[0], hs[1], ... (wrapping), unless it already is
+static int multi_graph_get(MultiGraph& mg, const fw_handle* hs, int n_handles, int count, int spl) {
+    bool hit = mg.exec && mg.spl == spl && (int)mg.hs.size() == count;
+    for (int k = 0; hit && k < count; ++k) hit = mg.hs[k] == hs[k % n_handles];
+    if (hit) return FW_OK;
+    if (mg.exec) { cudaGraphExecDestroy(mg.exec); mg.exec = nullptr; }
+    if (mg.graph) { cudaGraphDestroy(mg.graph); mg.graph = nullptr; }
+    mg.hs.clear();
+    CU(cudaGraphCreate(&mg.graph, 0));
+    cudaGraphNode_t prev, node;
+    for (int k = 0; k < count; ++k) {
+        FwSim* h = hs[k % n_handles];
+        CU(fwk_graph_add_random_step(mg.graph, k ? &prev : nullptr, h->dev, h->pl, spl, &node));
+        prev = node;
+    }
+    CU(cudaGraphInstantiate(&mg.exec, mg.graph, 0));
+    for (int k = 0; k < count; ++k) mg.hs.push_back(hs[k % n_handles]);
+    mg.spl = spl;
+    return FW_OK;
+}
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -302,13 +324,14 @@ extern "C" int fw_destroy(fw_handle h) {
     if (!h) return FW_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (FwSim* g : g_multi.hs)
-        if (g == h) {
-            if (g_multi.exec) cudaGraphExecDestroy(g_multi.exec);
-            if (g_multi.graph) cudaGraphDestroy(g_multi.graph);
-            g_multi = MultiGraph();
-            break;
-        }
+    for (MultiGraph* mg : {&g_multi, &g_rem})          // a cached launch graph that names this handle dies with it
+        for (FwSim* g : mg->hs)
+            if (g == h) {
+                if (mg->exec) cudaGraphExecDestroy(mg->exec);
+                if (mg->graph) cudaGraphDestroy(mg->graph);
+                *mg = MultiGraph();
+                break;
+            }
     if (h->plane_mem) cudaFree(h->plane_mem);
     if (h->d_act) cudaFree(h->d_act);
     if (h->d_obs) cudaFree(h->d_obs);
@@ -378,26 +401,21 @@ extern "C" int fw_rollout_random(const fw_handle* hs, int32_t n_handles, int32_t
     CU(cudaSetDevice(hs[0]->device));
     cudaStream_t st = (cudaStream_t)stream;
     int done = 0;
-    if (use_graph && n_launches >= n_handles) {
-        bool hit = g_multi.exec && g_multi.spl == steps_per_launch && (int)g_multi.hs.size() == n_handles;
-        for (int k = 0; hit && k < n_handles; ++k) hit = g_multi.hs[k] == hs[k];
-        if (!hit) {
-            if (g_multi.exec) { cudaGraphExecDestroy(g_multi.exec); g_multi.exec = nullptr; }
-            if (g_multi.graph) { cudaGraphDestroy(g_multi.graph); g_multi.graph = nullptr; }
-            CU(cudaGraphCreate(&g_multi.graph, 0));
-            cudaGraphNode_t prev, node;
-            for (int k = 0; k < n_handles; ++k) {
-                CU(fwk_graph_add_random_step(g_multi.graph, k ? &prev : nullptr, hs[k]->dev, hs[k]->pl, steps_per_launch, &node));
-                prev = node;
-            }
-            CU(cudaGraphInstantiate(&g_multi.exec, g_multi.graph, 0));
-            g_multi.hs.assign(hs, hs + n_handles);
-            g_multi.spl = steps_per_launch;
+    if (use_graph) {
+        const int rounds = n_launches / n_handles, rem = n_launches % n_handles;
+        if (rounds > 0) {
+            int rc = multi_graph_get(g_multi, hs, n_handles, n_handles, steps_per_launch);
+            if (rc != FW_OK) return rc;
+            for (int r = 0; r < rounds; ++r) CU(cudaGraphLaunch(g_multi.exec, st));
+            for (int k = 0; k < n_handles; ++k) hs[k]->launches += rounds;
         }
-        const int rounds = n_launches / n_handles;
-        for (int r = 0; r < rounds; ++r) CU(cudaGraphLaunch(g_multi.exec, st));
-        done = rounds * n_handles;
-        for (int k = 0; k < n_handles; ++k) hs[k]->launches += rounds;
+        if (rem > 0) {       // the tail of a launch count that is not a multiple of the list: one more (shorter) graph
+            int rc = multi_graph_get(g_rem, hs, n_handles, rem, steps_per_launch);
+            if (rc != FW_OK) return rc;
+            CU(cudaGraphLaunch(g_rem.exec, st));
+            for (int k = 0; k < rem; ++k) hs[k]->launches += 1;
+        }
+        done = n_launches;
     }
     for (int j = done; j < n_launches; ++j) {
         FwSim* h = hs[j % n_handles];
