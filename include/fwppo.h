@@ -57,14 +57,18 @@ int ppo_policy_forward_tc(const float* params, int32_t d, const float* obs_raw, 
                           int32_t deterministic, float* obs_norm, float* act_env, float* act_raw, float* logp,
                           float* value, void* stream);
 
-/* Wide-action variants (CUDA-core forward): action width a = 4 or 6.  a = 6 is the low-level env's MlpPolicy
+/* Wide-action variants: action width a = 4 or 6.  a = 6 is the low-level env's MlpPolicy
  * (train/train_lowlevel_cmd.py: FixedwingLowLevelEnv, Box(6) actions); the parameter vector has the layout above with
- * A = a, the action buffers are [n, a].  The tensor-core forward and the fused update are built for a = 4. */
+ * A = a, the action buffers are [n, a].  The fused update kernel (ppo_minibatch_grad) is built for a = 4. */
 int ppo_param_count_a(int32_t d, int32_t a);
 int ppo_policy_forward_a(const float* params, int32_t d, int32_t a, const float* obs_raw, const double* obs_stats,
                          float clip_obs, int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev,
                          int32_t deterministic, float* obs_norm, float* act_env, float* act_raw, float* logp, float* value,
                          void* stream);
+int ppo_policy_forward_tc_a(const float* params, int32_t d, int32_t a, const float* obs_raw, const double* obs_stats,
+                            float clip_obs, int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step,
+                            const uint32_t* step_dev, int32_t deterministic, float* obs_norm, float* act_env, float* act_raw,
+                            float* logp, float* value, void* stream);     /* tcgen05 forward, a = 4 or 6 */
 int ppo_value_forward_a(const float* params, int32_t d, int32_t a, const float* obs_raw, const double* obs_stats,
                         float clip_obs, int32_t n, float* value, void* stream);
 int ppo_timeout_bootstrap_a(const float* params, int32_t d, int32_t a, const float* term_obs_raw, const double* obs_stats,

@@ -8,6 +8,8 @@ PPO_SYMBOLS = [
     ("ppo_param_count_a", C.c_int, [C.c_int32, C.c_int32]),
     ("ppo_policy_forward_a", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _F, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, _P,
                                        C.c_int32, _P, _P, _P, _P, _P, _P]),
+    ("ppo_policy_forward_tc_a", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _F, C.c_int32, C.c_uint64, C.c_uint32, C.c_uint32, _P,
+                                          C.c_int32, _P, _P, _P, _P, _P, _P]),
     ("ppo_value_forward_a", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _F, C.c_int32, _P, _P]),
     ("ppo_timeout_bootstrap_a", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _F, _P, C.c_int32, _F, _P, _P]),
     ("ppo_moments_update", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P]),

@@ -108,19 +108,32 @@ extern "C" int ppo_policy_forward(const float* params, int32_t d, const float* o
     return FW_OK;
 }
 
-extern "C" int ppo_policy_forward_tc(const float* params, int32_t d, const float* obs_raw, const double* obs_stats,
-                                     float clip_obs, int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step,
-                                     const uint32_t* step_dev, int32_t deterministic, float* obs_norm, float* act_env,
-                                     float* act_raw, float* logp, float* value, void* stream) {
+extern "C" int ppo_policy_forward_tc_a(const float* params, int32_t d, int32_t a, const float* obs_raw,
+                                       const double* obs_stats, float clip_obs, int32_t n, uint64_t seed, uint32_t env_id0,
+                                       uint32_t step, const uint32_t* step_dev, int32_t deterministic, float* obs_norm,
+                                       float* act_env, float* act_raw, float* logp, float* value, void* stream) {
     if (!params || !obs_raw || !act_env || !value) return pfail(FW_EINVAL, "null argument");
     if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
     int rc = check_d(d);
     if (rc) return rc;
+    if ((rc = check_a(a)) != 0) return rc;
     if ((reinterpret_cast<uintptr_t>(act_env) & 15u) || (act_raw && (reinterpret_cast<uintptr_t>(act_raw) & 15u)))
         return pfail(FW_EINVAL, "action buffers must be 16-byte aligned");
-    PCU(ppok_forward_tc(params, d, obs_raw, obs_stats, clip_obs, n, seed, env_id0, step, step_dev, deterministic, obs_norm,
-                        act_env, act_raw, logp, value, (cudaStream_t)stream));
+    if (a == 4)
+        PCU(ppo_a4::ppok_forward_tc(params, d, obs_raw, obs_stats, clip_obs, n, seed, env_id0, step, step_dev, deterministic,
+                                    obs_norm, act_env, act_raw, logp, value, (cudaStream_t)stream));
+    else
+        PCU(ppo_a6::ppok_forward_tc(params, d, obs_raw, obs_stats, clip_obs, n, seed, env_id0, step, step_dev, deterministic,
+                                    obs_norm, act_env, act_raw, logp, value, (cudaStream_t)stream));
     return FW_OK;
+}
+
+extern "C" int ppo_policy_forward_tc(const float* params, int32_t d, const float* obs_raw, const double* obs_stats,
+                                     float clip_obs, int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step,
+                                     const uint32_t* step_dev, int32_t deterministic, float* obs_norm, float* act_env,
+                                     float* act_raw, float* logp, float* value, void* stream) {
+    return ppo_policy_forward_tc_a(params, d, PPO_ACT, obs_raw, obs_stats, clip_obs, n, seed, env_id0, step, step_dev,
+                                   deterministic, obs_norm, act_env, act_raw, logp, value, stream);
 }
 
 extern "C" int ppo_value_forward(const float* params, int32_t d, const float* obs_raw, const double* obs_stats,

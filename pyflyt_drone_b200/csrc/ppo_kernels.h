@@ -24,9 +24,16 @@ cudaError_t ppok_bootstrap(const float* params, int d, const float* term_obs, co
                            int a = PPO_A);
 cudaError_t ppok_gae(const float* rewards, const float* values, const float* dones, const float* last_values, int T, int n,
                      float gamma, float lam, float* adv, float* ret, cudaStream_t st);
-cudaError_t ppok_forward_tc(const float* params, int d, const float* obs_raw, const double* stats, float clip, int n,
-                            uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev, int deterministic,
-                            float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, cudaStream_t st);
+// tensor-core forward: one instantiation per action width (ppo_tc.cu compiled for 4, ppo_tc_a6.cu for 6)
+#define PPOK_DECLARE_FORWARD_TC(ns)                                                                                      \
+    namespace ns {                                                                                                        \
+    cudaError_t ppok_forward_tc(const float* params, int d, const float* obs_raw, const double* stats, float clip, int n, \
+                                uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev,                \
+                                int deterministic, float* obs_norm, float* act_env, float* act_raw, float* logp,         \
+                                float* value, cudaStream_t st);                                                          \
+    }
+PPOK_DECLARE_FORWARD_TC(ppo_a4)
+PPOK_DECLARE_FORWARD_TC(ppo_a6)
 int ppok_update_grid(int batch);
 cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, const float* act, const float* logp_old,
                                 const float* adv, const float* ret, const long long* idx, int batch, float clip_range,

@@ -15,8 +15,22 @@
 
 #include <cuda_runtime.h>
 
+// The file is compiled once per supported action width (ppo_tc_a6.cu includes it with PPO_A_BUILD = 6); everything
+// lives in a namespace named after the width.
+#ifndef PPO_A_BUILD
+#define PPO_A_BUILD 4
+#endif
+#if PPO_A_BUILD == 4
+namespace ppo_a4 {
+#elif PPO_A_BUILD == 6
+namespace ppo_a6 {
+#else
+#error "action width must be 4 or 6"
+#endif
+
 #define H PPO_H
-#define A PPO_A
+#define A PPO_A_BUILD
+#define AP ((A + 3) / 4 * 4)      // action width padded to whole float4s: the head weights are read as float4 rows
 #define DP PPO_DPAD
 #define TC_ROWS 128
 #define TC_THREADS 512
@@ -127,11 +141,12 @@ struct TcSmem {
     static constexpr int W2_VF = W2_PI + H * H * 4;
     static constexpr int SMALL = W2_VF + H * H * 4;       // biases, heads, stats, barrier, tmem pointer
     // floats inside SMALL
-    static constexpr int B1_PI = 0, B1_VF = 64, B2_PI = 128, B2_VF = 192, W3_PI = 256, W3_VF = 512, B3_PI = 576,
-                         B3_VF = 580, LOGSTD = 584, MEAN = 592, ISTD = 624, BAR = 656 /* 8-byte aligned */, TPTR = 660,
-                         NSMALL = 664;
-    static constexpr int HP = SMALL + NSMALL * 4;          // head partial sums [4 warpgroups][128 rows] float4, 8 KB
-    static constexpr int TOTAL = HP + 4 * TC_ROWS * 16;
+    static constexpr int B1_PI = 0, B1_VF = 64, B2_PI = 128, B2_VF = 192, W3_PI = 256 /* [64][AP] */, W3_VF = W3_PI + H * AP,
+                         B3_PI = W3_VF + H, B3_VF = B3_PI + 8, LOGSTD = B3_VF + 4, MEAN = LOGSTD + 8, ISTD = MEAN + DP,
+                         BAR = ISTD + DP /* 8-byte aligned */, TPTR = BAR + 4, NSMALL = TPTR + 4;
+    static_assert((BAR % 2) == 0 && (NSMALL % 4) == 0 && (W3_PI % 4) == 0 && (W3_VF % 4) == 0, "alignment of the small area");
+    static constexpr int HP = SMALL + NSMALL * 4;          // head partial sums [4 warpgroups][128 rows][AP] floats
+    static constexpr int TOTAL = HP + 4 * TC_ROWS * AP * 4;
 };
 
 __device__ void tc_load_weight(char* smem, int off, const float* __restrict__ g, int K, int d) {
@@ -209,7 +224,10 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
         small[TcSmem::B2_VF + tid] = g_vf[H * d + H + H * H + tid];
         small[TcSmem::W3_VF + tid] = g_vf[H * d + H + H * H + H + tid];
     }
-    for (int i = tid; i < A * H; i += blockDim.x) small[TcSmem::W3_PI + (i % H) * A + i / H] = g_pi[H * d + H + H * H + H + i];   // [j][a]
+    for (int i = tid; i < H * AP; i += blockDim.x) {                               // [j][a], zero padded to AP
+        const int j = i / AP, a = i % AP;
+        small[TcSmem::W3_PI + i] = a < A ? g_pi[H * d + H + H * H + H + a * H + j] : 0.0f;
+    }
     if (tid < A) {
         small[TcSmem::B3_PI + tid] = g_pi[H * d + H + H * H + H + A * H + tid];
         small[TcSmem::LOGSTD + tid] = params[pi_count + vf_count + tid];
@@ -301,14 +319,21 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
         // Gaussian noise for this row (warpgroup 0), drawn while the layer-2 MMAs run
         const int row = tile * TC_ROWS + lrow;
         const bool live = row < n;
-        float eps[A] = {0.f, 0.f, 0.f, 0.f};
+        float eps[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) eps[a] = 0.0f;
         if (q == 0 && live && !deterministic) {
-            uint4 r = tc_philox(seed_lo, seed_hi, env_id0 + (uint32_t)row, step_eff, 0u, 7u);
-            float ra = sqrtf(-2.0f * __logf(tc_u01(r.x))), rb = sqrtf(-2.0f * __logf(tc_u01(r.z)));
-            float s0, c0, s1, c1;
-            sincospif(2.0f * tc_u01(r.y), &s0, &c0);
-            sincospif(2.0f * tc_u01(r.w), &s1, &c1);
-            eps[0] = ra * c0; eps[1] = ra * s0; eps[2] = rb * c1; eps[3] = rb * s1;
+#pragma unroll
+            for (int g = 0; g < AP / 4; ++g) {          // four normals per Philox call; channels 4.. use counter word 2 = 1
+                uint4 r = tc_philox(seed_lo, seed_hi, env_id0 + (uint32_t)row, step_eff, (uint32_t)g, 7u);
+                float ra = sqrtf(-2.0f * __logf(tc_u01(r.x))), rb = sqrtf(-2.0f * __logf(tc_u01(r.z)));
+                float s0, c0, s1, c1;
+                sincospif(2.0f * tc_u01(r.y), &s0, &c0);
+                sincospif(2.0f * tc_u01(r.w), &s1, &c1);
+                const float e4[4] = {ra * c0, ra * s0, rb * c1, rb * s1};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) if (4 * g + k < A) eps[4 * g + k] = e4[k];
+            }
         }
         tc_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -316,7 +341,9 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
         {
             float v[32];
             tc_ld32(tcol + lane_base, v);
-            float ps[A] = {0.f, 0.f, 0.f, 0.f};
+            float ps[AP];
+#pragma unroll
+            for (int a = 0; a < AP; ++a) ps[a] = 0.0f;
 #pragma unroll
             for (int c4 = 0; c4 < 8; ++c4) {
                 const float4 b = *reinterpret_cast<const float4*>(b2 + 4 * c4);
@@ -325,9 +352,12 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
                 if (is_pi) {
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
-                        const float4 w = *reinterpret_cast<const float4*>(small + TcSmem::W3_PI + (j0 + 4 * c4 + r) * A);
-                        ps[0] = fmaf(w.x, h2[r], ps[0]); ps[1] = fmaf(w.y, h2[r], ps[1]);
-                        ps[2] = fmaf(w.z, h2[r], ps[2]); ps[3] = fmaf(w.w, h2[r], ps[3]);
+#pragma unroll
+                        for (int g = 0; g < AP / 4; ++g) {
+                            const float4 w = *reinterpret_cast<const float4*>(small + TcSmem::W3_PI + (j0 + 4 * c4 + r) * AP + 4 * g);
+                            ps[4 * g + 0] = fmaf(w.x, h2[r], ps[4 * g + 0]); ps[4 * g + 1] = fmaf(w.y, h2[r], ps[4 * g + 1]);
+                            ps[4 * g + 2] = fmaf(w.z, h2[r], ps[4 * g + 2]); ps[4 * g + 3] = fmaf(w.w, h2[r], ps[4 * g + 3]);
+                        }
                     }
                 } else {
                     const float4 w = *reinterpret_cast<const float4*>(small + TcSmem::W3_VF + j0 + 4 * c4);
@@ -335,29 +365,34 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
                     ps[0] = fmaf(w.z, h2[2], ps[0]); ps[0] = fmaf(w.w, h2[3], ps[0]);
                 }
             }
-            *reinterpret_cast<float4*>(smem + TcSmem::HP + (q * TC_ROWS + lrow) * 16) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+#pragma unroll
+            for (int g = 0; g < AP / 4; ++g)
+                *reinterpret_cast<float4*>(smem + TcSmem::HP + ((q * TC_ROWS + lrow) * AP + 4 * g) * 4) =
+                    make_float4(ps[4 * g + 0], ps[4 * g + 1], ps[4 * g + 2], ps[4 * g + 3]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         // ---- heads, diagonal-Gaussian sample and log-probability: one thread per env
         if (q == 0 && live) {
-            const float4 p0 = *reinterpret_cast<const float4*>(smem + TcSmem::HP + (0 * TC_ROWS + lrow) * 16);
-            const float4 p1 = *reinterpret_cast<const float4*>(smem + TcSmem::HP + (1 * TC_ROWS + lrow) * 16);
-            const float pv0 = *reinterpret_cast<const float*>(smem + TcSmem::HP + (2 * TC_ROWS + lrow) * 16);
-            const float pv1 = *reinterpret_cast<const float*>(smem + TcSmem::HP + (3 * TC_ROWS + lrow) * 16);
-            const float mean[A] = {small[TcSmem::B3_PI + 0] + p0.x + p1.x, small[TcSmem::B3_PI + 1] + p0.y + p1.y,
-                                   small[TcSmem::B3_PI + 2] + p0.z + p1.z, small[TcSmem::B3_PI + 3] + p0.w + p1.w};
+            const float* hp0 = reinterpret_cast<const float*>(smem + TcSmem::HP) + (0 * TC_ROWS + lrow) * AP;
+            const float* hp1 = reinterpret_cast<const float*>(smem + TcSmem::HP) + (1 * TC_ROWS + lrow) * AP;
+            const float pv0 = *(reinterpret_cast<const float*>(smem + TcSmem::HP) + (2 * TC_ROWS + lrow) * AP);
+            const float pv1 = *(reinterpret_cast<const float*>(smem + TcSmem::HP) + (3 * TC_ROWS + lrow) * AP);
             value[row] = small[TcSmem::B3_VF] + pv0 + pv1;
-            float lp = 0.0f, av[A];
+            float lp = 0.0f, av[A], ac[A];
 #pragma unroll
             for (int a = 0; a < A; ++a) {
+                const float mean = small[TcSmem::B3_PI + a] + hp0[a] + hp1[a];
                 const float ls = small[TcSmem::LOGSTD + a];
-                av[a] = fmaf(__expf(ls), eps[a], mean[a]);
+                av[a] = fmaf(__expf(ls), eps[a], mean);
+                ac[a] = fminf(fmaxf(av[a], -1.f), 1.f);
                 lp += -0.5f * eps[a] * eps[a] - ls - 0.91893853320467274178f;
             }
-            reinterpret_cast<float4*>(act_env)[row] = make_float4(fminf(fmaxf(av[0], -1.f), 1.f), fminf(fmaxf(av[1], -1.f), 1.f),
-                                                                  fminf(fmaxf(av[2], -1.f), 1.f), fminf(fmaxf(av[3], -1.f), 1.f));
-            if (act_raw != nullptr) reinterpret_cast<float4*>(act_raw)[row] = make_float4(av[0], av[1], av[2], av[3]);
+#pragma unroll
+            for (int a = 0; a < A; a += 2) {             // rows are A floats wide (8-byte aligned for the even widths)
+                reinterpret_cast<float2*>(act_env + (size_t)row * A)[a / 2] = make_float2(ac[a], ac[a + 1]);
+                if (act_raw != nullptr) reinterpret_cast<float2*>(act_raw + (size_t)row * A)[a / 2] = make_float2(av[a], av[a + 1]);
+            }
             if (logp != nullptr) logp[row] = lp;
         }
         // no trailing barrier: the partials live outside the operand buffers, and the two block-wide syncs of the next
@@ -388,3 +423,5 @@ cudaError_t ppok_forward_tc(const float* params, int d, const float* obs_raw, co
                                                                obs_norm, act_env, act_raw, logp, value);
     return cudaGetLastError();
 }
+
+}  // namespace ppo_a4 / ppo_a6

@@ -255,11 +255,10 @@ class PPO:
             raise ValueError("update must be 'kernel' (hand-written tcgen05 kernels) or 'torch' (autograd reference)")
         self.update = update
         if self.a != A:
-            # The tensor-core forward (K4) and the fused update (K6) are built for the 4-channel policies of the
-            # Waypoints / ObjLock scripts.  Six-channel policies (train_lowlevel_cmd.py) roll out with the CUDA-core
-            # forward kernel and update through the torch autograd path.
+            # The fused update (K6) is built for the 4-channel policies of the Waypoints / ObjLock scripts.  Six-channel
+            # policies (train_lowlevel_cmd.py) roll out with the same forward kernels (compiled for width 6) and update
+            # through the torch autograd path.
             self.update = "torch"
-            tensor_core_forward = False
         P = self.policy.count
         self._ws = torch.zeros(int(self.lib.ppo_update_workspace_floats(self.d)), **f32)
         self._grad = torch.zeros(P, **f32)
@@ -295,16 +294,10 @@ class PPO:
 
     def _forward(self, obs_raw, t, deterministic=False):
         b = self.buf
-        if self.a != A:
-            _lib.check(self.lib.ppo_policy_forward_a(
-                _p(self.policy.theta), self.d, self.a, _p(obs_raw), self._stats_ptr(), self.vecnorm.clip_obs, self.n_envs,
-                self.seed, self.env.env_id0, t, _p(self._step_dev), int(deterministic), _p(b["obs"][t]), _p(self.act_env),
-                _p(b["act"][t]), _p(b["logp"][t]), _p(b["val"][t]), _stream()))
-            return
-        fwd = self.lib.ppo_policy_forward_tc if self.tensor_core_forward else self.lib.ppo_policy_forward
+        fwd = self.lib.ppo_policy_forward_tc_a if self.tensor_core_forward else self.lib.ppo_policy_forward_a
         _lib.check(fwd(
-            _p(self.policy.theta), self.d, _p(obs_raw), self._stats_ptr(), self.vecnorm.clip_obs, self.n_envs, self.seed,
-            self.env.env_id0, t, _p(self._step_dev), int(deterministic), _p(b["obs"][t]), _p(self.act_env),
+            _p(self.policy.theta), self.d, self.a, _p(obs_raw), self._stats_ptr(), self.vecnorm.clip_obs, self.n_envs,
+            self.seed, self.env.env_id0, t, _p(self._step_dev), int(deterministic), _p(b["obs"][t]), _p(self.act_env),
             _p(b["act"][t]), _p(b["logp"][t]), _p(b["val"][t]), _stream()))
 
     def collect_rollouts(self) -> None:

@@ -111,23 +111,31 @@ def test_lowlevel_random_action_lane_and_tensor_lane(fo):
 
 
 def test_ppo_on_the_lowlevel_env_six_channel_policy():
-    """train/train_lowlevel_cmd.py on the device: rollouts with the CUDA-core forward kernel (6-channel Gaussian policy),
-    update through the torch autograd path.  The forward kernel must agree with the fp32 torch towers, and a short run
-    must improve the tracking reward."""
+    """train/train_lowlevel_cmd.py on the device: rollouts with the forward kernels compiled for a 6-channel Gaussian
+    policy (CUDA-core fp32 and tcgen05 TF32), update through the torch autograd path.  The forward kernels must agree
+    with the fp32 torch towers, and a short run must improve the return."""
     import torch
     from pyflyt_drone_b200.ppo import PPO
     from pyflyt_drone_b200.vec_env import FixedwingVecEnv
     env = FixedwingVecEnv(1024, preset="lowlevel", seed=3)
-    m = PPO("MlpPolicy", env, n_steps=32, batch_size=8192, n_epochs=4, seed=3, use_cuda_graph=False)
-    assert m.a == 6 and m.update == "torch" and not m.tensor_core_forward and m.policy.count == m.policy.theta.numel()
-    m.collect_rollouts()
-    torch.cuda.synchronize()
+    for tc, tol_max, tol_mean in ((False, 2e-4, 2e-5), (True, 3e-2, 3e-3)):          # fp32 kernel; TF32 + MUFU.TANH kernel
+        m = PPO("MlpPolicy", env, n_steps=32, batch_size=8192, n_epochs=4, seed=3, use_cuda_graph=False,
+                tensor_core_forward=tc)
+        assert m.a == 6 and m.update == "torch" and m.tensor_core_forward == tc and m.policy.count == m.policy.theta.numel()
+        with torch.no_grad():      # move the towers away from the near-zero initial action head
+            m.policy.theta.add_(0.05 * torch.randn(m.policy.count, device=m.device, generator=m._gen))
+        m.collect_rollouts()
+        torch.cuda.synchronize()
+        b = m.buf
+        obs, act = b["obs"].view(-1, 21), b["act"].view(-1, 6)
+        with torch.no_grad():
+            v, lp, _ = m.policy.evaluate_actions(obs, act)
+        dl, dv = (lp - b["logp"].view(-1)).abs(), (v - b["val"].view(-1)).abs()
+        assert float(dl.max()) < tol_max and float(dl.mean()) < tol_mean, (tc, float(dl.max()), float(dl.mean()))
+        assert float(dv.max()) < tol_max, (tc, float(dv.max()))
+        assert float(m.act_env.abs().max()) <= 1.0 and float(b["act"].std()) > 0.5       # sampled, clipped for the env
+    m = PPO("MlpPolicy", env, n_steps=32, batch_size=8192, n_epochs=4, seed=3)
     b = m.buf
-    obs, act = b["obs"].view(-1, 21), b["act"].view(-1, 6)
-    with torch.no_grad():
-        v, lp, _ = m.policy.evaluate_actions(obs, act)
-    assert float((lp - b["logp"].view(-1)).abs().max()) < 2e-4 and float((v - b["val"].view(-1)).abs().max()) < 2e-4
-    assert float(m.act_env.abs().max()) <= 1.0 and float(b["act"].std()) > 0.5           # sampled, clipped for the env
     r0, _, l0, _ = m.evaluate_policy(n_eval_episodes=512)
     m.learn(40 * 32 * 1024)
     r1, _, l1, _ = m.evaluate_policy(n_eval_episodes=512)
