@@ -25,12 +25,13 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 8
+#define FW_ABI_VERSION 9
 
 #define FW_NSURF 5            /* cmd order: left aileron, right aileron, h-tail, v-tail, main wing */
 #define FW_MAX_TARGETS 16
 #define FW_MAX_COL 16
 #define FW_MAX_OBST 32
+#define FW_MAX_HIST 4            /* duck-only task: frames of vision history in the observation */
 
 /* error codes */
 #define FW_OK 0
@@ -51,6 +52,8 @@ extern "C" {
 #define FW_TASK_PHYSICS   0   /* dynamics + ground/dome termination, no observation (BASELINE config 2) */
 #define FW_TASK_WAYPOINTS 1   /* PyFlyt/Fixedwing-Waypoints-v3 + FlattenWaypointEnv */
 #define FW_TASK_OBJLOCK   2   /* FixedwingWaypointObjLockEnv + FlattenWaypointEnv */
+#define FW_TASK_LOWLEVEL  3   /* FixedwingLowLevelEnv (envs/fixedwing_envs/fixedwing_lowlevel_env.py) */
+#define FW_TASK_DUCK      4   /* FixedwingObjLockEnv + FlattenObjLockEnv (envs/fixedwing_objlock_env.py, flatten_objlock_env.py) */
 
 /* Everything the kernels need to know about the aircraft and the task.  Raw physical parameters only;
  * derived constants are computed inside fw_create. */
@@ -82,18 +85,28 @@ typedef struct FwConfig {
     double obst_radius, obst_h_lo, obst_h_hi, obst_safe, obst_scale, obst_max_pen;
     double strike_dist, strike_reward, lock_step_reward, approach_scale, switch_min_area;
     double duck_radius, cam_offset[3], cam_near, cam_far;
+    /* duck-only task -- envs/fixedwing_objlock_env.py:37-118.  cam_tilt_deg = camera_angle_degrees ([UP-RECALL] rotation
+     * about body +y, positive = nose-down); the rest are the visual-shaping reward constants of :71-79 */
+    double cam_tilt_deg, duck_dist_scale, lock_center_radius, centering_scale, visible_step_reward, area_reward_scale;
+    double lock_lost_penalty, approach_clip;
 
     int32_t n_col;
     int32_t physics_per_control, substeps_per_inner, inner_per_step, warmup_inner;
     int32_t freestream_3d, cd90_degrees;
     int32_t task;   /* 0 physics only, 1 Waypoints-v3, 2 Waypoint+ObjLock, 3 low-level tracking (FixedwingLowLevelEnv:
-                     * 21-float obs, 6-channel action, one Aviary.step per env step, truncation at step_count >= max_steps) */
+                     * 21-float obs, 6-channel action, one Aviary.step per env step, truncation at step_count >= max_steps),
+                     * 4 duck-only lock/strike (FixedwingObjLockEnv: attitude + target_vector + 9*history (+4 deltas) obs) */
     int32_t num_targets, sparse_reward, angle_repr, max_steps, context_len;
     int32_t early_return_on_crash, complete_truncates;
     int32_t wind_mode, wind_randomize, wind_rand_phase, wind_start_substep;
     int32_t num_obstacles, cam_interval_substeps, lock_hold_steps, switch_min_seen, cam_res;
     int32_t force_generic_kernel;   /* 1 = never pick the kernels specialised for the standard aircraft layout (testing) */
-    int32_t _reserved[5];
+    int32_t cam_mode;               /* 0 tracking chase camera (looks at the aircraft from cam_offset), 1 fixed camera at
+                                     * cam_offset looking along body x tilted by cam_tilt_deg (is_tracking_camera = False) */
+    int32_t vision_hist_len;        /* duck_vision_history_len, 1..FW_MAX_HIST (task 4) */
+    int32_t vision_use_deltas;      /* duck_vision_use_deltas (task 4) */
+    int32_t lock_decay_steps;       /* duck_lock_decay_steps (task 4) */
+    int32_t _reserved[1];
 } FwConfig;
 
 /* Host-side view of the per-env state for parity injection / inspection.  Any pointer may be NULL
@@ -111,12 +124,14 @@ typedef struct FwStateHost {
     uint32_t* episode;   /* [N] */
     float* new_dist;     /* [N] WaypointHandler.new_distance */
     float* wind;         /* [N,7] base xyz, gust amp xyz, phase */
-    /* ObjLock task only (ignored otherwise) */
+    /* ObjLock tasks (2 and 4) only (ignored otherwise) */
     float* duck;         /* [N,3] duck position */
     float* obst;         /* [N,FW_MAX_OBST,3] cylinders x, y, height (first n_obst rows valid) */
     float* ol_f;         /* [N,12] last cx,cy,area,depth | frame cx,cy,area,depth | frame dL,dC,dR | prev_est_dist */
     int32_t* ol_i;       /* [N,9] duck_phase, has_prev, post_waypoints, cam_valid, frame_visible,
-                                  seen_consecutive, lock_steps, steps_since_seen, n_obst */
+                                  seen_consecutive (task 4: _vision_history_filled), lock_steps, steps_since_seen, n_obst */
+    float* vis_hist;     /* task 4: [N, FW_MAX_HIST*9 + 4] vision history rows (newest first; rows >= vision_hist_len unused)
+                                  followed by the four delta features */
 } FwStateHost;
 
 typedef struct FwSim* fw_handle;

@@ -49,6 +49,8 @@ int fwo_obs_dim(const fwo_config* c) {
     if (c->task == FWO_TASK_PHYSICS) return 0;
     if (c->task == FWO_TASK_LOWLEVEL) return 21;      /* fixedwing_lowlevel_env.py:64-68 */
     int att = (c->angle_repr == 0 ? 12 : 13) + 4 + 6;
+    if (c->task == FWO_TASK_DUCK)                     /* flatten_objlock_env.py:20-31: attitude + target_vector + duck_vision */
+        return att + 3 + 9 * c->vision_hist_len + (c->vision_use_deltas ? 4 : 0);
     return att + 3 * c->context_len;
 }
 
@@ -327,7 +329,7 @@ static int ground_contact(const fwo_config* c, const fwo_env* e, const double R[
 }
 
 static int obstacle_contact(const fwo_config* c, const fwo_env* e, const double R[9]) {
-    if (c->task != FWO_TASK_OBJLOCK) return 0;
+    if (c->task != FWO_TASK_OBJLOCK && c->task != FWO_TASK_DUCK) return 0;
     for (int i = 0; i < c->n_col; ++i) {
         double p[3], pw[3];
         p[0] = c->col_pts[i][0]; p[1] = c->col_pts[i][1]; p[2] = c->col_pts[i][2];
@@ -514,8 +516,17 @@ static void capture_frame(const fwo_config* c, fwo_env* e) {
     double off_w[3], cam[3], f[3], up[3] = {R[2], R[5], R[8]}, r[3], u[3];
     mat_vec(R, c->cam_offset, off_w);
     for (int k = 0; k < 3; ++k) cam[k] = e->pos[k] + off_w[k];
-    double ol = sqrt(dot3(off_w, off_w));
-    for (int k = 0; k < 3; ++k) f[k] = -off_w[k] / ol;
+    if (c->cam_mode == 0) {                       /* tracking camera: target = the aircraft, up = body z */
+        double ol = sqrt(dot3(off_w, off_w));
+        for (int k = 0; k < 3; ++k) f[k] = -off_w[k] / ol;
+    } else {
+        /* [UP-RECALL] PyFlyt Camera with is_tracking_camera = False (fixedwing_objlock_env.py:226-227): the camera sits at
+         * the offset and looks along the body x axis rotated about body +y by camera_angle_degrees */
+        double t = c->cam_tilt_deg * M_PI / 180.0;
+        double fb[3] = {cos(t), 0.0, -sin(t)}, ub[3] = {sin(t), 0.0, cos(t)};
+        mat_vec(R, fb, f);
+        mat_vec(R, ub, up);
+    }
     cross3(f, up, r);
     double rl = sqrt(dot3(r, r));
     for (int k = 0; k < 3; ++k) r[k] /= rl;
@@ -609,12 +620,62 @@ static void aviary_step(const fwo_config* c, fwo_env* e, uint64_t seed) {
     e->contact = 0;                                   /* contact_array &= False */
     for (int i = 0; i < c->substeps_per_inner; ++i) fwo_substep(c, e, seed);
     /* drone.update_last(): camera */
-    if (c->task == FWO_TASK_OBJLOCK && c->cam_interval_substeps > 0 &&
+    if ((c->task == FWO_TASK_OBJLOCK || c->task == FWO_TASK_DUCK) && c->cam_interval_substeps > 0 &&
         e->physics_steps % c->cam_interval_substeps == 0)
         capture_frame(c, e);
 }
 
+/* FixedwingObjLockEnv._build_duck_vision_observation (fixedwing_objlock_env.py:421-459): push the newest nine
+ * features into the history (row 0 = newest) and derive the four frame-to-frame deltas */
+static void duck_push_history(const fwo_config* c, fwo_env* e) {
+    const int H = c->vision_hist_len;
+    double prev[9];
+    for (int k = 0; k < 9; ++k) prev[k] = H >= 2 ? e->vis_hist[0][k] : 0.0;
+    for (int h = H - 1; h >= 1; --h)
+        for (int k = 0; k < 9; ++k) e->vis_hist[h][k] = e->vis_hist[h - 1][k];
+    for (int k = 0; k < 9; ++k) e->vis_hist[0][k] = e->vision[k];
+    e->hist_filled = e->hist_filled + 1 < H ? e->hist_filled + 1 : H;
+    for (int k = 0; k < 4; ++k) e->vis_deltas[k] = 0.0;
+    if (e->hist_filled >= 2 && e->vision[0] > 0.5 && prev[0] > 0.5)
+        for (int k = 0; k < 4; ++k) e->vis_deltas[k] = (double)(float)(e->vision[1 + k] - prev[1 + k]);
+}
+
+/* FixedwingObjLockEnv.compute_state (fixedwing_objlock_env.py:253-287) + FlattenObjLockEnv._flatten_obs
+ * (flatten_objlock_env.py:41-46).  update != 0: a live compute_state (advances the vision state and the history);
+ * update == 0: re-emit the observation of the current state. */
+static void duck_compute_obs(const fwo_config* c, fwo_env* e, double* obs, int update) {
+    double R[9], rpy[3], q2[4], R2[9], wb[3], vb[3];
+    fwo_quat_to_mat(e->quat, R);
+    fwo_quat_to_euler(e->quat, rpy);
+    fwo_euler_to_quat(rpy, q2);
+    fwo_quat_to_mat(q2, R2);
+    matT_vec(R, e->omega, wb);
+    matT_vec(R, e->vel, vb);
+    double d[3] = {e->duck_pos[0] - e->pos[0], e->duck_pos[1] - e->pos[1], e->duck_pos[2] - e->pos[2]};
+    matT_vec(R2, d, e->target_vec);
+    if (update) {
+        vision_features(c, e);
+        duck_push_history(c, e);
+    }
+    if (!obs) return;
+    int k = 0;
+    for (int i = 0; i < 3; ++i) obs[k++] = wb[i];
+    if (c->angle_repr == 0) { for (int i = 0; i < 3; ++i) obs[k++] = rpy[i]; }
+    else { for (int i = 0; i < 4; ++i) obs[k++] = q2[i]; }
+    for (int i = 0; i < 3; ++i) obs[k++] = vb[i];
+    for (int i = 0; i < 3; ++i) obs[k++] = e->pos[i];
+    for (int i = 0; i < 4; ++i) obs[k++] = e->last_action[i];
+    for (int i = 0; i < FWO_NSURF; ++i) obs[k++] = e->act[i];
+    obs[k++] = e->throttle;
+    for (int i = 0; i < 3; ++i) obs[k++] = e->target_vec[i];
+    for (int h = 0; h < c->vision_hist_len; ++h)
+        for (int i = 0; i < 9; ++i) obs[k++] = e->vis_hist[h][i];
+    if (c->vision_use_deltas)
+        for (int i = 0; i < 4; ++i) obs[k++] = e->vis_deltas[i];
+}
+
 void fwo_compute_obs(const fwo_config* c, fwo_env* e, double* obs, int update_dist) {
+    if (c->task == FWO_TASK_DUCK) { duck_compute_obs(c, e, obs, update_dist); return; }
     double R[9], rpy[3], q2[4], R2[9];
     fwo_quat_to_mat(e->quat, R);
     fwo_quat_to_euler(e->quat, rpy);
@@ -693,6 +754,49 @@ static void obstacle_penalty(const fwo_config* c, fwo_env* e, int is_duck_phase)
     e->reward -= pen;
 }
 
+/* FixedwingObjLockEnv.compute_term_trunc_reward after the base flags (fixedwing_objlock_env.py:293-372) */
+static void duck_reward(const fwo_config* c, fwo_env* e) {
+    if (e->info_collision || e->info_oob) return;                   /* :293-294 */
+    obstacle_penalty(c, e, 1);                                      /* :376-407, always the halved scale */
+    const double dist = sqrt(dot3(e->target_vec, e->target_vec));
+    if (!c->sparse_reward) {
+        e->reward += c->duck_dist_scale / fmax(dist, 2.0);
+        /* the reward reads the newest history row, which is the float32 feature vector of this compute_state */
+        const double* v = e->vis_hist[0];
+        if (v[0] > 0.5) {
+            const double cx = v[1], cy = v[2], area = v[3], est = v[4];
+            e->reward += c->visible_step_reward;
+            e->reward += c->area_reward_scale * fmax(0.0, area);
+            const double dc = sqrt((cx - 0.5) * (cx - 0.5) + (cy - 0.5) * (cy - 0.5));
+            const double rl = fmax(c->lock_center_radius, 1e-6);
+            e->reward += c->centering_scale * fmax(0.0, (rl - dc) / rl);
+            if (dc < rl) {
+                e->lock_steps = e->lock_steps + 1 < c->lock_hold_steps ? e->lock_steps + 1 : c->lock_hold_steps;
+                e->reward += c->lock_step_reward;
+            } else {
+                e->lock_steps = e->lock_steps - c->lock_decay_steps > 0 ? e->lock_steps - c->lock_decay_steps : 0;
+            }
+            if (e->has_prev_dist && est > 0.0 && isfinite(est)) {
+                double diff = e->prev_est_dist - est;
+                if (c->approach_clip > 0.0) diff = diff < -c->approach_clip ? -c->approach_clip : (diff > c->approach_clip ? c->approach_clip : diff);
+                e->reward += diff * c->approach_scale;
+            }
+            if (est > 0.0 && isfinite(est)) { e->prev_est_dist = est; e->has_prev_dist = 1; }
+            else { e->prev_est_dist = 0.0; e->has_prev_dist = 0; }
+        } else {
+            if (e->lock_steps > 0) e->reward -= c->lock_lost_penalty;
+            e->lock_steps = e->lock_steps - c->lock_decay_steps > 0 ? e->lock_steps - c->lock_decay_steps : 0;
+            e->prev_est_dist = 0.0; e->has_prev_dist = 0;
+        }
+    }
+    if (e->lock_steps >= c->lock_hold_steps && dist <= c->strike_dist) {           /* :366-372 */
+        e->termination = 1;
+        e->reward += c->strike_reward;
+        e->info_complete = 1;
+        e->info_strike = 1;
+    }
+}
+
 static void term_trunc_reward(const fwo_config* c, fwo_env* e) {
     /* compute_base_term_trunc_reward */
     if (e->step_count > c->max_steps) e->truncation = 1;
@@ -700,6 +804,7 @@ static void term_trunc_reward(const fwo_config* c, fwo_env* e) {
     double p2 = dot3(e->pos, e->pos);
     if (sqrt(p2) > c->dome) { e->reward = -100.0; e->info_oob = 1; e->termination = 1; }
     if (c->task == FWO_TASK_PHYSICS) return;
+    if (c->task == FWO_TASK_DUCK) { duck_reward(c, e); return; }
     if (c->early_return_on_crash && (e->info_collision || e->info_oob)) return;
 
     if (c->task == FWO_TASK_WAYPOINTS) {
@@ -820,6 +925,36 @@ static void spawn_duck_obstacles(const fwo_config* c, fwo_env* e, uint64_t seed)
     }
 }
 
+/* FixedwingObjLockEnv._reset_duck_state / _spawn_duck / _spawn_obstacles (fixedwing_objlock_env.py:409-419,461-578) */
+static void spawn_duck_only(const fwo_config* c, fwo_env* e, uint64_t seed) {
+    e->duck_phase = 0; e->seen_consecutive = 0; e->lock_steps = 0; e->has_prev_dist = 0; e->prev_est_dist = 0.0;
+    e->last_cx = 0.5; e->last_cy = 0.5; e->last_area = 0.0; e->last_depth = 0.0;
+    e->steps_since_seen = 60; e->post_waypoints = 0; e->cam_valid = 0; e->frame_visible = 0;
+    memset(e->vision, 0, sizeof(e->vision));
+    memset(e->vis_hist, 0, sizeof(e->vis_hist));
+    memset(e->vis_deltas, 0, sizeof(e->vis_deltas));
+    e->hist_filled = 0;
+    e->n_remaining = 0; e->target_idx = 0;
+    e->old_dist = INFINITY; e->new_dist = INFINITY;
+    uint32_t r[4];
+    fwo_philox(seed, e->env_id, e->episode, 0u, STREAM_DUCK, r);       /* x, y ~ U(-dome/2, dome/2); yaw unused (sphere) */
+    e->duck_pos[0] = -c->dome / 2 + fwo_u01(r[0]) * c->dome;
+    e->duck_pos[1] = -c->dome / 2 + fwo_u01(r[1]) * c->dome;
+    e->duck_pos[2] = 0.05;
+    e->n_obst = 0;
+    for (int i = 0; i < c->num_obstacles; ++i) {
+        fwo_philox(seed, e->env_id, e->episode, (uint32_t)i, STREAM_OBST, r);
+        double h = c->obst_h_lo + fwo_u01(r[0]) * (c->obst_h_hi - c->obst_h_lo);
+        double x = -c->dome / 2 + fwo_u01(r[1]) * c->dome;
+        double y = -c->dome / 2 + fwo_u01(r[2]) * c->dome;
+        double dx = x - e->duck_pos[0], dy = y - e->duck_pos[1];
+        if (sqrt(dx * dx + dy * dy) < 10.0) continue;                  /* :536-539 */
+        if (x * x + y * y < 100.0) continue;                           /* :542-543 */
+        e->obst[e->n_obst][0] = x; e->obst[e->n_obst][1] = y; e->obst[e->n_obst][2] = h;
+        e->n_obst++;
+    }
+}
+
 /* FixedwingLowLevelEnv._compute_obs (fixedwing_lowlevel_env.py:143-156): Aviary.state(0) flattened
  * [ang_vel_body, euler, lin_vel_body, lin_pos] + previous action (6) + target (3) */
 static void lowlevel_obs(const fwo_config* c, fwo_env* e, double* obs) {
@@ -879,7 +1014,8 @@ void fwo_reset(const fwo_config* c, fwo_env* e, uint64_t seed, uint32_t env_id, 
         e->target_ref[0] = -M_PI + 2.0 * M_PI * fwo_u01(r[0]);
         e->target_ref[1] = 5.0 + 15.0 * fwo_u01(r[1]);
         e->target_ref[2] = 10.0 + 10.0 * fwo_u01(r[2]);
-    } else if (c->task != FWO_TASK_PHYSICS) sample_targets(c, e, seed);
+    } else if (c->task == FWO_TASK_DUCK) spawn_duck_only(c, e, seed);
+    else if (c->task != FWO_TASK_PHYSICS) sample_targets(c, e, seed);
     if (c->task == FWO_TASK_OBJLOCK) spawn_duck_obstacles(c, e, seed);
     /* end_reset: set_mode(0) -> zero setpoint; 10 x Aviary.step; compute_state */
     for (int i = 0; i < c->warmup_inner; ++i) aviary_step(c, e, seed);

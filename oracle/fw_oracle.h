@@ -26,7 +26,8 @@ extern "C" {
 #define FWO_MAX_TARGETS 16
 #define FWO_MAX_COL 16
 #define FWO_MAX_OBST 32
-#define FWO_MAX_OBS 40
+#define FWO_MAX_OBS 72
+#define FWO_MAX_HIST 4     /* duck-only task: frames of vision history in the observation */
 
 /* flag bits returned by a step (same meaning as include/fwsim.h, restated independently) */
 #define FWO_TERM      1
@@ -41,6 +42,7 @@ extern "C" {
 #define FWO_TASK_WAYPOINTS 1  /* PyFlyt/Fixedwing-Waypoints-v3 + FlattenWaypointEnv */
 #define FWO_TASK_OBJLOCK   2  /* FixedwingWaypointObjLockEnv + FlattenWaypointEnv */
 #define FWO_TASK_LOWLEVEL  3  /* FixedwingLowLevelEnv: mode -1 six-channel control, psi/h/V tracking (fixedwing_lowlevel_env.py) */
+#define FWO_TASK_DUCK      4  /* FixedwingObjLockEnv + FlattenObjLockEnv: duck-only lock/strike, vision-history obs (fixedwing_objlock_env.py) */
 #define FWO_MAX_ACT 6
 
 typedef struct {
@@ -115,6 +117,16 @@ typedef struct {
     double cam_offset[3];            /* camera position offset, body frame (-3,0,1) */
     double cam_near, cam_far;
     int32_t cam_res;                 /* 128 */
+    int32_t cam_mode;                /* 0: tracking chase camera, looks at the aircraft from cam_offset;
+                                      * 1: fixed camera at cam_offset looking along the body x axis tilted by cam_tilt_deg
+                                      *    (is_tracking_camera = False, fixedwing_objlock_env.py:184-231) */
+    /* ---- duck-only task (FWO_TASK_DUCK): fixedwing_objlock_env.py:37-118 ---- */
+    double cam_tilt_deg;             /* camera_angle_degrees; [UP-RECALL] rotation about body +y, positive = nose-down */
+    double duck_dist_scale, lock_center_radius, centering_scale, visible_step_reward, area_reward_scale;
+    double lock_lost_penalty, approach_clip;
+    int32_t vision_hist_len;         /* duck_vision_history_len, 1..FWO_MAX_HIST */
+    int32_t vision_use_deltas;       /* duck_vision_use_deltas */
+    int32_t lock_decay_steps;        /* duck_lock_decay_steps (>= 1) */
     int32_t _pad1;
 } fwo_config;
 
@@ -157,6 +169,11 @@ typedef struct {
     int32_t frame_visible; int32_t _pad;
     double frame_cx, frame_cy, frame_area, frame_depth, frame_dl, frame_dc, frame_dr;
     double ep_return; int32_t ep_length; int32_t _pad2;
+    /* duck-only task: _vision_history (row 0 = newest), the four delta features, _vision_history_filled */
+    double vis_hist[FWO_MAX_HIST][9];
+    double vis_deltas[4];
+    double target_vec[3];            /* state["target_vector"]: duck position relative to the aircraft, body frame */
+    int32_t hist_filled; int32_t _pad3;
 } fwo_env;
 
 /* size checks for the ctypes mirror */

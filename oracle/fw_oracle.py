@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libfw_oracle.so")
 
-NSURF, MAX_TARGETS, MAX_COL, MAX_OBST, MAX_OBS = 5, 16, 16, 32, 40
+NSURF, MAX_TARGETS, MAX_COL, MAX_OBST, MAX_OBS, MAX_HIST = 5, 16, 16, 32, 72, 4
 _D, _I, _U = C.c_double, C.c_int32, C.c_uint32
 _V3 = _D * 3
 
@@ -48,7 +48,10 @@ class OConfig(C.Structure):
         ("lock_hold_steps", _I), ("switch_min_seen", _I),
         ("strike_dist", _D), ("strike_reward", _D), ("lock_step_reward", _D), ("approach_scale", _D),
         ("switch_min_area", _D), ("duck_radius", _D), ("cam_offset", _V3), ("cam_near", _D), ("cam_far", _D),
-        ("cam_res", _I), ("_pad1", _I),
+        ("cam_res", _I), ("cam_mode", _I),
+        ("cam_tilt_deg", _D), ("duck_dist_scale", _D), ("lock_center_radius", _D), ("centering_scale", _D),
+        ("visible_step_reward", _D), ("area_reward_scale", _D), ("lock_lost_penalty", _D), ("approach_clip", _D),
+        ("vision_hist_len", _I), ("vision_use_deltas", _I), ("lock_decay_steps", _I), ("_pad1", _I),
     ]
 
 
@@ -70,6 +73,7 @@ class OEnv(C.Structure):
         ("frame_cx", _D), ("frame_cy", _D), ("frame_area", _D), ("frame_depth", _D), ("frame_dl", _D),
         ("frame_dc", _D), ("frame_dr", _D),
         ("ep_return", _D), ("ep_length", _I), ("_pad2", _I),
+        ("vis_hist", (_D * 9) * MAX_HIST), ("vis_deltas", _D * 4), ("target_vec", _V3), ("hist_filled", _I), ("_pad3", _I),
     ]
 
 
@@ -207,7 +211,7 @@ class OracleVecEnv:
             out["physics_steps"][i] = e.physics_steps; out["episode"][i] = e.episode
             out["new_dist"][i] = e.new_dist if np.isfinite(e.new_dist) else 0.0
             out["wind"][i, :3] = e.wind_base[:]; out["wind"][i, 3:6] = e.gust_amp[:]; out["wind"][i, 6] = e.gust_phase
-        if self.cfg.task == 2:
+        if self.cfg.task in (2, 4):
             out["duck"] = np.zeros((n, 3)); out["obst"] = np.zeros((n, MAX_OBST, 3))
             out["ol_f"] = np.zeros((n, 12)); out["ol_i"] = np.zeros((n, 9), np.int32)
             for i in range(n):
@@ -219,6 +223,14 @@ class OracleVecEnv:
                                   e.frame_depth, e.frame_dl, e.frame_dc, e.frame_dr, e.prev_est_dist]
                 out["ol_i"][i] = [e.duck_phase, e.has_prev_dist, e.post_waypoints, e.cam_valid, e.frame_visible,
                                   e.seen_consecutive, e.lock_steps, e.steps_since_seen, e.n_obst]
+        if self.cfg.task == 4:                           # duck-only task: history rows (newest first), deltas; slot 5 = filled
+            out["vis_hist"] = np.zeros((n, MAX_HIST * 9 + 4))
+            for i in range(n):
+                e = self.envs[i]
+                for h in range(MAX_HIST):
+                    out["vis_hist"][i, h * 9:(h + 1) * 9] = e.vis_hist[h][:]
+                out["vis_hist"][i, MAX_HIST * 9:] = e.vis_deltas[:]
+                out["ol_i"][i, 5] = e.hist_filled
         return out
 
     def set_state(self, s: dict) -> None:
@@ -257,6 +269,13 @@ class OracleVecEnv:
                 v = [int(x) for x in s["ol_i"][i]]
                 (e.duck_phase, e.has_prev_dist, e.post_waypoints, e.cam_valid, e.frame_visible, e.seen_consecutive,
                  e.lock_steps, e.steps_since_seen, e.n_obst) = v
+                if self.cfg.task == 4:
+                    e.hist_filled = v[5]
+            if "vis_hist" in s and self.cfg.task == 4:
+                vh = [float(x) for x in s["vis_hist"][i]]
+                for h in range(MAX_HIST):
+                    e.vis_hist[h][:] = vh[h * 9:(h + 1) * 9]
+                e.vis_deltas[:] = vh[MAX_HIST * 9:MAX_HIST * 9 + 4]
             if "obst" in s:
                 for k in range(MAX_OBST):
                     e.obst[k][:] = [float(x) for x in s["obst"][i][k]]

@@ -2,9 +2,9 @@
 
 Host side is Python; the env step is hand-written sm_100a CUDA in libfwsim.so (C ABI: include/fwsim.h).
 """
-from .config import EnvConfig, from_gym_kwargs, make_config, waypoints_v3, waypoint_objlock, physics_only, lowlevel  # noqa: F401
+from .config import EnvConfig, from_gym_kwargs, make_config, waypoints_v3, waypoint_objlock, physics_only, lowlevel, objlock_duck  # noqa: F401
 
-__all__ = ["EnvConfig", "make_config", "from_gym_kwargs", "waypoints_v3", "waypoint_objlock", "physics_only", "lowlevel",
+__all__ = ["EnvConfig", "make_config", "from_gym_kwargs", "waypoints_v3", "waypoint_objlock", "physics_only", "lowlevel", "objlock_duck",
            "FixedwingVecEnv"]
 
 

@@ -16,6 +16,7 @@ class FwStateHostC(C.Structure):
         ("targets", C.c_void_p), ("target_idx", C.c_void_p), ("step_count", C.c_void_p),
         ("physics_steps", C.c_void_p), ("episode", C.c_void_p), ("new_dist", C.c_void_p), ("wind", C.c_void_p),
         ("duck", C.c_void_p), ("obst", C.c_void_p), ("ol_f", C.c_void_p), ("ol_i", C.c_void_p),
+        ("vis_hist", C.c_void_p),
     ]
 
 

@@ -18,7 +18,8 @@ from . import aircraft
 
 NSURF, MAX_TARGETS, MAX_COL, MAX_OBST = 5, 16, 16, 32
 
-TASK_PHYSICS, TASK_WAYPOINTS, TASK_OBJLOCK, TASK_LOWLEVEL = 0, 1, 2, 3
+TASK_PHYSICS, TASK_WAYPOINTS, TASK_OBJLOCK, TASK_LOWLEVEL, TASK_DUCK = 0, 1, 2, 3, 4
+MAX_HIST = 4
 
 FLAG_TERM, FLAG_TRUNC, FLAG_COLLISION, FLAG_OOB, FLAG_COMPLETE, FLAG_STRIKE = 1, 2, 4, 8, 16, 32
 
@@ -50,6 +51,8 @@ class FwConfigC(C.Structure):
         ("strike_dist", _D), ("strike_reward", _D), ("lock_step_reward", _D), ("approach_scale", _D),
         ("switch_min_area", _D),
         ("duck_radius", _D), ("cam_offset", _D * 3), ("cam_near", _D), ("cam_far", _D),
+        ("cam_tilt_deg", _D), ("duck_dist_scale", _D), ("lock_center_radius", _D), ("centering_scale", _D),
+        ("visible_step_reward", _D), ("area_reward_scale", _D), ("lock_lost_penalty", _D), ("approach_clip", _D),
         ("n_col", _I),
         ("physics_per_control", _I), ("substeps_per_inner", _I), ("inner_per_step", _I), ("warmup_inner", _I),
         ("freestream_3d", _I), ("cd90_degrees", _I),
@@ -60,7 +63,8 @@ class FwConfigC(C.Structure):
         ("num_obstacles", _I), ("cam_interval_substeps", _I), ("lock_hold_steps", _I), ("switch_min_seen", _I),
         ("cam_res", _I),
         ("force_generic_kernel", _I),
-        ("_reserved", _I * 5),
+        ("cam_mode", _I), ("vision_hist_len", _I), ("vision_use_deltas", _I), ("lock_decay_steps", _I),
+        ("_reserved", _I * 1),
     ]
 
 
@@ -162,6 +166,19 @@ class EnvConfig:
     cam_near: float = 0.1
     cam_far: float = 255.0
     cam_res: int = 128
+    cam_mode: int = 0                                    # 0 tracking chase camera, 1 fixed (cockpit) camera tilted by cam_tilt_deg
+    # ---- duck-only task (defaults of FixedwingObjLockEnv.__init__, envs/fixedwing_objlock_env.py:37-81) ----
+    cam_tilt_deg: float = 0.0                            # camera_angle_degrees; [UP-RECALL] about body +y, positive = nose-down
+    duck_dist_scale: float = 1.0
+    lock_center_radius: float = 0.55
+    centering_scale: float = 3.0
+    visible_step_reward: float = 2.0
+    area_reward_scale: float = 5.0
+    lock_lost_penalty: float = 0.5
+    approach_clip: float = 2.0
+    vision_hist_len: int = 3
+    vision_use_deltas: int = 1
+    lock_decay_steps: int = 1
     force_generic_kernel: int = 0                       # testing: run the generic kernels even for the standard layout
 
     # ------------------------------------------------------------------
@@ -169,7 +186,12 @@ class EnvConfig:
     def obs_dim(self) -> int:
         if self.task == TASK_PHYSICS:
             return 0
-        return (12 if self.angle_repr == 0 else 13) + 4 + 6 + 3 * self.context_len
+        if self.task == TASK_LOWLEVEL:
+            return 21
+        att = (12 if self.angle_repr == 0 else 13) + 4 + 6
+        if self.task == TASK_DUCK:                        # flatten_objlock_env.py:20-31
+            return att + 3 + 9 * self.vision_hist_len + (4 if self.vision_use_deltas else 0)
+        return att + 3 * self.context_len
 
     @property
     def n_col(self) -> int:
@@ -316,8 +338,33 @@ def lowlevel(wind: dict | None = None, **overrides) -> EnvConfig:
     return cfg.replace(**overrides) if overrides else cfg
 
 
+def objlock_duck(wind: dict | None = None, **overrides) -> EnvConfig:
+    """FixedwingObjLockEnv + FlattenObjLockEnv as built by train/train_objlock.py:27-146 (duck-only lock and strike):
+    start (0,0,100), 200 m dome, 60 s episodes, cockpit camera (offset (0.8,0,0.12), -5 deg, not tracking) captured every
+    2*12 physics steps at render_resolution 480 (render_mode="rgb_array"), no obstacles, 3-frame vision history + deltas,
+    56-float observation.  duck_radius is the analytic stand-in for the duck mesh at globalScaling 60 (0.05 m per unit
+    of scaling, the ratio the waypoint_objlock preset uses at scaling 30)."""
+    if wind is None:
+        wind = {
+            "enabled": True, "mode": "gust_sine", "wind_enu_mps": [0.0, 0.0, 0.0],
+            "wind_enu_mps_range": [[-10.0, 10.0], [-10.0, 10.0], [-0.10, 0.10]],
+            "gust_amp_enu_mps": [0.0, 0.0, 0.0], "gust_amp_enu_mps_range": [[0.0, 3.0], [0.0, 3.0], [0.0, 0.3]],
+            "gust_freq_hz": 0.2, "gust_phase_rad": 0.0, "randomize_on_reset": True, "randomize_gust_phase": True,
+        }
+    cfg = EnvConfig(
+        task=TASK_DUCK, num_targets=0, sparse_reward=0, angle_repr=0, dome=200.0, spawn_size=200.0,
+        max_steps=int(30 * 60.0), context_len=0, start_pos=[0.0, 0.0, 100.0], early_return_on_crash=1, complete_truncates=0,
+        num_obstacles=0, obst_radius=2.0, obst_h_lo=10.0, obst_h_hi=30.0, obst_safe=10.0, obst_scale=1.0, obst_max_pen=5.0,
+        cam_interval_substeps=2 * 12, lock_hold_steps=5, strike_dist=10.0, strike_reward=400.0, lock_step_reward=0.2,
+        approach_scale=0.1, duck_radius=3.0, cam_mode=1, cam_offset=[0.8, 0.0, 0.12], cam_tilt_deg=-5.0, cam_res=480,
+        vision_hist_len=3, vision_use_deltas=1,
+        **_wind_fields(wind, "env"),
+    ).with_aircraft()
+    return cfg.replace(**overrides) if overrides else cfg
+
+
 PRESETS = {"waypoints_v3": waypoints_v3, "waypoint_objlock": waypoint_objlock, "physics_only": physics_only,
-           "lowlevel": lowlevel}
+           "lowlevel": lowlevel, "objlock_duck": objlock_duck}
 
 
 def from_gym_kwargs(preset: str = "waypoints_v3", *, sparse_reward=None, num_targets=None, goal_reach_distance=None,

@@ -82,11 +82,19 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
     memset(&d, 0, sizeof(d));
     const double PI = 3.14159265358979323846, DEG = PI / 180.0;
     if (!(c.dt > 0) || !(c.mass > 0)) return fail(FW_EINVAL, "dt and mass must be positive");
-    if (c.task < 0 || c.task > 3) return fail(FW_EINVAL, "task %d unknown (0 physics, 1 waypoints, 2 waypoint+objlock, 3 low-level)", c.task);
-    if (c.task == 2 && (c.num_obstacles < 0 || c.num_obstacles > FW_MAX_OBST)) return fail(FW_EINVAL, "num_obstacles out of range");
-    if (c.task == 2 && (c.cam_res < 3 || c.cam_res > 1024)) return fail(FW_EINVAL, "cam_res out of range");
+    if (c.task < 0 || c.task > 4) return fail(FW_EINVAL, "task %d unknown (0 physics, 1 waypoints, 2 waypoint+objlock, 3 low-level, 4 duck-only objlock)", c.task);
+    const bool cam_task = c.task == 2 || c.task == 4;
+    if (cam_task && (c.num_obstacles < 0 || c.num_obstacles > FW_MAX_OBST)) return fail(FW_EINVAL, "num_obstacles out of range");
+    if (cam_task && (c.cam_res < 3 || c.cam_res > 1024)) return fail(FW_EINVAL, "cam_res out of range");
+    if (cam_task && c.cam_mode != 0 && c.cam_mode != 1) return fail(FW_EINVAL, "cam_mode must be 0 (tracking) or 1 (fixed)");
+    if (cam_task && c.cam_mode == 0 && c.cam_offset[0] == 0 && c.cam_offset[1] == 0 && c.cam_offset[2] == 0)
+        return fail(FW_EINVAL, "a tracking camera needs a non-zero cam_offset");
+    if (c.task == 4 && (c.vision_hist_len < 1 || c.vision_hist_len > FW_MAX_HIST)) return fail(FW_EINVAL, "vision_hist_len out of range (1..%d)", FW_MAX_HIST);
+    if (c.task == 4 && c.lock_decay_steps < 1) return fail(FW_EINVAL, "lock_decay_steps must be >= 1");
+    if (c.task == 4 && c.context_len != 0) return fail(FW_EINVAL, "the duck-only task has no waypoint context (context_len must be 0)");
     if (c.num_targets < 0 || c.num_targets > FW_MAX_TARGETS) return fail(FW_EINVAL, "num_targets out of range");
-    if (c.task != 0 && c.num_targets < 1) return fail(FW_EINVAL, "waypoint task needs num_targets >= 1");
+    if (c.task != 0 && c.task != 4 && c.num_targets < 1) return fail(FW_EINVAL, "waypoint task needs num_targets >= 1");
+    if (c.task == 4 && c.num_targets != 0) return fail(FW_EINVAL, "the duck-only task has no waypoints (num_targets must be 0)");
     if (c.context_len < 0 || c.context_len > 4) return fail(FW_EINVAL, "context_len out of range");
     if (c.n_col < 0 || c.n_col > FW_MAX_COL) return fail(FW_EINVAL, "n_col out of range");
     if (c.physics_per_control < 1 || c.substeps_per_inner < 1 || c.inner_per_step < 1 || c.warmup_inner < 0)
@@ -191,6 +199,7 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
     d.task = c.task; d.num_targets = c.num_targets; d.sparse_reward = c.sparse_reward; d.angle_repr = c.angle_repr;
     d.max_steps = c.max_steps; d.context_len = c.context_len;
     d.obs_dim = c.task == 0 ? 0 : (c.task == 3 ? 21 : ((c.angle_repr == 0 ? 12 : 13) + 4 + 6 + 3 * c.context_len));
+    if (c.task == 4) d.obs_dim += 3 + 9 * c.vision_hist_len + (c.vision_use_deltas ? 4 : 0);   // flatten_objlock_env.py:20-31
     d.act_dim = c.task == 3 ? 6 : 4;
     d.early_return_on_crash = c.early_return_on_crash; d.complete_truncates = c.complete_truncates;
     d.goal_reach = (float)c.goal_reach; d.dome = (float)c.dome; d.dome2 = (float)(c.dome * c.dome); d.spawn_size = (float)c.spawn_size; d.min_height = (float)c.min_height;
@@ -210,6 +219,18 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
     d.approach_scale = (float)c.approach_scale; d.switch_min_area = (float)c.switch_min_area;
     d.duck_radius = (float)c.duck_radius; d.cam_near = (float)c.cam_near; d.cam_far = (float)c.cam_far;
     for (int k = 0; k < 3; ++k) d.cam_offset[k] = (float)c.cam_offset[k];
+    d.cam_mode = c.cam_mode;
+    {   // fixed camera: forward and up hint = body x and z rotated about body +y by the tilt (positive = nose-down)
+        const double t = c.cam_tilt_deg * DEG;
+        d.cam_fb[0] = (float)cos(t); d.cam_fb[1] = 0.0f; d.cam_fb[2] = (float)(-sin(t));
+        d.cam_ub[0] = (float)sin(t); d.cam_ub[1] = 0.0f; d.cam_ub[2] = (float)cos(t);
+    }
+    d.hist_len = c.task == 4 ? c.vision_hist_len : 0; d.use_deltas = c.vision_use_deltas; d.lock_decay = c.lock_decay_steps;
+    d.hist_slots = c.task == 4 ? 9 * c.vision_hist_len + 4 : 0;
+    d.duck_dist_scale = (float)c.duck_dist_scale; d.lock_center_radius = (float)c.lock_center_radius;
+    d.centering_scale = (float)c.centering_scale; d.visible_step_reward = (float)c.visible_step_reward;
+    d.area_reward_scale = (float)c.area_reward_scale; d.lock_lost_penalty = (float)c.lock_lost_penalty;
+    d.approach_clip = (float)c.approach_clip;
     d.warm_cached = 0;
     d.seed_lo = (uint32_t)(seed & 0xffffffffu); d.seed_hi = (uint32_t)(seed >> 32); d.env_id0 = env_id0;
     d.n = n;
@@ -267,17 +288,19 @@ extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, ui
     if (rc != FW_OK) { delete h; return rc; }
     h->obs_dim = h->dev.obs_dim;
     const size_t N = (size_t)n_envs, T = (size_t)(cfg->num_targets > 0 ? cfg->num_targets : 1);
-    size_t off = 0, o_s[6], o_w0, o_w1, o_t, o_ep, o_st, o_ol[5] = {0, 0, 0, 0, 0}, o_ob = 0;
+    size_t off = 0, o_s[6], o_w0, o_w1, o_t, o_ep, o_st, o_ol[5] = {0, 0, 0, 0, 0}, o_ob = 0, o_hist = 0;
+    const bool cam_task = cfg->task == 2 || cfg->task == 4;
     for (int k = 0; k < 6; ++k) { o_s[k] = off; off = align_up(off + N * 16, 256); }
     o_w0 = off; off = align_up(off + N * 16, 256);
     o_w1 = off; off = align_up(off + N * 16, 256);
     o_t = off; off = align_up(off + T * 3 * N * 4, 256);
     o_ep = off; off = align_up(off + N * 4, 256);
     o_st = off; off = align_up(off + 8 * sizeof(double), 256);
-    if (cfg->task == 2) {
+    if (cam_task) {
         for (int k = 0; k < 5; ++k) { o_ol[k] = off; off = align_up(off + N * 16, 256); }
         o_ob = off; off = align_up(off + (size_t)FW_MAX_OBST * 3 * N * 4, 256);
     }
+    if (cfg->task == 4) { o_hist = off; off = align_up(off + (size_t)h->dev.hist_slots * N * 4, 256); }
     h->plane_bytes = off;
     ce = cudaMalloc((void**)&h->plane_mem, off);
     if (ce != cudaSuccess) { delete h; return fail(FW_ENOMEM, "cudaMalloc(%zu): %s", off, cudaGetErrorString(ce)); }
@@ -289,7 +312,8 @@ extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, ui
     pl.w0 = (float4*)(h->plane_mem + o_w0); pl.w1 = (float4*)(h->plane_mem + o_w1);
     pl.targets = (float*)(h->plane_mem + o_t); pl.ep_ret = (float*)(h->plane_mem + o_ep);
     pl.stats = (double*)(h->plane_mem + o_st);
-    if (cfg->task == 2) {
+    if (cfg->task == 4) pl.hist = (float*)(h->plane_mem + o_hist);
+    if (cam_task) {
         pl.dk = (float4*)(h->plane_mem + o_ol[0]); pl.v0 = (float4*)(h->plane_mem + o_ol[1]);
         pl.v1 = (float4*)(h->plane_mem + o_ol[2]); pl.v2 = (float4*)(h->plane_mem + o_ol[3]);
         pl.v3 = (int4*)(h->plane_mem + o_ol[4]); pl.obst = (float*)(h->plane_mem + o_ob);
@@ -302,7 +326,7 @@ extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, ui
 
 
     // cache the deterministic warm-up result when no wind acts during it
-    if (h->dev.task != 2 && (h->dev.wind_mode == 0 || h->dev.wind_start_substep >= h->dev.warmup_substeps)) {
+    if (!cam_task && (h->dev.wind_mode == 0 || h->dev.wind_start_substep >= h->dev.warmup_substeps)) {
         float* d_warm = nullptr;
         CU(cudaMalloc((void**)&d_warm, 20 * sizeof(float)));
         CU(fwk_launch_warm(h->dev, h->pl, d_warm, h->io_stream));
@@ -524,6 +548,7 @@ struct HostPlanes {
     std::vector<float4> dk, v0, v1, v2;
     std::vector<int4> v3;
     std::vector<float> obst;
+    std::vector<float> hist;
 };
 
 static int pull(FwSim* h, HostPlanes& hp) {
@@ -535,7 +560,11 @@ static int pull(FwSim* h, HostPlanes& hp) {
     hp.w0.resize(N); CU(cudaMemcpy(hp.w0.data(), h->pl.w0, N * 16, cudaMemcpyDeviceToHost));
     hp.w1.resize(N); CU(cudaMemcpy(hp.w1.data(), h->pl.w1, N * 16, cudaMemcpyDeviceToHost));
     hp.targets.resize(T * 3 * N); CU(cudaMemcpy(hp.targets.data(), h->pl.targets, T * 3 * N * 4, cudaMemcpyDeviceToHost));
-    if (h->cfg.task == 2) {
+    if (h->cfg.task == 4) {
+        hp.hist.resize((size_t)h->dev.hist_slots * N);
+        CU(cudaMemcpy(hp.hist.data(), h->pl.hist, hp.hist.size() * 4, cudaMemcpyDeviceToHost));
+    }
+    if (h->cfg.task == 2 || h->cfg.task == 4) {
         hp.dk.resize(N); hp.v0.resize(N); hp.v1.resize(N); hp.v2.resize(N); hp.v3.resize(N);
         CU(cudaMemcpy(hp.dk.data(), h->pl.dk, N * 16, cudaMemcpyDeviceToHost));
         CU(cudaMemcpy(hp.v0.data(), h->pl.v0, N * 16, cudaMemcpyDeviceToHost));
@@ -556,7 +585,8 @@ static int push(FwSim* h, const HostPlanes& hp) {
     CU(cudaMemcpy(h->pl.w0, hp.w0.data(), N * 16, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->pl.w1, hp.w1.data(), N * 16, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->pl.targets, hp.targets.data(), T * 3 * N * 4, cudaMemcpyHostToDevice));
-    if (h->cfg.task == 2) {
+    if (h->cfg.task == 4) CU(cudaMemcpy(h->pl.hist, hp.hist.data(), hp.hist.size() * 4, cudaMemcpyHostToDevice));
+    if (h->cfg.task == 2 || h->cfg.task == 4) {
         CU(cudaMemcpy(h->pl.dk, hp.dk.data(), N * 16, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(h->pl.v0, hp.v0.data(), N * 16, cudaMemcpyHostToDevice));
         CU(cudaMemcpy(h->pl.v1, hp.v1.data(), N * 16, cudaMemcpyHostToDevice));
@@ -600,7 +630,15 @@ extern "C" int fw_get_state(fw_handle h, FwStateHost* s) {
         if (s->targets)
             for (int t = 0; t < T; ++t)
                 for (int k = 0; k < 3; ++k) s->targets[(i * T + t) * 3 + k] = hp.targets[(size_t)(t * 3 + k) * N + i];
-        if (h->cfg.task == 2) {
+        if (h->cfg.task == 4 && s->vis_hist) {
+            // device slots: hist_len rows of 9, then 4 deltas; host layout: FW_MAX_HIST rows of 9, then 4 deltas
+            float* o = s->vis_hist + (size_t)(FW_MAX_HIST * 9 + 4) * i;
+            const int H = h->dev.hist_len;
+            for (int k = 0; k < FW_MAX_HIST * 9 + 4; ++k) o[k] = 0.0f;
+            for (int k = 0; k < 9 * H; ++k) o[k] = hp.hist[(size_t)k * N + i];
+            for (int k = 0; k < 4; ++k) o[FW_MAX_HIST * 9 + k] = hp.hist[(size_t)(9 * H + k) * N + i];
+        }
+        if (h->cfg.task == 2 || h->cfg.task == 4) {
             const float4 &dk = hp.dk[i], &v0 = hp.v0[i], &v1 = hp.v1[i], &v2 = hp.v2[i];
             const int4& v3 = hp.v3[i];
             if (s->duck) { s->duck[3 * i] = dk.x; s->duck[3 * i + 1] = dk.y; s->duck[3 * i + 2] = dk.z; }
@@ -654,7 +692,13 @@ extern "C" int fw_set_state(fw_handle h, const FwStateHost* s) {
         if (s->targets)
             for (int t = 0; t < T; ++t)
                 for (int k = 0; k < 3; ++k) hp.targets[(size_t)(t * 3 + k) * N + i] = s->targets[(i * T + t) * 3 + k];
-        if (h->cfg.task == 2) {
+        if (h->cfg.task == 4 && s->vis_hist) {
+            const float* o = s->vis_hist + (size_t)(FW_MAX_HIST * 9 + 4) * i;
+            const int H = h->dev.hist_len;
+            for (int k = 0; k < 9 * H; ++k) hp.hist[(size_t)k * N + i] = o[k];
+            for (int k = 0; k < 4; ++k) hp.hist[(size_t)(9 * H + k) * N + i] = o[FW_MAX_HIST * 9 + k];
+        }
+        if (h->cfg.task == 2 || h->cfg.task == 4) {
             float4 &dk = hp.dk[i], &v0 = hp.v0[i], &v1 = hp.v1[i], &v2 = hp.v2[i];
             int4& v3 = hp.v3[i];
             if (s->duck) dk = make_float4(s->duck[3 * i], s->duck[3 * i + 1], s->duck[3 * i + 2], 0.0f);

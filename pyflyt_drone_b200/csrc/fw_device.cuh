@@ -20,6 +20,7 @@
 #define FWD_STREAM_NOISE 2u
 #define FWD_STREAM_ACTION 3u
 #define FWD_STREAM_WIND 4u
+#define FWD_STREAM_DUCK 5u
 #define FWD_STREAM_OBST 6u
 
 #define FWD_PI 3.14159265358979323846f
@@ -79,6 +80,13 @@ struct FwDev {
     float obst_radius, obst_h_lo, obst_h_hi, obst_safe, obst_scale, obst_max_pen;
     float strike_dist, strike_reward, lock_step_reward, approach_scale, switch_min_area;
     float duck_radius, cam_offset[3], cam_near, cam_far;
+    // camera model: 0 tracking chase camera, 1 fixed camera with body-frame forward / up-hint axes cam_fb / cam_ub
+    int cam_mode;
+    float cam_fb[3], cam_ub[3];
+    // duck-only task (fixedwing_objlock_env.py:37-118)
+    int hist_len, use_deltas, lock_decay, hist_slots;     // hist_slots = 9 * hist_len + 4
+    float duck_dist_scale, lock_center_radius, centering_scale, visible_step_reward, area_reward_scale;
+    float lock_lost_penalty, approach_clip;
     // cached post-warm-up state (valid when no wind acts during the warm-up): pos3 quat4 vel3 omega3 act5 thr
     int warm_cached;
     float warm[20];
@@ -112,6 +120,7 @@ struct FwPlanes {
     float4* v2;      // frame d_left, d_center, d_right, prev_est_dist
     int4* v3;        // bits (duck_phase, has_prev, post_wp, cam_valid, frame_visible, n_obst<<8), seen, lock, since
     float* obst;     // [MAX_OBST][3][N]  x, y, height
+    float* hist;     // duck-only task: [9 * hist_len + 4][N] vision history rows (newest first) then the four deltas
 };
 
 struct EnvState {

@@ -307,13 +307,19 @@ fw_reset_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const uint8_
 
 // reset of the lanes with `doing` set: begin_reset, waypoints, duck/obstacles, warm-up with the camera frame PyFlyt
 // captures at physics step 12 of it, then the compute_state of end_reset (fixedwing_waypoint_objlock_env.py:170-195)
+template <int TASK>
 __device__ __forceinline__ void ol_reset_lanes(const FwDev& p, const FwPlanes& pl, bool doing, EnvState& e, OlState& ol,
-                                               float* so, float* depth_row, int i, uint32_t gid, uint32_t episode, int tid) {
+                                               float* so, float* depth_row, float* hs, int i, uint32_t gid, uint32_t episode,
+                                               int tid) {
     float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
     if (doing) {
         fw_reset_begin(p, pl, e, i, gid, episode, w0, w1);
-        fw_sample_targets(p, pl, i, gid, episode);
-        ol_reset(p, pl, ol, i, gid, episode, so, tid, FW_BLOCK);
+        if (TASK == 2) {
+            fw_sample_targets(p, pl, i, gid, episode);
+            ol_reset(p, pl, ol, i, gid, episode, so, tid, FW_BLOCK);
+        } else {
+            ol_reset_duck(p, pl, ol, i, gid, episode, so, hs, tid, FW_BLOCK);
+        }
     }
     __syncwarp();
     int dn = 0;
@@ -327,13 +333,27 @@ __device__ __forceinline__ void ol_reset_lanes(const FwDev& p, const FwPlanes& p
     }
     if (doing) {
         fw_reset_finish(p, pl, e, i);
-        ol_vision_and_phase(p, ol, e.tidx >= p.num_targets);
+        ol_vision_and_phase(p, ol, TASK == 2 && e.tidx >= p.num_targets);
+        if (TASK == 4) ol_hist_push(p, ol, hs, tid, FW_BLOCK);
+    }
+}
+
+// flattened observation of either ObjLock task into `row`
+template <int TASK>
+__device__ __forceinline__ void ol_write_obs(const FwDev& p, const FwPlanes& pl, const EnvState& e, const OlState& ol,
+                                             const float* hs, int i, int obs_tidx, float a0, float a1, float a2, float a3,
+                                             float* row, int tid) {
+    if (TASK == 2) fw_write_obs(p, pl, e, i, obs_tidx, a0, a1, a2, a3, row, true, ol.dkx, ol.dky, ol.dkz);
+    else {
+        fw_write_obs(p, pl, e, i, 0, a0, a1, a2, a3, row);            // context_len == 0: the attitude block only
+        ol_write_obs_duck_tail(p, e, ol, hs, tid, FW_BLOCK, row + ((p.angle_repr == 0 ? 12 : 13) + 10));
     }
 }
 
 // one agent step for the whole warp; `active` = lane owns an env
+template <int TASK>
 __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPlanes& pl, bool active, EnvState& e, OlState& ol,
-                                                     float* so, float* depth_row, int i, uint32_t gid, float a0, float a1,
+                                                     float* so, float* depth_row, float* hs, int i, uint32_t gid, float a0, float a1,
                                                      float a2, float a3, float4& w0, float4& w1, float& ep_ret, float* row,
                                                      float* term_obs_row, uint32_t& bits) {
     const int tid = threadIdx.x;
@@ -375,19 +395,22 @@ __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPla
             // compute_state
             float old_dist = e.new_dist;
             obs_tidx = e.tidx;
-            if (e.tidx < p.num_targets) {
+            if (TASK == 2 && e.tidx < p.num_targets) {
                 float dx = pl.targets[(size_t)(e.tidx * 3 + 0) * p.n + i] - e.px;
                 float dy = pl.targets[(size_t)(e.tidx * 3 + 1) * p.n + i] - e.py;
                 float dz = pl.targets[(size_t)(e.tidx * 3 + 2) * p.n + i] - e.pz;
                 e.new_dist = sqrtf(dx * dx + dy * dy + dz * dz);
             }
-            ol_vision_and_phase(p, ol, e.tidx >= p.num_targets);
+            ol_vision_and_phase(p, ol, TASK == 2 && e.tidx >= p.num_targets);
+            if (TASK == 4) ol_hist_push(p, ol, hs, tid, FW_BLOCK);
             // compute_base_term_trunc_reward
             if (e.step_count > p.max_steps) trunc = true;
             if (contact) { reward = -100.0f; col = true; term = true; }
             if (e.px * e.px + e.py * e.py + e.pz * e.pz > p.dome2) { reward = -100.0f; oob = true; term = true; }
             if (!(col || oob)) {                       // early return on crash (objlock_env.py:282-283)
-                if (e.tidx < p.num_targets) {
+                if (TASK == 4) {
+                    ol_duck_reward(p, e, ol, reward, term, complete, strike);
+                } else if (e.tidx < p.num_targets) {
                     if (!p.sparse_reward) {
                         reward += fmaxf(3.0f * (old_dist - e.new_dist), 0.0f);
                         reward += 1.0f / e.new_dist;
@@ -424,7 +447,7 @@ __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPla
     }
     if (active) e.step_count += 1;
     const bool done = active && (term || trunc);
-    if (active && row != nullptr) fw_write_obs(p, pl, e, i, obs_tidx, a0, a1, a2, a3, row, true, ol.dkx, ol.dky, ol.dkz);
+    if (active && row != nullptr) ol_write_obs<TASK>(p, pl, e, ol, hs, i, obs_tidx, a0, a1, a2, a3, row, tid);
     if (active) ep_ret += reward;
     if (__any_sync(0xffffffffu, done)) {
         if (done) {
@@ -440,10 +463,10 @@ __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPla
             if (strike) atomicAdd(&pl.stats[7], 1.0);
         }
         // SubprocVecEnv worker: obs = env.reset()
-        ol_reset_lanes(p, pl, done, e, ol, so, depth_row, i, gid, e.episode + 1u, tid);
+        ol_reset_lanes<TASK>(p, pl, done, e, ol, so, depth_row, hs, i, gid, e.episode + 1u, tid);
         if (done) {
             if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
-            if (row != nullptr) fw_write_obs(p, pl, e, i, 0, 0.f, 0.f, 0.f, 0.f, row, true, ol.dkx, ol.dky, ol.dkz);
+            if (row != nullptr) ol_write_obs<TASK>(p, pl, e, ol, hs, i, 0, 0.f, 0.f, 0.f, 0.f, row, tid);
             ep_ret = 0.0f;
         }
     }
@@ -452,13 +475,16 @@ __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPla
 }
 
 // smem: [obs staging (FW_BLOCK x D)] [obstacle table (num_obstacles x 3 x FW_BLOCK)] [depth rows (warps x cam_res)]
-__device__ __forceinline__ void ol_smem_carve(const FwDev& p, float* stage, float*& so, float*& depth_row) {
+//       [task 4: vision history (hist_slots x FW_BLOCK)]
+__device__ __forceinline__ void ol_smem_carve(const FwDev& p, float* stage, float*& so, float*& depth_row, float*& hs) {
     so = stage + (size_t)FW_BLOCK * (p.obs_dim > 0 ? p.obs_dim : 1);
-    depth_row = so + (size_t)(p.num_obstacles > 0 ? p.num_obstacles : 1) * 3 * FW_BLOCK + (size_t)(threadIdx.x >> 5) * p.cam_res;
+    float* rows = so + (size_t)(p.num_obstacles > 0 ? p.num_obstacles : 1) * 3 * FW_BLOCK;
+    depth_row = rows + (size_t)(threadIdx.x >> 5) * p.cam_res;
+    hs = rows + (size_t)(FW_BLOCK / 32) * p.cam_res;
 }
 
 // 7 blocks/SM x 64 threads x 146 registers: 148 x 448 = 66,304 >= 65,536 envs, still a single wave
-template <bool RANDOM_ACT>
+template <bool RANDOM_ACT, int TASK>
 __global__ void __launch_bounds__(FW_BLOCK, 7)
 fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4* __restrict__ act,
                        float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ flg,
@@ -469,8 +495,8 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
     const int D = p.obs_dim;
     float* stage_warp = stage + (size_t)warp * 32 * D;
     float* row = obs != nullptr ? stage_warp + (size_t)lane * D : nullptr;
-    float *so, *depth_row;
-    ol_smem_carve(p, stage, so, depth_row);
+    float *so, *depth_row, *hs;
+    ol_smem_carve(p, stage, so, depth_row, hs);
     const bool active = i < p.i_end;
     const uint32_t gid = p.env_id0 + (uint32_t)i;
     EnvState e = {};
@@ -482,6 +508,7 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
         fw_load(pl, i, e);
         ol_load(pl, i, ol);
         ol_stage_obstacles(p, pl, i, ol.n_obst, so, threadIdx.x, FW_BLOCK);
+        if (TASK == 4) ol_hist_load(p, pl, i, hs, threadIdx.x, FW_BLOCK);
         if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
         ep_ret = pl.ep_ret[i];
     }
@@ -499,7 +526,7 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
                 a0 = a.x; a1 = a.y; a2 = a.z; a3 = a.w;
             }
         }
-        reward = fw_env_step_objlock(p, pl, active, e, ol, so, depth_row, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
+        reward = fw_env_step_objlock<TASK>(p, pl, active, e, ol, so, depth_row, hs, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
                                      (st == nsteps - 1) ? row : nullptr,
                                      (!RANDOM_ACT && term_obs != nullptr && row != nullptr && active) ? term_obs + (size_t)i * D : nullptr,
                                      bits);
@@ -508,6 +535,7 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
         pl.ep_ret[i] = ep_ret;
         fw_store(pl, i, e);
         ol_store(pl, i, ol);
+        if (TASK == 4) ol_hist_store(p, pl, i, hs, threadIdx.x, FW_BLOCK);
         if (rew != nullptr) rew[i] = reward;
         if (flg != nullptr) flg[i] = (uint8_t)bits;
     }
@@ -517,6 +545,7 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
     }
 }
 
+template <int TASK>
 __global__ void __launch_bounds__(FW_BLOCK)
 fw_reset_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const uint8_t* __restrict__ mask,
                         float* __restrict__ obs, int bulk_ok, int emit_only) {
@@ -526,20 +555,24 @@ fw_reset_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, cons
     const int D = p.obs_dim;
     float* stage_warp = stage + (size_t)warp * 32 * D;
     float* row = stage_warp + (size_t)lane * D;
-    float *so, *depth_row;
-    ol_smem_carve(p, stage, so, depth_row);
+    float *so, *depth_row, *hs;
+    ol_smem_carve(p, stage, so, depth_row, hs);
     const bool active = i < p.n;
     EnvState e = {};
     OlState ol = {};
-    if (active) { fw_load(pl, i, e); ol_load(pl, i, ol); }
+    if (active) {
+        fw_load(pl, i, e); ol_load(pl, i, ol);
+        if (TASK == 4) ol_hist_load(p, pl, i, hs, threadIdx.x, FW_BLOCK);
+    }
     const bool sel = active && !emit_only && (mask == nullptr || mask[i] != 0);
-    ol_reset_lanes(p, pl, sel, e, ol, so, depth_row, i, p.env_id0 + (uint32_t)i, e.episode + 1u, threadIdx.x);
+    ol_reset_lanes<TASK>(p, pl, sel, e, ol, so, depth_row, hs, i, p.env_id0 + (uint32_t)i, e.episode + 1u, threadIdx.x);
     if (sel) {
         pl.ep_ret[i] = 0.0f;
         fw_store(pl, i, e);
         ol_store(pl, i, ol);
+        if (TASK == 4) ol_hist_store(p, pl, i, hs, threadIdx.x, FW_BLOCK);
     }
-    if (active) fw_write_obs(p, pl, e, i, e.tidx, 0.f, 0.f, 0.f, 0.f, row, true, ol.dkx, ol.dky, ol.dkz);
+    if (active) ol_write_obs<TASK>(p, pl, e, ol, hs, i, e.tidx, 0.f, 0.f, 0.f, 0.f, row, threadIdx.x);
     if (obs != nullptr) {
         const int first_env = blockIdx.x * FW_BLOCK + warp * 32;
         if (first_env < p.n) fw_flush_obs(obs, stage_warp, D, first_env, p.n, lane, bulk_ok != 0);
@@ -564,9 +597,10 @@ __global__ void fw_warm_kernel(const __grid_constant__ FwDev p, const FwPlanes p
 // ------------------------------------------------------------------ launchers
 static inline size_t stage_bytes(const FwDev& p) {
     size_t obs = (size_t)(FW_BLOCK / 32) * 32 * (size_t)(p.obs_dim > 0 ? p.obs_dim : 1) * 4;
-    size_t obst = p.task == 2 ? ((size_t)(p.num_obstacles > 0 ? p.num_obstacles : 1) * 3 * FW_BLOCK +
-                                 (size_t)(FW_BLOCK / 32) * p.cam_res) * 4 : 0;
-    return obs + obst;
+    size_t obst = (p.task == 2 || p.task == 4) ? ((size_t)(p.num_obstacles > 0 ? p.num_obstacles : 1) * 3 * FW_BLOCK +
+                                                  (size_t)(FW_BLOCK / 32) * p.cam_res) * 4 : 0;
+    size_t hist = p.task == 4 ? (size_t)p.hist_slots * FW_BLOCK * 4 : 0;
+    return obs + obst + hist;
 }
 static inline int grid_for(int n) { return (n + FW_BLOCK - 1) / FW_BLOCK; }
 
@@ -579,8 +613,17 @@ static fw_step_fn step_fn(int task, bool random_act, bool std_geom) {
     if (task == 3) return random_act ? fw_step_kernel<3, true, false> : fw_step_kernel<3, false, false>;
     if (task == 0) return random_act ? fw_step_kernel<0, true, false> : fw_step_kernel<0, false, false>;
     if (task == 1) return random_act ? fw_step_kernel<1, true, false> : fw_step_kernel<1, false, false>;
-    if (task == 2) return random_act ? fw_step_objlock_kernel<true> : fw_step_objlock_kernel<false>;
+    if (task == 2) return random_act ? fw_step_objlock_kernel<true, 2> : fw_step_objlock_kernel<false, 2>;
+    if (task == 4) return random_act ? fw_step_objlock_kernel<true, 4> : fw_step_objlock_kernel<false, 4>;
     return nullptr;
+}
+
+// dynamic shared memory beyond the 48 KB default needs an explicit opt-in per kernel (large obstacle tables or camera
+// rows); returns false when the request exceeds what an SM offers
+static bool smem_opt_in(const void* fn, size_t bytes) {
+    if (bytes <= 48 * 1024) return true;
+    if (bytes > 227 * 1024) return false;
+    return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess;
 }
 
 cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act, float* obs, float* rew, uint8_t* flg,
@@ -588,6 +631,7 @@ cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act
     const int bulk_ok = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) && ((p.obs_dim * 128) % 16 == 0);
     fw_step_fn fn = step_fn(p.task, random_act, p.std_geom != 0);
     if (fn == nullptr) return cudaErrorNotSupported;
+    if (!smem_opt_in((const void*)fn, stage_bytes(p))) return cudaErrorInvalidValue;
     fn<<<grid_for(p.i_end - p.i_begin), FW_BLOCK, stage_bytes(p), st>>>(p, pl, reinterpret_cast<const float4*>(act), obs, rew, flg, term_obs,
                                                          spl, bulk_ok);
     return cudaGetLastError();
@@ -599,6 +643,7 @@ cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* dep, const
                                       cudaGraphNode_t* out) {
     fw_step_fn fn = step_fn(p.task, true, p.std_geom != 0);
     if (fn == nullptr) return cudaErrorNotSupported;
+    if (!smem_opt_in((const void*)fn, stage_bytes(p))) return cudaErrorInvalidValue;
     FwDev pc = p; FwPlanes plc = pl;
     const float4* act = nullptr; float* obs = nullptr; float* rew = nullptr; uint8_t* flg = nullptr; float* term = nullptr;
     int spl_ = spl, bulk = 0;
@@ -615,8 +660,11 @@ cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* dep, const
 cudaError_t fwk_launch_reset(const FwDev& p, const FwPlanes& pl, const uint8_t* mask, float* obs, bool emit_only,
                              cudaStream_t st) {
     const int bulk_ok = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0);
-    if (p.task == 2) fw_reset_objlock_kernel<<<grid_for(p.n), FW_BLOCK, stage_bytes(p), st>>>(p, pl, mask, obs, bulk_ok, emit_only ? 1 : 0);
-    else fw_reset_kernel<<<grid_for(p.n), FW_BLOCK, stage_bytes(p), st>>>(p, pl, mask, obs, bulk_ok, emit_only ? 1 : 0);
+    if (p.task == 2 || p.task == 4) {
+        auto fn = p.task == 2 ? fw_reset_objlock_kernel<2> : fw_reset_objlock_kernel<4>;
+        if (!smem_opt_in((const void*)fn, stage_bytes(p))) return cudaErrorInvalidValue;
+        fn<<<grid_for(p.n), FW_BLOCK, stage_bytes(p), st>>>(p, pl, mask, obs, bulk_ok, emit_only ? 1 : 0);
+    } else fw_reset_kernel<<<grid_for(p.n), FW_BLOCK, stage_bytes(p), st>>>(p, pl, mask, obs, bulk_ok, emit_only ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -166,9 +166,19 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
         float ofy = m[3] * p.cam_offset[0] + m[4] * p.cam_offset[1] + m[5] * p.cam_offset[2];
         float ofz = m[6] * p.cam_offset[0] + m[7] * p.cam_offset[1] + m[8] * p.cam_offset[2];
         cx = e.px + ofx; cy = e.py + ofy; cz = e.pz + ofz;
-        float il = rsqrtf(ofx * ofx + ofy * ofy + ofz * ofz);
-        float fx = -ofx * il, fy = -ofy * il, fz = -ofz * il;
-        float ux = m[2], uy = m[5], uz = m[8];
+        float fx, fy, fz, ux, uy, uz;
+        if (p.cam_mode == 0) {       // tracking camera: looks at the aircraft, up hint = body z
+            float il = rsqrtf(ofx * ofx + ofy * ofy + ofz * ofz);
+            fx = -ofx * il; fy = -ofy * il; fz = -ofz * il;
+            ux = m[2]; uy = m[5]; uz = m[8];
+        } else {                     // fixed camera (is_tracking_camera = False): tilted body axes, folded on the host
+            fx = m[0] * p.cam_fb[0] + m[1] * p.cam_fb[1] + m[2] * p.cam_fb[2];
+            fy = m[3] * p.cam_fb[0] + m[4] * p.cam_fb[1] + m[5] * p.cam_fb[2];
+            fz = m[6] * p.cam_fb[0] + m[7] * p.cam_fb[1] + m[8] * p.cam_fb[2];
+            ux = m[0] * p.cam_ub[0] + m[1] * p.cam_ub[1] + m[2] * p.cam_ub[2];
+            uy = m[3] * p.cam_ub[0] + m[4] * p.cam_ub[1] + m[5] * p.cam_ub[2];
+            uz = m[6] * p.cam_ub[0] + m[7] * p.cam_ub[1] + m[8] * p.cam_ub[2];
+        }
         rx = fy * uz - fz * uy; ry = fz * ux - fx * uz; rz = fx * uy - fy * ux;
         float rl = rsqrtf(rx * rx + ry * ry + rz * rz);
         rx *= rl; ry *= rl; rz *= rl;
@@ -401,6 +411,123 @@ __device__ __forceinline__ void ol_reset(const FwDev& p, const FwPlanes& pl, OlS
         float x = -0.5f * p.dome + fw_u01(r.y) * p.dome;
         float y = -0.5f * p.dome + fw_u01(r.z) * p.dome;
         if (x * x + y * y < 100.0f) continue;
+        OL_S(so, n, 0, tid, stride) = x; OL_S(so, n, 1, tid, stride) = y; OL_S(so, n, 2, tid, stride) = h;
+        pl.obst[(size_t)(n * 3 + 0) * p.n + i] = x;
+        pl.obst[(size_t)(n * 3 + 1) * p.n + i] = y;
+        pl.obst[(size_t)(n * 3 + 2) * p.n + i] = h;
+        ++n;
+    }
+    o.n_obst = n;
+}
+
+// ================================================================== duck-only task (FixedwingObjLockEnv, task 4)
+// Restates /root/reference/envs/fixedwing_objlock_env.py: reset/_spawn_duck/_spawn_obstacles :177-251,461-578,
+// compute_state :253-287, _build_duck_vision_observation :421-459, compute_term_trunc_reward :289-372 and
+// FlattenObjLockEnv._flatten_obs (/root/reference/envs/flatten_objlock_env.py:41-46).
+// The vision history (hist_len x 9 floats + 4 deltas per env) lives in shared memory during a step:
+// hs[slot * stride + tid], slot = h * 9 + c for history row h (0 = newest), then the deltas.  `o.seen` carries
+// _vision_history_filled in this task (the waypoint task's consecutive-seen counter has no use here).
+#define OL_H(hs, slot, tid, stride) (hs)[(slot) * (stride) + (tid)]
+
+__device__ __forceinline__ void ol_hist_load(const FwDev& p, const FwPlanes& pl, int i, float* hs, int tid, int stride) {
+    for (int k = 0; k < p.hist_slots; ++k) OL_H(hs, k, tid, stride) = pl.hist[(size_t)k * p.n + i];
+}
+__device__ __forceinline__ void ol_hist_store(const FwDev& p, const FwPlanes& pl, int i, const float* hs, int tid, int stride) {
+    for (int k = 0; k < p.hist_slots; ++k) pl.hist[(size_t)k * p.n + i] = OL_H(hs, k, tid, stride);
+}
+
+// _build_duck_vision_observation: newest feature vector in, oldest out, deltas against the previous newest row
+__device__ __forceinline__ void ol_hist_push(const FwDev& p, OlState& o, float* hs, int tid, int stride) {
+    const int H = p.hist_len;
+    float base[9];
+    base[0] = o.vis_flag; base[1] = o.last_cx; base[2] = o.last_cy; base[3] = o.last_area; base[4] = o.last_depth;
+    base[5] = (float)o.since * (1.0f / 60.0f);
+    base[6] = o.vis_dl; base[7] = o.vis_dc; base[8] = o.vis_dr;
+    float prev[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) prev[c] = H >= 2 ? OL_H(hs, c, tid, stride) : 0.0f;
+    for (int h = H - 1; h >= 1; --h)
+#pragma unroll
+        for (int c = 0; c < 9; ++c) OL_H(hs, h * 9 + c, tid, stride) = OL_H(hs, (h - 1) * 9 + c, tid, stride);
+#pragma unroll
+    for (int c = 0; c < 9; ++c) OL_H(hs, c, tid, stride) = base[c];
+    o.seen = min(o.seen + 1, H);
+    const bool both = o.seen >= 2 && base[0] > 0.5f && prev[0] > 0.5f;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) OL_H(hs, 9 * H + c, tid, stride) = both ? base[1 + c] - prev[1 + c] : 0.0f;
+}
+
+// compute_term_trunc_reward past the early return on crash (:296-372).  `dist` = |target_vector|.
+__device__ __forceinline__ void ol_duck_reward(const FwDev& p, const EnvState& e, OlState& o, float& reward, bool& term,
+                                               bool& complete, bool& strike) {
+    reward -= ol_obstacle_penalty(p, o, true);                      // always the halved scale (:403)
+    const float ddx = o.dkx - e.px, ddy = o.dky - e.py, ddz = o.dkz - e.pz;
+    const float dist = sqrtf(ddx * ddx + ddy * ddy + ddz * ddz);
+    if (!p.sparse_reward) {
+        reward += p.duck_dist_scale / fmaxf(dist, 2.0f);
+        if (o.vis_flag > 0.5f) {
+            const float est = o.last_depth;
+            reward += p.visible_step_reward;
+            reward += p.area_reward_scale * fmaxf(0.0f, o.last_area);
+            const float cxd = o.last_cx - 0.5f, cyd = o.last_cy - 0.5f;
+            const float dc = sqrtf(cxd * cxd + cyd * cyd);
+            const float rl = fmaxf(p.lock_center_radius, 1e-6f);
+            reward += p.centering_scale * fmaxf(0.0f, (rl - dc) / rl);
+            if (dc < rl) { o.lock = min(o.lock + 1, p.lock_hold); reward += p.lock_step_reward; }
+            else o.lock = max(o.lock - p.lock_decay, 0);
+            if (o.has_prev && est > 0.0f) {
+                float diff = o.prev_est - est;
+                if (p.approach_clip > 0.0f) diff = fminf(fmaxf(diff, -p.approach_clip), p.approach_clip);
+                reward += diff * p.approach_scale;
+            }
+            if (est > 0.0f) { o.prev_est = est; o.has_prev = 1; } else { o.prev_est = 0.0f; o.has_prev = 0; }
+        } else {
+            if (o.lock > 0) reward -= p.lock_lost_penalty;
+            o.lock = max(o.lock - p.lock_decay, 0);
+            o.prev_est = 0.0f; o.has_prev = 0;
+        }
+    }
+    if (o.lock >= p.lock_hold && dist <= p.strike_dist) {
+        term = true; reward += p.strike_reward; complete = true; strike = true;
+    }
+}
+
+// the part of the flattened observation after the attitude: target_vector (duck relative to the aircraft, body
+// frame), the history rows and the deltas
+__device__ __forceinline__ void ol_write_obs_duck_tail(const FwDev& p, const EnvState& e, const OlState& o, const float* hs,
+                                                       int tid, int stride, float* tail) {
+    Mat3 R = fw_quat_mat(e.qx, e.qy, e.qz, e.qw);
+    const float* m = R.m;
+    const float dx = o.dkx - e.px, dy = o.dky - e.py, dz = o.dkz - e.pz;
+    tail[0] = m[0] * dx + m[3] * dy + m[6] * dz;
+    tail[1] = m[1] * dx + m[4] * dy + m[7] * dz;
+    tail[2] = m[2] * dx + m[5] * dy + m[8] * dz;
+    const int nv = 9 * p.hist_len + (p.use_deltas ? 4 : 0);
+    for (int k = 0; k < nv; ++k) tail[3 + k] = OL_H(hs, k, tid, stride);
+}
+
+// _reset_duck_state + _spawn_duck + _spawn_obstacles of the duck-only env
+__device__ __forceinline__ void ol_reset_duck(const FwDev& p, const FwPlanes& pl, OlState& o, int i, uint32_t gid,
+                                              uint32_t episode, float* so, float* hs, int tid, int stride) {
+    o.duck_phase = 0; o.seen = 0; o.lock = 0; o.has_prev = 0; o.prev_est = 0.0f;
+    o.last_cx = 0.5f; o.last_cy = 0.5f; o.last_area = 0.0f; o.last_depth = 0.0f;
+    o.since = 60; o.post_wp = 0; o.cam_valid = 0; o.f_visible = 0;
+    o.f_cx = o.f_cy = o.f_area = o.f_depth = 0.0f; o.f_dl = o.f_dc = o.f_dr = 0.0f;
+    o.vis_dl = o.vis_dc = o.vis_dr = 0.0f; o.vis_flag = 0.0f;
+    for (int k = 0; k < p.hist_slots; ++k) OL_H(hs, k, tid, stride) = 0.0f;
+    uint4 rd = fw_philox(p.seed_lo, p.seed_hi, gid, episode, 0u, FWD_STREAM_DUCK);
+    o.dkx = -0.5f * p.dome + fw_u01(rd.x) * p.dome;
+    o.dky = -0.5f * p.dome + fw_u01(rd.y) * p.dome;
+    o.dkz = 0.05f;
+    int n = 0;
+    for (int k = 0; k < p.num_obstacles; ++k) {
+        uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid, episode, (uint32_t)k, FWD_STREAM_OBST);
+        float h = p.obst_h_lo + fw_u01(r.x) * (p.obst_h_hi - p.obst_h_lo);
+        float x = -0.5f * p.dome + fw_u01(r.y) * p.dome;
+        float y = -0.5f * p.dome + fw_u01(r.z) * p.dome;
+        const float qx = x - o.dkx, qy = y - o.dky;
+        if (qx * qx + qy * qy < 100.0f) continue;           // within 10 m of the duck
+        if (x * x + y * y < 100.0f) continue;               // within 10 m of the start position
         OL_S(so, n, 0, tid, stride) = x; OL_S(so, n, 1, tid, stride) = y; OL_S(so, n, 2, tid, stride) = h;
         pl.obst[(size_t)(n * 3 + 0) * p.n + i] = x;
         pl.obst[(size_t)(n * 3 + 1) * p.n + i] = y;

@@ -298,6 +298,182 @@ class FixedwingLowLevelEnv:
         self._vec.close()
 
 
+class FixedwingObjLockEnv:
+    """Single-env gymnasium view of the duck-only lock/strike task, the interface of
+    envs/fixedwing_objlock_env.py:17-175: same keyword names and defaults as the reference's constructor, Dict
+    observation {attitude, target_vector(3), duck_vision(9*history [+4])}, ``info`` keys ``duck_strike`` /
+    ``env_complete`` / ``is_success`` / ``collision`` / ``out_of_bounds``.  The camera is the analytic stand-in
+    (DESIGN.md): ``camera_FOV_degrees`` must be 90, ``duck_urdf_path`` / ``use_egl`` are accepted and ignored,
+    ``render_mode="rgb_array"`` only selects the capture resolution the way the reference does (:213-218)."""
+
+    metadata = {"render_modes": ["rgb_array"], "render_fps": 30}
+
+    def __init__(self, sparse_reward: bool = False, flight_mode: int = 0, flight_dome_size: float = 100.0,
+                 max_duration_seconds: float = 120.0, angle_representation: str = "quaternion", agent_hz: int = 30,
+                 render_mode=None, render_resolution=(480, 480), duck_urdf_path=None, use_egl: bool = False,
+                 camera_profile: str = "cockpit_fpv", camera_position_offset=None, camera_angle_degrees=None,
+                 camera_FOV_degrees=None, camera_resolution=None,
+                 num_obstacles: int = 5, obstacle_radius: float = 2.0, obstacle_height_range=(10.0, 30.0),
+                 obstacle_safe_distance_m: float = 20.0, obstacle_avoid_reward_scale: float = 1.0,
+                 obstacle_avoid_max_penalty: float = 2.0,
+                 duck_camera_capture_interval_steps: int = 12, duck_lock_hold_steps: int = 10,
+                 duck_strike_distance_m: float = 2.0, duck_strike_reward: float = 200.0,
+                 duck_lock_step_reward: float = 0.1, duck_approach_reward_scale: float = 0.05,
+                 duck_global_scaling: float = 20.0, duck_vision_history_len: int = 3, duck_vision_use_deltas: bool = True,
+                 duck_distance_reward_scale: float = 1.0, duck_lock_center_radius: float = 0.55,
+                 duck_centering_reward_scale: float = 3, duck_visible_step_reward: float = 2,
+                 duck_area_reward_scale: float = 5.0, duck_lock_decay_steps: int = 1, duck_lock_lost_penalty: float = 0.5,
+                 duck_approach_reward_clip_m: float = 2.0, wind_config: dict | None = None,
+                 device: int = 0, seed: int = 0):
+        if 120 % agent_hz != 0:
+            lowest = int(120 / (int(120 / agent_hz) + 1))
+            highest = int(120 / int(120 / agent_hz))
+            raise ValueError(f"`agent_hz` must be round denominator of 120, try {lowest} or {highest}.")
+        if angle_representation not in ("euler", "quaternion"):
+            raise ValueError(f"angle_representation must be either `euler` or `quaternion`, not {angle_representation}")
+        if flight_mode != 0:
+            raise ValueError("only flight_mode 0 (roll, pitch, yaw, thrust) is implemented")
+        if render_mode not in (None, "rgb_array"):
+            raise ValueError("only render_mode None or 'rgb_array' (capture resolution only) is accepted")
+        if camera_FOV_degrees is not None and int(camera_FOV_degrees) != 90:
+            raise ValueError("the analytic camera is built for the reference's 90 degree field of view")
+        if camera_profile == "cockpit_fpv":                          # fixedwing_objlock_env.py:184-192,226-229
+            offset, angle, mode = [0.8, 0.0, 0.12], -5, 1
+        else:                                                        # "chase", and PyFlyt's own default camera
+            offset, angle, mode = [-3.0, 0.0, 1.0], 0, 0
+        if camera_position_offset is not None:
+            offset = [float(x) for x in camera_position_offset]
+        if camera_angle_degrees is not None:
+            angle = int(camera_angle_degrees)
+        res = camera_resolution if camera_resolution is not None else (render_resolution if render_mode is not None else (128, 128))
+        hlo, hhi = float(min(obstacle_height_range)), float(max(obstacle_height_range))
+        over = dict(
+            sparse_reward=int(bool(sparse_reward)), dome=float(flight_dome_size), spawn_size=float(flight_dome_size),
+            max_steps=int(agent_hz * max_duration_seconds), inner_per_step=int(120 / agent_hz),
+            angle_repr=0 if angle_representation == "euler" else 1,
+            cam_mode=mode, cam_offset=offset, cam_tilt_deg=float(angle), cam_res=int(res[1]),
+            num_obstacles=int(num_obstacles), obst_radius=float(obstacle_radius), obst_h_lo=hlo, obst_h_hi=hhi,
+            obst_safe=float(obstacle_safe_distance_m), obst_scale=float(obstacle_avoid_reward_scale),
+            obst_max_pen=float(obstacle_avoid_max_penalty),
+            cam_interval_substeps=2 * int(duck_camera_capture_interval_steps), lock_hold_steps=int(duck_lock_hold_steps),
+            strike_dist=float(duck_strike_distance_m), strike_reward=float(duck_strike_reward),
+            lock_step_reward=float(duck_lock_step_reward), approach_scale=float(duck_approach_reward_scale),
+            duck_radius=0.05 * float(duck_global_scaling), vision_hist_len=int(max(1, duck_vision_history_len)),
+            vision_use_deltas=int(bool(duck_vision_use_deltas)), duck_dist_scale=float(duck_distance_reward_scale),
+            lock_center_radius=float(duck_lock_center_radius), centering_scale=float(duck_centering_reward_scale),
+            visible_step_reward=float(duck_visible_step_reward), area_reward_scale=float(duck_area_reward_scale),
+            lock_decay_steps=int(max(1, duck_lock_decay_steps)), lock_lost_penalty=float(duck_lock_lost_penalty),
+            approach_clip=float(max(0.0, duck_approach_reward_clip_m)))
+        self.cfg: EnvConfig = make_config("objlock_duck", wind=wind_config if wind_config is not None else {"enabled": False},
+                                          **over)
+        self._device, self._seed0 = device, int(seed)
+        self._vec = FixedwingVecEnv(1, config=self.cfg, device=device, seed=self._seed0)
+        att = (12 if self.cfg.angle_repr == 0 else 13) + 4 + 6
+        self._att = att
+        self.combined_space = spaces.Box(low=-np.inf, high=np.inf, shape=(att,), dtype=np.float64)
+        self.action_space = spaces.Box(low=-np.ones(4), high=np.ones(4), dtype=np.float64)
+        nv = 9 * self.cfg.vision_hist_len + (4 if self.cfg.vision_use_deltas else 0)
+        self.observation_space = spaces.Dict({
+            "attitude": self.combined_space,
+            "target_vector": spaces.Box(low=-np.inf, high=np.inf, shape=(3,), dtype=np.float64),
+            "duck_vision": spaces.Box(low=-np.inf, high=np.inf, shape=(nv,), dtype=np.float32)})
+        self.sparse_reward = bool(sparse_reward)
+        self.np_random = np.random.default_rng(self._seed0)
+        self.state: dict | None = None
+        self.info: dict = {}
+        self.termination = self.truncation = False
+        self.step_count = 0
+        self.action = np.zeros(4)
+        self._needs_reset = True
+
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def duck_pos(self) -> np.ndarray:
+        return self._vec.get_state()["duck"][0].astype(np.float64)
+
+    def _obs_dict(self, flat: np.ndarray) -> dict:
+        a = self._att
+        return {"attitude": flat[:a].astype(np.float64), "target_vector": flat[a:a + 3].astype(np.float64),
+                "duck_vision": flat[a + 3:].astype(np.float32)}
+
+    def reset(self, *, seed: int | None = None, options: dict | None = None) -> tuple[dict, dict]:
+        if seed is not None:
+            self._seed0 = int(seed)
+            self.np_random = np.random.default_rng(self._seed0)
+            self._vec.seed(self._seed0)
+        flat = self._vec.reset()[0]
+        self.step_count, self.termination, self.truncation = 0, False, False
+        self.action = np.zeros(4)
+        self.info = {"out_of_bounds": False, "collision": False, "env_complete": False, "duck_strike": False,
+                     "is_success": False}
+        self.state = self._obs_dict(flat)
+        self._needs_reset = False
+        return self.state, self.info
+
+    def step(self, action) -> tuple[dict, float, bool, bool, dict]:
+        if self._needs_reset:
+            raise RuntimeError("call reset() before step() (the previous episode has ended)")
+        a = np.asarray(action, dtype=np.float32).reshape(1, 4)
+        self.action = a[0].astype(np.float64)
+        obs, rew, flags, term = self._vec.step_arrays(a, want_terminal_obs=True)
+        f = int(flags[0])
+        self.termination, self.truncation = bool(f & FLAG_TERM), bool(f & FLAG_TRUNC)
+        self.step_count += 1
+        self.info["collision"] = self.info["collision"] or bool(f & FLAG_COLLISION)
+        self.info["out_of_bounds"] = self.info["out_of_bounds"] or bool(f & FLAG_OOB)
+        self.info["env_complete"] = bool(f & FLAG_COMPLETE)
+        self.info["duck_strike"] = self.info["is_success"] = bool(f & FLAG_STRIKE)
+        if self.termination or self.truncation:      # the device batch has already auto-reset: hand back the terminal observation
+            self.state = self._obs_dict(term[0].copy())
+            self._needs_reset = True
+        else:
+            self.state = self._obs_dict(obs[0].copy())
+        return self.state, float(rew[0]), self.termination, self.truncation, self.info
+
+    def close(self) -> None:
+        self._vec.close()
+
+    def render(self):
+        raise ValueError("rendered frames are out of scope for the batched simulator")
+
+
+class FlattenObjLockEnv:
+    """Dict -> Box flattening of FixedwingObjLockEnv, as envs/flatten_objlock_env.py:8-46:
+    ``concatenate([attitude, target_vector, duck_vision]).astype(float32)``."""
+
+    def __init__(self, env: FixedwingObjLockEnv):
+        self.env = env
+        sp = env.observation_space
+        self.attitude_shape = sp["attitude"].shape[0]
+        self.target_shape = sp["target_vector"].shape[0]
+        self.vision_shape = sp["duck_vision"].shape[0]
+        self.observation_space = spaces.Box(low=-np.inf, high=np.inf,
+                                            shape=(self.attitude_shape + self.target_shape + self.vision_shape,),
+                                            dtype=np.float32)
+        self.action_space = env.action_space
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
+
+    def _flatten_obs(self, obs: dict) -> np.ndarray:
+        return np.concatenate([obs["attitude"], obs["target_vector"], obs["duck_vision"]], axis=0).astype(np.float32)
+
+    def reset(self, **kwargs):
+        obs, info = self.env.reset(**kwargs)
+        return self._flatten_obs(obs), info
+
+    def step(self, action):
+        obs, reward, term, trunc, info = self.env.step(action)
+        return self._flatten_obs(obs), reward, term, trunc, info
+
+    def close(self):
+        self.env.close()
+
+
 class FlattenWaypointEnv:
     """Dict -> Box flattening of a waypoints env, as envs/flatten_waypoint_env.py:14-72 (zero padded)."""
 

@@ -31,8 +31,11 @@ _STATE_FIELDS = {
     "new_dist": (np.float32, 0), "wind": (np.float32, 7),
     # ObjLock task only
     "duck": (np.float32, 3), "obst": (np.float32, (32, 3)), "ol_f": (np.float32, 12), "ol_i": (np.int32, 9),
+    # duck-only task: MAX_HIST history rows of 9 (newest first) + 4 deltas
+    "vis_hist": (np.float32, 4 * 9 + 4),
 }
 _OBJLOCK_FIELDS = ("duck", "obst", "ol_f", "ol_i")
+_DUCK_FIELDS = ("vis_hist",)
 
 
 class FixedwingVecEnv:
@@ -137,8 +140,10 @@ class FixedwingVecEnv:
              "env_complete": bool(f & FLAG_COMPLETE)}
         if tidx is not None:
             d["num_targets_reached"] = tidx
-        if self.cfg.task == 2:
+        if self.cfg.task in (2, 4):
             d["duck_strike"] = bool(f & FLAG_STRIKE)
+        if self.cfg.task == 4:
+            d["is_success"] = bool(f & FLAG_STRIKE)          # fixedwing_objlock_env.py:235,372
         return d
 
     def _make_infos(self, flags: np.ndarray, dones: np.ndarray, term: np.ndarray) -> list[dict]:
@@ -261,7 +266,7 @@ class FixedwingVecEnv:
         out = {}
         s = _lib.FwStateHostC()
         for k, (dt, w) in _STATE_FIELDS.items():
-            if k in _OBJLOCK_FIELDS and self.cfg.task != 2:
+            if (k in _OBJLOCK_FIELDS and self.cfg.task not in (2, 4)) or (k in _DUCK_FIELDS and self.cfg.task != 4):
                 continue
             shape = self._state_shape(k, w, n, T)
             out[k] = np.zeros(shape, dtype=dt)
@@ -285,7 +290,7 @@ class FixedwingVecEnv:
             if k not in _STATE_FIELDS:
                 raise KeyError(f"unknown state field {k!r}")
             dt, w = _STATE_FIELDS[k]
-            if k in _OBJLOCK_FIELDS and self.cfg.task != 2:
+            if (k in _OBJLOCK_FIELDS and self.cfg.task not in (2, 4)) or (k in _DUCK_FIELDS and self.cfg.task != 4):
                 continue
             shape = self._state_shape(k, w, n, T)
             a = np.ascontiguousarray(np.asarray(v).astype(dt)).reshape(shape)
