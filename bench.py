@@ -38,8 +38,9 @@ if ROOT not in sys.path:
 METRIC = "fixedwing_env_steps_per_sec"
 UNIT = "env-steps/s"
 # SURVEY.md section 8(d); lowlevel (2 substeps per env-step): state 76 in + 76 out, action 24, target 12, obs 84, reward 4
-BYTES_PER_STEP = {"physics_only": 152, "waypoints_v3": 332, "waypoint_objlock": 400, "lowlevel": 276}
-FLOPS_PER_STEP = {"physics_only": 6400, "waypoints_v3": 7000, "waypoint_objlock": 7000, "lowlevel": 1750}
+# objlock_duck: state 76 + 76, action 16, wind 32, duck/vision planes 80 + 80, vision history 124 + 124, obs 224, reward 4
+BYTES_PER_STEP = {"physics_only": 152, "waypoints_v3": 332, "waypoint_objlock": 400, "lowlevel": 276, "objlock_duck": 836}
+FLOPS_PER_STEP = {"physics_only": 6400, "waypoints_v3": 7000, "waypoint_objlock": 7000, "lowlevel": 1750, "objlock_duck": 7000}
 L2_BYTES = 126 * 1024 * 1024
 
 
@@ -50,7 +51,8 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU per launch")
-    ap.add_argument("--workload", choices=["physics_only", "waypoints_v3", "waypoint_objlock", "lowlevel", "ppo"], default="physics_only",
+    ap.add_argument("--workload", choices=["physics_only", "waypoints_v3", "waypoint_objlock", "lowlevel", "objlock_duck", "ppo"],
+                    default="physics_only",
                     help="ppo = BASELINE configs[2]: PPO Fixedwing-Waypoints rollout+update (a step is one PPO iteration)")
     ap.add_argument("--ppo-preset", choices=["waypoints_v3", "waypoint_objlock"], default="waypoints_v3")
     ap.add_argument("--ppo-envs", type=int, default=4096)
@@ -257,7 +259,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     over = {}
     cfg = fw.make_config(args.workload, **over)
     N = args.envs
-    state_bytes = N * (6 * 16 + 4 + (cfg.num_targets * 12) + (5 * 16 + 32 * 12 if cfg.task == 2 else 0))
+    state_bytes = N * (6 * 16 + 4 + (cfg.num_targets * 12) + (5 * 16 + 32 * 12 if cfg.task in (2, 4) else 0)
+                       + (31 * 4 if cfg.task == 4 else 0))
     replicas = max(2, int(np.ceil(2 * L2_BYTES / state_bytes)))
     envs = [FixedwingVecEnv(N, config=cfg, device=local_rank, seed=1234, env_id0=(rank * replicas + r) * N)
             for r in range(replicas)]

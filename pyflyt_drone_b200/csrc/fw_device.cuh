@@ -545,10 +545,18 @@ __device__ __forceinline__ void fw_write_obs_lowlevel(const FwPlanes& pl, const 
 static __device__ __noinline__ void fw_warmup_loop(const FwDev& p, EnvState& e, float4 w0, float4 w1, int nsub) {
     float cmd[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     bool contact = false;
+    if (p.std_geom) {                // same choice of physics path as the step kernels (uniform branch)
+        for (int k = 0; k < nsub; ++k) {
+            float wx, wy, wz;
+            fw_wind(p, e.physics_steps, w0, w1, wx, wy, wz);
+            fw_substep<true>(p, e, cmd, wx, wy, wz, 0.0f, contact);   // throttle is 0 during warm-up: noise term is 0
+        }
+        return;
+    }
     for (int k = 0; k < nsub; ++k) {
         float wx, wy, wz;
         fw_wind(p, e.physics_steps, w0, w1, wx, wy, wz);
-        fw_substep(p, e, cmd, wx, wy, wz, 0.0f, contact);   // throttle is 0 during warm-up: noise term is 0
+        fw_substep(p, e, cmd, wx, wy, wz, 0.0f, contact);
     }
 }
 

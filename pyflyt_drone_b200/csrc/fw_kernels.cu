@@ -351,7 +351,7 @@ __device__ __forceinline__ void ol_write_obs(const FwDev& p, const FwPlanes& pl,
 }
 
 // one agent step for the whole warp; `active` = lane owns an env
-template <int TASK>
+template <int TASK, bool STD>
 __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPlanes& pl, bool active, EnvState& e, OlState& ol,
                                                      float* so, float* depth_row, float* hs, int i, uint32_t gid, float a0, float a1,
                                                      float a2, float a3, float4& w0, float4& w1, float& ep_ret, float* row,
@@ -364,6 +364,8 @@ __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPla
     float n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
     bool have_noise = false;
     int obs_tidx = e.tidx;
+    bool duck_near = false;
+    const uint32_t cand = active ? ol_contact_candidates(p, e, ol, so, tid, FW_BLOCK, duck_near) : 0u;
 
     for (int it = 0; it < p.inner_per_step; ++it) {
         const bool run = active && !(term || trunc);        // FixedwingBaseEnv.step: `if termination or truncation: break`
@@ -384,8 +386,8 @@ __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPla
                 }
                 float wx, wy, wz;
                 fw_wind(p, ps, w0, w1, wx, wy, wz);
-                contact = contact || ol_contact(p, e, ol, so, tid, FW_BLOCK);          // pose entering the step
-                fw_substep(p, e, cmd, wx, wy, wz, nz, contact);
+                contact = contact || ol_contact(p, e, ol, so, tid, FW_BLOCK, cand, duck_near);    // pose
+                fw_substep<STD>(p, e, cmd, wx, wy, wz, nz, contact);
             }
         }
         // drone.update_last(): camera frame every cam_interval physics steps
@@ -484,7 +486,7 @@ __device__ __forceinline__ void ol_smem_carve(const FwDev& p, float* stage, floa
 }
 
 // 7 blocks/SM x 64 threads x 146 registers: 148 x 448 = 66,304 >= 65,536 envs, still a single wave
-template <bool RANDOM_ACT, int TASK>
+template <bool RANDOM_ACT, int TASK, bool STD>
 __global__ void __launch_bounds__(FW_BLOCK, 7)
 fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4* __restrict__ act,
                        float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ flg,
@@ -526,7 +528,7 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
                 a0 = a.x; a1 = a.y; a2 = a.z; a3 = a.w;
             }
         }
-        reward = fw_env_step_objlock<TASK>(p, pl, active, e, ol, so, depth_row, hs, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
+        reward = fw_env_step_objlock<TASK, STD>(p, pl, active, e, ol, so, depth_row, hs, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
                                      (st == nsteps - 1) ? row : nullptr,
                                      (!RANDOM_ACT && term_obs != nullptr && row != nullptr && active) ? term_obs + (size_t)i * D : nullptr,
                                      bits);
@@ -613,8 +615,10 @@ static fw_step_fn step_fn(int task, bool random_act, bool std_geom) {
     if (task == 3) return random_act ? fw_step_kernel<3, true, false> : fw_step_kernel<3, false, false>;
     if (task == 0) return random_act ? fw_step_kernel<0, true, false> : fw_step_kernel<0, false, false>;
     if (task == 1) return random_act ? fw_step_kernel<1, true, false> : fw_step_kernel<1, false, false>;
-    if (task == 2) return random_act ? fw_step_objlock_kernel<true, 2> : fw_step_objlock_kernel<false, 2>;
-    if (task == 4) return random_act ? fw_step_objlock_kernel<true, 4> : fw_step_objlock_kernel<false, 4>;
+    if (task == 2 && std_geom) return random_act ? fw_step_objlock_kernel<true, 2, true> : fw_step_objlock_kernel<false, 2, true>;
+    if (task == 4 && std_geom) return random_act ? fw_step_objlock_kernel<true, 4, true> : fw_step_objlock_kernel<false, 4, true>;
+    if (task == 2) return random_act ? fw_step_objlock_kernel<true, 2, false> : fw_step_objlock_kernel<false, 2, false>;
+    if (task == 4) return random_act ? fw_step_objlock_kernel<true, 4, false> : fw_step_objlock_kernel<false, 4, false>;
     return nullptr;
 }
 

@@ -136,6 +136,17 @@ __device__ __forceinline__ void ol_col_interval(float Ax, float Ay, float Bx, fl
         lo = max(0, (int)floorf(fmaxf(c0, -4.0f)) - 1);
         hi = min(w - 1, (int)ceilf(fminf(c1, (float)w + 4.0f)) + 1);
     }
+    // The quadratic bounds LINES through the camera, so an axis behind the camera passes it as well.  A ray t > 0 along
+    // d = A + xn B reaches the disk only if P.d + rad |d| > 0; P.d is linear and |d|^2 convex in xn, so both are largest
+    // at an end of the interval: when the test fails at both ends (and the camera is outside the disk) no column of the
+    // interval can hit the cylinder or its cap, and skipping it leaves the frame unchanged.
+    if (lo <= hi && px * px + py * py > rr) {
+        const float xl = (2.0f * (float)lo + 1.0f) / (float)w - 1.0f, xh = (2.0f * (float)hi + 1.0f) / (float)w - 1.0f;
+        const float PA = px * Ax + py * Ay, PB = px * Bx + py * By;
+        const float pd = fmaxf(fmaf(xl, PB, PA), fmaf(xh, PB, PA));
+        const float dd = fmaxf(fmaf(xl, fmaf(xl, BB, 2.0f * AB), AA), fmaf(xh, fmaf(xh, BB, 2.0f * AB), AA));
+        if (pd <= 0.0f && pd * pd >= rr * dd) { lo = 1; hi = 0; }
+    }
 }
 
 // Camera.capture_image stand-in + the image reductions of _compute_vision_features, WARP-COOPERATIVE.
@@ -204,14 +215,8 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
         const float bdx = __shfl_sync(FULL, ddx, s), bdy = __shfl_sync(FULL, ddy, s), bdz = __shfl_sync(FULL, ddz, s);
         const float bdist = __shfl_sync(FULL, dist, s);
         const int bcand = __shfl_sync(FULL, cand, s), bn = __shfl_sync(FULL, o.n_obst, s);
-        // phase 0 (lanes = columns): the ground plane
-        for (int col = lane; col < w; col += 32) {
-            float xn = 2.0f * ((float)col + 0.5f) / (float)w - 1.0f;
-            float dz = bAz + xn * brz;
-            float best = INF;
-            if (dz < -1e-12f) { float t = -bcz / dz; if (t > 0.0f) best = t; }
-            depth_row[col] = best;
-        }
+        // phase 0 (lanes = columns): clear the depth row (the ground plane is intersected in phase B)
+        for (int col = lane; col < w; col += 32) depth_row[col] = INF;
         __syncwarp();
         // phase A: lane k owns cylinder k for the set-up (column interval, duck-occlusion ray); the (cylinder,
         // column) pairs to rasterise are then dealt out evenly over the 32 lanes through a warp prefix sum, so a
@@ -264,9 +269,13 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
         int c0 = 0, c1 = 0, c2 = 0;
         for (int col = lane; col < w; col += 32) {
+            const float xn = 2.0f * ((float)col + 0.5f) / (float)w - 1.0f;
             float best = depth_row[col];
+            {
+                const float dz = bAz + xn * brz;
+                if (dz < -1e-12f) { const float t = -bcz / dz; if (t > 0.0f) best = fminf(best, t); }
+            }
             if (col >= dlo && col <= dhi) {
-                float xn = 2.0f * ((float)col + 0.5f) / (float)w - 1.0f;
                 float td = ol_ray_sphere(bcx, bcy, bcz, bAx + xn * brx, bAy + xn * bry, bAz + xn * brz, bsx, bsy, bsz, Rd);
                 if (td < best) continue;
             }
@@ -339,19 +348,44 @@ __device__ __forceinline__ float ol_obstacle_penalty(const FwDev& p, const OlSta
     return fminf(scale * (p.obst_safe - dmin) / p.obst_safe, p.obst_max_pen);
 }
 
-// contact with obstacles / duck on the pose entering the step (collision probe points vs cylinders and sphere)
+// Bodies the aircraft could touch during the coming agent step: bit k = cylinder k, `duck_near` = the duck.  The velocity
+// clamp bounds the travel of one agent step (sqrt(3) max_vel dt per substep), so a body farther than that plus its
+// own reach cannot be in contact on any of the step's substeps; the per-substep test then only visits the set bits
+// (usually none) instead of scanning the whole obstacle table eight times per step.
+__device__ __forceinline__ uint32_t ol_contact_candidates(const FwDev& p, const EnvState& e, const OlState& o, const float* so,
+                                                          int tid, int stride, bool& duck_near) {
+    const float reach = p.col_radius + p.contact_margin;
+    const float travel = 1.7320508f * p.max_vel * p.dt * (float)(p.substeps_per_inner * p.inner_per_step) * 1.001f + 1e-3f;
+    uint32_t mask = 0u;
+    const float rr = p.obst_radius + reach + travel;
+    for (int k = 0; k < o.n_obst; ++k) {
+        float ddx = e.px - OL_S(so, k, 0, tid, stride), ddy = e.py - OL_S(so, k, 1, tid, stride);
+        if (ddx * ddx + ddy * ddy <= rr * rr && e.pz <= OL_S(so, k, 2, tid, stride) + reach + travel) mask |= 1u << k;
+    }
+    {
+        float ddx = e.px - o.dkx, ddy = e.py - o.dky, ddz = e.pz - (o.dkz + p.duck_radius);
+        float rd = p.duck_radius + reach + travel;
+        duck_near = ddx * ddx + ddy * ddy + ddz * ddz <= rd * rd;
+    }
+    return mask;
+}
+
+// contact with obstacles / duck on the pose entering the step (collision probe points vs cylinders and sphere);
+// `cand` = ol_contact_candidates of the agent step this substep belongs to
 __device__ __forceinline__ bool ol_contact(const FwDev& p, const EnvState& e, const OlState& o, const float* so, int tid,
-                                           int stride) {
+                                           int stride, uint32_t cand, bool duck_near) {
+    if (cand == 0u && !duck_near) return false;
     bool hit = false;
     const float reach = p.col_radius + p.contact_margin;
     // cheap reject first: most aircraft are nowhere near an obstacle, so the rotation matrix is rarely needed
     bool near_any = false;
-    for (int k = 0; k < o.n_obst; ++k) {
+    for (uint32_t mk = cand; mk; mk &= mk - 1u) {
+        const int k = __ffs(mk) - 1;
         float ddx = e.px - OL_S(so, k, 0, tid, stride), ddy = e.py - OL_S(so, k, 1, tid, stride);
         float rr = p.obst_radius + reach;
         near_any = near_any || (ddx * ddx + ddy * ddy <= rr * rr && e.pz <= OL_S(so, k, 2, tid, stride) + reach);
     }
-    {
+    if (duck_near) {
         float ddx = e.px - o.dkx, ddy = e.py - o.dky, ddz = e.pz - (o.dkz + p.duck_radius);
         float rr = p.duck_radius + reach;
         near_any = near_any || (ddx * ddx + ddy * ddy + ddz * ddz <= rr * rr);
@@ -359,7 +393,8 @@ __device__ __forceinline__ bool ol_contact(const FwDev& p, const EnvState& e, co
     if (!near_any) return false;
     Mat3 R = fw_quat_mat(e.qx, e.qy, e.qz, e.qw);
     const float* m = R.m;
-    for (int k = 0; k < o.n_obst; ++k) {
+    for (uint32_t mk = cand; mk; mk &= mk - 1u) {
+        const int k = __ffs(mk) - 1;
         float ox = OL_S(so, k, 0, tid, stride), oy = OL_S(so, k, 1, tid, stride), oh = OL_S(so, k, 2, tid, stride);
         float ddx = e.px - ox, ddy = e.py - oy;
         float rr = p.obst_radius + reach;
@@ -373,7 +408,7 @@ __device__ __forceinline__ bool ol_contact(const FwDev& p, const EnvState& e, co
             hit = hit || (qx * qx + qy * qy <= r2 && wz <= oh + p.contact_margin);
         }
     }
-    {
+    if (duck_near) {
         float sx = o.dkx, sy = o.dky, sz = o.dkz + p.duck_radius;
         float ddx = e.px - sx, ddy = e.py - sy, ddz = e.pz - sz;
         float rr = p.duck_radius + reach;
