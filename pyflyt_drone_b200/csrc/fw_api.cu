@@ -137,6 +137,14 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
             o.lift[k] = (float)l[k]; o.fwd[k] = (float)f[k]; o.tq[k] = (float)t[k]; o.r[k] = (float)r[k];
             o.ra[k] = (float)ra[k]; o.rb[k] = (float)rb[k];
         }
+        // the same numbers packed for the standard-layout kernels (SurfHot, fw_device.cuh)
+        float4* g = d.hot[s];
+        g[0] = make_float4(o.k_act, o.r[0], o.r[1], o.r[2]);
+        g[1] = make_float4(o.a0_base, o.k_te, o.asp_base, o.asn_base);
+        g[2] = make_float4(o.k_shift, o.cla, o.cla_ipa, o.cd0);
+        g[3] = make_float4(c.cd90_degrees ? o.defl_deg : o.defl_rad, o.stall_k, o.cm1c, o.cm0c);
+        g[4] = make_float4(o.qarea, o.ra[0], o.ra[1], o.ra[2]);
+        g[5] = make_float4(o.rb[0], o.rb[1], o.rb[2], 0.0f);
     }
     if (!(c.motor_tau > 0) || !(c.thrust_coef > 0)) return fail(FW_EINVAL, "bad motor constants");
     d.motor_k = (float)(c.dt / c.motor_tau);

@@ -47,7 +47,35 @@ struct SurfDev {
     float k_te, k_shift, cm0c, cm1c, cla_ipa;
 };
 
+// The per-surface constants the standard-layout substep reads, packed in the order of use as six 16-byte groups: on
+// sm_100a every constant operand reaches the FP pipe through a uniform register filled by an LDCU, and one LDCU.128
+// fetches a whole group (the scalar fields of SurfDev cost one LDCU each: 90 of the 629 instructions of a substep).
+//   g0: k_act, r.x, r.y, r.z          g1: a0_base, k_te, asp_base, asn_base     g2: k_shift, cla, cla_ipa, cd0
+//   g3: defl (deg|rad as cd90_degrees says), stall_k, cm1c, cm0c                g4: qarea, ra.x, ra.y, ra.z
+//   g5: rb.x, rb.y, rb.z, -
+struct SurfHot {
+    float k_act, r[3];
+    float a0_base, k_te, asp_base, asn_base;
+    float k_shift, cla, cla_ipa, cd0;
+    float defl_sel, stall_k, cm1c, cm0c;
+    float qarea, ra[3];
+    float rb[3];
+};
+
+__device__ __forceinline__ SurfHot fw_load_hot(const float4 (&g)[6]) {
+    const float4 g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3], g4 = g[4], g5 = g[5];
+    SurfHot h;
+    h.k_act = g0.x; h.r[0] = g0.y; h.r[1] = g0.z; h.r[2] = g0.w;
+    h.a0_base = g1.x; h.k_te = g1.y; h.asp_base = g1.z; h.asn_base = g1.w;
+    h.k_shift = g2.x; h.cla = g2.y; h.cla_ipa = g2.z; h.cd0 = g2.w;
+    h.defl_sel = g3.x; h.stall_k = g3.y; h.cm1c = g3.z; h.cm0c = g3.w;
+    h.qarea = g4.x; h.ra[0] = g4.y; h.ra[1] = g4.z; h.ra[2] = g4.w;
+    h.rb[0] = g5.x; h.rb[1] = g5.y; h.rb[2] = g5.z;
+    return h;
+}
+
 struct FwDev {
+    alignas(16) float4 hot[FWD_NSURF][6];
     SurfDev surf[FWD_NSURF];
     // motor
     float motor_k, noise_ratio, thrust_max, torque_max;
@@ -214,11 +242,18 @@ __device__ __forceinline__ Mat3 fw_quat_mat(float x, float y, float z, float w) 
 // surface's torque axis (lift x fwd).
 // STD (standard layout, checked on the host): forward unit = +x and lift unit = +z, or +y when LIFT_Y -- the two dot
 // products are plain component picks.
-template <bool STD = false, bool LIFT_Y = false>
-__device__ __forceinline__ void fw_surface(const FwDev& p, const SurfDev& sf, float act, float vx, float vy, float vz,
+__device__ __forceinline__ float fw_dot_lift(const SurfDev& sf, float vx, float vy, float vz) { return vx * sf.lift[0] + vy * sf.lift[1] + vz * sf.lift[2]; }
+__device__ __forceinline__ float fw_dot_fwd(const SurfDev& sf, float vx, float vy, float vz) { return vx * sf.fwd[0] + vy * sf.fwd[1] + vz * sf.fwd[2]; }
+__device__ __forceinline__ float fw_dot_lift(const SurfHot&, float, float, float) { return 0.0f; }   // standard layout: never called
+__device__ __forceinline__ float fw_dot_fwd(const SurfHot&, float, float, float) { return 0.0f; }
+__device__ __forceinline__ float fw_defl(const FwDev& p, const SurfDev& sf, float act) { return p.cd90_degrees ? act * sf.defl_deg : act * sf.defl_rad; }
+__device__ __forceinline__ float fw_defl(const FwDev&, const SurfHot& sf, float act) { return act * sf.defl_sel; }
+
+template <bool STD = false, bool LIFT_Y = false, class SF = SurfDev>
+__device__ __forceinline__ void fw_surface(const FwDev& p, const SF& sf, float act, float vx, float vy, float vz,
                                            float& fn, float& fp, float& tq) {
-    float vl = STD ? (LIFT_Y ? vy : vz) : vx * sf.lift[0] + vy * sf.lift[1] + vz * sf.lift[2];
-    float vf = STD ? vx : vx * sf.fwd[0] + vy * sf.fwd[1] + vz * sf.fwd[2];
+    float vl = STD ? (LIFT_Y ? vy : vz) : fw_dot_lift(sf, vx, vy, vz);
+    float vf = STD ? vx : fw_dot_fwd(sf, vx, vy, vz);
     float h2 = fmaf(vl, vl, vf * vf);
     float V2;
     if (STD) { const float vo = LIFT_Y ? vz : vy; V2 = p.freestream_3d ? fmaf(vo, vo, h2) : h2; }   // the third component
@@ -249,7 +284,7 @@ __device__ __forceinline__ void fw_surface(const FwDev& p, const SurfDev& sf, fl
 
     float CT_a = sf.cd0 * c;
     float CN_a = __fdividef(fmaf(CT_a, s, cl_lin), c);
-    float d = p.cd90_degrees ? act * sf.defl_deg : act * sf.defl_rad;
+    float d = fw_defl(p, sf, act);
     float cd90 = fmaf(fmaf(-4.26e-2f, d, 2.1e-1f), d, 1.98f);
     float CN_s = cd90 * s * (__fdividef(1.0f, fmaf(0.44f, fabsf(s), 0.56f)) - sf.stall_k);
     float CN = nostall ? CN_a : CN_s;
@@ -294,27 +329,37 @@ __device__ __forceinline__ void fw_substep(const FwDev& p, EnvState& e, const fl
     float Fx = 0.f, Fy = 0.f, Fz = 0.f, Tx = 0.f, Ty = 0.f, Tz = 0.f;
 #pragma unroll
     for (int s = 0; s < FWD_NSURF; ++s) {
+        if (STD) {
+            const SurfHot sf = fw_load_hot(p.hot[s]);
+            e.act[s] += sf.k_act * (cmd[s] - e.act[s]);
+            // local airflow at the link CoM: v_O + w x r  (wind already subtracted from v_O)
+            float sx = fmaf(wby, sf.r[2], fmaf(-wbz, sf.r[1], vbx));
+            float sy = fmaf(wbz, sf.r[0], fmaf(-wbx, sf.r[2], vby));
+            float sz = fmaf(wbx, sf.r[1], fmaf(-wby, sf.r[0], vbz));
+            float fn, fp, tq;
+            // force = lift*fn + fwd*fp at the link CoM; torque about O = fn (r x lift) + fp (r x fwd) + tq (lift x fwd)
+            if (s != 3) {               // lift +z, fwd +x: ra = (ry, -rx, 0), rb = (0, rz, -ry), lift x fwd = +y
+                fw_surface<true, false>(p, sf, e.act[s], sx, sy, sz, fn, fp, tq);
+                Fx += fp; Fz += fn;
+                Tx += sf.ra[0] * fn;
+                Ty += sf.ra[1] * fn + sf.rb[1] * fp + tq;
+                Tz += sf.rb[2] * fp;
+            } else {                    // lift +y, fwd +x: ra = (-rz, 0, rx), rb = (0, rz, -ry), lift x fwd = -z
+                fw_surface<true, true>(p, sf, e.act[s], sx, sy, sz, fn, fp, tq);
+                Fx += fp; Fy += fn;
+                Tx += sf.ra[0] * fn;
+                Ty += sf.rb[1] * fp;
+                Tz += sf.ra[2] * fn + sf.rb[2] * fp - tq;
+            }
+            continue;
+        }
         const SurfDev& sf = p.surf[s];
         e.act[s] += sf.k_act * (cmd[s] - e.act[s]);
-        // local airflow at the link CoM: v_O + w x r  (wind already subtracted from v_O)
         float sx = fmaf(wby, sf.r[2], fmaf(-wbz, sf.r[1], vbx));
         float sy = fmaf(wbz, sf.r[0], fmaf(-wbx, sf.r[2], vby));
         float sz = fmaf(wbx, sf.r[1], fmaf(-wby, sf.r[0], vbz));
         float fn, fp, tq;
-        // force = lift*fn + fwd*fp at the link CoM; torque about O = fn (r x lift) + fp (r x fwd) + tq (lift x fwd)
-        if (STD && s != 3) {            // lift +z, fwd +x: ra = (ry, -rx, 0), rb = (0, rz, -ry), lift x fwd = +y
-            fw_surface<true, false>(p, sf, e.act[s], sx, sy, sz, fn, fp, tq);
-            Fx += fp; Fz += fn;
-            Tx += sf.ra[0] * fn;
-            Ty += sf.ra[1] * fn + sf.rb[1] * fp + tq;
-            Tz += sf.rb[2] * fp;
-        } else if (STD) {               // lift +y, fwd +x: ra = (-rz, 0, rx), rb = (0, rz, -ry), lift x fwd = -z
-            fw_surface<true, true>(p, sf, e.act[s], sx, sy, sz, fn, fp, tq);
-            Fx += fp; Fy += fn;
-            Tx += sf.ra[0] * fn;
-            Ty += sf.rb[1] * fp;
-            Tz += sf.ra[2] * fn + sf.rb[2] * fp - tq;
-        } else {
+        {
             fw_surface(p, sf, e.act[s], sx, sy, sz, fn, fp, tq);
             Fx += sf.lift[0] * fn + sf.fwd[0] * fp;
             Fy += sf.lift[1] * fn + sf.fwd[1] * fp;
