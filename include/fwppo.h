@@ -27,7 +27,8 @@ extern "C" {
 
 #define PPO_HIDDEN 64
 #define PPO_ACT 4
-#define PPO_MAX_OBS 32
+#define PPO_MAX_OBS 64      /* CUDA-core forward, value, bootstrap, running moments */
+#define PPO_TC_MAX_OBS 32   /* tcgen05 forward (ppo_policy_forward_tc*) and fused minibatch gradient (ppo_minibatch_grad) */
 
 /* number of floats in the parameter vector for observation width d */
 int ppo_param_count(int32_t d);

@@ -187,6 +187,15 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
                 if (lat_i != lat_j && fabs(Ai[6 * i + j]) > 1e-12 * amax) std_ok = false;
             }
         d.std_geom = (std_ok && c.force_generic_kernel == 0) ? 1 : 0;
+        // packed rigid-body / motor constants of the standard-layout substep (FwDev::rbk)
+        const int lat[9] = {0, 2, 4, 12, 14, 16, 24, 26, 28}, lon[9] = {7, 9, 11, 19, 21, 23, 31, 33, 35};
+        float k[FWD_RBK * 4] = {0};
+        k[0] = d.motor_k; k[1] = d.noise_ratio; k[2] = d.thrust_max; k[3] = d.torque_max;
+        k[4] = d.r_motor[1]; k[5] = d.r_motor[2]; k[6] = (float)c.gravity; k[7] = d.mass;
+        k[8] = d.com[0]; k[9] = d.com[1]; k[10] = d.com[2]; k[11] = (float)c.max_coord_vel;
+        for (int q = 0; q < 9; ++q) k[12 + q] = d.inertia[q];
+        for (int q = 0; q < 9; ++q) { k[21 + q] = d.minv[lat[q]]; k[30 + q] = d.minv[lon[q]]; }
+        for (int q = 0; q < FWD_RBK; ++q) d.rbk[q] = make_float4(k[4 * q], k[4 * q + 1], k[4 * q + 2], k[4 * q + 3]);
     }
     double rad = 0.0;
     for (int i = 0; i < c.n_col; ++i) {

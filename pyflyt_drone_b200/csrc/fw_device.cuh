@@ -74,8 +74,15 @@ __device__ __forceinline__ SurfHot fw_load_hot(const float4 (&g)[6]) {
     return h;
 }
 
+// Rigid-body / motor constants of the standard-layout substep, packed the same way (fw_api.cu: derive()):
+//   0: motor_k, noise_ratio, thrust_max, torque_max      1: r_motor.y, r_motor.z, gravity, mass
+//   2: com.xyz, max_vel                                  3-4: inertia[0..7]        5: inertia[8], lateral minv 0,2,4 ...
+//   5.y-7.z: lateral block minv[0,2,4,12,14,16,24,26,28]   7.w-9.w: longitudinal block minv[7,9,11,19,21,23,31,33,35]
+#define FWD_RBK 10
+
 struct FwDev {
     alignas(16) float4 hot[FWD_NSURF][6];
+    alignas(16) float4 rbk[FWD_RBK];
     SurfDev surf[FWD_NSURF];
     // motor
     float motor_k, noise_ratio, thrust_max, torque_max;
@@ -369,16 +376,38 @@ __device__ __forceinline__ void fw_substep(const FwDev& p, EnvState& e, const fl
             Tz += sf.ra[2] * fn + sf.rb[2] * fp + sf.tq[2] * tq;
         }
     }
+    // constants of the rest of the step: packed groups on the standard path, plain fields otherwise
+    float k_motor_k, k_noise, k_thrust_max, k_torque_max, k_rm1, k_rm2, k_gravity, k_mass, k_com[3], k_mv, k_I[9], k_minv[18];
+    if (STD) {
+        const float4 q0 = p.rbk[0], q1 = p.rbk[1], q2 = p.rbk[2], q3 = p.rbk[3], q4 = p.rbk[4], q5 = p.rbk[5], q6 = p.rbk[6],
+                     q7 = p.rbk[7], q8 = p.rbk[8], q9 = p.rbk[9];
+        k_motor_k = q0.x; k_noise = q0.y; k_thrust_max = q0.z; k_torque_max = q0.w;
+        k_rm1 = q1.x; k_rm2 = q1.y; k_gravity = q1.z; k_mass = q1.w;
+        k_com[0] = q2.x; k_com[1] = q2.y; k_com[2] = q2.z; k_mv = q2.w;
+        k_I[0] = q3.x; k_I[1] = q3.y; k_I[2] = q3.z; k_I[3] = q3.w; k_I[4] = q4.x; k_I[5] = q4.y; k_I[6] = q4.z; k_I[7] = q4.w;
+        k_I[8] = q5.x;
+        k_minv[0] = q5.y; k_minv[1] = q5.z; k_minv[2] = q5.w; k_minv[3] = q6.x; k_minv[4] = q6.y; k_minv[5] = q6.z;
+        k_minv[6] = q6.w; k_minv[7] = q7.x; k_minv[8] = q7.y; k_minv[9] = q7.z; k_minv[10] = q7.w; k_minv[11] = q8.x;
+        k_minv[12] = q8.y; k_minv[13] = q8.z; k_minv[14] = q8.w; k_minv[15] = q9.x; k_minv[16] = q9.y; k_minv[17] = q9.z;
+    } else {
+        k_motor_k = p.motor_k; k_noise = p.noise_ratio; k_thrust_max = p.thrust_max; k_torque_max = p.torque_max;
+        k_rm1 = p.r_motor[1]; k_rm2 = p.r_motor[2]; k_gravity = p.gravity; k_mass = p.mass;
+        k_com[0] = p.com[0]; k_com[1] = p.com[1]; k_com[2] = p.com[2]; k_mv = p.max_vel;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) k_I[k] = p.inertia[k];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) k_minv[k] = 0.0f;       // the generic solve below reads p.minv
+    }
     {   // motor: first-order lag, multiplicative gaussian noise, thrust ~ rpm^2
-        e.thr += p.motor_k * (cmd[5] - e.thr);
-        e.thr += nz * e.thr * p.noise_ratio;
+        e.thr += k_motor_k * (cmd[5] - e.thr);
+        e.thr += nz * e.thr * k_noise;
         float t2 = e.thr * e.thr;
-        float thrust = t2 * p.thrust_max, torque = t2 * p.torque_max;
+        float thrust = t2 * k_thrust_max, torque = t2 * k_torque_max;
         if (STD) {                      // thrust along +x
             Fx += thrust;
             Tx += torque;
-            Ty += p.r_motor[2] * thrust;
-            Tz -= p.r_motor[1] * thrust;
+            Ty += k_rm2 * thrust;
+            Tz -= k_rm1 * thrust;
         } else {
             float fx = thrust * p.thrust_unit[0], fy = thrust * p.thrust_unit[1], fz = thrust * p.thrust_unit[2];
             Fx += fx; Fy += fy; Fz += fz;
@@ -395,33 +424,33 @@ __device__ __forceinline__ void fw_substep(const FwDev& p, EnvState& e, const fl
         }
     }
     // gravity on every link == M g at the composite CoM; g_body = R^T (0,0,-g)
-    float gx = -p.gravity * m[6], gy = -p.gravity * m[7], gz = -p.gravity * m[8];
-    Fx += p.mass * gx; Fy += p.mass * gy; Fz += p.mass * gz;
-    Tx += p.mass * (p.com[1] * gz - p.com[2] * gy);
-    Ty += p.mass * (p.com[2] * gx - p.com[0] * gz);
-    Tz += p.mass * (p.com[0] * gy - p.com[1] * gx);
+    float gx = -k_gravity * m[6], gy = -k_gravity * m[7], gz = -k_gravity * m[8];
+    Fx += k_mass * gx; Fy += k_mass * gy; Fz += k_mass * gz;
+    Tx += k_mass * (k_com[1] * gz - k_com[2] * gy);
+    Ty += k_mass * (k_com[2] * gx - k_com[0] * gz);
+    Tz += k_mass * (k_com[0] * gy - k_com[1] * gx);
     // bias terms: w x (I w) and M w x (w x c)
-    float Iwx = p.inertia[0] * wbx + p.inertia[1] * wby + p.inertia[2] * wbz;
-    float Iwy = p.inertia[3] * wbx + p.inertia[4] * wby + p.inertia[5] * wbz;
-    float Iwz = p.inertia[6] * wbx + p.inertia[7] * wby + p.inertia[8] * wbz;
+    float Iwx = k_I[0] * wbx + k_I[1] * wby + k_I[2] * wbz;
+    float Iwy = k_I[3] * wbx + k_I[4] * wby + k_I[5] * wbz;
+    float Iwz = k_I[6] * wbx + k_I[7] * wby + k_I[8] * wbz;
     float b0 = Tx - (wby * Iwz - wbz * Iwy);
     float b1 = Ty - (wbz * Iwx - wbx * Iwz);
     float b2 = Tz - (wbx * Iwy - wby * Iwx);
-    float cx = wby * p.com[2] - wbz * p.com[1];
-    float cy = wbz * p.com[0] - wbx * p.com[2];
-    float cz = wbx * p.com[1] - wby * p.com[0];
-    float b3 = Fx - p.mass * (wby * cz - wbz * cy);
-    float b4 = Fy - p.mass * (wbz * cx - wbx * cz);
-    float b5 = Fz - p.mass * (wbx * cy - wby * cx);
+    float cx = wby * k_com[2] - wbz * k_com[1];
+    float cy = wbz * k_com[0] - wbx * k_com[2];
+    float cz = wbx * k_com[1] - wby * k_com[0];
+    float b3 = Fx - k_mass * (wby * cz - wbz * cy);
+    float b4 = Fy - k_mass * (wbz * cx - wbx * cz);
+    float b5 = Fz - k_mass * (wbx * cy - wby * cx);
     float acc[6];
     if (STD) {
         // lateral block {0: wx, 2: wz, 4: vy} and longitudinal block {1: wy, 3: vx, 5: vz}
-        acc[0] = p.minv[0] * b0 + p.minv[2] * b2 + p.minv[4] * b4;
-        acc[2] = p.minv[12] * b0 + p.minv[14] * b2 + p.minv[16] * b4;
-        acc[4] = p.minv[24] * b0 + p.minv[26] * b2 + p.minv[28] * b4;
-        acc[1] = p.minv[7] * b1 + p.minv[9] * b3 + p.minv[11] * b5;
-        acc[3] = p.minv[19] * b1 + p.minv[21] * b3 + p.minv[23] * b5;
-        acc[5] = p.minv[31] * b1 + p.minv[33] * b3 + p.minv[35] * b5;
+        acc[0] = k_minv[0] * b0 + k_minv[1] * b2 + k_minv[2] * b4;
+        acc[2] = k_minv[3] * b0 + k_minv[4] * b2 + k_minv[5] * b4;
+        acc[4] = k_minv[6] * b0 + k_minv[7] * b2 + k_minv[8] * b4;
+        acc[1] = k_minv[9] * b1 + k_minv[10] * b3 + k_minv[11] * b5;
+        acc[3] = k_minv[12] * b1 + k_minv[13] * b3 + k_minv[14] * b5;
+        acc[5] = k_minv[15] * b1 + k_minv[16] * b3 + k_minv[17] * b5;
     } else {
 #pragma unroll
         for (int i = 0; i < 6; ++i)
@@ -435,7 +464,7 @@ __device__ __forceinline__ void fw_substep(const FwDev& p, EnvState& e, const fl
     float Awx = m[0] * acc[3] + m[1] * acc[4] + m[2] * acc[5];
     float Awy = m[3] * acc[3] + m[4] * acc[4] + m[5] * acc[5];
     float Awz = m[6] * acc[3] + m[7] * acc[4] + m[8] * acc[5];
-    const float mv = p.max_vel;
+    const float mv = k_mv;
     e.wx = fminf(fmaxf(e.wx + awx * dt, -mv), mv);
     e.wy = fminf(fmaxf(e.wy + awy * dt, -mv), mv);
     e.wz = fminf(fmaxf(e.wz + awz * dt, -mv), mv);

@@ -30,6 +30,13 @@ static int check_d(int d) {
     if (d < 1 || d > PPO_MAX_OBS) return pfail(FW_EINVAL, "obs width %d out of range [1,%d]", d, PPO_MAX_OBS);
     return FW_OK;
 }
+// the tcgen05 kernels (K4 forward, K6 minibatch gradient) stage one 32-wide K slab of observations per tile
+static int check_d_tc(int d) {
+    if (d < 1 || d > PPO_TC_MAX_OBS)
+        return pfail(FW_EINVAL, "obs width %d out of range [1,%d] for the tensor-core kernels (use the CUDA-core forward / "
+                                "the torch update)", d, PPO_TC_MAX_OBS);
+    return FW_OK;
+}
 
 static int check_a(int a) {
     if (a != 4 && a != 6) return pfail(FW_EINVAL, "action width %d not supported (4 or 6)", a);
@@ -114,7 +121,7 @@ extern "C" int ppo_policy_forward_tc_a(const float* params, int32_t d, int32_t a
                                        float* act_env, float* act_raw, float* logp, float* value, void* stream) {
     if (!params || !obs_raw || !act_env || !value) return pfail(FW_EINVAL, "null argument");
     if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
-    int rc = check_d(d);
+    int rc = check_d_tc(d);
     if (rc) return rc;
     if ((rc = check_a(a)) != 0) return rc;
     if ((reinterpret_cast<uintptr_t>(act_env) & 15u) || (act_raw && (reinterpret_cast<uintptr_t>(act_raw) & 15u)))
@@ -201,7 +208,7 @@ extern "C" int ppo_minibatch_grad(const float* params, int32_t d, const float* o
     if (!params || !obs_norm || !act || !logp_old || !adv || !ret || !idx || !workspace || !grad)
         return pfail(FW_EINVAL, "null argument");
     if (batch <= 0) return pfail(FW_EINVAL, "batch must be positive");
-    int rc = check_d(d);
+    int rc = check_d_tc(d);
     if (rc) return rc;
     if ((reinterpret_cast<uintptr_t>(workspace) & 15u) || (reinterpret_cast<uintptr_t>(act) & 15u))
         return pfail(FW_EINVAL, "workspace and action buffer must be 16-byte aligned");

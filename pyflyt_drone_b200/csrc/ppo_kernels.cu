@@ -11,7 +11,8 @@
 
 #define H PPO_H
 #define A PPO_A
-#define DP PPO_DPAD      // observation width padded to 32 for float4 weight rows
+// DP (template parameter below) = observation width padded to 32 or 64 for float4 weight rows: 32 covers the
+// 28/29-float Waypoints observations and the 21-float low-level one, 64 the 56-float duck-only ObjLock observation
 
 // ------------------------------------------------------------------ shared helpers
 __device__ __forceinline__ uint4 ppo_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
@@ -35,16 +36,16 @@ __device__ __forceinline__ float ppo_tanh(float x) {
 }
 
 // smem layout of one tower: W1[H][DP] b1[H] W2[H][H] b2[H] W3[OUT][H] b3[OUT]
-template <int OUT>
+template <int OUT, int DP>
 struct TowerOff {
     static constexpr int W1 = 0, B1 = W1 + H * DP, W2 = B1 + H, B2 = W2 + H * H, W3 = B2 + H, B3 = W3 + OUT * H,
                          SIZE = ((B3 + OUT + 3) / 4) * 4;
 };
 
 // copy one tower from the packed global parameter vector ([out,in] rows of width d) into padded smem
-template <int OUT>
+template <int OUT, int DP>
 __device__ void load_tower(float* s, const float* __restrict__ g, int d) {
-    using O = TowerOff<OUT>;
+    using O = TowerOff<OUT, DP>;
     const int tid = threadIdx.x, nt = blockDim.x;
     for (int i = tid; i < H * DP; i += nt) { int j = i / DP, k = i % DP; s[O::W1 + i] = k < d ? g[j * d + k] : 0.0f; }
     const float* gb1 = g + H * d;
@@ -61,9 +62,9 @@ __device__ void load_tower(float* s, const float* __restrict__ g, int d) {
 
 // One tower for the calling thread's row.  x: normalised observation in registers (DP wide, zero padded);
 // hbuf: this block's [H][blockDim.x] activation scratch (column = thread, conflict-free).  out[OUT].
-template <int OUT>
+template <int OUT, int DP>
 __device__ __forceinline__ void tower_forward(const float* __restrict__ s, const float (&x)[DP], float* hbuf, float (&out)[OUT]) {
-    using O = TowerOff<OUT>;
+    using O = TowerOff<OUT, DP>;
     const int tid = threadIdx.x, nt = blockDim.x;
     // layer 1: weights broadcast from smem (every thread reads the same address), inputs in registers
     for (int j = 0; j < H; ++j) {
@@ -101,6 +102,7 @@ __device__ __forceinline__ void tower_forward(const float* __restrict__ s, const
 }
 
 // normalise one observation row into registers (VecNormalize.normalize_obs) and optionally store it
+template <int DP>
 __device__ __forceinline__ void load_obs(const float* __restrict__ obs_raw, const float* s_mean, const float* s_istd,
                                          float clip, int d, int row, float (&x)[DP], float* __restrict__ obs_norm) {
 #pragma unroll
@@ -115,6 +117,7 @@ __device__ __forceinline__ void load_obs(const float* __restrict__ obs_raw, cons
     }
 }
 
+template <int DP>
 __device__ __forceinline__ void stage_stats(const double* __restrict__ stats, int d, float* s_mean, float* s_istd) {
     for (int k = threadIdx.x; k < DP; k += blockDim.x) {
         if (stats != nullptr && k < d) {
@@ -126,7 +129,7 @@ __device__ __forceinline__ void stage_stats(const double* __restrict__ stats, in
 
 // ------------------------------------------------------------------ K4: policy + value forward, one thread per env
 // AO = action width: 4 (roll, pitch, yaw, thrust) or 6 (the low-level env's surface / thrust channels)
-template <int AO>
+template <int AO, int DP>
 __global__ void __launch_bounds__(PPO_FWD_THREADS)
 ppo_forward_kernel(const float* __restrict__ params, int d, const float* __restrict__ obs_raw,
                    const double* __restrict__ stats, float clip, int n, uint32_t seed_lo, uint32_t seed_hi,
@@ -145,25 +148,25 @@ ppo_forward_kernel(const float* __restrict__ params, int d, const float* __restr
         if (!__syncthreads_or(boot_need ? 1 : 0)) return;
     }
     float* s_pi = smem;
-    float* s_vf = s_pi + TowerOff<AO>::SIZE;
-    float* s_mean = s_vf + TowerOff<1>::SIZE;
+    float* s_vf = s_pi + TowerOff<AO, DP>::SIZE;
+    float* s_mean = s_vf + TowerOff<1, DP>::SIZE;
     float* s_istd = s_mean + DP;
     float* s_logstd = s_istd + DP;
     float* hbuf = s_logstd + 8;
     const int pi_count = H * d + H + H * H + H + AO * H + AO;
     const int vf_count = H * d + H + H * H + H + H + 1;
-    if (want_policy) load_tower<AO>(s_pi, params, d);
-    load_tower<1>(s_vf, params + pi_count, d);
-    stage_stats(stats, d, s_mean, s_istd);
+    if (want_policy) load_tower<AO, DP>(s_pi, params, d);
+    load_tower<1, DP>(s_vf, params + pi_count, d);
+    stage_stats<DP>(stats, d, s_mean, s_istd);
     if (threadIdx.x < AO) s_logstd[threadIdx.x] = params[pi_count + vf_count + threadIdx.x];
     __syncthreads();
 
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n) return;
     float x[DP];
-    load_obs(obs_raw, stats ? s_mean : nullptr, s_istd, clip, d, row, x, obs_norm);
+    load_obs<DP>(obs_raw, stats ? s_mean : nullptr, s_istd, clip, d, row, x, obs_norm);
     float v[1];
-    tower_forward<1>(s_vf, x, hbuf, v);
+    tower_forward<1, DP>(s_vf, x, hbuf, v);
     if (boot_flags != nullptr) {
         if (boot_need) boot_rew[row] = fmaf(boot_gamma, v[0], boot_rew[row]);    // TimeLimit.truncated
         return;
@@ -171,7 +174,7 @@ ppo_forward_kernel(const float* __restrict__ params, int d, const float* __restr
     value[row] = v[0];
     if (!want_policy) return;
     float mean[AO];
-    tower_forward<AO>(s_pi, x, hbuf, mean);
+    tower_forward<AO, DP>(s_pi, x, hbuf, mean);
     // diagonal Gaussian: a = mu + sigma * eps ; log pi(a) = sum -0.5 eps^2 - log sigma - 0.5 log 2pi
     const uint32_t step_eff = step + (step_dev != nullptr ? step_dev[0] : 0u);   // device counter: graph-replayable
     float eps[AO];
@@ -205,26 +208,26 @@ ppo_forward_kernel(const float* __restrict__ params, int d, const float* __restr
     if (logp != nullptr) logp[row] = lp;
 }
 
-template <int AO>
+template <int AO, int DP>
 static size_t ppo_forward_smem_t() {
-    return (size_t)(TowerOff<AO>::SIZE + TowerOff<1>::SIZE + 2 * DP + 8 + H * PPO_FWD_THREADS) * sizeof(float);
+    return (size_t)(TowerOff<AO, DP>::SIZE + TowerOff<1, DP>::SIZE + 2 * DP + 8 + H * PPO_FWD_THREADS) * sizeof(float);
 }
-size_t ppo_forward_smem() { return ppo_forward_smem_t<A>(); }
+size_t ppo_forward_smem() { return ppo_forward_smem_t<A, 32>(); }
 
-template <int AO>
+template <int AO, int DP>
 static cudaError_t ppok_forward_t(const float* params, int d, const float* obs_raw, const double* stats, float clip, int n,
                                   uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev, int deterministic,
                                   float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, int want_policy,
                                   cudaStream_t st, const uint8_t* boot_flags, float boot_gamma, float* boot_rew) {
     static bool attr_set = false;
-    const size_t sm = ppo_forward_smem_t<AO>();
+    const size_t sm = ppo_forward_smem_t<AO, DP>();
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ppo_forward_kernel<AO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        cudaError_t e = cudaFuncSetAttribute(ppo_forward_kernel<AO, DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     const int grid = (n + PPO_FWD_THREADS - 1) / PPO_FWD_THREADS;
-    ppo_forward_kernel<AO><<<grid, PPO_FWD_THREADS, sm, st>>>(params, d, obs_raw, stats, clip, n, (uint32_t)(seed & 0xffffffffu),
+    ppo_forward_kernel<AO, DP><<<grid, PPO_FWD_THREADS, sm, st>>>(params, d, obs_raw, stats, clip, n, (uint32_t)(seed & 0xffffffffu),
                                                               (uint32_t)(seed >> 32), env_id0, step, step_dev, deterministic,
                                                               obs_norm, act_env, act_raw, logp, value, want_policy, boot_flags,
                                                               boot_gamma, boot_rew);
@@ -235,12 +238,14 @@ cudaError_t ppok_forward(const float* params, int d, const float* obs_raw, const
                          uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev, int deterministic,
                          float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, int want_policy,
                          cudaStream_t st, const uint8_t* boot_flags, float boot_gamma, float* boot_rew, int a) {
-    if (a == 4)
-        return ppok_forward_t<4>(params, d, obs_raw, stats, clip, n, seed, env_id0, step, step_dev, deterministic, obs_norm,
-                                 act_env, act_raw, logp, value, want_policy, st, boot_flags, boot_gamma, boot_rew);
-    if (a == 6)
-        return ppok_forward_t<6>(params, d, obs_raw, stats, clip, n, seed, env_id0, step, step_dev, deterministic, obs_norm,
-                                 act_env, act_raw, logp, value, want_policy, st, boot_flags, boot_gamma, boot_rew);
+    if (d > 64) return cudaErrorInvalidValue;
+#define FWD_DISPATCH(AO_, DP_)                                                                                             \
+    return ppok_forward_t<AO_, DP_>(params, d, obs_raw, stats, clip, n, seed, env_id0, step, step_dev, deterministic, obs_norm, \
+                                    act_env, act_raw, logp, value, want_policy, st, boot_flags, boot_gamma, boot_rew)
+    if (a == 4 && d <= 32) FWD_DISPATCH(4, 32);
+    if (a == 6 && d <= 32) FWD_DISPATCH(6, 32);
+    if (a == 4) FWD_DISPATCH(4, 64);                 // the 56-float duck-only ObjLock observation
+#undef FWD_DISPATCH
     return cudaErrorInvalidValue;
 }
 
@@ -250,31 +255,35 @@ cudaError_t ppok_forward(const float* params, int d, const float* obs_raw, const
 __global__ void __launch_bounds__(256)
 ppo_moments_kernel(const float* __restrict__ x, int n, int d, double* __restrict__ stats, double* __restrict__ scratch,
                    double* __restrict__ accum, int rows_per_block) {
-    __shared__ float s_sum[8][PPO_DPAD], s_sq[8][PPO_DPAD];
+    __shared__ float s_sum[8][32], s_sq[8][32];
     __shared__ bool is_last;
     // thread layout: 32 columns x 8 row-lanes; a warp reads 32 consecutive floats of one row when d == 32, and
     // d/32 of a 128-byte line otherwise (rows are contiguous, so the block still streams whole lines)
-    const int col = threadIdx.x & 31, lane_row = threadIdx.x >> 5;
+    const int lane_row = threadIdx.x >> 5;
     const int r0 = blockIdx.x * rows_per_block, r1 = min(n, r0 + rows_per_block);
-    float sum = 0.0f, sq = 0.0f;
-    if (col < d) {
-        // all of this thread's loads are issued before the first add (MOM_ROWS / 8 = 16 independent requests)
-        float v[MOM_ROWS / 8];
+    for (int c0 = 0; c0 < d; c0 += 32) {             // observations wider than 32 floats: one pass per 32-column chunk
+        const int col = c0 + (threadIdx.x & 31);
+        float sum = 0.0f, sq = 0.0f;
+        if (col < d) {
+            // all of this thread's loads are issued before the first add (MOM_ROWS / 8 = 16 independent requests)
+            float v[MOM_ROWS / 8];
 #pragma unroll
-        for (int k = 0; k < MOM_ROWS / 8; ++k) {
-            const int r = r0 + lane_row + 8 * k;
-            v[k] = r < r1 ? x[(size_t)r * d + col] : 0.0f;
+            for (int k = 0; k < MOM_ROWS / 8; ++k) {
+                const int r = r0 + lane_row + 8 * k;
+                v[k] = r < r1 ? x[(size_t)r * d + col] : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < MOM_ROWS / 8; ++k) { sum += v[k]; sq = fmaf(v[k], v[k], sq); }
         }
-#pragma unroll
-        for (int k = 0; k < MOM_ROWS / 8; ++k) { sum += v[k]; sq = fmaf(v[k], v[k], sq); }
-    }
-    s_sum[lane_row][col] = sum; s_sq[lane_row][col] = sq;
-    __syncthreads();
-    if (lane_row == 0 && col < d) {
-        double a = 0.0, b = 0.0;
-        for (int k = 0; k < 8; ++k) { a += (double)s_sum[k][col]; b += (double)s_sq[k][col]; }
-        atomicAdd(&scratch[col], a);
-        atomicAdd(&scratch[d + col], b);
+        if (c0) __syncthreads();                     // the previous chunk's partials have been consumed
+        s_sum[lane_row][threadIdx.x & 31] = sum; s_sq[lane_row][threadIdx.x & 31] = sq;
+        __syncthreads();
+        if (lane_row == 0 && col < d) {
+            double a = 0.0, b = 0.0;
+            for (int k = 0; k < 8; ++k) { a += (double)s_sum[k][threadIdx.x & 31]; b += (double)s_sq[k][threadIdx.x & 31]; }
+            atomicAdd(&scratch[col], a);
+            atomicAdd(&scratch[d + col], b);
+        }
     }
     __threadfence();
     __syncthreads();

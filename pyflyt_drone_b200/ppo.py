@@ -254,10 +254,10 @@ class PPO:
         if update not in ("kernel", "torch"):
             raise ValueError("update must be 'kernel' (hand-written tcgen05 kernels) or 'torch' (autograd reference)")
         self.update = update
-        if self.a != A:
-            # The fused update (K6) is built for the 4-channel policies of the Waypoints / ObjLock scripts.  Six-channel
-            # policies (train_lowlevel_cmd.py) roll out with the same forward kernels (compiled for width 6) and update
-            # through the torch autograd path.
+        if self.a != A or self.d > 32:
+            # The fused update (K6) is built for the 4-channel, <= 32-float-observation policies of the Waypoints /
+            # Waypoint-ObjLock scripts.  Six-channel policies (train_lowlevel_cmd.py) and the 56-float duck-only ObjLock
+            # observation (train_objlock.py) roll out with the forward kernels and update through the torch autograd path.
             self.update = "torch"
         P = self.policy.count
         self._ws = torch.zeros(int(self.lib.ppo_update_workspace_floats(self.d)), **f32)
@@ -267,7 +267,8 @@ class PPO:
         self._grad_norm = torch.zeros(1, **f32)
         self._stats, self._stats_mb = torch.zeros(8, **f32), torch.zeros(8, **f32)
         self.use_graph = bool(use_cuda_graph)
-        self.tensor_core_forward = bool(tensor_core_forward)
+        # the tcgen05 forward stages one 32-wide K slab of observations per tile; wider observations use the CUDA-core one
+        self.tensor_core_forward = bool(tensor_core_forward) and self.d <= 32
         self._graph = None
         self._pending_capture = False
         self._obs = None               # raw observation tensor (view of the env's persistent buffer)

@@ -222,3 +222,52 @@ def test_duck_gym_view_and_vec_infos():
     obs, rew, dones, infos = v.step(np.zeros((8, 4), np.float32))
     assert obs.shape == (8, 56) and set(infos[0]) >= {"collision", "out_of_bounds", "env_complete", "duck_strike", "is_success"}
     v.close()
+
+
+def test_ppo_on_the_duck_env_wide_observation():
+    """train/train_objlock.py on the device: the 56-float observation runs through the CUDA-core forward / value /
+    bootstrap / running-moment kernels built for observations up to 64 floats wide (the tcgen05 kernels stage one
+    32-wide K slab), update through the torch autograd path.  The forward must agree with the fp32 torch towers, the
+    running moments with NumPy, and a short run must improve the return."""
+    import torch
+    from pyflyt_drone_b200.ppo import PPO
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    env = FixedwingVecEnv(1024, preset="objlock_duck", seed=3)
+    m = PPO("MlpPolicy", env, n_steps=32, batch_size=8192, n_epochs=4, seed=3, use_cuda_graph=False)
+    assert m.d == 56 and m.a == 4 and m.update == "torch" and m.tensor_core_forward is False
+    assert m.policy.count == m.policy.theta.numel() == int(m.lib.ppo_param_count(56))
+    with torch.no_grad():
+        m.policy.theta.add_(0.05 * torch.randn(m.policy.count, device=m.device, generator=m._gen))
+    m.collect_rollouts()
+    torch.cuda.synchronize()
+    b = m.buf
+    obs, act = b["obs"].view(-1, 56), b["act"].view(-1, 4)
+    with torch.no_grad():
+        torch.backends.cuda.matmul.allow_tf32 = False
+        v, lp, _ = m.policy.evaluate_actions(obs, act)
+    dl, dv = (lp - b["logp"].view(-1)).abs(), (v - b["val"].view(-1)).abs()
+    assert float(dl.max()) < 2e-4 and float(dl.mean()) < 2e-5, (float(dl.max()), float(dl.mean()))
+    assert float(dv.max()) < 2e-4, float(dv.max())
+    assert float(obs.abs().max()) <= 10.0 + 1e-6                      # VecNormalize clip on all 56 columns
+    # running moments of a 56-column batch (two 32-column passes) against NumPy
+    from pyflyt_drone_b200 import _lib
+    from pyflyt_drone_b200.ppo import DeviceVecNormalize, _p, _stream
+    vn = DeviceVecNormalize(56, 3000, m.device)
+    x = (np.random.default_rng(0).normal(size=(3000, 56)) * np.linspace(2.0, 30, 56) + np.linspace(-50, 50, 56)).astype(np.float32)
+    _lib.check(m.lib.ppo_moments_update(_p(torch.from_numpy(x).to(m.device)), 3000, 56, _p(vn.obs_stats), _p(vn.obs_scratch),
+                                        _p(vn.obs_accum), _stream()))
+    got = vn.obs_stats.cpu().numpy()
+    bm, bv = x.astype(np.float64).mean(0), x.astype(np.float64).var(0)
+    tot = 1e-4 + 3000
+    assert np.allclose(got[:56], bm * 3000 / tot, rtol=1e-6, atol=1e-6)
+    assert np.allclose(got[56:112], (1e-4 + bv * 3000 + bm ** 2 * 1e-4 * 3000 / tot) / tot, rtol=1e-4)
+    # the tensor-core entry points refuse the wide observation instead of mis-staging it
+    assert m.lib.ppo_policy_forward_tc_a(_p(m.policy.theta), 56, 4, _p(obs), None, 10.0, 1024, 0, 0, 0, None, 0, None,
+                                         _p(m.act_env), None, None, _p(b["val"][0]), _stream()) == -1
+    m2 = PPO("MlpPolicy", env, n_steps=32, batch_size=8192, n_epochs=4, seed=3)
+    r0, _, l0, _ = m2.evaluate_policy(n_eval_episodes=512)
+    m2.learn(30 * 32 * 1024)
+    r1, _, l1, _ = m2.evaluate_policy(n_eval_episodes=512)
+    print(f"\n[duck ppo] raw return per episode {r0:.1f} -> {r1:.1f}, episode length {l0:.0f} -> {l1:.0f}")
+    assert r1 > r0, (r0, r1, l0, l1)
+    env.close()
