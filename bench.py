@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--workload", choices=["physics_only", "waypoints_v3", "waypoint_objlock", "lowlevel", "objlock_duck", "ppo"],
                     default="physics_only",
                     help="ppo = BASELINE configs[2]: PPO Fixedwing-Waypoints rollout+update (a step is one PPO iteration)")
-    ap.add_argument("--ppo-preset", choices=["waypoints_v3", "waypoint_objlock"], default="waypoints_v3")
+    ap.add_argument("--ppo-preset", choices=["waypoints_v3", "waypoint_objlock", "lowlevel", "objlock_duck"], default="waypoints_v3")
     ap.add_argument("--ppo-envs", type=int, default=4096)
     ap.add_argument("--ppo-n-steps", type=int, default=128)
     ap.add_argument("--ppo-minibatches", type=int, default=4)
@@ -406,8 +406,10 @@ def run_ppo(args, rank: int, local_rank: int, world: int):
                            "envs_per_gpu": N, "n_steps": T, "minibatches_per_epoch": args.ppo_minibatches,
                            "n_epochs": args.ppo_epochs, "rollout_s": st.rollout_s, "update_s": st.update_s,
                            "rollout_env_steps_per_sec": st.env_steps / max(st.rollout_s, 1e-9),
-                           "update": "fused tcgen05 minibatch gradient kernel + clip/Adam kernel (csrc/ppo_update_tc.cu)",
-                           "forward": "tcgen05 kind::tf32 policy/value forward (csrc/ppo_tc.cu)", "rollout": "CUDA graph"},
+                           "update": "fused tcgen05 minibatch gradient kernel + clip/Adam kernel (csrc/ppo_update_tc.cu)"
+                                     if model.update == "kernel" else "torch autograd (6-channel or > 32-float policies)",
+                           "forward": "tcgen05 kind::tf32 policy/value forward (csrc/ppo_tc.cu)" if model.tensor_core_forward
+                                      else "CUDA-core fp32 policy/value forward (csrc/ppo_kernels.cu)", "rollout": "CUDA graph"},
                 # the rollout is one CUDA-graph replay, which bypasses the C-side launch counter: count this repo's kernels
                 # from the launch sequence instead -- per rollout step: obs moments, policy forward, env step, return
                 # moments, reward finalise, bootstrap value forward, step counter; per rollout: last values, GAE; per

@@ -2,8 +2,8 @@
 """PPO training on the B200-native simulator with the reference's TRAIN_CONFIG keys.
 
 Counterpart of /root/reference/train/train_Fixedwing_Waypoints_v3.py (--task waypoints) and
-train_Fixedwing_Waypoints_ObjLock.py (--task objlock) / train_lowlevel_cmd.py (--task lowlevel): same hyper-parameter
-dictionary, same flow
+train_Fixedwing_Waypoints_ObjLock.py (--task objlock) / train_lowlevel_cmd.py (--task lowlevel) / train_objlock.py
+(--task duck, the duck-only lock-and-strike env): same hyper-parameter dictionary, same flow
 (vectorised env -> observation/reward normalisation -> PPO("MlpPolicy", ...).learn -> save model + vecnorm),
 with SubprocVecEnv/VecNormalize/PPO replaced by their device-resident equivalents.
 
@@ -36,6 +36,11 @@ TRAIN_CONFIG = {
         "gamma": 0.99, "gae_lambda": 0.95, "clip_range": 0.2, "ent_coef": 0.0, "vf_coef": 0.5, "max_grad_norm": 0.5, "seed": 42,
         "model_dir": "models/lowlevel_ppo_b200", "preset": "lowlevel",
     },
+    "duck": {        # train_objlock.py:27-85 (FixedwingObjLockEnv + FlattenObjLockEnv: 56-float vision-history observation)
+        "total_timesteps": 1_000_000, "num_envs": 16, "learning_rate": 3e-4, "n_steps": 2048, "batch_size": 64, "n_epochs": 10,
+        "gamma": 0.99, "gae_lambda": 0.95, "clip_range": 0.2, "ent_coef": 0.001, "vf_coef": 0.5, "max_grad_norm": 0.5, "seed": 42,
+        "model_dir": "models/obj_lock_only_ppo_b200", "preset": "objlock_duck",
+    },
 }
 
 
@@ -63,8 +68,8 @@ def main():
     from pyflyt_drone_b200.ppo import PPO
     from pyflyt_drone_b200.vec_env import FixedwingVecEnv
 
-    if args.task == "lowlevel":
-        env = FixedwingVecEnv(cfg["num_envs"], preset="lowlevel", device=local_rank, seed=cfg["seed"],
+    if args.task in ("lowlevel", "duck"):       # the preset carries the whole env configuration of the script
+        env = FixedwingVecEnv(cfg["num_envs"], preset=cfg["preset"], device=local_rank, seed=cfg["seed"],
                               env_id0=rank * cfg["num_envs"])
     else:
         env = FixedwingVecEnv(cfg["num_envs"], preset=cfg["preset"], device=local_rank, seed=cfg["seed"],
