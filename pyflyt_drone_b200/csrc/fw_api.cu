@@ -499,6 +499,16 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
     // posted PCIe writes, complete when the kernel is); only the observations (95 % of the bytes) go through device
     // memory and the copy engine.
     const bool want_term = term_obs_host && D;
+    // A caller buffer that is itself page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) is read by the
+    // kernel in place, like the library's own staging buffer: no host-side copy at all.
+    const float* act_dev_view = nullptr;
+    if (act_host != h->h_act && (reinterpret_cast<uintptr_t>(act_host) & 15u) == 0) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, act_host) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr)
+            act_dev_view = static_cast<const float*>(pa.devicePointer);
+        else
+            (void)cudaGetLastError();
+    }
     const int chunks = h->n >= 16384 ? FW_HOST_CHUNKS : 1;
     const int per = (((h->n + chunks - 1) / chunks) + 63) / 64 * 64;
     for (int c = 0; c < chunks; ++c) {
@@ -507,10 +517,10 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
         const size_t n0 = (size_t)c0, cn = (size_t)(c1 - c0);
         cudaStream_t st = h->io_streams[c & 1];
         const size_t Aw = (size_t)h->dev.act_dim;
-        if (act_host != h->h_act) memcpy(h->h_act + n0 * Aw, act_host + n0 * Aw, cn * Aw * sizeof(float));
+        if (act_host != h->h_act && act_dev_view == nullptr) memcpy(h->h_act + n0 * Aw, act_host + n0 * Aw, cn * Aw * sizeof(float));
         FwDev pc = h->dev;
         pc.i_begin = c0; pc.i_end = c1;
-        CU(fwk_launch_step(pc, h->pl, h->h_act, D ? h->d_obs : nullptr, h->h_rew, h->h_flg, want_term ? h->d_term : nullptr,
+        CU(fwk_launch_step(pc, h->pl, act_dev_view ? act_dev_view : h->h_act, D ? h->d_obs : nullptr, h->h_rew, h->h_flg, want_term ? h->d_term : nullptr,
                            false, 1, st));
         h->launches++;
         if (obs_host && D) CU(cudaMemcpyAsync(h->h_obs + n0 * D, h->d_obs + n0 * D, cn * D * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -301,3 +301,31 @@ def test_standard_layout_kernels_match_the_generic_kernels():
         for k in keys:
             assert rel(s1[k], s0[k]).max() < 2e-5, (t, k, rel(s1[k], s0[k]).max())
     std.close(); gen.close()
+
+
+def test_page_locked_caller_actions_are_read_in_place():
+    """fw_step_host stages pageable action arrays chunk by chunk, but reads a page-locked caller buffer (torch
+    pin_memory, cudaHostAlloc) directly from the kernel: both routes must give bitwise identical steps."""
+    import torch
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    N = 20000                                             # above the chunking threshold of the host lane
+    a_env = FixedwingVecEnv(N, preset="waypoints_v3", seed=8)
+    b_env = FixedwingVecEnv(N, preset="waypoints_v3", seed=8)
+    a_env.reset(); b_env.reset()
+    rng = np.random.default_rng(0)
+    pinned = torch.empty((N, 4), dtype=torch.float32, pin_memory=True)
+    for _ in range(5):
+        a = rng.uniform(-1, 1, (N, 4)).astype(np.float32)
+        pinned.numpy()[:] = a
+        o1, r1, f1, _ = a_env.step_arrays(a)
+        o2, r2, f2, _ = b_env.step_arrays(pinned.numpy())
+        assert np.array_equal(o1, o2) and np.array_equal(r1, r2) and np.array_equal(f1, f2)
+    # an unaligned view of pinned memory falls back to the staging copy
+    wide = torch.empty((N * 4 + 1,), dtype=torch.float32, pin_memory=True)
+    off = wide.numpy()[1:].reshape(N, 4)
+    a = rng.uniform(-1, 1, (N, 4)).astype(np.float32)
+    off[:] = a
+    o1, r1, f1, _ = a_env.step_arrays(a)
+    o2, r2, f2, _ = b_env.step_arrays(off)
+    assert np.array_equal(o1, o2) and np.array_equal(r1, r2) and np.array_equal(f1, f2)
+    a_env.close(); b_env.close()
