@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -29,7 +30,7 @@ static int fail(int code, const char* fmt, ...) {
         if (_e != cudaSuccess) return fail(FW_ECUDA, "%s: %s", #call, cudaGetErrorString(_e)); \
     } while (0)
 
-#define FW_HOST_CHUNKS 4      // host lane: chunks per step (kernel of chunk c+1 overlaps the D2H copy of chunk c)
+#define FW_HOST_CHUNKS 2      // host lane: chunks per step, alternating between two streams (measured best of 1..16)
 
 struct FwSim {
     FwConfig cfg;
@@ -492,12 +493,10 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
     int rc = ensure_host_io(h);
     if (rc != FW_OK) return rc;
     const size_t N = (size_t)h->n, D = (size_t)h->obs_dim;
-    // The batch is cut into chunks, alternating between two streams: [step kernel -> D2H observations] of chunk c+1 runs
-    // while the copy engine drains chunk c, and caller-owned (pageable) actions are staged chunk by chunk under that GPU
-    // work.  The small per-env streams get no DMA operations of their own (each costs microseconds of fixed latency): the
-    // kernel reads the actions from and writes rewards and flags to the pinned host buffers directly (unified addressing;
-    // posted PCIe writes, complete when the kernel is); only the observations (95 % of the bytes) go through device
-    // memory and the copy engine.
+    // The batch is cut into chunks that alternate between two streams, so that the staging of caller-owned (pageable)
+    // actions for chunk c+1 runs under the kernel of chunk c.  No DMA operation is issued at all (each costs several
+    // microseconds of fixed latency, see the chunk sweep in DESIGN.md): the kernel reads the actions from and writes every
+    // output to pinned host memory directly (unified addressing; posted PCIe writes, complete when the kernel is).
     const bool want_term = term_obs_host && D;
     // A caller buffer that is itself page-locked (cudaHostAlloc / cudaHostRegister / torch pin_memory) is read by the
     // kernel in place, like the library's own staging buffer: no host-side copy at all.
@@ -509,7 +508,12 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
         else
             (void)cudaGetLastError();
     }
-    const int chunks = h->n >= 16384 ? FW_HOST_CHUNKS : 1;
+    static const int tuned_chunks = [] {               // FWSIM_HOST_CHUNKS=<n> overrides the default (tuning aid)
+        const char* e = getenv("FWSIM_HOST_CHUNKS");
+        const int v = e ? atoi(e) : 0;
+        return v >= 1 && v <= 64 ? v : FW_HOST_CHUNKS;
+    }();
+    const int chunks = h->n >= 16384 ? tuned_chunks : 1;
     const int per = (((h->n + chunks - 1) / chunks) + 63) / 64 * 64;
     for (int c = 0; c < chunks; ++c) {
         const int c0 = c * per, c1 = (c + 1) * per < h->n ? (c + 1) * per : h->n;
@@ -520,11 +524,20 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
         if (act_host != h->h_act && act_dev_view == nullptr) memcpy(h->h_act + n0 * Aw, act_host + n0 * Aw, cn * Aw * sizeof(float));
         FwDev pc = h->dev;
         pc.i_begin = c0; pc.i_end = c1;
-        CU(fwk_launch_step(pc, h->pl, act_dev_view ? act_dev_view : h->h_act, D ? h->d_obs : nullptr, h->h_rew, h->h_flg, want_term ? h->d_term : nullptr,
-                           false, 1, st));
+        // Observations, rewards, flags and terminal observations are written by the kernel straight into the pinned
+        // host buffers (unified addressing; the observation rows leave each CTA as one bulk store, so the PCIe writes
+        // are 7 KB bursts).  Measured at 65,536 envs: 188 us per step against 200-212 us with a device buffer and a
+        // D2H copy per chunk, and the terminal observations (rows of finished episodes only) cost nothing instead of
+        // a second 7.3 MB copy.  FWSIM_HOST_ZEROCOPY_OBS=0 restores the copy-engine route.
+        static const bool zc_obs = [] { const char* e = getenv("FWSIM_HOST_ZEROCOPY_OBS"); return !(e && atoi(e) == 0); }();
+        float* obs_dst = D ? (zc_obs ? h->h_obs : h->d_obs) : nullptr;
+        float* term_dst = want_term ? (zc_obs ? h->h_term : h->d_term) : nullptr;
+        CU(fwk_launch_step(pc, h->pl, act_dev_view ? act_dev_view : h->h_act, obs_dst, h->h_rew, h->h_flg, term_dst, false, 1, st));
         h->launches++;
-        if (obs_host && D) CU(cudaMemcpyAsync(h->h_obs + n0 * D, h->d_obs + n0 * D, cn * D * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (want_term) CU(cudaMemcpyAsync(h->h_term + n0 * D, h->d_term + n0 * D, cn * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (!zc_obs) {
+            if (obs_host && D) CU(cudaMemcpyAsync(h->h_obs + n0 * D, h->d_obs + n0 * D, cn * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+            if (want_term) CU(cudaMemcpyAsync(h->h_term + n0 * D, h->d_term + n0 * D, cn * D * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
     }
     h->fresh = false;
     CU(cudaStreamSynchronize(h->io_streams[0]));
