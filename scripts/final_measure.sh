@@ -11,10 +11,10 @@ for w in waypoints_v3 waypoint_objlock lowlevel objlock_duck; do
 done
 python bench.py --steps 1000 --warmup 50 --steps-per-launch 8 --no-cpu-baseline > $O/${T}_fused8.json 2>> $O/${T}_bench.err
 python bench.py --steps 300 --warmup 20 --envs 1048576 --no-cpu-baseline > $O/${T}_1m.json 2>> $O/${T}_bench.err
-python bench.py --workload ppo --steps 3 --warmup 1 > $O/${T}_ppo4096.json 2>> $O/${T}_bench.err
-python bench.py --workload ppo --steps 3 --warmup 1 --ppo-envs 65536 --ppo-n-steps 64 > $O/${T}_ppo65536.json 2>> $O/${T}_bench.err
-python bench.py --workload ppo --steps 3 --warmup 1 --ppo-envs 65536 --ppo-n-steps 64 --ppo-preset waypoint_objlock > $O/${T}_ppo_ol.json 2>> $O/${T}_bench.err
-python bench.py --workload ppo --steps 3 --warmup 1 --ppo-envs 4096 --ppo-n-steps 128 --ppo-preset objlock_duck > $O/${T}_ppo_duck.json 2>> $O/${T}_bench.err
+python bench.py --workload ppo --steps 5 --warmup 2 > $O/${T}_ppo4096.json 2>> $O/${T}_bench.err
+python bench.py --workload ppo --steps 5 --warmup 2 --ppo-envs 65536 --ppo-n-steps 64 > $O/${T}_ppo65536.json 2>> $O/${T}_bench.err
+python bench.py --workload ppo --steps 5 --warmup 2 --ppo-envs 65536 --ppo-n-steps 64 --ppo-preset waypoint_objlock > $O/${T}_ppo_ol.json 2>> $O/${T}_bench.err
+python bench.py --workload ppo --steps 5 --warmup 2 --ppo-envs 4096 --ppo-n-steps 128 --ppo-preset objlock_duck > $O/${T}_ppo_duck.json 2>> $O/${T}_bench.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${T}_launches_default_bench.csv \
     python bench.py --steps 200 --warmup 20 --no-cpu-baseline > $O/${T}_ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:fw_step_kernel --launch-skip 60 --launch-count 1 -f \
