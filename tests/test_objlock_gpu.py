@@ -163,3 +163,61 @@ def test_objlock_standard_layout_kernels_match_the_generic_kernels(preset):
         assert (np.abs(r1 - r0)[same] > 1e-3 * np.maximum(1.0, np.abs(r0[same]))).mean() < 0.002
     assert bad_flags <= 2
     std.close(); gen.close()
+
+
+@pytest.mark.parametrize("preset", ["waypoint_objlock", "objlock_duck"])
+def test_camera_tasks_full_size_invariants_65536(preset):
+    """BASELINE config 4's per-GPU size (and the duck-only head at the same size): properties that need no oracle."""
+    import torch
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    cfg = fw.make_config(preset) if preset == "waypoint_objlock" else fw.make_config(preset, num_obstacles=12)
+    N = 65536
+    env = FixedwingVecEnv(N, config=cfg, seed=0)
+    obs = env.reset_tensor()
+    strikes = 0
+    for s in range(6):
+        rew, flags = env.step_random(25, with_outputs=True)
+    a = torch.zeros((N, 4), device="cuda")
+    obs, rew, flags = env.step_tensor(a)
+    torch.cuda.synchronize()
+    o = obs.cpu().numpy()
+    st = env.get_state()
+    assert np.isfinite(o).all() and np.isfinite(rew.cpu().numpy()).all()
+    assert np.abs(np.linalg.norm(st["quat"], axis=1) - 1).max() < 1e-5
+    for k in ("pos", "vel", "omega", "act", "duck", "ol_f"):
+        assert np.isfinite(st[k]).all(), k
+    assert np.abs(st["vel"]).max() <= 100.0 and np.abs(st["omega"]).max() <= 100.0          # Bullet's clamp
+    assert np.linalg.norm(st["pos"], axis=1).max() <= cfg.dome + 100 * 8 / 240 + 1e-3       # dome + one step
+    # obstacles: counts, heights and the exclusion zones of the two spawn routines
+    n_ob = st["ol_i"][:, 8]
+    assert n_ob.max() <= cfg.num_obstacles and n_ob.min() >= 0
+    k = np.arange(32)[None, :] < n_ob[:, None]
+    ob = st["obst"]
+    assert (ob[..., 2][k] >= cfg.obst_h_lo - 1e-4).all() and (ob[..., 2][k] <= cfg.obst_h_hi + 1e-4).all()
+    assert (ob[..., 0][k] ** 2 + ob[..., 1][k] ** 2 >= 100.0 - 1e-2).all()
+    assert (np.abs(ob[..., :2][k]) <= cfg.dome / 2 + 1e-3).all()
+    if preset == "objlock_duck":
+        d2 = (ob[..., 0] - st["duck"][:, None, 0]) ** 2 + (ob[..., 1] - st["duck"][:, None, 1]) ** 2
+        assert (d2[k] >= 100.0 - 1e-2).all()
+        assert (np.abs(st["duck"][:, :2]) <= cfg.dome / 2 + 1e-3).all()
+    assert np.allclose(st["duck"][:, 2], 0.05)
+    # vision state: image-plane features in range, counters within their caps
+    f, i = st["ol_f"], st["ol_i"]
+    assert (f[:, 0] >= 0).all() and (f[:, 0] <= 1).all() and (f[:, 1] >= 0).all() and (f[:, 1] <= 1).all()
+    assert (f[:, 2] >= 0).all() and (f[:, 2] <= 1).all() and (f[:, 3] >= 0).all() and (f[:, 3] <= cfg.cam_far).all()
+    assert (f[:, 8:11] >= 0).all() and (f[:, 8:11] <= cfg.cam_far + 1e-3).all()              # band depths in metres, 0 = none
+    assert (i[:, 7] >= 0).all() and (i[:, 7] <= 60).all()                                   # steps_since_seen
+    assert (i[:, 6] >= 0).all() and (i[:, 6] <= max(cfg.lock_hold_steps, i[:, 6].max() if preset == "waypoint_objlock" else 0)).all()
+    if preset == "objlock_duck":
+        assert (i[:, 6] <= cfg.lock_hold_steps).all() and (i[:, 5] >= 1).all() and (i[:, 5] <= cfg.vision_hist_len).all()
+        # the observation's newest history row is the vision state the env holds
+        v0 = o[:, 25:34]
+        assert np.array_equal(v0[:, 1:5], f[:, 0:4]) and np.allclose(v0[:, 5], i[:, 7] / 60.0)
+        assert np.array_equal((v0[:, 0] > 0.5), (i[:, 3] == 1) & (i[:, 4] == 1) & (i[:, 7] == 0))
+        assert np.allclose(np.linalg.norm(o[:, 22:25], axis=1), np.linalg.norm(st["duck"] - st["pos"], axis=1), rtol=1e-4, atol=1e-3)
+    stats = env.episode_stats()
+    assert stats["episodes"] == st["episode"].astype(np.int64).sum()
+    assert stats["collisions"] + stats["out_of_bounds"] + stats["strikes"] >= stats["episodes"] * 0.98
+    print(f"\n[{preset} 65,536] episodes {stats['episodes']:.0f}, collisions {stats['collisions']:.0f}, out of bounds "
+          f"{stats['out_of_bounds']:.0f}, frames with the duck visible {int(i[:, 4].sum())}")
+    env.close()
