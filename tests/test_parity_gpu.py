@@ -197,16 +197,20 @@ def test_tensor_lane_equals_host_lane(fo):
     a_env.close(); b_env.close()
 
 
-def test_sharding_is_split_invariant(fo):
-    """Global env ids key the RNG: two half batches reproduce one full batch bit for bit (multi-GPU contract)."""
+@pytest.mark.parametrize("preset", ["waypoints_v3", "waypoint_objlock", "lowlevel", "objlock_duck"])
+def test_sharding_is_split_invariant(fo, preset):
+    """Global env ids key the RNG: two half batches reproduce one full batch bit for bit (multi-GPU contract) -- targets,
+    wind, obstacles, duck positions, camera frames and vision history included."""
     from pyflyt_drone_b200.vec_env import FixedwingVecEnv
-    cfg = fw.waypoints_v3()
+    cfg = fw.make_config(preset) if preset != "objlock_duck" else fw.make_config(preset, num_obstacles=10)
     full = FixedwingVecEnv(128, config=cfg, seed=2)
     lo, hi = FixedwingVecEnv(64, config=cfg, seed=2, env_id0=0), FixedwingVecEnv(64, config=cfg, seed=2, env_id0=64)
     assert np.array_equal(full.reset(), np.concatenate([lo.reset(), hi.reset()]))
     full.step_random(40); lo.step_random(40); hi.step_random(40)
     sf, sl, sh = full.get_state(), lo.get_state(), hi.get_state()
-    for k in ("pos", "quat", "episode", "targets"):
+    keys = ["pos", "quat", "episode", "targets", "wind", "act"]
+    keys += [k for k in ("duck", "obst", "ol_f", "ol_i", "vis_hist") if k in sf]
+    for k in keys:
         assert np.array_equal(sf[k], np.concatenate([sl[k], sh[k]])), k
     for e in (full, lo, hi):
         e.close()
