@@ -169,6 +169,12 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
     const float Rd = p.duck_radius;
     const int w = p.cam_res, x1 = w / 3, x2 = 2 * w / 3, ymid = w / 2;
     const float vrow = 2.0f * ((float)ymid + 0.5f) / (float)w - 1.0f;
+    // normalised coordinate of pixel column c: xn = 2 (c + 0.5) / w - 1 = c * xs + x0
+    const float xs = 2.0f / (float)w, x0 = 0.5f * xs - 1.0f;
+    // the depth row is all-INF whenever a frame starts: cleared here once per call, and every frame's band pass puts INF
+    // back into the entries it has read
+    for (int col = lane; col < w; col += 32) depth_row[col] = INF;
+    __syncwarp();
     if (need) {
         Mat3 R = fw_quat_mat(e.qx, e.qy, e.qz, e.qw);
         const float* m = R.m;
@@ -215,9 +221,6 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
         const float bdx = __shfl_sync(FULL, ddx, s), bdy = __shfl_sync(FULL, ddy, s), bdz = __shfl_sync(FULL, ddz, s);
         const float bdist = __shfl_sync(FULL, dist, s);
         const int bcand = __shfl_sync(FULL, cand, s), bn = __shfl_sync(FULL, o.n_obst, s);
-        // phase 0 (lanes = columns): clear the depth row (the ground plane is intersected in phase B)
-        for (int col = lane; col < w; col += 32) depth_row[col] = INF;
-        __syncwarp();
         // phase A: lane k owns cylinder k for the set-up (column interval, duck-occlusion ray); the (cylinder,
         // column) pairs to rasterise are then dealt out evenly over the 32 lanes through a warp prefix sum, so a
         // wide nearby cylinder does not serialise the warp behind one lane
@@ -256,7 +259,7 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
             const float kx = __shfl_sync(FULL, ox, kk), ky = __shfl_sync(FULL, oy, kk), kh = __shfl_sync(FULL, oh, kk);
             if (pidx < total) {
                 const int col = klo + (pidx - kst);
-                float xn = 2.0f * ((float)col + 0.5f) / (float)w - 1.0f;
+                const float xn = fmaf((float)col, xs, x0);
                 float t = ol_ray_cylinder(bcx, bcy, bcz, bAx + xn * brx, bAy + xn * bry, bAz + xn * brz, kx, ky, kh, p.obst_radius);
                 if (t < INF) atomicMin(reinterpret_cast<int*>(&depth_row[col]), __float_as_int(t));
             }
@@ -267,10 +270,11 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
         int dlo, dhi;
         ol_col_interval(bAx, bAy, brx, bry, AA, AB, BB, bsx - bcx, bsy - bcy, Rd, w, dlo, dhi);
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
-        int c0 = 0, c1 = 0, c2 = 0;
+        int cnt3 = 0;                                    // the three band counts, 10 bits each (cam_res <= 1024)
         for (int col = lane; col < w; col += 32) {
-            const float xn = 2.0f * ((float)col + 0.5f) / (float)w - 1.0f;
+            const float xn = fmaf((float)col, xs, x0);
             float best = depth_row[col];
+            depth_row[col] = INF;                        // ready for the next frame
             {
                 const float dz = bAz + xn * brz;
                 if (dz < -1e-12f) { const float t = -bcz / dz; if (t > 0.0f) best = fminf(best, t); }
@@ -280,15 +284,19 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
                 if (td < best) continue;
             }
             float iv = (best < INF) ? ol_inv_depth(p, best) : 1.0f / p.cam_far;
-            if (col < x1) { sum0 += iv; c0++; } else if (col < x2) { sum1 += iv; c1++; } else { sum2 += iv; c2++; }
+            if (col < x1) { sum0 += iv; cnt3 += 1; } else if (col < x2) { sum1 += iv; cnt3 += 1 << 10; } else { sum2 += iv; cnt3 += 1 << 20; }
         }
         // NOTE: fp32 addition is not associative; the oracle sums columns left to right in fp64, so the order
         // here only moves the last bits of a quantity that is compared with a 2e-4 relative tolerance
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
             sum0 += __shfl_xor_sync(FULL, sum0, off); sum1 += __shfl_xor_sync(FULL, sum1, off); sum2 += __shfl_xor_sync(FULL, sum2, off);
-            c0 += __shfl_xor_sync(FULL, c0, off); c1 += __shfl_xor_sync(FULL, c1, off); c2 += __shfl_xor_sync(FULL, c2, off);
+            cnt3 += __shfl_xor_sync(FULL, cnt3, off);
         }
+        // mean inverse depth -> metres for the three bands at once: lane b evaluates band b (every lane holds all sums)
+        const float bsum = lane == 0 ? sum0 : (lane == 1 ? sum1 : sum2);
+        const float bmet = ol_band_metres(p, bsum, (cnt3 >> (10 * min(lane, 2))) & 1023);
+        const float met_l = __shfl_sync(FULL, bmet, 0), met_c = __shfl_sync(FULL, bmet, 1), met_r = __shfl_sync(FULL, bmet, 2);
         if (lane == s) {
             const int vis = (cand && hidden == 0u) ? 1 : 0;
             o.f_visible = vis;
@@ -300,9 +308,7 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
                 o.f_area = fminf(a, 1.0f);
                 o.f_depth = zc - Rd;
             }
-            o.f_dl = ol_band_metres(p, sum0, c0);
-            o.f_dc = ol_band_metres(p, sum1, c1);
-            o.f_dr = ol_band_metres(p, sum2, c2);
+            o.f_dl = met_l; o.f_dc = met_c; o.f_dr = met_r;
             o.cam_valid = 1;
         }
         __syncwarp();
