@@ -229,6 +229,7 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
     d.wind_mode = c.wind_mode; d.wind_randomize = c.wind_randomize; d.wind_rand_phase = c.wind_rand_phase;
     d.wind_start_substep = c.wind_start_substep;
     d.gust_omega = (float)(2.0 * PI * c.gust_freq); d.gust_phase = (float)c.gust_phase;
+    d.gust_cyc = (float)(c.gust_freq * c.dt);
     d.num_obstacles = c.num_obstacles; d.cam_interval = c.cam_interval_substeps; d.lock_hold = c.lock_hold_steps;
     d.switch_min_seen = c.switch_min_seen; d.cam_res = c.cam_res;
     d.obst_radius = (float)c.obst_radius; d.obst_h_lo = (float)c.obst_h_lo; d.obst_h_hi = (float)c.obst_h_hi;

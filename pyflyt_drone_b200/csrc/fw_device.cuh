@@ -110,6 +110,7 @@ struct FwDev {
     float wind_base[3], wind_base_lo[3], wind_base_hi[3];
     float gust_amp[3], gust_amp_lo[3], gust_amp_hi[3];
     float gust_omega, gust_phase;   // 2*pi*f
+    float gust_cyc;                 // f * dt: gust cycles per physics substep
     // ObjLock task (fixedwing_waypoint_objlock_env.py:42-168)
     int num_obstacles, cam_interval, lock_hold, switch_min_seen, cam_res;
     float obst_radius, obst_h_lo, obst_h_hi, obst_safe, obst_scale, obst_max_pen;
@@ -510,7 +511,12 @@ __device__ __forceinline__ void fw_wind(const FwDev& p, int ps, const float4& w0
     int stamp = ps - 1;
     if (stamp < 0 || stamp < p.wind_start_substep) return;
     if (p.wind_mode == 1) { x = w0.x; y = w0.y; z = w0.z; return; }
-    float s = sinf(p.gust_omega * ((float)stamp * p.dt) + w0.w);
+    // sin(2 pi f t + phi) with the range reduction done on the cycle count: stamp * (f dt) cycles, minus whole turns,
+    // leaves an argument in [-pi, pi] for MUFU.SIN (libdevice sinf spends ~40 instructions per substep on arguments of
+    // up to 150 rad; the fp32 rounding of the argument itself, ~1e-5 rad at t = 120 s, is the same either way)
+    float turns = fmaf(w0.w, 0.15915494309189535f, (float)stamp * p.gust_cyc);
+    turns -= rintf(turns);
+    float s = __sinf(6.283185307179586f * turns);
     x = w0.x + w1.x * s; y = w0.y + w1.y * s; z = w0.z + w1.z * s;
 }
 
