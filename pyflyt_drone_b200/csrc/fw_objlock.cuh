@@ -133,8 +133,10 @@ __device__ __forceinline__ void ol_col_interval(float Ax, float Ay, float Bx, fl
         const float sq = sqrtf(disc), inv = 1.0f / qa;
         const float x0 = (-qb - sq) * inv, x1 = (-qb + sq) * inv;
         const float c0 = (x0 + 1.0f) * 0.5f * (float)w - 0.5f, c1 = (x1 + 1.0f) * 0.5f * (float)w - 0.5f;
-        lo = max(0, (int)floorf(fmaxf(c0, -4.0f)) - 1);
-        hi = min(w - 1, (int)ceilf(fminf(c1, (float)w + 4.0f)) + 1);
+        // column j can be hit only if c0 <= j <= c1; floor / ceil leave up to one column of slack on each side on top of the
+        // 1 % inflation of the radius, far more than the ~1e-4 columns of fp32 error in c0 and c1
+        lo = max(0, (int)floorf(fmaxf(c0, -4.0f)));
+        hi = min(w - 1, (int)ceilf(fminf(c1, (float)w + 4.0f)));
     }
     // The quadratic bounds LINES through the camera, so an axis behind the camera passes it as well.  A ray t > 0 along
     // d = A + xn B reaches the disk only if P.d + rad |d| > 0; P.d is linear and |d|^2 convex in xn, so both are largest
