@@ -6,11 +6,15 @@ trajectory divergence over a 1 s horizon (30 agent steps = 240 substeps) reporte
 norm-wise per observation group with a floor of 1.0 on the reference norm, i.e.
 |x_gpu - x_ref|_inf <= 1e-4 * max(|x_ref|_inf, 1).
 """
+import os
+
 import numpy as np
 import pytest
 
 import pyflyt_drone_b200 as fw
 from pyflyt_drone_b200.config import FLAG_TERM, FLAG_TRUNC
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -335,3 +339,37 @@ def test_page_locked_caller_actions_are_read_in_place():
     o2, r2, f2, _ = b_env.step_arrays(off)
     assert np.array_equal(o1, o2) and np.array_equal(r1, r2) and np.array_equal(f1, f2)
     a_env.close(); b_env.close()
+
+
+def test_host_lane_routes_agree(tmp_path):
+    """The default host lane lets the kernel write observations straight into pinned host memory; FWSIM_HOST_ZEROCOPY_OBS=0
+    (read once per process) restores the device-buffer + copy-engine route, and FWSIM_HOST_CHUNKS changes the chunking.
+    All of them must return bitwise identical steps, terminal observations included."""
+    import subprocess
+    import sys
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    script = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {str(ROOT)!r})\n"
+        "from pyflyt_drone_b200.vec_env import FixedwingVecEnv\n"
+        "env = FixedwingVecEnv(20000, preset='waypoints_v3', seed=8)\n"
+        "env.reset(); rng = np.random.default_rng(0); out = {}\n"
+        "for k in range(30):\n"
+        "    a = rng.uniform(-1, 1, (20000, 4)).astype(np.float32); a[:, 1] = -1.0\n"
+        "    o, r, f, t = env.step_arrays(a)\n"
+        "    out[f'o{k}'], out[f'r{k}'], out[f'f{k}'] = o.copy(), r.copy(), f.copy()\n"
+        "    done = (f & 3) != 0\n"
+        "    out[f't{k}'] = t[done].copy()\n"
+        "np.savez(sys.argv[1], **out)\n")
+    results = []
+    for name, extra in (("default", {}), ("dma", {"FWSIM_HOST_ZEROCOPY_OBS": "0"}),
+                        ("dma4", {"FWSIM_HOST_ZEROCOPY_OBS": "0", "FWSIM_HOST_CHUNKS": "4"}), ("one", {"FWSIM_HOST_CHUNKS": "1"})):
+        path = tmp_path / f"{name}.npz"
+        env = dict(os.environ, **extra)
+        subprocess.run([sys.executable, "-c", script, str(path)], check=True, env=env, timeout=300)
+        results.append(np.load(path))
+    ref = results[0]
+    assert sum(len(ref[f"t{k}"]) for k in range(30)) > 0, "the scripted dive must end some episodes"
+    for other in results[1:]:
+        for key in ref.files:
+            assert np.array_equal(ref[key], other[key]), key
