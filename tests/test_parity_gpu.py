@@ -373,3 +373,38 @@ def test_host_lane_routes_agree(tmp_path):
     for other in results[1:]:
         for key in ref.files:
             assert np.array_equal(ref[key], other[key]), key
+
+
+def test_config0_single_env_10k_random_action_steps(fo):
+    """BASELINE configs[0] / SURVEY 8(d) config 1: ONE Fixedwing-Waypoints env (FlattenWaypointEnv, euler, 8 targets, reach
+    4 m, sparse reward, motor noise on), 10,100 steps with actions np.random.default_rng(0).uniform(-1, 1, (10100, 4)),
+    re-reset on done.  The fp64 oracle free-runs that trajectory; before every step its state is injected into the
+    one-env CUDA batch, both step with the same action, and observation / reward / flags (and the terminal observation and
+    the post-reset observation of finished episodes) are compared at the single-step tolerance."""
+    cfg = fw.waypoints_v3()
+    env, orc = make_pair(fo, 1, cfg, seed=0)
+    og, oc = env.reset(), orc.reset()
+    assert max(group_err(og, oc).values()) < RTOL
+    acts = np.random.default_rng(0).uniform(-1, 1, (10100, 4))
+    rows, episodes, worst_rew = [], 0, 0.0
+    for t in range(10100):
+        env.set_state(orc.get_state())
+        a = acts[t:t + 1]
+        og, rg, fg, tg = env.step_arrays(a.astype(np.float32))
+        oc, rc, fc, tc = orc.step(a)
+        assert int(fg[0]) == int(fc[0]), (t, int(fg[0]), int(fc[0]))
+        worst_rew = max(worst_rew, float(abs(rg[0] - rc[0]) / max(1.0, abs(rc[0]))))
+        e = max(group_err(angle_safe(og.astype(np.float64), oc), oc).values())
+        if fc[0] & (FLAG_TERM | FLAG_TRUNC):
+            episodes += 1
+            e = max(e, max(group_err(angle_safe(tg.astype(np.float64), tc), tc).values()))
+        rows.append(e)
+    rows = np.array(rows)
+    flips = int((rows >= RTOL).sum())
+    print(f"\n[configs[0]] 10,100 single-env steps, {episodes} episodes: median step error {np.median(rows):.1e}, "
+          f"99.9th percentile {np.quantile(rows, 0.999):.1e}, steps past {RTOL:g}: {flips}, worst {rows.max():.1e}; "
+          f"worst reward error {worst_rew:.1e}")
+    assert episodes >= 20
+    assert worst_rew <= 1e-4
+    assert flips <= 5 and rows.max() < 5e-3          # stall-boundary branch flips (see tests/test_duck_gpu.py), if any
+    env.close()
