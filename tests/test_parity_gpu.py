@@ -408,3 +408,25 @@ def test_config0_single_env_10k_random_action_steps(fo):
     assert worst_rew <= 1e-4
     assert flips <= 5 and rows.max() < 5e-3          # stall-boundary branch flips (see tests/test_duck_gpu.py), if any
     env.close()
+
+
+def test_sweep_end_points_invariants():
+    """BASELINE configs[4] sweeps 1K..1M envs per GPU: oracle-free properties at both ends (1,024 and 1,048,576 envs),
+    and the two sizes agree on the envs they share (the RNG is keyed by the global env id, not by the batch size)."""
+    import torch
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    small = FixedwingVecEnv(1024, preset="physics_only", seed=3)
+    big = FixedwingVecEnv(1 << 20, preset="physics_only", seed=3)
+    small.step_random(60); big.step_random(60)
+    torch.cuda.synchronize()
+    ss, sb = small.get_state(), big.get_state()
+    for k in ("pos", "quat", "vel", "omega", "act", "episode", "physics_steps"):
+        assert np.array_equal(ss[k], sb[k][:1024]), k
+    assert np.abs(np.linalg.norm(sb["quat"], axis=1) - 1).max() < 1e-5
+    for k in ("pos", "vel", "omega", "act"):
+        assert np.isfinite(sb[k]).all(), k
+    assert np.abs(sb["vel"]).max() <= 100.0 and np.abs(sb["omega"]).max() <= 100.0
+    assert np.linalg.norm(sb["pos"], axis=1).max() <= 100.0 + 100 * 8 / 240 + 1e-3
+    st = big.episode_stats()
+    assert st["episodes"] == sb["episode"].astype(np.int64).sum() and st["episodes"] > 0
+    small.close(); big.close()
