@@ -271,6 +271,45 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
         // phase B (lanes = columns): duck pixels drop out, the rest feed the three harmonic band means
         int dlo, dhi;
         ol_col_interval(bAx, bAy, brx, bry, AA, AB, BB, bsx - bcx, bsy - bcy, Rd, w, dlo, dhi);
+        // Frames with nothing but the ground plane in the middle row (no cylinder candidate, the duck sphere clear of the
+        // row's ray plane) need no per-column pass: the inverse depth of the ground along the row is LINEAR in the column
+        // index, iv_j = clamp(alpha + beta j, 1/far, 1/near) -- a ray that misses the ground has alpha + beta j <= 0 and
+        // clamps to 1/far like a miss -- so each band sum is two clamped runs plus one arithmetic series.  Lanes 0..2
+        // evaluate the three bands.  (The duck-only training configuration has no obstacles: most of its frames.)
+        bool fast = total == 0;
+        if (fast && dlo <= dhi) {
+            // distance of the sphere centre from the plane of the row's rays (normal (0, 1, vrow) in camera coordinates)
+            const float byc = __shfl_sync(FULL, yc, s), bzc = __shfl_sync(FULL, zc, s);
+            fast = fabsf(fmaf(vrow, bzc, byc)) > (Rd * 1.001f + 1e-4f) * sqrtf(fmaf(vrow, vrow, 1.0f));
+        }
+        float bsum;
+        int bcnt;
+        if (fast) {
+            const float inv_far = 1.0f / p.cam_far, inv_near = 1.0f / p.cam_near;
+            const int j0 = lane == 0 ? 0 : (lane == 1 ? x1 : x2), j1 = lane == 0 ? x1 : (lane == 1 ? x2 : w);
+            float alpha = 0.0f, beta = 0.0f;                     // camera at or below the ground: every ray misses
+            if (bcz > 0.0f) {
+                const float icz = 1.0f / bcz;
+                alpha = -fmaf(x0, brz, bAz) * icz; beta = -(xs * brz) * icz;
+            }
+            float total_iv;
+            const float n = (float)(j1 - j0);
+            if (fabsf(beta) * (float)w < 1e-12f) {
+                total_iv = n * fminf(fmaxf(alpha, inv_far), inv_near);
+            } else {
+                const float ib = 1.0f / beta;
+                const float ja = (inv_far - alpha) * ib, jb = (inv_near - alpha) * ib;      // where the two clamps engage
+                const float jA = fminf(fmaxf(fminf(ja, jb), -1.0f), (float)w + 1.0f);
+                const float jB = fminf(fmaxf(fmaxf(ja, jb), -1.0f), (float)w + 1.0f);
+                const int cA = min(max((int)ceilf(jA), j0), j1);                            // below: [j0, cA)
+                const int cB = min(max((int)floorf(jB) + 1, cA), j1);                       // linear: [cA, cB), above: [cB, j1)
+                const float below = beta > 0.0f ? inv_far : inv_near, above = beta > 0.0f ? inv_near : inv_far;
+                const float nm = (float)(cB - cA);
+                total_iv = below * (float)(cA - j0) + above * (float)(j1 - cB) +
+                           fmaf(beta, 0.5f * (float)(cA + cB - 1) * nm, alpha * nm);
+            }
+            bsum = total_iv; bcnt = j1 - j0;
+        } else {
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
         int cnt3 = 0;                                    // the three band counts, 10 bits each (cam_res <= 1024)
         for (int col = lane; col < w; col += 32) {
@@ -295,9 +334,12 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
             sum0 += __shfl_xor_sync(FULL, sum0, off); sum1 += __shfl_xor_sync(FULL, sum1, off); sum2 += __shfl_xor_sync(FULL, sum2, off);
             cnt3 += __shfl_xor_sync(FULL, cnt3, off);
         }
-        // mean inverse depth -> metres for the three bands at once: lane b evaluates band b (every lane holds all sums)
-        const float bsum = lane == 0 ? sum0 : (lane == 1 ? sum1 : sum2);
-        const float bmet = ol_band_metres(p, bsum, (cnt3 >> (10 * min(lane, 2))) & 1023);
+        // every lane holds all sums: lane b keeps band b
+        bsum = lane == 0 ? sum0 : (lane == 1 ? sum1 : sum2);
+        bcnt = (cnt3 >> (10 * min(lane, 2))) & 1023;
+        }
+        // mean inverse depth -> metres for the three bands at once (lane b evaluates band b)
+        const float bmet = ol_band_metres(p, bsum, bcnt);
         const float met_l = __shfl_sync(FULL, bmet, 0), met_c = __shfl_sync(FULL, bmet, 1), met_r = __shfl_sync(FULL, bmet, 2);
         if (lane == s) {
             const int vis = (cand && hidden == 0u) ? 1 : 0;
