@@ -310,33 +310,35 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
             }
             bsum = total_iv; bcnt = j1 - j0;
         } else {
-        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
-        int cnt3 = 0;                                    // the three band counts, 10 bits each (cam_res <= 1024)
-        for (int col = lane; col < w; col += 32) {
-            const float xn = fmaf((float)col, xs, x0);
-            float best = depth_row[col];
-            depth_row[col] = INF;                        // ready for the next frame
-            {
-                const float dz = bAz + xn * brz;
-                if (dz < -1e-12f) { const float t = -bcz / dz; if (t > 0.0f) best = fminf(best, t); }
+            float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
+            int cnt3 = 0;                                    // the three band counts, 10 bits each (cam_res <= 1024)
+            for (int col = lane; col < w; col += 32) {
+                const float xn = fmaf((float)col, xs, x0);
+                float best = depth_row[col];
+                depth_row[col] = INF;                        // ready for the next frame
+                {
+                    const float dz = bAz + xn * brz;
+                    if (dz < -1e-12f) { const float t = -bcz / dz; if (t > 0.0f) best = fminf(best, t); }
+                }
+                if (col >= dlo && col <= dhi) {
+                    float td = ol_ray_sphere(bcx, bcy, bcz, bAx + xn * brx, bAy + xn * bry, bAz + xn * brz, bsx, bsy, bsz, Rd);
+                    if (td < best) continue;
+                }
+                float iv = (best < INF) ? ol_inv_depth(p, best) : 1.0f / p.cam_far;
+                if (col < x1) { sum0 += iv; cnt3 += 1; }
+                else if (col < x2) { sum1 += iv; cnt3 += 1 << 10; }
+                else { sum2 += iv; cnt3 += 1 << 20; }
             }
-            if (col >= dlo && col <= dhi) {
-                float td = ol_ray_sphere(bcx, bcy, bcz, bAx + xn * brx, bAy + xn * bry, bAz + xn * brz, bsx, bsy, bsz, Rd);
-                if (td < best) continue;
-            }
-            float iv = (best < INF) ? ol_inv_depth(p, best) : 1.0f / p.cam_far;
-            if (col < x1) { sum0 += iv; cnt3 += 1; } else if (col < x2) { sum1 += iv; cnt3 += 1 << 10; } else { sum2 += iv; cnt3 += 1 << 20; }
-        }
-        // NOTE: fp32 addition is not associative; the oracle sums columns left to right in fp64, so the order
-        // here only moves the last bits of a quantity that is compared with a 2e-4 relative tolerance
+            // NOTE: fp32 addition is not associative; the oracle sums columns left to right in fp64, so the order
+            // here only moves the last bits of a quantity that is compared with a 2e-4 relative tolerance
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            sum0 += __shfl_xor_sync(FULL, sum0, off); sum1 += __shfl_xor_sync(FULL, sum1, off); sum2 += __shfl_xor_sync(FULL, sum2, off);
-            cnt3 += __shfl_xor_sync(FULL, cnt3, off);
-        }
-        // every lane holds all sums: lane b keeps band b
-        bsum = lane == 0 ? sum0 : (lane == 1 ? sum1 : sum2);
-        bcnt = (cnt3 >> (10 * min(lane, 2))) & 1023;
+            for (int off = 16; off > 0; off >>= 1) {
+                sum0 += __shfl_xor_sync(FULL, sum0, off); sum1 += __shfl_xor_sync(FULL, sum1, off);
+                sum2 += __shfl_xor_sync(FULL, sum2, off); cnt3 += __shfl_xor_sync(FULL, cnt3, off);
+            }
+            // every lane holds all sums: lane b keeps band b
+            bsum = lane == 0 ? sum0 : (lane == 1 ? sum1 : sum2);
+            bcnt = (cnt3 >> (10 * min(lane, 2))) & 1023;
         }
         // mean inverse depth -> metres for the three bands at once (lane b evaluates band b)
         const float bmet = ol_band_metres(p, bsum, bcnt);
