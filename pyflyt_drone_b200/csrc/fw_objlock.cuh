@@ -271,31 +271,25 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
         // phase B (lanes = columns): duck pixels drop out, the rest feed the three harmonic band means
         int dlo, dhi;
         ol_col_interval(bAx, bAy, brx, bry, AA, AB, BB, bsx - bcx, bsy - bcy, Rd, w, dlo, dhi);
-        // Frames with nothing but the ground plane in the middle row (no cylinder candidate, the duck sphere clear of the
-        // row's ray plane) need no per-column pass: the inverse depth of the ground along the row is LINEAR in the column
-        // index, iv_j = clamp(alpha + beta j, 1/far, 1/near) -- a ray that misses the ground has alpha + beta j <= 0 and
-        // clamps to 1/far like a miss -- so each band sum is two clamped runs plus one arithmetic series.  Lanes 0..2
-        // evaluate the three bands.  (The duck-only training configuration has no obstacles: most of its frames.)
-        bool fast = total == 0;
-        if (fast && dlo <= dhi) {
-            // distance of the sphere centre from the plane of the row's rays (normal (0, 1, vrow) in camera coordinates)
-            const float byc = __shfl_sync(FULL, yc, s), bzc = __shfl_sync(FULL, zc, s);
-            fast = fabsf(fmaf(vrow, bzc, byc)) > (Rd * 1.001f + 1e-4f) * sqrtf(fmaf(vrow, vrow, 1.0f));
+        // The inverse depth of the GROUND along the middle row is linear in the column index, iv_j = clamp(alpha + beta j,
+        // 1/far, 1/near) -- a ray that misses the ground has alpha + beta j <= 0 and clamps to 1/far like a miss -- so the
+        // ground-only sum of a band is two clamped runs plus one arithmetic series: lanes 0..2 evaluate the three bands in
+        // closed form.  Only columns a cylinder was rasterised into, or that may show the duck, are then visited to CORRECT
+        // those sums (32-column groups without such a column are skipped; frames without any -- most frames of the
+        // obstacle-free duck-only configuration -- need no column pass at all).
+        const float inv_far = 1.0f / p.cam_far, inv_near = 1.0f / p.cam_near;
+        float alpha = 0.0f, beta = 0.0f;                         // camera at or below the ground: every ray misses
+        if (bcz > 0.0f) {
+            const float icz = 1.0f / bcz;
+            alpha = -fmaf(x0, brz, bAz) * icz; beta = -(xs * brz) * icz;
         }
         float bsum;
         int bcnt;
-        if (fast) {
-            const float inv_far = 1.0f / p.cam_far, inv_near = 1.0f / p.cam_near;
+        {
             const int j0 = lane == 0 ? 0 : (lane == 1 ? x1 : x2), j1 = lane == 0 ? x1 : (lane == 1 ? x2 : w);
-            float alpha = 0.0f, beta = 0.0f;                     // camera at or below the ground: every ray misses
-            if (bcz > 0.0f) {
-                const float icz = 1.0f / bcz;
-                alpha = -fmaf(x0, brz, bAz) * icz; beta = -(xs * brz) * icz;
-            }
-            float total_iv;
             const float n = (float)(j1 - j0);
             if (fabsf(beta) * (float)w < 1e-12f) {
-                total_iv = n * fminf(fmaxf(alpha, inv_far), inv_near);
+                bsum = n * fminf(fmaxf(alpha, inv_far), inv_near);
             } else {
                 const float ib = 1.0f / beta;
                 const float ja = (inv_far - alpha) * ib, jb = (inv_near - alpha) * ib;      // where the two clamps engage
@@ -305,40 +299,55 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
                 const int cB = min(max((int)floorf(jB) + 1, cA), j1);                       // linear: [cA, cB), above: [cB, j1)
                 const float below = beta > 0.0f ? inv_far : inv_near, above = beta > 0.0f ? inv_near : inv_far;
                 const float nm = (float)(cB - cA);
-                total_iv = below * (float)(cA - j0) + above * (float)(j1 - cB) +
-                           fmaf(beta, 0.5f * (float)(cA + cB - 1) * nm, alpha * nm);
+                bsum = below * (float)(cA - j0) + above * (float)(j1 - cB) + fmaf(beta, 0.5f * (float)(cA + cB - 1) * nm, alpha * nm);
             }
-            bsum = total_iv; bcnt = j1 - j0;
-        } else {
-            float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
-            int cnt3 = 0;                                    // the three band counts, 10 bits each (cam_res <= 1024)
-            for (int col = lane; col < w; col += 32) {
-                const float xn = fmaf((float)col, xs, x0);
-                float best = depth_row[col];
-                depth_row[col] = INF;                        // ready for the next frame
-                {
-                    const float dz = bAz + xn * brz;
-                    if (dz < -1e-12f) { const float t = -bcz / dz; if (t > 0.0f) best = fminf(best, t); }
+            bcnt = j1 - j0;
+        }
+        bool duck_row = dlo <= dhi;
+        if (duck_row) {
+            // the sphere shows in the row only if its centre is within a radius of the plane of the row's rays (normal
+            // (0, 1, vrow) in camera coordinates)
+            const float byc = __shfl_sync(FULL, yc, s), bzc = __shfl_sync(FULL, zc, s);
+            duck_row = fabsf(fmaf(vrow, bzc, byc)) <= (Rd * 1.001f + 1e-4f) * sqrtf(fmaf(vrow, vrow, 1.0f));
+        }
+        if (total != 0 || duck_row) {
+            float cor0 = 0.f, cor1 = 0.f, cor2 = 0.f;
+            int dec3 = 0;                                    // duck pixels leaving the three bands, 10 bits each
+            for (int base = 0; base < w; base += 32) {
+                const int col = base + lane;
+                const bool valid = col < w;
+                const float tc = valid ? depth_row[col] : INF;
+                const bool touched = tc < INF;
+                const bool ind = duck_row && valid && col >= dlo && col <= dhi;
+                if (!__any_sync(FULL, touched || ind)) continue;
+                if (touched) depth_row[col] = INF;           // ready for the next frame
+                if (touched || ind) {
+                    const float gl = fmaf(beta, (float)col, alpha);              // ground, unclamped (<= 0: no hit)
+                    const float ground = fminf(fmaxf(gl, inv_far), inv_near);
+                    const float itc = touched ? 1.0f / tc : 0.0f;
+                    bool duck_px = false;
+                    if (ind) {
+                        const float xn = fmaf((float)col, xs, x0);
+                        const float td = ol_ray_sphere(bcx, bcy, bcz, bAx + xn * brx, bAy + xn * bry, bAz + xn * brz, bsx, bsy, bsz, Rd);
+                        duck_px = td < INF && 1.0f / td > fmaxf(itc, gl);        // nearer than the cylinder and the ground
+                    }
+                    // a duck pixel leaves its band; otherwise the nearer of cylinder and ground replaces the ground
+                    const float corr = duck_px ? -ground : fmaxf(fminf(fmaxf(itc, inv_far), inv_near), ground) - ground;
+                    const int dec = duck_px ? 1 : 0;
+                    if (col < x1) { cor0 += corr; dec3 += dec; }
+                    else if (col < x2) { cor1 += corr; dec3 += dec << 10; }
+                    else { cor2 += corr; dec3 += dec << 20; }
                 }
-                if (col >= dlo && col <= dhi) {
-                    float td = ol_ray_sphere(bcx, bcy, bcz, bAx + xn * brx, bAy + xn * bry, bAz + xn * brz, bsx, bsy, bsz, Rd);
-                    if (td < best) continue;
-                }
-                float iv = (best < INF) ? ol_inv_depth(p, best) : 1.0f / p.cam_far;
-                if (col < x1) { sum0 += iv; cnt3 += 1; }
-                else if (col < x2) { sum1 += iv; cnt3 += 1 << 10; }
-                else { sum2 += iv; cnt3 += 1 << 20; }
             }
             // NOTE: fp32 addition is not associative; the oracle sums columns left to right in fp64, so the order
             // here only moves the last bits of a quantity that is compared with a 2e-4 relative tolerance
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
-                sum0 += __shfl_xor_sync(FULL, sum0, off); sum1 += __shfl_xor_sync(FULL, sum1, off);
-                sum2 += __shfl_xor_sync(FULL, sum2, off); cnt3 += __shfl_xor_sync(FULL, cnt3, off);
+                cor0 += __shfl_xor_sync(FULL, cor0, off); cor1 += __shfl_xor_sync(FULL, cor1, off);
+                cor2 += __shfl_xor_sync(FULL, cor2, off); dec3 += __shfl_xor_sync(FULL, dec3, off);
             }
-            // every lane holds all sums: lane b keeps band b
-            bsum = lane == 0 ? sum0 : (lane == 1 ? sum1 : sum2);
-            bcnt = (cnt3 >> (10 * min(lane, 2))) & 1023;
+            bsum += lane == 0 ? cor0 : (lane == 1 ? cor1 : cor2);
+            bcnt -= (dec3 >> (10 * min(lane, 2))) & 1023;
         }
         // mean inverse depth -> metres for the three bands at once (lane b evaluates band b)
         const float bmet = ol_band_metres(p, bsum, bcnt);
