@@ -304,13 +304,10 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     venv.reset()
     rng = np.random.default_rng(rank)
     # the step's inputs wait in pinned host memory (bench contract); FixedwingVecEnv reads page-locked caller buffers in place
-    acts = []
-    for _ in range(4):
-        buf = torch.empty((N, 4), dtype=torch.float32, pin_memory=True)
-        buf.numpy()[:] = rng.uniform(-1, 1, (N, 4)).astype(np.float32)
-        acts.append(buf)
-    acts_keepalive = acts
-    acts = [b.numpy() for b in acts]
+    pinned = [torch.empty((N, 4), dtype=torch.float32, pin_memory=True) for _ in range(4)]   # owns the memory
+    acts = [b.numpy() for b in pinned]
+    for a in acts:
+        a[:] = rng.uniform(-1, 1, (N, 4)).astype(np.float32)
     for s in range(5):
         venv.step_arrays(acts[s % 4], want_terminal_obs=False)
     barrier()
