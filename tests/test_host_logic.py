@@ -140,3 +140,26 @@ def test_from_gym_kwargs_reproduces_the_training_script_preset():
         from_gym_kwargs("waypoints_v3", agent_hz=50)           # fixedwing_base_env.py:97-100: agent_hz must divide 120
     with pytest.raises(ValueError):
         from_gym_kwargs("waypoints_v3", angle_representation="dcm")
+
+
+def test_duck_only_config_round_trips_and_rejects_bad_arguments():
+    """objlock_duck preset -> C struct (the task-4 fields added in ABI 9), and the argument checks of the single-env view
+    that fire before any device is touched (envs/fixedwing_objlock_env.py:37-118 keyword names)."""
+    c = fw.make_config("objlock_duck").to_c()
+    assert c.task == 4 and c.num_targets == 0 and c.context_len == 0 and c.cam_mode == 1 and c.cam_res == 480
+    assert c.cam_tilt_deg == -5.0 and c.cam_offset[0] == pytest.approx(0.8) and c.cam_offset[2] == pytest.approx(0.12)
+    assert (c.vision_hist_len, c.vision_use_deltas, c.lock_decay_steps) == (3, 1, 1)
+    assert (c.duck_dist_scale, c.lock_center_radius, c.centering_scale, c.visible_step_reward, c.area_reward_scale,
+            c.lock_lost_penalty, c.approach_clip) == (1.0, 0.55, 3.0, 2.0, 5.0, 0.5, 2.0)
+    assert c.strike_reward == 400.0 and c.lock_hold_steps == 5 and c.wind_base_hi[0] == 10.0
+    from pyflyt_drone_b200.gym_env import FixedwingObjLockEnv
+    with pytest.raises(ValueError, match="agent_hz"):
+        FixedwingObjLockEnv(agent_hz=50)
+    with pytest.raises(ValueError, match="angle_representation"):
+        FixedwingObjLockEnv(angle_representation="axis_angle")
+    with pytest.raises(ValueError, match="flight_mode"):
+        FixedwingObjLockEnv(flight_mode=-1)
+    with pytest.raises(ValueError, match="render_mode"):
+        FixedwingObjLockEnv(render_mode="human")
+    with pytest.raises(ValueError, match="90 degree"):
+        FixedwingObjLockEnv(camera_FOV_degrees=60)
