@@ -268,9 +268,19 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
         }
         const unsigned hidden = __ballot_sync(FULL, occl);
         __syncwarp();
-        // phase B (lanes = columns): duck pixels drop out, the rest feed the three harmonic band means
-        int dlo, dhi;
-        ol_col_interval(bAx, bAy, brx, bry, AA, AB, BB, bsx - bcx, bsy - bcy, Rd, w, dlo, dhi);
+        // phase B: the three harmonic band means of the middle row; duck pixels drop out.  The sphere shows in the row only
+        // if its centre lies within a radius of the plane of the row's rays (normal (0, 1, vrow) in camera coordinates) and
+        // not wholly behind the camera; only then is its column interval worked out.
+        int dlo = 1, dhi = 0;
+        bool duck_row;
+        {
+            const float byc = __shfl_sync(FULL, yc, s), bzc = __shfl_sync(FULL, zc, s);
+            duck_row = fabsf(fmaf(vrow, bzc, byc)) <= (Rd * 1.001f + 1e-4f) * sqrtf(fmaf(vrow, vrow, 1.0f)) && bzc + Rd > 0.0f;
+        }
+        if (duck_row) {
+            ol_col_interval(bAx, bAy, brx, bry, AA, AB, BB, bsx - bcx, bsy - bcy, Rd, w, dlo, dhi);
+            duck_row = dlo <= dhi;
+        }
         // The inverse depth of the GROUND along the middle row is linear in the column index, iv_j = clamp(alpha + beta j,
         // 1/far, 1/near) -- a ray that misses the ground has alpha + beta j <= 0 and clamps to 1/far like a miss -- so the
         // ground-only sum of a band is two clamped runs plus one arithmetic series: lanes 0..2 evaluate the three bands in
@@ -302,13 +312,6 @@ __device__ __forceinline__ void ol_capture_warp(const FwDev& p, bool need, const
                 bsum = below * (float)(cA - j0) + above * (float)(j1 - cB) + fmaf(beta, 0.5f * (float)(cA + cB - 1) * nm, alpha * nm);
             }
             bcnt = j1 - j0;
-        }
-        bool duck_row = dlo <= dhi;
-        if (duck_row) {
-            // the sphere shows in the row only if its centre is within a radius of the plane of the row's rays (normal
-            // (0, 1, vrow) in camera coordinates)
-            const float byc = __shfl_sync(FULL, yc, s), bzc = __shfl_sync(FULL, zc, s);
-            duck_row = fabsf(fmaf(vrow, bzc, byc)) <= (Rd * 1.001f + 1e-4f) * sqrtf(fmaf(vrow, vrow, 1.0f));
         }
         if (total != 0 || duck_row) {
             float cor0 = 0.f, cor1 = 0.f, cor2 = 0.f;
