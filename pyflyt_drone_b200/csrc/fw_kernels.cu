@@ -485,7 +485,8 @@ __device__ __forceinline__ void ol_smem_carve(const FwDev& p, float* stage, floa
     hs = rows + (size_t)(FW_BLOCK / 32) * p.cam_res;
 }
 
-// 7 blocks/SM x 64 threads x 146 registers: 148 x 448 = 66,304 >= 65,536 envs, still a single wave
+// launch bound 7 blocks/SM x 64 threads (register cap 146; ptxas settles at 128 with ~70 bytes of spills, so 8 blocks fit):
+// 148 x 448 = 66,304 >= 65,536 envs, a single wave either way
 template <bool RANDOM_ACT, int TASK, bool STD>
 __global__ void __launch_bounds__(FW_BLOCK, 7)
 fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4* __restrict__ act,
