@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 9
+#define FW_ABI_VERSION 10
 
 #define FW_NSURF 5            /* cmd order: left aileron, right aileron, h-tail, v-tail, main wing */
 #define FW_MAX_TARGETS 16
@@ -48,6 +48,10 @@ extern "C" {
 #define FW_FLAG_OOB       8   /* info["out_of_bounds"] */
 #define FW_FLAG_COMPLETE  16  /* info["env_complete"] */
 #define FW_FLAG_STRIKE    32  /* info["duck_strike"] */
+#define FW_FLAG_FAULT     64  /* no reference counterpart: the env's state went non-finite; it was terminated with reward 0,
+                               * counted (fw_fault_count) and reset, and its terminal observation is the first observation
+                               * of the new episode.  The reference swallows simulator exceptions instead
+                               * (fixedwing_waypoint_objlock_env.py:401,449,502). */
 
 #define FW_TASK_PHYSICS   0   /* dynamics + ground/dome termination, no observation (BASELINE config 2) */
 #define FW_TASK_WAYPOINTS 1   /* PyFlyt/Fixedwing-Waypoints-v3 + FlattenWaypointEnv */
@@ -180,6 +184,21 @@ int fw_rollout_random(const fw_handle* hs, int32_t n_handles, int32_t n_launches
 int fw_step_host(fw_handle h, const float* act_host, float* obs_host, float* rew_host, uint8_t* flags_host,
                  float* term_obs_host);
 int fw_reset_host(fw_handle h, float* obs_host);
+/* Observation of the CURRENT state of every env without resetting anything (last action unknown -> zeros in the action
+ * slots): what a single-env gymnasium view returns from reset() right after a finished episode, when the batch has
+ * already auto-reset itself (the SubprocVecEnv worker's obs = env.reset()). */
+int fw_observe_host(fw_handle h, float* obs_host);
+
+/* info["num_targets_reached"] (fixedwing_waypoint_objlock_env.py:296, upstream FixedwingWaypointsEnv) of the last step,
+ * per env, taken BEFORE the auto-reset of a finished episode -- what WaypointEvalCallback._log_success_callback reads
+ * on every done (train_Fixedwing_Waypoints_v3.py:136-138, train_Fixedwing_Waypoints_ObjLock.py:181-185).
+ * Host lane: a pinned [N] byte buffer owned by the handle that every fw_step_host fills (tasks 1 and 2).
+ * Device lane: an asynchronous device-to-device copy of the same plane as written by the last fw_step. */
+int fw_host_info_buffer(fw_handle h, uint8_t** targets_reached);
+int fw_targets_reached(fw_handle h, uint8_t* dst_dev, void* stream);
+
+/* number of envs force-reset because their state went non-finite (FW_FLAG_FAULT) since fw_create (synchronous) */
+int fw_fault_count(fw_handle h, int64_t* nonfinite_resets);
 /* The library's pinned staging buffers ([N,4] actions, [N,obs_dim] obs, [N] rewards, [N] flag bytes,
  * [N,obs_dim] terminal obs).  Passing these very pointers to fw_step_host / fw_reset_host makes the call
  * zero-copy on the host side (DMA straight from/to the caller-visible memory).  Owned by the handle. */

@@ -1059,6 +1059,7 @@ void fwo_step(const fwo_config* c, fwo_env* e, uint64_t seed, const double* acti
 typedef struct {
     const fwo_config* c; fwo_env* envs; int lo, hi; uint64_t seed; uint32_t env_id0;
     const double* actions; double* obs; double* rewards; int32_t* flags; double* term_obs;
+    int32_t* targets_reached;   /* info["num_targets_reached"] of the step, before the worker's reset-on-done */
     int steps; int mode;
 } fwo_job;
 
@@ -1077,6 +1078,8 @@ static void run_range(fwo_job* j) {
             fwo_step(c, e, j->seed, j->actions + (size_t)i * fwo_act_dim(c), o, &r, &fl);
             if (j->rewards) j->rewards[i] = r;
             if (j->flags) j->flags[i] = fl;
+            /* WaypointHandler.num_targets_reached = n - len(targets) (fixedwing_waypoint_objlock_env.py:296) */
+            if (j->targets_reached) j->targets_reached[i] = c->num_targets > 0 ? c->num_targets - e->n_remaining : 0;
             if (fl & (FWO_TERM | FWO_TRUNC)) {
                 /* SubprocVecEnv worker: info["terminal_observation"] = obs; obs = env.reset() */
                 if (j->term_obs) memcpy(j->term_obs + (size_t)i * D, o, sizeof(double) * D);
@@ -1128,6 +1131,15 @@ void fwo_vec_step(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, cons
     fwo_job j; memset(&j, 0, sizeof(j));
     j.c = c; j.envs = envs; j.seed = seed; j.actions = actions; j.obs = obs; j.rewards = rewards;
     j.flags = flags; j.term_obs = term_obs; j.mode = 1;
+    parallel_run(&j, n, nthreads);
+}
+
+void fwo_vec_step_info(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, const double* actions,
+                       double* obs, double* rewards, int32_t* flags, double* term_obs, int32_t* targets_reached,
+                       int nthreads) {
+    fwo_job j; memset(&j, 0, sizeof(j));
+    j.c = c; j.envs = envs; j.seed = seed; j.actions = actions; j.obs = obs; j.rewards = rewards;
+    j.flags = flags; j.term_obs = term_obs; j.targets_reached = targets_reached; j.mode = 1;
     parallel_run(&j, n, nthreads);
 }
 

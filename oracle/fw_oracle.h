@@ -205,6 +205,10 @@ void fwo_step(const fwo_config* c, fwo_env* e, uint64_t seed, const double* acti
 /* SubprocVecEnv worker semantics: step, and on done stash terminal obs then reset */
 void fwo_vec_step(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, const double* actions,
                   double* obs, double* rewards, int32_t* flags, double* term_obs, int nthreads);
+/* fwo_vec_step plus info["num_targets_reached"] of every env, taken before the reset-on-done of a finished episode */
+void fwo_vec_step_info(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, const double* actions,
+                       double* obs, double* rewards, int32_t* flags, double* term_obs, int32_t* targets_reached,
+                       int nthreads);
 void fwo_vec_reset(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, uint32_t env_id0,
                    double* obs, int nthreads);
 /* random-action rollout used as the CPU baseline: returns env-steps executed */

@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
         L.fwo_vec_reset.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_int, C.c_uint64, _U, C.c_void_p, C.c_int]
         L.fwo_vec_step.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_int, C.c_uint64, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.fwo_vec_step_info.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_int, C.c_uint64, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.fwo_rollout_random.restype = C.c_long
         L.fwo_rollout_random.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_int, C.c_uint64, C.c_int, C.c_int]
         L.fwo_compute_obs.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_void_p, C.c_int]
@@ -184,8 +186,9 @@ class OracleVecEnv:
         D = max(self.obs_dim, 1)
         obs = np.zeros((self.n, D)); term = np.zeros((self.n, D))
         rew = np.zeros(self.n); flags = np.zeros(self.n, dtype=np.int32)
-        self.L.fwo_vec_step(C.byref(self.cfg), self.envs, self.n, self.seed, _ptr(a), _ptr(obs), _ptr(rew), _ptr(flags),
-                            _ptr(term), self.nthreads)
+        self.last_targets_reached = np.zeros(self.n, dtype=np.int32)      # info["num_targets_reached"], pre-reset
+        self.L.fwo_vec_step_info(C.byref(self.cfg), self.envs, self.n, self.seed, _ptr(a), _ptr(obs), _ptr(rew), _ptr(flags),
+                                 _ptr(term), _ptr(self.last_targets_reached), self.nthreads)
         return obs[:, : self.obs_dim], rew, flags, term[:, : self.obs_dim]
 
     def rollout_random(self, steps: int) -> int:

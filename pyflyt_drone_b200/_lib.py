@@ -43,6 +43,10 @@ SYMBOLS = [
     ("fw_rollout_random", C.c_int, [C.POINTER(_P), C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     ("fw_step_host", C.c_int, [_P, _P, _P, _P, _P, _P]),
     ("fw_reset_host", C.c_int, [_P, _P]),
+    ("fw_observe_host", C.c_int, [_P, _P]),
+    ("fw_host_info_buffer", C.c_int, [_P, C.POINTER(_P)]),
+    ("fw_targets_reached", C.c_int, [_P, _P, _P]),
+    ("fw_fault_count", C.c_int, [_P, C.POINTER(C.c_int64)]),
     ("fw_host_buffers", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     ("fw_set_state", C.c_int, [_P, C.POINTER(FwStateHostC)]),
     ("fw_get_state", C.c_int, [_P, C.POINTER(FwStateHostC)]),
@@ -52,14 +56,20 @@ SYMBOLS = [
 ]
 
 
+ABI_VERSION = 10        # include/fwsim.h FW_ABI_VERSION this binding was written against
+
+
 def load() -> C.CDLL:
-    """Load libfwsim.so (building it first if nvcc is present and sources are newer)."""
+    """Load libfwsim.so, (re)building it first when nvcc is present and a source is newer than the library
+    (build.build() is a no-op otherwise).  A box without nvcc -- the GPU box -- uses the shipped library as it is."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    from . import build as _build
+    if _build.have_nvcc():
         _build.build()
+    elif not os.path.exists(LIB_PATH):
+        raise FwError(f"{LIB_PATH} is missing and nvcc is not available to build it; the env step has no CPU fallback")
     try:
         lib = C.CDLL(LIB_PATH)
     except OSError as e:
@@ -74,6 +84,9 @@ def load() -> C.CDLL:
         _bind_ppo(lib)
     except ImportError:
         pass
+    if lib.fw_abi_version() != ABI_VERSION:
+        raise FwError(f"libfwsim.so has ABI {lib.fw_abi_version()}, this package binds ABI {ABI_VERSION}: rebuild with "
+                      "`python -m pyflyt_drone_b200.build --force`")
     if lib.fw_config_size() != C.sizeof(FwConfigC):
         raise FwError(f"FwConfig ABI mismatch: C {lib.fw_config_size()} bytes vs ctypes {C.sizeof(FwConfigC)}")
     _lib = lib

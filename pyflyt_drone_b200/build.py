@@ -31,6 +31,14 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: libfwsim.so cannot be built (there is no CPU fallback)")
 
 
+def have_nvcc() -> bool:
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
 def sources() -> list[str]:
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 

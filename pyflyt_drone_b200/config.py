@@ -21,7 +21,7 @@ NSURF, MAX_TARGETS, MAX_COL, MAX_OBST = 5, 16, 16, 32
 TASK_PHYSICS, TASK_WAYPOINTS, TASK_OBJLOCK, TASK_LOWLEVEL, TASK_DUCK = 0, 1, 2, 3, 4
 MAX_HIST = 4
 
-FLAG_TERM, FLAG_TRUNC, FLAG_COLLISION, FLAG_OOB, FLAG_COMPLETE, FLAG_STRIKE = 1, 2, 4, 8, 16, 32
+FLAG_TERM, FLAG_TRUNC, FLAG_COLLISION, FLAG_OOB, FLAG_COMPLETE, FLAG_STRIKE, FLAG_FAULT = 1, 2, 4, 8, 16, 32, 64
 
 _D = C.c_double
 _I = C.c_int32

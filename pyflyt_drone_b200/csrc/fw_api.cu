@@ -46,9 +46,25 @@ struct FwSim {
     uint8_t* h_flg;
     float *d_act, *d_obs, *d_rew, *d_term;
     uint8_t* d_flg;
+    uint8_t* h_tidx;   // host lane: info["num_targets_reached"] per env, written by the step kernel (pinned, device-mapped)
     int64_t launches;
     bool fresh;   // true until the state created by fw_create has been stepped or overwritten
+    // Lane ordering: the device lane enqueues on the caller's stream, the host lane on private non-blocking streams, and
+    // both touch the same state planes.  The host lane is synchronous (it waits for its own streams before returning), so
+    // the only hazard is device-lane work still in flight when a host-lane call starts: the flag makes that call wait
+    // for the device first.  Pure-host and pure-device users never pay for it.
+    bool dev_lane_dirty;
 };
+
+// host-lane entry: wait for device-lane launches that may still be running on the caller's streams
+static int host_lane_enter(FwSim* h) {
+    if (h->dev_lane_dirty) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return fail(FW_ECUDA, "cudaDeviceSynchronize: %s", cudaGetErrorString(e));
+        h->dev_lane_dirty = false;
+    }
+    return FW_OK;
+}
 
 // shared with ppo_api.cu so that fw_last_error() reports PPO kernel errors too
 extern "C" void fw_set_last_error_(const char* msg) { g_err = msg ? msg : ""; }
@@ -290,6 +306,8 @@ static int multi_graph_get(MultiGraph& mg, const fw_handle* hs, int n_handles, i
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+static int fw_create_impl(const FwConfig* cfg, int32_t n_envs, int32_t device, uint64_t seed, uint32_t env_id0, FwSim* h);
+
 extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, uint64_t seed, uint32_t env_id0, fw_handle* out) {
     if (!cfg || !out) return fail(FW_EINVAL, "null argument");
     if (n_envs <= 0) return fail(FW_EINVAL, "n_envs must be positive");
@@ -302,19 +320,33 @@ extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, ui
     CU(cudaSetDevice(device));
     FwSim* h = new FwSim();
     memset(h, 0, sizeof(*h));
+    const int rc = fw_create_impl(cfg, n_envs, device, seed, env_id0, h);
+    if (rc != FW_OK) {                       // every early return of the body lands here: nothing leaks
+        const std::string keep = g_err;
+        fw_destroy(h);
+        g_err = keep;
+        return rc;
+    }
+    *out = h;
+    return FW_OK;
+}
+
+static int fw_create_impl(const FwConfig* cfg, int32_t n_envs, int32_t device, uint64_t seed, uint32_t env_id0, FwSim* h) {
+    cudaError_t ce;
     h->cfg = *cfg; h->n = n_envs; h->device = device;
     int rc = derive(*cfg, n_envs, seed, env_id0, h->dev);
-    if (rc != FW_OK) { delete h; return rc; }
+    if (rc != FW_OK) return rc;
     h->obs_dim = h->dev.obs_dim;
     const size_t N = (size_t)n_envs, T = (size_t)(cfg->num_targets > 0 ? cfg->num_targets : 1);
-    size_t off = 0, o_s[6], o_w0, o_w1, o_t, o_ep, o_st, o_ol[5] = {0, 0, 0, 0, 0}, o_ob = 0, o_hist = 0;
+    size_t off = 0, o_s[6], o_w0, o_w1, o_t, o_ep, o_st, o_ti, o_ol[5] = {0, 0, 0, 0, 0}, o_ob = 0, o_hist = 0;
     const bool cam_task = cfg->task == 2 || cfg->task == 4;
     for (int k = 0; k < 6; ++k) { o_s[k] = off; off = align_up(off + N * 16, 256); }
     o_w0 = off; off = align_up(off + N * 16, 256);
     o_w1 = off; off = align_up(off + N * 16, 256);
     o_t = off; off = align_up(off + T * 3 * N * 4, 256);
     o_ep = off; off = align_up(off + N * 4, 256);
-    o_st = off; off = align_up(off + 8 * sizeof(double), 256);
+    o_st = off; off = align_up(off + 16 * sizeof(double), 256);
+    o_ti = off; off = align_up(off + N, 256);
     if (cam_task) {
         for (int k = 0; k < 5; ++k) { o_ol[k] = off; off = align_up(off + N * 16, 256); }
         o_ob = off; off = align_up(off + (size_t)FW_MAX_OBST * 3 * N * 4, 256);
@@ -322,7 +354,7 @@ extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, ui
     if (cfg->task == 4) { o_hist = off; off = align_up(off + (size_t)h->dev.hist_slots * N * 4, 256); }
     h->plane_bytes = off;
     ce = cudaMalloc((void**)&h->plane_mem, off);
-    if (ce != cudaSuccess) { delete h; return fail(FW_ENOMEM, "cudaMalloc(%zu): %s", off, cudaGetErrorString(ce)); }
+    if (ce != cudaSuccess) return fail(FW_ENOMEM, "cudaMalloc(%zu): %s", off, cudaGetErrorString(ce));
     cudaMemset(h->plane_mem, 0, off);
     FwPlanes& pl = h->pl;
     pl.s0 = (float4*)(h->plane_mem + o_s[0]); pl.s1 = (float4*)(h->plane_mem + o_s[1]);
@@ -331,6 +363,7 @@ extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, ui
     pl.w0 = (float4*)(h->plane_mem + o_w0); pl.w1 = (float4*)(h->plane_mem + o_w1);
     pl.targets = (float*)(h->plane_mem + o_t); pl.ep_ret = (float*)(h->plane_mem + o_ep);
     pl.stats = (double*)(h->plane_mem + o_st);
+    pl.tidx_out = (uint8_t*)(h->plane_mem + o_ti);
     if (cfg->task == 4) pl.hist = (float*)(h->plane_mem + o_hist);
     if (cam_task) {
         pl.dk = (float4*)(h->plane_mem + o_ol[0]); pl.v0 = (float4*)(h->plane_mem + o_ol[1]);
@@ -359,7 +392,6 @@ extern "C" int fw_create(const FwConfig* cfg, int32_t n_envs, int32_t device, ui
     h->launches++;
     CU(cudaStreamSynchronize(h->io_stream));
     h->fresh = true;
-    *out = h;
     return FW_OK;
 }
 
@@ -386,6 +418,7 @@ extern "C" int fw_destroy(fw_handle h) {
     if (h->h_rew) cudaFreeHost(h->h_rew);
     if (h->h_term) cudaFreeHost(h->h_term);
     if (h->h_flg) cudaFreeHost(h->h_flg);
+    if (h->h_tidx) cudaFreeHost(h->h_tidx);
     if (h->io_stream) cudaStreamDestroy(h->io_stream);
     if (h->io_streams[1]) cudaStreamDestroy(h->io_streams[1]);
     delete h;
@@ -405,6 +438,7 @@ extern "C" int fw_reset(fw_handle h, const uint8_t* mask_dev, float* obs_dev, vo
     CU(fwk_launch_reset(h->dev, h->pl, mask_dev, obs_dev, emit_only, (cudaStream_t)stream));
     h->launches++;
     h->fresh = false;
+    h->dev_lane_dirty = true;
     return FW_OK;
 }
 
@@ -417,6 +451,7 @@ extern "C" int fw_step(fw_handle h, const float* act_dev, float* obs_dev, float*
     CU(fwk_launch_step(h->dev, h->pl, act_dev, obs_dev, rew_dev, flags_dev, term_obs_dev, false, 1, (cudaStream_t)stream));
     h->launches++;
     h->fresh = false;
+    h->dev_lane_dirty = true;
     return FW_OK;
 }
 
@@ -425,6 +460,7 @@ extern "C" int fw_step_random(fw_handle h, int32_t n_steps, float* rew_dev, uint
     if (n_steps < 0) return fail(FW_EINVAL, "n_steps < 0");
     CU(cudaSetDevice(h->device));
     h->fresh = false;
+    h->dev_lane_dirty = true;
     for (int s = 0; s < n_steps; ++s) {
         CU(fwk_launch_step(h->dev, h->pl, nullptr, nullptr, rew_dev, flags_dev, nullptr, true, 1, (cudaStream_t)stream));
         h->launches++;
@@ -440,6 +476,7 @@ extern "C" int fw_rollout_random(const fw_handle* hs, int32_t n_handles, int32_t
         if (!hs[k]) return fail(FW_EINVAL, "null handle in list");
         if (hs[k]->device != hs[0]->device) return fail(FW_EINVAL, "handles of one rollout must share a device");
         hs[k]->fresh = false;
+        hs[k]->dev_lane_dirty = true;
     }
     CU(cudaSetDevice(hs[0]->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -477,6 +514,8 @@ static int ensure_host_io(FwSim* h) {
     CU(cudaMallocHost((void**)&h->h_rew, N * sizeof(float)));
     CU(cudaMallocHost((void**)&h->h_term, N * D * sizeof(float)));
     CU(cudaMallocHost((void**)&h->h_flg, N));
+    CU(cudaMallocHost((void**)&h->h_tidx, N));
+    memset(h->h_tidx, 0, N);
     CU(cudaMalloc((void**)&h->d_act, N * Aw * sizeof(float)));
     CU(cudaMalloc((void**)&h->d_obs, N * D * sizeof(float)));
     CU(cudaMalloc((void**)&h->d_rew, N * sizeof(float)));
@@ -492,6 +531,8 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
     if (!act_host) return fail(FW_EINVAL, "act_host is null");
     CU(cudaSetDevice(h->device));
     int rc = ensure_host_io(h);
+    if (rc != FW_OK) return rc;
+    rc = host_lane_enter(h);
     if (rc != FW_OK) return rc;
     const size_t N = (size_t)h->n, D = (size_t)h->obs_dim;
     // The batch is cut into chunks that alternate between two streams, so that the staging of caller-owned (pageable)
@@ -533,7 +574,9 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
         static const bool zc_obs = [] { const char* e = getenv("FWSIM_HOST_ZEROCOPY_OBS"); return !(e && atoi(e) == 0); }();
         float* obs_dst = D ? (zc_obs ? h->h_obs : h->d_obs) : nullptr;
         float* term_dst = want_term ? (zc_obs ? h->h_term : h->d_term) : nullptr;
-        CU(fwk_launch_step(pc, h->pl, act_dev_view ? act_dev_view : h->h_act, obs_dst, h->h_rew, h->h_flg, term_dst, false, 1, st));
+        FwPlanes plh = h->pl;
+        plh.tidx_out = h->h_tidx;          // info["num_targets_reached"] goes straight to the host like the flags
+        CU(fwk_launch_step(pc, plh, act_dev_view ? act_dev_view : h->h_act, obs_dst, h->h_rew, h->h_flg, term_dst, false, 1, st));
         h->launches++;
         if (!zc_obs) {
             if (obs_host && D) CU(cudaMemcpyAsync(h->h_obs + n0 * D, h->d_obs + n0 * D, cn * D * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -564,16 +607,50 @@ extern "C" int fw_host_buffers(fw_handle h, float** act, float** obs, float** re
     return FW_OK;
 }
 
-extern "C" int fw_reset_host(fw_handle h, float* obs_host) {
+extern "C" int fw_host_info_buffer(fw_handle h, uint8_t** targets_reached) {
     if (!h) return fail(FW_EINVAL, "null handle");
     CU(cudaSetDevice(h->device));
     int rc = ensure_host_io(h);
     if (rc != FW_OK) return rc;
+    if (targets_reached) *targets_reached = h->h_tidx;
+    return FW_OK;
+}
+
+extern "C" int fw_targets_reached(fw_handle h, uint8_t* dst_dev, void* stream) {
+    if (!h || !dst_dev) return fail(FW_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(dst_dev, h->pl.tidx_out, (size_t)h->n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return FW_OK;
+}
+
+extern "C" int fw_fault_count(fw_handle h, int64_t* nonfinite_resets) {
+    if (!h || !nonfinite_resets) return fail(FW_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    double v = 0.0;
+    CU(cudaMemcpy(&v, h->pl.stats + 8, sizeof(double), cudaMemcpyDeviceToHost));
+    *nonfinite_resets = (int64_t)v;
+    return FW_OK;
+}
+
+static int reset_host_impl(fw_handle h, float* obs_host, bool observe_only);
+
+extern "C" int fw_reset_host(fw_handle h, float* obs_host) { return reset_host_impl(h, obs_host, false); }
+extern "C" int fw_observe_host(fw_handle h, float* obs_host) { return reset_host_impl(h, obs_host, true); }
+
+static int reset_host_impl(fw_handle h, float* obs_host, bool observe_only) {
+    if (!h) return fail(FW_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    int rc = ensure_host_io(h);
+    if (rc != FW_OK) return rc;
+    rc = host_lane_enter(h);
+    if (rc != FW_OK) return rc;
+    if (!observe_only) memset(h->h_tidx, 0, (size_t)h->n);
     const size_t N = (size_t)h->n, D = (size_t)h->obs_dim;
     cudaStream_t st = h->io_stream;
-    CU(fwk_launch_reset(h->dev, h->pl, nullptr, D ? h->d_obs : nullptr, h->fresh, st));
+    CU(fwk_launch_reset(h->dev, h->pl, nullptr, D ? h->d_obs : nullptr, h->fresh || observe_only, st));
     h->launches++;
-    h->fresh = false;
+    if (!observe_only) h->fresh = false;
     if (obs_host && D) CU(cudaMemcpyAsync(h->h_obs, h->d_obs, N * D * sizeof(float), cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     if (obs_host && D && obs_host != h->h_obs) memcpy(obs_host, h->h_obs, N * D * sizeof(float));

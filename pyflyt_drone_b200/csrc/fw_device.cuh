@@ -148,7 +148,8 @@ struct FwPlanes {
     float4* w1;   // gust amp xyz, -
     float* targets;  // [T][3][N]
     float* ep_ret;   // [N]
-    double* stats;   // [8] global episode accumulators
+    double* stats;   // [16] global accumulators: [0..7] episode statistics (fw_episode_stats), [8] non-finite-state resets
+    uint8_t* tidx_out;  // [N] info["num_targets_reached"] of the step just taken (before any auto-reset); may be host-mapped
     // ObjLock task only
     float4* dk;      // duck xyz
     float4* v0;      // last_cx, last_cy, last_area, last_depth
@@ -737,6 +738,16 @@ __device__ __forceinline__ void fw_reset_env(const FwDev& p, const FwPlanes& pl,
     if (p.task != 0) fw_sample_targets(p, pl, i, gid, episode);
     fw_warm(p, e, w0, w1, p.warmup_substeps, true);
     fw_reset_finish(p, pl, e, i);
+}
+
+// Non-finite-state guard (failure detection): true when every state float is finite.  The reference
+// swallows simulator exceptions (fixedwing_waypoint_objlock_env.py:401,449,502) and has no such check; here a poisoned
+// env is flagged (FW_FLAG_FAULT), counted in stats[8] and force-reset instead of spreading NaNs into the running
+// observation moments of the PPO loop.  One add chain + one compare per agent step.
+__device__ __forceinline__ bool fw_state_finite(const EnvState& e) {
+    float s = ((e.px + e.py) + (e.pz + e.qx)) + ((e.qy + e.qz) + (e.qw + e.vx)) + ((e.vy + e.vz) + (e.wx + e.wy)) +
+              ((e.wz + e.thr) + (e.act[0] + e.act[1])) + ((e.act[2] + e.act[3]) + e.act[4]);
+    return fabsf(s) < 3.0e38f;            // false for NaN and +-inf
 }
 
 __device__ __forceinline__ void fw_load(const FwPlanes& pl, int i, EnvState& e) {

@@ -12,8 +12,11 @@
 // demands is staged per warp in shared memory and written with ONE bulk async copy
 // (cp.async.bulk.global.shared::cta -> SASS UBLKCP) of 32*obs_dim*4 contiguous bytes, instead of 32 strided
 // row stores.  Aircraft/task constants arrive as a __grid_constant__ kernel parameter, i.e. in the constant
-// bank: every FFMA reads them as a c[][] operand with no load instruction (all threads use the same address,
-// which is the case the constant cache is built for; shared-memory staging would add an LDS per use).
+// bank.  On sm_100a an FP instruction cannot name a c[][] operand any more: each constant reaches the pipe through a
+// uniform register filled by an LDCU (ncu: 720 LDCU among the 7,161 warp-instructions of an env-step before packing),
+// so the constants of the hot substep are stored as 16-byte groups in order of use (FwDev::hot / rbk) and fetched with
+// LDCU.128.  All threads use the same address, which is the case the constant cache is built for; shared-memory
+// staging would cost an LDS per use instead.
 #include "fw_device.cuh"
 #include "fw_objlock.cuh"
 #include "fw_kernels.h"
@@ -61,7 +64,7 @@ template <int TASK, bool STD>
 __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl, EnvState& e, int i,
                                              uint32_t gid, float a0, float a1, float a2, float a3, const float4& w0_in,
                                              const float4& w1_in, float& ep_ret, float* row, float* term_obs_row,
-                                             uint32_t& bits) {
+                                             uint32_t& bits, int& tidx_info) {
     float4 w0 = w0_in, w1 = w1_in;
     // FixedwingBaseEnv.step: reward reset once, thrust remapped to [0,1], setpoint latched
     float reward = -0.1f;
@@ -120,13 +123,17 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
     }
     e.step_count += 1;
     if (TASK == 1) complete = e.tidx >= p.num_targets;     // info["env_complete"] is sticky within an episode
+    tidx_info = e.tidx;                                    // info["num_targets_reached"], before any auto-reset
+    const bool fault = !fw_state_finite(e);                // poisoned state: terminate without reward, count, reset
+    if (fault) { term = true; reward = 0.0f; }
 
     const bool done = term || trunc;
     if (TASK != 0 && row != nullptr) fw_write_obs(p, pl, e, i, obs_tidx, a0, a1, a2, a3, row);
     ep_ret += reward;
     if (done) {
-        if (TASK != 0 && term_obs_row != nullptr)
+        if (TASK != 0 && term_obs_row != nullptr && !fault)
             for (int k = 0; k < p.obs_dim; ++k) term_obs_row[k] = row[k];
+        if (fault) atomicAdd(&pl.stats[8], 1.0);
         atomicAdd(&pl.stats[0], 1.0);
         atomicAdd(&pl.stats[1], (double)ep_ret);
         atomicAdd(&pl.stats[2], (double)e.step_count);
@@ -138,9 +145,11 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
         fw_reset_env(p, pl, e, i, gid, e.episode + 1u);
         if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
         if (TASK != 0 && row != nullptr) fw_write_obs(p, pl, e, i, 0, 0.f, 0.f, 0.f, 0.f, row);
+        if (fault && TASK != 0 && term_obs_row != nullptr)     // a finite stand-in: the first observation of the new episode
+            for (int k = 0; k < p.obs_dim; ++k) term_obs_row[k] = row[k];
         ep_ret = 0.0f;
     }
-    bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (col ? 4u : 0u) | (oob ? 8u : 0u) | (complete ? 16u : 0u);
+    bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (col ? 4u : 0u) | (oob ? 8u : 0u) | (complete ? 16u : 0u) | (fault ? 64u : 0u);
     return reward;
 }
 
@@ -181,10 +190,13 @@ __device__ __forceinline__ float fw_env_step_lowlevel(const FwDev& p, const FwPl
     bool term = false, oob = false;
     if (e.pz < 1.0f || e.pz > 100.0f) { term = true; oob = true; reward -= 100.0f; }
     const bool trunc = e.step_count >= p.max_steps;
+    const bool fault = !fw_state_finite(e);
+    if (fault) { term = true; oob = false; reward = 0.0f; }
     ep_ret += reward;
     if (term || trunc) {
-        if (term_obs_row != nullptr && row != nullptr)
+        if (term_obs_row != nullptr && row != nullptr && !fault)
             for (int k = 0; k < p.obs_dim; ++k) term_obs_row[k] = row[k];
+        if (fault) atomicAdd(&pl.stats[8], 1.0);
         atomicAdd(&pl.stats[0], 1.0);
         atomicAdd(&pl.stats[1], (double)ep_ret);
         atomicAdd(&pl.stats[2], (double)e.step_count);
@@ -193,10 +205,12 @@ __device__ __forceinline__ float fw_env_step_lowlevel(const FwDev& p, const FwPl
         if (row != nullptr) {
             const float z6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             fw_write_obs_lowlevel(pl, e, i, p.n, z6, row, yaw, speed, tref);
+            if (fault && term_obs_row != nullptr)
+                for (int k = 0; k < p.obs_dim; ++k) term_obs_row[k] = row[k];
         }
         ep_ret = 0.0f;
     }
-    bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (oob ? 8u : 0u);
+    bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (oob ? 8u : 0u) | (fault ? 64u : 0u);
     return reward;
 }
 
@@ -224,6 +238,7 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
         float ep_ret = pl.ep_ret[i];
         float reward = 0.f;
         uint32_t bits = 0u;
+        int tidx_info = 0;
         if (TASK == 3) {
             float* orow = obs != nullptr ? stage_warp + (size_t)lane * D : nullptr;
             const int nst = RANDOM_ACT ? spl : 1;
@@ -251,18 +266,19 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
                 float a2 = 2.0f * fw_u01(r.z) - 1.0f, a3 = 2.0f * fw_u01(r.w) - 1.0f;
                 if (p.wind_mode != 0 && st > 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
                 reward = fw_env_step<TASK, STD>(p, pl, e, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
-                                           st == spl - 1 ? row : nullptr, nullptr, bits);
+                                           st == spl - 1 ? row : nullptr, nullptr, bits, tidx_info);
             }
         } else {
             float4 a = act[i];
             reward = fw_env_step<TASK, STD>(p, pl, e, i, gid, a.x, a.y, a.z, a.w, w0, w1, ep_ret, row,
                                        (TASK != 0 && term_obs != nullptr && row != nullptr) ? term_obs + (size_t)i * D : nullptr,
-                                       bits);
+                                       bits, tidx_info);
         }
         pl.ep_ret[i] = ep_ret;
         fw_store(pl, i, e);
         if (rew != nullptr) rew[i] = reward;
         if (flg != nullptr) flg[i] = (uint8_t)bits;
+        if (TASK == 1 && !RANDOM_ACT && pl.tidx_out != nullptr) pl.tidx_out[i] = (uint8_t)tidx_info;
     }
     if (TASK != 0 && obs != nullptr) {
         const int first_env = p.i_begin + blockIdx.x * FW_BLOCK + warp * 32;
@@ -355,7 +371,7 @@ template <int TASK, bool STD>
 __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPlanes& pl, bool active, EnvState& e, OlState& ol,
                                                      float* so, float* depth_row, float* hs, int i, uint32_t gid, float a0, float a1,
                                                      float a2, float a3, float4& w0, float4& w1, float& ep_ret, float* row,
-                                                     float* term_obs_row, uint32_t& bits) {
+                                                     float* term_obs_row, uint32_t& bits, int& tidx_info) {
     const int tid = threadIdx.x;
     float reward = -0.1f;
     bool term = false, trunc = false, col = false, oob = false, complete = false, strike = false;
@@ -448,13 +464,17 @@ __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPla
         }
     }
     if (active) e.step_count += 1;
+    tidx_info = e.tidx;                                    // info["num_targets_reached"], before any auto-reset
+    const bool fault = active && !fw_state_finite(e);      // poisoned state: terminate without reward, count, reset
+    if (fault) { term = true; reward = 0.0f; }
     const bool done = active && (term || trunc);
     if (active && row != nullptr) ol_write_obs<TASK>(p, pl, e, ol, hs, i, obs_tidx, a0, a1, a2, a3, row, tid);
     if (active) ep_ret += reward;
     if (__any_sync(0xffffffffu, done)) {
         if (done) {
-            if (term_obs_row != nullptr)
+            if (term_obs_row != nullptr && !fault)
                 for (int k = 0; k < p.obs_dim; ++k) term_obs_row[k] = row[k];
+            if (fault) atomicAdd(&pl.stats[8], 1.0);
             atomicAdd(&pl.stats[0], 1.0);
             atomicAdd(&pl.stats[1], (double)ep_ret);
             atomicAdd(&pl.stats[2], (double)e.step_count);
@@ -469,10 +489,13 @@ __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPla
         if (done) {
             if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
             if (row != nullptr) ol_write_obs<TASK>(p, pl, e, ol, hs, i, 0, 0.f, 0.f, 0.f, 0.f, row, tid);
+            if (fault && term_obs_row != nullptr && row != nullptr)
+                for (int k = 0; k < p.obs_dim; ++k) term_obs_row[k] = row[k];
             ep_ret = 0.0f;
         }
     }
-    bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (col ? 4u : 0u) | (oob ? 8u : 0u) | (complete ? 16u : 0u) | (strike ? 32u : 0u);
+    bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (col ? 4u : 0u) | (oob ? 8u : 0u) | (complete ? 16u : 0u) | (strike ? 32u : 0u) |
+           (fault ? 64u : 0u);
     return reward;
 }
 
@@ -507,6 +530,7 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
     float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
     float ep_ret = 0.f, reward = 0.f;
     uint32_t bits = 0u;
+    int tidx_info = 0;
     if (active) {
         fw_load(pl, i, e);
         ol_load(pl, i, ol);
@@ -532,7 +556,7 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
         reward = fw_env_step_objlock<TASK, STD>(p, pl, active, e, ol, so, depth_row, hs, i, gid, a0, a1, a2, a3, w0, w1, ep_ret,
                                      (st == nsteps - 1) ? row : nullptr,
                                      (!RANDOM_ACT && term_obs != nullptr && row != nullptr && active) ? term_obs + (size_t)i * D : nullptr,
-                                     bits);
+                                     bits, tidx_info);
     }
     if (active) {
         pl.ep_ret[i] = ep_ret;
@@ -541,6 +565,7 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
         if (TASK == 4) ol_hist_store(p, pl, i, hs, threadIdx.x, FW_BLOCK);
         if (rew != nullptr) rew[i] = reward;
         if (flg != nullptr) flg[i] = (uint8_t)bits;
+        if (TASK == 2 && !RANDOM_ACT && pl.tidx_out != nullptr) pl.tidx_out[i] = (uint8_t)tidx_info;
     }
     if (obs != nullptr) {
         const int first_env = p.i_begin + blockIdx.x * FW_BLOCK + warp * 32;

@@ -199,13 +199,18 @@ class FixedwingWaypointsEnv:
         self._vec.close()
         self._vec = FixedwingVecEnv(1, config=self.cfg, device=self._device, seed=self._seed0)
         self._needs_reset = True
+        self._auto_reset_done = False
 
     def reset(self, *, seed: int | None = None, options: dict | None = None) -> tuple[dict, dict]:
         if seed is not None:
             self._seed0 = int(seed)
             self.np_random = np.random.default_rng(self._seed0)
-            self._vec.seed(self._seed0)
-        flat = self._vec.reset()[0]
+            self._vec.seed(self._seed0)                  # always rebuilds: reset(seed=s) is reproducible
+            self._auto_reset_done = False
+        # after a finished episode the device batch has already opened the next one (SubprocVecEnv semantics): hand out
+        # its first observation instead of discarding a whole episode (and, for ObjLock, its warm-up and camera frame)
+        flat = self._vec.observe()[0] if getattr(self, "_auto_reset_done", False) else self._vec.reset()[0]
+        self._auto_reset_done = False
         self._cache = None
         self.step_count, self.termination, self.truncation = 0, False, False
         self.action = np.zeros(4)
@@ -236,9 +241,9 @@ class FixedwingWaypointsEnv:
         if done:
             # the device batch has already auto-reset (SubprocVecEnv semantics); hand back the terminal observation
             self.state = self._obs_dict(term[0].copy(), terminal=True)
-            if f & FLAG_COMPLETE and self.task == "waypoints":
-                self.info["num_targets_reached"] = self.cfg.num_targets
+            self.info["num_targets_reached"] = int(self._vec.last_targets_reached[0])
             self._needs_reset = True
+            self._auto_reset_done = True
         else:
             self.info["num_targets_reached"] = max(pre_idx, self.waypoints.num_targets_reached)
             self.state = self._obs_dict(obs[0].copy(), terminal=False)

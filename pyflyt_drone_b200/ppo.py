@@ -465,56 +465,72 @@ class PPO:
 
     # ------------------------------------------------------------------ inference / checkpoint
     def predict(self, obs_raw: torch.Tensor, deterministic: bool = True) -> torch.Tensor:
+        """Actions for raw (un-normalised) observations.  Stochastic predictions draw fresh Philox noise on every call
+        (a call counter is the step index of the draw; the key is offset from the training stream's)."""
         obs_raw = obs_raw.to(self.device, torch.float32).contiguous()
         n = obs_raw.shape[0]
         act = torch.zeros((n, self.a), dtype=torch.float32, device=self.device)
         val = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self._predict_calls = getattr(self, "_predict_calls", 0) + 1
         _lib.check(self.lib.ppo_policy_forward_a(_p(self.policy.theta), self.d, self.a, _p(obs_raw), self._stats_ptr(),
-                                                 self.vecnorm.clip_obs, n, self.seed, 0, 0, _p(self._step_dev),
+                                                 self.vecnorm.clip_obs, n, (self.seed ^ 0x5BD1E995) & (2 ** 63 - 1), 0,
+                                                 self._predict_calls & 0x3FFFFFFF, _p(self._step_dev),
                                                  int(deterministic), None, _p(act), None, None, _p(val), _stream()))
         return act
+
+    @staticmethod
+    def episode_quotas(n_eval_episodes: int, n_envs: int) -> list[int]:
+        """How many episodes each env contributes, as stable_baselines3.common.evaluation.evaluate_policy divides them:
+        ``(n_eval_episodes + i) // n_envs`` for env ``i``.  Counting only up to the quota keeps fast-failing envs (a crash
+        takes ~100 steps, a full flight 3,600) from filling the sample with short, bad episodes."""
+        return [(int(n_eval_episodes) + i) // int(n_envs) for i in range(int(n_envs))]
 
     def evaluate_policy(self, env=None, n_eval_episodes: int = 100, deterministic: bool = True, max_steps: int | None = None):
         """stable_baselines3.common.evaluation.evaluate_policy as the reference uses it (eval/eval_waypoints.py:96-160,
         WaypointEvalCallback in train_Fixedwing_Waypoints_v3.py:163-172): frozen VecNormalize statistics, raw (un-normalised)
-        rewards, deterministic actions by default.  Runs every env of ``env`` (default: the training env's configuration
-        on a fresh batch) on the device until ``n_eval_episodes`` episodes have finished; returns
-        ``(mean_reward, std_reward, mean_length, mean_targets_reached)`` over the first episodes to finish."""
+        rewards, deterministic actions by default, and SB3's per-env episode quotas (``episode_quotas``).  Runs on the device
+        until every env of ``env`` (default: the training env's configuration on a fresh batch of at most
+        ``n_eval_episodes`` envs) has delivered its quota; returns ``(mean_reward, std_reward, mean_length,
+        mean_targets_reached)`` -- all four over the same selected episodes."""
         from .vec_env import FixedwingVecEnv
         own = env is None
         if own:
-            n = min(self.n_envs, max(64, int(n_eval_episodes)))
+            n = max(1, min(self.n_envs, int(n_eval_episodes)))
             env = FixedwingVecEnv(n, config=self.env.cfg, device=self.env.device_index, seed=self.seed + 7919,
                                   env_id0=self.env.env_id0 + (1 << 24))
         obs = env.reset_tensor()
         n = env.num_envs
+        quota = torch.tensor(self.episode_quotas(n_eval_episodes, n), dtype=torch.int64, device=self.device)
+        count = torch.zeros(n, dtype=torch.int64, device=self.device)
         ret = torch.zeros(n, dtype=torch.float64, device=self.device)
         length = torch.zeros(n, dtype=torch.int64, device=self.device)
-        done_ret, done_len = [], []
-        have = 0
-        limit = max_steps if max_steps is not None else 4 * int(env.cfg.max_steps) + 8
+        has_targets = env.cfg.task in (1, 2)
+        done_ret, done_len, done_tr = [], [], []
+        # every env needs at most quota episodes of at most max_steps + 2 steps
+        limit = max_steps if max_steps is not None else (int(quota.max()) * (int(env.cfg.max_steps) + 2) + 8)
         for _ in range(limit):
             act = self.predict(obs, deterministic=deterministic)
             obs, rew, flags = env.step_tensor(act)
             ret += rew.double()
             length += 1
             fin = (flags & 3) != 0
-            k = int(fin.sum())
-            if k:
-                done_ret.append(ret[fin].clone()); done_len.append(length[fin].clone())
-                ret[fin] = 0.0; length[fin] = 0
-                have += k
-                if have >= n_eval_episodes:
-                    break
-        stats = env.episode_stats()
+            take = fin & (count < quota)
+            if bool(take.any()):
+                done_ret.append(ret[take].clone()); done_len.append(length[take].clone())
+                if has_targets:
+                    done_tr.append(env.targets_reached_tensor()[take].double())
+                count += take.to(torch.int64)
+            ret[fin] = 0.0; length[fin] = 0
+            if bool((count >= quota).all()):
+                break
         if own:
             env.close()
         if not done_ret:
             return float("nan"), float("nan"), float("nan"), float("nan")
-        r = torch.cat(done_ret)[:n_eval_episodes]
-        ln = torch.cat(done_len)[:n_eval_episodes].double()
-        targets = stats["targets_reached_sum"] / max(stats["episodes"], 1.0)
-        return float(r.mean()), float(r.std(unbiased=False)), float(ln.mean()), float(targets)
+        r = torch.cat(done_ret)
+        ln = torch.cat(done_len).double()
+        targets = float(torch.cat(done_tr).mean()) if done_tr else 0.0
+        return float(r.mean()), float(r.std(unbiased=False)), float(ln.mean()), targets
 
     def save(self, path: str) -> None:
         torch.save({"policy": self.policy.state_dict(), "optimizer": self.optimizer.state_dict(),

@@ -21,7 +21,8 @@ import numpy as np
 
 from . import _lib
 from .compat import spaces
-from .config import (EnvConfig, FLAG_COLLISION, FLAG_COMPLETE, FLAG_OOB, FLAG_STRIKE, FLAG_TERM, FLAG_TRUNC,
+from .compat.vec_env import VecEnv
+from .config import (EnvConfig, FLAG_COLLISION, FLAG_COMPLETE, FLAG_FAULT, FLAG_OOB, FLAG_STRIKE, FLAG_TERM, FLAG_TRUNC,
                      make_config)
 
 _STATE_FIELDS = {
@@ -38,8 +39,12 @@ _OBJLOCK_FIELDS = ("duck", "obst", "ol_f", "ol_i")
 _DUCK_FIELDS = ("vis_hist",)
 
 
-class FixedwingVecEnv:
-    """``num_envs`` fixed-wing environments stepped by one CUDA kernel launch per agent step."""
+class FixedwingVecEnv(VecEnv):
+    """``num_envs`` fixed-wing environments stepped by one CUDA kernel launch per agent step.
+
+    Derives from ``stable_baselines3.common.vec_env.VecEnv`` when SB3 is importable (compat.vec_env keeps a stand-in of
+    the same shape otherwise), so ``VecNormalize(env)``, ``PPO("MlpPolicy", env)`` and ``evaluate_policy(model, env,
+    callback=...)`` of the reference's scripts take it as they take a ``SubprocVecEnv``."""
 
     metadata = {"render_modes": []}
 
@@ -60,6 +65,8 @@ class FixedwingVecEnv:
             raise ValueError("info_mode must be 'auto', 'full' or 'lazy'")
         self.info_mode = info_mode
         self._open()
+        VecEnv.__init__(self, self.num_envs, self.observation_space, self.action_space)
+        self._user_attrs: dict[str, list] = {}     # set_attr() storage (per-env Python-side attributes)
         self._pending: np.ndarray | None = None
         self._t = None  # lazily created torch buffers for the tensor lane
         self._closed = False
@@ -88,10 +95,19 @@ class FixedwingVecEnv:
         self._h_rew = view(ptrs[2], (self.num_envs,), C.c_float, np.float32)
         self._h_flags = view(ptrs[3], (self.num_envs,), C.c_uint8, np.uint8)
         self._h_term = view(ptrs[4], (self.num_envs, D), C.c_float, np.float32)
+        tp = C.c_void_p()
+        _lib.check(self.lib.fw_host_info_buffer(self._h, C.byref(tp)))
+        self._h_tidx = view(tp, (self.num_envs,), C.c_uint8, np.uint8)      # info["num_targets_reached"], pre-reset
 
     # ------------------------------------------------------------------ SB3 VecEnv (host NumPy lane)
     def reset(self) -> np.ndarray:
         _lib.check(self.lib.fw_reset_host(self._h, self._h_obs.ctypes.data_as(C.c_void_p)))
+        self.reset_infos = [{} for _ in range(self.num_envs)]
+        return self._h_obs[:, : self.obs_dim].copy()
+
+    def observe(self) -> np.ndarray:
+        """Observation of the current state of every env, nothing reset (see fw_observe_host)."""
+        _lib.check(self.lib.fw_observe_host(self._h, self._h_obs.ctypes.data_as(C.c_void_p)))
         return self._h_obs[:, : self.obs_dim].copy()
 
     def step_async(self, actions: np.ndarray) -> None:
@@ -144,28 +160,48 @@ class FixedwingVecEnv:
             d["duck_strike"] = bool(f & FLAG_STRIKE)
         if self.cfg.task == 4:
             d["is_success"] = bool(f & FLAG_STRIKE)          # fixedwing_objlock_env.py:235,372
+        if f & FLAG_FAULT:
+            d["state_fault"] = True                          # non-finite state: force-reset by the kernel (no reference key)
         return d
 
     def _make_infos(self, flags: np.ndarray, dones: np.ndarray, term: np.ndarray) -> list[dict]:
+        """The info dicts of the reference env (fixedwing_base_env.py:212-215; fixedwing_waypoint_objlock_env.py:296,
+        336-337).  ``num_targets_reached`` is the value the env held BEFORE the auto-reset of a finished episode -- the
+        one WaypointEvalCallback._log_success_callback reads on every done (train_Fixedwing_Waypoints_v3.py:136-138).
+        ``info_mode="lazy"`` (default above 4,096 envs) builds full dicts for finished envs only; the others share one
+        blank dict, and the per-env values stay available as arrays (``last_flags``, ``last_targets_reached``)."""
+        has_t = self.cfg.task in (1, 2)
+        tr = self._h_tidx
         idx = np.nonzero(dones)[0]
         if self.info_mode == "lazy":
-            blank = self._info_of(0, None)
+            blank = self._info_of(0, None)                       # no per-env value in the shared dict: the key is absent
             infos: list[dict] = [blank] * self.num_envs
         else:
-            infos = [self._info_of(int(f), None) for f in flags]
+            infos = [self._info_of(int(f), int(t) if has_t else None) for f, t in zip(flags, tr)]
         for i in idx:
             f = int(flags[i])
-            d = self._info_of(f, None)
+            d = self._info_of(f, int(tr[i]) if has_t else None)
             d["terminal_observation"] = term[i].copy()
             d["TimeLimit.truncated"] = bool(f & FLAG_TRUNC) and not bool(f & FLAG_TERM)
             infos[i] = d
         return infos
 
+    @property
+    def last_flags(self) -> np.ndarray:
+        """Flag bytes of the last host-lane step (view of pinned memory, valid until the next step)."""
+        return self._h_flags
+
+    @property
+    def last_targets_reached(self) -> np.ndarray:
+        """``info["num_targets_reached"]`` of the last host-lane step for every env, taken before any auto-reset."""
+        return self._h_tidx
+
     def close(self) -> None:
         if not self._closed and self._h:
-            self._h_act = self._h_obs = self._h_rew = self._h_flags = self._h_term = None   # views die with the handle
+            self._h_act = self._h_obs = self._h_rew = self._h_flags = self._h_term = self._h_tidx = None   # views die with the handle
             self.lib.fw_destroy(self._h)
             self._h = C.c_void_p()
+            self._t = None
             self._closed = True
 
     def __del__(self):
@@ -175,10 +211,13 @@ class FixedwingVecEnv:
             pass
 
     def seed(self, seed: int | None = None) -> list[int | None]:
-        """SB3 API parity.  The Philox key is fixed at construction; re-seeding rebuilds the batch."""
-        if seed is not None and int(seed) != self._seed:
+        """SB3 ``VecEnv.seed``: env ``i`` gets ``seed + i``.  The Philox key is fixed per batch, so passing a seed
+        ALWAYS rebuilds the batch -- also when it equals the current one, which makes ``seed(s); reset()`` reproduce
+        the same first episode every time (the gymnasium ``reset(seed=s)`` contract the reference's eval scripts use)."""
+        if seed is not None:
             self._seed = int(seed)
-            self._h_act = self._h_obs = self._h_rew = self._h_flags = self._h_term = None
+            self._h_act = self._h_obs = self._h_rew = self._h_flags = self._h_term = self._h_tidx = None
+            self._t = None
             self.lib.fw_destroy(self._h)
             self._open()
         return [self._seed + self.env_id0 + i for i in range(self.num_envs)]
@@ -190,18 +229,47 @@ class FixedwingVecEnv:
             return [indices]
         return indices
 
+    # Python-level per-env attributes / methods (SB3 reaches the sub-envs of a SubprocVecEnv with these).  The batch has
+    # no sub-env objects: attributes are the VecEnv's own, then the shared EnvConfig, then whatever set_attr stored;
+    # env_method calls the VecEnv's batched method of that name once and hands every selected env the same result.
     def get_attr(self, attr_name: str, indices=None) -> list[Any]:
-        val = getattr(self, attr_name) if hasattr(self, attr_name) else getattr(self.cfg, attr_name)
-        return [val for _ in self._indices(indices)]
+        idx = self._indices(indices)
+        if attr_name in self._user_attrs:
+            return [self._user_attrs[attr_name][i] for i in idx]
+        if attr_name == "render_mode":
+            return [None for _ in idx]
+        if hasattr(self, attr_name):
+            val = getattr(self, attr_name)
+        elif hasattr(self.cfg, attr_name):
+            val = getattr(self.cfg, attr_name)
+        else:
+            raise AttributeError(f"FixedwingVecEnv envs have no attribute {attr_name!r}")
+        return [val for _ in idx]
 
     def set_attr(self, attr_name: str, value: Any, indices=None) -> None:
-        raise NotImplementedError("per-env attributes are compiled into the batch config; rebuild the VecEnv")
+        """Stores a Python-side attribute per env (returned by ``get_attr``).  Fields of the compiled batch
+        configuration cannot change under a live batch: build a new ``FixedwingVecEnv`` for that."""
+        if hasattr(self.cfg, attr_name):
+            raise AttributeError(f"{attr_name!r} is part of the compiled batch configuration (EnvConfig); "
+                                 "build a new FixedwingVecEnv with that override instead of set_attr")
+        slot = self._user_attrs.setdefault(attr_name, [None] * self.num_envs)
+        for i in self._indices(indices):
+            slot[i] = value
 
     def env_method(self, method_name: str, *args, indices=None, **kwargs) -> list[Any]:
-        raise NotImplementedError(f"env_method({method_name!r}) has no batched counterpart")
+        fn = getattr(self, method_name, None)
+        if method_name.startswith("_") or not callable(fn) or method_name in ("reset", "step", "step_async", "step_wait",
+                                                                              "close", "seed", "env_method"):
+            raise AttributeError(f"FixedwingVecEnv envs have no per-env method {method_name!r} (a batch is stepped and "
+                                 "reset as a whole; use reset()/step() or the *_tensor lane)")
+        out = fn(*args, **kwargs)
+        return [out for _ in self._indices(indices)]
 
     def env_is_wrapped(self, wrapper_class, indices=None) -> list[bool]:
         return [False for _ in self._indices(indices)]
+
+    def get_images(self):
+        raise NotImplementedError("rendered frames are out of scope (DESIGN.md section 9)")
 
     # ------------------------------------------------------------------ device-tensor lane (B1')
     def _tensors(self):
@@ -214,6 +282,7 @@ class FixedwingVecEnv:
                 rew=torch.zeros(self.num_envs, dtype=torch.float32, device=dev),
                 flags=torch.zeros(self.num_envs, dtype=torch.uint8, device=dev),
                 term=torch.zeros((self.num_envs, D), dtype=torch.float32, device=dev),
+                tidx=torch.zeros(self.num_envs, dtype=torch.uint8, device=dev),
             )
         return self._t
 
@@ -242,6 +311,19 @@ class FixedwingVecEnv:
         if want_terminal_obs:
             return t["obs"][:, : self.obs_dim], t["rew"], t["flags"], t["term"][:, : self.obs_dim]
         return t["obs"][:, : self.obs_dim], t["rew"], t["flags"]
+
+    def targets_reached_tensor(self):
+        """Device lane: ``info["num_targets_reached"]`` of the last ``step_tensor`` for every env (uint8 CUDA tensor,
+        pre-reset values; an asynchronous copy on the current stream)."""
+        t = self._tensors()
+        _lib.check(self.lib.fw_targets_reached(self._h, C.c_void_p(t["tidx"].data_ptr()), C.c_void_p(self._stream())))
+        return t["tidx"]
+
+    def fault_count(self) -> int:
+        """Envs force-reset so far because their state went non-finite (FLAG_FAULT)."""
+        out = C.c_int64(0)
+        _lib.check(self.lib.fw_fault_count(self._h, C.byref(out)))
+        return int(out.value)
 
     def step_random(self, n_steps: int = 1, with_outputs: bool = False):
         """Random-action workload (BASELINE config 2): actions drawn in-kernel, one launch per env-step."""
