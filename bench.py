@@ -1,31 +1,39 @@
 #!/usr/bin/env python
-"""bench.py -- fixed-wing env-steps/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+"""bench.py -- fixed-wing env-steps/sec on B200 (BASELINE.json metric) + PPO SPS, one JSON line on stdout.
 
-Our arm (default):
-  a "step" is ONE launch of the fused env-step kernel over one batch of `--envs` environments per GPU
-  (default 65,536 = BASELINE configs[1], "batched fixed-wing physics step only, random actions"):
-  8 physics substeps at 240 Hz per env, actions drawn in-kernel from Philox, motor noise on,
-  auto-reset on ground/dome.  `value` = envs * K * n_gpus / device time (CUDA events on the launching
-  stream, barrier + synchronize on both sides, MAX over ranks).
-  L2 hygiene: the per-batch state (~7 MB) would sit in the 126 MB L2 between launches, so the timed loop
-  rotates over enough independent env batches that the working set exceeds 2x L2 ("l2" in config).
-  `e2e` = the same metric through the reference-facing host call: FixedwingVecEnv.step_arrays(actions)
-  (the VecEnv.step seam; C ABI fw_step_host) on the Fixedwing-Waypoints-v3 task with HOST buffers:
-  H2D of the actions and D2H of obs/reward/flags inside the timed region.
-  `roofline`   : dominant kernel fw_step_kernel; algorithmic bytes (152 B/env-step physics-only)
-                 over its mean launch duration against the measured HBM peak, plus the FP32-pipe view that
-                 actually binds it (6,400 flop/env-step against a live-measured FMA-chain peak).
-  `cpu_baseline`: the fp64 oracle (kind "port") on the host cores, bounded sample, rank 0 at N=1 only.
+Our arm (default)
+  step      ONE launch of the fused env-step kernel over one batch of `--envs` environments per GPU (default 65,536 =
+            BASELINE configs[1], "batched fixed-wing physics step only, random actions"): 8 physics substeps at 240 Hz per
+            env, actions drawn in-kernel from Philox, motor noise on, auto-reset on ground/dome.
+  value     envs * n_gpus / (device time of one step).  A timed REGION is the K-launch CUDA graph sequence replayed R times
+            so that it lasts >= 50 ms on the device (`timed_launches` = R*K per region); 5 regions, median; CUDA events are
+            recorded in the enqueue order behind a warm launch, so host launch latency is outside the region; MAX over
+            ranks.  (K = 20 launches alone are 0.4 ms -- a window in which host jitter, not the GPU, sets the number.)
+  L2        the per-batch state (~7 MB) would sit in the 126 MB L2 between launches, so the loop rotates over enough
+            independent env batches that the working set exceeds 2x L2 ("l2" in config).
+  e2e       the same metric through the reference-facing host call FixedwingVecEnv.step_arrays(actions) (VecEnv.step seam;
+            C ABI fw_step_host) on the Fixedwing-Waypoints-v3 task with HOST buffers: H2D of the actions and D2H of
+            obs/reward/flags inside the timed region (wall clock, >= 50 ms regions, median of 5).
+  roofline  dominant kernel fw_step_kernel.  `bound` names the pipe that binds it -- FP32 issue (6,400 flop per
+            physics env-step against an FMA-chain peak measured in the same run); the HBM view (152 algorithmic bytes per
+            env-step against MEASURED_PEAKS.json) rides along as `roofline.hbm`.
+  ppo       PPO SPS (the second half of BASELINE's metric), rank-parallel with the NCCL gradient all-reduce INSIDE the timed
+            region: configs[2] at 4,096 envs/GPU -- variant B (n_steps 128, 4 minibatches/epoch) and the SB3-faithful variant
+            A (n_steps 2048, batch 128: 65,536 optimiser steps per epoch) -- and configs[3], Waypoint-ObjLock at 65,536
+            envs/GPU, n_steps 64.
+  cpu_baseline  the fp64 oracle (kind "port") on the host cores, bounded sample, rank 0 at N=1 only.
 
-Reference arm (--impl reference): the reference's CPU path for this metric.  PyFlyt/pybullet cannot be
-installed offline and the reference has no compilable sources, so this times the oracle port of the same
-semantics on ALL host cores (bounded sample per step); rank 0 only under torchrun.
+Reference arm (--impl reference): the reference's CPU path.  PyFlyt/pybullet/SB3 cannot be installed offline and the
+reference has no compilable sources, so this times the oracle port (all host threads) on the workload of our arm's `e2e`
+-- Fixedwing-Waypoints-v3 stepped through host buffers -- plus the physics-only rate and a CPU PPO (oracle VecEnv + fp32
+torch-CPU PPO, same hyper-parameters, bounded samples); rank 0 only under torchrun.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import statistics
 import subprocess
 import sys
 import threading
@@ -42,25 +50,35 @@ UNIT = "env-steps/s"
 BYTES_PER_STEP = {"physics_only": 152, "waypoints_v3": 332, "waypoint_objlock": 400, "lowlevel": 276, "objlock_duck": 836}
 FLOPS_PER_STEP = {"physics_only": 6400, "waypoints_v3": 7000, "waypoint_objlock": 7000, "lowlevel": 1750, "objlock_duck": 7000}
 L2_BYTES = 126 * 1024 * 1024
+REGION_MS = 50.0          # minimum device time of one timed region
+N_REGIONS = 5
+E2E_WORKLOAD = "waypoints_v3"
+# reference's PPO hyper-parameters (train_Fixedwing_Waypoints_v3.py:27-55, train_Fixedwing_Waypoints_ObjLock.py:35-57)
+PPO_HP = dict(learning_rate=3e-4, gamma=0.99, gae_lambda=0.95, clip_range=0.2, ent_coef=0.001, vf_coef=0.5, max_grad_norm=0.5)
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--envs", type=int, default=65536, help="environments per GPU per launch")
     ap.add_argument("--workload", choices=["physics_only", "waypoints_v3", "waypoint_objlock", "lowlevel", "objlock_duck", "ppo"],
                     default="physics_only",
-                    help="ppo = BASELINE configs[2]: PPO Fixedwing-Waypoints rollout+update (a step is one PPO iteration)")
+                    help="ppo = only the PPO measurements (a step is one PPO iteration), as its own JSON line")
     ap.add_argument("--ppo-preset", choices=["waypoints_v3", "waypoint_objlock", "lowlevel", "objlock_duck"], default="waypoints_v3")
     ap.add_argument("--ppo-envs", type=int, default=4096)
     ap.add_argument("--ppo-n-steps", type=int, default=128)
     ap.add_argument("--ppo-minibatches", type=int, default=4)
+    ap.add_argument("--ppo-batch-size", type=int, default=0, help="overrides --ppo-minibatches (SB3-faithful: 128)")
     ap.add_argument("--ppo-epochs", type=int, default=20)
-    ap.add_argument("--e2e-steps", type=int, default=200)
-    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of the CPU baseline sample")
+    ap.add_argument("--ppo-a-epochs", type=int, default=1,
+                    help="variant A (batch 128): epochs of the 20 actually run per timed iteration in the default line; the "
+                         "full-iteration SPS is then projected from the measured epoch time and labelled so")
+    ap.add_argument("--ppo-a-full", action="store_true", help="variant A: run all 20 epochs (about half a minute per iteration)")
+    ap.add_argument("--no-ppo", action="store_true", help="skip the ppo object of the default line")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--steps-per-launch", type=int, default=1,
                     help="env-steps fused into one launch (state kept in registers); a bench step is one launch")
@@ -81,7 +99,7 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """SM clocks / throttle reasons during the timed region (the quantities of the B200_PROFILING.md nvidia-smi recipe,
+    """SM clocks / throttle reasons during the timed regions (the quantities of the B200_PROFILING.md nvidia-smi recipe,
     read through NVML when nvidia_ml_py is importable, else by polling nvidia-smi)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -93,8 +111,6 @@ class ClockSampler(threading.Thread):
         self.index, self.samples, self._stop_evt = index, [], threading.Event()
 
     def _nvml(self):
-        """Fast path: NVML through nvidia_ml_py (sub-millisecond per sample, so a 40 ms timed region still gets tens of
-        samples); None when the module or the device is not available -> nvidia-smi polling."""
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -137,14 +153,6 @@ class ClockSampler(threading.Thread):
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        if not self.samples:
-            # a timed region shorter than one polling interval: read the clocks once, right after it
-            sample = self._nvml()
-            try:
-                if sample is not None:
-                    self.samples.append(sample())
-            except Exception:
-                pass
         sm, mx, reasons = [], [], set()
         for p in self.samples:
             try:
@@ -178,17 +186,29 @@ def cpu_model() -> str:
     return "unknown"
 
 
-def workload_name(workload: str, n: int) -> str:
-    """config.workload, identical for our arm and the reference arm."""
-    if workload == "physics_only":
-        return (f"{workload}: BASELINE configs[1] batched fixed-wing physics step, {n} envs/GPU, in-kernel Philox random "
-                f"actions, motor noise on")
-    return f"{workload}: {n} envs/GPU, random actions"
+def bench_config(args) -> dict:
+    """`config` of the JSON line: a function of the command line only, so that both arms print the same object."""
+    n = args.envs
+    if args.workload == "physics_only":
+        wl = (f"physics_only: BASELINE configs[1] batched fixed-wing physics step, {n} envs/GPU, in-kernel Philox random "
+              f"actions, motor noise on")
+    else:
+        wl = f"{args.workload}: {n} envs/GPU, random actions"
+    return {"workload": wl, "envs_per_gpu": n, "substeps_per_env_step": 2 if args.workload == "lowlevel" else 8,
+            "env_steps_per_launch": max(1, args.steps_per_launch),
+            "e2e_workload": f"{E2E_WORKLOAD}: Fixedwing-Waypoints-v3 stepped through the host-buffer VecEnv.step seam "
+                            f"(actions in host arrays; obs, reward, flags back in host memory), {n} envs/GPU",
+            "reference_workload": "the reference arm times the CPU implementation on e2e_workload (its value and e2e) and "
+                                  "reports the physics-only rate beside it",
+            "ppo_workloads": ["configs[2] waypoints_v3 4096 envs/GPU: variant B n_steps 128 x 4 minibatches, variant A n_steps "
+                              "2048 / batch 128", "configs[3] waypoint_objlock 65536 envs/GPU n_steps 64 x 4 minibatches"],
+            "timing": f">= {REGION_MS:.0f} ms regions (the K-step sequence replayed), median of {N_REGIONS}"}
 
 
+# ----------------------------------------------------------------------------------------------------------- CPU arm
 def oracle_rate(workload: str, threads: int, seconds: float, n_envs: int = 4096):
-    """Time the fp64 oracle (oracle/) on a bounded sample of the same workload: random actions from the
-    same Philox stream, same auto-reset.  Returns (env-steps/s, sample description)."""
+    """Time the fp64 oracle (oracle/) on a bounded sample of the same workload: random actions from the same Philox
+    stream, same auto-reset.  Returns (env-steps/s, sample description)."""
     from oracle import fw_oracle as fo
     import pyflyt_drone_b200 as fw
     cfg = fw.make_config(workload)
@@ -204,40 +224,200 @@ def oracle_rate(workload: str, threads: int, seconds: float, n_envs: int = 4096)
     return done / dt, f"{n_envs} envs x {steps} agent steps ({done} env-steps, {dt:.1f} s, {threads} threads, fp64 oracle port)"
 
 
+def oracle_host_step_rate(workload: str, threads: int, n_envs: int, min_seconds: float, regions: int = 5):
+    """The CPU counterpart of our arm's `e2e`: OracleVecEnv.step(actions) with host arrays in and obs/reward/flags/terminal
+    obs out (the SubprocVecEnv.step contract), random actions prepared beforehand.  Median of `regions` regions of at
+    least `min_seconds` each.  Returns (env-steps/s, steps per region, spread)."""
+    import numpy as np
+    from oracle import fw_oracle as fo
+    import pyflyt_drone_b200 as fw
+    cfg = fw.make_config(workload)
+    env = fo.OracleVecEnv(cfg.as_dict(), n_envs, seed=0, nthreads=threads)
+    env.reset()
+    rng = np.random.default_rng(0)
+    acts = [rng.uniform(-1, 1, (n_envs, env.act_dim)) for _ in range(8)]
+    for s in range(4):                       # page in, spin the thread pool up
+        env.step(acts[s % 8])
+    t0 = time.perf_counter()
+    for s in range(8):
+        env.step(acts[s % 8])
+    per = (time.perf_counter() - t0) / 8
+    steps = max(4, int(np.ceil(min_seconds * 1.1 / max(per, 1e-7))))
+    rates = []
+    for _ in range(regions):
+        t0 = time.perf_counter()
+        for s in range(steps):
+            env.step(acts[s % 8])
+        rates.append(n_envs * steps / (time.perf_counter() - t0))
+    rates.sort()
+    return rates[len(rates) // 2], steps, (rates[-1] - rates[0]) / rates[len(rates) // 2]
+
+
+def cpu_ppo(preset: str, n_envs: int, n_steps: int, batch_size: int, n_epochs: int, threads: int, iters: int = 1,
+            warm: int = 0, epochs_run: int | None = None) -> dict:
+    """CPU PPO SPS on a bounded sample: the fp64 oracle VecEnv on host threads + fp32 torch-CPU PPO with the reference's
+    hyper-parameters (oracle/ppo_cpu.py; stable_baselines3 is not installable here).  epochs_run < n_epochs: only that
+    many epochs of the update are run and the full iteration is projected (every epoch is the same number of identical
+    optimiser steps), exactly as our arm does for variant A."""
+    import torch
+    import pyflyt_drone_b200 as fw
+    from oracle.ppo_cpu import CpuPPO
+    # thread counts that are fastest for the sample at hand: a 128-row minibatch through a 64-wide MLP loses time to
+    # intra-op thread hand-offs, and an env step of a few dozen envs to thread start-up (measured here: 5.8 ms per
+    # optimiser step with 8 torch threads against 3.9 ms with one)
+    torch_threads = threads if batch_size >= 2048 else 1
+    env_threads = max(1, min(threads, n_envs // 16))
+    torch.set_num_threads(torch_threads)
+    hp = dict(PPO_HP)
+    run_epochs = n_epochs if epochs_run is None else min(epochs_run, n_epochs)
+    m = CpuPPO(fw.make_config(preset).as_dict(), n_envs, n_steps, batch_size, run_epochs, lr=hp["learning_rate"], gamma=hp["gamma"],
+               gae_lambda=hp["gae_lambda"], clip_range=hp["clip_range"], ent_coef=hp["ent_coef"], vf_coef=hp["vf_coef"],
+               max_grad_norm=hp["max_grad_norm"], seed=42, nthreads=env_threads)
+    for _ in range(warm):
+        m.iteration()
+    m.rollout_s = m.update_s = 0.0
+    m.samples = 0
+    for _ in range(iters):
+        m.iteration()
+    mb = -(-n_envs * n_steps // batch_size)
+    rollout_s, update_s = m.rollout_s / iters, m.update_s / iters
+    full = rollout_s + update_s * n_epochs / run_epochs
+    out = {"sps": n_envs * n_steps / full, "rollout_s": rollout_s, "update_s": update_s, "envs": n_envs,
+           "n_steps": n_steps, "batch_size": batch_size, "n_epochs": n_epochs, "iterations": iters,
+           "optimizer_steps_per_iteration": run_epochs * mb, "optimizer_step_us": update_s / (run_epochs * mb) * 1e6,
+           "threads": threads, "torch_threads": torch_threads, "env_threads": env_threads,
+           "full_iteration": run_epochs == n_epochs,
+           "kind": "port", "impl": "fp64 oracle VecEnv + fp32 torch-CPU PPO (oracle/ppo_cpu.py)"}
+    if run_epochs < n_epochs:
+        out["epochs_timed"] = run_epochs
+        out["sps_note"] = (f"update timed for {run_epochs} of {n_epochs} epochs; sps = env-steps of one rollout / (rollout_s + "
+                           f"{n_epochs} x epoch_s)")
+    return out
+
+
+def reference_ppo(threads: int) -> dict:
+    """Bounded CPU samples of the three PPO workloads of our arm's `ppo` object (same hyper-parameters; fewer envs: the
+    per-sample cost is what the rate measures)."""
+    out = {}
+    out["waypoints_v3_B"] = cpu_ppo("waypoints_v3", 256, 128, 256 * 128 // 4, 20, threads)
+    out["waypoints_v3_B"]["sample"] = "256 of 4096 envs, n_steps 128, 4 minibatches x 20 epochs, 1 iteration"
+    # the reference's own configuration: 32 envs x 2048 steps, batch 128, 20 epochs (train_Fixedwing_Waypoints_v3.py:28-40)
+    out["waypoints_v3_A"] = cpu_ppo("waypoints_v3", 32, 2048, 128, 20, threads, epochs_run=2)
+    out["waypoints_v3_A"]["sample"] = "32 envs (the reference's num_envs) of 4096, n_steps 2048, batch 128, 2 of 20 epochs timed"
+    out["waypoint_objlock"] = cpu_ppo("waypoint_objlock", 256, 64, 256 * 64 // 4, 20, threads)
+    out["waypoint_objlock"]["sample"] = "256 of 65536 envs, n_steps 64, 4 minibatches x 20 epochs, 1 iteration"
+    return out
+
+
 def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     threads = host_cores()
-    from oracle import fw_oracle as fo
-    import pyflyt_drone_b200 as fw
-    cfg = fw.make_config(args.workload)
-    n_envs = 4096
-    env = fo.OracleVecEnv(cfg.as_dict(), n_envs, seed=0, nthreads=threads)
-    env.reset()
-    # bound the run: K "steps" of the reference arm are K agent steps of the sample batch, capped to ~60 s
-    t0 = time.perf_counter(); env.rollout_random(1); per = time.perf_counter() - t0
-    K = max(1, min(args.steps, int(60.0 / max(per, 1e-6))))
-    W = max(1, min(args.warmup, max(1, int(5.0 / max(per, 1e-6)))))
-    env.rollout_random(W)
-    t0 = time.perf_counter()
-    done = env.rollout_random(K)
-    dt = time.perf_counter() - t0
-    v = done / dt
-    sample = f"{n_envs} envs per step, {K} timed steps ({done} env-steps), {threads} host threads, {cpu_model()}"
+    n_envs = 16384        # per-step sample: large enough that the per-call thread start-up of the oracle's parallel-for is noise
+    wl = E2E_WORKLOAD if args.workload == "physics_only" else args.workload
+    v, steps, spread = oracle_host_step_rate(wl, threads, n_envs, 2.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K, "warmup": W,
-        "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, args.envs), "envs_per_gpu": args.envs,
-                   "sample_envs_per_step": n_envs,
-                   "note": "reference CPU path restated as the fp64 oracle port (PyFlyt/pybullet are not installable "
-                           "offline); each step is a bounded sample of the workload: one agent step of a "
-                           f"{n_envs}-env slice of the batch on all host threads"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": n_envs / v * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": bench_config(args),
+        "timed": {"regions": 5, "steps_per_region": steps, "sample_envs_per_step": n_envs, "region_s": steps * n_envs / v,
+                  "spread": spread, "statistic": "median"},
+        "note": "reference CPU path restated as the fp64 oracle port (PyFlyt/pybullet/SB3 are not installable offline); each "
+                f"step is a bounded sample of the workload: one agent step of a {n_envs}-env slice of the batch through "
+                "OracleVecEnv.step (host arrays in and out) on all host threads",
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{wl}: {n_envs} envs per step through host buffers, 5 regions of {steps} steps (>= 2 s each), "
+                                   f"median, {threads} host threads, {cpu_model()}"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.workload == "physics_only":
+        pv, psample = oracle_rate("physics_only", threads, 3.0)
+        line["physics_only"] = {"value": pv, "unit": UNIT, "sample": psample,
+                                "note": "like-for-like CPU figure for our arm's device-timed `value`"}
+    if not args.no_ppo:
+        try:
+            line["ppo"] = reference_ppo(threads)
+        except Exception as e:        # the CPU PPO must never take the env-step line down with it
+            line["ppo"] = {"error": f"{type(e).__name__}: {e}"}
     print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------- our arm
+def _max_over_ranks(x: float, world: int) -> float:
+    import torch
+    import torch.distributed as dist
+    if world == 1:
+        return float(x)
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def ppo_measure(preset: str, n_envs: int, n_steps: int, batch_size: int, n_epochs: int, rank: int, local_rank: int,
+                world: int, iters: int = 2, warm: int = 1, epochs_run: int | None = None) -> dict:
+    """One PPO workload: `warm` untimed iterations (the second one captures the rollout CUDA graph), then `iters` timed
+    iterations of rollout + update between barriers, device-synchronised on both sides, MAX over ranks.  The NCCL
+    all-reduce of the 49 KB gradient runs inside the update of every optimiser step when world > 1.
+    epochs_run < n_epochs: the update runs only that many of the n_epochs epochs (variant A's bounded default)."""
+    import torch
+    import torch.distributed as dist
+    from pyflyt_drone_b200.ppo import PPO
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    env = FixedwingVecEnv(n_envs, preset=preset, device=local_rank, seed=42, env_id0=rank * n_envs)
+    run_epochs = n_epochs if epochs_run is None else min(epochs_run, n_epochs)
+    model = PPO("MlpPolicy", env, n_steps=n_steps, batch_size=batch_size, n_epochs=run_epochs, seed=42, **PPO_HP)
+    per_iter = n_envs * n_steps * world
+    model.learn(max(2, warm + 1) * per_iter)        # eager rollout, then graph capture + replay
+    model.stats.__init__()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    model.learn(iters * per_iter)
+    torch.cuda.synchronize()
+    dt = _max_over_ranks(time.perf_counter() - t0, world)
+    st = model.stats
+    rollout_s = _max_over_ranks(st.rollout_s, world) / iters
+    update_s = _max_over_ranks(st.update_s, world) / iters
+    mb = -(-n_envs * n_steps // batch_size)
+    ar_us = 0.0
+    if world > 1:                                    # cost of the path's one collective, measured on its own
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(20):
+            dist.all_reduce(model._grad)
+        torch.cuda.synchronize(); dist.barrier()
+        e0.record()
+        for _ in range(200):
+            dist.all_reduce(model._grad)
+        e1.record(); torch.cuda.synchronize()
+        ar_us = _max_over_ranks(e0.elapsed_time(e1) / 200 * 1e3, world)
+    out = {"sps": iters * per_iter / dt, "n_gpus": world, "envs_per_gpu": n_envs, "n_steps": n_steps, "batch_size_per_gpu": batch_size,
+           "n_epochs": n_epochs, "iterations": iters, "iter_ms": dt / iters * 1e3, "rollout_s": rollout_s, "update_s": update_s,
+           "rollout_env_steps_per_sec": per_iter / max(rollout_s, 1e-9),
+           "optimizer_steps_per_iteration": run_epochs * mb, "optimizer_step_us": update_s / max(run_epochs * mb, 1) * 1e6,
+           "allreduce_us": ar_us, "allreduce_bytes": int(model._grad.numel() * 4),
+           "allreduce_in_timed_region": world > 1,
+           "update": "fused tcgen05 minibatch gradient kernel + clip/Adam kernel" if model.update == "kernel" else "torch autograd",
+           "forward": "tcgen05 kind::tf32 policy/value forward" if model.tensor_core_forward else "CUDA-core fp32 forward",
+           # rollout graph per step: obs moments, policy forward, env step, return moments + reward finalise, bootstrap;
+           # per rollout: counter, last values, GAE; per epoch: permutation; per minibatch: adv stats, gradient, reduce, Adam
+           "gpu_launches": int(iters * (n_steps * 6 + 3 + run_epochs * (1 + mb * 4)))}
+    if run_epochs < n_epochs:
+        epoch_s = update_s / run_epochs
+        full = rollout_s + n_epochs * epoch_s
+        out.update({"full_iteration": False, "epochs_timed": run_epochs, "epoch_s": epoch_s,
+                    "sps_timed_region": out.pop("sps"),
+                    "sps": per_iter / full,
+                    "sps_note": f"update timed for {run_epochs} of {n_epochs} epochs ({run_epochs * mb} optimiser steps); sps = env-steps "
+                                f"of one rollout / (rollout_s + {n_epochs} x epoch_s), every epoch being {mb} identical optimiser "
+                                "steps; `--ppo-a-full` runs all of them"})
+    else:
+        out["full_iteration"] = True
+    env.close()
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(args, rank: int, local_rank: int, world: int):
@@ -256,50 +436,63 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     from pyflyt_drone_b200 import _lib
     from pyflyt_drone_b200.vec_env import FixedwingVecEnv
 
-    over = {}
-    cfg = fw.make_config(args.workload, **over)
+    cfg = fw.make_config(args.workload)
     N = args.envs
     state_bytes = N * (6 * 16 + 4 + (cfg.num_targets * 12) + (5 * 16 + 32 * 12 if cfg.task in (2, 4) else 0)
                        + (31 * 4 if cfg.task == 4 else 0))
     replicas = max(2, int(np.ceil(2 * L2_BYTES / state_bytes)))
     envs = [FixedwingVecEnv(N, config=cfg, device=local_rank, seed=1234, env_id0=(rank * replicas + r) * N)
             for r in range(replicas)]
-    K, W = args.steps, max(3, args.warmup)
+    K, W = max(1, args.steps), max(3, args.warmup)
+    graph = not args.no_graph
+    spl = max(1, args.steps_per_launch)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    spl = max(1, args.steps_per_launch)
-    FixedwingVecEnv.rollout_random(envs, W, spl, use_graph=False)
-    if not args.no_graph:
-        # one untimed pass through the launch graph: its construction / instantiation is not part of a step
-        FixedwingVecEnv.rollout_random(envs, replicas, spl, use_graph=True)
-        if K % replicas:
-            FixedwingVecEnv.rollout_random(envs, K % replicas, spl, use_graph=True)     # and the graph of the tail
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+
+    FixedwingVecEnv.rollout_random(envs, W, spl, use_graph=False)                 # W untimed warm-up steps
+    FixedwingVecEnv.rollout_random(envs, replicas, spl, use_graph=graph)          # builds + instantiates the launch graph
+    # calibrate R: how many times the K-step sequence is replayed so that a region lasts >= REGION_MS on the device
+    c0, c1 = ev(), ev()
+    torch.cuda.synchronize()
+    c0.record()
+    FixedwingVecEnv.rollout_random(envs, K * 4, spl, use_graph=graph)
+    c1.record(); torch.cuda.synchronize()
+    est_ms = max(c0.elapsed_time(c1) / (K * 4), 1e-4)
+    R = max(1, int(np.ceil(REGION_MS * 1.15 / (est_ms * K))))
+    R = int(_max_over_ranks(R, world))
     launches0 = sum(e.launch_count for e in envs)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    region_ms = []
+    barrier()
     if sampler:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    FixedwingVecEnv.rollout_random(envs, K, spl, use_graph=not args.no_graph)
-    e1.record()
-    barrier()
-    clocks = sampler.stop() if sampler else None       # sampled during the timed region only
-    ms = e0.elapsed_time(e1)
+    for _ in range(N_REGIONS):
+        e0, e1 = ev(), ev()
+        FixedwingVecEnv.rollout_random(envs, replicas, spl, use_graph=graph)       # warm launch: the GPU is busy ...
+        e0.record()                                                                # ... so the region opens behind it, in enqueue order
+        FixedwingVecEnv.rollout_random(envs, K * R, spl, use_graph=graph)
+        e1.record()
+        barrier()
+        region_ms.append(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None        # sampled during the timed regions only
     launches = sum(e.launch_count for e in envs) - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    value = N * K * spl * world / (ms * 1e-3)
-    kernel_ms = ms / K          # back-to-back launches of one kernel: the mean launch-to-launch duration
+    med = statistics.median(region_ms)
+    step_ms = _max_over_ranks(med / (K * R), world)      # MAX over ranks of each rank's median
+    best_ms = _max_over_ranks(min(region_ms) / (K * R), world)
+    value = N * spl * world / (step_ms * 1e-3)
+    kernel_ms = step_ms          # back-to-back launches of one kernel: the mean launch-to-launch duration
+    for e in envs:
+        e.close()
+    envs = []
 
     # ---- e2e: the VecEnv.step seam with host buffers (Waypoints-v3 task, obs/reward/flags come back) ----
-    e2e_cfg = fw.make_config("waypoints_v3", **over)
+    e2e_cfg = fw.make_config(E2E_WORKLOAD)
     venv = FixedwingVecEnv(N, config=e2e_cfg, device=local_rank, seed=99, env_id0=rank * N)
     venv.reset()
     rng = np.random.default_rng(rank)
@@ -308,20 +501,39 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     acts = [b.numpy() for b in pinned]
     for a in acts:
         a[:] = rng.uniform(-1, 1, (N, 4)).astype(np.float32)
-    for s in range(5):
-        venv.step_arrays(acts[s % 4], want_terminal_obs=False)
-    barrier()
     t0 = time.perf_counter()
-    for s in range(args.e2e_steps):
+    for s in range(8):
         venv.step_arrays(acts[s % 4], want_terminal_obs=False)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = N * args.e2e_steps * world / float(t.item())
+    e2e_steps = max(8, int(np.ceil(REGION_MS * 1.1e-3 / ((time.perf_counter() - t0) / 8))))
+    e2e_steps = int(_max_over_ranks(e2e_steps, world))
+    e2e_dt = []
+    for _ in range(N_REGIONS):
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(e2e_steps):
+            venv.step_arrays(acts[s % 4], want_terminal_obs=False)
+        torch.cuda.synchronize()
+        e2e_dt.append(time.perf_counter() - t0)
+    e2e_step_s = _max_over_ranks(statistics.median(e2e_dt) / e2e_steps, world)
+    e2e_value = N * world / e2e_step_s
     h2d = N * 4 * 4
-    d2h = N * venv.obs_dim * 4 + N * 4 + N
+    d2h = N * venv.obs_dim * 4 + N * 4 + N + N          # obs, reward, flag byte, targets-reached byte
+    e2e_launches = N_REGIONS * e2e_steps * (2 if N >= 16384 else 1)
+    venv.close()
+
+    # ---- PPO SPS: every rank takes part (gradient all-reduce inside the timed region) ----
+    ppo = None
+    if not args.no_ppo and args.workload == "physics_only":
+        ppo = {}
+        try:
+            ppo["waypoints_v3_B"] = ppo_measure("waypoints_v3", 4096, 128, 4096 * 128 // 4, 20, rank, local_rank, world, iters=3)
+            ppo["waypoints_v3_A"] = ppo_measure("waypoints_v3", 4096, 2048, 128, 20, rank, local_rank, world, iters=1, warm=1,
+                                                epochs_run=None if args.ppo_a_full else args.ppo_a_epochs)
+            ppo["waypoint_objlock"] = ppo_measure("waypoint_objlock", 65536, 64, 65536 * 64 // 4, 20, rank, local_rank, world, iters=2)
+        except Exception as e:
+            ppo["error"] = f"{type(e).__name__}: {e}"
+            if world > 1:
+                raise
 
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
@@ -330,97 +542,70 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         per_gpu = N * spl / (kernel_ms * 1e-3)
         achieved_gbs = per_gpu * BYTES_PER_STEP[args.workload] / 1e9
         fp32_tf = per_gpu * FLOPS_PER_STEP[args.workload] / 1e12
-        traffic = None
+        traffic, executed = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = json.load(open(tpath)).get(f"{args.workload}_{N}")
+                tj = json.load(open(tpath))
+                traffic = tj.get(f"{args.workload}_{N}")
+                executed = tj.get(f"{args.workload}_executed_fp32_flop_per_env_step")
             except Exception:
                 traffic = None
+        roof = {"bound": "fp32", "achieved": fp32_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": fp32_tf / tf.value,
+                "traffic": traffic, "kernel": "fw_step_kernel", "kernel_ms": kernel_ms,
+                "flops_per_env_step": FLOPS_PER_STEP[args.workload], "sm_count": sms.value,
+                "peak_source": "FP32 FMA chain measured in this run (fw_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 entry",
+                "binding_pipe": "fp32 issue (arithmetic intensity 42 flop/B against a ridge of 11)",
+                "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                        "algorithmic_bytes_per_env_step": BYTES_PER_STEP[args.workload], "peak_source": peak_src}}
+        if executed:
+            roof["executed_fp32_flop_per_env_step"] = executed
+            roof["executed_frac"] = per_gpu * executed / 1e12 / tf.value
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload, N),
-                       "envs_per_gpu": N, "substeps_per_env_step": cfg.inner_per_step * cfg.substeps_per_inner,
-                       "physics_substeps_per_sec": value * cfg.inner_per_step * cfg.substeps_per_inner,
-                       "l2": f"rotating {replicas} env batches ({replicas * state_bytes / 2**20:.0f} MiB > 2x L2)",
-                       "env_steps_per_launch": spl,
-                       "launch": "host loop" if args.no_graph else f"CUDA graph of {replicas} launches", "e2e_workload": "waypoints_v3 via FixedwingVecEnv.step_arrays (actions in pinned host numpy arrays, obs/reward/flags back in host memory)"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches),
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": bench_config(args),
+            "timed": {"regions": N_REGIONS, "replays_per_region": R, "timed_launches": K * R, "region_ms": region_ms,
+                      "statistic": "median region / (K*R), MAX over ranks", "best_region_ms_per_step": best_ms,
+                      "physics_substeps_per_sec": value * cfg.inner_per_step * cfg.substeps_per_inner,
+                      "l2": f"rotating {replicas} env batches ({replicas * state_bytes / 2**20:.0f} MiB > 2x L2)",
+                      "launch": "host loop" if args.no_graph else f"CUDA graph of {replicas} launches"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "us_per_step": e2e_step_s * 1e6, "steps_per_region": e2e_steps, "regions": N_REGIONS},
+            "gpu_launches": int(launches + e2e_launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "fw_step_kernel", "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_env_step": BYTES_PER_STEP[args.workload],
-                         "binding_pipe": "fp32",
-                         "fp32": {"achieved": fp32_tf, "peak": tf.value, "unit": "TFLOP/s", "frac": fp32_tf / tf.value,
-                                  "flops_per_env_step": FLOPS_PER_STEP[args.workload], "sm_count": sms.value,
-                                  "peak_source": "FMA chain measured in this run (fw_measure_fp32_peak)"}},
+            "roofline": roof,
         }
+        if ppo is not None:
+            line["ppo"] = ppo
         if world == 1 and not args.no_cpu_baseline:
             v, sample = oracle_rate(args.workload, host_cores(), args.cpu_seconds)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": host_cores(), "kind": "port",
                                     "sample": sample + f"; {cpu_model()}"}
         print(json.dumps(line), flush=True)
-    for e in envs:
-        e.close()
-    venv.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
 def run_ppo(args, rank: int, local_rank: int, world: int):
-    """BASELINE configs[2]: PPO on Fixedwing-Waypoints (train_Fixedwing_Waypoints_v3 hyper-parameters, scaled
-    variant B of SURVEY 8d: n_steps 128, 4 minibatches per epoch).  A step = one rollout + one update."""
+    """`--workload ppo`: one PPO workload as its own JSON line (a step = one rollout + one update)."""
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    from pyflyt_drone_b200.ppo import PPO
-    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
     N, T = args.ppo_envs, args.ppo_n_steps
-    env = FixedwingVecEnv(N, preset=args.ppo_preset, device=local_rank, seed=42, env_id0=rank * N)
-    model = PPO("MlpPolicy", env, learning_rate=3e-4, n_steps=T, batch_size=N * T // args.ppo_minibatches,
-                n_epochs=args.ppo_epochs, gamma=0.99, gae_lambda=0.95, clip_range=0.2, ent_coef=0.001, vf_coef=0.5,
-                max_grad_norm=0.5, seed=42)
-    K, W = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    model.learn(W * N * T * world)
-    model.stats.__init__()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    model.learn(K * N * T * world)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
+    bs = args.ppo_batch_size if args.ppo_batch_size > 0 else N * T // args.ppo_minibatches
+    K = max(1, min(args.steps, 5))
+    r = ppo_measure(args.ppo_preset, N, T, bs, args.ppo_epochs, rank, local_rank, world, iters=K, warm=1)
     if rank == 0:
-        st = model.stats
-        line = {"metric": "ppo_env_steps_per_sec", "value": K * N * T * world / dt, "unit": "env-steps/s", "n_gpus": world,
-                "steps": K, "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
+        line = {"metric": "ppo_env_steps_per_sec", "value": r["sps"], "unit": "env-steps/s", "n_gpus": world,
+                "steps": K, "warmup": 2, "ms_per_step": r["iter_ms"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"ppo: {args.ppo_preset} PPO rollout+update (BASELINE configs[2]/[3])",
-                           "envs_per_gpu": N, "n_steps": T, "minibatches_per_epoch": args.ppo_minibatches,
-                           "n_epochs": args.ppo_epochs, "rollout_s": st.rollout_s, "update_s": st.update_s,
-                           "rollout_env_steps_per_sec": st.env_steps / max(st.rollout_s, 1e-9),
-                           "update": "fused tcgen05 minibatch gradient kernel + clip/Adam kernel (csrc/ppo_update_tc.cu)"
-                                     if model.update == "kernel" else "torch autograd (6-channel or > 32-float policies)",
-                           "forward": "tcgen05 kind::tf32 policy/value forward (csrc/ppo_tc.cu)" if model.tensor_core_forward
-                                      else "CUDA-core fp32 policy/value forward (csrc/ppo_kernels.cu)", "rollout": "CUDA graph"},
-                # the rollout is one CUDA-graph replay, which bypasses the C-side launch counter: count this repo's kernels
-                # from the launch sequence instead -- per rollout step: obs moments, policy forward, env step, return
-                # moments, reward finalise, bootstrap value forward, step counter; per rollout: last values, GAE; per
-                # epoch: permutation; per minibatch: advantage stats, gradient, partial reduce, clip+Adam
-                "gpu_launches": int(K * (T * 7 + 2 + args.ppo_epochs * (1 + args.ppo_minibatches * 4)))}
+                "config": {"workload": f"ppo: {args.ppo_preset} PPO rollout+update (BASELINE configs[2]/[3])", **r},
+                "gpu_launches": r["gpu_launches"]}
         print(json.dumps(line), flush=True)
-    env.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -66,6 +66,9 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
                                              const float4& w1_in, float& ep_ret, float* row, float* term_obs_row,
                                              uint32_t& bits, int& tidx_info) {
     float4 w0 = w0_in, w1 = w1_in;
+    // checked on entry as well: the per-coordinate velocity clamp below turns a NaN velocity into -max_vel (fmaxf/fminf
+    // return the non-NaN operand, in the oracle's C fmax/fmin too), which would launder a poisoned state
+    const bool fault_in = !fw_state_finite(e);
     // FixedwingBaseEnv.step: reward reset once, thrust remapped to [0,1], setpoint latched
     float reward = -0.1f;
     bool term = false, trunc = false, col = false, oob = false, complete = false;
@@ -124,8 +127,8 @@ __device__ __forceinline__ float fw_env_step(const FwDev& p, const FwPlanes& pl,
     e.step_count += 1;
     if (TASK == 1) complete = e.tidx >= p.num_targets;     // info["env_complete"] is sticky within an episode
     tidx_info = e.tidx;                                    // info["num_targets_reached"], before any auto-reset
-    const bool fault = !fw_state_finite(e);                // poisoned state: terminate without reward, count, reset
-    if (fault) { term = true; reward = 0.0f; }
+    const bool fault = fault_in || !fw_state_finite(e);    // poisoned state: terminate without reward, count, reset
+    if (fault) { term = true; trunc = false; col = false; oob = false; reward = 0.0f; }
 
     const bool done = term || trunc;
     if (TASK != 0 && row != nullptr) fw_write_obs(p, pl, e, i, obs_tidx, a0, a1, a2, a3, row);
@@ -161,6 +164,7 @@ __device__ __forceinline__ float fw_env_step_lowlevel(const FwDev& p, const FwPl
                                                       const float a[6], const float4& w0_in, const float4& w1_in, float& ep_ret,
                                                       float* row, float* term_obs_row, uint32_t& bits) {
     float4 w0 = w0_in, w1 = w1_in;
+    const bool fault_in = !fw_state_finite(e);           // see fw_env_step
     e.step_count += 1;                                   // self._episode_steps += 1
     float cmd[6];
 #pragma unroll
@@ -190,7 +194,7 @@ __device__ __forceinline__ float fw_env_step_lowlevel(const FwDev& p, const FwPl
     bool term = false, oob = false;
     if (e.pz < 1.0f || e.pz > 100.0f) { term = true; oob = true; reward -= 100.0f; }
     const bool trunc = e.step_count >= p.max_steps;
-    const bool fault = !fw_state_finite(e);
+    const bool fault = fault_in || !fw_state_finite(e);
     if (fault) { term = true; oob = false; reward = 0.0f; }
     ep_ret += reward;
     if (term || trunc) {
@@ -373,6 +377,7 @@ __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPla
                                                      float a2, float a3, float4& w0, float4& w1, float& ep_ret, float* row,
                                                      float* term_obs_row, uint32_t& bits, int& tidx_info) {
     const int tid = threadIdx.x;
+    const bool fault_in = active && !fw_state_finite(e);   // see fw_env_step
     float reward = -0.1f;
     bool term = false, trunc = false, col = false, oob = false, complete = false, strike = false;
     float cmd[6];
@@ -465,8 +470,8 @@ __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPla
     }
     if (active) e.step_count += 1;
     tidx_info = e.tidx;                                    // info["num_targets_reached"], before any auto-reset
-    const bool fault = active && !fw_state_finite(e);      // poisoned state: terminate without reward, count, reset
-    if (fault) { term = true; reward = 0.0f; }
+    const bool fault = fault_in || (active && !fw_state_finite(e));   // poisoned state: terminate without reward, count, reset
+    if (fault) { term = true; trunc = false; col = false; oob = false; complete = false; strike = false; reward = 0.0f; }
     const bool done = active && (term || trunc);
     if (active && row != nullptr) ol_write_obs<TASK>(p, pl, e, ol, hs, i, obs_tidx, a0, a1, a2, a3, row, tid);
     if (active) ep_ret += reward;
