@@ -110,7 +110,9 @@ typedef struct FwConfig {
     int32_t vision_hist_len;        /* duck_vision_history_len, 1..FW_MAX_HIST (task 4) */
     int32_t vision_use_deltas;      /* duck_vision_use_deltas (task 4) */
     int32_t lock_decay_steps;       /* duck_lock_decay_steps (task 4) */
-    int32_t _reserved[1];
+    int32_t packed_pairs;           /* 1 = tasks 0/1/3 on the standard layout step TWO envs per thread on the packed fp32x2
+                                     * instructions of sm_100a (csrc/fw_pack.cuh).  Opt-in: measured slower than the one-env
+                                     * kernels on B200 (profiles/r2_k1_packed.md); results agree to fp32 rounding. */
 } FwConfig;
 
 /* Host-side view of the per-env state for parity injection / inspection.  Any pointer may be NULL

@@ -64,7 +64,7 @@ class FwConfigC(C.Structure):
         ("cam_res", _I),
         ("force_generic_kernel", _I),
         ("cam_mode", _I), ("vision_hist_len", _I), ("vision_use_deltas", _I), ("lock_decay_steps", _I),
-        ("_reserved", _I * 1),
+        ("packed_pairs", _I),
     ]
 
 
@@ -180,6 +180,7 @@ class EnvConfig:
     vision_use_deltas: int = 1
     lock_decay_steps: int = 1
     force_generic_kernel: int = 0                       # testing: run the generic kernels even for the standard layout
+    packed_pairs: int = 0                               # 1: two envs per thread on the packed fp32x2 path (csrc/fw_pack.cuh; opt-in)
 
     # ------------------------------------------------------------------
     @property
@@ -231,8 +232,6 @@ class EnvConfig:
         names = {f[0] for f in FwConfigC._fields_}
         d = self.as_dict()
         for name, ctype in FwConfigC._fields_:
-            if name == "_reserved":
-                continue
             v = d[name]
             if name == "col_pts":
                 for i, p in enumerate(v):

@@ -267,6 +267,7 @@ static int derive(const FwConfig& c, int n, uint64_t seed, uint32_t env_id0, FwD
     d.area_reward_scale = (float)c.area_reward_scale; d.lock_lost_penalty = (float)c.lock_lost_penalty;
     d.approach_clip = (float)c.approach_clip;
     d.warm_cached = 0;
+    d.packed = c.packed_pairs != 0 ? 1 : 0;
     d.seed_lo = (uint32_t)(seed & 0xffffffffu); d.seed_hi = (uint32_t)(seed >> 32); d.env_id0 = env_id0;
     d.n = n;
     d.i_begin = 0; d.i_end = n;

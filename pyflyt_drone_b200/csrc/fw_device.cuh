@@ -128,6 +128,8 @@ struct FwDev {
     float warm[20];
     // 1 when the aircraft has the standard layout the STD kernels are specialised for (see fw_substep)
     int std_geom;
+    // 1: step tasks 0/1/3 with two envs per thread on the packed fp32x2 path (fw_pack.cuh; needs std_geom, no quat limiter)
+    int packed;
     // rng / sharding
     uint32_t seed_lo, seed_hi, env_id0;
     int n;

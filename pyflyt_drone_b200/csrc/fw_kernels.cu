@@ -19,8 +19,10 @@
 // staging would cost an LDS per use instead.
 #include "fw_device.cuh"
 #include "fw_objlock.cuh"
+#include "fw_pack.cuh"
 #include "fw_kernels.h"
 
+#include <cstdlib>
 #include <cstring>
 
 #define FW_BLOCK 64
@@ -35,16 +37,17 @@ __device__ __forceinline__ uint32_t fw_smem_addr(const void* p) {
 }
 
 // Flush one warp's staged observation rows (32 x D floats, dense) to global memory.
+template <int ROWS = 32>
 __device__ __forceinline__ void fw_flush_obs(float* __restrict__ dst_base, const float* stage_warp, int D,
                                              int first_env, int n, int lane, bool bulk_ok) {
-    const int rows = min(32, n - first_env);
+    const int rows = min(ROWS, n - first_env);
     float* dst = dst_base + (size_t)first_env * D;
-    if (bulk_ok && rows == 32) {
+    if (bulk_ok && rows == ROWS) {
         // generic-proxy writes -> async proxy, then one elected lane issues the TMA bulk store
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) {
-            uint32_t bytes = 32u * (uint32_t)D * 4u;
+            uint32_t bytes = (uint32_t)ROWS * (uint32_t)D * 4u;
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                          :: "l"(dst), "r"(fw_smem_addr(stage_warp)), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -287,6 +290,313 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
     if (TASK != 0 && obs != nullptr) {
         const int first_env = p.i_begin + blockIdx.x * FW_BLOCK + warp * 32;
         if (first_env < p.i_end) fw_flush_obs(obs, stage_warp, D, first_env, p.i_end, lane, bulk_ok != 0);
+    }
+}
+
+// ================================================================== K1p: two environments per thread (fw_pack.cuh)
+// The same agent step as fw_step_kernel for the standard aircraft layout, with the physics of a PAIR of envs (2t, 2t+1)
+// carried in the two lanes of packed fp32x2 instructions.  Everything per-env that is not arithmetic (flags, rewards,
+// waypoint bookkeeping, auto-reset) is the scalar code above, run once per lane.
+#define FW2_THREADS 64
+// 4 resident blocks/SM x 64 threads x 255 registers; 148 x 4 x 128 = 75,776 >= 65,536 envs: a 64K-env launch is one wave
+#ifndef FW2_MIN_BLOCKS
+#define FW2_MIN_BLOCKS 4
+#endif
+#define FW2_SNAP 20       // floats of physical state snapshotted when a lane finishes in the middle of an agent step
+
+__device__ __forceinline__ void fw2_snapshot(float* snap, const EnvState2& e, int k) {
+    snap[0] = e.px[k]; snap[1] = e.py[k]; snap[2] = e.pz[k];
+    snap[3] = e.qx[k]; snap[4] = e.qy[k]; snap[5] = e.qz[k]; snap[6] = e.qw[k];
+    snap[7] = e.vx[k]; snap[8] = e.vy[k]; snap[9] = e.vz[k];
+    snap[10] = e.wx[k]; snap[11] = e.wy[k]; snap[12] = e.wz[k];
+#pragma unroll
+    for (int s = 0; s < FWD_NSURF; ++s) snap[13 + s] = e.act[s][k];
+    snap[18] = e.thr[k]; snap[19] = __int_as_float(e.physics_steps[k]);
+}
+__device__ __forceinline__ void fw2_restore(const float* snap, EnvState2& e, int k) {
+    fw_set(e.px.v, k, snap[0]); fw_set(e.py.v, k, snap[1]); fw_set(e.pz.v, k, snap[2]);
+    fw_set(e.qx.v, k, snap[3]); fw_set(e.qy.v, k, snap[4]); fw_set(e.qz.v, k, snap[5]); fw_set(e.qw.v, k, snap[6]);
+    fw_set(e.vx.v, k, snap[7]); fw_set(e.vy.v, k, snap[8]); fw_set(e.vz.v, k, snap[9]);
+    fw_set(e.wx.v, k, snap[10]); fw_set(e.wy.v, k, snap[11]); fw_set(e.wz.v, k, snap[12]);
+#pragma unroll
+    for (int s = 0; s < FWD_NSURF; ++s) fw_set(e.act[s].v, k, snap[13 + s]);
+    fw_set(e.thr.v, k, snap[18]); e.physics_steps[k] = __float_as_int(snap[19]);
+}
+
+// motor-noise draw of lane k for its physics step (the normals are redrawn every fourth step, as in fw_env_step)
+__device__ __forceinline__ float fw2_noise(const FwDev& p, uint32_t gid, uint32_t episode, int ps, float (&nn)[4], bool& have) {
+    if (!have || (ps & 3) == 0) { fw_normals4(p, gid, episode, (uint32_t)ps >> 2, nn); have = true; }
+    const int q = ps & 3;
+    return q == 0 ? nn[0] : (q == 1 ? nn[1] : (q == 2 ? nn[2] : nn[3]));
+}
+
+// FixedwingBaseEnv.step + SubprocVecEnv reset-on-done for the pair (tasks 0 and 1): fw_env_step, lane by lane
+template <int TASK>
+__device__ __forceinline__ void fw_env_step2(const FwDev& p, const FwPlanes& pl, EnvState2& e, int i0, uint32_t gid0,
+                                             const float (&a)[2][4], float4 (&w0)[2], float4 (&w1)[2], float (&ep_ret)[2],
+                                             float* const (&row)[2], float* const (&term_row)[2], float* snap,
+                                             float (&reward)[2], uint32_t (&bits)[2], int (&tidx_info)[2], bool has1) {
+    // lane y of the last thread of an odd batch mirrors lane x: it computes along and has no side effects
+    const bool valid[2] = {true, has1};
+    bool term[2] = {false, false}, trunc[2] = {false, false}, col[2] = {false, false}, oob[2] = {false, false};
+    bool frozen[2] = {false, false}, fault_in[2], have_noise[2] = {false, false};
+    float nn[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    int obs_tidx[2] = {e.tidx[0], e.tidx[1]};
+    f2 cmd[6];
+    {
+        float c0[6], c1[6];
+        fw_map_setpoint(p, a[0][0], a[0][1], a[0][2], a[0][3] * 0.5f + 0.5f, c0);
+        fw_map_setpoint(p, a[1][0], a[1][1], a[1][2], a[1][3] * 0.5f + 0.5f, c1);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) cmd[c] = f2(c0[c], c1[c]);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { reward[k] = -0.1f; fault_in[k] = !fw_state_finite(fw_lane(e, k)); }
+
+    for (int it = 0; it < p.inner_per_step; ++it) {
+        const bool live[2] = {!(term[0] || trunc[0]), valid[1] && !(term[1] || trunc[1])};
+        if (!live[0] && !live[1]) break;
+        bool contact[2] = {false, false};
+        for (int s = 0; s < p.substeps_per_inner; ++s) {
+            f2 nz(0.0f), wx(0.0f), wy(0.0f), wz(0.0f);
+            if (p.noise_ratio > 0.0f)
+                nz = f2(fw2_noise(p, gid0, e.episode[0], e.physics_steps[0], nn[0], have_noise[0]),
+                        fw2_noise(p, gid0 + 1u, e.episode[1], e.physics_steps[1], nn[1], have_noise[1]));
+            if (p.wind_mode != 0) {
+                float x0, y0, z0, x1, y1, z1;
+                fw_wind(p, e.physics_steps[0], w0[0], w1[0], x0, y0, z0);
+                fw_wind(p, e.physics_steps[1], w0[1], w1[1], x1, y1, z1);
+                wx = f2(x0, x1); wy = f2(y0, y1); wz = f2(z0, z1);
+            }
+            fw_substep_p(p, e, cmd, wx, wy, wz, nz, contact);
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (!live[k]) continue;            // this lane broke out of the loop earlier (`if term or trunc: break`)
+            const int i = i0 + k;
+            const float px = e.px[k], py = e.py[k], pz = e.pz[k];
+            // compute_state: WaypointHandler.distance_to_targets (old <- new, new <- |delta_0|)
+            const float old_dist = e.new_dist[k];
+            float new_dist = old_dist;
+            obs_tidx[k] = e.tidx[k];
+            if (TASK >= 1 && e.tidx[k] < p.num_targets) {
+                const float dx = pl.targets[(size_t)(e.tidx[k] * 3 + 0) * p.n + i] - px;
+                const float dy = pl.targets[(size_t)(e.tidx[k] * 3 + 1) * p.n + i] - py;
+                const float dz = pl.targets[(size_t)(e.tidx[k] * 3 + 2) * p.n + i] - pz;
+                new_dist = sqrtf(dx * dx + dy * dy + dz * dz);
+                fw_set(e.new_dist.v, k, new_dist);
+            }
+            // compute_base_term_trunc_reward
+            if (e.step_count[k] > p.max_steps) trunc[k] = true;
+            if (contact[k]) { reward[k] = -100.0f; col[k] = true; term[k] = true; }
+            if (px * px + py * py + pz * pz > p.dome2) { reward[k] = -100.0f; oob[k] = true; term[k] = true; }
+            if (TASK == 1 && e.tidx[k] < p.num_targets && !(p.early_return_on_crash && (col[k] || oob[k]))) {
+                if (!p.sparse_reward) {
+                    reward[k] += fmaxf(3.0f * (old_dist - new_dist), 0.0f);
+                    reward[k] += 1.0f / new_dist;
+                }
+                if (new_dist < p.goal_reach) {
+                    reward[k] = 100.0f;
+                    e.tidx[k] += 1;                                  // advance_targets
+                    if (p.complete_truncates && e.tidx[k] >= p.num_targets) trunc[k] = true;
+                }
+            }
+            // a lane that ends its step before the last inner iteration keeps riding in the packed arithmetic of its
+            // neighbour: park the state its observation has to show
+            if ((term[k] || trunc[k]) && it + 1 < p.inner_per_step) { fw2_snapshot(snap + k * FW2_SNAP, e, k); frozen[k] = true; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (!valid[k]) continue;
+        if (frozen[k]) fw2_restore(snap + k * FW2_SNAP, e, k);
+        const int i = i0 + k;
+        const uint32_t gid = gid0 + (uint32_t)k;
+        e.step_count[k] += 1;
+        bool complete = false;
+        if (TASK == 1) complete = e.tidx[k] >= p.num_targets;
+        tidx_info[k] = e.tidx[k];
+        EnvState ek = fw_lane(e, k);
+        const bool fault = fault_in[k] || !fw_state_finite(ek);
+        if (fault) { term[k] = true; trunc[k] = false; col[k] = false; oob[k] = false; reward[k] = 0.0f; }
+        const bool done = term[k] || trunc[k];
+        if (TASK != 0 && row[k] != nullptr) fw_write_obs(p, pl, ek, i, obs_tidx[k], a[k][0], a[k][1], a[k][2], a[k][3], row[k]);
+        ep_ret[k] += reward[k];
+        if (done) {
+            if (TASK != 0 && term_row[k] != nullptr && !fault)
+                for (int c = 0; c < p.obs_dim; ++c) term_row[k][c] = row[k][c];
+            if (fault) atomicAdd(&pl.stats[8], 1.0);
+            atomicAdd(&pl.stats[0], 1.0);
+            atomicAdd(&pl.stats[1], (double)ep_ret[k]);
+            atomicAdd(&pl.stats[2], (double)ek.step_count);
+            atomicAdd(&pl.stats[3], (double)ek.tidx);
+            if (col[k]) atomicAdd(&pl.stats[4], 1.0);
+            if (oob[k]) atomicAdd(&pl.stats[5], 1.0);
+            if (complete) atomicAdd(&pl.stats[6], 1.0);
+            fw_reset_env(p, pl, ek, i, gid, ek.episode + 1u);         // SubprocVecEnv worker: obs = env.reset()
+            if (p.wind_mode != 0) { w0[k] = pl.w0[i]; w1[k] = pl.w1[i]; }
+            if (TASK != 0 && row[k] != nullptr) fw_write_obs(p, pl, ek, i, 0, 0.f, 0.f, 0.f, 0.f, row[k]);
+            if (fault && TASK != 0 && term_row[k] != nullptr)
+                for (int c = 0; c < p.obs_dim; ++c) term_row[k][c] = row[k][c];
+            ep_ret[k] = 0.0f;
+            fw_set_lane(e, k, ek);
+        }
+        bits[k] = (term[k] ? 1u : 0u) | (trunc[k] ? 2u : 0u) | (col[k] ? 4u : 0u) | (oob[k] ? 8u : 0u) | (complete ? 16u : 0u) |
+                  (fault ? 64u : 0u);
+    }
+}
+
+// FixedwingLowLevelEnv.step for the pair (task 3): fw_env_step_lowlevel, lane by lane
+__device__ __forceinline__ void fw_env_step2_lowlevel(const FwDev& p, const FwPlanes& pl, EnvState2& e, int i0, uint32_t gid0,
+                                                      const float (&a)[2][6], float4 (&w0)[2], float4 (&w1)[2],
+                                                      float (&ep_ret)[2], float* const (&row)[2], float* const (&term_row)[2],
+                                                      float (&reward)[2], uint32_t (&bits)[2], bool has1) {
+    bool fault_in[2], have_noise[2] = {false, false};
+    float nn[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    f2 cmd[6];
+#pragma unroll
+    for (int c = 0; c < 6; ++c) cmd[c] = f2(a[0][c], a[1][c]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { fault_in[k] = !fw_state_finite(fw_lane(e, k)); e.step_count[k] += 1; }
+    bool contact[2] = {false, false};
+    for (int s = 0; s < p.substeps_per_inner; ++s) {
+        f2 nz(0.0f), wx(0.0f), wy(0.0f), wz(0.0f);
+        if (p.noise_ratio > 0.0f)
+            nz = f2(fw2_noise(p, gid0, e.episode[0], e.physics_steps[0], nn[0], have_noise[0]),
+                    fw2_noise(p, gid0 + 1u, e.episode[1], e.physics_steps[1], nn[1], have_noise[1]));
+        if (p.wind_mode != 0) {
+            float x0, y0, z0, x1, y1, z1;
+            fw_wind(p, e.physics_steps[0], w0[0], w1[0], x0, y0, z0);
+            fw_wind(p, e.physics_steps[1], w0[1], w1[1], x1, y1, z1);
+            wx = f2(x0, x1); wy = f2(y0, y1); wz = f2(z0, z1);
+        }
+        fw_substep_p(p, e, cmd, wx, wy, wz, nz, contact);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if (k == 1 && !has1) continue;
+        const int i = i0 + k;
+        EnvState ek = fw_lane(e, k);
+        float yaw, speed, tref[3];
+        fw_write_obs_lowlevel(pl, ek, i, p.n, a[k], row[k], yaw, speed, tref);
+        float dpsi = tref[0] - yaw + FWD_PI;
+        dpsi -= 2.0f * FWD_PI * floorf(dpsi * (0.5f / FWD_PI));
+        dpsi -= FWD_PI;
+        reward[k] = -(fabsf(dpsi) + fabsf(tref[1] - ek.pz) + 0.5f * fabsf(tref[2] - speed)) + 0.1f;
+        bool term = false, oob = false;
+        if (ek.pz < 1.0f || ek.pz > 100.0f) { term = true; oob = true; reward[k] -= 100.0f; }
+        const bool trunc = ek.step_count >= p.max_steps;
+        const bool fault = fault_in[k] || !fw_state_finite(ek);
+        if (fault) { term = true; oob = false; reward[k] = 0.0f; }
+        ep_ret[k] += reward[k];
+        if (term || trunc) {
+            if (term_row[k] != nullptr && row[k] != nullptr && !fault)
+                for (int c = 0; c < p.obs_dim; ++c) term_row[k][c] = row[k][c];
+            if (fault) atomicAdd(&pl.stats[8], 1.0);
+            atomicAdd(&pl.stats[0], 1.0);
+            atomicAdd(&pl.stats[1], (double)ep_ret[k]);
+            atomicAdd(&pl.stats[2], (double)ek.step_count);
+            if (oob) atomicAdd(&pl.stats[5], 1.0);
+            fw_reset_env(p, pl, ek, i, gid0 + (uint32_t)k, ek.episode + 1u);
+            if (p.wind_mode != 0) { w0[k] = pl.w0[i]; w1[k] = pl.w1[i]; }
+            if (row[k] != nullptr) {
+                const float z6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                fw_write_obs_lowlevel(pl, ek, i, p.n, z6, row[k], yaw, speed, tref);
+                if (fault && term_row[k] != nullptr)
+                    for (int c = 0; c < p.obs_dim; ++c) term_row[k][c] = row[k][c];
+            }
+            ep_ret[k] = 0.0f;
+            fw_set_lane(e, k, ek);
+        }
+        bits[k] = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (oob ? 8u : 0u) | (fault ? 64u : 0u);
+    }
+}
+
+// smem: [obs staging: 128 rows x D] [snapshots: 64 threads x 2 x FW2_SNAP]
+template <int TASK, bool RANDOM_ACT>
+__global__ void __launch_bounds__(FW2_THREADS, FW2_MIN_BLOCKS)
+fw_step2_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4* __restrict__ act,
+                float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ flg,
+                float* __restrict__ term_obs, int spl, int bulk_ok) {
+    extern __shared__ __align__(128) float stage[];
+    const int t = blockIdx.x * FW2_THREADS + threadIdx.x;
+    const int i0 = p.i_begin + 2 * t;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = p.obs_dim;
+    float* stage_warp = stage + (size_t)warp * 64 * D;
+    float* snap = stage + (size_t)(FW2_THREADS * 2) * (D > 0 ? D : 1) + (size_t)threadIdx.x * 2 * FW2_SNAP;
+    const bool want_obs = TASK != 0 && obs != nullptr;
+
+    if (i0 < p.i_end) {
+        const bool has1 = i0 + 1 < p.i_end;
+        const uint32_t gid0 = p.env_id0 + (uint32_t)i0;
+        EnvState2 e;
+        fw_load2(pl, i0, p.i_end, e);
+        const int i1 = has1 ? i0 + 1 : i0;
+        float4 w0[2], w1[2];
+        w0[0] = w0[1] = w1[0] = w1[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.wind_mode != 0) { w0[0] = pl.w0[i0]; w1[0] = pl.w1[i0]; w0[1] = pl.w0[i1]; w1[1] = pl.w1[i1]; }
+        float ep_ret[2] = {pl.ep_ret[i0], pl.ep_ret[i1]};
+        float reward[2] = {0.f, 0.f};
+        uint32_t bits[2] = {0u, 0u};
+        int tidx_info[2] = {0, 0};
+        float* const row[2] = {want_obs ? stage_warp + (size_t)(2 * lane) * D : nullptr,
+                               want_obs ? stage_warp + (size_t)(2 * lane + 1) * D : nullptr};
+        const bool want_term = !RANDOM_ACT && want_obs && term_obs != nullptr;
+        float* const term_row[2] = {want_term ? term_obs + (size_t)i0 * D : nullptr, (want_term && has1) ? term_obs + (size_t)i1 * D : nullptr};
+        float* const no_row[2] = {nullptr, nullptr};
+        const int nst = RANDOM_ACT ? spl : 1;
+        for (int st = 0; st < nst; ++st) {
+            if (p.wind_mode != 0 && st > 0) { w0[0] = pl.w0[i0]; w1[0] = pl.w1[i0]; w0[1] = pl.w0[i1]; w1[1] = pl.w1[i1]; }
+            const bool last = st == nst - 1;
+            if (TASK == 3) {
+                float a6[2][6];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (RANDOM_ACT) {
+                        const uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid0 + k, e.episode[k], (uint32_t)e.step_count[k], FWD_STREAM_ACTION);
+                        const uint4 r2 = fw_philox(p.seed_lo, p.seed_hi, gid0 + k, e.episode[k], (uint32_t)e.step_count[k] | 0x40000000u, FWD_STREAM_ACTION);
+                        a6[k][0] = 2.0f * fw_u01(r.x) - 1.0f; a6[k][1] = 2.0f * fw_u01(r.y) - 1.0f; a6[k][2] = 2.0f * fw_u01(r.z) - 1.0f;
+                        a6[k][3] = 2.0f * fw_u01(r.w) - 1.0f; a6[k][4] = 2.0f * fw_u01(r2.x) - 1.0f; a6[k][5] = 2.0f * fw_u01(r2.y) - 1.0f;
+                    } else {
+                        const float2* af = reinterpret_cast<const float2*>(act) + (size_t)(k ? i1 : i0) * 3;     // [N, 6] row-major
+                        const float2 u0 = af[0], u1 = af[1], u2 = af[2];
+                        a6[k][0] = u0.x; a6[k][1] = u0.y; a6[k][2] = u1.x; a6[k][3] = u1.y; a6[k][4] = u2.x; a6[k][5] = u2.y;
+                    }
+                }
+                if (last) fw_env_step2_lowlevel(p, pl, e, i0, gid0, a6, w0, w1, ep_ret, row, term_row, reward, bits, has1);
+                else fw_env_step2_lowlevel(p, pl, e, i0, gid0, a6, w0, w1, ep_ret, no_row, no_row, reward, bits, has1);
+            } else {
+                float a4[2][4];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (RANDOM_ACT) {
+                        const uint4 r = fw_philox(p.seed_lo, p.seed_hi, gid0 + k, e.episode[k], (uint32_t)e.step_count[k], FWD_STREAM_ACTION);
+                        a4[k][0] = 2.0f * fw_u01(r.x) - 1.0f; a4[k][1] = 2.0f * fw_u01(r.y) - 1.0f;
+                        a4[k][2] = 2.0f * fw_u01(r.z) - 1.0f; a4[k][3] = 2.0f * fw_u01(r.w) - 1.0f;
+                    } else {
+                        const float4 v = act[k ? i1 : i0];
+                        a4[k][0] = v.x; a4[k][1] = v.y; a4[k][2] = v.z; a4[k][3] = v.w;
+                    }
+                }
+                if (last) fw_env_step2<TASK>(p, pl, e, i0, gid0, a4, w0, w1, ep_ret, row, term_row, snap, reward, bits, tidx_info, has1);
+                else fw_env_step2<TASK>(p, pl, e, i0, gid0, a4, w0, w1, ep_ret, no_row, no_row, snap, reward, bits, tidx_info, has1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (k == 1 && !has1) break;
+            const int i = i0 + k;
+            pl.ep_ret[i] = ep_ret[k];
+            fw_store(pl, i, fw_lane(e, k));
+            if (rew != nullptr) rew[i] = reward[k];
+            if (flg != nullptr) flg[i] = (uint8_t)bits[k];
+            if (TASK == 1 && !RANDOM_ACT && pl.tidx_out != nullptr) pl.tidx_out[i] = (uint8_t)tidx_info[k];
+        }
+    }
+    if (want_obs) {
+        const int first_env = p.i_begin + (blockIdx.x * FW2_THREADS + warp * 32) * 2;
+        if (first_env < p.i_end) fw_flush_obs<64>(obs, stage_warp, D, first_env, p.i_end, lane, bulk_ok != 0);
     }
 }
 
@@ -639,18 +949,47 @@ static inline int grid_for(int n) { return (n + FW_BLOCK - 1) / FW_BLOCK; }
 
 typedef void (*fw_step_fn)(const FwDev, const FwPlanes, const float4*, float*, float*, uint8_t*, float*, int, int);
 
-static fw_step_fn step_fn(int task, bool random_act, bool std_geom) {
-    if (task == 0 && std_geom) return random_act ? fw_step_kernel<0, true, true> : fw_step_kernel<0, false, true>;
-    if (task == 1 && std_geom) return random_act ? fw_step_kernel<1, true, true> : fw_step_kernel<1, false, true>;
-    if (task == 3 && std_geom) return random_act ? fw_step_kernel<3, true, true> : fw_step_kernel<3, false, true>;
-    if (task == 3) return random_act ? fw_step_kernel<3, true, false> : fw_step_kernel<3, false, false>;
-    if (task == 0) return random_act ? fw_step_kernel<0, true, false> : fw_step_kernel<0, false, false>;
-    if (task == 1) return random_act ? fw_step_kernel<1, true, false> : fw_step_kernel<1, false, false>;
-    if (task == 2 && std_geom) return random_act ? fw_step_objlock_kernel<true, 2, true> : fw_step_objlock_kernel<false, 2, true>;
-    if (task == 4 && std_geom) return random_act ? fw_step_objlock_kernel<true, 4, true> : fw_step_objlock_kernel<false, 4, true>;
-    if (task == 2) return random_act ? fw_step_objlock_kernel<true, 2, false> : fw_step_objlock_kernel<false, 2, false>;
-    if (task == 4) return random_act ? fw_step_objlock_kernel<true, 4, false> : fw_step_objlock_kernel<false, 4, false>;
-    return nullptr;
+// a step kernel with its launch geometry
+struct StepLaunch {
+    fw_step_fn fn;
+    int threads, envs_per_block;
+    size_t smem;
+};
+
+static inline size_t stage_bytes2(const FwDev& p) {
+    return ((size_t)(FW2_THREADS * 2) * (size_t)(p.obs_dim > 0 ? p.obs_dim : 1) + (size_t)FW2_THREADS * 2 * FW2_SNAP) * 4;
+}
+
+// FwConfig.packed_pairs selects the two-env-per-thread kernels per handle; FWSIM_PACKED=1 / 0 overrides it for every
+// handle of the process (A/B measurements)
+static bool packed_enabled(const FwDev& p) {
+    const char* e = getenv("FWSIM_PACKED");
+    if (e != nullptr && *e != 0) return atoi(e) != 0;
+    return p.packed != 0;
+}
+
+static StepLaunch step_launch(const FwDev& p, bool random_act) {
+    const int task = p.task;
+    const bool std_geom = p.std_geom != 0;
+    fw_step_fn fn = nullptr;
+    // two envs per thread on the packed fp32x2 path: standard layout, no quaternion step limiter (fw_pack.cuh)
+    if (std_geom && !p.quat_limiter && packed_enabled(p) && (task == 0 || task == 1 || task == 3)) {
+        if (task == 0) fn = random_act ? fw_step2_kernel<0, true> : fw_step2_kernel<0, false>;
+        if (task == 1) fn = random_act ? fw_step2_kernel<1, true> : fw_step2_kernel<1, false>;
+        if (task == 3) fn = random_act ? fw_step2_kernel<3, true> : fw_step2_kernel<3, false>;
+        return StepLaunch{fn, FW2_THREADS, FW2_THREADS * 2, stage_bytes2(p)};
+    }
+    if (task == 0 && std_geom) fn = random_act ? fw_step_kernel<0, true, true> : fw_step_kernel<0, false, true>;
+    else if (task == 1 && std_geom) fn = random_act ? fw_step_kernel<1, true, true> : fw_step_kernel<1, false, true>;
+    else if (task == 3 && std_geom) fn = random_act ? fw_step_kernel<3, true, true> : fw_step_kernel<3, false, true>;
+    else if (task == 3) fn = random_act ? fw_step_kernel<3, true, false> : fw_step_kernel<3, false, false>;
+    else if (task == 0) fn = random_act ? fw_step_kernel<0, true, false> : fw_step_kernel<0, false, false>;
+    else if (task == 1) fn = random_act ? fw_step_kernel<1, true, false> : fw_step_kernel<1, false, false>;
+    else if (task == 2 && std_geom) fn = random_act ? fw_step_objlock_kernel<true, 2, true> : fw_step_objlock_kernel<false, 2, true>;
+    else if (task == 4 && std_geom) fn = random_act ? fw_step_objlock_kernel<true, 4, true> : fw_step_objlock_kernel<false, 4, true>;
+    else if (task == 2) fn = random_act ? fw_step_objlock_kernel<true, 2, false> : fw_step_objlock_kernel<false, 2, false>;
+    else if (task == 4) fn = random_act ? fw_step_objlock_kernel<true, 4, false> : fw_step_objlock_kernel<false, 4, false>;
+    return StepLaunch{fn, FW_BLOCK, FW_BLOCK, stage_bytes(p)};
 }
 
 // dynamic shared memory beyond the 48 KB default needs an explicit opt-in per kernel (large obstacle tables or camera
@@ -663,12 +1002,16 @@ static bool smem_opt_in(const void* fn, size_t bytes) {
 
 cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act, float* obs, float* rew, uint8_t* flg,
                             float* term_obs, bool random_act, int spl, cudaStream_t st) {
-    const int bulk_ok = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) && ((p.obs_dim * 128) % 16 == 0);
-    fw_step_fn fn = step_fn(p.task, random_act, p.std_geom != 0);
-    if (fn == nullptr) return cudaErrorNotSupported;
-    if (!smem_opt_in((const void*)fn, stage_bytes(p))) return cudaErrorInvalidValue;
-    fn<<<grid_for(p.i_end - p.i_begin), FW_BLOCK, stage_bytes(p), st>>>(p, pl, reinterpret_cast<const float4*>(act), obs, rew, flg, term_obs,
-                                                         spl, bulk_ok);
+    const StepLaunch L = step_launch(p, random_act);
+    if (L.fn == nullptr) return cudaErrorNotSupported;
+    // the bulk store of a warp's observation rows needs a 16-byte aligned destination and size
+    const int rows = L.envs_per_block == FW_BLOCK ? 32 : 64;
+    const int bulk_ok = (obs != nullptr) && ((reinterpret_cast<uintptr_t>(obs) & 15u) == 0) && ((p.obs_dim * rows * 4) % 16 == 0) &&
+                        (((size_t)p.i_begin * p.obs_dim * 4) % 16 == 0);
+    if (!smem_opt_in((const void*)L.fn, L.smem)) return cudaErrorInvalidValue;
+    const int n = p.i_end - p.i_begin;
+    L.fn<<<(n + L.envs_per_block - 1) / L.envs_per_block, L.threads, L.smem, st>>>(p, pl, reinterpret_cast<const float4*>(act), obs, rew,
+                                                                                  flg, term_obs, spl, bulk_ok);
     return cudaGetLastError();
 }
 
@@ -676,18 +1019,19 @@ cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act
 // graph can later be launched on any stream including the legacy default stream torch hands us).
 cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* dep, const FwDev& p, const FwPlanes& pl, int spl,
                                       cudaGraphNode_t* out) {
-    fw_step_fn fn = step_fn(p.task, true, p.std_geom != 0);
-    if (fn == nullptr) return cudaErrorNotSupported;
-    if (!smem_opt_in((const void*)fn, stage_bytes(p))) return cudaErrorInvalidValue;
+    const StepLaunch L = step_launch(p, true);
+    if (L.fn == nullptr) return cudaErrorNotSupported;
+    if (!smem_opt_in((const void*)L.fn, L.smem)) return cudaErrorInvalidValue;
     FwDev pc = p; FwPlanes plc = pl;
     const float4* act = nullptr; float* obs = nullptr; float* rew = nullptr; uint8_t* flg = nullptr; float* term = nullptr;
     int spl_ = spl, bulk = 0;
     void* args[] = {&pc, &plc, &act, &obs, &rew, &flg, &term, &spl_, &bulk};
     cudaKernelNodeParams kp;
     memset(&kp, 0, sizeof(kp));
-    kp.func = (void*)fn;
-    kp.gridDim = dim3(grid_for(p.i_end - p.i_begin)); kp.blockDim = dim3(FW_BLOCK);
-    kp.sharedMemBytes = (unsigned)stage_bytes(p);
+    kp.func = (void*)L.fn;
+    const int n = p.i_end - p.i_begin;
+    kp.gridDim = dim3((n + L.envs_per_block - 1) / L.envs_per_block); kp.blockDim = dim3(L.threads);
+    kp.sharedMemBytes = (unsigned)L.smem;
     kp.kernelParams = args; kp.extra = nullptr;
     return cudaGraphAddKernelNode(out, g, dep, dep ? 1 : 0, &kp);
 }
