@@ -172,6 +172,36 @@ def load_urdf(path: str = DEFAULT_URDF) -> RigidBody:
     return RigidBody(float(total), com, inertia_o, offsets, np.array(pts, dtype=np.float64), placeholder, links)
 
 
+def quat_matrix(q) -> np.ndarray:
+    """pybullet (x, y, z, w) quaternion -> rotation matrix."""
+    x, y, z, w = (float(v) for v in q)
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]], dtype=np.float64)
+
+
+def body_from_bullet(links: list[dict], collision_points=None) -> RigidBody:
+    """Composite rigid body from what pybullet reports for a loaded multibody (scripts/record_pyflyt_golden.py dumps it):
+    one dict per link with ``name``, ``mass``, ``inertia_diag`` (getDynamicsInfo local inertia diagonal, in the link's
+    inertial frame), ``com`` (link CoM relative to the base-link CoM, base axes, body at the identity orientation) and
+    ``inertial_quat`` (orientation of the inertial frame in base axes, xyzw).  The first link is the base.  This is the
+    path by which a recording made with the REAL fixedwing.urdf replaces params/fixedwing_placeholder.urdf."""
+    out: list[Link] = []
+    for d in links:
+        R = quat_matrix(d.get("inertial_quat", (0.0, 0.0, 0.0, 1.0)))
+        I = R @ np.diag(np.asarray(d["inertia_diag"], dtype=np.float64)) @ R.T
+        out.append(Link(str(d["name"]), float(d["mass"]), np.asarray(d["com"], dtype=np.float64), I, R))
+    total = sum(l.mass for l in out)
+    if total <= 0:
+        raise ValueError("body has no mass")
+    com = sum(l.mass * l.com for l in out) / total
+    inertia_o = sum(parallel_axis(l.inertia, l.mass, l.com) for l in out)
+    offsets = {l.name: l.com for l in out}
+    pts = np.asarray(collision_points if collision_points is not None and len(collision_points) else [[0.0, 0.0, 0.0]],
+                     dtype=np.float64)
+    return RigidBody(float(total), com, inertia_o, offsets, pts, False, out)
+
+
 @dataclass
 class AeroTable:
     names: list[str]

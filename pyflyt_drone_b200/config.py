@@ -206,8 +206,12 @@ class EnvConfig:
         d["n_col"] = self.n_col
         return d
 
-    def with_aircraft(self, urdf_path: str | None = None, aero_path: str | None = None) -> "EnvConfig":
-        body = aircraft.load_urdf(urdf_path or aircraft.DEFAULT_URDF)
+    def with_aircraft(self, urdf_path: str | None = None, aero_path: str | None = None,
+                      body: "aircraft.RigidBody | None" = None) -> "EnvConfig":
+        """Fill the aircraft fields from a URDF (or an already reduced ``RigidBody``, e.g. aircraft.body_from_bullet of a
+        PyFlyt recording) and the aero table."""
+        if body is None:
+            body = aircraft.load_urdf(urdf_path or aircraft.DEFAULT_URDF)
         aero = aircraft.load_aero(aero_path or aircraft.DEFAULT_AERO)
         cols = aero.cols
         out = self.replace(
