@@ -99,22 +99,31 @@ def replay_waypoints(make_env, rec: dict, cfg, steps: int | None = None):
 
 def resolve_conventions(make_env, rec: dict, verbose: bool = True) -> dict:
     """Try every combination of the appendix-B convention flags; keep the one with the smallest error over the first
-    control / agent steps.  Aero flags come from scenario A (mode -1 needs no signs), signs from scenario B."""
-    best_a, flags = None, {}
+    control / agent steps.  Aero flags come from scenario A (mode -1 needs no signs), signs from scenario B.  A flag whose
+    alternatives reproduce the recording equally well (e.g. ``cd90_degrees`` when no surface stalls inside the horizon) is
+    listed under ``"ambiguous"`` and keeps the package default."""
+    scores_a = {}
     for f3, cd in itertools.product(*AERO_FLAGS.values()):
         cfg = config_from_body(rec["body"], "lowlevel", freestream_3d=f3, cd90_degrees=cd)
-        e = replay_mode_m1(make_env, rec["mode_m1"], cfg, steps=24)
-        score = max(v.max() for v in e.values())
-        if best_a is None or score < best_a:
-            best_a, flags = score, {"freestream_3d": f3, "cd90_degrees": cd}
-    best_b, signs = None, {}
+        e = replay_mode_m1(make_env, rec["mode_m1"], cfg, steps=60)
+        scores_a[(f3, cd)] = max(v.max() for v in e.values())
+    (f3, cd), best_a = min(scores_a.items(), key=lambda kv: kv[1])
+    flags = {"freestream_3d": f3, "cd90_degrees": cd}
+    scores_b = {}
     for (al, ar), ps, ys in itertools.product(*SIGN_FLAGS.values()):
         cfg = config_from_body(rec["body"], "waypoints_v3", ail_left_sign=al, ail_right_sign=ar, pitch_sign=ps, yaw_sign=ys, **flags)
         oerr, _, _ = replay_waypoints(make_env, rec["waypoints"], cfg, steps=6)
-        score = oerr.max()
-        if best_b is None or score < best_b:
-            best_b, signs = score, {"ail_left_sign": al, "ail_right_sign": ar, "pitch_sign": ps, "yaw_sign": ys}
-    out = {**flags, **signs}
+        scores_b[(al, ar, ps, ys)] = oerr.max()
+    (al, ar, ps, ys), best_b = min(scores_b.items(), key=lambda kv: kv[1])
+    out = {**flags, "ail_left_sign": al, "ail_right_sign": ar, "pitch_sign": ps, "yaw_sign": ys}
+    tie = lambda a, b: abs(a - b) <= 1e-12 + 1e-3 * min(a, b)      # noqa: E731
+    amb = []
+    if tie(scores_a[(1 - f3, cd)], best_a): amb.append("freestream_3d")
+    if tie(scores_a[(f3, 1 - cd)], best_a): amb.append("cd90_degrees")
+    if tie(scores_b[(-al, -ar, ps, ys)], best_b): amb.extend(["ail_left_sign", "ail_right_sign"])
+    if tie(scores_b[(al, ar, -ps, ys)], best_b): amb.append("pitch_sign")
+    if tie(scores_b[(al, ar, ps, -ys)], best_b): amb.append("yaw_sign")
+    out["ambiguous"] = amb
     if verbose:
         print(f"\n[upstream parity] resolved conventions: {out} (scenario A error {best_a:.2e}, scenario B error {best_b:.2e})")
     return out
