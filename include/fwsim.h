@@ -199,6 +199,11 @@ int fw_observe_host(fw_handle h, float* obs_host);
 int fw_host_info_buffer(fw_handle h, uint8_t** targets_reached);
 int fw_targets_reached(fw_handle h, uint8_t* dst_dev, void* stream);
 
+/* Camera tasks (2, 4): how the in-step auto-resets were served since fw_create -- out[0] from a pre-warmed spare episode
+ * (prepared ahead of time by dedicated blocks of the previous step launch), out[1] inline in the
+ * step kernel (no valid spare: e.g. after fw_set_state, or FWSIM_SPARE=0).  Both give the same state.  Synchronous. */
+int fw_spare_stats(fw_handle h, int64_t out[2]);
+
 /* number of envs force-reset because their state went non-finite (FW_FLAG_FAULT) since fw_create (synchronous) */
 int fw_fault_count(fw_handle h, int64_t* nonfinite_resets);
 /* The library's pinned staging buffers ([N,4] actions, [N,obs_dim] obs, [N] rewards, [N] flag bytes,

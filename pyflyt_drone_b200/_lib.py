@@ -7,7 +7,8 @@ import os
 from .config import FwConfigC
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfwsim.so")
+# FWSIM_LIB=<path>: load an experiment build instead (A/B measurements; scripts/ab_build.py)
+LIB_PATH = os.environ.get("FWSIM_LIB") or os.path.join(_HERE, "libfwsim.so")
 
 
 class FwStateHostC(C.Structure):
@@ -47,6 +48,7 @@ SYMBOLS = [
     ("fw_host_info_buffer", C.c_int, [_P, C.POINTER(_P)]),
     ("fw_targets_reached", C.c_int, [_P, _P, _P]),
     ("fw_fault_count", C.c_int, [_P, C.POINTER(C.c_int64)]),
+    ("fw_spare_stats", C.c_int, [_P, C.POINTER(C.c_int64)]),
     ("fw_host_buffers", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
     ("fw_set_state", C.c_int, [_P, C.POINTER(FwStateHostC)]),
     ("fw_get_state", C.c_int, [_P, C.POINTER(FwStateHostC)]),
@@ -66,7 +68,9 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     from . import build as _build
-    if _build.have_nvcc():
+    if os.environ.get("FWSIM_LIB"):
+        pass
+    elif _build.have_nvcc():
         _build.build()
     elif not os.path.exists(LIB_PATH):
         raise FwError(f"{LIB_PATH} is missing and nvcc is not available to build it; the env step has no CPU fallback")

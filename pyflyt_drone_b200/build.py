@@ -53,10 +53,11 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines: tuple[str, ...] = ()) -> str:
+    """`out` / `defines`: experiment builds (scripts/ab_build.py) next to the product library."""
+    if out is None and not force and not is_stale():
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB, *sources()]
+    cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-shared", "-o", out or LIB, *sources()]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -64,7 +65,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError(f"nvcc failed ({r.returncode}):\n{' '.join(cmd)}\n{r.stdout}\n{r.stderr}")
     if verbose:
         print(r.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -47,6 +47,16 @@ struct FwSim {
     float *d_act, *d_obs, *d_rew, *d_term;
     uint8_t* d_flg;
     uint8_t* h_tidx;   // host lane: info["num_targets_reached"] per env, written by the step kernel (pinned, device-mapped)
+    // pre-warmed spare episodes of the camera tasks (FwPlanes::sp_*): second plane arena, two request lists used alternately
+    // (ctl[0], ctl[1] = their entry counts, ctl[2], ctl[3] = finished-block counters of the refill kernels), and the
+    // low-priority side stream the refill runs on beside the next step
+    char* spare_mem;
+    int2* refill_list[2];
+    int* refill_ctl;
+    int parity;
+    bool spare_on;
+    cudaStream_t side;
+    cudaEvent_t ev_fork, ev_join;
     int64_t launches;
     bool fresh;   // true until the state created by fw_create has been stepped or overwritten
     // Lane ordering: the device lane enqueues on the caller's stream, the host lane on private non-blocking streams, and
@@ -293,11 +303,26 @@ static int multi_graph_get(MultiGraph& mg, const fw_handle* hs, int n_handles, i
     if (mg.graph) { cudaGraphDestroy(mg.graph); mg.graph = nullptr; }
     mg.hs.clear();
     CU(cudaGraphCreate(&mg.graph, 0));
-    cudaGraphNode_t prev, node;
+    // Step launches form one chain.  With spare episodes, handle h's refill (serving the list its step of the PREVIOUS pass
+    // filled -- list 0 for every graph launch) is a branch that forks off three launches ahead of h's step and joins at it:
+    // it runs beside other handles' steps and nothing dangles at the end of the graph.  (count <= n_handles: every handle
+    // appears at most once per graph; successive graph launches of one stream do not overlap.)
+    std::vector<cudaGraphNode_t> steps((size_t)count);
     for (int k = 0; k < count; ++k) {
         FwSim* h = hs[k % n_handles];
-        CU(fwk_graph_add_random_step(mg.graph, k ? &prev : nullptr, h->dev, h->pl, spl, &node));
-        prev = node;
+        cudaGraphNode_t deps[2];
+        int nd = 0;
+        if (k > 0) deps[nd++] = steps[(size_t)k - 1];
+        FwPlanes plc = h->pl;
+        if (h->spare_on) {
+            cudaGraphNode_t rf;
+            const int fork = k - 3;
+            CU(fwk_graph_add_refill(mg.graph, fork >= 0 ? &steps[(size_t)fork] : nullptr, fork >= 0 ? 1 : 0, h->dev, h->pl,
+                                    h->refill_list[0], h->refill_ctl, h->refill_ctl + 2, h->n, &rf));
+            deps[nd++] = rf;
+            plc.refill_list = h->refill_list[0]; plc.refill_count = h->refill_ctl;
+        }
+        CU(fwk_graph_add_random_step(mg.graph, nd ? deps : nullptr, nd, h->dev, plc, spl, &steps[(size_t)k]));
     }
     CU(cudaGraphInstantiate(&mg.exec, mg.graph, 0));
     for (int k = 0; k < count; ++k) mg.hs.push_back(hs[k % n_handles]);
@@ -306,6 +331,29 @@ static int multi_graph_get(MultiGraph& mg, const fw_handle* hs, int n_handles, i
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Lay the per-env planes out in one arena (256-byte aligned sub-ranges); base == nullptr only measures.
+static size_t carve_planes(const FwConfig& cfg, const FwDev& dev, size_t N, char* base, FwPlanes& pl) {
+    const size_t T = (size_t)(cfg.num_targets > 0 ? cfg.num_targets : 1);
+    const bool cam_task = cfg.task == 2 || cfg.task == 4;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off = align_up(off + bytes, 256); return p; };
+    memset(&pl, 0, sizeof(pl));
+    pl.s0 = (float4*)take(N * 16); pl.s1 = (float4*)take(N * 16); pl.s2 = (float4*)take(N * 16);
+    pl.s3 = (float4*)take(N * 16); pl.s4 = (float4*)take(N * 16); pl.s5 = (int4*)take(N * 16);
+    pl.w0 = (float4*)take(N * 16); pl.w1 = (float4*)take(N * 16);
+    pl.targets = (float*)take(T * 3 * N * 4);
+    pl.ep_ret = (float*)take(N * 4);
+    pl.stats = (double*)take(16 * sizeof(double));
+    pl.tidx_out = (uint8_t*)take(N);
+    if (cam_task) {
+        pl.dk = (float4*)take(N * 16); pl.v0 = (float4*)take(N * 16); pl.v1 = (float4*)take(N * 16);
+        pl.v2 = (float4*)take(N * 16); pl.v3 = (int4*)take(N * 16);
+        pl.obst = (float*)take((size_t)FW_MAX_OBST * 3 * N * 4);
+    }
+    if (cfg.task == 4) pl.hist = (float*)take((size_t)dev.hist_slots * N * 4);
+    return off;
+}
 
 static int fw_create_impl(const FwConfig* cfg, int32_t n_envs, int32_t device, uint64_t seed, uint32_t env_id0, FwSim* h);
 
@@ -338,39 +386,14 @@ static int fw_create_impl(const FwConfig* cfg, int32_t n_envs, int32_t device, u
     int rc = derive(*cfg, n_envs, seed, env_id0, h->dev);
     if (rc != FW_OK) return rc;
     h->obs_dim = h->dev.obs_dim;
-    const size_t N = (size_t)n_envs, T = (size_t)(cfg->num_targets > 0 ? cfg->num_targets : 1);
-    size_t off = 0, o_s[6], o_w0, o_w1, o_t, o_ep, o_st, o_ti, o_ol[5] = {0, 0, 0, 0, 0}, o_ob = 0, o_hist = 0;
+    const size_t N = (size_t)n_envs;
     const bool cam_task = cfg->task == 2 || cfg->task == 4;
-    for (int k = 0; k < 6; ++k) { o_s[k] = off; off = align_up(off + N * 16, 256); }
-    o_w0 = off; off = align_up(off + N * 16, 256);
-    o_w1 = off; off = align_up(off + N * 16, 256);
-    o_t = off; off = align_up(off + T * 3 * N * 4, 256);
-    o_ep = off; off = align_up(off + N * 4, 256);
-    o_st = off; off = align_up(off + 16 * sizeof(double), 256);
-    o_ti = off; off = align_up(off + N, 256);
-    if (cam_task) {
-        for (int k = 0; k < 5; ++k) { o_ol[k] = off; off = align_up(off + N * 16, 256); }
-        o_ob = off; off = align_up(off + (size_t)FW_MAX_OBST * 3 * N * 4, 256);
-    }
-    if (cfg->task == 4) { o_hist = off; off = align_up(off + (size_t)h->dev.hist_slots * N * 4, 256); }
-    h->plane_bytes = off;
-    ce = cudaMalloc((void**)&h->plane_mem, off);
-    if (ce != cudaSuccess) return fail(FW_ENOMEM, "cudaMalloc(%zu): %s", off, cudaGetErrorString(ce));
-    cudaMemset(h->plane_mem, 0, off);
+    h->plane_bytes = carve_planes(*cfg, h->dev, N, nullptr, h->pl);
+    ce = cudaMalloc((void**)&h->plane_mem, h->plane_bytes);
+    if (ce != cudaSuccess) return fail(FW_ENOMEM, "cudaMalloc(%zu): %s", h->plane_bytes, cudaGetErrorString(ce));
+    cudaMemset(h->plane_mem, 0, h->plane_bytes);
+    carve_planes(*cfg, h->dev, N, h->plane_mem, h->pl);
     FwPlanes& pl = h->pl;
-    pl.s0 = (float4*)(h->plane_mem + o_s[0]); pl.s1 = (float4*)(h->plane_mem + o_s[1]);
-    pl.s2 = (float4*)(h->plane_mem + o_s[2]); pl.s3 = (float4*)(h->plane_mem + o_s[3]);
-    pl.s4 = (float4*)(h->plane_mem + o_s[4]); pl.s5 = (int4*)(h->plane_mem + o_s[5]);
-    pl.w0 = (float4*)(h->plane_mem + o_w0); pl.w1 = (float4*)(h->plane_mem + o_w1);
-    pl.targets = (float*)(h->plane_mem + o_t); pl.ep_ret = (float*)(h->plane_mem + o_ep);
-    pl.stats = (double*)(h->plane_mem + o_st);
-    pl.tidx_out = (uint8_t*)(h->plane_mem + o_ti);
-    if (cfg->task == 4) pl.hist = (float*)(h->plane_mem + o_hist);
-    if (cam_task) {
-        pl.dk = (float4*)(h->plane_mem + o_ol[0]); pl.v0 = (float4*)(h->plane_mem + o_ol[1]);
-        pl.v1 = (float4*)(h->plane_mem + o_ol[2]); pl.v2 = (float4*)(h->plane_mem + o_ol[3]);
-        pl.v3 = (int4*)(h->plane_mem + o_ol[4]); pl.obst = (float*)(h->plane_mem + o_ob);
-    }
     // episode counter starts at -1 so that the first reset opens episode 0
     cudaMemset(pl.s5, 0xff, N * 16);
     CU(cudaStreamCreateWithFlags(&h->io_stream, cudaStreamNonBlocking));
@@ -393,6 +416,62 @@ static int fw_create_impl(const FwConfig* cfg, int32_t n_envs, int32_t device, u
     h->launches++;
     CU(cudaStreamSynchronize(h->io_stream));
     h->fresh = true;
+    // Spare episodes for the camera tasks, whose reset cannot be cached (per-episode wind during the warm-up, a camera frame
+    // inside it).  FWSIM_SPARE=0 turns the feature off (inline resets only; the results are the same).
+    const char* sp_env = getenv("FWSIM_SPARE");
+    if (cam_task && !(sp_env && atoi(sp_env) == 0)) {
+        FwPlanes sv;
+        const size_t bytes = carve_planes(*cfg, h->dev, N, nullptr, sv);
+        ce = cudaMalloc((void**)&h->spare_mem, bytes);
+        if (ce != cudaSuccess) return fail(FW_ENOMEM, "cudaMalloc(%zu) for the spare episodes: %s", bytes, cudaGetErrorString(ce));
+        CU(cudaMemset(h->spare_mem, 0, bytes));
+        carve_planes(*cfg, h->dev, N, h->spare_mem, sv);
+        for (int k = 0; k < 2; ++k) CU(cudaMalloc((void**)&h->refill_list[k], N * sizeof(int2)));
+        CU(cudaMalloc((void**)&h->refill_ctl, 4 * sizeof(int)));
+        CU(cudaMemset(h->refill_ctl, 0, 4 * sizeof(int)));
+        {
+            int lo = 0, hi = 0;
+            CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CU(cudaStreamCreateWithPriority(&h->side, cudaStreamNonBlocking, lo));   // lowest: the step's blocks are placed first
+        }
+        CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        FwPlanes& l = h->pl;
+        l.sp_s0 = sv.s0; l.sp_s1 = sv.s1; l.sp_s2 = sv.s2; l.sp_s3 = sv.s3; l.sp_s4 = sv.s4; l.sp_s5 = sv.s5;
+        l.sp_w0 = sv.w0; l.sp_w1 = sv.w1; l.sp_targets = sv.targets;
+        l.sp_dk = sv.dk; l.sp_v0 = sv.v0; l.sp_v1 = sv.v1; l.sp_v2 = sv.v2; l.sp_v3 = sv.v3; l.sp_obst = sv.obst; l.sp_hist = sv.hist;
+        l.refill_cap = n_envs;
+        CU(cudaMemset(sv.s5, 0xff, N * 16));                              // tag -1: no spare yet
+        CU(fwk_launch_refill(h->dev, h->pl, nullptr, nullptr, nullptr, n_envs, n_envs, h->io_stream));   // episode 1 of every env
+        h->launches++;
+        CU(cudaStreamSynchronize(h->io_stream));
+        h->spare_on = true;
+    }
+    return FW_OK;
+}
+
+// One step launch with the spare-episode traffic around it: the refill of the PREVIOUS launch's request list runs on the
+// low-priority side stream beside this step's kernel (fork / join through events, so a stream capture of the caller's
+// stream records a two-branch graph); this step appends to the other list, which the refill that served it last has
+// left empty.
+static int launch_step(FwSim* h, const FwDev& dev, FwPlanes pl, const float* act, float* obs, float* rew, uint8_t* flg,
+                       float* term_obs, bool random_act, int spl, cudaStream_t st) {
+    if (!h->spare_on) {
+        CU(fwk_launch_step(dev, pl, act, obs, rew, flg, term_obs, random_act, spl, st));
+        h->launches++;
+        return FW_OK;
+    }
+    const int par = h->parity, prev = par ^ 1;
+    CU(cudaEventRecord(h->ev_fork, st));
+    CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    pl.refill_list = h->refill_list[par];
+    pl.refill_count = h->refill_ctl + par;
+    CU(fwk_launch_step(dev, pl, act, obs, rew, flg, term_obs, random_act, spl, st));     // first: its blocks are placed first
+    CU(fwk_launch_refill(dev, h->pl, h->refill_list[prev], h->refill_ctl + prev, h->refill_ctl + 2 + prev, h->n, 0, h->side));
+    CU(cudaEventRecord(h->ev_join, h->side));
+    CU(cudaStreamWaitEvent(st, h->ev_join, 0));
+    h->launches += 2;
+    h->parity ^= 1;
     return FW_OK;
 }
 
@@ -420,6 +499,13 @@ extern "C" int fw_destroy(fw_handle h) {
     if (h->h_term) cudaFreeHost(h->h_term);
     if (h->h_flg) cudaFreeHost(h->h_flg);
     if (h->h_tidx) cudaFreeHost(h->h_tidx);
+    if (h->spare_mem) cudaFree(h->spare_mem);
+    if (h->refill_list[0]) cudaFree(h->refill_list[0]);
+    if (h->refill_list[1]) cudaFree(h->refill_list[1]);
+    if (h->refill_ctl) cudaFree(h->refill_ctl);
+    if (h->side) cudaStreamDestroy(h->side);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->io_stream) cudaStreamDestroy(h->io_stream);
     if (h->io_streams[1]) cudaStreamDestroy(h->io_streams[1]);
     delete h;
@@ -449,8 +535,8 @@ extern "C" int fw_step(fw_handle h, const float* act_dev, float* obs_dev, float*
     if (!act_dev) return fail(FW_EINVAL, "act_dev is null");
     if ((reinterpret_cast<uintptr_t>(act_dev) & 15u) != 0) return fail(FW_EINVAL, "act_dev must be 16-byte aligned");
     CU(cudaSetDevice(h->device));
-    CU(fwk_launch_step(h->dev, h->pl, act_dev, obs_dev, rew_dev, flags_dev, term_obs_dev, false, 1, (cudaStream_t)stream));
-    h->launches++;
+    int rc = launch_step(h, h->dev, h->pl, act_dev, obs_dev, rew_dev, flags_dev, term_obs_dev, false, 1, (cudaStream_t)stream);
+    if (rc != FW_OK) return rc;
     h->fresh = false;
     h->dev_lane_dirty = true;
     return FW_OK;
@@ -463,8 +549,8 @@ extern "C" int fw_step_random(fw_handle h, int32_t n_steps, float* rew_dev, uint
     h->fresh = false;
     h->dev_lane_dirty = true;
     for (int s = 0; s < n_steps; ++s) {
-        CU(fwk_launch_step(h->dev, h->pl, nullptr, nullptr, rew_dev, flags_dev, nullptr, true, 1, (cudaStream_t)stream));
-        h->launches++;
+        int rc = launch_step(h, h->dev, h->pl, nullptr, nullptr, rew_dev, flags_dev, nullptr, true, 1, (cudaStream_t)stream);
+        if (rc != FW_OK) return rc;
     }
     return FW_OK;
 }
@@ -488,20 +574,20 @@ extern "C" int fw_rollout_random(const fw_handle* hs, int32_t n_handles, int32_t
             int rc = multi_graph_get(g_multi, hs, n_handles, n_handles, steps_per_launch);
             if (rc != FW_OK) return rc;
             for (int r = 0; r < rounds; ++r) CU(cudaGraphLaunch(g_multi.exec, st));
-            for (int k = 0; k < n_handles; ++k) hs[k]->launches += rounds;
+            for (int k = 0; k < n_handles; ++k) hs[k]->launches += rounds * (hs[k]->spare_on ? 2 : 1);
         }
         if (rem > 0) {       // the tail of a launch count that is not a multiple of the list: one more (shorter) graph
             int rc = multi_graph_get(g_rem, hs, n_handles, rem, steps_per_launch);
             if (rc != FW_OK) return rc;
             CU(cudaGraphLaunch(g_rem.exec, st));
-            for (int k = 0; k < rem; ++k) hs[k]->launches += 1;
+            for (int k = 0; k < rem; ++k) hs[k]->launches += hs[k]->spare_on ? 2 : 1;
         }
         done = n_launches;
     }
     for (int j = done; j < n_launches; ++j) {
         FwSim* h = hs[j % n_handles];
-        CU(fwk_launch_step(h->dev, h->pl, nullptr, nullptr, nullptr, nullptr, nullptr, true, steps_per_launch, st));
-        h->launches++;
+        int rc = launch_step(h, h->dev, h->pl, nullptr, nullptr, nullptr, nullptr, nullptr, true, steps_per_launch, st);
+        if (rc != FW_OK) return rc;
     }
     return FW_OK;
 }
@@ -558,6 +644,13 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
     }();
     const int chunks = h->n >= 16384 ? tuned_chunks : 1;
     const int per = (((h->n + chunks - 1) / chunks) + 63) / 64 * 64;
+    // spare episodes: the previous step's request list is served on the side stream beside this step's chunk kernels, which
+    // all append to the other list
+    const int par = h->parity, prev = par ^ 1;
+    if (h->spare_on) {
+        CU(cudaEventRecord(h->ev_fork, h->io_streams[0]));
+        CU(cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    }
     for (int c = 0; c < chunks; ++c) {
         const int c0 = c * per, c1 = (c + 1) * per < h->n ? (c + 1) * per : h->n;
         if (c0 >= c1) break;
@@ -577,6 +670,7 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
         float* term_dst = want_term ? (zc_obs ? h->h_term : h->d_term) : nullptr;
         FwPlanes plh = h->pl;
         plh.tidx_out = h->h_tidx;          // info["num_targets_reached"] goes straight to the host like the flags
+        if (h->spare_on) { plh.refill_list = h->refill_list[par]; plh.refill_count = h->refill_ctl + par; }
         CU(fwk_launch_step(pc, plh, act_dev_view ? act_dev_view : h->h_act, obs_dst, h->h_rew, h->h_flg, term_dst, false, 1, st));
         h->launches++;
         if (!zc_obs) {
@@ -585,8 +679,13 @@ extern "C" int fw_step_host(fw_handle h, const float* act_host, float* obs_host,
         }
     }
     h->fresh = false;
+    if (h->spare_on) {
+        CU(fwk_launch_refill(h->dev, h->pl, h->refill_list[prev], h->refill_ctl + prev, h->refill_ctl + 2 + prev, h->n, 0, h->side));
+        h->launches++;
+    }
     CU(cudaStreamSynchronize(h->io_streams[0]));
     if (chunks > 1) CU(cudaStreamSynchronize(h->io_streams[1]));
+    if (h->spare_on) { CU(cudaStreamSynchronize(h->side)); h->parity ^= 1; }
     // buffers obtained from fw_host_buffers are the pinned staging itself: nothing left to copy
     if (obs_host && D && obs_host != h->h_obs) memcpy(obs_host, h->h_obs, N * D * sizeof(float));
     if (rew_host && rew_host != h->h_rew) memcpy(rew_host, h->h_rew, N * sizeof(float));
@@ -635,6 +734,16 @@ extern "C" int fw_fault_count(fw_handle h, int64_t* nonfinite_resets) {
 }
 
 static int reset_host_impl(fw_handle h, float* obs_host, bool observe_only);
+
+extern "C" int fw_spare_stats(fw_handle h, int64_t out[2]) {
+    if (!h || !out) return fail(FW_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaDeviceSynchronize());
+    double v[2] = {0.0, 0.0};
+    CU(cudaMemcpy(v, h->pl.stats + 9, 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    out[0] = (int64_t)v[0]; out[1] = (int64_t)v[1];
+    return FW_OK;
+}
 
 extern "C" int fw_reset_host(fw_handle h, float* obs_host) { return reset_host_impl(h, obs_host, false); }
 extern "C" int fw_observe_host(fw_handle h, float* obs_host) { return reset_host_impl(h, obs_host, true); }

@@ -160,6 +160,24 @@ struct FwPlanes {
     int4* v3;        // bits (duck_phase, has_prev, post_wp, cam_valid, frame_visible, n_obst<<8), seen, lock, since
     float* obst;     // [MAX_OBST][3][N]  x, y, height
     float* hist;     // duck-only task: [9 * hist_len + 4][N] vision history rows (newest first) then the four deltas
+    // Pre-warmed spare episodes (camera tasks): a second set of the planes above holding every env's NEXT episode already
+    // reset, warmed up and observed.  The state an env resets to depends only on (seed, env id, episode), so it can be
+    // prepared ahead of time by fw_refill_objlock_kernel -- a few requests per warp, on a side stream beside the next step --
+    // instead of by the one or two finished lanes of a stepping warp dragging 30 idle ones through 20 warm-up substeps and
+    // a camera frame.  sp_s5[i].z (the episode number) is the validity tag: an env that finishes episode k takes the spare
+    // iff the tag reads k + 1, else it resets inline; either way it appends (i, k + 2) to the request list of the launch.
+    // All nullptr / 0 when the feature is off.
+    float4 *sp_s0, *sp_s1, *sp_s2, *sp_s3, *sp_s4;
+    int4* sp_s5;
+    float4 *sp_w0, *sp_w1;
+    float* sp_targets;
+    float4 *sp_dk, *sp_v0, *sp_v1, *sp_v2;
+    int4* sp_v3;
+    float* sp_obst;
+    float* sp_hist;
+    int2* refill_list;   // [refill_cap] (env index, episode to prepare): requests of THIS launch
+    int* refill_count;
+    int refill_cap;
 };
 
 struct EnvState {

@@ -668,6 +668,90 @@ __device__ __forceinline__ void ol_reset_lanes(const FwDev& p, const FwPlanes& p
     }
 }
 
+// ---- pre-warmed spare episodes (see FwPlanes)
+#define OL_REFILL_PER_WARP 8      // requests served per warp pass: the camera serves a warp's frames one after the other, so
+                                  // a full warp would spend 32 frame times on the warm-up frame alone (140 us measured)
+
+__device__ __forceinline__ float4 sp_ld(const float4* p) { return __ldcg(p); }     // L2: written by another block of a
+__device__ __forceinline__ int4 sp_ld(const int4* p) { return __ldcg(p); }         // (possibly concurrent) launch
+__device__ __forceinline__ float sp_ld(const float* p) { return __ldcg(p); }
+
+// Try to start episode `want` of env i from its spare.  On success the live per-episode planes (wind, targets, obstacle
+// table) and the shared-memory copies are overwritten from the spare and the tag is cleared.
+template <int TASK>
+__device__ __forceinline__ bool ol_take_spare(const FwDev& p, const FwPlanes& pl, EnvState& e, OlState& ol, float* so, float* hs,
+                                              int i, uint32_t want, int tid, float4& w0, float4& w1) {
+    const int tag = *reinterpret_cast<volatile const int*>(&pl.sp_s5[i].z);
+    if ((uint32_t)tag != want) return false;
+    __threadfence();                                   // acquire: the planes were written before the tag
+    const float4 a = sp_ld(&pl.sp_s0[i]), b = sp_ld(&pl.sp_s1[i]), c = sp_ld(&pl.sp_s2[i]), d = sp_ld(&pl.sp_s3[i]), f = sp_ld(&pl.sp_s4[i]);
+    const int4 g = sp_ld(&pl.sp_s5[i]);
+    const float4 dk = sp_ld(&pl.sp_dk[i]), v0 = sp_ld(&pl.sp_v0[i]), v1 = sp_ld(&pl.sp_v1[i]), v2 = sp_ld(&pl.sp_v2[i]);
+    const int4 v3 = sp_ld(&pl.sp_v3[i]);
+    if (p.wind_mode != 0) { w0 = sp_ld(&pl.sp_w0[i]); w1 = sp_ld(&pl.sp_w1[i]); pl.w0[i] = w0; pl.w1[i] = w1; }
+    e.px = a.x; e.py = a.y; e.pz = a.z; e.thr = a.w;
+    e.qx = b.x; e.qy = b.y; e.qz = b.z; e.qw = b.w;
+    e.vx = c.x; e.vy = c.y; e.vz = c.z; e.act[0] = c.w;
+    e.wx = d.x; e.wy = d.y; e.wz = d.z; e.act[1] = d.w;
+    e.act[2] = f.x; e.act[3] = f.y; e.act[4] = f.z; e.new_dist = f.w;
+    e.step_count = g.x; e.physics_steps = g.y; e.episode = want; e.tidx = g.w;
+    ol.dkx = dk.x; ol.dky = dk.y; ol.dkz = dk.z;
+    ol.last_cx = v0.x; ol.last_cy = v0.y; ol.last_area = v0.z; ol.last_depth = v0.w;
+    ol.f_cx = v1.x; ol.f_cy = v1.y; ol.f_area = v1.z; ol.f_depth = v1.w;
+    ol.f_dl = v2.x; ol.f_dc = v2.y; ol.f_dr = v2.z; ol.prev_est = v2.w;
+    ol.duck_phase = v3.x & 1; ol.has_prev = (v3.x >> 1) & 1; ol.post_wp = (v3.x >> 2) & 1; ol.cam_valid = (v3.x >> 3) & 1;
+    ol.f_visible = (v3.x >> 4) & 1; ol.n_obst = (v3.x >> 8) & 0xff;
+    ol.seen = v3.y; ol.lock = v3.z; ol.since = v3.w;
+    ol.vis_dl = ol.vis_dc = ol.vis_dr = 0.0f; ol.vis_flag = 0.0f;
+    // the per-episode tables: loads in batches of eight before their stores, so that one lane's copy costs a few L2 round
+    // trips instead of one per element
+    const size_t n = (size_t)p.n;
+    const int nt = p.num_targets * 3;
+    for (int t0 = 0; t0 < nt; t0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (t0 + u < nt) ? sp_ld(&pl.sp_targets[(size_t)(t0 + u) * n + i]) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (t0 + u < nt) pl.targets[(size_t)(t0 + u) * n + i] = v[u];
+    }
+    const int no = ol.n_obst * 3;
+    for (int t0 = 0; t0 < no; t0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (t0 + u < no) ? sp_ld(&pl.sp_obst[(size_t)(t0 + u) * n + i]) : 0.0f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (t0 + u < no) { pl.obst[(size_t)(t0 + u) * n + i] = v[u]; so[(t0 + u) * FW_BLOCK + tid] = v[u]; }
+    }
+    if (TASK == 4) {
+        for (int t0 = 0; t0 < p.hist_slots; t0 += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (t0 + u < p.hist_slots) ? sp_ld(&pl.sp_hist[(size_t)(t0 + u) * n + i]) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (t0 + u < p.hist_slots) OL_H(hs, t0 + u, tid, FW_BLOCK) = v[u];
+        }
+    }
+    pl.sp_s5[i].z = -1;                                 // consumed
+    return true;
+}
+
+// ask for the spare of episode `episode` of env i to be prepared
+__device__ __forceinline__ void ol_request_spare(const FwPlanes& pl, int i, uint32_t episode) {
+    if (pl.refill_list == nullptr) return;
+    const int idx = atomicAdd(pl.refill_count, 1);
+    if (idx < pl.refill_cap) pl.refill_list[idx] = make_int2(i, (int)episode);
+}
+
+// the FwPlanes whose primary pointers are the spare set: the code of the in-step reset then writes there
+__device__ __forceinline__ FwPlanes ol_spare_view(const FwPlanes& pl) {
+    FwPlanes v = pl;
+    v.s0 = pl.sp_s0; v.s1 = pl.sp_s1; v.s2 = pl.sp_s2; v.s3 = pl.sp_s3; v.s4 = pl.sp_s4; v.s5 = pl.sp_s5;
+    v.w0 = pl.sp_w0; v.w1 = pl.sp_w1; v.targets = pl.sp_targets;
+    v.dk = pl.sp_dk; v.v0 = pl.sp_v0; v.v1 = pl.sp_v1; v.v2 = pl.sp_v2; v.v3 = pl.sp_v3; v.obst = pl.sp_obst; v.hist = pl.sp_hist;
+    return v;
+}
+
 // flattened observation of either ObjLock task into `row`
 template <int TASK>
 __device__ __forceinline__ void ol_write_obs(const FwDev& p, const FwPlanes& pl, const EnvState& e, const OlState& ol,
@@ -677,6 +761,49 @@ __device__ __forceinline__ void ol_write_obs(const FwDev& p, const FwPlanes& pl,
     else {
         fw_write_obs(p, pl, e, i, 0, a0, a1, a2, a3, row);            // context_len == 0: the attitude block only
         ol_write_obs_duck_tail(p, e, ol, hs, tid, FW_BLOCK, row + ((p.angle_repr == 0 ? 12 : 13) + 10));
+    }
+}
+
+// Episode end of the lanes with `done` set (all 32 lanes call): terminal observation, episode statistics, then the
+// SubprocVecEnv worker's obs = env.reset().  The next episode normally waits ready-made in the env's spare planes; lanes
+// without a valid spare (first episodes after an injected state, two finishes in quick succession, FWSIM_SPARE=0) run the
+// reset inline.  (Inlined: out-of-line versions -- `e` / `ol` passed through local copies, or the refill as a role of this
+// kernel's leading blocks -- measured 3-15 % slower: the step kernel is sensitive to its stack frame, profiles/r2_objlock.md.)
+template <int TASK>
+__device__ __forceinline__ void ol_finish_episode(const FwDev& p, const FwPlanes& pl, bool done, uint32_t info, EnvState& e,
+                                                      OlState& ol, float4& w0, float4& w1, float& ep_ret, float* so,
+                                                      float* depth_row, float* hs, int i, uint32_t gid, float* row,
+                                                      float* term_obs_row) {
+    const int tid = threadIdx.x;
+    const bool fault = info & 1u;
+    if (done) {
+        if (term_obs_row != nullptr && !fault)
+            for (int k = 0; k < p.obs_dim; ++k) term_obs_row[k] = row[k];
+        if (fault) atomicAdd(&pl.stats[8], 1.0);
+        atomicAdd(&pl.stats[0], 1.0);
+        atomicAdd(&pl.stats[1], (double)ep_ret);
+        atomicAdd(&pl.stats[2], (double)e.step_count);
+        atomicAdd(&pl.stats[3], (double)e.tidx);
+        if (info & 2u) atomicAdd(&pl.stats[4], 1.0);
+        if (info & 4u) atomicAdd(&pl.stats[5], 1.0);
+        if (info & 8u) atomicAdd(&pl.stats[6], 1.0);
+        if (info & 16u) atomicAdd(&pl.stats[7], 1.0);
+    }
+    bool inline_reset = done;
+    if (done && pl.sp_s5 != nullptr) {
+        const uint32_t want = e.episode + 1u;
+        inline_reset = !ol_take_spare<TASK>(p, pl, e, ol, so, hs, i, want, tid, w0, w1);
+        ol_request_spare(pl, i, want + 1u);
+        atomicAdd(&pl.stats[inline_reset ? 10 : 9], 1.0);      // fw_spare_stats: resets served inline / from a spare
+    }
+    if (__any_sync(0xffffffffu, inline_reset))
+        ol_reset_lanes<TASK>(p, pl, inline_reset, e, ol, so, depth_row, hs, i, gid, e.episode + 1u, tid);
+    if (done) {
+        if (p.wind_mode != 0 && inline_reset) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
+        if (row != nullptr) ol_write_obs<TASK>(p, pl, e, ol, hs, i, 0, 0.f, 0.f, 0.f, 0.f, row, tid);
+        if (fault && term_obs_row != nullptr && row != nullptr)
+            for (int k = 0; k < p.obs_dim; ++k) term_obs_row[k] = row[k];
+        ep_ret = 0.0f;
     }
 }
 
@@ -702,6 +829,9 @@ __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPla
         const bool run = active && !(term || trunc);        // FixedwingBaseEnv.step: `if termination or truncation: break`
         bool contact = false;
         if (run) {
+            // one copy of the substep in the loop body: this kernel's inner iteration (substeps + camera + rewards) is
+            // instruction-cache bound (ncu: no_instruction ~0.9 stalls per issue), unrolling the pair of substeps costs 10 KB
+#pragma unroll 1
             for (int s = 0; s < p.substeps_per_inner; ++s) {
                 const int ps = e.physics_steps;
                 float nz = 0.0f;
@@ -786,28 +916,8 @@ __device__ __forceinline__ float fw_env_step_objlock(const FwDev& p, const FwPla
     if (active && row != nullptr) ol_write_obs<TASK>(p, pl, e, ol, hs, i, obs_tidx, a0, a1, a2, a3, row, tid);
     if (active) ep_ret += reward;
     if (__any_sync(0xffffffffu, done)) {
-        if (done) {
-            if (term_obs_row != nullptr && !fault)
-                for (int k = 0; k < p.obs_dim; ++k) term_obs_row[k] = row[k];
-            if (fault) atomicAdd(&pl.stats[8], 1.0);
-            atomicAdd(&pl.stats[0], 1.0);
-            atomicAdd(&pl.stats[1], (double)ep_ret);
-            atomicAdd(&pl.stats[2], (double)e.step_count);
-            atomicAdd(&pl.stats[3], (double)e.tidx);
-            if (col) atomicAdd(&pl.stats[4], 1.0);
-            if (oob) atomicAdd(&pl.stats[5], 1.0);
-            if (complete) atomicAdd(&pl.stats[6], 1.0);
-            if (strike) atomicAdd(&pl.stats[7], 1.0);
-        }
-        // SubprocVecEnv worker: obs = env.reset()
-        ol_reset_lanes<TASK>(p, pl, done, e, ol, so, depth_row, hs, i, gid, e.episode + 1u, tid);
-        if (done) {
-            if (p.wind_mode != 0) { w0 = pl.w0[i]; w1 = pl.w1[i]; }
-            if (row != nullptr) ol_write_obs<TASK>(p, pl, e, ol, hs, i, 0, 0.f, 0.f, 0.f, 0.f, row, tid);
-            if (fault && term_obs_row != nullptr && row != nullptr)
-                for (int k = 0; k < p.obs_dim; ++k) term_obs_row[k] = row[k];
-            ep_ret = 0.0f;
-        }
+        const uint32_t info = (fault ? 1u : 0u) | (col ? 2u : 0u) | (oob ? 4u : 0u) | (complete ? 8u : 0u) | (strike ? 16u : 0u);
+        ol_finish_episode<TASK>(p, pl, done, info, e, ol, w0, w1, ep_ret, so, depth_row, hs, i, gid, row, term_obs_row);
     }
     bits = (term ? 1u : 0u) | (trunc ? 2u : 0u) | (col ? 4u : 0u) | (oob ? 8u : 0u) | (complete ? 16u : 0u) | (strike ? 32u : 0u) |
            (fault ? 64u : 0u);
@@ -831,7 +941,8 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
                        float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ flg,
                        float* __restrict__ term_obs, int spl, int bulk_ok) {
     extern __shared__ __align__(128) float stage[];
-    const int i = p.i_begin + blockIdx.x * FW_BLOCK + threadIdx.x;
+    const int bx = (int)blockIdx.x;
+    const int i = p.i_begin + bx * FW_BLOCK + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = p.obs_dim;
     float* stage_warp = stage + (size_t)warp * 32 * D;
@@ -883,7 +994,7 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
         if (TASK == 2 && !RANDOM_ACT && pl.tidx_out != nullptr) pl.tidx_out[i] = (uint8_t)tidx_info;
     }
     if (obs != nullptr) {
-        const int first_env = p.i_begin + blockIdx.x * FW_BLOCK + warp * 32;
+        const int first_env = p.i_begin + bx * FW_BLOCK + warp * 32;
         if (first_env < p.i_end) fw_flush_obs(obs, stage_warp, D, first_env, p.i_end, lane, bulk_ok != 0);
     }
 }
@@ -919,6 +1030,56 @@ fw_reset_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, cons
     if (obs != nullptr) {
         const int first_env = blockIdx.x * FW_BLOCK + warp * 32;
         if (first_env < p.n) fw_flush_obs(obs, stage_warp, D, first_env, p.n, lane, bulk_ok != 0);
+    }
+}
+
+// Producer side of the spare episodes, a kernel of its own (its stack frame and registers stay out of the step kernel):
+// entry k of the list = (env index, episode).  OL_REFILL_PER_WARP requests per warp pass -- begin_reset, waypoints / duck /
+// obstacles, the warm-up under wind with its camera frame, end_reset's compute_state -- through ol_reset_lanes on the
+// spare view of the planes, i.e. the very code of the in-step reset; data first, tag last.  The last block to finish
+// clears the list's counter for the step launch that appends to it next.
+// whole_batch > 0: episode (live episode + 1) of every env 0..whole_batch-1, full warps (fw_create, right after the first reset).
+#define FW_REFILL_GRID 64
+template <int TASK>
+__global__ void __launch_bounds__(FW_BLOCK, 7)
+fw_refill_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const int2* __restrict__ list,
+                         int* __restrict__ count, int* __restrict__ blocks_done, int cap, int whole_batch) {
+    extern __shared__ __align__(128) float stage[];
+    float *so, *depth_row, *hs;
+    ol_smem_carve(p, stage, so, depth_row, hs);
+    const FwPlanes sv = ol_spare_view(pl);
+    const int n = whole_batch > 0 ? whole_batch : min(*reinterpret_cast<volatile int*>(count), cap);
+    const int per = whole_batch > 0 ? 32 : OL_REFILL_PER_WARP;
+    const int lane = threadIdx.x & 31;
+    const int wg = blockIdx.x * (FW_BLOCK / 32) + (threadIdx.x >> 5), nw = gridDim.x * (FW_BLOCK / 32);
+    for (int base = wg * per; base < n; base += nw * per) {
+        const int idx = base + lane;
+        const bool doing = lane < per && idx < n;
+        int2 ent = make_int2(0, 0);
+        if (doing) ent = whole_batch > 0 ? make_int2(idx, pl.s5[idx].z + 1) : list[idx];
+        const int i = ent.x;
+        EnvState e = {};
+        OlState ol = {};
+        ol_reset_lanes<TASK>(p, sv, doing, e, ol, so, depth_row, hs, i, p.env_id0 + (uint32_t)i, (uint32_t)ent.y, threadIdx.x);
+        if (doing) {
+            sv.s0[i] = make_float4(e.px, e.py, e.pz, e.thr);
+            sv.s1[i] = make_float4(e.qx, e.qy, e.qz, e.qw);
+            sv.s2[i] = make_float4(e.vx, e.vy, e.vz, e.act[0]);
+            sv.s3[i] = make_float4(e.wx, e.wy, e.wz, e.act[1]);
+            sv.s4[i] = make_float4(e.act[2], e.act[3], e.act[4], e.new_dist);
+            ol_store(sv, i, ol);
+            if (TASK == 4) ol_hist_store(p, sv, i, hs, threadIdx.x, FW_BLOCK);
+            __threadfence();                            // release: everything above is visible before the tag
+            sv.s5[i] = make_int4(e.step_count, e.physics_steps, ent.y, e.tidx);
+        }
+        __syncwarp();
+    }
+    if (whole_batch == 0) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(blocks_done, 1) == (int)gridDim.x - 1) { *count = 0; *blocks_done = 0; __threadfence(); }
+        }
     }
 }
 
@@ -1017,8 +1178,8 @@ cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act
 
 // Append one random-action step launch to a CUDA graph (explicit node: works without stream capture, so the
 // graph can later be launched on any stream including the legacy default stream torch hands us).
-cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* dep, const FwDev& p, const FwPlanes& pl, int spl,
-                                      cudaGraphNode_t* out) {
+cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* deps, int ndeps, const FwDev& p, const FwPlanes& pl,
+                                      int spl, cudaGraphNode_t* out) {
     const StepLaunch L = step_launch(p, true);
     if (L.fn == nullptr) return cudaErrorNotSupported;
     if (!smem_opt_in((const void*)L.fn, L.smem)) return cudaErrorInvalidValue;
@@ -1033,7 +1194,51 @@ cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* dep, const
     kp.gridDim = dim3((n + L.envs_per_block - 1) / L.envs_per_block); kp.blockDim = dim3(L.threads);
     kp.sharedMemBytes = (unsigned)L.smem;
     kp.kernelParams = args; kp.extra = nullptr;
-    return cudaGraphAddKernelNode(out, g, dep, dep ? 1 : 0, &kp);
+    return cudaGraphAddKernelNode(out, g, deps, ndeps, &kp);
+}
+
+static int refill_grid(int work, bool whole_batch) {
+    const int per_block = (FW_BLOCK / 32) * (whole_batch ? 32 : OL_REFILL_PER_WARP);
+    const int grid = (work + per_block - 1) / per_block;
+    const int gmax = whole_batch ? 1036 : FW_REFILL_GRID;
+    return grid > gmax ? gmax : (grid < 1 ? 1 : grid);
+}
+
+// serve a request list (whole_batch == 0) or prepare the next episode of every env (whole_batch = n, right after fw_create)
+cudaError_t fwk_launch_refill(const FwDev& p, const FwPlanes& pl, const int2* list, int* count, int* blocks_done, int cap,
+                              int whole_batch, cudaStream_t st) {
+    if (p.task != 2 && p.task != 4) return cudaErrorNotSupported;
+    auto fn = p.task == 2 ? fw_refill_objlock_kernel<2> : fw_refill_objlock_kernel<4>;
+    if (!smem_opt_in((const void*)fn, stage_bytes(p))) return cudaErrorInvalidValue;
+    fn<<<refill_grid(whole_batch > 0 ? whole_batch : cap, whole_batch > 0), FW_BLOCK, stage_bytes(p), st>>>(p, pl, list, count, blocks_done,
+                                                                                                          cap, whole_batch);
+    return cudaGetLastError();
+}
+
+cudaError_t fwk_graph_add_refill(cudaGraph_t g, cudaGraphNode_t* deps, int ndeps, const FwDev& p, const FwPlanes& pl,
+                                 const int2* list, int* count, int* blocks_done, int cap, cudaGraphNode_t* out) {
+    auto fn = p.task == 2 ? fw_refill_objlock_kernel<2> : fw_refill_objlock_kernel<4>;
+    if (!smem_opt_in((const void*)fn, stage_bytes(p))) return cudaErrorInvalidValue;
+    FwDev pc = p; FwPlanes plc = pl;
+    const int2* l = list; int* c = count; int* bd = blocks_done; int cap_ = cap, wb = 0;
+    void* args[] = {&pc, &plc, &l, &c, &bd, &cap_, &wb};
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.func = (void*)fn;
+    kp.gridDim = dim3(refill_grid(cap, false)); kp.blockDim = dim3(FW_BLOCK);
+    kp.sharedMemBytes = (unsigned)stage_bytes(p);
+    kp.kernelParams = args; kp.extra = nullptr;
+    cudaError_t e = cudaGraphAddKernelNode(out, g, deps, ndeps, &kp);
+    if (e != cudaSuccess) return e;
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess && lo != hi) {
+        cudaKernelNodeAttrValue v;
+        memset(&v, 0, sizeof(v));
+        v.priority = lo;                               // numerically largest = lowest priority: the step's blocks go first
+        (void)cudaGraphKernelNodeSetAttribute(*out, cudaLaunchAttributePriority, &v);
+        (void)cudaGetLastError();
+    }
+    return cudaSuccess;
 }
 
 cudaError_t fwk_launch_reset(const FwDev& p, const FwPlanes& pl, const uint8_t* mask, float* obs, bool emit_only,

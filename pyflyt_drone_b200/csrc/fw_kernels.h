@@ -8,9 +8,13 @@ struct FwPlanes;
 
 cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act, float* obs, float* rew, uint8_t* flg,
                             float* term_obs, bool random_act, int spl, cudaStream_t st);
-cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* dep, const FwDev& p, const FwPlanes& pl, int spl,
-                                      cudaGraphNode_t* out);
+cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* deps, int ndeps, const FwDev& p, const FwPlanes& pl,
+                                      int spl, cudaGraphNode_t* out);
 cudaError_t fwk_launch_reset(const FwDev& p, const FwPlanes& pl, const uint8_t* mask, float* obs, bool emit_only,
                              cudaStream_t st);
+cudaError_t fwk_launch_refill(const FwDev& p, const FwPlanes& pl, const int2* list, int* count, int* blocks_done, int cap,
+                              int whole_batch, cudaStream_t st);
+cudaError_t fwk_graph_add_refill(cudaGraph_t g, cudaGraphNode_t* deps, int ndeps, const FwDev& p, const FwPlanes& pl,
+                                 const int2* list, int* count, int* blocks_done, int cap, cudaGraphNode_t* out);
 cudaError_t fwk_launch_warm(const FwDev& p, const FwPlanes& pl, float* out, cudaStream_t st);
 cudaError_t fwk_fma_peak(int sm_count, int iters, float* scratch, double* flops_per_launch, cudaStream_t st);

@@ -325,6 +325,12 @@ class FixedwingVecEnv(VecEnv):
         _lib.check(self.lib.fw_fault_count(self._h, C.byref(out)))
         return int(out.value)
 
+    def spare_stats(self) -> dict[str, int]:
+        """Camera tasks: in-step auto-resets served from a pre-warmed spare episode / inline (fw_spare_stats)."""
+        out = (C.c_int64 * 2)()
+        _lib.check(self.lib.fw_spare_stats(self._h, out))
+        return {"from_spare": int(out[0]), "inline": int(out[1])}
+
     def step_random(self, n_steps: int = 1, with_outputs: bool = False):
         """Random-action workload (BASELINE config 2): actions drawn in-kernel, one launch per env-step."""
         t = self._tensors() if with_outputs else None
