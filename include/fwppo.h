@@ -60,7 +60,7 @@ int ppo_policy_forward_tc(const float* params, int32_t d, const float* obs_raw, 
 
 /* Wide-action variants: action width a = 4 or 6.  a = 6 is the low-level env's MlpPolicy
  * (train/train_lowlevel_cmd.py: FixedwingLowLevelEnv, Box(6) actions); the parameter vector has the layout above with
- * A = a, the action buffers are [n, a].  The fused update kernel (ppo_minibatch_grad) is built for a = 4. */
+ * A = a, the action buffers are [n, a]. */
 int ppo_param_count_a(int32_t d, int32_t a);
 int ppo_policy_forward_a(const float* params, int32_t d, int32_t a, const float* obs_raw, const double* obs_stats,
                          float clip_obs, int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev,
@@ -113,6 +113,13 @@ int ppo_random_permutation(int64_t* out, int64_t n, uint64_t seed, uint64_t epoc
  * stats[8] (may be NULL) = sums over the minibatch of {policy loss, squared value error, approx KL, clipped,
  * ratio, samples, 0, 0}.  workspace: ppo_update_workspace_floats(d) floats, 16-byte aligned, zero on first use. */
 int ppo_update_workspace_floats(int32_t d);
+/* action width a = 4 or 6 (the six-channel MlpPolicy of train/train_lowlevel_cmd.py:97-110): parameter vector, action
+ * rows and gradient in the layout above with A = a */
+int ppo_update_workspace_floats_a(int32_t d, int32_t a);
+int ppo_minibatch_grad_a(const float* params, int32_t d, int32_t a, const float* obs_norm, const float* act,
+                         const float* logp_old, const float* adv, const float* ret, const int64_t* idx, int32_t batch,
+                         float clip_range, float ent_coef, float vf_coef, float* workspace, float* grad, float* stats,
+                         void* stream);
 int ppo_minibatch_grad(const float* params, int32_t d, const float* obs_norm, const float* act, const float* logp_old,
                        const float* adv, const float* ret, const int64_t* idx, int32_t batch, float clip_range,
                        float ent_coef, float vf_coef, float* workspace, float* grad, float* stats, void* stream);

@@ -23,6 +23,8 @@ PPO_SYMBOLS = [
     ("ppo_reward_normalize", C.c_int, [_P, _P, C.c_int32, _F, _F, _P, _P, _P, _P, _P, _P, _P]),
     ("ppo_timeout_bootstrap", C.c_int, [_P, C.c_int32, _P, _P, _F, _P, C.c_int32, _F, _P, _P, _P]),
     ("ppo_update_workspace_floats", C.c_int, [C.c_int32]),
+    ("ppo_update_workspace_floats_a", C.c_int, [C.c_int32, C.c_int32]),
+    ("ppo_minibatch_grad_a", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, _F, _F, _F, _P, _P, _P, _P]),
     ("ppo_minibatch_grad", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, _F, _F, _F, _P, _P, _P, _P]),
     ("ppo_adam_step", C.c_int, [_P, _P, _P, _P, C.c_int32, _F, _F, _F, _F, _F, _F, _P, _P, _P]),
     ("ppo_gae", C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _F, _F, _P, _P, _P]),

@@ -199,29 +199,44 @@ extern "C" int ppo_counter_add(uint32_t* counter, uint32_t inc, void* stream) {
 
 // workspace layout (floats): [0,8) two doubles+pad as scratch (must start zeroed) | [8,16) adv stats |
 // [16, 16 + 160*P) per-CTA gradient partials | then 160*8 per-CTA loss statistics
-extern "C" int ppo_update_workspace_floats(int32_t d) { return 16 + 160 * ppo_param_count(d) + 160 * 8; }
+extern "C" int ppo_update_workspace_floats_a(int32_t d, int32_t a) { return 16 + 160 * ppo_param_count_a(d, a) + 160 * 8; }
+extern "C" int ppo_update_workspace_floats(int32_t d) { return ppo_update_workspace_floats_a(d, PPO_ACT); }
 
-extern "C" int ppo_minibatch_grad(const float* params, int32_t d, const float* obs_norm, const float* act,
-                                  const float* logp_old, const float* adv, const float* ret, const int64_t* idx,
-                                  int32_t batch, float clip_range, float ent_coef, float vf_coef, float* workspace,
-                                  float* grad, float* stats, void* stream) {
+extern "C" int ppo_minibatch_grad_a(const float* params, int32_t d, int32_t a, const float* obs_norm, const float* act,
+                                    const float* logp_old, const float* adv, const float* ret, const int64_t* idx,
+                                    int32_t batch, float clip_range, float ent_coef, float vf_coef, float* workspace,
+                                    float* grad, float* stats, void* stream) {
     if (!params || !obs_norm || !act || !logp_old || !adv || !ret || !idx || !workspace || !grad)
         return pfail(FW_EINVAL, "null argument");
     if (batch <= 0) return pfail(FW_EINVAL, "batch must be positive");
     int rc = check_d_tc(d);
     if (rc) return rc;
+    if ((rc = check_a(a)) != 0) return rc;
     if ((reinterpret_cast<uintptr_t>(workspace) & 15u) || (reinterpret_cast<uintptr_t>(act) & 15u))
         return pfail(FW_EINVAL, "workspace and action buffer must be 16-byte aligned");
-    const int P = ppo_param_count(d);
+    const int P = ppo_param_count_a(d, a);
     if (ppok_update_grid(batch) > 160) return pfail(FW_ESTATE, "more SMs than the workspace was sized for");
     double* scratch = reinterpret_cast<double*>(workspace);
     float* adv_stats = workspace + 8;
     float* partial = workspace + 16;
     float* stats_partial = partial + (size_t)160 * P;
-    PCU(ppok_minibatch_grad(params, d, obs_norm, act, logp_old, adv, ret, reinterpret_cast<const long long*>(idx), batch,
-                            clip_range, ent_coef, vf_coef, scratch, adv_stats, partial, stats_partial, grad, stats,
-                            (cudaStream_t)stream));
+    if (a == 4)
+        PCU(ppo_a4::ppok_minibatch_grad(params, d, obs_norm, act, logp_old, adv, ret, reinterpret_cast<const long long*>(idx), batch,
+                                        clip_range, ent_coef, vf_coef, scratch, adv_stats, partial, stats_partial, grad, stats,
+                                        (cudaStream_t)stream));
+    else
+        PCU(ppo_a6::ppok_minibatch_grad(params, d, obs_norm, act, logp_old, adv, ret, reinterpret_cast<const long long*>(idx), batch,
+                                        clip_range, ent_coef, vf_coef, scratch, adv_stats, partial, stats_partial, grad, stats,
+                                        (cudaStream_t)stream));
     return FW_OK;
+}
+
+extern "C" int ppo_minibatch_grad(const float* params, int32_t d, const float* obs_norm, const float* act,
+                                  const float* logp_old, const float* adv, const float* ret, const int64_t* idx,
+                                  int32_t batch, float clip_range, float ent_coef, float vf_coef, float* workspace,
+                                  float* grad, float* stats, void* stream) {
+    return ppo_minibatch_grad_a(params, d, PPO_ACT, obs_norm, act, logp_old, adv, ret, idx, batch, clip_range, ent_coef, vf_coef,
+                                workspace, grad, stats, stream);
 }
 
 extern "C" int ppo_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t n_params, float lr,

@@ -17,17 +17,34 @@
 //             tanh' is recomputed from the fp32 pre-activations kept in TMEM, not from rounded activations.)
 // Both towers are stacked along M (= 128 output neurons) for the weight gradients, which accumulate in TMEM
 // across all tiles of the CTA and are read out once at the end into a per-CTA partial gradient.
+// The file is compiled once per supported action width (ppo_update_tc_a6.cu includes it with PPO_A_BUILD = 6: the
+// six-channel MlpPolicy of train/train_lowlevel_cmd.py:97-110); the gradient kernel and its launcher live in a namespace
+// named after the width, the width-independent kernels (advantage statistics, partial reduction, Adam) in the first build.
 #include "ppo_kernels.h"
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#ifndef PPO_A_BUILD
+#define PPO_A_BUILD 4
+#endif
+#if PPO_A_BUILD == 4
+#define PPO_UT_NS ppo_a4
+#elif PPO_A_BUILD == 6
+#define PPO_UT_NS ppo_a6
+#else
+#error "action width must be 4 or 6"
+#endif
+
 #define H PPO_H
-#define A PPO_A
+#define A PPO_A_BUILD
+#define AP ((A + 3) / 4 * 4)      // action width padded to whole float4s
 #define DP PPO_DPAD
 #define UT_ROWS 128
 #define UT_THREADS 512
 #define UT_TMEM_COLS 512
+
+namespace PPO_UT_NS {
 
 __device__ __forceinline__ uint32_t ut_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -168,8 +185,13 @@ struct UtSmem {
     static constexpr int W2B_VF = W2B_PI + H * H * 2;
     static constexpr int SMALL = W2B_VF + H * H * 2;
     // floats inside SMALL
-    static constexpr int B1 = 0 /* pi 64 | vf 64 */, B2 = 128, W3_PI = 256 /* [64][4]: one float4 per hidden unit */, W3_VF = 512, B3_PI = 576, B3_VF = 580,
-                         LOGSTD = 584, RED = 592 /* 24 block-reduction slots */, BAR = 616, TPTR = 620, NSMALL = 624;
+    static constexpr int B1 = 0 /* pi 64 | vf 64 */, B2 = 128, W3_PI = 256 /* [64][AP]: AP/4 float4s per hidden unit */,
+                         W3_VF = W3_PI + H * AP, B3_PI = W3_VF + H, B3_VF = B3_PI + AP, LOGSTD = B3_VF + 4,
+                         RED = LOGSTD + AP /* 24 block-reduction slots */, BAR = RED + 24, TPTR = BAR + 4, NSMALL = TPTR + 4;
+    // the layer-1 operand buffer XB is dead after M1 and then carries, per tile: the policy-head partial sums of warpgroups
+    // 0 and 1 (AP floats per row each), the value-head partials of warpgroups 2 and 3, and each row's loss inputs
+    static constexpr int PS_PI = 0, PS_VF = PS_PI + 2 * UT_ROWS * AP * 4, LIN = PS_VF + 2 * UT_ROWS * 4, LIN_ROW = (AP + 4) * 4;
+    static_assert(LIN + UT_ROWS * LIN_ROW <= UT_ROWS * DP * 4, "head partials + loss inputs must fit the layer-1 operand buffer");
     static constexpr int TOTAL = SMALL + NSMALL * 4;
 };
 
@@ -179,9 +201,9 @@ struct UtSmem {
 #define UT_DA 256    // 64 : [dZ2]^T H1_pi   (rows 0-63 = dW2_pi)
 #define UT_DB 320    // 64 : [dZ2]^T H1_vf   (rows 64-127 = dW2_vf)
 #define UT_DW1 384   // 32 : [dZ1]^T X       (rows 0-63 dW1_pi, 64-127 dW1_vf)
-#define UT_D3 416    // 16 : [H2]^T dOut     (rows 0-63 x cols 0-3 = dW3_pi^T ; rows 64-127 x col 4 = dW3_vf)
-#define UT_DB2 432   // 16 : [dZ2]^T dOut|1  (col 5 = db2)
-#define UT_DB1 448   // 16 : [dZ1]^T dOut|1  (col 5 = db1)
+#define UT_D3 416    // 16 : [H2]^T dOut     (rows 0-63 x cols 0..A-1 = dW3_pi^T ; rows 64-127 x col A = dW3_vf)
+#define UT_DB2 432   // 16 : [dZ2]^T dOut|1  (col A+1 = db2)
+#define UT_DB1 448   // 16 : [dZ1]^T dOut|1  (col A+1 = db1)
 
 __device__ void ut_load_weight(char* smem, int off, const float* __restrict__ g, int K, int d, int off_bf16 = -1) {
     for (int i = threadIdx.x; i < H * K; i += blockDim.x) {
@@ -256,7 +278,10 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         small[UtSmem::B2 + H + tid] = g_vf[H * d + H + H * H + tid];
         small[UtSmem::W3_VF + tid] = g_vf[H * d + H + H * H + H + tid];
     }
-    for (int i = tid; i < A * H; i += blockDim.x) small[UtSmem::W3_PI + (i % H) * A + i / H] = g_pi[H * d + H + H * H + H + i];   // [j][a]
+    for (int i = tid; i < AP * H; i += blockDim.x) {                                               // [j][a], zero padded to AP
+        const int j = i / AP, a = i % AP;
+        small[UtSmem::W3_PI + i] = a < A ? g_pi[H * d + H + H * H + H + a * H + j] : 0.0f;
+    }
     if (tid < A) {
         small[UtSmem::B3_PI + tid] = g_pi[H * d + H + H * H + H + A * H + tid];
         small[UtSmem::LOGSTD + tid] = params[pi_count + vf_count + tid];
@@ -285,7 +310,9 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
     const float adv_mean = adv_stats[0], adv_istd = 1.0f / (adv_stats[1] + 1e-8f);
 
     // per-thread running sums over this CTA's samples (warpgroup 0 only): db3_pi[4], db3_vf, dlogstd[4], loss statistics[6]
-    float acc_db3[A] = {0.f, 0.f, 0.f, 0.f}, acc_db3v = 0.f, acc_dls[A] = {0.f, 0.f, 0.f, 0.f};
+    float acc_db3[A], acc_db3v = 0.f, acc_dls[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) { acc_db3[a] = 0.f; acc_dls[a] = 0.f; }
     float st_pl = 0.f, st_vl = 0.f, st_kl = 0.f, st_clip = 0.f, st_ratio = 0.f, st_n = 0.f;
 
     const int ntiles = (batch + UT_ROWS - 1) / UT_ROWS;
@@ -344,10 +371,19 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         // that they fly under E1, M2 and E2, and shared through smem next to the head partials
         const int srow = tile * UT_ROWS + row;
         const bool live = srow < batch;
-        float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float av[AP];
+#pragma unroll
+        for (int a = 0; a < AP; ++a) av[a] = 0.f;
         float lpo = 0.f, advv = 0.f, retv = 0.f;
         if (q == 0 && live) {
-            a4 = reinterpret_cast<const float4*>(act)[g_loss];
+            if (A == 4) {
+                const float4 a4 = reinterpret_cast<const float4*>(act)[g_loss];
+                av[0] = a4.x; av[1] = a4.y; av[2] = a4.z; av[3] = a4.w;
+            } else {                                      // rows of A floats: 8-byte aligned for even A
+                const float2* ap = reinterpret_cast<const float2*>(act + (size_t)g_loss * A);
+#pragma unroll
+                for (int a = 0; a < A / 2; ++a) { const float2 t = ap[a]; av[2 * a] = t.x; av[2 * a + 1] = t.y; }
+            }
             lpo = logp_old[g_loss]; advv = adv[g_loss]; retv = ret[g_loss];
         }
         // ---- E1: H1 = tanh(z1 + b1): fp32 for the forward, bf16 for the weight gradient of layer 2; keep 1 - H1^2
@@ -387,7 +423,9 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         {
             float v[32];
             ut_ld32(tmem + UT_T2 + lane_base + q * 32, v);
-            float ps[A] = {0.f, 0.f, 0.f, 0.f};
+            float ps[AP];
+#pragma unroll
+            for (int a = 0; a < AP; ++a) ps[a] = 0.f;
 #pragma unroll
             for (int c8 = 0; c8 < 4; ++c8) {
                 const int j = q * 32 + 8 * c8;
@@ -399,9 +437,12 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
                 if (q < 2) {
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        const float4 w = *reinterpret_cast<const float4*>(small + UtSmem::W3_PI + (j + r) * A);
-                        ps[0] = fmaf(w.x, h[r], ps[0]); ps[1] = fmaf(w.y, h[r], ps[1]);
-                        ps[2] = fmaf(w.z, h[r], ps[2]); ps[3] = fmaf(w.w, h[r], ps[3]);
+#pragma unroll
+                        for (int a4i = 0; a4i < AP / 4; ++a4i) {
+                            const float4 w = *reinterpret_cast<const float4*>(small + UtSmem::W3_PI + (j + r) * AP + 4 * a4i);
+                            ps[4 * a4i + 0] = fmaf(w.x, h[r], ps[4 * a4i + 0]); ps[4 * a4i + 1] = fmaf(w.y, h[r], ps[4 * a4i + 1]);
+                            ps[4 * a4i + 2] = fmaf(w.z, h[r], ps[4 * a4i + 2]); ps[4 * a4i + 3] = fmaf(w.w, h[r], ps[4 * a4i + 3]);
+                        }
                     }
                 } else {
                     const float4 wa = *reinterpret_cast<const float4*>(small + UtSmem::W3_VF + j - H), wb = *reinterpret_cast<const float4*>(small + UtSmem::W3_VF + j - H + 4);
@@ -413,32 +454,51 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
                 for (int r = 0; r < 4; ++r)
                     d2p[4 * c8 + r] = ut_pack2(fmaf(-h[2 * r], h[2 * r], 1.0f), fmaf(-h[2 * r + 1], h[2 * r + 1], 1.0f));
             }
-            // XB is dead after M1: its first 8 KB carry the head partials of the four warpgroups, the next 4 KB the
-            // loss inputs of each row
-            *reinterpret_cast<float4*>(smem + UtSmem::XB + (q * UT_ROWS + row) * 16) = make_float4(ps[0], ps[1], ps[2], ps[3]);
+            // XB is dead after M1: it carries the head partials of the four warpgroups and the loss inputs of each row
+            if (q < 2) {
+#pragma unroll
+                for (int a4i = 0; a4i < AP / 4; ++a4i)
+                    *reinterpret_cast<float4*>(smem + UtSmem::XB + UtSmem::PS_PI + ((q * UT_ROWS + row) * AP + 4 * a4i) * 4) =
+                        make_float4(ps[4 * a4i], ps[4 * a4i + 1], ps[4 * a4i + 2], ps[4 * a4i + 3]);
+            } else {
+                *reinterpret_cast<float*>(smem + UtSmem::XB + UtSmem::PS_VF + ((q - 2) * UT_ROWS + row) * 4) = ps[0];
+            }
             if (q == 0) {
-                *reinterpret_cast<float4*>(smem + UtSmem::XB + 8192 + row * 32) = a4;
-                *reinterpret_cast<float4*>(smem + UtSmem::XB + 8192 + row * 32 + 16) = make_float4(lpo, advv, retv, 0.f);
+                char* lin = smem + UtSmem::XB + UtSmem::LIN + row * UtSmem::LIN_ROW;
+#pragma unroll
+                for (int a4i = 0; a4i < AP / 4; ++a4i)
+                    *reinterpret_cast<float4*>(lin + 16 * a4i) = make_float4(av[4 * a4i], av[4 * a4i + 1], av[4 * a4i + 2], av[4 * a4i + 3]);
+                *reinterpret_cast<float4*>(lin + AP * 4) = make_float4(lpo, advv, retv, 0.f);
             }
         }
         __syncthreads();
         if (q != 0) {
-            a4 = *reinterpret_cast<const float4*>(smem + UtSmem::XB + 8192 + row * 32);
-            const float4 t = *reinterpret_cast<const float4*>(smem + UtSmem::XB + 8192 + row * 32 + 16);
+            const char* lin = smem + UtSmem::XB + UtSmem::LIN + row * UtSmem::LIN_ROW;
+#pragma unroll
+            for (int a4i = 0; a4i < AP / 4; ++a4i) {
+                const float4 t = *reinterpret_cast<const float4*>(lin + 16 * a4i);
+                av[4 * a4i] = t.x; av[4 * a4i + 1] = t.y; av[4 * a4i + 2] = t.z; av[4 * a4i + 3] = t.w;
+            }
+            const float4 t = *reinterpret_cast<const float4*>(lin + AP * 4);
             lpo = t.x; advv = t.y; retv = t.z;
         }
         // ---- losses and their gradients w.r.t. the head outputs (stable_baselines3 PPO.train)
-        float dout[A] = {0.f, 0.f, 0.f, 0.f}, doutv = 0.f;     // pre-scaled by grad_scale
+        float dout[AP], doutv = 0.f;     // pre-scaled by grad_scale
+#pragma unroll
+        for (int a = 0; a < AP; ++a) dout[a] = 0.f;
         {
-            const float4 p0 = *reinterpret_cast<const float4*>(smem + UtSmem::XB + (0 * UT_ROWS + row) * 16);
-            const float4 p1 = *reinterpret_cast<const float4*>(smem + UtSmem::XB + (1 * UT_ROWS + row) * 16);
-            const float pv0 = *reinterpret_cast<const float*>(smem + UtSmem::XB + (2 * UT_ROWS + row) * 16);
-            const float pv1 = *reinterpret_cast<const float*>(smem + UtSmem::XB + (3 * UT_ROWS + row) * 16);
-            const float mean[A] = {small[UtSmem::B3_PI + 0] + p0.x + p1.x, small[UtSmem::B3_PI + 1] + p0.y + p1.y,
-                                   small[UtSmem::B3_PI + 2] + p0.z + p1.z, small[UtSmem::B3_PI + 3] + p0.w + p1.w};
+            float mean[AP];
+#pragma unroll
+            for (int a4i = 0; a4i < AP / 4; ++a4i) {
+                const float4 p0 = *reinterpret_cast<const float4*>(smem + UtSmem::XB + UtSmem::PS_PI + ((0 * UT_ROWS + row) * AP + 4 * a4i) * 4);
+                const float4 p1 = *reinterpret_cast<const float4*>(smem + UtSmem::XB + UtSmem::PS_PI + ((1 * UT_ROWS + row) * AP + 4 * a4i) * 4);
+                mean[4 * a4i + 0] = small[UtSmem::B3_PI + 4 * a4i + 0] + p0.x + p1.x; mean[4 * a4i + 1] = small[UtSmem::B3_PI + 4 * a4i + 1] + p0.y + p1.y;
+                mean[4 * a4i + 2] = small[UtSmem::B3_PI + 4 * a4i + 2] + p0.z + p1.z; mean[4 * a4i + 3] = small[UtSmem::B3_PI + 4 * a4i + 3] + p0.w + p1.w;
+            }
+            const float pv0 = *reinterpret_cast<const float*>(smem + UtSmem::XB + UtSmem::PS_VF + (0 * UT_ROWS + row) * 4);
+            const float pv1 = *reinterpret_cast<const float*>(smem + UtSmem::XB + UtSmem::PS_VF + (1 * UT_ROWS + row) * 4);
             const float val = small[UtSmem::B3_VF] + pv0 + pv1;
             if (live) {
-                const float av[A] = {a4.x, a4.y, a4.z, a4.w};
                 float z[A], sinv[A], lp = 0.0f;
 #pragma unroll
                 for (int a = 0; a < A; ++a) {
@@ -470,9 +530,10 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
                 doutv = dv * cfg.grad_scale;
             }
             if (q == 0) {
-                // dOut row (bf16): [dmean0..3, dvalue, 1, 0...]; the ones column turns the same MMAs into bias-gradient sums
-                float row16[16] = {dout[0], dout[1], dout[2], dout[3], doutv, live ? 1.0f : 0.0f, 0.f, 0.f,
-                                   0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                // dOut row (bf16): [dmean0..A-1, dvalue, 1, 0...]; the ones column turns the same MMAs into bias-gradient sums
+                float row16[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) row16[c] = c < A ? dout[c] : (c == A ? doutv : (c == A + 1 ? (live ? 1.0f : 0.0f) : 0.0f));
                 *reinterpret_cast<uint4*>(smem + UtSmem::DO + ut_off16(row, 0, 16)) = ut_pack8(row16);
                 *reinterpret_cast<uint4*>(smem + UtSmem::DO + ut_off16(row, 8, 16)) = ut_pack8(row16 + 8);
             }
@@ -493,8 +554,12 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
                 for (int r = 0; r < 8; ++r) {
                     float dh;
                     if (q < 2) {
-                        const float4 w = *reinterpret_cast<const float4*>(small + UtSmem::W3_PI + (j + r) * A);
-                        dh = dout[0] * w.x + dout[1] * w.y + dout[2] * w.z + dout[3] * w.w;
+                        dh = 0.0f;
+#pragma unroll
+                        for (int a4i = 0; a4i < AP / 4; ++a4i) {
+                            const float4 w = *reinterpret_cast<const float4*>(small + UtSmem::W3_PI + (j + r) * AP + 4 * a4i);
+                            dh += dout[4 * a4i] * w.x + dout[4 * a4i + 1] * w.y + dout[4 * a4i + 2] * w.z + dout[4 * a4i + 3] * w.w;
+                        }
                     } else {
                         dh = doutv * wv[r];
                     }
@@ -589,14 +654,14 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
 #pragma unroll
                 for (int a = 0; a < A; ++a) outp[o_w3 + a * H + j] = v3[a] * cfg.inv_grad_scale;
             } else {
-                outp[o_w3 + j] = v3[4] * cfg.inv_grad_scale;
+                outp[o_w3 + j] = v3[A] * cfg.inv_grad_scale;
             }
         } else {               // hidden biases (ones column)
             float vb2[16], vb1[16];
             ut_ld16(tmem + UT_DB2 + lane_base, vb2);
             ut_ld16(tmem + UT_DB1 + lane_base, vb1);
-            outp[o_b2 + j] = vb2[5] * cfg.inv_grad_scale;
-            outp[o_b1 + j] = vb1[5] * cfg.inv_grad_scale;
+            outp[o_b2 + j] = vb2[A + 1] * cfg.inv_grad_scale;
+            outp[o_b1 + j] = vb1[A + 1] * cfg.inv_grad_scale;
         }
     } else {
         // this CTA had no tile: its partial is all zeros
@@ -604,10 +669,15 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
     }
     // small sums (held by warpgroup 0): warp shuffle then shared atomics (24 slots), then threads 0..23 write them
     if (q == 0) {
-        float red[15] = {acc_db3[0], acc_db3[1], acc_db3[2], acc_db3[3], acc_db3v, acc_dls[0], acc_dls[1], acc_dls[2], acc_dls[3],
-                         st_pl, st_vl, st_kl, st_clip, st_ratio, st_n};
+        // slots: db3_pi[A], db3_vf, dlog_std[A], then the six loss statistics
+        float red[2 * A + 7];
 #pragma unroll
-        for (int k = 0; k < 15; ++k) {
+        for (int a = 0; a < A; ++a) { red[a] = acc_db3[a]; red[A + 1 + a] = acc_dls[a]; }
+        red[A] = acc_db3v;
+        red[2 * A + 1] = st_pl; red[2 * A + 2] = st_vl; red[2 * A + 3] = st_kl; red[2 * A + 4] = st_clip; red[2 * A + 5] = st_ratio;
+        red[2 * A + 6] = st_n;
+#pragma unroll
+        for (int k = 0; k < 2 * A + 7; ++k) {
             float x = red[k];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
@@ -619,18 +689,21 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
     if (tid < A) {
         outp[pi_count - A + tid] = small[UtSmem::RED + tid];                                  // db3_pi
         // entropy bonus: loss += -ent_coef * mean(entropy), d/dlog_std = -ent_coef (added once, by CTA 0)
-        outp[pi_count + vf_count + tid] = small[UtSmem::RED + 5 + tid] + (blockIdx.x == 0 ? -cfg.ent_coef : 0.0f);
+        outp[pi_count + vf_count + tid] = small[UtSmem::RED + A + 1 + tid] + (blockIdx.x == 0 ? -cfg.ent_coef : 0.0f);
     }
-    if (tid == 0) outp[pi_count + vf_count - 1] = small[UtSmem::RED + 4];                     // db3_vf
+    if (tid == 0) outp[pi_count + vf_count - 1] = small[UtSmem::RED + A];                     // db3_vf
     if (tid < 8) {
         float v = 0.0f;
-        if (tid < 6) v = small[UtSmem::RED + 9 + tid];
+        if (tid < 6) v = small[UtSmem::RED + 2 * A + 1 + tid];
         out_stats[(size_t)blockIdx.x * 8 + tid] = v;
     }
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)UT_TMEM_COLS) : "memory");
 }
 
+}  // namespace PPO_UT_NS
+
+#if PPO_A_BUILD == 4
 // ------------------------------------------------------------------ minibatch advantage statistics (mean, unbiased std)
 __global__ void __launch_bounds__(256)
 ppo_adv_stats_kernel(const float* __restrict__ adv, const long long* __restrict__ idx, int batch, double* __restrict__ scratch,
@@ -747,42 +820,26 @@ ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, floa
 }
 
 // ------------------------------------------------------------------ launchers
-static int g_ut_sm_count = 0;
+static int g_ut_sm_count_shared = 0;
 
 int ppok_update_grid(int batch) {
-    if (g_ut_sm_count == 0) {
+    if (g_ut_sm_count_shared == 0) {
         int dev = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-        if (cudaDeviceGetAttribute(&g_ut_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-        if (cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL) != cudaSuccess) {
-            g_ut_sm_count = 0;
-            return -1;
-        }
+        if (cudaDeviceGetAttribute(&g_ut_sm_count_shared, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     }
     const int ntiles = (batch + UT_ROWS - 1) / UT_ROWS;
-    return ntiles < g_ut_sm_count ? ntiles : g_ut_sm_count;
+    return ntiles < g_ut_sm_count_shared ? ntiles : g_ut_sm_count_shared;
 }
 
-cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, const float* act, const float* logp_old,
-                                const float* adv, const float* ret, const long long* idx, int batch, float clip_range,
-                                float ent_coef, float vf_coef, double* scratch, float* adv_stats, float* partial,
-                                float* stats_partial, float* grad, float* stats, cudaStream_t st) {
-    const int grid = ppok_update_grid(batch);
-    if (grid <= 0) return cudaErrorUnknown;
-    const int H_ = PPO_H, A_ = PPO_A;
-    const int P = (H_ * d + H_ + H_ * H_ + H_ + A_ * H_ + A_) + (H_ * d + H_ + H_ * H_ + H_ + H_ + 1) + A_;
+void ppok_launch_adv_stats(const float* adv, const long long* idx, int batch, double* scratch, float* adv_stats, cudaStream_t st) {
     int sblocks = (batch + 255) / 256;            // one gathered element per thread up to 4 blocks per SM
     if (sblocks > 592) sblocks = 592;
     ppo_adv_stats_kernel<<<sblocks, 256, 0, st>>>(adv, idx, batch, scratch, adv_stats);
-    // per-sample head gradients carry a 1/batch factor; rescale them to O(1) before the bf16 rounding of the backward
-    // operands (a power of two, so the scaling itself is exact) and undo it when the accumulators are read out
-    float gs = 1.0f;
-    while (gs < (float)batch && gs < 1048576.0f) gs *= 2.0f;
-    PpoLossCfg cfg{clip_range, ent_coef, vf_coef, 1.0f / (float)batch, gs, 1.0f / gs};
-    ppo_grad_tc_kernel<<<grid, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, adv_stats, cfg,
-                                                             partial, stats_partial, P);
+}
+
+void ppok_launch_grad_reduce(const float* partial, const float* stats_partial, int grid, int P, float* grad, float* stats, cudaStream_t st) {
     ppo_grad_reduce_kernel<<<(P + RED_KX - 1) / RED_KX, RED_KX * RED_CY, 0, st>>>(partial, stats_partial, grid, P, grad, stats);
-    return cudaGetLastError();
 }
 
 cudaError_t ppok_adam(float* params, const float* grad, float* m, float* v, int P, float lr, float beta1, float beta2, float eps,
@@ -791,3 +848,36 @@ cudaError_t ppok_adam(float* params, const float* grad, float* m, float* v, int 
     ppo_adam_kernel<<<1, ADAM_THREADS, 0, st>>>(params, grad, m, v, P, lr, beta1, beta2, eps, max_norm, grad_scale, step_ctr, norm_out);
     return cudaGetLastError();
 }
+#endif  // PPO_A_BUILD == 4
+
+void ppok_launch_adv_stats(const float* adv, const long long* idx, int batch, double* scratch, float* adv_stats, cudaStream_t st);
+void ppok_launch_grad_reduce(const float* partial, const float* stats_partial, int grid, int P, float* grad, float* stats, cudaStream_t st);
+
+namespace PPO_UT_NS {
+static bool g_ut_attr_set = false;
+
+cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, const float* act, const float* logp_old,
+                                const float* adv, const float* ret, const long long* idx, int batch, float clip_range,
+                                float ent_coef, float vf_coef, double* scratch, float* adv_stats, float* partial,
+                                float* stats_partial, float* grad, float* stats, cudaStream_t st) {
+    if (!g_ut_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL);
+        if (e != cudaSuccess) return e;
+        g_ut_attr_set = true;
+    }
+    const int grid = ppok_update_grid(batch);
+    if (grid <= 0) return cudaErrorUnknown;
+    const int H_ = PPO_H, A_ = A;
+    const int P = (H_ * d + H_ + H_ * H_ + H_ + A_ * H_ + A_) + (H_ * d + H_ + H_ * H_ + H_ + H_ + 1) + A_;
+    ppok_launch_adv_stats(adv, idx, batch, scratch, adv_stats, st);
+    // per-sample head gradients carry a 1/batch factor; rescale them to O(1) before the bf16 rounding of the backward
+    // operands (a power of two, so the scaling itself is exact) and undo it when the accumulators are read out
+    float gs = 1.0f;
+    while (gs < (float)batch && gs < 1048576.0f) gs *= 2.0f;
+    PpoLossCfg cfg{clip_range, ent_coef, vf_coef, 1.0f / (float)batch, gs, 1.0f / gs};
+    ppo_grad_tc_kernel<<<grid, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, adv_stats, cfg,
+                                                             partial, stats_partial, P);
+    ppok_launch_grad_reduce(partial, stats_partial, grid, P, grad, stats, st);
+    return cudaGetLastError();
+}
+}  // namespace PPO_UT_NS

@@ -254,13 +254,13 @@ class PPO:
         if update not in ("kernel", "torch"):
             raise ValueError("update must be 'kernel' (hand-written tcgen05 kernels) or 'torch' (autograd reference)")
         self.update = update
-        if self.a != A or self.d > 32:
-            # The fused update (K6) is built for the 4-channel, <= 32-float-observation policies of the Waypoints /
-            # Waypoint-ObjLock scripts.  Six-channel policies (train_lowlevel_cmd.py) and the 56-float duck-only ObjLock
-            # observation (train_objlock.py) roll out with the forward kernels and update through the torch autograd path.
+        if self.d > 32:
+            # The fused update (K6) stages one 32-wide K slab of observations per tile: the 4- and 6-channel policies of the
+            # Waypoints / Waypoint-ObjLock / low-level scripts (28, 29 and 21 floats).  The 56-float duck-only ObjLock
+            # observation (train_objlock.py) rolls out with the forward kernels and updates through the torch autograd path.
             self.update = "torch"
         P = self.policy.count
-        self._ws = torch.zeros(int(self.lib.ppo_update_workspace_floats(self.d)), **f32)
+        self._ws = torch.zeros(int(self.lib.ppo_update_workspace_floats_a(min(self.d, 32), self.a)), **f32)
         self._grad = torch.zeros(P, **f32)
         self._adam_m, self._adam_v = torch.zeros(P, **f32), torch.zeros(P, **f32)
         self._adam_t = torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -357,8 +357,8 @@ class PPO:
     def _minibatch_grad_kernel(self, idx: torch.Tensor, grad: torch.Tensor, stats: torch.Tensor | None = None) -> None:
         """Fused tcgen05 forward+backward of one minibatch (csrc/ppo_update_tc.cu) into `grad`."""
         b = self.buf
-        _lib.check(self.lib.ppo_minibatch_grad(
-            _p(self.policy.theta), self.d, _p(b["obs"]), _p(b["act"]), _p(b["logp"]), _p(b["adv"]), _p(b["ret"]), _p(idx),
+        _lib.check(self.lib.ppo_minibatch_grad_a(
+            _p(self.policy.theta), self.d, self.a, _p(b["obs"]), _p(b["act"]), _p(b["logp"]), _p(b["adv"]), _p(b["ret"]), _p(idx),
             int(idx.numel()), self.clip_range, self.ent_coef, self.vf_coef, _p(self._ws), _p(grad), _p(stats), _stream()))
 
     def train(self) -> dict:

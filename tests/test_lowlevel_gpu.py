@@ -112,7 +112,8 @@ def test_lowlevel_random_action_lane_and_tensor_lane(fo):
 
 def test_ppo_on_the_lowlevel_env_six_channel_policy():
     """train/train_lowlevel_cmd.py on the device: rollouts with the forward kernels compiled for a 6-channel Gaussian
-    policy (CUDA-core fp32 and tcgen05 TF32), update through the torch autograd path.  The forward kernels must agree
+    policy (CUDA-core fp32 and tcgen05 TF32), update through the fused tcgen05 gradient kernel compiled for action width 6.
+    The forward kernels must agree
     with the fp32 torch towers, and a short run must improve the return."""
     import torch
     from pyflyt_drone_b200.ppo import PPO
@@ -121,7 +122,7 @@ def test_ppo_on_the_lowlevel_env_six_channel_policy():
     for tc, tol_max, tol_mean in ((False, 2e-4, 2e-5), (True, 3e-2, 3e-3)):          # fp32 kernel; TF32 + MUFU.TANH kernel
         m = PPO("MlpPolicy", env, n_steps=32, batch_size=8192, n_epochs=4, seed=3, use_cuda_graph=False,
                 tensor_core_forward=tc)
-        assert m.a == 6 and m.update == "torch" and m.tensor_core_forward == tc and m.policy.count == m.policy.theta.numel()
+        assert m.a == 6 and m.update == "kernel" and m.tensor_core_forward == tc and m.policy.count == m.policy.theta.numel()
         with torch.no_grad():      # move the towers away from the near-zero initial action head
             m.policy.theta.add_(0.05 * torch.randn(m.policy.count, device=m.device, generator=m._gen))
         m.collect_rollouts()

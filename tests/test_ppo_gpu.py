@@ -216,7 +216,7 @@ def _torch_minibatch_grad(model, idx):
     """Plain PyTorch fp32 reference of one SB3 PPO minibatch gradient on the flat parameter vector."""
     b = model.buf
     D = model.d
-    obs, act = b["obs"].view(-1, D)[idx], b["act"].view(-1, 4)[idx]
+    obs, act = b["obs"].view(-1, D)[idx], b["act"].view(-1, model.a)[idx]
     adv, ret, lp_old = b["adv"].view(-1)[idx], b["ret"].view(-1)[idx], b["logp"].view(-1)[idx]
     a = (adv - adv.mean()) / (adv.std() + 1e-8)
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -232,11 +232,7 @@ def _torch_minibatch_grad(model, idx):
     return g, float(pl), float(vl), float(((ratio - 1) - (logp - lp_old)).mean())
 
 
-@pytest.mark.parametrize("batch", [100, 128, 4000, 12000])
-def test_fused_tensor_core_gradient_matches_torch_autograd(model, batch):
-    """ppo_minibatch_grad (tcgen05: TF32 forward, bf16 backward operands, fp32 accumulate) vs torch autograd in fp32.
-    Tolerance per parameter tensor: relative L2 error <= 4e-2 and cosine >= 0.999 (bf16 backward operands, TF32 +
-    MUFU.TANH forward), on samples away from the PPO clip boundary."""
+def _check_fused_gradient(model, batch):
     model.collect_rollouts()
     with torch.no_grad():      # move the policy away from the data-collecting one so that ratios / clipping are live
         model.policy.theta.add_(0.01 * torch.randn(model.policy.count, device=model.device, generator=model._gen))
@@ -246,7 +242,7 @@ def test_fused_tensor_core_gradient_matches_torch_autograd(model, batch):
     # whether the forward pass ran in TF32 or fp32, which is a property of the loss (a jump), not of the kernel.
     with torch.no_grad():
         b = model.buf
-        _, lp_all, _ = model.policy.evaluate_actions(b["obs"].view(-1, model.d), b["act"].view(-1, 4))
+        _, lp_all, _ = model.policy.evaluate_actions(b["obs"].view(-1, model.d), b["act"].view(-1, model.a))
         ratio_all = torch.exp(lp_all - b["logp"].view(-1))
         safe = ((ratio_all - (1 - model.clip_range)).abs() > 3e-3) & ((ratio_all - (1 + model.clip_range)).abs() > 3e-3)
     idx = perm[safe[perm]][:batch]
@@ -267,6 +263,29 @@ def test_fused_tensor_core_gradient_matches_torch_autograd(model, batch):
     assert float(stats[0]) / n == pytest.approx(pl, rel=2e-2, abs=2e-3)
     assert float(stats[1]) / n == pytest.approx(vl, rel=2e-2, abs=2e-3)
     assert float(stats[2]) / n == pytest.approx(kl, rel=5e-2, abs=1e-3)
+
+
+@pytest.mark.parametrize("batch", [100, 128, 4000, 12000])
+def test_fused_tensor_core_gradient_matches_torch_autograd(model, batch):
+    """ppo_minibatch_grad (tcgen05: TF32 forward, bf16 backward operands, fp32 accumulate) vs torch autograd in fp32.
+    Tolerance per parameter tensor: relative L2 error <= 4e-2 and cosine >= 0.999 (bf16 backward operands, TF32 +
+    MUFU.TANH forward), on samples away from the PPO clip boundary."""
+    _check_fused_gradient(model, batch)
+
+
+@pytest.mark.parametrize("batch", [100, 4000])
+def test_fused_gradient_for_the_six_channel_policy(batch):
+    """The same kernel compiled for action width 6 (csrc/ppo_update_tc_a6.cu): the low-level env's MlpPolicy, D = 21, A = 6
+    (train/train_lowlevel_cmd.py:97-110)."""
+    from pyflyt_drone_b200.ppo import PPO
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    env = FixedwingVecEnv(512, preset="lowlevel", seed=5)
+    m = PPO("MlpPolicy", env, n_steps=32, batch_size=4096, n_epochs=2, ent_coef=0.001, seed=5, use_cuda_graph=False)
+    assert m.a == 6 and m.d == 21 and m.update == "kernel"
+    with torch.no_grad():      # the action head starts near zero (gain 0.01): give every gradient path signal
+        m.policy.theta.add_(0.05 * torch.randn(m.policy.count, device=m.device, generator=m._gen))
+    _check_fused_gradient(m, batch)
+    env.close()
 
 
 def test_random_permutation_is_a_fresh_bijection_every_epoch(model):
