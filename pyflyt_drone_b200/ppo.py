@@ -549,30 +549,53 @@ class PPO:
         self._step_dev.fill_(int(ck["global_step"]))
         return self
 
-    def export_sb3(self, directory: str) -> dict:
+    def export_sb3(self, directory: str, space_dtype=np.float64) -> dict:
         """Write what stable_baselines3 needs to replay this policy in the reference's eval scripts
-        (eval/eval_waypoints.py:96-107 loads a VecNormalize and a PPO model):
-          policy.pth   -- ``ActorCriticPolicy.state_dict()`` (MlpPolicy, net_arch pi=vf=[64, 64], Tanh): load with
-                          ``model.policy.load_state_dict(torch.load("policy.pth"))``
-          vecnorm.npz  -- the running moments under VecNormalize's attribute names: obs_rms_{mean,var,count},
-                          ret_rms_{mean,var,count}, clip_obs, clip_reward, gamma, epsilon
-        A full ``model.zip`` / ``vecnorm.pkl`` needs stable_baselines3's own classes to pickle and is left to the
-        machine that has them.  Returns the two paths."""
+        (eval/eval_waypoints.py:96-107: ``VecNormalize.load(vecnorm_path, env)`` then ``PPO.load(model_path, env=env)``):
+          final_model.zip -- SB3's own archive layout (sb3_io.write_model_zip): ``data`` JSON, ``policy.pth``,
+                             ``policy.optimizer.pth``, ``pytorch_variables.pth``, version and system info
+          vecnorm.pkl     -- a pickled ``VecNormalize`` without its venv (sb3_io.write_vecnorm_pkl)
+          policy.pth      -- ``ActorCriticPolicy.state_dict()`` on its own (MlpPolicy, net_arch pi = vf = [64, 64], Tanh)
+          vecnorm.npz     -- the running moments as plain arrays under VecNormalize's attribute names
+        The two SB3 containers are written without SB3 (it is not installable here) from its on-disk format; INTEGRATION.md
+        section 5 has the one-line load check for a machine that has it.  Returns the four paths."""
         import os
+        from . import sb3_io
         os.makedirs(directory, exist_ok=True)
         pol_path, vn_path = os.path.join(directory, "policy.pth"), os.path.join(directory, "vecnorm.npz")
         torch.save({k: v.detach().cpu() for k, v in self.policy.state_dict().items()}, pol_path)
         export_vecnorm_npz(self.vecnorm.state_dict(), vn_path)
-        return {"policy": pol_path, "vecnorm": vn_path}
+        zip_path = sb3_io.write_model_zip(os.path.join(directory, "final_model.zip"), self, space_dtype)
+        pkl_path = sb3_io.write_vecnorm_pkl(os.path.join(directory, "vecnorm.pkl"), self.vecnorm.state_dict(), self.d, self.a,
+                                            self.n_envs, space_dtype)
+        return {"policy": pol_path, "vecnorm": vn_path, "model_zip": zip_path, "vecnorm_pkl": pkl_path}
 
     def import_sb3(self, directory: str) -> "PPO":
-        """Inverse of export_sb3; also accepts a policy.pth saved from a real SB3 ``model.policy.state_dict()``."""
+        """Inverse of export_sb3.  Also takes what SB3 itself wrote: ``final_model.zip`` / ``best_model.zip`` (``model.save``)
+        and ``vecnorm.pkl`` (``VecNormalize.save``) of the reference's training runs, or a bare ``policy.pth``."""
         import os
-        sd = torch.load(os.path.join(directory, "policy.pth"), map_location="cpu", weights_only=True)
-        self.policy.load_state_dict(sd)
-        vn = os.path.join(directory, "vecnorm.npz")
-        if os.path.exists(vn):
-            self.vecnorm.load_state_dict(import_vecnorm_npz(vn))
+        from . import sb3_io
+        zips = [f for f in ("final_model.zip", "best_model.zip", "model.zip") if os.path.exists(os.path.join(directory, f))]
+        if zips:
+            ck = sb3_io.read_model_zip(os.path.join(directory, zips[0]))
+            self.policy.load_state_dict(ck["policy"])
+            for i, st in ck.get("optimizer", {}).get("state", {}).items():          # Adam moments, SB3 parameter order
+                key = sb3_io.SB3_PARAM_ORDER[int(i)]
+                base, _, leaf = key.rpartition(".")
+                m = {"mlp_extractor.policy_net.0": "pi.0", "mlp_extractor.policy_net.2": "pi.2",
+                     "mlp_extractor.value_net.0": "vf.0", "mlp_extractor.value_net.2": "vf.2"}
+                a, b, _ = self.policy.slices[f"{m[base]}.{leaf}" if base in m else key]
+                self._adam_m[a:b] = st["exp_avg"].reshape(-1).to(self.device)
+                self._adam_v[a:b] = st["exp_avg_sq"].reshape(-1).to(self.device)
+                self._adam_t.fill_(int(float(st["step"])))
+        else:
+            sd = torch.load(os.path.join(directory, "policy.pth"), map_location="cpu", weights_only=True)
+            self.policy.load_state_dict(sd)
+        pkl, npz = os.path.join(directory, "vecnorm.pkl"), os.path.join(directory, "vecnorm.npz")
+        if os.path.exists(pkl):
+            self.vecnorm.load_state_dict(sb3_io.read_vecnorm_pkl(pkl))
+        elif os.path.exists(npz):
+            self.vecnorm.load_state_dict(import_vecnorm_npz(npz))
         return self
 
     def get_parameters(self) -> dict:
