@@ -10,7 +10,9 @@ Our arm (default)
             recorded in the enqueue order behind a warm launch, so host launch latency is outside the region; MAX over
             ranks.  (K = 20 launches alone are 0.4 ms -- a window in which host jitter, not the GPU, sets the number.)
   L2        the per-batch state (~7 MB) would sit in the 126 MB L2 between launches, so the loop rotates over enough
-            independent env batches that the working set exceeds 2x L2 ("l2" in config).
+            independent env batches that the working set exceeds 2x L2 ("l2" in config).  The launches of the graph are
+            chained by programmatic dependent launch edges: consecutive launches step different batches, so the next one
+            places its blocks while the previous one drains (its tail otherwise idles 54 % of the schedulers).
   e2e       the same metric through the reference-facing host call FixedwingVecEnv.step_arrays(actions) (VecEnv.step seam;
             C ABI fw_step_host) on the Fixedwing-Waypoints-v3 task with HOST buffers: H2D of the actions and D2H of
             obs/reward/flags inside the timed region (wall clock, >= 50 ms regions, median of 5).
@@ -569,7 +571,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                       "statistic": "median region / (K*R), MAX over ranks", "best_region_ms_per_step": best_ms,
                       "physics_substeps_per_sec": value * cfg.inner_per_step * cfg.substeps_per_inner,
                       "l2": f"rotating {replicas} env batches ({replicas * state_bytes / 2**20:.0f} MiB > 2x L2)",
-                      "launch": "host loop" if args.no_graph else f"CUDA graph of {replicas} launches"},
+                      "launch": "host loop" if args.no_graph else
+                                f"CUDA graph of {replicas} launches chained by programmatic dependent launch edges (each launch steps "
+                                f"another env batch; the next one places its blocks while this one drains; FWSIM_PDL=0 = plain edges)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "us_per_step": e2e_step_s * 1e6, "steps_per_region": e2e_steps, "regions": N_REGIONS},
             "gpu_launches": int(launches + e2e_launches),

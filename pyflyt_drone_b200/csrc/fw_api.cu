@@ -322,7 +322,16 @@ static int multi_graph_get(MultiGraph& mg, const fw_handle* hs, int n_handles, i
             deps[nd++] = rf;
             plc.refill_list = h->refill_list[0]; plc.refill_count = h->refill_ctl;
         }
-        CU(fwk_graph_add_random_step(mg.graph, nd ? deps : nullptr, nd, h->dev, plc, spl, &steps[(size_t)k]));
+        // programmatic dependent launch along the chain: the next step launch places its blocks while this one drains.  A
+        // launch touches the state of its own handle only, and the one before it in the chain belongs to another handle
+        // whenever the list has several (mode 2: no wait); a handle stepping itself waits for its predecessor (mode 1).
+        // FWSIM_PDL=0 turns it off.
+        static const bool pdl_on = [] { const char* e = getenv("FWSIM_PDL"); return !(e && atoi(e) == 0); }();
+        // Every (n_handles / 2)-th edge stays an ordinary one: two launches on the same handle are n_handles apart, so they can
+        // never be in flight together whatever the block scheduler does.
+        const int period = n_handles / 2;
+        const int pdl = (pdl_on && !h->spare_on && !(n_handles >= 4 && k % period == 0)) ? (n_handles >= 4 ? 2 : 1) : 0;
+        CU(fwk_graph_add_random_step(mg.graph, nd ? deps : nullptr, nd, h->dev, plc, spl, &steps[(size_t)k], pdl));
     }
     CU(cudaGraphInstantiate(&mg.exec, mg.graph, 0));
     for (int k = 0; k < count; ++k) mg.hs.push_back(hs[k % n_handles]);

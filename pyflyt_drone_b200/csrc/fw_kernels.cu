@@ -230,6 +230,14 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
                float* __restrict__ obs, float* __restrict__ rew, uint8_t* __restrict__ flg,
                float* __restrict__ term_obs, int spl, int bulk_ok) {
     extern __shared__ __align__(128) float stage[];
+    // Programmatic dependent launch (bits 1-2 of `bulk_ok`): let the next launch of the chain start placing its blocks as
+    // this one's finish -- the 54 % of the schedulers that hold 3 warps instead of 4 otherwise idle through the last quarter
+    // of every launch -- and, when that next launch reads what this one writes (mode 1), make it wait for our completion
+    // before it touches the planes.  Mode 2 = the chain steps a different env batch next (fw_rollout_random over handles).
+    const int pdl = (bulk_ok >> 1) & 3;
+    bulk_ok &= 1;
+    if (pdl != 0) asm volatile("griddepcontrol.launch_dependents;");
+    if (pdl == 1) asm volatile("griddepcontrol.wait;" ::: "memory");
     const int i = p.i_begin + blockIdx.x * FW_BLOCK + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int D = p.obs_dim;
@@ -1178,14 +1186,19 @@ cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act
 
 // Append one random-action step launch to a CUDA graph (explicit node: works without stream capture, so the
 // graph can later be launched on any stream including the legacy default stream torch hands us).
+// pdl: 0 = ordinary dependencies; 1 / 2 = the single dependency (if any) becomes a programmatic edge and the kernel runs in
+// PDL mode 1 / 2 (see fw_step_kernel) -- only the one-env-per-thread K1 kernels implement the prologue
+bool fwk_step_supports_pdl(const FwDev& p) { return step_launch(p, true).envs_per_block == FW_BLOCK && (p.task == 0 || p.task == 1 || p.task == 3); }
+
 cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* deps, int ndeps, const FwDev& p, const FwPlanes& pl,
-                                      int spl, cudaGraphNode_t* out) {
+                                      int spl, cudaGraphNode_t* out, int pdl) {
     const StepLaunch L = step_launch(p, true);
     if (L.fn == nullptr) return cudaErrorNotSupported;
     if (!smem_opt_in((const void*)L.fn, L.smem)) return cudaErrorInvalidValue;
+    if (pdl != 0 && (!fwk_step_supports_pdl(p) || ndeps > 1)) pdl = 0;
     FwDev pc = p; FwPlanes plc = pl;
     const float4* act = nullptr; float* obs = nullptr; float* rew = nullptr; uint8_t* flg = nullptr; float* term = nullptr;
-    int spl_ = spl, bulk = 0;
+    int spl_ = spl, bulk = pdl << 1;
     void* args[] = {&pc, &plc, &act, &obs, &rew, &flg, &term, &spl_, &bulk};
     cudaKernelNodeParams kp;
     memset(&kp, 0, sizeof(kp));
@@ -1194,7 +1207,14 @@ cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* deps, int 
     kp.gridDim = dim3((n + L.envs_per_block - 1) / L.envs_per_block); kp.blockDim = dim3(L.threads);
     kp.sharedMemBytes = (unsigned)L.smem;
     kp.kernelParams = args; kp.extra = nullptr;
-    return cudaGraphAddKernelNode(out, g, deps, ndeps, &kp);
+    if (pdl == 0 || ndeps == 0) return cudaGraphAddKernelNode(out, g, deps, ndeps, &kp);
+    cudaError_t e = cudaGraphAddKernelNode(out, g, nullptr, 0, &kp);
+    if (e != cudaSuccess) return e;
+    cudaGraphEdgeData ed;
+    memset(&ed, 0, sizeof(ed));
+    ed.from_port = cudaGraphKernelNodePortProgrammatic;
+    ed.type = cudaGraphDependencyTypeProgrammatic;
+    return cudaGraphAddDependencies_v2(g, deps, out, &ed, 1);
 }
 
 static int refill_grid(int work, bool whole_batch) {

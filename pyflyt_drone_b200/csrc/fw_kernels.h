@@ -9,7 +9,8 @@ struct FwPlanes;
 cudaError_t fwk_launch_step(const FwDev& p, const FwPlanes& pl, const float* act, float* obs, float* rew, uint8_t* flg,
                             float* term_obs, bool random_act, int spl, cudaStream_t st);
 cudaError_t fwk_graph_add_random_step(cudaGraph_t g, cudaGraphNode_t* deps, int ndeps, const FwDev& p, const FwPlanes& pl,
-                                      int spl, cudaGraphNode_t* out);
+                                      int spl, cudaGraphNode_t* out, int pdl = 0);
+bool fwk_step_supports_pdl(const FwDev& p);
 cudaError_t fwk_launch_reset(const FwDev& p, const FwPlanes& pl, const uint8_t* mask, float* obs, bool emit_only,
                              cudaStream_t st);
 cudaError_t fwk_launch_refill(const FwDev& p, const FwPlanes& pl, const int2* list, int* count, int* blocks_done, int cap,
