@@ -28,7 +28,8 @@ extern "C" {
 #define PPO_HIDDEN 64
 #define PPO_ACT 4
 #define PPO_MAX_OBS 64      /* CUDA-core forward, value, bootstrap, running moments */
-#define PPO_TC_MAX_OBS 32   /* tcgen05 forward (ppo_policy_forward_tc*) and fused minibatch gradient (ppo_minibatch_grad) */
+#define PPO_TC_MAX_OBS 32   /* tcgen05 forward (ppo_policy_forward_tc*); fused minibatch gradient with a = 6.  The a = 4
+                             * gradient also takes d up to PPO_MAX_OBS (64-wide build, csrc/ppo_update_tc_d64.cu) */
 
 /* number of floats in the parameter vector for observation width d */
 int ppo_param_count(int32_t d);
@@ -109,7 +110,8 @@ int ppo_random_permutation(int64_t* out, int64_t n, uint64_t seed, uint64_t epoc
  *     -mean(min(A r, A clip(r, 1 +- clip_range))) - ent_coef * mean(entropy) + vf_coef * mean((ret - V)^2)
  * over the `batch` samples idx[0..batch) (int64 row indices into the flattened rollout buffers), with the
  * per-minibatch advantage normalisation (A - mean) / (std + 1e-8), r = exp(logp - logp_old).  Forward and backward
- * of both towers run on the tcgen05 tensor cores (TF32).  grad receives all ppo_param_count(d) entries;
+ * of both towers run on the tcgen05 tensor cores (TF32 forward, bf16 backward operands, fp32 accumulation; for
+ * d > 32 layer 2 of the forward is a bf16 hi/lo split instead of TF32).  grad receives all ppo_param_count(d) entries;
  * stats[8] (may be NULL) = sums over the minibatch of {policy loss, squared value error, approx KL, clipped,
  * ratio, samples, 0, 0}.  workspace: ppo_update_workspace_floats(d) floats, 16-byte aligned, zero on first use. */
 int ppo_update_workspace_floats(int32_t d);

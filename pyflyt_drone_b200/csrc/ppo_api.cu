@@ -209,7 +209,8 @@ extern "C" int ppo_minibatch_grad_a(const float* params, int32_t d, int32_t a, c
     if (!params || !obs_norm || !act || !logp_old || !adv || !ret || !idx || !workspace || !grad)
         return pfail(FW_EINVAL, "null argument");
     if (batch <= 0) return pfail(FW_EINVAL, "batch must be positive");
-    int rc = check_d_tc(d);
+    // one 32-wide observation slab for both action widths; a 64-wide one (bf16-split layer 2) for four-channel policies
+    int rc = (a == 4) ? check_d(d) : check_d_tc(d);
     if (rc) return rc;
     if ((rc = check_a(a)) != 0) return rc;
     if ((reinterpret_cast<uintptr_t>(workspace) & 15u) || (reinterpret_cast<uintptr_t>(act) & 15u))
@@ -220,7 +221,11 @@ extern "C" int ppo_minibatch_grad_a(const float* params, int32_t d, int32_t a, c
     float* adv_stats = workspace + 8;
     float* partial = workspace + 16;
     float* stats_partial = partial + (size_t)160 * P;
-    if (a == 4)
+    if (a == 4 && d > PPO_TC_MAX_OBS)
+        PCU(ppo_a4d64::ppok_minibatch_grad(params, d, obs_norm, act, logp_old, adv, ret, reinterpret_cast<const long long*>(idx), batch,
+                                           clip_range, ent_coef, vf_coef, scratch, adv_stats, partial, stats_partial, grad, stats,
+                                           (cudaStream_t)stream));
+    else if (a == 4)
         PCU(ppo_a4::ppok_minibatch_grad(params, d, obs_norm, act, logp_old, adv, ret, reinterpret_cast<const long long*>(idx), batch,
                                         clip_range, ent_coef, vf_coef, scratch, adv_stats, partial, stats_partial, grad, stats,
                                         (cudaStream_t)stream));

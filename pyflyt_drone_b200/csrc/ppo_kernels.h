@@ -35,7 +35,8 @@ cudaError_t ppok_gae(const float* rewards, const float* values, const float* don
 PPOK_DECLARE_FORWARD_TC(ppo_a4)
 PPOK_DECLARE_FORWARD_TC(ppo_a6)
 int ppok_update_grid(int batch);
-// fused minibatch gradient: one instantiation per action width (ppo_update_tc.cu compiled for 4, ppo_update_tc_a6.cu for 6)
+// fused minibatch gradient: one instantiation per (action width, observation slab): ppo_update_tc.cu = (4, 32),
+// ppo_update_tc_a6.cu = (6, 32), ppo_update_tc_d64.cu = (4, 64)
 #define PPOK_DECLARE_MINIBATCH_GRAD(ns)                                                                                    \
     namespace ns {                                                                                                          \
     cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, const float* act, const float* logp_old, \
@@ -45,5 +46,6 @@ int ppok_update_grid(int batch);
     }
 PPOK_DECLARE_MINIBATCH_GRAD(ppo_a4)
 PPOK_DECLARE_MINIBATCH_GRAD(ppo_a6)
+PPOK_DECLARE_MINIBATCH_GRAD(ppo_a4d64)
 cudaError_t ppok_adam(float* params, const float* grad, float* m, float* v, int P, float lr, float beta1, float beta2, float eps,
                       float max_norm, float grad_scale, int* step_ctr, float* norm_out, cudaStream_t st);

@@ -28,18 +28,28 @@
 #ifndef PPO_A_BUILD
 #define PPO_A_BUILD 4
 #endif
-#if PPO_A_BUILD == 4
+#ifndef PPO_D_BUILD
+#define PPO_D_BUILD 32
+#endif
+#if PPO_A_BUILD == 4 && PPO_D_BUILD == 32
 #define PPO_UT_NS ppo_a4
-#elif PPO_A_BUILD == 6
+#define PPO_UT_SHARED 1          // this build also carries the width-independent kernels
+#elif PPO_A_BUILD == 6 && PPO_D_BUILD == 32
 #define PPO_UT_NS ppo_a6
+#elif PPO_A_BUILD == 4 && PPO_D_BUILD == 64
+#define PPO_UT_NS ppo_a4d64
 #else
-#error "action width must be 4 or 6"
+#error "supported builds: action width 4 or 6 with a 32-wide observation slab, action width 4 with a 64-wide one"
 #endif
 
 #define H PPO_H
 #define A PPO_A_BUILD
 #define AP ((A + 3) / 4 * 4)      // action width padded to whole float4s
-#define DP PPO_DPAD
+#define DP PPO_D_BUILD           // observation columns staged per tile (layer-1 K)
+// 64-wide build: layer 2 of the forward pass runs as a bf16 hi/lo split (three kind::f16 MMAs: hi*hi + lo*hi + hi*lo,
+// ~2^-16 relative, tighter than TF32) so that the bf16 operands the backward pass needs anyway (H1 hi = wgrad B,
+// W2 hi = dgrad B) double as forward operands; the 48 KB this frees pay for the wider X / W1 buffers.
+#define UT_SPLIT (DP > 32)
 #define UT_ROWS 128
 #define UT_THREADS 512
 #define UT_TMEM_COLS 512
@@ -171,19 +181,38 @@ __device__ __forceinline__ float ut_tanh(float x) {
 struct UtSmem {
     static constexpr int XB = 0;                              // X  f32       [128 x 32]    16 KB  forward L1 A
     static constexpr int H1C = XB + UT_ROWS * DP * 4;         // H1 f32 pi|vf [128 x 128]   64 KB  forward L2 A
+#if UT_SPLIT
+    static constexpr int DZ2 = H1C + UT_ROWS * 2 * H * 2;     // dZ2 bf16     [128 x 128]   32 KB  aliases H1 lo (dead after M2)
+#else
     static constexpr int DZ2 = H1C;                           // dZ2 bf16     [128 x 128]   32 KB  aliases H1C (dead after M2)
+#endif
     static constexpr int H2B = H1C + UT_ROWS * 2 * H * 4;     // H2 bf16 pi|vf[128 x 128]   32 KB  wgrad L3 A
     static constexpr int DZ1 = H2B;                           // dZ1 bf16     [128 x 128]   32 KB  aliases H2B (dead after M3)
+#if UT_SPLIT
+    // split build: the 64 KB at H1C hold H1 hi (bf16, forward L2 A and wgrad L2 B) then H1 lo (forward only; dZ2 lands there)
+    static constexpr int H1B = H1C;
+    static constexpr int H1L = H1C + UT_ROWS * 2 * H * 2;
+    static constexpr int XBB = H2B + UT_ROWS * 2 * H * 2;     // X  bf16      [128 x 64]    16 KB  wgrad L1 B
+#else
     static constexpr int H1B = H2B + UT_ROWS * 2 * H * 2;     // H1 bf16 pi|vf[128 x 128]   32 KB  wgrad L2 B
     static constexpr int XBB = H1B + UT_ROWS * 2 * H * 2;     // X  bf16      [128 x 32]     8 KB  wgrad L1 B
+#endif
     static constexpr int DO = XBB + UT_ROWS * DP * 2;         // dOut|1 bf16  [128 x 16]     4 KB
     static constexpr int W1_PI = DO + UT_ROWS * 16 * 2;       // W1 f32       [64 x 32]      8 KB each
     static constexpr int W1_VF = W1_PI + H * DP * 4;
+#if UT_SPLIT
+    static constexpr int W2B_PI = W1_VF + H * DP * 4;         // W2 hi bf16   [64 x 64]      8 KB each (forward B, dgrad B)
+    static constexpr int W2B_VF = W2B_PI + H * H * 2;
+    static constexpr int W2L_PI = W2B_VF + H * H * 2;         // W2 lo bf16   [64 x 64]      8 KB each (forward B)
+    static constexpr int W2L_VF = W2L_PI + H * H * 2;
+    static constexpr int SMALL = W2L_VF + H * H * 2;
+#else
     static constexpr int W2_PI = W1_VF + H * DP * 4;          // W2 f32       [64 x 64]     16 KB each
     static constexpr int W2_VF = W2_PI + H * H * 4;
     static constexpr int W2B_PI = W2_VF + H * H * 4;          // W2 bf16      [64 x 64]      8 KB each (dgrad B)
     static constexpr int W2B_VF = W2B_PI + H * H * 2;
     static constexpr int SMALL = W2B_VF + H * H * 2;
+#endif
     // floats inside SMALL
     static constexpr int B1 = 0 /* pi 64 | vf 64 */, B2 = 128, W3_PI = 256 /* [64][AP]: AP/4 float4s per hidden unit */,
                          W3_VF = W3_PI + H * AP, B3_PI = W3_VF + H, B3_VF = B3_PI + AP, LOGSTD = B3_VF + 4,
@@ -193,6 +222,7 @@ struct UtSmem {
     static constexpr int PS_PI = 0, PS_VF = PS_PI + 2 * UT_ROWS * AP * 4, LIN = PS_VF + 2 * UT_ROWS * 4, LIN_ROW = (AP + 4) * 4;
     static_assert(LIN + UT_ROWS * LIN_ROW <= UT_ROWS * DP * 4, "head partials + loss inputs must fit the layer-1 operand buffer");
     static constexpr int TOTAL = SMALL + NSMALL * 4;
+    static_assert(TOTAL <= 227 * 1024, "a CTA owns at most 227 KB of shared memory");
 };
 
 // TMEM column plan
@@ -200,28 +230,34 @@ struct UtSmem {
 #define UT_T2 128    // 128: layer-2 pre-activations, later the data gradient dH1
 #define UT_DA 256    // 64 : [dZ2]^T H1_pi   (rows 0-63 = dW2_pi)
 #define UT_DB 320    // 64 : [dZ2]^T H1_vf   (rows 64-127 = dW2_vf)
-#define UT_DW1 384   // 32 : [dZ1]^T X       (rows 0-63 dW1_pi, 64-127 dW1_vf)
-#define UT_D3 416    // 16 : [H2]^T dOut     (rows 0-63 x cols 0..A-1 = dW3_pi^T ; rows 64-127 x col A = dW3_vf)
-#define UT_DB2 432   // 16 : [dZ2]^T dOut|1  (col A+1 = db2)
-#define UT_DB1 448   // 16 : [dZ1]^T dOut|1  (col A+1 = db1)
+#define UT_DW1 384   // DP : [dZ1]^T X       (rows 0-63 dW1_pi, 64-127 dW1_vf)
+#define UT_D3 (UT_DW1 + DP)   // 16 : [H2]^T dOut     (rows 0-63 x cols 0..A-1 = dW3_pi^T ; rows 64-127 x col A = dW3_vf)
+#define UT_DB2 (UT_D3 + 16)   // 16 : [dZ2]^T dOut|1  (col A+1 = db2)
+#define UT_DB1 (UT_DB2 + 16)  // 16 : [dZ1]^T dOut|1  (col A+1 = db1)
+static_assert(UT_DB1 + 16 <= UT_TMEM_COLS, "TMEM column plan");
 
-__device__ void ut_load_weight(char* smem, int off, const float* __restrict__ g, int K, int d, int off_bf16 = -1) {
+// off: fp32 copy (or -1), off_bf16: bf16 copy (or -1), off_lo: bf16 of the remainder v - bf16(v) (or -1)
+__device__ void ut_load_weight(char* smem, int off, const float* __restrict__ g, int K, int d, int off_bf16 = -1, int off_lo = -1) {
     for (int i = threadIdx.x; i < H * K; i += blockDim.x) {
         int j = i / K, k = i % K;
         const float v = k < d ? g[j * d + k] : 0.0f;
-        *reinterpret_cast<float*>(smem + off + ut_off(j, k, K)) = v;
-        if (off_bf16 >= 0) *reinterpret_cast<__nv_bfloat16*>(smem + off_bf16 + ut_off16(j, k, K)) = __float2bfloat16(v);
+        if (off >= 0) *reinterpret_cast<float*>(smem + off + ut_off(j, k, K)) = v;
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        if (off_bf16 >= 0) *reinterpret_cast<__nv_bfloat16*>(smem + off_bf16 + ut_off16(j, k, K)) = hi;
+        if (off_lo >= 0) *reinterpret_cast<__nv_bfloat16*>(smem + off_lo + ut_off16(j, k, K)) = __float2bfloat16(v - __bfloat162float(hi));
     }
 }
 
 struct PpoLossCfg { float clip_range, ent_coef, vf_coef, inv_batch, grad_scale, inv_grad_scale; };
 
-// Asynchronously gather 8 consecutive observation columns [8*part, 8*part+8) of rollout row g straight into the
+// Asynchronously gather 8 consecutive observation columns [8*part, 8*part+8) (per 32-column slab) of rollout row g straight into the
 // fp32 layer-1 A operand (cp.async with zero fill for padding columns and dead rows): the random 112-byte row reads
 // cost DRAM latency, and unlike register loads they cannot stall the issuing warp.
 __device__ __forceinline__ void ut_gather_async(char* smem, const float* __restrict__ obs, int d, long long g, bool live,
                                                 int grow, int part) {
     const float* src = obs + (size_t)g * d;
+#pragma unroll
+    for (int slab = 0; slab < DP / 32; ++slab, part += 4)
     if ((d & 3) == 0) {                                   // rows are 16-byte aligned: two 16-byte copies
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -269,8 +305,13 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
 
     ut_load_weight(smem, UtSmem::W1_PI, g_pi, DP, d);
     ut_load_weight(smem, UtSmem::W1_VF, g_vf, DP, d);
+#if UT_SPLIT
+    ut_load_weight(smem, -1, g_pi + H * d + H, H, H, UtSmem::W2B_PI, UtSmem::W2L_PI);
+    ut_load_weight(smem, -1, g_vf + H * d + H, H, H, UtSmem::W2B_VF, UtSmem::W2L_VF);
+#else
     ut_load_weight(smem, UtSmem::W2_PI, g_pi + H * d + H, H, H, UtSmem::W2B_PI);
     ut_load_weight(smem, UtSmem::W2_VF, g_vf + H * d + H, H, H, UtSmem::W2B_VF);
+#endif
     if (tid < H) {
         small[UtSmem::B1 + tid] = g_pi[H * d + tid];
         small[UtSmem::B1 + H + tid] = g_vf[H * d + tid];
@@ -359,12 +400,14 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // bf16 copy of X (B operand of the layer-1 weight gradient): packed now, stored once the previous tile's M5,
         // which still reads the old copy, has drained (after the M2 wait)
-        uint4 xbb;
-        {
-            const float4 xa = *reinterpret_cast<const float4*>(smem + UtSmem::XB + ut_off(grow, 8 * gpart, DP));
-            const float4 xb = *reinterpret_cast<const float4*>(smem + UtSmem::XB + ut_off(grow, 8 * gpart + 4, DP));
+        uint4 xbb[DP / 32];
+#pragma unroll
+        for (int slab = 0; slab < DP / 32; ++slab) {
+            const int k = 8 * (gpart + 4 * slab);
+            const float4 xa = *reinterpret_cast<const float4*>(smem + UtSmem::XB + ut_off(grow, k, DP));
+            const float4 xb = *reinterpret_cast<const float4*>(smem + UtSmem::XB + ut_off(grow, k + 4, DP));
             const float x8[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-            xbb = ut_pack8(x8);
+            xbb[slab] = ut_pack8(x8);
         }
         // loss inputs of the tile's samples: gathered by warpgroup 0 only (four separate random lines per sample; doing it
         // in all four warpgroups quadrupled the L1 wavefronts and stalled the block on the load queue), requested here so
@@ -399,9 +442,22 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
                 const float bias[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
                 for (int r = 0; r < 8; ++r) { h[r] = ut_tanh(v[8 * c8 + r] + bias[r]); dd[r] = fmaf(-h[r], h[r], 1.0f); }
+#if UT_SPLIT
+                {
+                    const uint4 hi = ut_pack8(h);
+                    *reinterpret_cast<uint4*>(smem + UtSmem::H1B + ut_off16(row, j, 2 * H)) = hi;
+                    const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w};
+                    float lo[8];
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)       // a bf16 is the top half of an fp32: hi as float by a shift / mask
+                        lo[r] = h[r] - __uint_as_float((r & 1) ? (hw[r >> 1] & 0xffff0000u) : (hw[r >> 1] << 16));
+                    *reinterpret_cast<uint4*>(smem + UtSmem::H1L + ut_off16(row, j, 2 * H)) = ut_pack8(lo);
+                }
+#else
                 *reinterpret_cast<float4*>(smem + UtSmem::H1C + ut_off(row, j, 2 * H)) = make_float4(h[0], h[1], h[2], h[3]);
                 *reinterpret_cast<float4*>(smem + UtSmem::H1C + ut_off(row, j + 4, 2 * H)) = make_float4(h[4], h[5], h[6], h[7]);
                 *reinterpret_cast<uint4*>(smem + UtSmem::H1B + ut_off16(row, j, 2 * H)) = ut_pack8(h);
+#endif
 #pragma unroll
                 for (int r = 0; r < 4; ++r) d1p[4 * c8 + r] = ut_pack2(dd[2 * r], dd[2 * r + 1]);
             }
@@ -409,15 +465,29 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         UT_FENCE_SYNC();
         // ---- M2: forward layer 2 (A = the tower's 64-column sub-block of H1C)
         if (tid == 0) {
+#if UT_SPLIT
+            // z2 = H1 W2^T as hi*hi + lo*hi + hi*lo (bf16 operands, fp32 accumulation); tower t = columns 64t.. of H1
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const uint32_t ahi = sb + UtSmem::H1B + t * 8 * 128, alo = sb + UtSmem::H1L + t * 8 * 128;
+                const uint32_t bhi = sb + (t ? UtSmem::W2B_VF : UtSmem::W2B_PI), blo = sb + (t ? UtSmem::W2L_VF : UtSmem::W2L_PI);
+                ut_gemm<true, H / 16>(tmem + UT_T2 + t * H, ahi, 128, 2 * H * 16, 256, bhi, 128, H * 16, 256, ut_idesc(1, H, 0, 0), 0u);
+                ut_gemm<true, H / 16>(tmem + UT_T2 + t * H, alo, 128, 2 * H * 16, 256, bhi, 128, H * 16, 256, ut_idesc(1, H, 0, 0), 1u);
+                ut_gemm<true, H / 16>(tmem + UT_T2 + t * H, ahi, 128, 2 * H * 16, 256, blo, 128, H * 16, 256, ut_idesc(1, H, 0, 0), 1u);
+            }
+#else
             ut_gemm<false, H / 8>(tmem + UT_T2, sb + UtSmem::H1C, 128, 2 * H * 32, 256, sb + UtSmem::W2_PI, 128, H * 32, 256,
                            ut_idesc(2, H, 0, 0), 0u);
             ut_gemm<false, H / 8>(tmem + UT_T2 + H, sb + UtSmem::H1C + 16 * 128, 128, 2 * H * 32, 256, sb + UtSmem::W2_VF, 128, H * 32, 256,
                            ut_idesc(2, H, 0, 0), 0u);
+#endif
             ut_commit(bar);
         }
         ut_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        *reinterpret_cast<uint4*>(smem + UtSmem::XBB + ut_off16(grow, 8 * gpart, DP)) = xbb;
+#pragma unroll
+        for (int slab = 0; slab < DP / 32; ++slab)
+            *reinterpret_cast<uint4*>(smem + UtSmem::XBB + ut_off16(grow, 8 * (gpart + 4 * slab), DP)) = xbb[slab];
         // ---- E2: H2 = tanh(z2 + b2) (bf16 copy for the head weight gradient); partial head sums over this
         //      warpgroup's 32 hidden units (policy: 4 action means; value: 1)
         {
@@ -642,11 +712,14 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
 #pragma unroll
             for (int c = 0; c < 16; ++c) outp[o_w2 + j * H + q * 16 + c] = v[c] * cfg.inv_grad_scale;
         }
-        if (q < 2) {   // dW1: 16 columns each
-            float v[16];
-            ut_ld16(tmem + UT_DW1 + lane_base + q * 16, v);
+        if (q < 2) {   // dW1: DP/2 columns each
 #pragma unroll
-            for (int c = 0; c < 16; ++c) if (q * 16 + c < d) outp[o_w1 + j * d + q * 16 + c] = v[c] * cfg.inv_grad_scale;
+            for (int c0 = q * (DP / 2); c0 < (q + 1) * (DP / 2); c0 += 16) {
+                float v[16];
+                ut_ld16(tmem + UT_DW1 + lane_base + c0, v);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) if (c0 + c < d) outp[o_w1 + j * d + c0 + c] = v[c] * cfg.inv_grad_scale;
+            }
         } else if (q == 2) {   // head weights
             float v3[16];
             ut_ld16(tmem + UT_D3 + lane_base, v3);
@@ -703,7 +776,7 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
 
 }  // namespace PPO_UT_NS
 
-#if PPO_A_BUILD == 4
+#ifdef PPO_UT_SHARED
 // ------------------------------------------------------------------ minibatch advantage statistics (mean, unbiased std)
 __global__ void __launch_bounds__(256)
 ppo_adv_stats_kernel(const float* __restrict__ adv, const long long* __restrict__ idx, int batch, double* __restrict__ scratch,
@@ -848,7 +921,7 @@ cudaError_t ppok_adam(float* params, const float* grad, float* m, float* v, int 
     ppo_adam_kernel<<<1, ADAM_THREADS, 0, st>>>(params, grad, m, v, P, lr, beta1, beta2, eps, max_norm, grad_scale, step_ctr, norm_out);
     return cudaGetLastError();
 }
-#endif  // PPO_A_BUILD == 4
+#endif  // PPO_UT_SHARED
 
 void ppok_launch_adv_stats(const float* adv, const long long* idx, int batch, double* scratch, float* adv_stats, cudaStream_t st);
 void ppok_launch_grad_reduce(const float* partial, const float* stats_partial, int grid, int P, float* grad, float* stats, cudaStream_t st);
@@ -860,6 +933,7 @@ cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, co
                                 const float* adv, const float* ret, const long long* idx, int batch, float clip_range,
                                 float ent_coef, float vf_coef, double* scratch, float* adv_stats, float* partial,
                                 float* stats_partial, float* grad, float* stats, cudaStream_t st) {
+    if (d > DP) return cudaErrorInvalidValue;
     if (!g_ut_attr_set) {
         cudaError_t e = cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL);
         if (e != cudaSuccess) return e;

@@ -254,13 +254,13 @@ class PPO:
         if update not in ("kernel", "torch"):
             raise ValueError("update must be 'kernel' (hand-written tcgen05 kernels) or 'torch' (autograd reference)")
         self.update = update
-        if self.d > 32:
-            # The fused update (K6) stages one 32-wide K slab of observations per tile: the 4- and 6-channel policies of the
-            # Waypoints / Waypoint-ObjLock / low-level scripts (28, 29 and 21 floats).  The 56-float duck-only ObjLock
-            # observation (train_objlock.py) rolls out with the forward kernels and updates through the torch autograd path.
+        if self.d > 32 and self.a != 4:
+            # The fused update (K6) is built for (action width, observation slab) = (4, 32), (6, 32) and (4, 64): the
+            # Waypoints / Waypoint-ObjLock / low-level / duck-only ObjLock policies (28, 29, 21 and 56 floats).  A six-channel
+            # policy over more than 32 floats has no reference script; it would update through the torch autograd path.
             self.update = "torch"
         P = self.policy.count
-        self._ws = torch.zeros(int(self.lib.ppo_update_workspace_floats_a(min(self.d, 32), self.a)), **f32)
+        self._ws = torch.zeros(int(self.lib.ppo_update_workspace_floats_a(self.d, self.a)), **f32)
         self._grad = torch.zeros(P, **f32)
         self._adam_m, self._adam_v = torch.zeros(P, **f32), torch.zeros(P, **f32)
         self._adam_t = torch.zeros(1, dtype=torch.int32, device=self.device)

@@ -226,15 +226,15 @@ def test_duck_gym_view_and_vec_infos():
 
 def test_ppo_on_the_duck_env_wide_observation():
     """train/train_objlock.py on the device: the 56-float observation runs through the CUDA-core forward / value /
-    bootstrap / running-moment kernels built for observations up to 64 floats wide (the tcgen05 kernels stage one
-    32-wide K slab), update through the torch autograd path.  The forward must agree with the fp32 torch towers, the
+    bootstrap / running-moment kernels built for observations up to 64 floats wide (the tcgen05 forward stages one
+    32-wide K slab), update through the fused gradient kernel's 64-wide build.  The forward must agree with the fp32 torch towers, the
     running moments with NumPy, and a short run must improve the return."""
     import torch
     from pyflyt_drone_b200.ppo import PPO
     from pyflyt_drone_b200.vec_env import FixedwingVecEnv
     env = FixedwingVecEnv(1024, preset="objlock_duck", seed=3)
     m = PPO("MlpPolicy", env, n_steps=32, batch_size=8192, n_epochs=4, seed=3, use_cuda_graph=False)
-    assert m.d == 56 and m.a == 4 and m.update == "torch" and m.tensor_core_forward is False
+    assert m.d == 56 and m.a == 4 and m.update == "kernel" and m.tensor_core_forward is False
     assert m.policy.count == m.policy.theta.numel() == int(m.lib.ppo_param_count(56))
     with torch.no_grad():
         m.policy.theta.add_(0.05 * torch.randn(m.policy.count, device=m.device, generator=m._gen))

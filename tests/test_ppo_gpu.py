@@ -229,7 +229,7 @@ def _torch_minibatch_grad(model, idx):
     loss.backward()
     g = model.policy.theta.grad.detach().clone()
     model.policy.theta.grad = None
-    return g, float(pl), float(vl), float(((ratio - 1) - (logp - lp_old)).mean())
+    return g, float(pl.detach()), float(vl.detach()), float(((ratio - 1) - (logp - lp_old)).mean().detach())
 
 
 def _check_fused_gradient(model, batch):
@@ -283,6 +283,21 @@ def test_fused_gradient_for_the_six_channel_policy(batch):
     m = PPO("MlpPolicy", env, n_steps=32, batch_size=4096, n_epochs=2, ent_coef=0.001, seed=5, use_cuda_graph=False)
     assert m.a == 6 and m.d == 21 and m.update == "kernel"
     with torch.no_grad():      # the action head starts near zero (gain 0.01): give every gradient path signal
+        m.policy.theta.add_(0.05 * torch.randn(m.policy.count, device=m.device, generator=m._gen))
+    _check_fused_gradient(m, batch)
+    env.close()
+
+
+@pytest.mark.parametrize("batch", [100, 4000])
+def test_fused_gradient_for_the_56_float_duck_observation(batch):
+    """The same kernel compiled with a 64-wide layer-1 slab (csrc/ppo_update_tc_d64.cu; layer 2 of the forward pass as a
+    bf16 hi/lo split): the duck-only ObjLock policy, D = 56, A = 4 (train/train_objlock.py:186-290)."""
+    from pyflyt_drone_b200.ppo import PPO
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    env = FixedwingVecEnv(512, preset="objlock_duck", seed=5)
+    m = PPO("MlpPolicy", env, n_steps=32, batch_size=4096, n_epochs=2, ent_coef=0.001, seed=5, use_cuda_graph=False)
+    assert m.a == 4 and m.d == 56 and m.update == "kernel"
+    with torch.no_grad():
         m.policy.theta.add_(0.05 * torch.randn(m.policy.count, device=m.device, generator=m._gen))
     _check_fused_gradient(m, batch)
     env.close()
