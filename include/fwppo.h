@@ -104,6 +104,11 @@ int ppo_gae(const float* rewards, const float* values, const float* dones, const
  * (seed, epoch).  Replaces the np.random.permutation of RolloutBuffer.get (a Feistel bijection with cycle walking
  * instead of a sort). */
 int ppo_random_permutation(int64_t* out, int64_t n, uint64_t seed, uint64_t epoch, void* stream);
+/* One window of that permutation with the position kept on the device: counters = uint32[2] {epoch, window};
+ * out[t] = permutation_epoch(window * window_len + t) for t < window_len (indices past n are not written), then the
+ * window advances (wrapping to the next epoch after the last one).  The launch arguments never change, which is what lets
+ * a CUDA graph of "indices of the next window -> its minibatch updates" serve every window of every epoch. */
+int ppo_random_permutation_window(int64_t* out, int64_t n, uint64_t seed, uint32_t* counters, int64_t window_len, void* stream);
 
 /* ---- PPO minibatch update (stable_baselines3 PPO.train for one minibatch), csrc/ppo_update_tc.cu ----
  * ppo_minibatch_grad: gradient of

@@ -191,15 +191,29 @@ extern "C" int ppo_random_permutation(int64_t* out, int64_t n, uint64_t seed, ui
     return FW_OK;
 }
 
+extern "C" int ppo_random_permutation_window(int64_t* out, int64_t n, uint64_t seed, uint32_t* counters, int64_t window_len,
+                                             void* stream) {
+    if (!out || !counters || n < 0 || window_len <= 0)
+        return pfail(FW_EINVAL, "ppo_random_permutation_window: null argument, negative length or empty window");
+    if (n >= (1ll << 62)) return pfail(FW_EINVAL, "ppo_random_permutation_window: n too large");
+    PCU(ppok_permutation_window(reinterpret_cast<long long*>(out), (long long)n, seed, counters, (long long)window_len,
+                                (cudaStream_t)stream));
+    return FW_OK;
+}
+
 extern "C" int ppo_counter_add(uint32_t* counter, uint32_t inc, void* stream) {
     if (!counter) return pfail(FW_EINVAL, "null argument");
     PCU(ppok_counter_add(counter, inc, (cudaStream_t)stream));
     return FW_OK;
 }
 
-// workspace layout (floats): [0,8) two doubles+pad as scratch (must start zeroed) | [8,16) adv stats |
-// [16, 16 + 160*P) per-CTA gradient partials | then 160*8 per-CTA loss statistics
-extern "C" int ppo_update_workspace_floats_a(int32_t d, int32_t a) { return 16 + 160 * ppo_param_count_a(d, a) + 160 * 8; }
+// workspace layout (floats): [0,8) pad | [8,16) adv stats | [16, 16 + 160*P) per-CTA gradient partials | 160*8 per-CTA loss
+// statistics | PPO_ADV_SCRATCH floats = doubles for the advantage statistics (arrival counter + 592 block partials; the
+// arrival counter must start zeroed, the kernel leaves it zeroed)
+#define PPO_ADV_SCRATCH (2 * (2 + 2 * 592))
+extern "C" int ppo_update_workspace_floats_a(int32_t d, int32_t a) {
+    return 16 + 160 * ppo_param_count_a(d, a) + 160 * 8 + PPO_ADV_SCRATCH;
+}
 extern "C" int ppo_update_workspace_floats(int32_t d) { return ppo_update_workspace_floats_a(d, PPO_ACT); }
 
 extern "C" int ppo_minibatch_grad_a(const float* params, int32_t d, int32_t a, const float* obs_norm, const float* act,
@@ -217,10 +231,11 @@ extern "C" int ppo_minibatch_grad_a(const float* params, int32_t d, int32_t a, c
         return pfail(FW_EINVAL, "workspace and action buffer must be 16-byte aligned");
     const int P = ppo_param_count_a(d, a);
     if (ppok_update_grid(batch) > 160) return pfail(FW_ESTATE, "more SMs than the workspace was sized for");
-    double* scratch = reinterpret_cast<double*>(workspace);
     float* adv_stats = workspace + 8;
     float* partial = workspace + 16;
     float* stats_partial = partial + (size_t)160 * P;
+    // 8-byte aligned: the workspace is 16-byte aligned and 16 + 160 * (P + 8) is even
+    double* scratch = reinterpret_cast<double*>(stats_partial + 160 * 8);
     if (a == 4 && d > PPO_TC_MAX_OBS)
         PCU(ppo_a4d64::ppok_minibatch_grad(params, d, obs_norm, act, logp_old, adv, ret, reinterpret_cast<const long long*>(idx), batch,
                                            clip_range, ent_coef, vf_coef, scratch, adv_stats, partial, stats_partial, grad, stats,

@@ -421,13 +421,64 @@ ppo_permutation_kernel(long long* __restrict__ out, long long n, int hb, uint32_
     out[i] = (long long)x;
 }
 
-cudaError_t ppok_permutation(long long* out, long long n, uint64_t seed, uint64_t epoch, cudaStream_t st) {
-    if (n <= 0) return cudaSuccess;
+__host__ __device__ __forceinline__ void ppo_perm_keys(uint64_t seed, uint64_t epoch, uint32_t& k0, uint32_t& k1) {
+    k0 = (uint32_t)(seed ^ (epoch * 0x9E3779B97F4A7C15ull));
+    k1 = (uint32_t)((seed >> 32) ^ ((epoch * 0xC2B2AE3D27D4EB4Full) >> 32) ^ 0xA5A5A5A5u);
+}
+
+__device__ __forceinline__ long long ppo_perm_at(long long i, long long n, int hb, uint32_t k0, uint32_t k1) {
+    const uint32_t mask = (1u << hb) - 1u;
+    unsigned long long x = (unsigned long long)i;
+    do {
+        uint32_t L = (uint32_t)(x >> hb) & mask, R = (uint32_t)x & mask;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint32_t t = L ^ (ppo_mix32(R, k0 + 0x9E3779B9u * (uint32_t)r) ^ ppo_mix32(R ^ k1, (uint32_t)r)) & mask;
+            L = R; R = t & mask;
+        }
+        x = ((unsigned long long)L << hb) | R;
+    } while (x >= (unsigned long long)n);
+    return (long long)x;
+}
+
+// The same permutation, one window at a time, with (epoch, window) read from device memory: the launch arguments never
+// change, so a CUDA graph of "window of indices -> its minibatch updates" can be replayed for every window of every epoch.
+// out[t] = perm_epoch(window * window_len + t)
+__global__ void __launch_bounds__(256)
+ppo_permutation_window_kernel(long long* __restrict__ out, long long n, int hb, uint64_t seed, const uint32_t* __restrict__ ctr,
+                              long long window_len) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = (long long)ctr[1] * window_len + t;
+    if (t >= window_len || i >= n) return;
+    uint32_t k0, k1;
+    ppo_perm_keys(seed, (uint64_t)ctr[0], k0, k1);
+    out[t] = ppo_perm_at(i, n, hb, k0, k1);
+}
+__global__ void ppo_permutation_advance_kernel(uint32_t* ctr, long long n, long long window_len) {
+    const uint32_t w = ctr[1] + 1u;
+    if ((long long)w * window_len >= n) { ctr[1] = 0u; ctr[0] += 1u; } else ctr[1] = w;
+}
+
+static int perm_half_bits(long long n) {
     int hb = 1;
     while (hb < 31 && (1ull << (2 * hb)) < (unsigned long long)n) ++hb;
-    const uint32_t k0 = (uint32_t)(seed ^ (epoch * 0x9E3779B97F4A7C15ull));
-    const uint32_t k1 = (uint32_t)((seed >> 32) ^ ((epoch * 0xC2B2AE3D27D4EB4Full) >> 32) ^ 0xA5A5A5A5u);
-    ppo_permutation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out, n, hb, k0, k1);
+    return hb;
+}
+
+cudaError_t ppok_permutation(long long* out, long long n, uint64_t seed, uint64_t epoch, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    uint32_t k0, k1;
+    ppo_perm_keys(seed, epoch, k0, k1);
+    ppo_permutation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(out, n, perm_half_bits(n), k0, k1);
+    return cudaGetLastError();
+}
+
+cudaError_t ppok_permutation_window(long long* out, long long n, uint64_t seed, uint32_t* ctr, long long window_len, cudaStream_t st) {
+    if (n <= 0 || window_len <= 0) return cudaSuccess;
+    ppo_permutation_window_kernel<<<(unsigned)((window_len + 255) / 256), 256, 0, st>>>(out, n, perm_half_bits(n), seed, ctr, window_len);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    ppo_permutation_advance_kernel<<<1, 1, 0, st>>>(ctr, n, window_len);
     return cudaGetLastError();
 }
 

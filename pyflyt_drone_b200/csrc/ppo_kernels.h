@@ -15,6 +15,7 @@ cudaError_t ppok_forward(const float* params, int d, const float* obs_raw, const
                          float* boot_rew = nullptr, int a = PPO_A);
 cudaError_t ppok_counter_add(uint32_t* ctr, uint32_t inc, cudaStream_t st);
 cudaError_t ppok_permutation(long long* out, long long n, uint64_t seed, uint64_t epoch, cudaStream_t st);
+cudaError_t ppok_permutation_window(long long* out, long long n, uint64_t seed, uint32_t* ctr, long long window_len, cudaStream_t st);
 cudaError_t ppok_moments(const float* x, int n, int d, double* stats, double* scratch, double* accum, cudaStream_t st);
 cudaError_t ppok_reward_normalize(const float* rew, const uint8_t* flags, int n, float gamma, float clip, float* ret,
                                   double* ret_stats, double* scratch, double* accum, float* rew_norm, float* done_out,

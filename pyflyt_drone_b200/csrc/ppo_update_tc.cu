@@ -222,6 +222,7 @@ struct UtSmem {
     static constexpr int PS_PI = 0, PS_VF = PS_PI + 2 * UT_ROWS * AP * 4, LIN = PS_VF + 2 * UT_ROWS * 4, LIN_ROW = (AP + 4) * 4;
     static_assert(LIN + UT_ROWS * LIN_ROW <= UT_ROWS * DP * 4, "head partials + loss inputs must fit the layer-1 operand buffer");
     static constexpr int TOTAL = SMALL + NSMALL * 4;
+    static_assert(2 * A + 7 <= 24, "block-reduction slots");
     static_assert(TOTAL <= 227 * 1024, "a CTA owns at most 227 KB of shared memory");
 };
 
@@ -328,7 +329,6 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         small[UtSmem::LOGSTD + tid] = params[pi_count + vf_count + tid];
     }
     if (tid == 0) small[UtSmem::B3_VF] = g_vf[H * d + H + H * H + H + H];
-    if (tid < 24) small[UtSmem::RED + tid] = 0.0f;
     const uint32_t bar = ut_smem_u32(&small[UtSmem::BAR]);
     uint32_t* tptr = reinterpret_cast<uint32_t*>(&small[UtSmem::TPTR]);
     if (tid == 0) {
@@ -740,7 +740,9 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         // this CTA had no tile: its partial is all zeros
         for (int k = tid; k < P; k += blockDim.x) outp[k] = 0.0f;
     }
-    // small sums (held by warpgroup 0): warp shuffle then shared atomics (24 slots), then threads 0..23 write them
+    // small sums (held by warpgroup 0): warp shuffle, one slot per (warp, sum) in the dead layer-1 operand buffer, then a
+    // fixed-order sum over the four warps -- no floating-point atomics, the update is bit-reproducible
+    float* wred = reinterpret_cast<float*>(smem + UtSmem::XB);
     if (q == 0) {
         // slots: db3_pi[A], db3_vf, dlog_std[A], then the six loss statistics
         float red[2 * A + 7];
@@ -754,10 +756,12 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
             float x = red[k];
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-            if ((tid & 31) == 0) atomicAdd(&small[UtSmem::RED + k], x);
+            if ((tid & 31) == 0) wred[warp * 24 + k] = x;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (tid < 2 * A + 7) small[UtSmem::RED + tid] = (wred[tid] + wred[24 + tid]) + (wred[48 + tid] + wred[72 + tid]);
     __syncthreads();
     if (tid < A) {
         outp[pi_count - A + tid] = small[UtSmem::RED + tid];                                  // db3_pi
@@ -778,6 +782,9 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
 
 #ifdef PPO_UT_SHARED
 // ------------------------------------------------------------------ minibatch advantage statistics (mean, unbiased std)
+// scratch: [0] block-arrival counter, [2 + 2b], [3 + 2b] = block b's sum / sum of squares; the last block to arrive adds the
+// block partials in index order (no floating-point atomics: the statistics do not depend on the block schedule)
+#define ADV_MAX_BLOCKS 592
 __global__ void __launch_bounds__(256)
 ppo_adv_stats_kernel(const float* __restrict__ adv, const long long* __restrict__ idx, int batch, double* __restrict__ scratch,
                      float* __restrict__ out) {
@@ -795,20 +802,25 @@ ppo_adv_stats_kernel(const float* __restrict__ adv, const long long* __restrict_
     if (threadIdx.x == 0) {
         double ta = 0, tb = 0;
         for (int k = 0; k < 8; ++k) { ta += s_a[k]; tb += s_b[k]; }
-        atomicAdd(&scratch[0], ta); atomicAdd(&scratch[1], tb);
+        scratch[2 + 2 * blockIdx.x] = ta; scratch[3 + 2 * blockIdx.x] = tb;
         __threadfence();
-        double prev = atomicAdd(&scratch[2], 1.0);
+        double prev = atomicAdd(&scratch[0], 1.0);
         is_last = (prev == (double)(gridDim.x - 1));
     }
     __syncthreads();
-    if (!is_last || threadIdx.x != 0) return;
+    if (!is_last || threadIdx.x >= 32) return;
     __threadfence();
-    volatile double* sc = scratch;
-    double n = (double)batch, mean = sc[0] / n;
-    double var = batch > 1 ? (sc[1] - n * mean * mean) / (n - 1.0) : 0.0;       // torch.std(): unbiased
+    const volatile double* sc = scratch;
+    double ta = 0.0, tb = 0.0;
+    for (int k = threadIdx.x; k < (int)gridDim.x; k += 32) { ta += sc[2 + 2 * k]; tb += sc[3 + 2 * k]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ta += __shfl_xor_sync(0xffffffffu, ta, o); tb += __shfl_xor_sync(0xffffffffu, tb, o); }
+    if (threadIdx.x != 0) return;
+    double n = (double)batch, mean = ta / n;
+    double var = batch > 1 ? (tb - n * mean * mean) / (n - 1.0) : 0.0;       // torch.std(): unbiased
     if (var < 0.0) var = 0.0;
     out[0] = (float)mean; out[1] = (float)sqrt(var);
-    scratch[0] = 0.0; scratch[1] = 0.0; scratch[2] = 0.0;
+    scratch[0] = 0.0;
 }
 
 // ------------------------------------------------------------------ partial-gradient reduction: grad[k] = sum_c partial[c][k]
@@ -907,7 +919,7 @@ int ppok_update_grid(int batch) {
 
 void ppok_launch_adv_stats(const float* adv, const long long* idx, int batch, double* scratch, float* adv_stats, cudaStream_t st) {
     int sblocks = (batch + 255) / 256;            // one gathered element per thread up to 4 blocks per SM
-    if (sblocks > 592) sblocks = 592;
+    if (sblocks > ADV_MAX_BLOCKS) sblocks = ADV_MAX_BLOCKS;
     ppo_adv_stats_kernel<<<sblocks, 256, 0, st>>>(adv, idx, batch, scratch, adv_stats);
 }
 

@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import time
 from dataclasses import dataclass
 
@@ -271,6 +272,12 @@ class PPO:
         self.tensor_core_forward = bool(tensor_core_forward) and self.d <= 32
         self._graph = None
         self._pending_capture = False
+        # the update's optimizer steps as a replayed graph of up to update_graph_steps consecutive minibatches (see _train_kernel)
+        self.update_graph = os.environ.get("FWPPO_UPDATE_GRAPH", "1") != "0"
+        self.update_graph_steps = 256
+        self._ugraph, self._ugraph_key, self._perm_win = None, None, None
+        self._perm_ctr = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self._perm_epoch = 0
         self._obs = None               # raw observation tensor (view of the env's persistent buffer)
         self._gen = torch.Generator(device=self.device).manual_seed(seed)
         self.stats = RolloutStats()
@@ -369,32 +376,62 @@ class PPO:
         NCCL all-reduce of the 49 KB gradient when world > 1, and one clip+Adam kernel.  No host sync inside."""
         total = self.n_steps * self.n_envs
         bs = min(self.batch_size, total)
-        theta = self.policy.theta.data
         lr, (b1, b2), eps = (self.optimizer.param_groups[0][k] for k in ("lr", "betas", "eps"))
         self._stats.zero_()
-        for _ in range(self.n_epochs):
-            perm = self._epoch_permutation(total)
-            for s in range(0, total, bs):
-                idx = perm[s:s + bs]
-                self._minibatch_grad_kernel(idx, self._grad, self._stats_mb)
-                if self.world > 1:
-                    import torch.distributed as dist
-                    dist.all_reduce(self._grad)                       # the path's one collective: 49 KB over NVLink
-                _lib.check(self.lib.ppo_adam_step(_p(theta), _p(self._grad), _p(self._adam_m), _p(self._adam_v),
-                                                  self.policy.count, lr, b1, b2, eps, self.max_grad_norm, 1.0 / self.world,
-                                                  _p(self._adam_t), _p(self._grad_norm), _stream()))
+        self._train_calls = getattr(self, "_train_calls", 0) + 1
+        steps_per_epoch = total // bs
+        # Optimizer steps are launch-latency sized at small minibatches (batch 128: four ~5 us kernels): from the second call
+        # on, a window of consecutive steps is one CUDA graph, replayed for every window of every epoch (the permutation
+        # position lives on the device).  The first call runs eagerly -- it is the warm-up a capture needs.
+        if self.use_graph and self.update_graph and self._train_calls > 1 and total % bs == 0:
+            chunk = max(c for c in range(1, min(steps_per_epoch, self.update_graph_steps) + 1) if steps_per_epoch % c == 0)
+            key = (total, bs, chunk, lr, b1, b2, eps, self.clip_range, self.ent_coef, self.vf_coef, self.max_grad_norm)
+            if self._ugraph is None or self._ugraph_key != key:
+                self._capture_update_graph(total, bs, chunk, lr, b1, b2, eps)
+                self._ugraph_key = key
+            self._perm_ctr.copy_(torch.tensor([self._perm_epoch + 1, 0], dtype=torch.int32), non_blocking=False)
+            for _ in range(self.n_epochs * (steps_per_epoch // chunk)):
+                self._ugraph.replay()
+            self._perm_epoch += self.n_epochs
+        else:
+            for _ in range(self.n_epochs):
+                perm = self._epoch_permutation(total)
+                for s in range(0, total, bs):
+                    self._optimizer_step(perm[s:s + bs], lr, b1, b2, eps)
         st = self._stats_mb
         n = max(float(st[5]), 1.0)
         return dict(policy_loss=float(st[0]) / n, value_loss=float(st[1]) / n, approx_kl=float(st[2]) / n,
                     clip_fraction=float(st[3]) / n, loss=float(st[0]) / n + self.vf_coef * float(st[1]) / n,
                     grad_norm=float(self._grad_norm))
 
+    def _optimizer_step(self, idx: torch.Tensor, lr: float, b1: float, b2: float, eps: float) -> None:
+        self._minibatch_grad_kernel(idx, self._grad, self._stats_mb)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._grad)                               # the path's one collective: 49 KB over NVLink
+        _lib.check(self.lib.ppo_adam_step(_p(self.policy.theta.data), _p(self._grad), _p(self._adam_m), _p(self._adam_v),
+                                          self.policy.count, lr, b1, b2, eps, self.max_grad_norm, 1.0 / self.world,
+                                          _p(self._adam_t), _p(self._grad_norm), _stream()))
+
+    def _capture_update_graph(self, total: int, bs: int, chunk: int, lr: float, b1: float, b2: float, eps: float) -> None:
+        """Graph of one window: indices of the next `chunk` minibatches (ppo_random_permutation_window advances the device
+        counters), then per minibatch the gradient kernels, the NCCL all-reduce when world > 1, and clip + Adam."""
+        if self._perm_win is None or self._perm_win.numel() != chunk * bs:
+            self._perm_win = torch.empty(chunk * bs, dtype=torch.int64, device=self.device)
+        torch.cuda.synchronize()
+        self._ugraph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._ugraph):
+            _lib.check(self.lib.ppo_random_permutation_window(_p(self._perm_win), total, self.seed & (2 ** 64 - 1),
+                                                              _p(self._perm_ctr), chunk * bs, _stream()))
+            for k in range(chunk):
+                self._optimizer_step(self._perm_win[k * bs:(k + 1) * bs], lr, b1, b2, eps)
+
     def _epoch_permutation(self, total: int) -> torch.Tensor:
         """Minibatch order of the next epoch (RolloutBuffer.get's np.random.permutation): a keyed Feistel bijection
         from one small kernel -- torch.randperm is a multi-pass radix sort of ``total`` keys, ~0.4 ms at 4 M samples."""
         if getattr(self, "_perm", None) is None or self._perm.numel() != total:
             self._perm = torch.empty(total, dtype=torch.int64, device=self.device)
-        self._perm_epoch = getattr(self, "_perm_epoch", 0) + 1
+        self._perm_epoch += 1
         _lib.check(self.lib.ppo_random_permutation(_p(self._perm), total, self.seed & (2 ** 64 - 1), self._perm_epoch,
                                                    _stream()))
         return self._perm

@@ -327,6 +327,56 @@ def test_random_permutation_is_a_fresh_bijection_every_epoch(model):
             assert 0.2 * n < d < 0.5 * n, (n, d)
 
 
+def test_windowed_permutation_walks_the_same_permutation(model):
+    """ppo_random_permutation_window (device-side epoch / window counters) yields exactly the slices of
+    ppo_random_permutation, window after window, and rolls over to the next epoch's permutation."""
+    import ctypes as C
+    lib = model.lib
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    n, wl = 10000, 2048                      # five windows per epoch, the last one short
+    ctr = torch.tensor([7, 0], dtype=torch.int32, device="cuda")
+    full = torch.empty(n, dtype=torch.int64, device="cuda")
+    for epoch in (7, 8):
+        assert lib.ppo_random_permutation(C.c_void_p(full.data_ptr()), n, 99, epoch, st) == 0
+        for w in range(5):
+            win = torch.full((wl,), -1, dtype=torch.int64, device="cuda")
+            assert lib.ppo_random_permutation_window(C.c_void_p(win.data_ptr()), n, 99, C.c_void_p(ctr.data_ptr()), wl, st) == 0
+            m = min(wl, n - w * wl)
+            assert torch.equal(win[:m], full[w * wl:w * wl + m]) and bool((win[m:] == -1).all())
+    assert ctr.tolist() == [9, 0]
+
+
+def test_graph_replayed_update_equals_the_eager_update():
+    """From the second train() call on, windows of optimizer steps run as one replayed CUDA graph: from the same rollout
+    buffer, parameters and optimizer state, the graph-replayed update and the eager loop end bit-identical (parameters, Adam
+    moments, step and epoch counters)."""
+    from pyflyt_drone_b200.ppo import PPO
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    env = FixedwingVecEnv(256, preset="waypoints_v3", seed=9)
+    m = PPO("MlpPolicy", env, n_steps=16, batch_size=128, n_epochs=3, seed=9)
+    m.update_graph_steps = 8                 # 32 minibatches per epoch -> four windows of eight
+    m.collect_rollouts()
+    m.train()                                # first call: eager warm-up
+    snap = [t.clone() for t in (m.policy.theta.data, m._adam_m, m._adam_v, m._adam_t)]
+    epoch0 = m._perm_epoch
+    out = {}
+    for mode in (True, False):
+        for dst, src in zip((m.policy.theta.data, m._adam_m, m._adam_v, m._adam_t), snap):
+            dst.copy_(src)
+        m._perm_epoch = epoch0
+        m.update_graph = mode
+        m.train()
+        torch.cuda.synchronize()
+        out[mode] = (m.policy.theta.detach().clone(), m._adam_m.clone(), m._adam_v.clone(), int(m._adam_t), m._perm_epoch,
+                     m._stats_mb.clone())
+    assert m._ugraph is not None
+    assert out[True][3] == out[False][3] == 2 * 3 * 32 and out[True][4] == out[False][4] == epoch0 + 3
+    assert not torch.equal(out[True][0], snap[0])
+    for a, b in zip(out[True][:3] + out[True][5:], out[False][:3] + out[False][5:]):
+        assert torch.equal(a, b)
+    env.close()
+
+
 def test_adam_step_matches_torch_optim(model):
     from pyflyt_drone_b200 import _lib
     from pyflyt_drone_b200.ppo import _p, _stream
