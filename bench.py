@@ -394,6 +394,16 @@ def ppo_measure(preset: str, n_envs: int, n_steps: int, batch_size: int, n_epoch
             dist.all_reduce(model._grad)
         e1.record(); torch.cuda.synchronize()
         ar_us = _max_over_ranks(e0.elapsed_time(e1) / 200 * 1e3, world)
+    in_sync = True
+    if world > 1:                                    # every rank must hold the same parameters after the timed updates
+        th = model.policy.theta.detach().clone()
+        dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.equal(th, model.policy.theta.detach()))
+        flag = torch.tensor([1.0 if in_sync else 0.0], device=th.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        in_sync = bool(flag.item() > 0.5)
+    chunk = model._ugraph_key[2] if getattr(model, "_ugraph_key", None) else 0
+    perm_launches = 2 * (mb // chunk) if chunk else 1          # per epoch: window + advance kernels per graph, or one permutation
     out = {"sps": iters * per_iter / dt, "n_gpus": world, "envs_per_gpu": n_envs, "n_steps": n_steps, "batch_size_per_gpu": batch_size,
            "n_epochs": n_epochs, "iterations": iters, "iter_ms": dt / iters * 1e3, "rollout_s": rollout_s, "update_s": update_s,
            "rollout_env_steps_per_sec": per_iter / max(rollout_s, 1e-9),
@@ -404,7 +414,8 @@ def ppo_measure(preset: str, n_envs: int, n_steps: int, batch_size: int, n_epoch
            "forward": "tcgen05 kind::tf32 policy/value forward" if model.tensor_core_forward else "CUDA-core fp32 forward",
            # rollout graph per step: obs moments, policy forward, env step, return moments + reward finalise, bootstrap;
            # per rollout: counter, last values, GAE; per epoch: permutation; per minibatch: adv stats, gradient, reduce, Adam
-           "gpu_launches": int(iters * (n_steps * 6 + 3 + run_epochs * (1 + mb * 4)))}
+           "update_graph_steps": chunk, "ranks_in_sync": in_sync,
+           "gpu_launches": int(iters * (n_steps * 6 + 3 + run_epochs * (perm_launches + mb * 4)))}
     if run_epochs < n_epochs:
         epoch_s = update_s / run_epochs
         full = rollout_s + n_epochs * epoch_s

@@ -131,6 +131,18 @@ int ppo_minibatch_grad(const float* params, int32_t d, const float* obs_norm, co
                        const float* adv, const float* ret, const int64_t* idx, int32_t batch, float clip_range,
                        float ent_coef, float vf_coef, float* workspace, float* grad, float* stats, void* stream);
 
+/* `steps` consecutive optimizer steps of a single process in ONE launch of one thread block: for s = 0..steps-1 the minibatch
+ * idx[s*batch .. (s+1)*batch) goes through its advantage statistics, the gradient above, clip_grad_norm_ and Adam.step
+ * (the arithmetic of ppo_minibatch_grad + ppo_adam_step, grad_scale 1), the parameters staying in global memory between
+ * steps.  For stable_baselines3-sized minibatches (batch_size 128 = one tile): an optimizer step is then bounded by the
+ * tile's latency instead of four kernel launches.  grad / stats / grad_norm_out hold the last step's values. */
+#define PPO_FUSED_MAX_BATCH 4096
+int ppo_minibatch_steps_a(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act, const float* logp_old,
+                          const float* adv, const float* ret, const int64_t* idx, int32_t batch, int32_t steps, float clip_range,
+                          float ent_coef, float vf_coef, float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2,
+                          float eps, float max_grad_norm, int32_t* step_counter, float* grad_norm_out, float* grad, float* stats,
+                          void* stream);
+
 /* torch.nn.utils.clip_grad_norm_(max_grad_norm) followed by torch.optim.Adam.step (no weight decay / amsgrad) on the
  * flat parameter vector; grad is pre-multiplied by grad_scale (1 / world_size after the NCCL sum).
  * step_counter: device int32 incremented by the call (bias correction). */

@@ -251,6 +251,34 @@ extern "C" int ppo_minibatch_grad_a(const float* params, int32_t d, int32_t a, c
     return FW_OK;
 }
 
+extern "C" int ppo_minibatch_steps_a(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act,
+                                     const float* logp_old, const float* adv, const float* ret, const int64_t* idx,
+                                     int32_t batch, int32_t steps, float clip_range, float ent_coef, float vf_coef,
+                                     float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                                     float max_grad_norm, int32_t* step_counter, float* grad_norm_out, float* grad, float* stats,
+                                     void* stream) {
+    if (!params || !obs_norm || !act || !logp_old || !adv || !ret || !idx || !exp_avg || !exp_avg_sq || !step_counter || !grad ||
+        !stats)
+        return pfail(FW_EINVAL, "null argument");
+    if (batch <= 0 || batch > PPO_FUSED_MAX_BATCH)
+        return pfail(FW_EINVAL, "batch %d out of range [1,%d] for the single-CTA optimizer steps", batch, PPO_FUSED_MAX_BATCH);
+    if (steps <= 0) return pfail(FW_EINVAL, "steps must be positive");
+    int rc = (a == 4) ? check_d(d) : check_d_tc(d);
+    if (rc) return rc;
+    if ((rc = check_a(a)) != 0) return rc;
+    if (reinterpret_cast<uintptr_t>(act) & 15u) return pfail(FW_EINVAL, "action buffer must be 16-byte aligned");
+    if (ppo_param_count_a(d, a) > 16384) return pfail(FW_EINVAL, "parameter vector too long");
+    const long long* ix = reinterpret_cast<const long long*>(idx);
+    cudaStream_t st = (cudaStream_t)stream;
+#define STEPS_ARGS params, d, obs_norm, act, logp_old, adv, ret, ix, batch, steps, clip_range, ent_coef, vf_coef, exp_avg, exp_avg_sq, \
+                   lr, beta1, beta2, eps, max_grad_norm, step_counter, grad_norm_out, grad, stats, st
+    if (a == 4 && d > PPO_TC_MAX_OBS) PCU(ppo_a4d64::ppok_minibatch_steps(STEPS_ARGS));
+    else if (a == 4) PCU(ppo_a4::ppok_minibatch_steps(STEPS_ARGS));
+    else PCU(ppo_a6::ppok_minibatch_steps(STEPS_ARGS));
+#undef STEPS_ARGS
+    return FW_OK;
+}
+
 extern "C" int ppo_minibatch_grad(const float* params, int32_t d, const float* obs_norm, const float* act,
                                   const float* logp_old, const float* adv, const float* ret, const int64_t* idx,
                                   int32_t batch, float clip_range, float ent_coef, float vf_coef, float* workspace,

@@ -44,6 +44,11 @@ int ppok_update_grid(int batch);
                                     const float* adv, const float* ret, const long long* idx, int batch, float clip_range, \
                                     float ent_coef, float vf_coef, double* scratch, float* adv_stats, float* partial,      \
                                     float* stats_partial, float* grad, float* stats, cudaStream_t st);                     \
+    cudaError_t ppok_minibatch_steps(float* params, int d, const float* obs, const float* act, const float* logp_old,       \
+                                     const float* adv, const float* ret, const long long* idx, int batch, int steps,       \
+                                     float clip_range, float ent_coef, float vf_coef, float* m, float* v, float lr,        \
+                                     float beta1, float beta2, float eps, float max_norm, int* step_ctr, float* norm_out,  \
+                                     float* grad, float* stats, cudaStream_t st);                                          \
     }
 PPOK_DECLARE_MINIBATCH_GRAD(ppo_a4)
 PPOK_DECLARE_MINIBATCH_GRAD(ppo_a6)

@@ -216,7 +216,8 @@ struct UtSmem {
     // floats inside SMALL
     static constexpr int B1 = 0 /* pi 64 | vf 64 */, B2 = 128, W3_PI = 256 /* [64][AP]: AP/4 float4s per hidden unit */,
                          W3_VF = W3_PI + H * AP, B3_PI = W3_VF + H, B3_VF = B3_PI + AP, LOGSTD = B3_VF + 4,
-                         RED = LOGSTD + AP /* 24 block-reduction slots */, BAR = RED + 24, TPTR = BAR + 4, NSMALL = TPTR + 4;
+                         RED = LOGSTD + AP /* 24 block-reduction slots */, BAR = RED + 24, TPTR = BAR + 4,
+                         FUSED = TPTR + 4 /* adv mean, adv std, clip coefficient, Adam step (as int) */, NSMALL = FUSED + 4;
     // the layer-1 operand buffer XB is dead after M1 and then carries, per tile: the policy-head partial sums of warpgroups
     // 0 and 1 (AP floats per row each), the value-head partials of warpgroups 2 and 3, and each row's loss inputs
     static constexpr int PS_PI = 0, PS_VF = PS_PI + 2 * UT_ROWS * AP * 4, LIN = PS_VF + 2 * UT_ROWS * 4, LIN_ROW = (AP + 4) * 4;
@@ -238,10 +239,10 @@ struct UtSmem {
 static_assert(UT_DB1 + 16 <= UT_TMEM_COLS, "TMEM column plan");
 
 // off: fp32 copy (or -1), off_bf16: bf16 copy (or -1), off_lo: bf16 of the remainder v - bf16(v) (or -1)
-__device__ void ut_load_weight(char* smem, int off, const float* __restrict__ g, int K, int d, int off_bf16 = -1, int off_lo = -1) {
+__device__ void ut_load_weight(char* smem, int off, const float* g, int K, int d, int off_bf16 = -1, int off_lo = -1) {
     for (int i = threadIdx.x; i < H * K; i += blockDim.x) {
         int j = i / K, k = i % K;
-        const float v = k < d ? g[j * d + k] : 0.0f;
+        const float v = k < d ? __ldcg(g + j * d + k) : 0.0f;
         if (off >= 0) *reinterpret_cast<float*>(smem + off + ut_off(j, k, K)) = v;
         const __nv_bfloat16 hi = __float2bfloat16(v);
         if (off_bf16 >= 0) *reinterpret_cast<__nv_bfloat16*>(smem + off_bf16 + ut_off16(j, k, K)) = hi;
@@ -250,6 +251,10 @@ __device__ void ut_load_weight(char* smem, int off, const float* __restrict__ g,
 }
 
 struct PpoLossCfg { float clip_range, ent_coef, vf_coef, inv_batch, grad_scale, inv_grad_scale; };
+// Fused mode (steps > 0; one CTA): `steps` consecutive optimizer steps in one launch -- per step the minibatch's advantage
+// statistics, the gradient (written to the caller's gradient buffer), clip_grad_norm_ and Adam on the parameters in global
+// memory, which the next step then stages again.  stable_baselines3's batch_size = 128 is one tile per step.
+struct PpoFusedCfg { int steps; float lr, beta1, beta2, eps, max_norm; float* params; float* m; float* v; int* step_ctr; float* norm_out; };
 
 // Asynchronously gather 8 consecutive observation columns [8*part, 8*part+8) (per 32-column slab) of rollout row g straight into the
 // fp32 layer-1 A operand (cp.async with zero fill for padding columns and dead rows): the random 112-byte row reads
@@ -289,10 +294,10 @@ __device__ __forceinline__ void ut_gather_async(char* smem, const float* __restr
 // epilogue, so the per-thread serial work is a quarter of a row and 16 warps hide each other's TMEM/SFU latency.
 // tanh' factors are kept in registers (packed bf16) from the forward epilogues instead of being recomputed.
 __global__ void __launch_bounds__(UT_THREADS, 1)
-ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restrict__ obs, const float* __restrict__ act,
+ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, const float* __restrict__ act,
                    const float* __restrict__ logp_old, const float* __restrict__ adv, const float* __restrict__ ret,
-                   const long long* __restrict__ idx, int batch, const float* __restrict__ adv_stats, PpoLossCfg cfg,
-                   float* __restrict__ out_partial, float* __restrict__ out_stats, int P) {
+                   const long long* __restrict__ idx_all, int batch, const float* __restrict__ adv_stats, PpoLossCfg cfg,
+                   float* out_partial, float* __restrict__ out_stats, int P, PpoFusedCfg fz) {
     extern __shared__ __align__(1024) char smem[];
     float* small = reinterpret_cast<float*>(smem + UtSmem::SMALL);
     const int tid = threadIdx.x, warp = tid >> 5;
@@ -304,31 +309,6 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
     const float* g_pi = params;
     const float* g_vf = params + pi_count;
 
-    ut_load_weight(smem, UtSmem::W1_PI, g_pi, DP, d);
-    ut_load_weight(smem, UtSmem::W1_VF, g_vf, DP, d);
-#if UT_SPLIT
-    ut_load_weight(smem, -1, g_pi + H * d + H, H, H, UtSmem::W2B_PI, UtSmem::W2L_PI);
-    ut_load_weight(smem, -1, g_vf + H * d + H, H, H, UtSmem::W2B_VF, UtSmem::W2L_VF);
-#else
-    ut_load_weight(smem, UtSmem::W2_PI, g_pi + H * d + H, H, H, UtSmem::W2B_PI);
-    ut_load_weight(smem, UtSmem::W2_VF, g_vf + H * d + H, H, H, UtSmem::W2B_VF);
-#endif
-    if (tid < H) {
-        small[UtSmem::B1 + tid] = g_pi[H * d + tid];
-        small[UtSmem::B1 + H + tid] = g_vf[H * d + tid];
-        small[UtSmem::B2 + tid] = g_pi[H * d + H + H * H + tid];
-        small[UtSmem::B2 + H + tid] = g_vf[H * d + H + H * H + tid];
-        small[UtSmem::W3_VF + tid] = g_vf[H * d + H + H * H + H + tid];
-    }
-    for (int i = tid; i < AP * H; i += blockDim.x) {                                               // [j][a], zero padded to AP
-        const int j = i / AP, a = i % AP;
-        small[UtSmem::W3_PI + i] = a < A ? g_pi[H * d + H + H * H + H + a * H + j] : 0.0f;
-    }
-    if (tid < A) {
-        small[UtSmem::B3_PI + tid] = g_pi[H * d + H + H * H + H + A * H + tid];
-        small[UtSmem::LOGSTD + tid] = params[pi_count + vf_count + tid];
-    }
-    if (tid == 0) small[UtSmem::B3_VF] = g_vf[H * d + H + H * H + H + H];
     const uint32_t bar = ut_smem_u32(&small[UtSmem::BAR]);
     uint32_t* tptr = reinterpret_cast<uint32_t*>(&small[UtSmem::TPTR]);
     if (tid == 0) {
@@ -348,7 +328,56 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
     const uint32_t sb = ut_smem_u32(smem);
     uint32_t phase = 0;
 
-    const float adv_mean = adv_stats[0], adv_istd = 1.0f / (adv_stats[1] + 1e-8f);
+
+    const int nsteps = fz.steps > 0 ? fz.steps : 1;
+    for (int os = 0; os < nsteps; ++os) {
+    const long long* __restrict__ idx = idx_all + (size_t)os * batch;
+    ut_load_weight(smem, UtSmem::W1_PI, g_pi, DP, d);
+    ut_load_weight(smem, UtSmem::W1_VF, g_vf, DP, d);
+#if UT_SPLIT
+    ut_load_weight(smem, -1, g_pi + H * d + H, H, H, UtSmem::W2B_PI, UtSmem::W2L_PI);
+    ut_load_weight(smem, -1, g_vf + H * d + H, H, H, UtSmem::W2B_VF, UtSmem::W2L_VF);
+#else
+    ut_load_weight(smem, UtSmem::W2_PI, g_pi + H * d + H, H, H, UtSmem::W2B_PI);
+    ut_load_weight(smem, UtSmem::W2_VF, g_vf + H * d + H, H, H, UtSmem::W2B_VF);
+#endif
+    if (tid < H) {
+        small[UtSmem::B1 + tid] = __ldcg(g_pi + H * d + tid);
+        small[UtSmem::B1 + H + tid] = __ldcg(g_vf + H * d + tid);
+        small[UtSmem::B2 + tid] = __ldcg(g_pi + H * d + H + H * H + tid);
+        small[UtSmem::B2 + H + tid] = __ldcg(g_vf + H * d + H + H * H + tid);
+        small[UtSmem::W3_VF + tid] = __ldcg(g_vf + H * d + H + H * H + H + tid);
+    }
+    for (int i = tid; i < AP * H; i += blockDim.x) {                                               // [j][a], zero padded to AP
+        const int j = i / AP, a = i % AP;
+        small[UtSmem::W3_PI + i] = a < A ? __ldcg(g_pi + H * d + H + H * H + H + a * H + j) : 0.0f;
+    }
+    if (tid < A) {
+        small[UtSmem::B3_PI + tid] = __ldcg(g_pi + H * d + H + H * H + H + A * H + tid);
+        small[UtSmem::LOGSTD + tid] = __ldcg(params + pi_count + vf_count + tid);
+    }
+    if (tid == 0) small[UtSmem::B3_VF] = __ldcg(g_vf + H * d + H + H * H + H + H);
+    if (fz.steps > 0) {
+        // minibatch advantage statistics (mean, unbiased std) in double, summed in a fixed order; staged in the H2 buffer
+        double sa = 0.0, sq = 0.0;
+        for (int i = tid; i < batch; i += UT_THREADS) { const double v = (double)adv[idx[i]]; sa += v; sq += v * v; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { sa += __shfl_xor_sync(0xffffffffu, sa, o); sq += __shfl_xor_sync(0xffffffffu, sq, o); }
+        double* sd = reinterpret_cast<double*>(smem + UtSmem::H2B);
+        if ((tid & 31) == 0) { sd[2 * warp] = sa; sd[2 * warp + 1] = sq; }
+        __syncthreads();
+        if (tid == 0) {
+            double ta = 0.0, tb = 0.0;
+            for (int k = 0; k < UT_THREADS / 32; ++k) { ta += sd[2 * k]; tb += sd[2 * k + 1]; }
+            const double n = (double)batch, mean = ta / n;
+            double var = batch > 1 ? (tb - n * mean * mean) / (n - 1.0) : 0.0;
+            if (var < 0.0) var = 0.0;
+            small[UtSmem::FUSED] = (float)mean; small[UtSmem::FUSED + 1] = (float)sqrt(var);
+        }
+    }
+    __syncthreads();
+    const float adv_mean = fz.steps > 0 ? small[UtSmem::FUSED] : adv_stats[0];
+    const float adv_istd = 1.0f / ((fz.steps > 0 ? small[UtSmem::FUSED + 1] : adv_stats[1]) + 1e-8f);
 
     // per-thread running sums over this CTA's samples (warpgroup 0 only): db3_pi[4], db3_vf, dlogstd[4], loss statistics[6]
     float acc_db3[A], acc_db3v = 0.f, acc_dls[A];
@@ -774,6 +803,41 @@ ppo_grad_tc_kernel(const float* __restrict__ params, int d, const float* __restr
         if (tid < 6) v = small[UtSmem::RED + 2 * A + 1 + tid];
         out_stats[(size_t)blockIdx.x * 8 + tid] = v;
     }
+    if (fz.steps > 0) {
+        // ---- clip_grad_norm_ + Adam on the gradient this CTA has just written (the arithmetic of ppo_adam_kernel)
+        __threadfence();
+        __syncthreads();
+        float ss = 0.0f;
+        for (int k = tid; k < P; k += UT_THREADS) { const float g = __ldcg(outp + k); ss = fmaf(g, g, ss); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if ((tid & 31) == 0) wred[warp] = ss;
+        __syncthreads();
+        if (tid == 0) {
+            float x = 0.0f;
+            for (int k = 0; k < UT_THREADS / 32; ++k) x += wred[k];
+            const float norm = sqrtf(x);
+            const int t = fz.step_ctr[0] + 1;
+            small[UtSmem::FUSED + 2] = fminf(1.0f, fz.max_norm / (norm + 1e-6f));
+            small[UtSmem::FUSED + 3] = __int_as_float(t);
+            fz.step_ctr[0] = t;
+            if (fz.norm_out != nullptr) fz.norm_out[0] = norm;
+        }
+        __syncthreads();
+        const float coef = small[UtSmem::FUSED + 2];
+        const float tf = (float)__float_as_int(small[UtSmem::FUSED + 3]);
+        const float inv_bc1 = 1.0f / (1.0f - powf(fz.beta1, tf)), inv_bc2 = 1.0f / (1.0f - powf(fz.beta2, tf));
+        for (int k = tid; k < P; k += UT_THREADS) {
+            const float gg = __ldcg(outp + k) * coef;
+            const float m1 = fz.beta1 * fz.m[k] + (1.0f - fz.beta1) * gg;
+            const float v1 = fz.beta2 * fz.v[k] + (1.0f - fz.beta2) * gg * gg;
+            fz.m[k] = m1; fz.v[k] = v1;
+            fz.params[k] = __ldcg(fz.params + k) - fz.lr * (m1 * inv_bc1) / (sqrtf(v1 * inv_bc2) + fz.eps);
+        }
+        __threadfence();
+        __syncthreads();       // the next step stages the updated parameters
+    }
+    }   // optimizer steps
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"((uint32_t)UT_TMEM_COLS) : "memory");
 }
@@ -961,9 +1025,32 @@ cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, co
     float gs = 1.0f;
     while (gs < (float)batch && gs < 1048576.0f) gs *= 2.0f;
     PpoLossCfg cfg{clip_range, ent_coef, vf_coef, 1.0f / (float)batch, gs, 1.0f / gs};
+    PpoFusedCfg fz{};
     ppo_grad_tc_kernel<<<grid, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, adv_stats, cfg,
-                                                             partial, stats_partial, P);
+                                                             partial, stats_partial, P, fz);
     ppok_launch_grad_reduce(partial, stats_partial, grid, P, grad, stats, st);
+    return cudaGetLastError();
+}
+
+// `steps` consecutive optimizer steps over idx[0 .. steps*batch) in ONE single-CTA launch (see PpoFusedCfg)
+cudaError_t ppok_minibatch_steps(float* params, int d, const float* obs, const float* act, const float* logp_old, const float* adv,
+                                 const float* ret, const long long* idx, int batch, int steps, float clip_range, float ent_coef,
+                                 float vf_coef, float* m, float* v, float lr, float beta1, float beta2, float eps, float max_norm,
+                                 int* step_ctr, float* norm_out, float* grad, float* stats, cudaStream_t st) {
+    if (d > DP || steps <= 0) return cudaErrorInvalidValue;
+    if (!g_ut_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL);
+        if (e != cudaSuccess) return e;
+        g_ut_attr_set = true;
+    }
+    const int H_ = PPO_H, A_ = A;
+    const int P = (H_ * d + H_ + H_ * H_ + H_ + A_ * H_ + A_) + (H_ * d + H_ + H_ * H_ + H_ + H_ + 1) + A_;
+    float gs = 1.0f;
+    while (gs < (float)batch && gs < 1048576.0f) gs *= 2.0f;
+    PpoLossCfg cfg{clip_range, ent_coef, vf_coef, 1.0f / (float)batch, gs, 1.0f / gs};
+    PpoFusedCfg fz{steps, lr, beta1, beta2, eps, max_norm, params, m, v, step_ctr, norm_out};
+    ppo_grad_tc_kernel<<<1, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, nullptr, cfg, grad,
+                                                          stats, P, fz);
     return cudaGetLastError();
 }
 }  // namespace PPO_UT_NS

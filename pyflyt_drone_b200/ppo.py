@@ -275,6 +275,8 @@ class PPO:
         # the update's optimizer steps as a replayed graph of up to update_graph_steps consecutive minibatches (see _train_kernel)
         self.update_graph = os.environ.get("FWPPO_UPDATE_GRAPH", "1") != "0"
         self.update_graph_steps = 256
+        # minibatches up to this size take the single-CTA multi-step kernel when there is no gradient all-reduce (world 1)
+        self.fused_steps_max_batch = int(os.environ.get("FWPPO_FUSED_MAX_BATCH", "256"))
         self._ugraph, self._ugraph_key, self._perm_win = None, None, None
         self._perm_ctr = torch.zeros(2, dtype=torch.int32, device=self.device)
         self._perm_epoch = 0
@@ -383,7 +385,21 @@ class PPO:
         # Optimizer steps are launch-latency sized at small minibatches (batch 128: four ~5 us kernels): from the second call
         # on, a window of consecutive steps is one CUDA graph, replayed for every window of every epoch (the permutation
         # position lives on the device).  The first call runs eagerly -- it is the warm-up a capture needs.
-        if self.use_graph and self.update_graph and self._train_calls > 1 and total % bs == 0:
+        if self.world == 1 and bs <= self.fused_steps_max_batch and total % bs == 0:
+            # stable_baselines3-sized minibatches (batch_size 128 = one 128-row tile): a window of consecutive optimizer steps
+            # is ONE single-CTA launch (ppo_minibatch_steps_a) -- advantage statistics, gradient, clip and Adam per step, no
+            # launch in between
+            b = self.buf
+            chunk = max(c for c in range(1, min(steps_per_epoch, self.update_graph_steps) + 1) if steps_per_epoch % c == 0)
+            for _ in range(self.n_epochs):
+                perm = self._epoch_permutation(total)
+                for s in range(0, total, chunk * bs):
+                    _lib.check(self.lib.ppo_minibatch_steps_a(
+                        _p(self.policy.theta.data), self.d, self.a, _p(b["obs"]), _p(b["act"]), _p(b["logp"]), _p(b["adv"]),
+                        _p(b["ret"]), _p(perm[s:s + chunk * bs]), bs, chunk, self.clip_range, self.ent_coef, self.vf_coef,
+                        _p(self._adam_m), _p(self._adam_v), lr, b1, b2, eps, self.max_grad_norm, _p(self._adam_t),
+                        _p(self._grad_norm), _p(self._grad), _p(self._stats_mb), _stream()))
+        elif self.use_graph and self.update_graph and self._train_calls > 1 and total % bs == 0:
             chunk = max(c for c in range(1, min(steps_per_epoch, self.update_graph_steps) + 1) if steps_per_epoch % c == 0)
             key = (total, bs, chunk, lr, b1, b2, eps, self.clip_range, self.ent_coef, self.vf_coef, self.max_grad_norm)
             if self._ugraph is None or self._ugraph_key != key:

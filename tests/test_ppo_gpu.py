@@ -355,6 +355,7 @@ def test_graph_replayed_update_equals_the_eager_update():
     env = FixedwingVecEnv(256, preset="waypoints_v3", seed=9)
     m = PPO("MlpPolicy", env, n_steps=16, batch_size=128, n_epochs=3, seed=9)
     m.update_graph_steps = 8                 # 32 minibatches per epoch -> four windows of eight
+    m.fused_steps_max_batch = 0              # not the single-CTA multi-step kernel: the launch-per-kernel path under test
     m.collect_rollouts()
     m.train()                                # first call: eager warm-up
     snap = [t.clone() for t in (m.policy.theta.data, m._adam_m, m._adam_v, m._adam_t)]
@@ -374,6 +375,49 @@ def test_graph_replayed_update_equals_the_eager_update():
     assert not torch.equal(out[True][0], snap[0])
     for a, b in zip(out[True][:3] + out[True][5:], out[False][:3] + out[False][5:]):
         assert torch.equal(a, b)
+    env.close()
+
+
+@pytest.mark.parametrize("preset,batch", [("waypoints_v3", 128), ("waypoints_v3", 200), ("lowlevel", 128), ("objlock_duck", 128)])
+def test_single_cta_optimizer_steps_equal_the_launch_per_kernel_update(preset, batch):
+    """ppo_minibatch_steps_a (a window of optimizer steps in one single-CTA launch: advantage statistics, gradient, clip,
+    Adam per step) against the same steps as separate launches (ppo_minibatch_grad_a + ppo_adam_step): same gradient kernel
+    body, so parameters after 12 steps agree to fp32 reduction-order noise, step counter and last-step statistics match."""
+    from pyflyt_drone_b200.ppo import PPO
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    env = FixedwingVecEnv(256, preset=preset, seed=4)
+    m = PPO("MlpPolicy", env, n_steps=16, batch_size=batch, n_epochs=1, seed=4, use_cuda_graph=False)
+    m.collect_rollouts()
+    with torch.no_grad():
+        m.policy.theta.add_(0.02 * torch.randn(m.policy.count, device=m.device, generator=m._gen))
+    snap = [t.clone() for t in (m.policy.theta.data, m._adam_m, m._adam_v, m._adam_t)]
+    perm = m._epoch_permutation(16 * 256).clone()
+    steps, out = 12, {}
+    for fused in (True, False):
+        for dst, src in zip((m.policy.theta.data, m._adam_m, m._adam_v, m._adam_t), snap):
+            dst.copy_(src)
+        if fused:
+            b = m.buf
+            _lib_check = __import__("pyflyt_drone_b200")._lib.check
+            from pyflyt_drone_b200.ppo import _p, _stream
+            _lib_check(m.lib.ppo_minibatch_steps_a(
+                _p(m.policy.theta.data), m.d, m.a, _p(b["obs"]), _p(b["act"]), _p(b["logp"]), _p(b["adv"]), _p(b["ret"]),
+                _p(perm), batch, steps, m.clip_range, m.ent_coef, m.vf_coef, _p(m._adam_m), _p(m._adam_v), 3e-4, 0.9, 0.999, 1e-5,
+                m.max_grad_norm, _p(m._adam_t), _p(m._grad_norm), _p(m._grad), _p(m._stats_mb), _stream()))
+        else:
+            for k in range(steps):
+                m._optimizer_step(perm[k * batch:(k + 1) * batch], 3e-4, 0.9, 0.999, 1e-5)
+        torch.cuda.synchronize()
+        out[fused] = (m.policy.theta.detach().clone(), m._adam_m.clone(), m._adam_v.clone(), int(m._adam_t), m._stats_mb.clone(),
+                      float(m._grad_norm), m._grad.clone())
+    assert out[True][3] == out[False][3] == int(snap[3]) + steps
+    moved = float((out[False][0] - snap[0]).abs().max())
+    assert moved > 1e-3
+    assert float((out[True][0] - out[False][0]).abs().max()) < 1e-3 * moved
+    assert torch.allclose(out[True][1], out[False][1], rtol=1e-3, atol=1e-6) and torch.allclose(out[True][2], out[False][2], rtol=1e-3, atol=1e-9)
+    assert torch.allclose(out[True][4], out[False][4], rtol=1e-3, atol=1e-4) and float(out[True][4][5]) == batch
+    assert out[True][5] == pytest.approx(out[False][5], rel=1e-3)
+    assert float((out[True][6] - out[False][6]).norm() / out[False][6].norm()) < 1e-3
     env.close()
 
 
