@@ -238,15 +238,63 @@ struct UtSmem {
 #define UT_DB1 (UT_DB2 + 16)  // 16 : [dZ1]^T dOut|1  (col A+1 = db1)
 static_assert(UT_DB1 + 16 <= UT_TMEM_COLS, "TMEM column plan");
 
-// off: fp32 copy (or -1), off_bf16: bf16 copy (or -1), off_lo: bf16 of the remainder v - bf16(v) (or -1)
-__device__ void ut_load_weight(char* smem, int off, const float* g, int K, int d, int off_bf16 = -1, int off_lo = -1) {
-    for (int i = threadIdx.x; i < H * K; i += blockDim.x) {
-        int j = i / K, k = i % K;
-        const float v = k < d ? __ldcg(g + j * d + k) : 0.0f;
-        if (off >= 0) *reinterpret_cast<float*>(smem + off + ut_off(j, k, K)) = v;
-        const __nv_bfloat16 hi = __float2bfloat16(v);
+// off: fp32 copy (or -1), off_bf16: bf16 copy (or -1), off_lo: bf16 of the remainder v - bf16(v) (or -1).
+// Every load of the thread is issued before the first store (H * K / 512 = 4 or 8 loads in flight per thread).
+template <int K>
+__device__ __forceinline__ void ut_load_weight(char* smem, int off, const float* g, int d, int off_bf16 = -1, int off_lo = -1) {
+    constexpr int N = H * K / UT_THREADS;
+    float v[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        const int i = threadIdx.x + n * UT_THREADS, j = i / K, k = i % K;
+        v[n] = k < d ? __ldcg(g + j * d + k) : 0.0f;
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        const int i = threadIdx.x + n * UT_THREADS, j = i / K, k = i % K;
+        if (off >= 0) *reinterpret_cast<float*>(smem + off + ut_off(j, k, K)) = v[n];
+        const __nv_bfloat16 hi = __float2bfloat16(v[n]);
         if (off_bf16 >= 0) *reinterpret_cast<__nv_bfloat16*>(smem + off_bf16 + ut_off16(j, k, K)) = hi;
-        if (off_lo >= 0) *reinterpret_cast<__nv_bfloat16*>(smem + off_lo + ut_off16(j, k, K)) = __float2bfloat16(v - __bfloat162float(hi));
+        if (off_lo >= 0) *reinterpret_cast<__nv_bfloat16*>(smem + off_lo + ut_off16(j, k, K)) = __float2bfloat16(v[n] - __bfloat162float(hi));
+    }
+}
+
+// Fused mode: the clip+Adam pass writes each updated parameter (flat index k of the parameter vector) straight into the
+// operand / bias slot the next step's MMAs and epilogues read it from -- the same slots the staging at kernel start fills.
+__device__ __forceinline__ void ut_store_param(char* smem, float* small, int k, float v, int d, uint32_t d_magic, int pi_count,
+                                               int vf_count) {
+    if (k >= pi_count + vf_count) { small[UtSmem::LOGSTD + k - pi_count - vf_count] = v; return; }
+    const int t = k >= pi_count ? 1 : 0;     // tower
+    int r = k - (t ? pi_count : 0);
+    if (r < H * d) {
+        const int j = (int)(((uint32_t)r * d_magic) >> 22), kk = r - j * d;     // r / d: exact for r < 2^22 / d
+        *reinterpret_cast<float*>(smem + (t ? UtSmem::W1_VF : UtSmem::W1_PI) + ut_off(j, kk, DP)) = v;
+        return;
+    }
+    r -= H * d;
+    if (r < H) { small[UtSmem::B1 + t * H + r] = v; return; }
+    r -= H;
+    if (r < H * H) {
+        const int j = r / H, kk = r % H;
+        const __nv_bfloat16 hi = __float2bfloat16(v);
+        *reinterpret_cast<__nv_bfloat16*>(smem + (t ? UtSmem::W2B_VF : UtSmem::W2B_PI) + ut_off16(j, kk, H)) = hi;
+#if UT_SPLIT
+        *reinterpret_cast<__nv_bfloat16*>(smem + (t ? UtSmem::W2L_VF : UtSmem::W2L_PI) + ut_off16(j, kk, H)) =
+            __float2bfloat16(v - __bfloat162float(hi));
+#else
+        *reinterpret_cast<float*>(smem + (t ? UtSmem::W2_VF : UtSmem::W2_PI) + ut_off(j, kk, H)) = v;
+#endif
+        return;
+    }
+    r -= H * H;
+    if (r < H) { small[UtSmem::B2 + t * H + r] = v; return; }
+    r -= H;
+    if (t == 0) {
+        if (r < A * H) small[UtSmem::W3_PI + (r % H) * AP + r / H] = v;
+        else small[UtSmem::B3_PI + r - A * H] = v;
+    } else {
+        if (r < H) small[UtSmem::W3_VF + r] = v;
+        else small[UtSmem::B3_VF] = v;
     }
 }
 
@@ -293,6 +341,7 @@ __device__ __forceinline__ void ut_gather_async(char* smem, const float* __restr
 // activation columns [32q, 32q+32) of the stacked pi|vf layer (q 0,1 = policy tower, 2,3 = value tower) in every
 // epilogue, so the per-thread serial work is a quarter of a row and 16 warps hide each other's TMEM/SFU latency.
 // tanh' factors are kept in registers (packed bf16) from the forward epilogues instead of being recomputed.
+template <bool FUSED>
 __global__ void __launch_bounds__(UT_THREADS, 1)
 ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, const float* __restrict__ act,
                    const float* __restrict__ logp_old, const float* __restrict__ adv, const float* __restrict__ ret,
@@ -329,17 +378,29 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
     uint32_t phase = 0;
 
 
-    const int nsteps = fz.steps > 0 ? fz.steps : 1;
-    for (int os = 0; os < nsteps; ++os) {
-    const long long* __restrict__ idx = idx_all + (size_t)os * batch;
-    ut_load_weight(smem, UtSmem::W1_PI, g_pi, DP, d);
-    ut_load_weight(smem, UtSmem::W1_VF, g_vf, DP, d);
-#if UT_SPLIT
-    ut_load_weight(smem, -1, g_pi + H * d + H, H, H, UtSmem::W2B_PI, UtSmem::W2L_PI);
-    ut_load_weight(smem, -1, g_vf + H * d + H, H, H, UtSmem::W2B_VF, UtSmem::W2L_VF);
+#ifdef UT_PROFILE   // experiment builds: phase time stamps (ns) of the last fused step into out_stats[8..]
+    unsigned long long ts[8];
+#define UT_STAMP(i) do { if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[i])); } while (0)
 #else
-    ut_load_weight(smem, UtSmem::W2_PI, g_pi + H * d + H, H, H, UtSmem::W2B_PI);
-    ut_load_weight(smem, UtSmem::W2_VF, g_vf + H * d + H, H, H, UtSmem::W2B_VF);
+#define UT_STAMP(i) do { } while (0)
+#endif
+    const int nsteps = FUSED ? fz.steps : 1;
+    // fused mode with whole tiles per minibatch: the steps' index lists form one contiguous tile stream, so the look-ahead
+    // (observation gather + indices) of a step's last tile simply runs into the next step's first tile
+    const bool stream = FUSED && (batch % UT_ROWS) == 0;
+    long long g_loss = 0, g_gat = 0;
+    for (int os = 0; os < nsteps; ++os) {
+    UT_STAMP(0);
+    const long long* __restrict__ idx = idx_all + (size_t)os * batch;
+    if (!FUSED || os == 0) {     // later fused steps: the Adam pass of the previous step has already written every slot
+    ut_load_weight<DP>(smem, UtSmem::W1_PI, g_pi, d);
+    ut_load_weight<DP>(smem, UtSmem::W1_VF, g_vf, d);
+#if UT_SPLIT
+    ut_load_weight<H>(smem, -1, g_pi + H * d + H, H, UtSmem::W2B_PI, UtSmem::W2L_PI);
+    ut_load_weight<H>(smem, -1, g_vf + H * d + H, H, UtSmem::W2B_VF, UtSmem::W2L_VF);
+#else
+    ut_load_weight<H>(smem, UtSmem::W2_PI, g_pi + H * d + H, H, UtSmem::W2B_PI);
+    ut_load_weight<H>(smem, UtSmem::W2_VF, g_vf + H * d + H, H, UtSmem::W2B_VF);
 #endif
     if (tid < H) {
         small[UtSmem::B1 + tid] = __ldcg(g_pi + H * d + tid);
@@ -357,7 +418,8 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
         small[UtSmem::LOGSTD + tid] = __ldcg(params + pi_count + vf_count + tid);
     }
     if (tid == 0) small[UtSmem::B3_VF] = __ldcg(g_vf + H * d + H + H * H + H + H);
-    if (fz.steps > 0) {
+    }
+    if (FUSED) {
         // minibatch advantage statistics (mean, unbiased std) in double, summed in a fixed order; staged in the H2 buffer
         double sa = 0.0, sq = 0.0;
         for (int i = tid; i < batch; i += UT_THREADS) { const double v = (double)adv[idx[i]]; sa += v; sq += v * v; }
@@ -376,8 +438,9 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
         }
     }
     __syncthreads();
-    const float adv_mean = fz.steps > 0 ? small[UtSmem::FUSED] : adv_stats[0];
-    const float adv_istd = 1.0f / ((fz.steps > 0 ? small[UtSmem::FUSED + 1] : adv_stats[1]) + 1e-8f);
+    UT_STAMP(1);
+    const float adv_mean = FUSED ? small[UtSmem::FUSED] : adv_stats[0];
+    const float adv_istd = 1.0f / ((FUSED ? small[UtSmem::FUSED + 1] : adv_stats[1]) + 1e-8f);
 
     // per-thread running sums over this CTA's samples (warpgroup 0 only): db3_pi[4], db3_vf, dlogstd[4], loss statistics[6]
     float acc_db3[A], acc_db3v = 0.f, acc_dls[A];
@@ -389,15 +452,16 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
     uint32_t first = 0;        // 0 on the first tile of this CTA: weight-gradient accumulators start from zero
     // Row indices run one tile ahead of the rows they address, so that neither the observation gather nor the
     // loss-input gather ever waits for an index: g_loss = this tile's sample, g_gat = next tile's gather row.
-    long long g_loss = 0, g_gat = 0;
-    if ((int)blockIdx.x < ntiles) {
+    const int ntiles_la = stream ? (nsteps - os) * ntiles : ntiles;       // look-ahead bounds (tiles, rows) from this step on
+    const int rows_la = stream ? (nsteps - os) * batch : batch;
+    if ((int)blockIdx.x < ntiles && !(stream && os > 0)) {
         const int sr = blockIdx.x * UT_ROWS + grow;
         const bool lv = sr < batch;
         ut_gather_async(smem, obs, d, lv ? idx[sr] : 0, lv, grow, gpart);
         const int sl = blockIdx.x * UT_ROWS + row;
         g_loss = sl < batch ? idx[sl] : 0;
         const int sn = (blockIdx.x + gridDim.x) * UT_ROWS + grow;
-        g_gat = sn < batch ? idx[sn] : 0;
+        g_gat = sn < rows_la ? idx[sn] : 0;
     }
     uint32_t m5_pending = 0;   // the previous tile's layer-1 weight-gradient MMAs are issued together with this tile's M1
     uint32_t m5_acc = 0;
@@ -674,11 +738,11 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
         {
             const int nt = tile + gridDim.x;
             const int sr = nt * UT_ROWS + grow;
-            ut_gather_async(smem, obs, d, g_gat, nt < ntiles && sr < batch, grow, gpart);
+            ut_gather_async(smem, obs, d, g_gat, nt < ntiles_la && sr < rows_la, grow, gpart);
             const int sl = nt * UT_ROWS + row;
-            g_loss = (nt < ntiles && sl < batch) ? idx[sl] : 0;
+            g_loss = (nt < ntiles_la && sl < rows_la) ? idx[sl] : 0;
             const int sn = (nt + gridDim.x) * UT_ROWS + grow;
-            g_gat = sn < batch ? idx[sn] : 0;
+            g_gat = sn < rows_la ? idx[sn] : 0;
         }
         // ---- M3 + M4 (bf16).  Committed part: the head weight gradient (reads the H2 copy that E4 overwrites) and the
         //      data gradient into layer 1 (E4 consumes it).  The layer-2 weight / bias gradients go out behind the commit:
@@ -718,7 +782,7 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
         first = 1u;
         m5_pending = 1u;
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");      // the last iteration's (empty) look-ahead gather
+    if (!stream) asm volatile("cp.async.wait_group 0;" ::: "memory");      // the last iteration's (empty) look-ahead gather
     if (first != 0u) {
         UT_FENCE_SYNC();
         if (tid == 0) { UT_ISSUE_M5(); ut_commit(bar); }
@@ -726,6 +790,7 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
 #undef UT_ISSUE_M5
+    UT_STAMP(2);
 
     // ---- read the accumulated weight gradients out of TMEM into this CTA's partial
     //      (TMEM lane = output neuron: lanes 0-63 policy tower, 64-127 value tower; warpgroup q takes a column slice)
@@ -738,16 +803,34 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
         {   // dW2: rows 0-63 of Da, rows 64-127 of Db; 16 columns per warpgroup
             float v[16];
             ut_ld16(tmem + (is_pi ? UT_DA : UT_DB) + lane_base + q * 16, v);
+            float* dst = outp + o_w2 + j * H + q * 16;
+            // a warp-wide scalar store touches 32 sectors per instruction: 16-byte stores where the row allows
+            if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
 #pragma unroll
-            for (int c = 0; c < 16; ++c) outp[o_w2 + j * H + q * 16 + c] = v[c] * cfg.inv_grad_scale;
+                for (int c = 0; c < 16; c += 4)
+                    *reinterpret_cast<float4*>(dst + c) = make_float4(v[c] * cfg.inv_grad_scale, v[c + 1] * cfg.inv_grad_scale,
+                                                                      v[c + 2] * cfg.inv_grad_scale, v[c + 3] * cfg.inv_grad_scale);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) dst[c] = v[c] * cfg.inv_grad_scale;
+            }
         }
         if (q < 2) {   // dW1: DP/2 columns each
 #pragma unroll
             for (int c0 = q * (DP / 2); c0 < (q + 1) * (DP / 2); c0 += 16) {
                 float v[16];
                 ut_ld16(tmem + UT_DW1 + lane_base + c0, v);
+                float* dst = outp + o_w1 + j * d + c0;
+                if ((d & 3) == 0 && (reinterpret_cast<uintptr_t>(outp + o_w1) & 15u) == 0) {
 #pragma unroll
-                for (int c = 0; c < 16; ++c) if (c0 + c < d) outp[o_w1 + j * d + c0 + c] = v[c] * cfg.inv_grad_scale;
+                    for (int c = 0; c < 16; c += 4)
+                        if (c0 + c < d)
+                            *reinterpret_cast<float4*>(dst + c) = make_float4(v[c] * cfg.inv_grad_scale, v[c + 1] * cfg.inv_grad_scale,
+                                                                              v[c + 2] * cfg.inv_grad_scale, v[c + 3] * cfg.inv_grad_scale);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 16; ++c) if (c0 + c < d) dst[c] = v[c] * cfg.inv_grad_scale;
+                }
             }
         } else if (q == 2) {   // head weights
             float v3[16];
@@ -769,9 +852,9 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
         // this CTA had no tile: its partial is all zeros
         for (int k = tid; k < P; k += blockDim.x) outp[k] = 0.0f;
     }
-    // small sums (held by warpgroup 0): warp shuffle, one slot per (warp, sum) in the dead layer-1 operand buffer, then a
+    // small sums (held by warpgroup 0): warp shuffle, one slot per (warp, sum) in the dead H2 buffer, then a
     // fixed-order sum over the four warps -- no floating-point atomics, the update is bit-reproducible
-    float* wred = reinterpret_cast<float*>(smem + UtSmem::XB);
+    float* wred = reinterpret_cast<float*>(smem + UtSmem::H2B);     // dead after the last M5; XB may hold the next step's rows
     if (q == 0) {
         // slots: db3_pi[A], db3_vf, dlog_std[A], then the six loss statistics
         float red[2 * A + 7];
@@ -803,12 +886,21 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
         if (tid < 6) v = small[UtSmem::RED + 2 * A + 1 + tid];
         out_stats[(size_t)blockIdx.x * 8 + tid] = v;
     }
-    if (fz.steps > 0) {
+    if (FUSED) {
         // ---- clip_grad_norm_ + Adam on the gradient this CTA has just written (the arithmetic of ppo_adam_kernel)
         __threadfence();
         __syncthreads();
+        UT_STAMP(3);
+        // squared norm over this thread's parameters (k = tid + 512 i); every load issued before the first use
+        constexpr int NP = 16384 / UT_THREADS;
         float ss = 0.0f;
-        for (int k = tid; k < P; k += UT_THREADS) { const float g = __ldcg(outp + k); ss = fmaf(g, g, ss); }
+        {
+            float g[NP];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) { const int k = tid + i * UT_THREADS; g[i] = k < P ? __ldcg(outp + k) : 0.0f; }
+#pragma unroll
+            for (int i = 0; i < NP; ++i) ss = fmaf(g[i], g[i], ss);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         if ((tid & 31) == 0) wred[warp] = ss;
@@ -824,18 +916,42 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
             if (fz.norm_out != nullptr) fz.norm_out[0] = norm;
         }
         __syncthreads();
+        UT_STAMP(4);
         const float coef = small[UtSmem::FUSED + 2];
         const float tf = (float)__float_as_int(small[UtSmem::FUSED + 3]);
         const float inv_bc1 = 1.0f / (1.0f - powf(fz.beta1, tf)), inv_bc2 = 1.0f / (1.0f - powf(fz.beta2, tf));
-        for (int k = tid; k < P; k += UT_THREADS) {
-            const float gg = __ldcg(outp + k) * coef;
-            const float m1 = fz.beta1 * fz.m[k] + (1.0f - fz.beta1) * gg;
-            const float v1 = fz.beta2 * fz.v[k] + (1.0f - fz.beta2) * gg * gg;
-            fz.m[k] = m1; fz.v[k] = v1;
-            fz.params[k] = __ldcg(fz.params + k) - fz.lr * (m1 * inv_bc1) / (sqrtf(v1 * inv_bc2) + fz.eps);
+        const uint32_t d_magic = ((1u << 22) + (uint32_t)d - 1u) / (uint32_t)d;
+#pragma unroll 1
+        for (int i0 = 0; i0 < NP; i0 += 8) {          // eight parameters at a time: 32 loads in flight, then arithmetic
+            if (i0 * UT_THREADS >= P) break;
+            float gk[8], mk[8], vk[8], pk[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = tid + (i0 + i) * UT_THREADS;
+                const bool ok = k < P;
+                gk[i] = ok ? __ldcg(outp + k) : 0.0f;
+                mk[i] = ok ? fz.m[k] : 0.0f; vk[i] = ok ? fz.v[k] : 0.0f; pk[i] = ok ? __ldcg(fz.params + k) : 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = tid + (i0 + i) * UT_THREADS;
+                if (k < P) {
+                    const float gg = gk[i] * coef;
+                    const float m1 = fz.beta1 * mk[i] + (1.0f - fz.beta1) * gg;
+                    const float v1 = fz.beta2 * vk[i] + (1.0f - fz.beta2) * gg * gg;
+                    fz.m[k] = m1; fz.v[k] = v1;
+                    const float pn = pk[i] - fz.lr * (m1 * inv_bc1) / (sqrtf(v1 * inv_bc2) + fz.eps);
+                    fz.params[k] = pn;
+                    ut_store_param(smem, small, k, pn, d, d_magic, pi_count, vf_count);
+                }
+            }
         }
         __threadfence();
         __syncthreads();       // the next step stages the updated parameters
+        UT_STAMP(5);
+#ifdef UT_PROFILE
+        if (tid == 0) for (int i = 0; i < 5; ++i) out_stats[8 + i] = (float)(ts[i + 1] - ts[i]);
+#endif
     }
     }   // optimizer steps
     if (warp == 0)
@@ -1003,7 +1119,7 @@ void ppok_launch_adv_stats(const float* adv, const long long* idx, int batch, do
 void ppok_launch_grad_reduce(const float* partial, const float* stats_partial, int grid, int P, float* grad, float* stats, cudaStream_t st);
 
 namespace PPO_UT_NS {
-static bool g_ut_attr_set = false;
+static bool g_ut_attr_set = false, g_ut_fused_attr_set = false;
 
 cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, const float* act, const float* logp_old,
                                 const float* adv, const float* ret, const long long* idx, int batch, float clip_range,
@@ -1011,7 +1127,7 @@ cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, co
                                 float* stats_partial, float* grad, float* stats, cudaStream_t st) {
     if (d > DP) return cudaErrorInvalidValue;
     if (!g_ut_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(ppo_grad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL);
         if (e != cudaSuccess) return e;
         g_ut_attr_set = true;
     }
@@ -1026,7 +1142,7 @@ cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, co
     while (gs < (float)batch && gs < 1048576.0f) gs *= 2.0f;
     PpoLossCfg cfg{clip_range, ent_coef, vf_coef, 1.0f / (float)batch, gs, 1.0f / gs};
     PpoFusedCfg fz{};
-    ppo_grad_tc_kernel<<<grid, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, adv_stats, cfg,
+    ppo_grad_tc_kernel<false><<<grid, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, adv_stats, cfg,
                                                              partial, stats_partial, P, fz);
     ppok_launch_grad_reduce(partial, stats_partial, grid, P, grad, stats, st);
     return cudaGetLastError();
@@ -1038,10 +1154,10 @@ cudaError_t ppok_minibatch_steps(float* params, int d, const float* obs, const f
                                  float vf_coef, float* m, float* v, float lr, float beta1, float beta2, float eps, float max_norm,
                                  int* step_ctr, float* norm_out, float* grad, float* stats, cudaStream_t st) {
     if (d > DP || steps <= 0) return cudaErrorInvalidValue;
-    if (!g_ut_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ppo_grad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL);
+    if (!g_ut_fused_attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(ppo_grad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL);
         if (e != cudaSuccess) return e;
-        g_ut_attr_set = true;
+        g_ut_fused_attr_set = true;
     }
     const int H_ = PPO_H, A_ = A;
     const int P = (H_ * d + H_ + H_ * H_ + H_ + A_ * H_ + A_) + (H_ * d + H_ + H_ * H_ + H_ + H_ + 1) + A_;
@@ -1049,7 +1165,7 @@ cudaError_t ppok_minibatch_steps(float* params, int d, const float* obs, const f
     while (gs < (float)batch && gs < 1048576.0f) gs *= 2.0f;
     PpoLossCfg cfg{clip_range, ent_coef, vf_coef, 1.0f / (float)batch, gs, 1.0f / gs};
     PpoFusedCfg fz{steps, lr, beta1, beta2, eps, max_norm, params, m, v, step_ctr, norm_out};
-    ppo_grad_tc_kernel<<<1, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, nullptr, cfg, grad,
+    ppo_grad_tc_kernel<true><<<1, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, nullptr, cfg, grad,
                                                           stats, P, fz);
     return cudaGetLastError();
 }
