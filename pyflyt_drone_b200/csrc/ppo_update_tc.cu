@@ -380,8 +380,11 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
 
 #ifdef UT_PROFILE   // experiment builds: phase time stamps (ns) of the last fused step into out_stats[8..]
     unsigned long long ts[8];
+    unsigned long long tt[10];     // ... and of its last tile into out_stats[16..]
 #define UT_STAMP(i) do { if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts[i])); } while (0)
+#define UT_TSTAMP(i) do { if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt[i])); } while (0)
 #else
+#define UT_TSTAMP(i) do { } while (0)
 #define UT_STAMP(i) do { } while (0)
 #endif
     const int nsteps = FUSED ? fz.steps : 1;
@@ -475,10 +478,12 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
     } while (0)
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        UT_TSTAMP(0);
         // ---- S0: the gathered (already normalised) observations are the fp32 A operand of layer 1: wait for this
         //      thread's async copies (issued one tile ago), then make them visible block-wide
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         UT_FENCE_SYNC();       // also publishes the previous tile's dZ1
+        UT_TSTAMP(1);
         // ---- M1: forward layer 1, both towers in one N = 128 GEMM (W1_pi and W1_vf are adjacent and form one
         //      [128 x 32] K-major B operand); then, behind the commit, M5 of the previous tile: it runs under E1 and is
         //      covered by M2's commit, before anything it reads (dZ1 = the H2 buffer, X bf16, dOut) is rewritten
@@ -490,6 +495,7 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
         }
         m5_acc = m5_pending;
         ut_wait(bar, phase); phase ^= 1u;
+        UT_TSTAMP(2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // bf16 copy of X (B operand of the layer-1 weight gradient): packed now, stored once the previous tile's M5,
         // which still reads the old copy, has drained (after the M2 wait)
@@ -556,6 +562,7 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
             }
         }
         UT_FENCE_SYNC();
+        UT_TSTAMP(3);
         // ---- M2: forward layer 2 (A = the tower's 64-column sub-block of H1C)
         if (tid == 0) {
 #if UT_SPLIT
@@ -577,6 +584,7 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
             ut_commit(bar);
         }
         ut_wait(bar, phase); phase ^= 1u;
+        UT_TSTAMP(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int slab = 0; slab < DP / 32; ++slab)
@@ -635,6 +643,7 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
             }
         }
         __syncthreads();
+        UT_TSTAMP(5);
         if (q != 0) {
             const char* lin = smem + UtSmem::XB + UtSmem::LIN + row * UtSmem::LIN_ROW;
 #pragma unroll
@@ -733,6 +742,7 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
             }
         }
         UT_FENCE_SYNC();
+        UT_TSTAMP(6);
         // XB (layer-1 operand, then head partials) is free from here on: start the next tile's observation gather, and
         // fetch the indices for the iteration after it
         {
@@ -761,6 +771,7 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
             ut_gemm<true, UT_ROWS / 16>(tmem + UT_DB2, sb + UtSmem::DZ2, 2 * H * 16, 128, 2 * 2 * H * 16, sb + UtSmem::DO, 16 * 16, 128, 2 * 16 * 16, ut_idesc(1, 16, 1, 1), first);
         }
         ut_wait(bar, phase); phase ^= 1u;
+        UT_TSTAMP(7);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         // ---- E4: dZ1 = dH1 * tanh'(z1) (bf16, already scaled) over the H2 copy (M3 has consumed it); its MMAs (M5)
         //      go out behind the next tile's M1
@@ -781,6 +792,7 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
         }
         first = 1u;
         m5_pending = 1u;
+        UT_TSTAMP(8);
     }
     if (!stream) asm volatile("cp.async.wait_group 0;" ::: "memory");      // the last iteration's (empty) look-ahead gather
     if (first != 0u) {
@@ -951,6 +963,7 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
         UT_STAMP(5);
 #ifdef UT_PROFILE
         if (tid == 0) for (int i = 0; i < 5; ++i) out_stats[8 + i] = (float)(ts[i + 1] - ts[i]);
+        if (tid == 0) for (int i = 0; i < 8; ++i) out_stats[16 + i] = (float)(tt[i + 1] - tt[i]);
 #endif
     }
     }   // optimizer steps

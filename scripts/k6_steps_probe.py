@@ -20,4 +20,5 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); run(256); e1.record(); torch.cuda.synchronize()
 print(f"256 steps: {e0.elapsed_time(e1) * 1000 / 256:.1f} us per step")
 print("last step phases (ns): stage+advstats, tiles, readout+sums, norm, adam:", [int(x) for x in stats[8:13].tolist()])
+print("last tile (ns): gather wait+sync, M1, E1, M2, E2, loss+E3, M3/M4, E4:", [int(x) for x in stats[16:24].tolist()])
 env.close()
