@@ -533,6 +533,28 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     d2h = N * venv.obs_dim * 4 + N * 4 + N + N          # obs, reward, flag byte, targets-reached byte
     e2e_launches = N_REGIONS * e2e_steps * (2 if N >= 16384 else 1)
     venv.close()
+    # what bounds e2e: the step's results cross PCIe (the kernel writes them into pinned host memory as it runs); the link's
+    # device->host rate is measured here with plain pinned copies of 64 MiB (copy engine, nothing else on the link)
+    pcie = None
+    try:
+        big_d = torch.empty(64 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        big_h = torch.empty(64 << 20, dtype=torch.uint8, pin_memory=True)
+        for _ in range(3):
+            big_h.copy_(big_d, non_blocking=True)
+        p0, p1 = ev(), ev()
+        p0.record()
+        for _ in range(10):
+            big_h.copy_(big_d, non_blocking=True)
+        p1.record(); torch.cuda.synchronize()
+        peak = 10 * (64 << 20) / (p0.elapsed_time(p1) * 1e-3) / 1e9
+        ach = d2h / e2e_step_s / 1e9
+        pcie = {"bound": "pcie_d2h", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "note": "achieved = d2h_bytes_per_step / step time of this rank's GPU; peak = 64 MiB pinned device->host copies "
+                        "measured in this run; a step is synchronous (the next actions depend on its observations), so host "
+                        "latency per step is inside"}
+        del big_d, big_h
+    except Exception as e:            # never lose the line over the side measurement
+        pcie = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- PPO SPS: every rank takes part (gradient all-reduce inside the timed region) ----
     ppo = None
@@ -586,7 +608,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                 f"CUDA graph of {replicas} launches chained by programmatic dependent launch edges (each launch steps "
                                 f"another env batch; the next one places its blocks while this one drains; FWSIM_PDL=0 = plain edges)"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "us_per_step": e2e_step_s * 1e6, "steps_per_region": e2e_steps, "regions": N_REGIONS},
+                    "us_per_step": e2e_step_s * 1e6, "steps_per_region": e2e_steps, "regions": N_REGIONS, "roofline": pcie},
             "gpu_launches": int(launches + e2e_launches),
             "clocks": clocks,
             "roofline": roof,
