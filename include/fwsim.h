@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FW_ABI_VERSION 10
+#define FW_ABI_VERSION 11
 
 #define FW_NSURF 5            /* cmd order: left aileron, right aileron, h-tail, v-tail, main wing */
 #define FW_MAX_TARGETS 16
@@ -203,6 +203,16 @@ int fw_targets_reached(fw_handle h, uint8_t* dst_dev, void* stream);
  * (prepared ahead of time by dedicated blocks of the previous step launch), out[1] inline in the
  * step kernel (no valid spare: e.g. after fw_set_state, or FWSIM_SPARE=0).  Both give the same state.  Synchronous. */
 int fw_spare_stats(fw_handle h, int64_t out[2]);
+
+/* Debug / evaluation frame of ONE env: FixedwingBaseEnv.render() -> pybullet getCameraImage
+ * [REF envs/fixedwing_envs/fixedwing_base_env.py:350-369; eval/eval_objlock.py:120-162 keeps seg and depth too].
+ * Device buffers, any may be NULL: rgba uint8 [height,width,4]; seg int32 [height,width] (-1 sky, 0 ground, 1 duck,
+ * 2+k obstacle k, 64+t waypoint t); depth float [height,width] = OpenGL depth-buffer values (1.0 = far plane).  The camera
+ * is the task's own (FwConfig cam_*; vertical field of view 90 degrees), the scene the analytic one the vision features
+ * are computed from (ground plane, obstacle cylinders, duck sphere, a goal_reach sphere per remaining waypoint) -- not
+ * pybullet's meshes.  Reads the state as of the last enqueued step on `stream`. */
+int fw_render(fw_handle h, int32_t env, int32_t width, int32_t height, uint8_t* rgba_dev, int32_t* seg_dev, float* depth_dev,
+              void* stream);
 
 /* number of envs force-reset because their state went non-finite (FW_FLAG_FAULT) since fw_create (synchronous) */
 int fw_fault_count(fw_handle h, int64_t* nonfinite_resets);

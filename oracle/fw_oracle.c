@@ -589,6 +589,100 @@ static void capture_frame(const fwo_config* c, fwo_env* e) {
     e->cam_valid = 1;
 }
 
+/* Debug / evaluation frame of ONE env (FixedwingBaseEnv.render -> getCameraImage,
+ * /root/reference/envs/fixedwing_envs/fixedwing_base_env.py:350-369; eval/eval_objlock.py:120-162 also keeps the
+ * segmentation mask and the depth buffer): the scene of capture_frame() through the same pin-hole camera (vertical field of
+ * view 90 degrees, horizontal scaled by W / H), every pixel ray-cast against the ground plane, the obstacle cylinders, the
+ * duck sphere (camera tasks) and one sphere of radius goal_reach per waypoint not reached yet.
+ *   seg:   -1 sky, 0 ground, 1 duck, 2 + k obstacle k, 64 + t waypoint t (index in the episode's original list)
+ *   depth: OpenGL depth-buffer value of the hit (1.0 = far plane / sky), what pybullet's getCameraImage returns
+ *   rgba:  flat colour per class, Lambert-shaded with a fixed light; alpha 255
+ * PyBullet's rasteriser and meshes are not restated (nothing of the hot path reads these pixels); the frame is consistent
+ * with the features the policy sees: its middle row at W = H = cam_res is the row capture_frame() integrates. */
+void fwo_render(const fwo_config* c, const fwo_env* e, int W, int H, uint8_t* rgba, int32_t* seg, double* depth) {
+    double R[9];
+    fwo_quat_to_mat(e->quat, R);
+    double off_w[3], cam[3], f[3], up[3] = {R[2], R[5], R[8]}, r[3], u[3];
+    mat_vec(R, c->cam_offset, off_w);
+    for (int k = 0; k < 3; ++k) cam[k] = e->pos[k] + off_w[k];
+    if (c->cam_mode == 0) {
+        double ol = sqrt(dot3(off_w, off_w));
+        for (int k = 0; k < 3; ++k) f[k] = -off_w[k] / ol;
+    } else {
+        double t = c->cam_tilt_deg * M_PI / 180.0;
+        double fb[3] = {cos(t), 0.0, -sin(t)}, ub[3] = {sin(t), 0.0, cos(t)};
+        mat_vec(R, fb, f);
+        mat_vec(R, ub, up);
+    }
+    cross3(f, up, r);
+    double rl = sqrt(dot3(r, r));
+    for (int k = 0; k < 3; ++k) r[k] /= rl;
+    cross3(r, f, u);
+    const int cam_task = c->task == FWO_TASK_OBJLOCK || c->task == FWO_TASK_DUCK;
+    const int wp_task = c->task == FWO_TASK_WAYPOINTS || c->task == FWO_TASK_OBJLOCK;
+    const double Rd = c->duck_radius;
+    const double ctr[3] = {e->duck_pos[0], e->duck_pos[1], e->duck_pos[2] + Rd};
+    const double L[3] = {0.30151134457776363, 0.20100756305184242, 0.9320390859672263};   /* (0.3, 0.2, 0.9273..) normalised */
+    const double aspect = (double)W / (double)H;
+    for (int y = 0; y < H; ++y) {
+        const double yn = 2.0 * (y + 0.5) / H - 1.0;
+        for (int x = 0; x < W; ++x) {
+            const double xn = (2.0 * (x + 0.5) / W - 1.0) * aspect;
+            double d[3];
+            for (int k = 0; k < 3; ++k) d[k] = f[k] + xn * r[k] - yn * u[k];
+            double best = INFINITY;
+            int id = -1;
+            if (d[2] < -1e-12) { double t = -cam[2] / d[2]; if (t > 0) { best = t; id = 0; } }
+            for (int o = 0; o < e->n_obst; ++o) {
+                double t = ray_cylinder(cam, d, e->obst[o], c->obst_radius);
+                if (t < best) { best = t; id = 2 + o; }
+            }
+            if (cam_task) {
+                double t = ray_sphere(cam, d, ctr, Rd);
+                if (t < best) { best = t; id = 1; }
+            }
+            if (wp_task)
+                for (int k = 0; k < e->n_remaining; ++k) {
+                    double t = ray_sphere(cam, d, e->targets[k], c->goal_reach);
+                    if (t < best) { best = t; id = 64 + e->target_idx + k; }
+                }
+            /* colour */
+            double base[3] = {135, 206, 235}, shade = 1.0;
+            if (id >= 0) {
+                double hit[3] = {cam[0] + best * d[0], cam[1] + best * d[1], cam[2] + best * d[2]}, n[3] = {0, 0, 1};
+                if (id == 0) {
+                    /* 10 m checker inside the far plane, one tone beyond it */
+                    int chk = ((long long)floor(hit[0] / 10.0) + (long long)floor(hit[1] / 10.0)) & 1;
+                    int nearg = best <= c->cam_far;
+                    base[0] = nearg ? (chk ? 96 : 80) : 88; base[1] = nearg ? (chk ? 160 : 140) : 150; base[2] = nearg ? (chk ? 96 : 80) : 88;
+                } else if (id == 1) {
+                    base[0] = 255; base[1] = 221; base[2] = 0;
+                    for (int k = 0; k < 3; ++k) n[k] = (hit[k] - ctr[k]) / Rd;
+                } else if (id < 64) {
+                    const double* cy = e->obst[id - 2];
+                    base[0] = 170; base[1] = 90; base[2] = 70;
+                    double dx = hit[0] - cy[0], dy = hit[1] - cy[1], rr = c->obst_radius;
+                    if (dx * dx + dy * dy >= rr * rr * (1.0 - 1e-3)) { n[0] = dx / rr; n[1] = dy / rr; n[2] = 0.0; }
+                } else {
+                    const double* tg = e->targets[id - 64 - e->target_idx];
+                    int cur = id - 64 == e->target_idx;
+                    base[0] = 60; base[1] = cur ? 220 : 120; base[2] = cur ? 60 : 255;
+                    for (int k = 0; k < 3; ++k) n[k] = (hit[k] - tg[k]) / c->goal_reach;
+                }
+                double nl = dot3(n, L);
+                shade = 0.55 + 0.45 * (nl > 0.0 ? nl : 0.0);
+            }
+            const size_t px = (size_t)y * W + x;
+            if (rgba) {
+                for (int k = 0; k < 3; ++k) rgba[4 * px + k] = (uint8_t)(base[k] * shade + 0.5);
+                rgba[4 * px + 3] = 255;
+            }
+            if (seg) seg[px] = id;
+            if (depth) depth[px] = isfinite(best) ? depth_buf(c, best) : 1.0;
+        }
+    }
+}
+
 /* _compute_vision_features + _build_vision_vector */
 static void vision_features(const fwo_config* c, fwo_env* e) {
     (void)c;

@@ -202,6 +202,9 @@ void fwo_reset(const fwo_config* c, fwo_env* e, uint64_t seed, uint32_t env_id, 
 int fwo_act_dim(const fwo_config* c);   /* 4, or 6 for the low-level task */
 void fwo_step(const fwo_config* c, fwo_env* e, uint64_t seed, const double* action,
               double* obs, double* reward, int32_t* flags);
+/* debug / evaluation frame of one env (FixedwingBaseEnv.render): rgba [H,W,4], seg [H,W], depth-buffer values [H,W]; any
+ * output may be NULL.  See fw_oracle.c for the scene and the class ids. */
+void fwo_render(const fwo_config* c, const fwo_env* e, int W, int H, uint8_t* rgba, int32_t* seg, double* depth);
 /* SubprocVecEnv worker semantics: step, and on done stash terminal obs then reset */
 void fwo_vec_step(const fwo_config* c, fwo_env* envs, int n, uint64_t seed, const double* actions,
                   double* obs, double* rewards, int32_t* flags, double* term_obs, int nthreads);

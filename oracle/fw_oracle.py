@@ -120,6 +120,8 @@ def lib() -> C.CDLL:
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.fwo_rollout_random.restype = C.c_long
         L.fwo_rollout_random.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_int, C.c_uint64, C.c_int, C.c_int]
+        L.fwo_render.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fwo_render.restype = None
         L.fwo_compute_obs.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_void_p, C.c_int]
         L.fwo_refresh_surface_vel.argtypes = [C.POINTER(OConfig), C.POINTER(OEnv), C.c_int]
         L.fwo_quat_to_euler.argtypes = [C.POINTER(_D), C.POINTER(_D)]
@@ -193,6 +195,13 @@ class OracleVecEnv:
 
     def rollout_random(self, steps: int) -> int:
         return int(self.L.fwo_rollout_random(C.byref(self.cfg), self.envs, self.n, self.seed, int(steps), self.nthreads))
+
+    def render(self, env_index: int = 0, width: int | None = None, height: int | None = None) -> dict:
+        """Debug frame of one env (fwo_render): rgba uint8 [H,W,4], seg int32 [H,W], depth-buffer values float64 [H,W]."""
+        W = int(width or self.cfg.cam_res); H = int(height or self.cfg.cam_res)
+        rgba = np.zeros((H, W, 4), np.uint8); seg = np.zeros((H, W), np.int32); depth = np.zeros((H, W), np.float64)
+        self.L.fwo_render(C.byref(self.cfg), C.byref(self.envs[int(env_index)]), W, H, _ptr(rgba), _ptr(seg), _ptr(depth))
+        return dict(rgba=rgba, seg=seg, depth=depth)
 
     # ---- state exchange with the device path (same field meaning as FwStateHost) ----
     def get_state(self) -> dict:

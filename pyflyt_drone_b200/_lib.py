@@ -47,6 +47,7 @@ SYMBOLS = [
     ("fw_observe_host", C.c_int, [_P, _P]),
     ("fw_host_info_buffer", C.c_int, [_P, C.POINTER(_P)]),
     ("fw_targets_reached", C.c_int, [_P, _P, _P]),
+    ("fw_render", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     ("fw_fault_count", C.c_int, [_P, C.POINTER(C.c_int64)]),
     ("fw_spare_stats", C.c_int, [_P, C.POINTER(C.c_int64)]),
     ("fw_host_buffers", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
@@ -58,7 +59,7 @@ SYMBOLS = [
 ]
 
 
-ABI_VERSION = 10        # include/fwsim.h FW_ABI_VERSION this binding was written against
+ABI_VERSION = 11        # include/fwsim.h FW_ABI_VERSION this binding was written against
 
 
 def load() -> C.CDLL:

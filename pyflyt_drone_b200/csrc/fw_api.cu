@@ -732,6 +732,18 @@ extern "C" int fw_targets_reached(fw_handle h, uint8_t* dst_dev, void* stream) {
     return FW_OK;
 }
 
+extern "C" int fw_render(fw_handle h, int32_t env, int32_t width, int32_t height, uint8_t* rgba_dev, int32_t* seg_dev,
+                         float* depth_dev, void* stream) {
+    if (!h) return fail(FW_EINVAL, "null handle");
+    if (env < 0 || env >= h->n) return fail(FW_EINVAL, "env index %d out of range [0,%d)", env, h->n);
+    if (width <= 0 || height <= 0 || width > 4096 || height > 4096) return fail(FW_EINVAL, "frame size must be in [1,4096]");
+    if (!rgba_dev && !seg_dev && !depth_dev) return fail(FW_EINVAL, "no output buffer");
+    CU(cudaSetDevice(h->device));
+    CU(fwk_render(h->dev, h->pl, env, width, height, rgba_dev, seg_dev, depth_dev, (cudaStream_t)stream));
+    h->launches++;
+    return FW_OK;
+}
+
 extern "C" int fw_fault_count(fw_handle h, int64_t* nonfinite_resets) {
     if (!h || !nonfinite_resets) return fail(FW_EINVAL, "null argument");
     CU(cudaSetDevice(h->device));

@@ -19,3 +19,6 @@ cudaError_t fwk_graph_add_refill(cudaGraph_t g, cudaGraphNode_t* deps, int ndeps
                                  const int2* list, int* count, int* blocks_done, int cap, cudaGraphNode_t* out);
 cudaError_t fwk_launch_warm(const FwDev& p, const FwPlanes& pl, float* out, cudaStream_t st);
 cudaError_t fwk_fma_peak(int sm_count, int iters, float* scratch, double* flops_per_launch, cudaStream_t st);
+// debug frame of one env (fw_render.cu): rgba [H,W,4], seg [H,W], depth [H,W] device buffers, any may be null
+cudaError_t fwk_render(const FwDev& p, const FwPlanes& pl, int env, int W, int H, uint8_t* rgba, int32_t* seg, float* depth,
+                       cudaStream_t st);

@@ -81,7 +81,7 @@ class _AviaryView:
 class FixedwingWaypointsEnv:
     """``PyFlyt/Fixedwing-Waypoints-v3`` (task="waypoints") or ``FixedwingWaypointObjLockEnv`` (task="objlock")."""
 
-    metadata = {"render_modes": [], "render_fps": 30}
+    metadata = {"render_modes": ["rgb_array"], "render_fps": 30}
 
     def __init__(self, sparse_reward: bool = False, num_targets: int = 4, goal_reach_distance: float = 2.0,
                  flight_mode: int = 0, flight_dome_size: float = 100.0, max_duration_seconds: float = 120.0,
@@ -95,8 +95,10 @@ class FixedwingWaypointsEnv:
             raise ValueError(f"angle_representation must be either `euler` or `quaternion`, not {angle_representation}")
         if flight_mode != 0:
             raise ValueError("only flight_mode 0 (roll, pitch, yaw, thrust) is implemented")
-        if render_mode is not None:
-            raise ValueError("rendering is out of scope for the batched simulator")
+        if render_mode not in (None, "rgb_array"):
+            raise ValueError("only render_mode None or 'rgb_array' is available (no window to draw into)")
+        self.render_mode = render_mode
+        self.render_resolution = (480, 480)                          # fixedwing_base_env.py:96 default
         preset = {"waypoints": "waypoints_v3", "objlock": "waypoint_objlock"}[task]
         over = dict(sparse_reward=int(bool(sparse_reward)), num_targets=int(num_targets), goal_reach=float(goal_reach_distance),
                     dome=float(flight_dome_size), spawn_size=float(flight_dome_size),
@@ -252,8 +254,12 @@ class FixedwingWaypointsEnv:
     def close(self) -> None:
         self._vec.close()
 
-    def render(self):
-        raise ValueError("rendering is out of scope for the batched simulator")
+    def render(self) -> np.ndarray:
+        """FixedwingBaseEnv.render (fixedwing_base_env.py:350-369): RGBA uint8 [H,W,4] at render_resolution, through the
+        aircraft's camera; the analytic scene (vec_env.render_layers), not pybullet's meshes."""
+        if self.render_mode is None:
+            raise ValueError("Please set `render_mode='human'` or `render_mode='rgb_array'` in init to use this function.")
+        return self._vec.render(env_index=0, width=self.render_resolution[1], height=self.render_resolution[0])
 
 
 class FixedwingLowLevelEnv:
@@ -309,7 +315,8 @@ class FixedwingObjLockEnv:
     observation {attitude, target_vector(3), duck_vision(9*history [+4])}, ``info`` keys ``duck_strike`` /
     ``env_complete`` / ``is_success`` / ``collision`` / ``out_of_bounds``.  The camera is the analytic stand-in
     (DESIGN.md): ``camera_FOV_degrees`` must be 90, ``duck_urdf_path`` / ``use_egl`` are accepted and ignored,
-    ``render_mode="rgb_array"`` only selects the capture resolution the way the reference does (:213-218)."""
+    ``render_mode="rgb_array"`` selects the capture resolution the way the reference does (:213-218) and enables
+    ``render()`` (frames of the analytic scene, see FixedwingVecEnv.render_layers)."""
 
     metadata = {"render_modes": ["rgb_array"], "render_fps": 30}
 
@@ -339,7 +346,8 @@ class FixedwingObjLockEnv:
         if flight_mode != 0:
             raise ValueError("only flight_mode 0 (roll, pitch, yaw, thrust) is implemented")
         if render_mode not in (None, "rgb_array"):
-            raise ValueError("only render_mode None or 'rgb_array' (capture resolution only) is accepted")
+            raise ValueError("only render_mode None or 'rgb_array' is available (no window to draw into)")
+        self.render_mode = render_mode
         if camera_FOV_degrees is not None and int(camera_FOV_degrees) != 90:
             raise ValueError("the analytic camera is built for the reference's 90 degree field of view")
         if camera_profile == "cockpit_fpv":                          # fixedwing_objlock_env.py:184-192,226-229
@@ -441,8 +449,11 @@ class FixedwingObjLockEnv:
     def close(self) -> None:
         self._vec.close()
 
-    def render(self):
-        raise ValueError("rendered frames are out of scope for the batched simulator")
+    def render(self) -> np.ndarray:
+        """RGBA uint8 [H,W,4] through the task camera at the capture resolution (see FixedwingWaypointsEnv.render)."""
+        if self.render_mode is None:
+            raise ValueError("Please set `render_mode='human'` or `render_mode='rgb_array'` in init to use this function.")
+        return self._vec.render(env_index=0)
 
 
 class FlattenObjLockEnv:

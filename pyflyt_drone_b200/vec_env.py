@@ -319,6 +319,33 @@ class FixedwingVecEnv(VecEnv):
         _lib.check(self.lib.fw_targets_reached(self._h, C.c_void_p(t["tidx"].data_ptr()), C.c_void_p(self._stream())))
         return t["tidx"]
 
+    def render_layers(self, env_index: int = 0, width: int | None = None, height: int | None = None) -> dict:
+        """Debug / evaluation frame of one env (``fw_render``): ``rgba`` uint8 [H,W,4], ``seg`` int32 [H,W] (-1 sky, 0 ground,
+        1 duck, 2+k obstacle k, 64+t waypoint t) and ``depth`` float32 [H,W] (OpenGL depth-buffer values, what pybullet's
+        ``getCameraImage`` returns) as NumPy arrays; default size = the task camera's resolution.  The scene is the analytic
+        one the vision features are computed from, seen through the task's own camera."""
+        import torch
+        W = int(width or self.cfg.cam_res); H = int(height or self.cfg.cam_res)
+        dev = torch.device("cuda", self.device_index)
+        rgba = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
+        seg = torch.empty((H, W), dtype=torch.int32, device=dev)
+        depth = torch.empty((H, W), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(self.lib.fw_render(self._h, int(env_index), W, H, C.c_void_p(rgba.data_ptr()), C.c_void_p(seg.data_ptr()),
+                                          C.c_void_p(depth.data_ptr()), C.c_void_p(st)))
+        return dict(rgba=rgba.cpu().numpy(), seg=seg.cpu().numpy(), depth=depth.cpu().numpy())
+
+    def render(self, mode: str = "rgb_array", env_index: int = 0, width: int | None = None, height: int | None = None):
+        """``FixedwingBaseEnv.render`` [REF fixedwing_base_env.py:350-369]: the RGBA frame (uint8 [H,W,4]) of one env."""
+        if mode != "rgb_array":
+            raise ValueError("only mode='rgb_array' is available (there is no window to draw into)")
+        return self.render_layers(env_index, width, height)["rgba"]
+
+    def get_images(self):
+        """stable_baselines3 ``VecEnv.get_images``: one frame per env -- meant for a handful of envs."""
+        return [self.render(env_index=i) for i in range(self.num_envs)]
+
     def fault_count(self) -> int:
         """Envs force-reset so far because their state went non-finite (FLAG_FAULT)."""
         out = C.c_int64(0)

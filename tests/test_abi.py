@@ -29,7 +29,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_abi_version_and_struct_size():
     lib = _lib.load()
-    assert lib.fw_abi_version() == 10 == _lib.ABI_VERSION
+    assert lib.fw_abi_version() == 11 == _lib.ABI_VERSION
     assert lib.fw_config_size() == C.sizeof(fw.config.FwConfigC)
 
 

@@ -157,3 +157,38 @@ def test_phase_switch_lock_and_strike(fo):
     _, rew, flags, _ = env2.step(ZERO)
     assert e2.duck_phase == 1 and e2.lock_steps >= 1
     assert rew[0] > -0.1           # dense 1/max(depth,2) + lock reward
+
+
+
+
+def test_oracle_debug_frame_geometry(fo):
+    """fwo_render: a duck placed straight ahead of a level aircraft projects to the image centre column,
+    its silhouette area agrees with the pin-hole estimate pi (R / z)^2 / 4 the vision features use, the ground fills the
+    lower half and depth-buffer values grow towards the horizon."""
+    cfg = fw.waypoint_objlock(num_obstacles=0)
+    o = fo.OracleVecEnv(cfg.as_dict(), 1, seed=1)
+    o.reset()
+    st = o.get_state()
+    st["pos"][0] = [0.0, 0.0, 20.0]; st["quat"][0] = [0.0, 0.0, 0.0, 1.0]; st["vel"][0] = [20.0, 0.0, 0.0]; st["omega"][0] = 0.0
+    st["duck"][0] = [60.0, 0.0, 0.0]
+    o.set_state(st)
+    W = 256
+    f = o.render(0, W, W)
+    seg, depth = f["seg"], f["depth"]
+    ys, xs = np.nonzero(seg == 1)
+    assert len(xs) > 20
+    assert abs(xs.mean() - (W - 1) / 2) < 1.0                       # centred left-right
+    cam = np.array([0.0, 0.0, 20.0]) + np.array(cfg.cam_offset)
+    ctr = np.array([60.0, 0.0, cfg.duck_radius])
+    fwd = -np.array(cfg.cam_offset) / np.linalg.norm(cfg.cam_offset)
+    right = np.cross(fwd, [0.0, 0.0, 1.0]); right /= np.linalg.norm(right)
+    upv = np.cross(right, fwd)
+    zc, yc = float((ctr - cam) @ fwd), float((ctr - cam) @ upv)
+    assert ys.mean() / W == pytest.approx(0.5 - 0.5 * yc / zc, abs=0.01)      # the row the vision features report as cy
+    area = np.pi * (cfg.duck_radius / zc) ** 2 / 4.0
+    assert len(xs) / (W * W) == pytest.approx(area, rel=0.15)
+    # ground (or a waypoint sphere in front of it) along the bottom row, sky (or a waypoint sphere) along the top
+    assert ((seg[-1] == 0) | (seg[-1] >= 64)).all() and ((seg[0] == -1) | (seg[0] >= 64)).all() and (seg[-1] == 0).any()
+    col = depth[:, 3]
+    g = col[seg[:, 3] == 0]
+    assert (np.diff(g) <= 1e-12).all() and g.max() <= 1.0           # rows further down are nearer
