@@ -143,6 +143,18 @@ int ppo_minibatch_steps_a(float* params, int32_t d, int32_t a, const float* obs_
                           float eps, float max_grad_norm, int32_t* step_counter, float* grad_norm_out, float* grad, float* stats,
                           void* stream);
 
+/* A window of n_minibatches (<= PPO_MAX_WINDOW) consecutive optimizer steps of a single process at ANY minibatch size:
+ * idx[k*batch .. (k+1)*batch) is minibatch k.  One launch computes the advantage statistics of all of them, then per
+ * minibatch the gradient kernel and the partial-gradient reduction whose last block applies clip_grad_norm_ + Adam.step
+ * (2 n + 1 launches instead of 4 n; results bit-identical to ppo_minibatch_grad_a + ppo_adam_step with grad_scale 1).
+ * workspace as for ppo_minibatch_grad_a. */
+#define PPO_MAX_WINDOW 16
+int ppo_window_update_a(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act, const float* logp_old,
+                        const float* adv, const float* ret, const int64_t* idx, int32_t batch, int32_t n_minibatches,
+                        float clip_range, float ent_coef, float vf_coef, float* exp_avg, float* exp_avg_sq, float lr, float beta1,
+                        float beta2, float eps, float max_grad_norm, int32_t* step_counter, float* grad_norm_out, float* workspace,
+                        float* grad, float* stats, void* stream);
+
 /* torch.nn.utils.clip_grad_norm_(max_grad_norm) followed by torch.optim.Adam.step (no weight decay / amsgrad) on the
  * flat parameter vector; grad is pre-multiplied by grad_scale (1 / world_size after the NCCL sum).
  * step_counter: device int32 incremented by the call (bias correction). */

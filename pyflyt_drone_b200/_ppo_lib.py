@@ -28,6 +28,8 @@ PPO_SYMBOLS = [
     ("ppo_minibatch_grad_a", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, _F, _F, _F, _P, _P, _P, _P]),
     ("ppo_minibatch_steps_a", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _F, _F, _F, _P, _P,
                                         _F, _F, _F, _F, _F, _P, _P, _P, _P, _P]),
+    ("ppo_window_update_a", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _F, _F, _F, _P, _P,
+                                      _F, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
     ("ppo_minibatch_grad", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, _F, _F, _F, _P, _P, _P, _P]),
     ("ppo_adam_step", C.c_int, [_P, _P, _P, _P, C.c_int32, _F, _F, _F, _F, _F, _F, _P, _P, _P]),
     ("ppo_gae", C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _F, _F, _P, _P, _P]),

@@ -207,12 +207,13 @@ extern "C" int ppo_counter_add(uint32_t* counter, uint32_t inc, void* stream) {
     return FW_OK;
 }
 
-// workspace layout (floats): [0,8) pad | [8,16) adv stats | [16, 16 + 160*P) per-CTA gradient partials | 160*8 per-CTA loss
-// statistics | PPO_ADV_SCRATCH floats = doubles for the advantage statistics (arrival counter + 592 block partials; the
-// arrival counter must start zeroed, the kernel leaves it zeroed)
+// workspace layout (floats): [0,8) arrival counter of the reduce+Adam kernel (unsigned, starts zeroed) + pad | [8,16) adv stats
+// of a single-minibatch call | [16, 16 + 160*P) per-CTA gradient partials | 160*8 per-CTA loss statistics | PPO_MAX_WINDOW
+// scratch slices of PPO_ADV_SCRATCH floats (doubles: arrival counter + 592 block partials; the counters start zeroed and
+// the kernel leaves them zeroed) | 2 * PPO_MAX_WINDOW floats: advantage statistics of a window's minibatches
 #define PPO_ADV_SCRATCH (2 * (2 + 2 * 592))
 extern "C" int ppo_update_workspace_floats_a(int32_t d, int32_t a) {
-    return 16 + 160 * ppo_param_count_a(d, a) + 160 * 8 + PPO_ADV_SCRATCH;
+    return 16 + 160 * ppo_param_count_a(d, a) + 160 * 8 + PPO_MAX_WINDOW * PPO_ADV_SCRATCH + 2 * PPO_MAX_WINDOW;
 }
 extern "C" int ppo_update_workspace_floats(int32_t d) { return ppo_update_workspace_floats_a(d, PPO_ACT); }
 
@@ -276,6 +277,54 @@ extern "C" int ppo_minibatch_steps_a(float* params, int32_t d, int32_t a, const 
     else if (a == 4) PCU(ppo_a4::ppok_minibatch_steps(STEPS_ARGS));
     else PCU(ppo_a6::ppok_minibatch_steps(STEPS_ARGS));
 #undef STEPS_ARGS
+    return FW_OK;
+}
+
+extern "C" int ppo_window_update_a(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act,
+                                   const float* logp_old, const float* adv, const float* ret, const int64_t* idx, int32_t batch,
+                                   int32_t n_minibatches, float clip_range, float ent_coef, float vf_coef, float* exp_avg,
+                                   float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float max_grad_norm,
+                                   int32_t* step_counter, float* grad_norm_out, float* workspace, float* grad, float* stats,
+                                   void* stream) {
+    if (!params || !obs_norm || !act || !logp_old || !adv || !ret || !idx || !exp_avg || !exp_avg_sq || !step_counter || !workspace ||
+        !grad)
+        return pfail(FW_EINVAL, "null argument");
+    if (batch <= 0) return pfail(FW_EINVAL, "batch must be positive");
+    if (n_minibatches <= 0 || n_minibatches > PPO_MAX_WINDOW)
+        return pfail(FW_EINVAL, "n_minibatches %d out of range [1,%d]", n_minibatches, PPO_MAX_WINDOW);
+    int rc = (a == 4) ? check_d(d) : check_d_tc(d);
+    if (rc) return rc;
+    if ((rc = check_a(a)) != 0) return rc;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 15u) || (reinterpret_cast<uintptr_t>(act) & 15u))
+        return pfail(FW_EINVAL, "workspace and action buffer must be 16-byte aligned");
+    const int P = ppo_param_count_a(d, a);
+    if (P > 16384) return pfail(FW_EINVAL, "parameter vector too long");
+    if (ppok_update_grid(batch) > 160) return pfail(FW_ESTATE, "more SMs than the workspace was sized for");
+    float* partial = workspace + 16;
+    float* stats_partial = partial + (size_t)160 * P;
+    double* scratch = reinterpret_cast<double*>(stats_partial + 160 * 8);
+    float* win_stats = stats_partial + 160 * 8 + (size_t)PPO_MAX_WINDOW * PPO_ADV_SCRATCH;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long* ix = reinterpret_cast<const long long*>(idx);
+    // one launch for the advantage statistics of every minibatch of the window, then per minibatch the gradient kernel and
+    // the reduction whose last block applies clip + Adam
+    ppok_launch_adv_stats(adv, ix, batch, n_minibatches, scratch, win_stats, st);
+    PCU(cudaGetLastError());
+    PpokAdam adam{lr, beta1, beta2, eps, max_grad_norm, params, exp_avg, exp_avg_sq, step_counter, grad_norm_out,
+                  reinterpret_cast<unsigned*>(workspace)};
+    for (int k = 0; k < n_minibatches; ++k) {
+        const long long* ik = ix + (size_t)k * batch;
+        float* as = win_stats + 2 * k;
+        if (a == 4 && d > PPO_TC_MAX_OBS)
+            PCU(ppo_a4d64::ppok_minibatch_grad(params, d, obs_norm, act, logp_old, adv, ret, ik, batch, clip_range, ent_coef, vf_coef,
+                                               scratch, as, partial, stats_partial, grad, stats, st, &adam, 1));
+        else if (a == 4)
+            PCU(ppo_a4::ppok_minibatch_grad(params, d, obs_norm, act, logp_old, adv, ret, ik, batch, clip_range, ent_coef, vf_coef,
+                                            scratch, as, partial, stats_partial, grad, stats, st, &adam, 1));
+        else
+            PCU(ppo_a6::ppok_minibatch_grad(params, d, obs_norm, act, logp_old, adv, ret, ik, batch, clip_range, ent_coef, vf_coef,
+                                            scratch, as, partial, stats_partial, grad, stats, st, &adam, 1));
+    }
     return FW_OK;
 }
 

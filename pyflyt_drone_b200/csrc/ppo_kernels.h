@@ -36,6 +36,9 @@ cudaError_t ppok_gae(const float* rewards, const float* values, const float* don
 PPOK_DECLARE_FORWARD_TC(ppo_a4)
 PPOK_DECLARE_FORWARD_TC(ppo_a6)
 int ppok_update_grid(int batch);
+// clip + Adam folded into the partial-gradient reduction (single process: nothing sits between gradient and optimizer)
+struct PpokAdam { float lr, beta1, beta2, eps, max_norm; float* params; float* m; float* v; int* step_ctr; float* norm_out; unsigned* arrivals; };
+void ppok_launch_adv_stats(const float* adv, const long long* idx, int batch, int nmb, double* scratch, float* adv_stats, cudaStream_t st);
 // fused minibatch gradient: one instantiation per (action width, observation slab): ppo_update_tc.cu = (4, 32),
 // ppo_update_tc_a6.cu = (6, 32), ppo_update_tc_d64.cu = (4, 64)
 #define PPOK_DECLARE_MINIBATCH_GRAD(ns)                                                                                    \
@@ -43,7 +46,8 @@ int ppok_update_grid(int batch);
     cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, const float* act, const float* logp_old, \
                                     const float* adv, const float* ret, const long long* idx, int batch, float clip_range, \
                                     float ent_coef, float vf_coef, double* scratch, float* adv_stats, float* partial,      \
-                                    float* stats_partial, float* grad, float* stats, cudaStream_t st);                     \
+                                    float* stats_partial, float* grad, float* stats, cudaStream_t st,                      \
+                                    const PpokAdam* adam = nullptr, int have_adv_stats = 0);                               \
     cudaError_t ppok_minibatch_steps(float* params, int d, const float* obs, const float* act, const float* logp_old,       \
                                      const float* adv, const float* ret, const long long* idx, int batch, int steps,       \
                                      float clip_range, float ent_coef, float vf_coef, float* m, float* v, float lr,        \

@@ -977,12 +977,15 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
 // ------------------------------------------------------------------ minibatch advantage statistics (mean, unbiased std)
 // scratch: [0] block-arrival counter, [2 + 2b], [3 + 2b] = block b's sum / sum of squares; the last block to arrive adds the
 // block partials in index order (no floating-point atomics: the statistics do not depend on the block schedule)
+// blockIdx.y = minibatch of a window of consecutive minibatches (its own index slice, scratch slice and output pair)
 #define ADV_MAX_BLOCKS 592
+#define ADV_SCRATCH_DOUBLES (2 + 2 * ADV_MAX_BLOCKS)
 __global__ void __launch_bounds__(256)
 ppo_adv_stats_kernel(const float* __restrict__ adv, const long long* __restrict__ idx, int batch, double* __restrict__ scratch,
                      float* __restrict__ out) {
     __shared__ double s_a[8], s_b[8];
     __shared__ bool is_last;
+    idx += (size_t)blockIdx.y * batch; scratch += (size_t)blockIdx.y * ADV_SCRATCH_DOUBLES; out += 2 * blockIdx.y;
     double a = 0.0, b = 0.0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < batch; i += gridDim.x * blockDim.x) {
         double v = (double)adv[idx[i]];
@@ -1020,9 +1023,18 @@ ppo_adv_stats_kernel(const float* __restrict__ adv, const long long* __restrict_
 // block = 64 parameters x 16 slices of the CTA axis: 16 independent load chains per parameter instead of one
 #define RED_KX 64
 #define RED_CY 16
+// adam.enabled: single-process update (no all-reduce between gradient and optimizer) -- the last block to finish its slice
+// of the reduction runs clip + Adam on the complete gradient, saving the optimizer's own launch
+struct PpoAdamArgs { int enabled; float lr, beta1, beta2, eps, max_norm; float* params; float* m; float* v; int* step_ctr; float* norm_out;
+                     unsigned* arrivals; };
+#define ADAM_THREADS 1024
+#define ADAM_PER 16          // parameters per thread held in registers: P <= 16384
+__device__ __forceinline__ void ppo_adam_block(float* params, const float* grad, float* m, float* v, int P, float lr, float beta1,
+                                               float beta2, float eps, float max_norm, float grad_scale, int* step_ctr,
+                                               float* norm_out, float* s_red, float* s_coef);
 __global__ void __launch_bounds__(RED_KX * RED_CY)
 ppo_grad_reduce_kernel(const float* __restrict__ partial, const float* __restrict__ stats_partial, int ncta, int P,
-                       float* __restrict__ grad, float* __restrict__ stats) {
+                       float* grad, float* __restrict__ stats, PpoAdamArgs adam) {
     __shared__ float s_part[RED_CY][RED_KX + 1];
     const int kx = threadIdx.x % RED_KX, cy = threadIdx.x / RED_KX;
     const int k = blockIdx.x * RED_KX + kx;
@@ -1042,17 +1054,31 @@ ppo_grad_reduce_kernel(const float* __restrict__ partial, const float* __restric
         for (int c = 0; c < ncta; ++c) t += stats_partial[(size_t)c * 8 + threadIdx.x];
         stats[threadIdx.x] = t;
     }
+    if (!adam.enabled) return;
+    __shared__ bool is_last;
+    __shared__ float s_red[32];
+    __shared__ float s_coef;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned prev = atomicAdd(adam.arrivals, 1u);
+        is_last = prev == gridDim.x - 1;
+        if (is_last) *adam.arrivals = 0u;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    ppo_adam_block(adam.params, grad, adam.m, adam.v, P, adam.lr, adam.beta1, adam.beta2, adam.eps, adam.max_norm, 1.0f,
+                   adam.step_ctr, adam.norm_out, s_red, &s_coef);
 }
 
 // ------------------------------------------------------------------ clip_grad_norm_ + Adam, one block
-#define ADAM_THREADS 1024
-#define ADAM_PER 16          // parameters per thread held in registers: P <= 16384
-__global__ void __launch_bounds__(ADAM_THREADS)
-ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v, int P,
-                float lr, float beta1, float beta2, float eps, float max_norm, float grad_scale, int* __restrict__ step_ctr,
-                float* __restrict__ norm_out) {
-    __shared__ float s_red[32];
-    __shared__ float s_coef;
+static_assert(ADAM_THREADS == RED_KX * RED_CY, "the reduction's last block runs the Adam body");
+// the whole update by ONE block of ADAM_THREADS threads; grad may have been written by other blocks of the same launch
+// (ppo_grad_reduce_kernel's last block), hence the L2 loads
+__device__ __forceinline__ void ppo_adam_block(float* params, const float* grad, float* m, float* v, int P, float lr, float beta1,
+                                               float beta2, float eps, float max_norm, float grad_scale, int* step_ctr,
+                                               float* norm_out, float* s_red, float* s_coef) {
     // every load of the update is issued before the norm reduction so that the second pass only does arithmetic
     float g[ADAM_PER], mk[ADAM_PER], vk[ADAM_PER], pk[ADAM_PER];
     float ss = 0.0f;
@@ -1060,7 +1086,7 @@ ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, floa
     for (int i = 0; i < ADAM_PER; ++i) {
         const int k = threadIdx.x + i * ADAM_THREADS;
         const bool ok = k < P;
-        g[i] = ok ? grad[k] * grad_scale : 0.0f;
+        g[i] = ok ? __ldcg(grad + k) * grad_scale : 0.0f;
         mk[i] = ok ? m[k] : 0.0f; vk[i] = ok ? v[k] : 0.0f; pk[i] = ok ? params[k] : 0.0f;
         ss = fmaf(g[i], g[i], ss);
     }
@@ -1075,13 +1101,13 @@ ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, floa
         for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
         if (threadIdx.x == 0) {
             const float norm = sqrtf(x);
-            s_coef = fminf(1.0f, max_norm / (norm + 1e-6f));          // torch.nn.utils.clip_grad_norm_
+            *s_coef = fminf(1.0f, max_norm / (norm + 1e-6f));          // torch.nn.utils.clip_grad_norm_
             if (norm_out != nullptr) norm_out[0] = norm;
             step_ctr[0] = t;
         }
     }
     __syncthreads();
-    const float coef = s_coef;
+    const float coef = *s_coef;
     const float bc1 = 1.0f - powf(beta1, (float)t), bc2 = 1.0f - powf(beta2, (float)t);
     const float inv_bc1 = 1.0f / bc1, inv_bc2 = 1.0f / bc2;
 #pragma unroll
@@ -1097,6 +1123,14 @@ ppo_adam_kernel(float* __restrict__ params, const float* __restrict__ grad, floa
     }
 }
 
+__global__ void __launch_bounds__(ADAM_THREADS)
+ppo_adam_kernel(float* params, const float* grad, float* m, float* v, int P, float lr, float beta1, float beta2, float eps,
+                float max_norm, float grad_scale, int* step_ctr, float* norm_out) {
+    __shared__ float s_red[32];
+    __shared__ float s_coef;
+    ppo_adam_block(params, grad, m, v, P, lr, beta1, beta2, eps, max_norm, grad_scale, step_ctr, norm_out, s_red, &s_coef);
+}
+
 // ------------------------------------------------------------------ launchers
 static int g_ut_sm_count_shared = 0;
 
@@ -1110,14 +1144,20 @@ int ppok_update_grid(int batch) {
     return ntiles < g_ut_sm_count_shared ? ntiles : g_ut_sm_count_shared;
 }
 
-void ppok_launch_adv_stats(const float* adv, const long long* idx, int batch, double* scratch, float* adv_stats, cudaStream_t st) {
+// nmb consecutive minibatches (idx slices of `batch`) in one launch: scratch / adv_stats slices per minibatch
+void ppok_launch_adv_stats(const float* adv, const long long* idx, int batch, int nmb, double* scratch, float* adv_stats, cudaStream_t st) {
     int sblocks = (batch + 255) / 256;            // one gathered element per thread up to 4 blocks per SM
     if (sblocks > ADV_MAX_BLOCKS) sblocks = ADV_MAX_BLOCKS;
-    ppo_adv_stats_kernel<<<sblocks, 256, 0, st>>>(adv, idx, batch, scratch, adv_stats);
+    ppo_adv_stats_kernel<<<dim3(sblocks, nmb), 256, 0, st>>>(adv, idx, batch, scratch, adv_stats);
 }
 
-void ppok_launch_grad_reduce(const float* partial, const float* stats_partial, int grid, int P, float* grad, float* stats, cudaStream_t st) {
-    ppo_grad_reduce_kernel<<<(P + RED_KX - 1) / RED_KX, RED_KX * RED_CY, 0, st>>>(partial, stats_partial, grid, P, grad, stats);
+void ppok_launch_grad_reduce(const float* partial, const float* stats_partial, int grid, int P, float* grad, float* stats,
+                             const PpokAdam* adam, cudaStream_t st) {
+    PpoAdamArgs a{};
+    if (adam != nullptr)
+        a = PpoAdamArgs{1, adam->lr, adam->beta1, adam->beta2, adam->eps, adam->max_norm, adam->params, adam->m, adam->v, adam->step_ctr,
+                        adam->norm_out, adam->arrivals};
+    ppo_grad_reduce_kernel<<<(P + RED_KX - 1) / RED_KX, RED_KX * RED_CY, 0, st>>>(partial, stats_partial, grid, P, grad, stats, a);
 }
 
 cudaError_t ppok_adam(float* params, const float* grad, float* m, float* v, int P, float lr, float beta1, float beta2, float eps,
@@ -1128,8 +1168,9 @@ cudaError_t ppok_adam(float* params, const float* grad, float* m, float* v, int 
 }
 #endif  // PPO_UT_SHARED
 
-void ppok_launch_adv_stats(const float* adv, const long long* idx, int batch, double* scratch, float* adv_stats, cudaStream_t st);
-void ppok_launch_grad_reduce(const float* partial, const float* stats_partial, int grid, int P, float* grad, float* stats, cudaStream_t st);
+void ppok_launch_adv_stats(const float* adv, const long long* idx, int batch, int nmb, double* scratch, float* adv_stats, cudaStream_t st);
+void ppok_launch_grad_reduce(const float* partial, const float* stats_partial, int grid, int P, float* grad, float* stats,
+                             const PpokAdam* adam, cudaStream_t st);
 
 namespace PPO_UT_NS {
 static bool g_ut_attr_set = false, g_ut_fused_attr_set = false;
@@ -1137,7 +1178,8 @@ static bool g_ut_attr_set = false, g_ut_fused_attr_set = false;
 cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, const float* act, const float* logp_old,
                                 const float* adv, const float* ret, const long long* idx, int batch, float clip_range,
                                 float ent_coef, float vf_coef, double* scratch, float* adv_stats, float* partial,
-                                float* stats_partial, float* grad, float* stats, cudaStream_t st) {
+                                float* stats_partial, float* grad, float* stats, cudaStream_t st, const PpokAdam* adam,
+                                int have_adv_stats) {
     if (d > DP) return cudaErrorInvalidValue;
     if (!g_ut_attr_set) {
         cudaError_t e = cudaFuncSetAttribute(ppo_grad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL);
@@ -1148,7 +1190,7 @@ cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, co
     if (grid <= 0) return cudaErrorUnknown;
     const int H_ = PPO_H, A_ = A;
     const int P = (H_ * d + H_ + H_ * H_ + H_ + A_ * H_ + A_) + (H_ * d + H_ + H_ * H_ + H_ + H_ + 1) + A_;
-    ppok_launch_adv_stats(adv, idx, batch, scratch, adv_stats, st);
+    if (!have_adv_stats) ppok_launch_adv_stats(adv, idx, batch, 1, scratch, adv_stats, st);
     // per-sample head gradients carry a 1/batch factor; rescale them to O(1) before the bf16 rounding of the backward
     // operands (a power of two, so the scaling itself is exact) and undo it when the accumulators are read out
     float gs = 1.0f;
@@ -1157,7 +1199,7 @@ cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, co
     PpoFusedCfg fz{};
     ppo_grad_tc_kernel<false><<<grid, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, adv_stats, cfg,
                                                              partial, stats_partial, P, fz);
-    ppok_launch_grad_reduce(partial, stats_partial, grid, P, grad, stats, st);
+    ppok_launch_grad_reduce(partial, stats_partial, grid, P, grad, stats, adam, st);
     return cudaGetLastError();
 }
 

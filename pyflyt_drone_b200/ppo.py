@@ -399,17 +399,27 @@ class PPO:
                         _p(b["ret"]), _p(perm[s:s + chunk * bs]), bs, chunk, self.clip_range, self.ent_coef, self.vf_coef,
                         _p(self._adam_m), _p(self._adam_v), lr, b1, b2, eps, self.max_grad_norm, _p(self._adam_t),
                         _p(self._grad_norm), _p(self._grad), _p(self._stats_mb), _stream()))
-        elif self.use_graph and self.update_graph and self._train_calls > 1 and total % bs == 0:
-            chunk = max(c for c in range(1, min(steps_per_epoch, self.update_graph_steps) + 1) if steps_per_epoch % c == 0)
-            key = (total, bs, chunk, lr, b1, b2, eps, self.clip_range, self.ent_coef, self.vf_coef, self.max_grad_norm)
-            if self._ugraph is None or self._ugraph_key != key:
-                self._capture_update_graph(total, bs, chunk, lr, b1, b2, eps)
-                self._ugraph_key = key
-            self._perm_ctr.copy_(torch.tensor([self._perm_epoch + 1, 0], dtype=torch.int32), non_blocking=False)
-            for _ in range(self.n_epochs * (steps_per_epoch // chunk)):
-                self._ugraph.replay()
-            self._perm_epoch += self.n_epochs
-        else:
+        elif total % bs == 0:
+            # windows of consecutive minibatches: a single process runs each window through ppo_window_update_a (one launch
+            # for the window's advantage statistics, clip + Adam inside the gradient reduction: 2 n + 1 launches for n
+            # steps); with an all-reduce between gradient and optimizer the steps stay four launches + NCCL each
+            cap = 16 if self.world == 1 else self.update_graph_steps
+            chunk = max(c for c in range(1, min(steps_per_epoch, cap) + 1) if steps_per_epoch % c == 0)
+            if self.use_graph and self.update_graph and self._train_calls > 1:
+                key = (total, bs, chunk, lr, b1, b2, eps, self.clip_range, self.ent_coef, self.vf_coef, self.max_grad_norm)
+                if self._ugraph is None or self._ugraph_key != key:
+                    self._capture_update_graph(total, bs, chunk, lr, b1, b2, eps)
+                    self._ugraph_key = key
+                self._perm_ctr.copy_(torch.tensor([self._perm_epoch + 1, 0], dtype=torch.int32), non_blocking=False)
+                for _ in range(self.n_epochs * (steps_per_epoch // chunk)):
+                    self._ugraph.replay()
+                self._perm_epoch += self.n_epochs
+            else:
+                for _ in range(self.n_epochs):
+                    perm = self._epoch_permutation(total)
+                    for s in range(0, total, chunk * bs):
+                        self._window_steps(perm[s:s + chunk * bs], bs, chunk, lr, b1, b2, eps)
+        else:                                          # ragged last minibatch (stable_baselines3 allows it): step by step
             for _ in range(self.n_epochs):
                 perm = self._epoch_permutation(total)
                 for s in range(0, total, bs):
@@ -429,6 +439,19 @@ class PPO:
                                           self.policy.count, lr, b1, b2, eps, self.max_grad_norm, 1.0 / self.world,
                                           _p(self._adam_t), _p(self._grad_norm), _stream()))
 
+    def _window_steps(self, idx: torch.Tensor, bs: int, nmb: int, lr: float, b1: float, b2: float, eps: float) -> None:
+        """`nmb` consecutive optimizer steps over the index window `idx` (nmb * bs entries)."""
+        if self.world == 1:
+            b = self.buf
+            _lib.check(self.lib.ppo_window_update_a(
+                _p(self.policy.theta.data), self.d, self.a, _p(b["obs"]), _p(b["act"]), _p(b["logp"]), _p(b["adv"]), _p(b["ret"]),
+                _p(idx), bs, nmb, self.clip_range, self.ent_coef, self.vf_coef, _p(self._adam_m), _p(self._adam_v), lr, b1, b2, eps,
+                self.max_grad_norm, _p(self._adam_t), _p(self._grad_norm), _p(self._ws), _p(self._grad), _p(self._stats_mb),
+                _stream()))
+        else:
+            for k in range(nmb):
+                self._optimizer_step(idx[k * bs:(k + 1) * bs], lr, b1, b2, eps)
+
     def _capture_update_graph(self, total: int, bs: int, chunk: int, lr: float, b1: float, b2: float, eps: float) -> None:
         """Graph of one window: indices of the next `chunk` minibatches (ppo_random_permutation_window advances the device
         counters), then per minibatch the gradient kernels, the NCCL all-reduce when world > 1, and clip + Adam."""
@@ -439,8 +462,7 @@ class PPO:
         with torch.cuda.graph(self._ugraph):
             _lib.check(self.lib.ppo_random_permutation_window(_p(self._perm_win), total, self.seed & (2 ** 64 - 1),
                                                               _p(self._perm_ctr), chunk * bs, _stream()))
-            for k in range(chunk):
-                self._optimizer_step(self._perm_win[k * bs:(k + 1) * bs], lr, b1, b2, eps)
+            self._window_steps(self._perm_win, bs, chunk, lr, b1, b2, eps)
 
     def _epoch_permutation(self, total: int) -> torch.Tensor:
         """Minibatch order of the next epoch (RolloutBuffer.get's np.random.permutation): a keyed Feistel bijection

@@ -421,6 +421,38 @@ def test_single_cta_optimizer_steps_equal_the_launch_per_kernel_update(preset, b
     env.close()
 
 
+@pytest.mark.parametrize("preset,batch", [("waypoints_v3", 1000), ("lowlevel", 512), ("objlock_duck", 700)])
+def test_window_update_is_bit_identical_to_separate_launches(preset, batch):
+    """ppo_window_update_a (one advantage-statistics launch per window, clip + Adam by the last block of the gradient
+    reduction) against ppo_minibatch_grad_a + ppo_adam_step per minibatch: same kernels' arithmetic, so parameters, Adam
+    moments, step counter, gradient, norm and statistics are bit-identical."""
+    from pyflyt_drone_b200.ppo import PPO
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    env = FixedwingVecEnv(256, preset=preset, seed=4)
+    m = PPO("MlpPolicy", env, n_steps=16, batch_size=batch, n_epochs=1, seed=4, use_cuda_graph=False)
+    m.collect_rollouts()
+    with torch.no_grad():
+        m.policy.theta.add_(0.02 * torch.randn(m.policy.count, device=m.device, generator=m._gen))
+    snap = [t.clone() for t in (m.policy.theta.data, m._adam_m, m._adam_v, m._adam_t)]
+    perm = m._epoch_permutation(16 * 256).clone()
+    nmb, out = 4, {}
+    for window in (True, False):
+        for dst, src in zip((m.policy.theta.data, m._adam_m, m._adam_v, m._adam_t), snap):
+            dst.copy_(src)
+        if window:
+            m._window_steps(perm[:nmb * batch], batch, nmb, 3e-4, 0.9, 0.999, 1e-5)
+        else:
+            for k in range(nmb):
+                m._optimizer_step(perm[k * batch:(k + 1) * batch], 3e-4, 0.9, 0.999, 1e-5)
+        torch.cuda.synchronize()
+        out[window] = (m.policy.theta.detach().clone(), m._adam_m.clone(), m._adam_v.clone(), m._adam_t.clone(), m._stats_mb.clone(),
+                       m._grad_norm.clone(), m._grad.clone())
+    assert int(out[True][3]) == int(snap[3]) + nmb and not torch.equal(out[True][0], snap[0])
+    for a, b in zip(out[True], out[False]):
+        assert torch.equal(a, b)
+    env.close()
+
+
 def test_adam_step_matches_torch_optim(model):
     from pyflyt_drone_b200 import _lib
     from pyflyt_drone_b200.ppo import _p, _stream
