@@ -28,8 +28,8 @@ extern "C" {
 #define PPO_HIDDEN 64
 #define PPO_ACT 4
 #define PPO_MAX_OBS 64      /* CUDA-core forward, value, bootstrap, running moments */
-#define PPO_TC_MAX_OBS 32   /* tcgen05 forward (ppo_policy_forward_tc*); fused minibatch gradient with a = 6.  The a = 4
-                             * gradient also takes d up to PPO_MAX_OBS (64-wide build, csrc/ppo_update_tc_d64.cu) */
+#define PPO_TC_MAX_OBS 32   /* tcgen05 forward (ppo_policy_forward_tc*) and fused minibatch gradient with a = 6.  With a = 4
+                             * both also take d up to PPO_MAX_OBS (64-wide builds, csrc/ppo_tc_d64.cu, ppo_update_tc_d64.cu) */
 
 /* number of floats in the parameter vector for observation width d */
 int ppo_param_count(int32_t d);

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfwsim.so")
-SOURCES = ["fw_api.cu", "fw_kernels.cu", "fw_render.cu", "ppo_kernels.cu", "ppo_tc.cu", "ppo_tc_a6.cu", "ppo_update_tc.cu", "ppo_update_tc_a6.cu", "ppo_update_tc_d64.cu", "ppo_api.cu"]
+SOURCES = ["fw_api.cu", "fw_kernels.cu", "fw_render.cu", "ppo_kernels.cu", "ppo_tc.cu", "ppo_tc_a6.cu", "ppo_tc_d64.cu", "ppo_update_tc.cu", "ppo_update_tc_a6.cu", "ppo_update_tc_d64.cu", "ppo_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # flush fp32 denormals: MUFU.RCP/RSQ/SIN/COS then need no 2^24 rescue sequences (4-6 instructions each)

@@ -121,12 +121,15 @@ extern "C" int ppo_policy_forward_tc_a(const float* params, int32_t d, int32_t a
                                        float* act_env, float* act_raw, float* logp, float* value, void* stream) {
     if (!params || !obs_raw || !act_env || !value) return pfail(FW_EINVAL, "null argument");
     if (n <= 0) return pfail(FW_EINVAL, "n must be positive");
-    int rc = check_d_tc(d);
+    int rc = (a == 4) ? check_d(d) : check_d_tc(d);        // 64-wide build for four-channel policies (ppo_tc_d64.cu)
     if (rc) return rc;
     if ((rc = check_a(a)) != 0) return rc;
     if ((reinterpret_cast<uintptr_t>(act_env) & 15u) || (act_raw && (reinterpret_cast<uintptr_t>(act_raw) & 15u)))
         return pfail(FW_EINVAL, "action buffers must be 16-byte aligned");
-    if (a == 4)
+    if (a == 4 && d > PPO_TC_MAX_OBS)
+        PCU(ppo_a4d64::ppok_forward_tc(params, d, obs_raw, obs_stats, clip_obs, n, seed, env_id0, step, step_dev, deterministic,
+                                       obs_norm, act_env, act_raw, logp, value, (cudaStream_t)stream));
+    else if (a == 4)
         PCU(ppo_a4::ppok_forward_tc(params, d, obs_raw, obs_stats, clip_obs, n, seed, env_id0, step, step_dev, deterministic,
                                     obs_norm, act_env, act_raw, logp, value, (cudaStream_t)stream));
     else

@@ -35,6 +35,7 @@ cudaError_t ppok_gae(const float* rewards, const float* values, const float* don
     }
 PPOK_DECLARE_FORWARD_TC(ppo_a4)
 PPOK_DECLARE_FORWARD_TC(ppo_a6)
+PPOK_DECLARE_FORWARD_TC(ppo_a4d64)
 int ppok_update_grid(int batch);
 // clip + Adam folded into the partial-gradient reduction (single process: nothing sits between gradient and optimizer)
 struct PpokAdam { float lr, beta1, beta2, eps, max_norm; float* params; float* m; float* v; int* step_ctr; float* norm_out; unsigned* arrivals; };

@@ -15,23 +15,30 @@
 
 #include <cuda_runtime.h>
 
-// The file is compiled once per supported action width (ppo_tc_a6.cu includes it with PPO_A_BUILD = 6); everything
-// lives in a namespace named after the width.
+// The file is compiled once per supported (action width, observation slab): ppo_tc_a6.cu includes it with PPO_A_BUILD = 6,
+// ppo_tc_d64.cu with PPO_D_BUILD = 64 (observations of 33..64 floats: two 32-column slabs per row); everything lives in a
+// namespace named after the build.
 #ifndef PPO_A_BUILD
 #define PPO_A_BUILD 4
 #endif
-#if PPO_A_BUILD == 4
+#ifndef PPO_D_BUILD
+#define PPO_D_BUILD 32
+#endif
+#if PPO_A_BUILD == 4 && PPO_D_BUILD == 32
 namespace ppo_a4 {
-#elif PPO_A_BUILD == 6
+#elif PPO_A_BUILD == 6 && PPO_D_BUILD == 32
 namespace ppo_a6 {
+#elif PPO_A_BUILD == 4 && PPO_D_BUILD == 64
+namespace ppo_a4d64 {
 #else
-#error "action width must be 4 or 6"
+#error "supported builds: action width 4 or 6 with a 32-wide observation slab, action width 4 with a 64-wide one"
 #endif
 
 #define H PPO_H
 #define A PPO_A_BUILD
 #define AP ((A + 3) / 4 * 4)      // action width padded to whole float4s: the head weights are read as float4 rows
-#define DP PPO_DPAD
+#define DP PPO_D_BUILD
+#define NSLAB (DP / 32)
 #define TC_ROWS 128
 #define TC_THREADS 512
 #define TC_TMEM_COLS 128
@@ -269,15 +276,22 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
     const float* b2 = small + (is_pi ? TcSmem::B2_PI : TcSmem::B2_VF) + j0;
 
     const int ntiles = (n + TC_ROWS - 1) / TC_ROWS;
-    float xcur[8];
+    float xcur[NSLAB][8];
     if ((int)blockIdx.x < ntiles) {
         const int gr = blockIdx.x * TC_ROWS + grow;
-        tc_load8(obs_raw, obs_norm, d, gr, gr < n, gpart, have_stats, small + TcSmem::MEAN, small + TcSmem::ISTD, clip, xcur);
+#pragma unroll
+        for (int sl = 0; sl < NSLAB; ++sl)
+            tc_load8(obs_raw, obs_norm, d, gr, gr < n, gpart + 4 * sl, have_stats, small + TcSmem::MEAN, small + TcSmem::ISTD, clip,
+                     xcur[sl]);
     }
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         // ---- stage the normalised observation slice as the A operand of layer 1
-        *reinterpret_cast<float4*>(smem + TcSmem::AX + tc_off(grow, 8 * gpart, DP)) = make_float4(xcur[0], xcur[1], xcur[2], xcur[3]);
-        *reinterpret_cast<float4*>(smem + TcSmem::AX + tc_off(grow, 8 * gpart + 4, DP)) = make_float4(xcur[4], xcur[5], xcur[6], xcur[7]);
+#pragma unroll
+        for (int sl = 0; sl < NSLAB; ++sl) {
+            const int k = 8 * (gpart + 4 * sl);
+            *reinterpret_cast<float4*>(smem + TcSmem::AX + tc_off(grow, k, DP)) = make_float4(xcur[sl][0], xcur[sl][1], xcur[sl][2], xcur[sl][3]);
+            *reinterpret_cast<float4*>(smem + TcSmem::AX + tc_off(grow, k + 4, DP)) = make_float4(xcur[sl][4], xcur[sl][5], xcur[sl][6], xcur[sl][7]);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
@@ -290,8 +304,10 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
         {
             const int nt = tile + gridDim.x;
             const int gr = nt * TC_ROWS + grow;
-            tc_load8(obs_raw, obs_norm, d, gr, nt < ntiles && gr < n, gpart, have_stats, small + TcSmem::MEAN,
-                     small + TcSmem::ISTD, clip, xcur);
+#pragma unroll
+            for (int sl = 0; sl < NSLAB; ++sl)
+                tc_load8(obs_raw, obs_norm, d, gr, nt < ntiles && gr < n, gpart + 4 * sl, have_stats, small + TcSmem::MEAN,
+                         small + TcSmem::ISTD, clip, xcur[sl]);
         }
         tc_wait(bar, phase); phase ^= 1u;
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -406,6 +422,7 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
 cudaError_t ppok_forward_tc(const float* params, int d, const float* obs_raw, const double* stats, float clip, int n,
                             uint64_t seed, uint32_t env_id0, uint32_t step, const uint32_t* step_dev, int deterministic,
                             float* obs_norm, float* act_env, float* act_raw, float* logp, float* value, cudaStream_t st) {
+    if (d > DP) return cudaErrorInvalidValue;
     static int sm_count = 0;
     if (sm_count == 0) {
         int dev = 0;
@@ -424,4 +441,4 @@ cudaError_t ppok_forward_tc(const float* params, int d, const float* obs_raw, co
     return cudaGetLastError();
 }
 
-}  // namespace ppo_a4 / ppo_a6
+}  // namespace ppo_a4 / ppo_a6 / ppo_a4d64

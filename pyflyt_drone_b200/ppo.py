@@ -268,8 +268,9 @@ class PPO:
         self._grad_norm = torch.zeros(1, **f32)
         self._stats, self._stats_mb = torch.zeros(8, **f32), torch.zeros(8, **f32)
         self.use_graph = bool(use_cuda_graph)
-        # the tcgen05 forward stages one 32-wide K slab of observations per tile; wider observations use the CUDA-core one
-        self.tensor_core_forward = bool(tensor_core_forward) and self.d <= 32
+        # the tcgen05 forward is built for (action width, observation slab) = (4, 32), (6, 32), (4, 64); anything else uses
+        # the CUDA-core forward
+        self.tensor_core_forward = bool(tensor_core_forward) and (self.d <= 32 or self.a == 4)
         self._graph = None
         self._pending_capture = False
         # the update's optimizer steps as a replayed graph of up to update_graph_steps consecutive minibatches (see _train_kernel)

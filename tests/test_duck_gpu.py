@@ -225,15 +225,16 @@ def test_duck_gym_view_and_vec_infos():
 
 
 def test_ppo_on_the_duck_env_wide_observation():
-    """train/train_objlock.py on the device: the 56-float observation runs through the CUDA-core forward / value /
-    bootstrap / running-moment kernels built for observations up to 64 floats wide (the tcgen05 forward stages one
-    32-wide K slab), update through the fused gradient kernel's 64-wide build.  The forward must agree with the fp32 torch towers, the
-    running moments with NumPy, and a short run must improve the return."""
+    """train/train_objlock.py on the device: the 56-float observation runs through the 64-wide builds of the tcgen05 forward
+    and of the fused gradient kernel, and through the value / bootstrap / running-moment kernels built for observations up
+    to 64 floats wide.  The CUDA-core forward must agree with the fp32 torch towers to fp32 rounding, the tcgen05 forward
+    within the TF32 tolerance, the running moments with NumPy, and a short run must improve the return."""
     import torch
     from pyflyt_drone_b200.ppo import PPO
     from pyflyt_drone_b200.vec_env import FixedwingVecEnv
     env = FixedwingVecEnv(1024, preset="objlock_duck", seed=3)
-    m = PPO("MlpPolicy", env, n_steps=32, batch_size=8192, n_epochs=4, seed=3, use_cuda_graph=False)
+    assert PPO("MlpPolicy", env, n_steps=32, batch_size=8192, seed=3).tensor_core_forward is True
+    m = PPO("MlpPolicy", env, n_steps=32, batch_size=8192, n_epochs=4, seed=3, use_cuda_graph=False, tensor_core_forward=False)
     assert m.d == 56 and m.a == 4 and m.update == "kernel" and m.tensor_core_forward is False
     assert m.policy.count == m.policy.theta.numel() == int(m.lib.ppo_param_count(56))
     with torch.no_grad():
@@ -261,8 +262,23 @@ def test_ppo_on_the_duck_env_wide_observation():
     tot = 1e-4 + 3000
     assert np.allclose(got[:56], bm * 3000 / tot, rtol=1e-6, atol=1e-6)
     assert np.allclose(got[56:112], (1e-4 + bv * 3000 + bm ** 2 * 1e-4 * 3000 / tot) / tot, rtol=1e-4)
-    # the tensor-core entry points refuse the wide observation instead of mis-staging it
-    assert m.lib.ppo_policy_forward_tc_a(_p(m.policy.theta), 56, 4, _p(obs), None, 10.0, 1024, 0, 0, 0, None, 0, None,
+    # the 64-wide tcgen05 forward against the CUDA-core one on the same rows and noise stream (TF32 tolerance, as for D = 28)
+    raw = (torch.randn(5000, 56, device=m.device, generator=m._gen) * 20).contiguous()
+    stats = m.vecnorm.obs_stats.clone()
+    outs = {}
+    for name, fn in (("tc", m.lib.ppo_policy_forward_tc_a), ("cc", m.lib.ppo_policy_forward_a)):
+        o = dict(obs_norm=torch.zeros(5000, 56, device=m.device), act_env=torch.zeros(5000, 4, device=m.device),
+                 act_raw=torch.zeros(5000, 4, device=m.device), logp=torch.zeros(5000, device=m.device),
+                 val=torch.zeros(5000, device=m.device))
+        _lib.check(fn(_p(m.policy.theta), 56, 4, _p(raw), _p(stats), 10.0, 5000, 77, 5, 3, None, 0, _p(o["obs_norm"]),
+                      _p(o["act_env"]), _p(o["act_raw"]), _p(o["logp"]), _p(o["val"]), _stream()))
+        outs[name] = o
+    torch.cuda.synchronize()
+    assert torch.equal(outs["tc"]["obs_norm"], outs["cc"]["obs_norm"]) and torch.equal(outs["tc"]["logp"], outs["cc"]["logp"])
+    assert float((outs["tc"]["val"] - outs["cc"]["val"]).abs().max()) < 1e-2
+    assert float((outs["tc"]["act_raw"] - outs["cc"]["act_raw"]).abs().max()) < 1e-2
+    # a six-channel policy has no 64-wide build: the entry point refuses instead of mis-staging
+    assert m.lib.ppo_policy_forward_tc_a(_p(m.policy.theta), 56, 6, _p(obs), None, 10.0, 1024, 0, 0, 0, None, 0, None,
                                          _p(m.act_env), None, None, _p(b["val"][0]), _stream()) == -1
     m2 = PPO("MlpPolicy", env, n_steps=32, batch_size=8192, n_epochs=4, seed=3)
     r0, _, l0, _ = m2.evaluate_policy(n_eval_episodes=512)
