@@ -40,6 +40,10 @@ int ppo_param_count(int32_t d);
  * multi-GPU run all-reduces once per rollout to reconcile the per-rank running statistics exactly. */
 int ppo_moments_update(const float* x, int32_t n, int32_t d, double* stats, double* scratch, double* accum,
                        void* stream);
+/* The same update from batch sums the env-step kernels accumulated in their epilogue (fw_set_obs_accumulator, fwsim.h):
+ * acc = slots x double[2*d] (column sums | sums of squares per slot), n = rows the sums cover.  Folds them into stats
+ * (and accum) and zeroes acc: one 64-thread block instead of a pass over the observation batch. */
+int ppo_moments_finalize(double* acc, int32_t slots, int32_t n, int32_t d, double* stats, double* accum, void* stream);
 
 /* Policy + value forward for n rows.  obs_raw [n,d]; obs_stats as above (NULL = no normalisation);
  * writes obs_norm [n,d] (what the policy saw; may be NULL), act_env [n,4] (clipped to [-1,1], what the env

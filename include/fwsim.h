@@ -204,6 +204,15 @@ int fw_targets_reached(fw_handle h, uint8_t* dst_dev, void* stream);
  * step kernel (no valid spare: e.g. after fw_set_state, or FWSIM_SPARE=0).  Both give the same state.  Synchronous. */
 int fw_spare_stats(fw_handle h, int64_t out[2]);
 
+/* Running-moment accumulation fused into the step kernels' epilogue (VecNormalize's obs_rms.update of the observations a
+ * step returns, train_Fixedwing_Waypoints_v3.py:254-270): acc_dev = device doubles, FW_OBS_ACC_SLOTS x 2 x obs_dim, zeroed by
+ * the caller; slot s holds [column sums | column sums of squares] added by the blocks with index = s mod FW_OBS_ACC_SLOTS of
+ * every fw_step enqueued while the accumulator is set (NULL clears it).  ppo_moments_finalize folds the slots into the
+ * running statistics and zeroes them.  Launches already enqueued (or captured in a CUDA graph) keep the pointer they were
+ * launched with. */
+#define FW_OBS_ACC_SLOTS 64
+int fw_set_obs_accumulator(fw_handle h, double* acc_dev);
+
 /* Debug / evaluation frame of ONE env: FixedwingBaseEnv.render() -> pybullet getCameraImage
  * [REF envs/fixedwing_envs/fixedwing_base_env.py:350-369; eval/eval_objlock.py:120-162 keeps seg and depth too].
  * Device buffers, any may be NULL: rgba uint8 [height,width,4]; seg int32 [height,width] (-1 sky, 0 ground, 1 duck,

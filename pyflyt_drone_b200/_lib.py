@@ -48,6 +48,7 @@ SYMBOLS = [
     ("fw_host_info_buffer", C.c_int, [_P, C.POINTER(_P)]),
     ("fw_targets_reached", C.c_int, [_P, _P, _P]),
     ("fw_render", C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    ("fw_set_obs_accumulator", C.c_int, [_P, _P]),
     ("fw_fault_count", C.c_int, [_P, C.POINTER(C.c_int64)]),
     ("fw_spare_stats", C.c_int, [_P, C.POINTER(C.c_int64)]),
     ("fw_host_buffers", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),

@@ -732,6 +732,13 @@ extern "C" int fw_targets_reached(fw_handle h, uint8_t* dst_dev, void* stream) {
     return FW_OK;
 }
 
+extern "C" int fw_set_obs_accumulator(fw_handle h, double* acc_dev) {
+    if (!h) return fail(FW_EINVAL, "null handle");
+    if (h->obs_dim <= 0 && acc_dev) return fail(FW_EINVAL, "this task has no observation");
+    h->pl.obs_acc = acc_dev;          // read by the step launches enqueued from now on (by value, at launch time)
+    return FW_OK;
+}
+
 extern "C" int fw_render(fw_handle h, int32_t env, int32_t width, int32_t height, uint8_t* rgba_dev, int32_t* seg_dev,
                          float* depth_dev, void* stream) {
     if (!h) return fail(FW_EINVAL, "null handle");

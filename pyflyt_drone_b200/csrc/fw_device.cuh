@@ -8,6 +8,7 @@
 //   and FlattenWaypointEnv.observation (/root/reference/envs/flatten_waypoint_env.py:52-72).
 // Aircraft constants: /root/reference/my_models/fixedwing/fixewing.yaml:1-71 (folded into SurfDev by fw_api.cu).
 #pragma once
+#define FW_OBS_ACC_SLOTS 64
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -152,6 +153,9 @@ struct FwPlanes {
     float* ep_ret;   // [N]
     double* stats;   // [16] global accumulators: [0..7] episode statistics (fw_episode_stats), [8] non-finite-state resets
     uint8_t* tidx_out;  // [N] info["num_targets_reached"] of the step just taken (before any auto-reset); may be host-mapped
+    // optional: FW_OBS_ACC_SLOTS x double[2 * obs_dim] = column sums | sums of squares of the observations a step writes
+    // (slot = block index mod FW_OBS_ACC_SLOTS, spreading the atomics); fw_set_obs_accumulator, consumed by ppo_moments_finalize
+    double* obs_acc;
     // ObjLock task only
     float4* dk;      // duck xyz
     float4* v0;      // last_cx, last_cy, last_area, last_depth

@@ -37,11 +37,24 @@ __device__ __forceinline__ uint32_t fw_smem_addr(const void* p) {
 }
 
 // Flush one warp's staged observation rows (32 x D floats, dense) to global memory.
+// acc (optional): this block's slot of the observation-moment accumulators, double[2 * D] = column sums | sums of squares
+// (VecNormalize's RunningMeanStd.update of the very observations being flushed): lane c sums column
+// c over the warp's rows out of shared memory -- a few instructions per env-step instead of a kernel that re-reads the batch.
 template <int ROWS = 32>
 __device__ __forceinline__ void fw_flush_obs(float* __restrict__ dst_base, const float* stage_warp, int D,
-                                             int first_env, int n, int lane, bool bulk_ok) {
+                                             int first_env, int n, int lane, bool bulk_ok, double* acc = nullptr) {
     const int rows = min(ROWS, n - first_env);
     float* dst = dst_base + (size_t)first_env * D;
+    if (acc != nullptr) {
+        __syncwarp();
+        for (int c = lane; c < D; c += 32) {
+            // in double: a column with a large mean and a small spread (altitude, airspeed) loses its variance to fp32 sums
+            double sm = 0.0, sq = 0.0;
+            for (int r = 0; r < rows; ++r) { const double x = (double)stage_warp[r * D + c]; sm += x; sq = fma(x, x, sq); }
+            atomicAdd(acc + c, sm);
+            atomicAdd(acc + D + c, sq);
+        }
+    }
     if (bulk_ok && rows == ROWS) {
         // generic-proxy writes -> async proxy, then one elected lane issues the TMA bulk store
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -297,7 +310,9 @@ fw_step_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4*
     }
     if (TASK != 0 && obs != nullptr) {
         const int first_env = p.i_begin + blockIdx.x * FW_BLOCK + warp * 32;
-        if (first_env < p.i_end) fw_flush_obs(obs, stage_warp, D, first_env, p.i_end, lane, bulk_ok != 0);
+        if (first_env < p.i_end)
+            fw_flush_obs(obs, stage_warp, D, first_env, p.i_end, lane, bulk_ok != 0,
+                         (!RANDOM_ACT && pl.obs_acc != nullptr) ? pl.obs_acc + (size_t)(blockIdx.x & (FW_OBS_ACC_SLOTS - 1)) * 2 * D : nullptr);
     }
 }
 
@@ -604,7 +619,9 @@ fw_step2_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const float4
     }
     if (want_obs) {
         const int first_env = p.i_begin + (blockIdx.x * FW2_THREADS + warp * 32) * 2;
-        if (first_env < p.i_end) fw_flush_obs<64>(obs, stage_warp, D, first_env, p.i_end, lane, bulk_ok != 0);
+        if (first_env < p.i_end)
+            fw_flush_obs<64>(obs, stage_warp, D, first_env, p.i_end, lane, bulk_ok != 0,
+                             (!RANDOM_ACT && pl.obs_acc != nullptr) ? pl.obs_acc + (size_t)(blockIdx.x & (FW_OBS_ACC_SLOTS - 1)) * 2 * D : nullptr);
     }
 }
 
@@ -1003,7 +1020,9 @@ fw_step_objlock_kernel(const __grid_constant__ FwDev p, const FwPlanes pl, const
     }
     if (obs != nullptr) {
         const int first_env = p.i_begin + bx * FW_BLOCK + warp * 32;
-        if (first_env < p.i_end) fw_flush_obs(obs, stage_warp, D, first_env, p.i_end, lane, bulk_ok != 0);
+        if (first_env < p.i_end)
+            fw_flush_obs(obs, stage_warp, D, first_env, p.i_end, lane, bulk_ok != 0,
+                         (!RANDOM_ACT && pl.obs_acc != nullptr) ? pl.obs_acc + (size_t)(bx & (FW_OBS_ACC_SLOTS - 1)) * 2 * D : nullptr);
     }
 }
 

@@ -100,6 +100,15 @@ extern "C" int ppo_moments_update(const float* x, int32_t n, int32_t d, double* 
     return FW_OK;
 }
 
+extern "C" int ppo_moments_finalize(double* acc, int32_t slots, int32_t n, int32_t d, double* stats, double* accum, void* stream) {
+    if (!acc || !stats) return pfail(FW_EINVAL, "null argument");
+    if (n <= 0 || slots <= 0) return pfail(FW_EINVAL, "n and slots must be positive");
+    int rc = check_d(d);
+    if (rc) return rc;
+    PCU(ppok_moments_finalize(acc, slots, n, d, stats, accum, (cudaStream_t)stream));
+    return FW_OK;
+}
+
 extern "C" int ppo_policy_forward(const float* params, int32_t d, const float* obs_raw, const double* obs_stats,
                                   float clip_obs, int32_t n, uint64_t seed, uint32_t env_id0, uint32_t step,
                                   const uint32_t* step_dev, int32_t deterministic, float* obs_norm, float* act_env,

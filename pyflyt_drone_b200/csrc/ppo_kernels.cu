@@ -314,6 +314,56 @@ ppo_moments_kernel(const float* __restrict__ x, int n, int d, double* __restrict
     for (int k = threadIdx.x; k < 2 * d + 2; k += blockDim.x) scratch[k] = 0.0;
 }
 
+// The same merge for batch sums the env-step kernels accumulated in their epilogue (fw_set_obs_accumulator): acc =
+// slots x double[2 d]; summed in slot order, folded into the running statistics, zeroed for the next step.
+#define MOMF_GROUPS 4          // slot groups: 256 threads = 4 groups x 64 columns, every load of a thread issued before its first add
+__global__ void __launch_bounds__(64 * MOMF_GROUPS)
+ppo_moments_finalize_kernel(double* __restrict__ acc, int slots, int n, int d, double* __restrict__ stats, double* __restrict__ accum) {
+    __shared__ double s_a[MOMF_GROUPS][64], s_b[MOMF_GROUPS][64];
+    const int k = threadIdx.x & 63, g = threadIdx.x >> 6;
+    constexpr int PER = 16;                              // slots per thread: slots <= MOMF_GROUPS * PER
+    double a = 0.0, b = 0.0;
+    if (k < d) {
+        double va[PER], vb[PER];
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int s = g * PER + i;
+            va[i] = s < slots ? acc[(size_t)s * 2 * d + k] : 0.0;
+            vb[i] = s < slots ? acc[(size_t)s * 2 * d + d + k] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int s = g * PER + i;
+            a += va[i]; b += vb[i];
+            if (s < slots) { acc[(size_t)s * 2 * d + k] = 0.0; acc[(size_t)s * 2 * d + d + k] = 0.0; }
+        }
+    }
+    s_a[g][k] = a; s_b[g][k] = b;
+    __syncthreads();
+    if (g == 0 && k < d) {
+        a = 0.0; b = 0.0;
+#pragma unroll
+        for (int i = 0; i < MOMF_GROUPS; ++i) { a += s_a[i][k]; b += s_b[i][k]; }      // slot order: deterministic
+        if (accum != nullptr) { accum[k] += a; accum[d + k] += b; }
+        double bmean = a / n;
+        double bvar = b / n - bmean * bmean;
+        if (bvar < 0.0) bvar = 0.0;
+        double count = stats[2 * d], mean = stats[k], var = stats[d + k];
+        double tot = count + (double)n, delta = bmean - mean;
+        double m2 = var * count + bvar * (double)n + delta * delta * count * (double)n / tot;
+        stats[k] = mean + delta * (double)n / tot;
+        stats[d + k] = m2 / tot;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { stats[2 * d] += (double)n; if (accum != nullptr) accum[2 * d] += (double)n; }
+}
+
+cudaError_t ppok_moments_finalize(double* acc, int slots, int n, int d, double* stats, double* accum, cudaStream_t st) {
+    if (d > 64 || slots > MOMF_GROUPS * 16) return cudaErrorInvalidValue;
+    ppo_moments_finalize_kernel<<<1, 64 * MOMF_GROUPS, 0, st>>>(acc, slots, n, d, stats, accum);
+    return cudaGetLastError();
+}
+
 cudaError_t ppok_moments(const float* x, int n, int d, double* stats, double* scratch, double* accum, cudaStream_t st) {
     const int rows_per_block = MOM_ROWS;
     const int grid = (n + rows_per_block - 1) / rows_per_block;

@@ -17,6 +17,7 @@ cudaError_t ppok_counter_add(uint32_t* ctr, uint32_t inc, cudaStream_t st);
 cudaError_t ppok_permutation(long long* out, long long n, uint64_t seed, uint64_t epoch, cudaStream_t st);
 cudaError_t ppok_permutation_window(long long* out, long long n, uint64_t seed, uint32_t* ctr, long long window_len, cudaStream_t st);
 cudaError_t ppok_moments(const float* x, int n, int d, double* stats, double* scratch, double* accum, cudaStream_t st);
+cudaError_t ppok_moments_finalize(double* acc, int slots, int n, int d, double* stats, double* accum, cudaStream_t st);
 cudaError_t ppok_reward_normalize(const float* rew, const uint8_t* flags, int n, float gamma, float clip, float* ret,
                                   double* ret_stats, double* scratch, double* accum, float* rew_norm, float* done_out,
                                   cudaStream_t st);

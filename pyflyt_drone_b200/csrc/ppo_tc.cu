@@ -156,11 +156,20 @@ struct TcSmem {
     static constexpr int TOTAL = HP + 4 * TC_ROWS * AP * 4;
 };
 
-__device__ void tc_load_weight(char* smem, int off, const float* __restrict__ g, int K, int d) {
-    for (int i = threadIdx.x; i < H * K; i += blockDim.x) {
-        int j = i / K, k = i % K;
-        float v = k < d ? g[j * d + k] : 0.0f;
-        *reinterpret_cast<float*>(smem + off + tc_off(j, k, K)) = v;
+// every load of the thread (H * K / 512 = 4 or 8) is issued before its first store: the staging is latency-bound
+template <int K>
+__device__ __forceinline__ void tc_load_weight(char* smem, int off, const float* __restrict__ g, int d) {
+    constexpr int N = H * K / TC_THREADS;
+    float v[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        const int i = threadIdx.x + n * TC_THREADS, j = i / K, k = i % K;
+        v[n] = k < d ? g[j * d + k] : 0.0f;
+    }
+#pragma unroll
+    for (int n = 0; n < N; ++n) {
+        const int i = threadIdx.x + n * TC_THREADS, j = i / K, k = i % K;
+        *reinterpret_cast<float*>(smem + off + tc_off(j, k, K)) = v[n];
     }
 }
 
@@ -220,10 +229,10 @@ ppo_forward_tc_kernel(const float* __restrict__ params, int d, const float* __re
     const int vf_count = H * d + H + H * H + H + H + 1;
 
     // ---- one-time: weights into the canonical operand layout, small vectors, barrier, TMEM
-    tc_load_weight(smem, TcSmem::W1_PI, g_pi, DP, d);
-    tc_load_weight(smem, TcSmem::W1_VF, g_vf, DP, d);
-    tc_load_weight(smem, TcSmem::W2_PI, g_pi + H * d + H, H, H);
-    tc_load_weight(smem, TcSmem::W2_VF, g_vf + H * d + H, H, H);
+    tc_load_weight<DP>(smem, TcSmem::W1_PI, g_pi, d);
+    tc_load_weight<DP>(smem, TcSmem::W1_VF, g_vf, d);
+    tc_load_weight<H>(smem, TcSmem::W2_PI, g_pi + H * d + H, H);
+    tc_load_weight<H>(smem, TcSmem::W2_VF, g_vf + H * d + H, H);
     if (tid < H) {
         small[TcSmem::B1_PI + tid] = g_pi[H * d + tid];
         small[TcSmem::B1_VF + tid] = g_vf[H * d + tid];

@@ -274,6 +274,9 @@ class PPO:
         self._graph = None
         self._pending_capture = False
         # the update's optimizer steps as a replayed graph of up to update_graph_steps consecutive minibatches (see _train_kernel)
+        # obs running moments accumulated by the env-step kernels' epilogue instead of a pass over the batch
+        self.fused_obs_moments = os.environ.get("FWPPO_FUSED_MOMENTS", "1") != "0"
+        self._obs_acc = torch.zeros(64 * 2 * self.d, dtype=torch.float64, device=self.device)
         self.update_graph = os.environ.get("FWPPO_UPDATE_GRAPH", "1") != "0"
         self.update_graph_steps = 256
         # minibatches up to this size take the single-CTA multi-step kernel when there is no gradient all-reduce (world 1)
@@ -342,10 +345,23 @@ class PPO:
 
     def _rollout_body(self) -> None:
         env, vn, b = self.env, self.vecnorm, self.buf
+        fused = self.fused_obs_moments and vn.norm_obs and vn.training
+        env.set_obs_accumulator(self._obs_acc if fused else None)
+        try:
+            self._rollout_steps(fused)
+        finally:
+            env.set_obs_accumulator(None)        # other callers of env.step (evaluation, user code) must not feed the sums
+
+    def _rollout_steps(self, fused: bool) -> None:
+        env, vn, b = self.env, self.vecnorm, self.buf
         for t in range(self.n_steps):
             self._forward(self._obs, t)
             obs, rew, flags, term = env.step_tensor(self.act_env, want_terminal_obs=True)
-            self._update_obs_moments(obs)
+            if fused:
+                _lib.check(self.lib.ppo_moments_finalize(_p(self._obs_acc), 64, self.n_envs, self.d, _p(vn.obs_stats),
+                                                         _p(vn.obs_accum), _stream()))
+            else:
+                self._update_obs_moments(obs)
             if vn.norm_reward:
                 _lib.check(self.lib.ppo_reward_normalize(_p(rew), _p(flags), self.n_envs, vn.gamma, vn.clip_reward, _p(vn.ret),
                                                          _p(vn.ret_stats), _p(vn.ret_scratch), _p(vn.ret_accum),

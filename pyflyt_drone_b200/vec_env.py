@@ -319,6 +319,14 @@ class FixedwingVecEnv(VecEnv):
         _lib.check(self.lib.fw_targets_reached(self._h, C.c_void_p(t["tidx"].data_ptr()), C.c_void_p(self._stream())))
         return t["tidx"]
 
+    def set_obs_accumulator(self, acc) -> None:
+        """Device float64 tensor of FW_OBS_ACC_SLOTS x 2 x obs_dim zeros (or None): the step kernels add the column sums and
+        sums of squares of the observations they return to it (``fw_set_obs_accumulator``); ``ppo_moments_finalize`` folds
+        them into the running statistics.  Applies to steps enqueued from now on."""
+        if acc is not None and (acc.numel() != 64 * 2 * self.obs_dim or str(acc.dtype) != "torch.float64" or not acc.is_cuda):
+            raise ValueError("accumulator must be a CUDA float64 tensor of 64 * 2 * obs_dim elements")
+        _lib.check(self.lib.fw_set_obs_accumulator(self._h, C.c_void_p(acc.data_ptr()) if acc is not None else None))
+
     def render_layers(self, env_index: int = 0, width: int | None = None, height: int | None = None) -> dict:
         """Debug / evaluation frame of one env (``fw_render``): ``rgba`` uint8 [H,W,4], ``seg`` int32 [H,W] (-1 sky, 0 ground,
         1 duck, 2+k obstacle k, 64+t waypoint t) and ``depth`` float32 [H,W] (OpenGL depth-buffer values, what pybullet's

@@ -453,6 +453,47 @@ def test_window_update_is_bit_identical_to_separate_launches(preset, batch):
     env.close()
 
 
+@pytest.mark.parametrize("preset,n", [("waypoints_v3", 1000), ("lowlevel", 4096), ("waypoint_objlock", 700), ("objlock_duck", 333)])
+def test_obs_moments_accumulated_by_the_step_kernels(preset, n):
+    """the env-step kernels add the column sums / sums of squares of the observations they return to the
+    accumulator slots (fw_set_obs_accumulator); ppo_moments_finalize folds them into the running statistics like
+    RunningMeanStd.update.  Checked against NumPy on the very observations the steps returned, over three steps, for every
+    step kernel (K1 Waypoints / low-level, K3 ObjLock / duck-only) and ragged batch sizes."""
+    from pyflyt_drone_b200 import _lib
+    from pyflyt_drone_b200.ppo import DeviceVecNormalize, _p, _stream
+    from pyflyt_drone_b200.vec_env import FixedwingVecEnv
+    env = FixedwingVecEnv(n, preset=preset, seed=6)
+    env.reset_tensor()
+    d, dev = env.obs_dim, torch.device("cuda", 0)
+    vn = DeviceVecNormalize(d, n, dev)
+    acc = torch.zeros(64 * 2 * d, dtype=torch.float64, device=dev)
+    env.set_obs_accumulator(acc)
+    g = torch.Generator(device=dev).manual_seed(1)
+    mean, var, count = np.zeros(d), np.ones(d), 1e-4
+    plib = _lib.load()
+    for _ in range(3):
+        a = (torch.rand(n, env.act_dim, device=dev, generator=g) * 2 - 1).contiguous()
+        obs = env.step_tensor(a, want_terminal_obs=False)[0]
+        _lib.check(plib.ppo_moments_finalize(_p(acc), 64, n, d, _p(vn.obs_stats), _p(vn.obs_accum), _stream()))
+        x = obs.cpu().numpy().astype(np.float64)
+        bm, bv = x.mean(0), x.var(0)
+        tot = count + n
+        delta = bm - mean
+        m2 = var * count + bv * n + delta ** 2 * count * n / tot
+        mean, var, count = mean + delta * n / tot, m2 / tot, tot
+    torch.cuda.synchronize()
+    got = vn.obs_stats.cpu().numpy()
+    assert float(acc.abs().max()) == 0.0                        # slots are left zeroed
+    assert got[2 * d] == pytest.approx(count)
+    assert np.allclose(got[:d], mean, rtol=1e-5, atol=1e-5)
+    assert np.allclose(got[d:2 * d], var, rtol=1e-4, atol=1e-6)
+    env.set_obs_accumulator(None)
+    env.step_tensor(a, want_terminal_obs=False)
+    torch.cuda.synchronize()
+    assert float(acc.abs().max()) == 0.0                        # cleared accumulator: steps add nothing
+    env.close()
+
+
 def test_adam_step_matches_torch_optim(model):
     from pyflyt_drone_b200 import _lib
     from pyflyt_drone_b200.ppo import _p, _stream
