@@ -577,7 +577,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         per_gpu = N * spl / (kernel_ms * 1e-3)
         achieved_gbs = per_gpu * BYTES_PER_STEP[args.workload] / 1e9
         fp32_tf = per_gpu * FLOPS_PER_STEP[args.workload] / 1e12
-        traffic, executed = None, None
+        traffic, executed, tj = None, None, {}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
@@ -596,6 +596,18 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         if executed:
             roof["executed_fp32_flop_per_env_step"] = executed
             roof["executed_frac"] = per_gpu * executed / 1e12 / tf.value
+        winst = tj.get(f"{args.workload}_executed_warp_inst_per_env_step")
+        if winst:
+            # the ceiling that actually binds K1: one warp instruction per scheduler per clock (4 schedulers per SM); the mix is
+            # 1 flop per instruction (FFMA 33 %, FMUL 23 %, FADD 12 %, the rest loads / compares / MUFU), so the FMA-chain
+            # peak above is not reachable by this instruction stream
+            mhz = (clocks or {}).get("sm_mhz") or khz.value / 1e3
+            issue_peak = sms.value * 4 * mhz * 1e6
+            issue_ach = per_gpu * winst / 32.0
+            roof["issue"] = {"achieved": issue_ach, "peak": issue_peak, "unit": "warp-instructions/s", "frac": issue_ach / issue_peak,
+                             "warp_inst_per_env_step": winst, "sm_mhz": mhz,
+                             "note": "executed warp instructions per env-step from the ncu capture x env-steps/s / 32 lanes, "
+                                     "against SMs x 4 schedulers x the SM clock sampled under load"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
