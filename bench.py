@@ -415,6 +415,9 @@ def ppo_measure(preset: str, n_envs: int, n_steps: int, batch_size: int, n_epoch
            # rollout graph per step: obs moments, policy forward, env step, return moments + reward finalise, bootstrap;
            # per rollout: counter, last values, GAE; per epoch: permutation; per minibatch: adv stats, gradient, reduce, Adam
            "update_graph_steps": chunk, "ranks_in_sync": in_sync,
+           "gradient_allreduce": ("none (one rank)" if world == 1 else
+                                  "in-kernel over NVLink peer memory (last block of the gradient reduction)" if getattr(model, "_p2p", None)
+                                  else "NCCL all_reduce between the gradient and Adam kernels"),
            "gpu_launches": int(iters * (n_steps * 6 + 3 + run_epochs * (perm_launches + mb * 4)))}
     if run_epochs < n_epochs:
         epoch_s = update_s / run_epochs

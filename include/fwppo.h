@@ -159,6 +159,37 @@ int ppo_window_update_a(float* params, int32_t d, int32_t a, const float* obs_no
                         float beta2, float eps, float max_grad_norm, int32_t* step_counter, float* grad_norm_out, float* workspace,
                         float* grad, float* stats, void* stream);
 
+/* The same window for `world` processes (one per GPU of an NVLink node, world <= 8) WITHOUT a collective library between the
+ * gradient and the optimizer: the last block of each rank's gradient reduction pushes the gradient into every rank's
+ * exchange buffer with remote stores over NVLink peer memory, raises a sequence-numbered flag, waits for the world's flags,
+ * sums the slots in rank order (the same bits on every rank) and applies clip + Adam with grad_scale 1/world -- what
+ * all_reduce(sum) + ppo_adam_step do, in the launch that produced the gradient.  peer_buffers[j] = rank j's exchange
+ * buffer as mapped into THIS process (own buffer at index `rank`); sequence = a zero-initialised device uint32 of this
+ * rank; every rank must make the same calls in the same order.  A rank whose peers do not arrive traps (CUDA error)
+ * after about a second instead of hanging.
+ *   ppo_peer_alloc / ppo_peer_free        one zeroed exchange buffer (ppo_peer_bytes() bytes, cudaMalloc)
+ *   ppo_peer_export / ppo_peer_import     its 64-byte CUDA IPC handle / the peer's buffer mapped here (ppo_peer_close) */
+int64_t ppo_peer_bytes(void);
+int ppo_peer_alloc(void** buffer);
+int ppo_peer_free(void* buffer);
+int ppo_peer_export(void* buffer, uint8_t handle[64]);
+int ppo_peer_import(const uint8_t handle[64], void** buffer);
+int ppo_peer_close(void* buffer);
+/* ppo_minibatch_steps_a for `world` processes: every rank's thread block exchanges the step's gradient with the same
+ * peer-memory protocol (peer_buffers / sequence as above) before its clip + Adam, `steps` times per launch. */
+int ppo_minibatch_steps_p2p_a(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act, const float* logp_old,
+                              const float* adv, const float* ret, const int64_t* idx, int32_t batch, int32_t steps,
+                              float clip_range, float ent_coef, float vf_coef, float* exp_avg, float* exp_avg_sq, float lr,
+                              float beta1, float beta2, float eps, float max_grad_norm, int32_t* step_counter, float* grad_norm_out,
+                              float* grad, float* stats, int32_t world, int32_t rank, void* const* peer_buffers,
+                              uint32_t* sequence, void* stream);
+int ppo_window_update_p2p_a(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act, const float* logp_old,
+                            const float* adv, const float* ret, const int64_t* idx, int32_t batch, int32_t n_minibatches,
+                            float clip_range, float ent_coef, float vf_coef, float* exp_avg, float* exp_avg_sq, float lr,
+                            float beta1, float beta2, float eps, float max_grad_norm, int32_t* step_counter, float* grad_norm_out,
+                            float* workspace, float* grad, float* stats, int32_t world, int32_t rank, void* const* peer_buffers,
+                            uint32_t* sequence, void* stream);
+
 /* torch.nn.utils.clip_grad_norm_(max_grad_norm) followed by torch.optim.Adam.step (no weight decay / amsgrad) on the
  * flat parameter vector; grad is pre-multiplied by grad_scale (1 / world_size after the NCCL sum).
  * step_counter: device int32 incremented by the call (bias correction). */

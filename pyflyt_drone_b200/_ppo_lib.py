@@ -31,6 +31,16 @@ PPO_SYMBOLS = [
                                         _F, _F, _F, _F, _F, _P, _P, _P, _P, _P]),
     ("ppo_window_update_a", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _F, _F, _F, _P, _P,
                                       _F, _F, _F, _F, _F, _P, _P, _P, _P, _P, _P]),
+    ("ppo_window_update_p2p_a", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _F, _F, _F, _P, _P,
+                                          _F, _F, _F, _F, _F, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    ("ppo_minibatch_steps_p2p_a", C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_int32, _F, _F, _F, _P, _P,
+                                            _F, _F, _F, _F, _F, _P, _P, _P, _P, C.c_int32, C.c_int32, _P, _P, _P]),
+    ("ppo_peer_bytes", C.c_int64, []),
+    ("ppo_peer_alloc", C.c_int, [C.POINTER(C.c_void_p)]),
+    ("ppo_peer_free", C.c_int, [_P]),
+    ("ppo_peer_export", C.c_int, [_P, _P]),
+    ("ppo_peer_import", C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    ("ppo_peer_close", C.c_int, [_P]),
     ("ppo_minibatch_grad", C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32, _F, _F, _F, _P, _P, _P, _P]),
     ("ppo_adam_step", C.c_int, [_P, _P, _P, _P, C.c_int32, _F, _F, _F, _F, _F, _F, _P, _P, _P]),
     ("ppo_gae", C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, _F, _F, _P, _P, _P]),

@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 #include <string>
 
 // error string shared with fw_api.cu through fw_last_error(): set via this hook
@@ -264,12 +265,12 @@ extern "C" int ppo_minibatch_grad_a(const float* params, int32_t d, int32_t a, c
     return FW_OK;
 }
 
-extern "C" int ppo_minibatch_steps_a(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act,
+static int minibatch_steps_impl(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act,
                                      const float* logp_old, const float* adv, const float* ret, const int64_t* idx,
                                      int32_t batch, int32_t steps, float clip_range, float ent_coef, float vf_coef,
                                      float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
                                      float max_grad_norm, int32_t* step_counter, float* grad_norm_out, float* grad, float* stats,
-                                     void* stream) {
+                                     void* stream, int world, int rank, void* const* peers, uint32_t* seq) {
     if (!params || !obs_norm || !act || !logp_old || !adv || !ret || !idx || !exp_avg || !exp_avg_sq || !step_counter || !grad ||
         !stats)
         return pfail(FW_EINVAL, "null argument");
@@ -284,7 +285,7 @@ extern "C" int ppo_minibatch_steps_a(float* params, int32_t d, int32_t a, const 
     const long long* ix = reinterpret_cast<const long long*>(idx);
     cudaStream_t st = (cudaStream_t)stream;
 #define STEPS_ARGS params, d, obs_norm, act, logp_old, adv, ret, ix, batch, steps, clip_range, ent_coef, vf_coef, exp_avg, exp_avg_sq, \
-                   lr, beta1, beta2, eps, max_grad_norm, step_counter, grad_norm_out, grad, stats, st
+                   lr, beta1, beta2, eps, max_grad_norm, step_counter, grad_norm_out, grad, stats, st, world, rank, peers, seq
     if (a == 4 && d > PPO_TC_MAX_OBS) PCU(ppo_a4d64::ppok_minibatch_steps(STEPS_ARGS));
     else if (a == 4) PCU(ppo_a4::ppok_minibatch_steps(STEPS_ARGS));
     else PCU(ppo_a6::ppok_minibatch_steps(STEPS_ARGS));
@@ -292,12 +293,41 @@ extern "C" int ppo_minibatch_steps_a(float* params, int32_t d, int32_t a, const 
     return FW_OK;
 }
 
-extern "C" int ppo_window_update_a(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act,
-                                   const float* logp_old, const float* adv, const float* ret, const int64_t* idx, int32_t batch,
-                                   int32_t n_minibatches, float clip_range, float ent_coef, float vf_coef, float* exp_avg,
-                                   float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float max_grad_norm,
-                                   int32_t* step_counter, float* grad_norm_out, float* workspace, float* grad, float* stats,
-                                   void* stream) {
+extern "C" int ppo_minibatch_steps_a(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act,
+                                     const float* logp_old, const float* adv, const float* ret, const int64_t* idx,
+                                     int32_t batch, int32_t steps, float clip_range, float ent_coef, float vf_coef,
+                                     float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                                     float max_grad_norm, int32_t* step_counter, float* grad_norm_out, float* grad, float* stats,
+                                     void* stream) {
+    return minibatch_steps_impl(params, d, a, obs_norm, act, logp_old, adv, ret, idx, batch, steps, clip_range, ent_coef, vf_coef, exp_avg,
+                                exp_avg_sq, lr, beta1, beta2, eps, max_grad_norm, step_counter, grad_norm_out, grad, stats, stream, 1, 0,
+                                nullptr, nullptr);
+}
+
+extern "C" int ppo_minibatch_steps_p2p_a(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act,
+                                         const float* logp_old, const float* adv, const float* ret, const int64_t* idx,
+                                         int32_t batch, int32_t steps, float clip_range, float ent_coef, float vf_coef,
+                                         float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                                         float max_grad_norm, int32_t* step_counter, float* grad_norm_out, float* grad,
+                                         float* stats, int32_t world, int32_t rank, void* const* peer_buffers, uint32_t* sequence,
+                                         void* stream) {
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return pfail(FW_EINVAL, "world must be in [1,8] and rank inside it");
+    if (world > 1) {
+        if (!peer_buffers || !sequence) return pfail(FW_EINVAL, "null peer buffers or sequence counter");
+        for (int j = 0; j < world; ++j)
+            if (!peer_buffers[j]) return pfail(FW_EINVAL, "peer buffer %d is null", j);
+    }
+    return minibatch_steps_impl(params, d, a, obs_norm, act, logp_old, adv, ret, idx, batch, steps, clip_range, ent_coef, vf_coef, exp_avg,
+                                exp_avg_sq, lr, beta1, beta2, eps, max_grad_norm, step_counter, grad_norm_out, grad, stats, stream, world,
+                                rank, peer_buffers, sequence);
+}
+
+static int window_update_impl(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act,
+                              const float* logp_old, const float* adv, const float* ret, const int64_t* idx, int32_t batch,
+                              int32_t n_minibatches, float clip_range, float ent_coef, float vf_coef, float* exp_avg,
+                              float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float max_grad_norm,
+                              int32_t* step_counter, float* grad_norm_out, float* workspace, float* grad, float* stats,
+                              void* stream, int world, int rank, void* const* peers, uint32_t* seq) {
     if (!params || !obs_norm || !act || !logp_old || !adv || !ret || !idx || !exp_avg || !exp_avg_sq || !step_counter || !workspace ||
         !grad)
         return pfail(FW_EINVAL, "null argument");
@@ -324,6 +354,10 @@ extern "C" int ppo_window_update_a(float* params, int32_t d, int32_t a, const fl
     PCU(cudaGetLastError());
     PpokAdam adam{lr, beta1, beta2, eps, max_grad_norm, params, exp_avg, exp_avg_sq, step_counter, grad_norm_out,
                   reinterpret_cast<unsigned*>(workspace)};
+    if (world > 1) {
+        adam.world = world; adam.rank = rank; adam.seq = seq;
+        for (int j = 0; j < world; ++j) adam.peer[j] = static_cast<float*>(peers[j]);
+    }
     for (int k = 0; k < n_minibatches; ++k) {
         const long long* ik = ix + (size_t)k * batch;
         float* as = win_stats + 2 * k;
@@ -339,6 +373,62 @@ extern "C" int ppo_window_update_a(float* params, int32_t d, int32_t a, const fl
     }
     return FW_OK;
 }
+
+extern "C" int ppo_window_update_a(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act,
+                                   const float* logp_old, const float* adv, const float* ret, const int64_t* idx, int32_t batch,
+                                   int32_t n_minibatches, float clip_range, float ent_coef, float vf_coef, float* exp_avg,
+                                   float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float max_grad_norm,
+                                   int32_t* step_counter, float* grad_norm_out, float* workspace, float* grad, float* stats,
+                                   void* stream) {
+    return window_update_impl(params, d, a, obs_norm, act, logp_old, adv, ret, idx, batch, n_minibatches, clip_range, ent_coef, vf_coef,
+                              exp_avg, exp_avg_sq, lr, beta1, beta2, eps, max_grad_norm, step_counter, grad_norm_out, workspace, grad,
+                              stats, stream, 1, 0, nullptr, nullptr);
+}
+
+extern "C" int ppo_window_update_p2p_a(float* params, int32_t d, int32_t a, const float* obs_norm, const float* act,
+                                       const float* logp_old, const float* adv, const float* ret, const int64_t* idx,
+                                       int32_t batch, int32_t n_minibatches, float clip_range, float ent_coef, float vf_coef,
+                                       float* exp_avg, float* exp_avg_sq, float lr, float beta1, float beta2, float eps,
+                                       float max_grad_norm, int32_t* step_counter, float* grad_norm_out, float* workspace,
+                                       float* grad, float* stats, int32_t world, int32_t rank, void* const* peer_buffers,
+                                       uint32_t* sequence, void* stream) {
+    if (world < 1 || world > 8 || rank < 0 || rank >= world) return pfail(FW_EINVAL, "world must be in [1,8] and rank inside it");
+    if (world > 1) {
+        if (!peer_buffers || !sequence) return pfail(FW_EINVAL, "null peer buffers or sequence counter");
+        for (int j = 0; j < world; ++j)
+            if (!peer_buffers[j]) return pfail(FW_EINVAL, "peer buffer %d is null", j);
+    }
+    return window_update_impl(params, d, a, obs_norm, act, logp_old, adv, ret, idx, batch, n_minibatches, clip_range, ent_coef, vf_coef,
+                              exp_avg, exp_avg_sq, lr, beta1, beta2, eps, max_grad_norm, step_counter, grad_norm_out, workspace, grad,
+                              stats, stream, world, rank, peer_buffers, sequence);
+}
+
+// ---- peer memory for the in-kernel gradient all-reduce: one cudaMalloc'ed exchange buffer per rank, shared through CUDA IPC
+extern "C" int64_t ppo_peer_bytes(void) { return (int64_t)ppok_peer_bytes(); }
+extern "C" int ppo_peer_alloc(void** out) {
+    if (!out) return pfail(FW_EINVAL, "null argument");
+    PCU(cudaMalloc(out, ppok_peer_bytes()));
+    PCU(cudaMemset(*out, 0, ppok_peer_bytes()));
+    PCU(cudaDeviceSynchronize());
+    return FW_OK;
+}
+extern "C" int ppo_peer_free(void* p) { if (p) PCU(cudaFree(p)); return FW_OK; }
+extern "C" int ppo_peer_export(void* p, uint8_t handle[64]) {
+    if (!p || !handle) return pfail(FW_EINVAL, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    cudaIpcMemHandle_t h;
+    PCU(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle, &h, 64);
+    return FW_OK;
+}
+extern "C" int ppo_peer_import(const uint8_t handle[64], void** out) {
+    if (!handle || !out) return pfail(FW_EINVAL, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    PCU(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return FW_OK;
+}
+extern "C" int ppo_peer_close(void* p) { if (p) PCU(cudaIpcCloseMemHandle(p)); return FW_OK; }
 
 extern "C" int ppo_minibatch_grad(const float* params, int32_t d, const float* obs_norm, const float* act,
                                   const float* logp_old, const float* adv, const float* ret, const int64_t* idx,

@@ -39,7 +39,10 @@ PPOK_DECLARE_FORWARD_TC(ppo_a6)
 PPOK_DECLARE_FORWARD_TC(ppo_a4d64)
 int ppok_update_grid(int batch);
 // clip + Adam folded into the partial-gradient reduction (single process: nothing sits between gradient and optimizer)
-struct PpokAdam { float lr, beta1, beta2, eps, max_norm; float* params; float* m; float* v; int* step_ctr; float* norm_out; unsigned* arrivals; };
+// world > 1: the last block of the reduction all-reduces the gradient through peer memory first (ppo_update_tc.cu, ppo_peer_*)
+struct PpokAdam { float lr, beta1, beta2, eps, max_norm; float* params; float* m; float* v; int* step_ctr; float* norm_out; unsigned* arrivals;
+                  int world = 1, rank = 0; unsigned* seq = nullptr; float* peer[8] = {}; };
+size_t ppok_peer_bytes();
 void ppok_launch_adv_stats(const float* adv, const long long* idx, int batch, int nmb, double* scratch, float* adv_stats, cudaStream_t st);
 // fused minibatch gradient: one instantiation per (action width, observation slab): ppo_update_tc.cu = (4, 32),
 // ppo_update_tc_a6.cu = (6, 32), ppo_update_tc_d64.cu = (4, 64)
@@ -54,7 +57,8 @@ void ppok_launch_adv_stats(const float* adv, const long long* idx, int batch, in
                                      const float* adv, const float* ret, const long long* idx, int batch, int steps,       \
                                      float clip_range, float ent_coef, float vf_coef, float* m, float* v, float lr,        \
                                      float beta1, float beta2, float eps, float max_norm, int* step_ctr, float* norm_out,  \
-                                     float* grad, float* stats, cudaStream_t st);                                          \
+                                     float* grad, float* stats, cudaStream_t st, int world = 1, int rank = 0,              \
+                                     void* const* peers = nullptr, unsigned* seq = nullptr);                               \
     }
 PPOK_DECLARE_MINIBATCH_GRAD(ppo_a4)
 PPOK_DECLARE_MINIBATCH_GRAD(ppo_a6)

@@ -54,6 +54,76 @@
 #define UT_THREADS 512
 #define UT_TMEM_COLS 512
 
+// In-kernel gradient all-reduce over NVLink peer memory (world > 1; ppo_peer_*): used by the last block of the gradient
+// reduction and by the single-CTA optimizer steps.
+// Low-latency protocol: every gradient element travels as one 8-byte store {value, sequence number} into slot
+// [parity][rank] of every peer's exchange buffer; the receiver polls the element itself until it carries this step's
+// sequence number -- an aligned 8-byte store arrives whole, so no fence and no separate flag sit between data and signal.
+// Each thread pushes and then collects its own elements; the slots are summed in rank order (the same bits on every rank).
+// Parity double-buffers the slots: a rank can only be one step ahead of a peer (it needs the peer's data of step q-1 to get
+// to step q), so the slot of step q-2 it overwrites has been consumed.
+#define PEER_MAX_WORLD 8
+#define PEER_STRIDE 16384                                   // elements per (parity, rank) slot: P <= 16384
+#define PEER_BYTES ((size_t)2 * PEER_MAX_WORLD * PEER_STRIDE * 8)
+__device__ __forceinline__ void peer_store(uint2* p, float v, unsigned q) {
+    // a plain (weak) vector store: the 32 lanes' 8-byte pairs leave as whole 128-byte writes -- measured 20 us per 12 K-element
+    // exchange from one SM with st.volatile (one NVLink packet per element), ~2 us coalesced; value and sequence number of
+    // an element share one aligned 8-byte word of one sector, so they still arrive together
+    asm volatile("st.global.v2.u32 [%0], {%1, %2};" :: "l"(p), "r"(__float_as_uint(v)), "r"(q) : "memory");
+}
+__device__ __forceinline__ uint2 peer_load(const uint2* p) {
+    uint2 r;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p) : "memory");
+    return r;
+}
+// peer_push: this thread's N elements (k = first + i * stride) to every other rank.  peer_collect: the other ranks' copies of
+// those elements, returned as rank-ordered sums in own[].  Every push of a step goes out before the first collect (a
+// push / collect pair per chunk would pay the link latency once per chunk); the polls of one peer's N elements are all in
+// flight before the first is examined, and an element that has not arrived yet is re-polled.
+template <int N>
+__device__ __forceinline__ void peer_push(const float (&own)[N], int P, int first, int stride, int W, int me, unsigned q,
+                                          float* const* peer) {
+    const size_t par_off = (size_t)(q & 1u) * PEER_MAX_WORLD * PEER_STRIDE;
+    for (int j = 0; j < W; ++j) {
+        if (j == me) continue;
+        uint2* dst = reinterpret_cast<uint2*>(peer[j]) + par_off + (size_t)me * PEER_STRIDE;
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const int k = first + i * stride; if (k < P) peer_store(dst + k, own[i], q); }
+    }
+}
+template <int N>
+__device__ __forceinline__ void peer_collect(float (&own)[N], int P, int first, int stride, int W, int me, unsigned q,
+                                             float* const* peer) {
+    const size_t par_off = (size_t)(q & 1u) * PEER_MAX_WORLD * PEER_STRIDE;
+    const uint2* mine = reinterpret_cast<const uint2*>(peer[me]) + par_off;
+    float sum[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) sum[i] = 0.0f;
+    for (int j = 0; j < W; ++j) {
+        if (j == me) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) sum[i] += own[i];
+            continue;
+        }
+        const uint2* src = mine + (size_t)j * PEER_STRIDE;
+        uint2 v[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) { const int k = first + i * stride; v[i] = k < P ? peer_load(src + k) : make_uint2(0u, q); }
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const int k = first + i * stride;
+            for (unsigned it = 0; v[i].y != q; ++it) {
+                if (it > (1u << 22)) __trap();               // a missing peer becomes an error the host sees, not a hang
+                __nanosleep(32);
+                v[i] = peer_load(src + k);
+            }
+            sum[i] += __uint_as_float(v[i].x);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) own[i] = sum[i];
+}
+
 namespace PPO_UT_NS {
 
 __device__ __forceinline__ uint32_t ut_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -302,7 +372,8 @@ struct PpoLossCfg { float clip_range, ent_coef, vf_coef, inv_batch, grad_scale, 
 // Fused mode (steps > 0; one CTA): `steps` consecutive optimizer steps in one launch -- per step the minibatch's advantage
 // statistics, the gradient (written to the caller's gradient buffer), clip_grad_norm_ and Adam on the parameters in global
 // memory, which the next step then stages again.  stable_baselines3's batch_size = 128 is one tile per step.
-struct PpoFusedCfg { int steps; float lr, beta1, beta2, eps, max_norm; float* params; float* m; float* v; int* step_ctr; float* norm_out; };
+struct PpoFusedCfg { int steps; float lr, beta1, beta2, eps, max_norm; float* params; float* m; float* v; int* step_ctr; float* norm_out;
+                     int world, rank; unsigned* seq; float* peer[PEER_MAX_WORLD]; };
 
 // Asynchronously gather 8 consecutive observation columns [8*part, 8*part+8) (per 32-column slab) of rollout row g straight into the
 // fp32 layer-1 A operand (cp.async with zero fill for padding columns and dead rows): the random 112-byte row reads
@@ -903,13 +974,41 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
         __threadfence();
         __syncthreads();
         UT_STAMP(3);
-        // squared norm over this thread's parameters (k = tid + 512 i); every load issued before the first use
         constexpr int NP = 16384 / UT_THREADS;
+        float gscale = 1.0f;
+        if (fz.world > 1) {
+            // gradient all-reduce over NVLink peer memory (value + sequence number per 8-byte store, see the top of the file):
+            // every rank's CTA pushes its elements to the others, collects theirs, and leaves the rank-ordered sum in outp
+            const unsigned qn = fz.seq[0] + 1u;
+#pragma unroll 1
+            for (int i0 = 0; i0 < NP; i0 += 8) {
+                if (i0 * UT_THREADS >= P) break;
+                float own[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const int k = tid + (i0 + i) * UT_THREADS; own[i] = k < P ? __ldcg(outp + k) : 0.0f; }
+                peer_push<8>(own, P, tid + i0 * UT_THREADS, UT_THREADS, fz.world, fz.rank, qn, fz.peer);
+            }
+#pragma unroll 1
+            for (int i0 = 0; i0 < NP; i0 += 8) {
+                if (i0 * UT_THREADS >= P) break;
+                float own[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const int k = tid + (i0 + i) * UT_THREADS; own[i] = k < P ? __ldcg(outp + k) : 0.0f; }
+                peer_collect<8>(own, P, tid + i0 * UT_THREADS, UT_THREADS, fz.world, fz.rank, qn, fz.peer);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const int k = tid + (i0 + i) * UT_THREADS; if (k < P) outp[k] = own[i]; }
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) fz.seq[0] = qn;
+            gscale = 1.0f / (float)fz.world;
+        }
+        // squared norm over this thread's parameters (k = tid + 512 i); every load issued before the first use
         float ss = 0.0f;
         {
             float g[NP];
 #pragma unroll
-            for (int i = 0; i < NP; ++i) { const int k = tid + i * UT_THREADS; g[i] = k < P ? __ldcg(outp + k) : 0.0f; }
+            for (int i = 0; i < NP; ++i) { const int k = tid + i * UT_THREADS; g[i] = k < P ? __ldcg(outp + k) * gscale : 0.0f; }
 #pragma unroll
             for (int i = 0; i < NP; ++i) ss = fmaf(g[i], g[i], ss);
         }
@@ -941,7 +1040,7 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
             for (int i = 0; i < 8; ++i) {
                 const int k = tid + (i0 + i) * UT_THREADS;
                 const bool ok = k < P;
-                gk[i] = ok ? __ldcg(outp + k) : 0.0f;
+                gk[i] = ok ? __ldcg(outp + k) * gscale : 0.0f;
                 mk[i] = ok ? fz.m[k] : 0.0f; vk[i] = ok ? fz.v[k] : 0.0f; pk[i] = ok ? __ldcg(fz.params + k) : 0.0f;
             }
 #pragma unroll
@@ -1026,7 +1125,7 @@ ppo_adv_stats_kernel(const float* __restrict__ adv, const long long* __restrict_
 // adam.enabled: single-process update (no all-reduce between gradient and optimizer) -- the last block to finish its slice
 // of the reduction runs clip + Adam on the complete gradient, saving the optimizer's own launch
 struct PpoAdamArgs { int enabled; float lr, beta1, beta2, eps, max_norm; float* params; float* m; float* v; int* step_ctr; float* norm_out;
-                     unsigned* arrivals; };
+                     unsigned* arrivals; int world, rank; unsigned* seq; float* peer[PEER_MAX_WORLD]; };
 #define ADAM_THREADS 1024
 #define ADAM_PER 16          // parameters per thread held in registers: P <= 16384
 __device__ __forceinline__ void ppo_adam_block(float* params, const float* grad, float* m, float* v, int P, float lr, float beta1,
@@ -1068,7 +1167,27 @@ ppo_grad_reduce_kernel(const float* __restrict__ partial, const float* __restric
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    ppo_adam_block(adam.params, grad, adam.m, adam.v, P, adam.lr, adam.beta1, adam.beta2, adam.eps, adam.max_norm, 1.0f,
+    float scale = 1.0f;
+    if (adam.world > 1) {
+        const unsigned q = adam.seq[0] + 1u;                 // sequence number of this optimizer step (same on every rank)
+        {
+            float own[ADAM_PER];
+#pragma unroll
+            for (int i = 0; i < ADAM_PER; ++i) { const int k = threadIdx.x + i * ADAM_THREADS; own[i] = k < P ? __ldcg(grad + k) : 0.0f; }
+            peer_push<ADAM_PER>(own, P, threadIdx.x, ADAM_THREADS, adam.world, adam.rank, q, adam.peer);
+            peer_collect<ADAM_PER>(own, P, threadIdx.x, ADAM_THREADS, adam.world, adam.rank, q, adam.peer);
+#pragma unroll
+            for (int i = 0; i < ADAM_PER; ++i) {    // what an all-reduce(sum) leaves in the gradient buffer
+                const int k = threadIdx.x + i * ADAM_THREADS;
+                if (k < P) grad[k] = own[i];
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) adam.seq[0] = q;
+        scale = 1.0f / (float)adam.world;
+    }
+    ppo_adam_block(adam.params, grad, adam.m, adam.v, P, adam.lr, adam.beta1, adam.beta2, adam.eps, adam.max_norm, scale,
                    adam.step_ctr, adam.norm_out, s_red, &s_coef);
 }
 
@@ -1132,6 +1251,7 @@ ppo_adam_kernel(float* params, const float* grad, float* m, float* v, int P, flo
 }
 
 // ------------------------------------------------------------------ launchers
+size_t ppok_peer_bytes() { return (size_t)PEER_BYTES; }
 static int g_ut_sm_count_shared = 0;
 
 int ppok_update_grid(int batch) {
@@ -1154,9 +1274,11 @@ void ppok_launch_adv_stats(const float* adv, const long long* idx, int batch, in
 void ppok_launch_grad_reduce(const float* partial, const float* stats_partial, int grid, int P, float* grad, float* stats,
                              const PpokAdam* adam, cudaStream_t st) {
     PpoAdamArgs a{};
-    if (adam != nullptr)
+    if (adam != nullptr) {
         a = PpoAdamArgs{1, adam->lr, adam->beta1, adam->beta2, adam->eps, adam->max_norm, adam->params, adam->m, adam->v, adam->step_ctr,
-                        adam->norm_out, adam->arrivals};
+                        adam->norm_out, adam->arrivals, adam->world, adam->rank, adam->seq, {}};
+        for (int j = 0; j < PEER_MAX_WORLD; ++j) a.peer[j] = j < adam->world ? adam->peer[j] : nullptr;
+    }
     ppo_grad_reduce_kernel<<<(P + RED_KX - 1) / RED_KX, RED_KX * RED_CY, 0, st>>>(partial, stats_partial, grid, P, grad, stats, a);
 }
 
@@ -1207,8 +1329,9 @@ cudaError_t ppok_minibatch_grad(const float* params, int d, const float* obs, co
 cudaError_t ppok_minibatch_steps(float* params, int d, const float* obs, const float* act, const float* logp_old, const float* adv,
                                  const float* ret, const long long* idx, int batch, int steps, float clip_range, float ent_coef,
                                  float vf_coef, float* m, float* v, float lr, float beta1, float beta2, float eps, float max_norm,
-                                 int* step_ctr, float* norm_out, float* grad, float* stats, cudaStream_t st) {
-    if (d > DP || steps <= 0) return cudaErrorInvalidValue;
+                                 int* step_ctr, float* norm_out, float* grad, float* stats, cudaStream_t st, int world, int rank,
+                                 void* const* peers, unsigned* seq) {
+    if (d > DP || steps <= 0 || world > PEER_MAX_WORLD) return cudaErrorInvalidValue;
     if (!g_ut_fused_attr_set) {
         cudaError_t e = cudaFuncSetAttribute(ppo_grad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL);
         if (e != cudaSuccess) return e;
@@ -1219,7 +1342,8 @@ cudaError_t ppok_minibatch_steps(float* params, int d, const float* obs, const f
     float gs = 1.0f;
     while (gs < (float)batch && gs < 1048576.0f) gs *= 2.0f;
     PpoLossCfg cfg{clip_range, ent_coef, vf_coef, 1.0f / (float)batch, gs, 1.0f / gs};
-    PpoFusedCfg fz{steps, lr, beta1, beta2, eps, max_norm, params, m, v, step_ctr, norm_out};
+    PpoFusedCfg fz{steps, lr, beta1, beta2, eps, max_norm, params, m, v, step_ctr, norm_out, world > 1 ? world : 1, rank, seq, {}};
+    for (int j = 0; j < PEER_MAX_WORLD; ++j) fz.peer[j] = (world > 1 && j < world) ? static_cast<float*>(peers[j]) : nullptr;
     ppo_grad_tc_kernel<true><<<1, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, nullptr, cfg, grad,
                                                           stats, P, fz);
     return cudaGetLastError();

@@ -295,6 +295,51 @@ class PPO:
                 dist.broadcast(self.policy.theta.data, src=0)          # one ncclBroadcast of the initial weights
         except Exception:
             self.world = 1
+        # gradient all-reduce inside the gradient reduction kernel over NVLink peer memory (one NVLink node, world <= 8);
+        # FWPPO_P2P=0 keeps the NCCL all-reduce between the kernels
+        self._p2p = None
+        if self.world > 1 and self.update == "kernel" and os.environ.get("FWPPO_P2P", "1") != "0":
+            self._setup_p2p()
+
+    def _setup_p2p(self) -> None:
+        """One exchange buffer per rank (cudaMalloc), shared with every other rank through CUDA IPC handles; all ranks agree
+        (an all-reduce of a success flag) whether the peer path is on."""
+        import torch.distributed as dist
+        rank, world, ok = dist.get_rank(), self.world, 1.0
+        own, peers, opened = C.c_void_p(), (C.c_void_p * world)(), []
+        try:
+            if world > 8:
+                raise RuntimeError("more than 8 ranks")
+            _lib.check(self.lib.ppo_peer_alloc(C.byref(own)))
+            handle = (C.c_uint8 * 64)()
+            _lib.check(self.lib.ppo_peer_export(own, handle))
+            mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.device)
+            gathered = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(gathered, mine)
+            for j in range(world):
+                if j == rank:
+                    peers[j] = own.value
+                else:
+                    h = (C.c_uint8 * 64)(*gathered[j].cpu().tolist())
+                    pj = C.c_void_p()
+                    _lib.check(self.lib.ppo_peer_import(h, C.byref(pj)))
+                    peers[j] = pj.value
+                    opened.append(pj)
+        except Exception as e:          # no peer access / IPC refused: every rank falls back to NCCL together
+            ok = 0.0
+            self._p2p_error = f"{type(e).__name__}: {e}"
+        flag = torch.tensor([ok], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag) < 0.5:
+            for pj in opened:
+                self.lib.ppo_peer_close(pj)
+            if own.value:
+                self.lib.ppo_peer_free(own)
+            return
+        self._p2p = dict(own=own, peers=peers, opened=opened, rank=rank,
+                         seq=torch.zeros(1, dtype=torch.int32, device=self.device))
+        torch.cuda.synchronize()
+        dist.barrier()
 
     # ------------------------------------------------------------------ kernels
     def _stats_ptr(self):
@@ -402,7 +447,7 @@ class PPO:
         # Optimizer steps are launch-latency sized at small minibatches (batch 128: four ~5 us kernels): from the second call
         # on, a window of consecutive steps is one CUDA graph, replayed for every window of every epoch (the permutation
         # position lives on the device).  The first call runs eagerly -- it is the warm-up a capture needs.
-        if self.world == 1 and bs <= self.fused_steps_max_batch and total % bs == 0:
+        if (self.world == 1 or self._p2p is not None) and bs <= self.fused_steps_max_batch and total % bs == 0:
             # stable_baselines3-sized minibatches (batch_size 128 = one 128-row tile): a window of consecutive optimizer steps
             # is ONE single-CTA launch (ppo_minibatch_steps_a) -- advantage statistics, gradient, clip and Adam per step, no
             # launch in between
@@ -411,16 +456,21 @@ class PPO:
             for _ in range(self.n_epochs):
                 perm = self._epoch_permutation(total)
                 for s in range(0, total, chunk * bs):
-                    _lib.check(self.lib.ppo_minibatch_steps_a(
-                        _p(self.policy.theta.data), self.d, self.a, _p(b["obs"]), _p(b["act"]), _p(b["logp"]), _p(b["adv"]),
-                        _p(b["ret"]), _p(perm[s:s + chunk * bs]), bs, chunk, self.clip_range, self.ent_coef, self.vf_coef,
-                        _p(self._adam_m), _p(self._adam_v), lr, b1, b2, eps, self.max_grad_norm, _p(self._adam_t),
-                        _p(self._grad_norm), _p(self._grad), _p(self._stats_mb), _stream()))
+                    args = (_p(self.policy.theta.data), self.d, self.a, _p(b["obs"]), _p(b["act"]), _p(b["logp"]), _p(b["adv"]),
+                            _p(b["ret"]), _p(perm[s:s + chunk * bs]), bs, chunk, self.clip_range, self.ent_coef, self.vf_coef,
+                            _p(self._adam_m), _p(self._adam_v), lr, b1, b2, eps, self.max_grad_norm, _p(self._adam_t),
+                            _p(self._grad_norm), _p(self._grad), _p(self._stats_mb))
+                    if self.world > 1:       # every rank's block exchanges the step's gradient over NVLink peer memory
+                        pp = self._p2p
+                        _lib.check(self.lib.ppo_minibatch_steps_p2p_a(*args, self.world, pp["rank"], pp["peers"], _p(pp["seq"]),
+                                                                      _stream()))
+                    else:
+                        _lib.check(self.lib.ppo_minibatch_steps_a(*args, _stream()))
         elif total % bs == 0:
             # windows of consecutive minibatches: a single process runs each window through ppo_window_update_a (one launch
             # for the window's advantage statistics, clip + Adam inside the gradient reduction: 2 n + 1 launches for n
             # steps); with an all-reduce between gradient and optimizer the steps stay four launches + NCCL each
-            cap = 16 if self.world == 1 else self.update_graph_steps
+            cap = 16 if (self.world == 1 or self._p2p is not None) else self.update_graph_steps
             chunk = max(c for c in range(1, min(steps_per_epoch, cap) + 1) if steps_per_epoch % c == 0)
             if self.use_graph and self.update_graph and self._train_calls > 1:
                 key = (total, bs, chunk, lr, b1, b2, eps, self.clip_range, self.ent_coef, self.vf_coef, self.max_grad_norm)
@@ -458,7 +508,14 @@ class PPO:
 
     def _window_steps(self, idx: torch.Tensor, bs: int, nmb: int, lr: float, b1: float, b2: float, eps: float) -> None:
         """`nmb` consecutive optimizer steps over the index window `idx` (nmb * bs entries)."""
-        if self.world == 1:
+        if self.world > 1 and self._p2p is not None:
+            b, pp = self.buf, self._p2p
+            _lib.check(self.lib.ppo_window_update_p2p_a(
+                _p(self.policy.theta.data), self.d, self.a, _p(b["obs"]), _p(b["act"]), _p(b["logp"]), _p(b["adv"]), _p(b["ret"]),
+                _p(idx), bs, nmb, self.clip_range, self.ent_coef, self.vf_coef, _p(self._adam_m), _p(self._adam_v), lr, b1, b2, eps,
+                self.max_grad_norm, _p(self._adam_t), _p(self._grad_norm), _p(self._ws), _p(self._grad), _p(self._stats_mb),
+                self.world, pp["rank"], pp["peers"], _p(pp["seq"]), _stream()))
+        elif self.world == 1:
             b = self.buf
             _lib.check(self.lib.ppo_window_update_a(
                 _p(self.policy.theta.data), self.d, self.a, _p(b["obs"]), _p(b["act"]), _p(b["logp"]), _p(b["adv"]), _p(b["ret"]),
