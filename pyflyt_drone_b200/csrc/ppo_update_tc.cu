@@ -412,7 +412,7 @@ __device__ __forceinline__ void ut_gather_async(char* smem, const float* __restr
 // activation columns [32q, 32q+32) of the stacked pi|vf layer (q 0,1 = policy tower, 2,3 = value tower) in every
 // epilogue, so the per-thread serial work is a quarter of a row and 16 warps hide each other's TMEM/SFU latency.
 // tanh' factors are kept in registers (packed bf16) from the forward epilogues instead of being recomputed.
-template <bool FUSED>
+template <bool FUSED, bool P2P = false>
 __global__ void __launch_bounds__(UT_THREADS, 1)
 ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, const float* __restrict__ act,
                    const float* __restrict__ logp_old, const float* __restrict__ adv, const float* __restrict__ ret,
@@ -976,7 +976,7 @@ ppo_grad_tc_kernel(const float* params, int d, const float* __restrict__ obs, co
         UT_STAMP(3);
         constexpr int NP = 16384 / UT_THREADS;
         float gscale = 1.0f;
-        if (fz.world > 1) {
+        if (P2P && fz.world > 1) {
             // gradient all-reduce over NVLink peer memory (value + sequence number per 8-byte store, see the top of the file):
             // every rank's CTA pushes its elements to the others, collects theirs, and leaves the rank-ordered sum in outp
             const unsigned qn = fz.seq[0] + 1u;
@@ -1333,7 +1333,9 @@ cudaError_t ppok_minibatch_steps(float* params, int d, const float* obs, const f
                                  void* const* peers, unsigned* seq) {
     if (d > DP || steps <= 0 || world > PEER_MAX_WORLD) return cudaErrorInvalidValue;
     if (!g_ut_fused_attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(ppo_grad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL);
+        cudaError_t e = cudaFuncSetAttribute(ppo_grad_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(ppo_grad_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, UtSmem::TOTAL);
         if (e != cudaSuccess) return e;
         g_ut_fused_attr_set = true;
     }
@@ -1344,8 +1346,12 @@ cudaError_t ppok_minibatch_steps(float* params, int d, const float* obs, const f
     PpoLossCfg cfg{clip_range, ent_coef, vf_coef, 1.0f / (float)batch, gs, 1.0f / gs};
     PpoFusedCfg fz{steps, lr, beta1, beta2, eps, max_norm, params, m, v, step_ctr, norm_out, world > 1 ? world : 1, rank, seq, {}};
     for (int j = 0; j < PEER_MAX_WORLD; ++j) fz.peer[j] = (world > 1 && j < world) ? static_cast<float*>(peers[j]) : nullptr;
-    ppo_grad_tc_kernel<true><<<1, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, nullptr, cfg, grad,
-                                                          stats, P, fz);
+    if (world > 1)
+        ppo_grad_tc_kernel<true, true><<<1, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, nullptr,
+                                                                          cfg, grad, stats, P, fz);
+    else
+        ppo_grad_tc_kernel<true, false><<<1, UT_THREADS, UtSmem::TOTAL, st>>>(params, d, obs, act, logp_old, adv, ret, idx, batch, nullptr,
+                                                                           cfg, grad, stats, P, fz);
     return cudaGetLastError();
 }
 }  // namespace PPO_UT_NS
