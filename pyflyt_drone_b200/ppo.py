@@ -6,13 +6,16 @@ Mirrors the reference's use of stable_baselines3 (train/train_Fixedwing_Waypoint
 vf_coef, max_grad_norm, seed, device).learn(total_timesteps)``.
 
 Rollout path (every agent step, no host sync): hand-written kernels of libfwsim.so --
-running moments (ppo_moments_update), policy/value forward + Gaussian sampling (ppo_policy_forward), env step
-(fw_step), reward normalisation (ppo_reward_normalize), time-limit bootstrap (ppo_timeout_bootstrap), and GAE
-(ppo_gae) once per rollout.  The minibatch update is hand-written too (update="kernel"): one fused tcgen05
-forward+backward kernel per minibatch (ppo_minibatch_grad) and one clip+Adam kernel (ppo_adam_step) on ONE flat
-parameter vector, whose gradient is a single contiguous 49 KB buffer -- exactly what the one collective of the
-path, the NCCL gradient all-reduce, wants.  update="torch" keeps a plain autograd implementation as the fp32
-reference the tests compare against.
+policy/value forward + Gaussian sampling (ppo_policy_forward[_tc]), env step (fw_step, whose epilogue also accumulates
+the observation moments: fw_set_obs_accumulator + ppo_moments_finalize), reward normalisation (ppo_reward_normalize),
+time-limit bootstrap (ppo_timeout_bootstrap), and GAE (ppo_gae) once per rollout; the whole rollout is one replayed
+CUDA graph.  The minibatch update is hand-written too (update="kernel"): one fused tcgen05 forward+backward kernel
+per minibatch on ONE flat parameter vector, whose gradient is a single contiguous 49 KB buffer, with clip + Adam in
+the gradient reduction (ppo_window_update_a) or, for stable_baselines3-sized minibatches, whole windows of optimizer
+steps in one single-block launch (ppo_minibatch_steps_a).  The one collective of the path, the gradient all-reduce
+of a multi-GPU run, happens inside those kernels over NVLink peer memory (ppo_*_p2p_a; NCCL all_reduce between the
+kernels when peer memory cannot be set up or FWPPO_P2P=0).  update="torch" keeps a plain autograd implementation as
+the fp32 reference the tests compare against.
 """
 from __future__ import annotations
 
@@ -340,6 +343,19 @@ class PPO:
                          seq=torch.zeros(1, dtype=torch.int32, device=self.device))
         torch.cuda.synchronize()
         dist.barrier()
+
+    def close_p2p(self) -> None:
+        """Unmap the peers' exchange buffers and free this rank's (idempotent; every rank should call it, or none)."""
+        pp, self._p2p = getattr(self, "_p2p", None), None
+        if not pp:
+            return
+        try:
+            torch.cuda.synchronize()
+            for pj in pp["opened"]:
+                self.lib.ppo_peer_close(pj)
+            self.lib.ppo_peer_free(pp["own"])
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------ kernels
     def _stats_ptr(self):
