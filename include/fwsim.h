@@ -176,7 +176,8 @@ int fw_step_random(fw_handle h, int32_t n_steps, float* rew_dev, uint8_t* flags_
 /* Random-action sweep over a list of env batches on one device: launch j advances batch hs[j % n_handles] by
  * steps_per_launch env-steps (state stays in registers between the fused steps; no observation is emitted).
  * use_graph != 0 replays a cached CUDA graph of one round-robin pass so launches are issued back to back
- * without host involvement.  Results are identical to fw_step_random step by step. */
+ * without host involvement.  Results are identical to fw_step_random step by step.  The graph cache is process-global:
+ * do not call this entry point from two host threads at once. */
 int fw_rollout_random(const fw_handle* hs, int32_t n_handles, int32_t n_launches, int32_t steps_per_launch,
                       int32_t use_graph, void* stream);
 

@@ -291,6 +291,10 @@ struct MultiGraph {
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
 };
+// Process-global (not per handle): fw_rollout_random takes a LIST of handles, so the cache belongs to the call site, keyed by
+// the list.  Consequence for the "handles are independent" contract: fw_rollout_random itself is not re-entrant -- two host
+// threads must not call it concurrently, even on disjoint handle lists (every other entry point only touches its handle);
+// fw_destroy drops a cached graph that names the handle.
 static MultiGraph g_multi;     // one full round-robin pass over the handle list
 static MultiGraph g_rem;       // the launches left over after the full passes (a prefix of the list)
 
