@@ -403,7 +403,22 @@ def ppo_measure(preset: str, n_envs: int, n_steps: int, batch_size: int, n_epoch
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         in_sync = bool(flag.item() > 0.5)
     chunk = model._ugraph_key[2] if getattr(model, "_ugraph_key", None) else 0
-    perm_launches = 2 * (mb // chunk) if chunk else 1          # per epoch: window + advance kernels per graph, or one permutation
+    # launches of OUR kernels per epoch of the update, by the path PPO._train_kernel took (see pyflyt_drone_b200/ppo.py)
+    in_kernel_reduce = world == 1 or getattr(model, "_p2p", None) is not None
+    if model.update != "kernel":
+        update_launches, update_path = 0, "torch autograd (reference path)"
+    elif in_kernel_reduce and batch_size <= model.fused_steps_max_batch and (n_envs * n_steps) % batch_size == 0:
+        win = max(c for c in range(1, min(mb, model.update_graph_steps) + 1) if mb % c == 0)
+        update_launches = 1 + mb // win                       # permutation + one single-block launch per window of steps
+        update_path = f"single-block launches of {win} optimizer steps"
+    elif chunk and in_kernel_reduce:
+        update_launches = (mb // chunk) * 3 + mb * 2          # per window: permutation window + advance + advantage statistics
+        update_path = f"graph windows of {chunk} steps: gradient kernel + reduction with clip/Adam (and the peer exchange) per step"
+    elif chunk:
+        update_launches = (mb // chunk) * 2 + mb * 4          # adv stats, gradient, reduce, [NCCL], Adam
+        update_path = f"graph windows of {chunk} steps with an NCCL all-reduce between reduce and Adam"
+    else:
+        update_launches, update_path = 1 + mb * 4, "eager optimizer steps"
     out = {"sps": iters * per_iter / dt, "n_gpus": world, "envs_per_gpu": n_envs, "n_steps": n_steps, "batch_size_per_gpu": batch_size,
            "n_epochs": n_epochs, "iterations": iters, "iter_ms": dt / iters * 1e3, "rollout_s": rollout_s, "update_s": update_s,
            "rollout_env_steps_per_sec": per_iter / max(rollout_s, 1e-9),
@@ -412,13 +427,14 @@ def ppo_measure(preset: str, n_envs: int, n_steps: int, batch_size: int, n_epoch
            "allreduce_in_timed_region": world > 1,
            "update": "fused tcgen05 minibatch gradient kernel + clip/Adam kernel" if model.update == "kernel" else "torch autograd",
            "forward": "tcgen05 kind::tf32 policy/value forward" if model.tensor_core_forward else "CUDA-core fp32 forward",
-           # rollout graph per step: obs moments, policy forward, env step, return moments + reward finalise, bootstrap;
-           # per rollout: counter, last values, GAE; per epoch: permutation; per minibatch: adv stats, gradient, reduce, Adam
+           # rollout graph per step: policy forward, env step (+ obs moment sums), moments finalize, return moments + reward
+           # finalise, bootstrap; per rollout: counter, last values, GAE; update: see update_launches above
            "update_graph_steps": chunk, "ranks_in_sync": in_sync,
            "gradient_allreduce": ("none (one rank)" if world == 1 else
                                   "in-kernel over NVLink peer memory (last block of the gradient reduction)" if getattr(model, "_p2p", None)
                                   else "NCCL all_reduce between the gradient and Adam kernels"),
-           "gpu_launches": int(iters * (n_steps * 6 + 3 + run_epochs * (perm_launches + mb * 4)))}
+           "update_path": update_path,
+           "gpu_launches": int(iters * (n_steps * 6 + 3 + run_epochs * update_launches))}
     if run_epochs < n_epochs:
         epoch_s = update_s / run_epochs
         full = rollout_s + n_epochs * epoch_s
