@@ -280,6 +280,7 @@ class PPO:
         # obs running moments accumulated by the env-step kernels' epilogue instead of a pass over the batch
         self.fused_obs_moments = os.environ.get("FWPPO_FUSED_MOMENTS", "1") != "0"
         self._obs_acc = torch.zeros(64 * 2 * self.d, dtype=torch.float64, device=self.device)
+        self._side = torch.cuda.Stream(device=self.device)
         self.update_graph = os.environ.get("FWPPO_UPDATE_GRAPH", "1") != "0"
         self.update_graph_steps = 256
         # minibatches up to this size take the single-CTA multi-step kernel when there is no gradient all-reduce (world 1)
@@ -419,8 +420,13 @@ class PPO:
             self._forward(self._obs, t)
             obs, rew, flags, term = env.step_tensor(self.act_env, want_terminal_obs=True)
             if fused:
-                _lib.check(self.lib.ppo_moments_finalize(_p(self._obs_acc), 64, self.n_envs, self.d, _p(vn.obs_stats),
-                                                         _p(vn.obs_accum), _stream()))
+                # the finalize of the observation moments only feeds the NEXT forward: it runs on a side stream beside the
+                # reward normalisation and the bootstrap (a fork / join inside the captured graph)
+                cur = torch.cuda.current_stream()
+                self._side.wait_stream(cur)
+                with torch.cuda.stream(self._side):
+                    _lib.check(self.lib.ppo_moments_finalize(_p(self._obs_acc), 64, self.n_envs, self.d, _p(vn.obs_stats),
+                                                             _p(vn.obs_accum), _stream()))
             else:
                 self._update_obs_moments(obs)
             if vn.norm_reward:
@@ -433,6 +439,8 @@ class PPO:
             _lib.check(self.lib.ppo_timeout_bootstrap_a(_p(self.policy.theta), self.d, self.a, _p(term), self._stats_ptr(),
                                                         vn.clip_obs, _p(flags), self.n_envs, self.gamma, _p(b["rew"][t]),
                                                         _stream()))
+            if fused:
+                torch.cuda.current_stream().wait_stream(self._side)
             self._obs = obs
         _lib.check(self.lib.ppo_counter_add(_p(self._step_dev), self.n_steps, _stream()))
         _lib.check(self.lib.ppo_value_forward_a(_p(self.policy.theta), self.d, self.a, _p(self._obs), self._stats_ptr(),
